@@ -1,0 +1,134 @@
+/* pof_b200 -- C ABI of the B200-native parallel-in-time IEKS hot path.
+ *
+ * The reference (nathanaelbosch/parallel-in-time-ode-filters, "pof") has no FFI of its own: the seam is cut at
+ * its Python function signatures.  Each entry point below names the reference function it replaces.
+ * Conventions: all pointers are DEVICE pointers unless stated "host"; fp64, row-major, contiguous, caller-owned;
+ * nothing is allocated inside (the caller passes a workspace); every call is stream-ordered and does not
+ * synchronise; return value 0 = ok, >0 = cudaError_t, <0 = argument error (POF_E_*).
+ *
+ * Shapes: N time points, n = N-1 steps, ODE dimension d, IWP order q, state dimension D = d*(q+1), state
+ * ordering [y1, y1', .., y1^(q), y2, ..] (reference pof/transitions.py:80-88).
+ */
+#ifndef POF_B200_H
+#define POF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pof_stream_t; /* cudaStream_t */
+
+#define POF_E_UNSUPPORTED_DQ (-1) /* (d, q) combination not compiled in */
+#define POF_E_WORKSPACE (-2)      /* workspace too small */
+#define POF_E_ARG (-3)
+#define POF_E_IVP (-4)            /* unknown built-in IVP id */
+
+/* indices into the `scalars` output (device, POF_NSCALARS doubles) */
+enum {
+  POF_S_NLL = 0,        /* -sum log N(innovation)      reference filter.py:96-102                */
+  POF_S_OBJ = 1,        /* smoother objective          reference smoother.py:20 (swapped args)   */
+  POF_S_SSQ = 2,        /* sigma^2, reference formula  reference filter.py:105-114, utils.py:110 */
+  POF_S_SSQ_PROPER = 3, /* sign-invariant sigma^2 = sum |S_L^{-1} y|^2 / (n d)                   */
+  POF_S_NOT_CLOSE = 4,  /* #entries of means failing isclose(old,new,rtol=1e-13,atol=1e-8)
+                           reference convergence_criteria.py:9                                    */
+  POF_S_CSCALE = 5,     /* sqrt(sigma^2) applied to the returned chol (1 if !calibrate)           */
+  POF_NSCALARS = 8
+};
+
+/* built-in vector fields (reference pof/ivp.py) for the fused f / Jacobian evaluation */
+enum {
+  POF_IVP_LOGISTIC = 0,      /* ivp.py:7-14    params: none                     */
+  POF_IVP_LOTKAVOLTERRA = 1, /* ivp.py:17-31   params: a,b,c,d                  */
+  POF_IVP_VANDERPOL = 2,     /* ivp.py:34-41   params: mu                       */
+  POF_IVP_FITZHUGHNAGUMO = 3,/* ivp.py:44-60   params: a,b,tinv,l               */
+  POF_IVP_ROBER = 4,         /* ivp.py:63-79   params: k1,k2,k3                 */
+  POF_IVP_RIGIDBODY = 5,     /* ivp.py:82-90   params: p0,p1,p2                 */
+  POF_IVP_SEIR = 6,          /* ivp.py:93-109  params: p0,p1,p2,p3              */
+  POF_IVP_THREEBODY = 7,     /* ivp.py:112-126 params: mu                       */
+  POF_IVP_HENONHEILES = 8,   /* ivp.py:137-152 params: p                        */
+  POF_IVP_LORENZ96 = 9       /* synthetic larger-state problem (BASELINE config 5), params: forcing */
+};
+
+/* 1 if the (d, q) leaf kernels are compiled in */
+int pof_supported(int d, int q);
+
+/* default chunk length (steps per thread) for a problem size, chosen to fill the GPU `sm_count` SMs */
+int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count);
+
+/* workspace bytes needed by pof_linear_filtsmooth_f64 / pof_ieks_* for the given chunk length */
+size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len);
+
+/* Batched associative operators on packed elements -- the reference's
+ *   sqrt_filtering_operator(elem1, elem2)   pof/parallel_filtsmooth/filter.py:117-142
+ *   sqrt_smoothing_operator(elem1, elem2)   pof/parallel_filtsmooth/smoother.py:53-63
+ * Packed layouts per element (doubles): filter [A D*D | b D | U D*D | eta D | Z D*D], smoother [g D | E D*D | D D*D].
+ * e1, e2, out: (n, elem) arrays.  elem1 = earlier in time for the filter; for the smoother the reference calls the
+ * operator on the reversed sequence, so elem1 = LATER in time.  One warp per element pair. */
+int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out);
+int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out);
+
+/* Fused linearisation for the built-in IVPs -- replaces vmap(linearize)(om, states[1:])
+ *   pof/step.py:12-22, pof/observations.py:35-40 with om = E1 x - f(E0 x) (pof/convenience.py:26-28):
+ *   H_k = E1 - J_f(E0 m_{k+1}) E0,  c_k = J_f y - f(y), y = E0 m_{k+1},  k = 0..n-1.
+ * scale0, scale1: the Nordsieck scalings E0 = scale0 * e_0^T, E1 = scale1 * e_1^T per block
+ * (pof/transitions.py:53-68).  params: host pointer.  means_t1: the (n,D) rows of states t = 1..n (i.e. means[1:])
+ * -> H (n,d,D), c (n,d). */
+int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
+                          double scale0, double scale1, const double* means_t1, double* H, double* c);
+
+/* One linear filter+smoother pass -- replaces
+ *   pof.parallel_filtsmooth.linear_filtsmooth(x0, dtm, dom)   pof/parallel_filtsmooth/__init__.py:5-10
+ * for the preconditioned IWP transition model (F = I_d (x) flip(pascal), QL = I_d (x) qL; pof/transitions.py:37-50)
+ * and noiseless affine observations (cholR = 0; pof/observations.py:35-40), plus the calibration of
+ * pof/step.py:42-44 and the means test of pof/convergence_criteria.py:9.
+ *   qL_host  : host pointer, (q+1)x(q+1) lower Cholesky factor of flip(hilbert(q+1))
+ *   x0_mean (D), x0_chol (D,D): initial state            H (n,d,D), c (n,d): linearised observation models
+ *   means (N,D): IN the previous trajectory means (compared for convergence), OUT the smoothed means
+ *   chols (N,D,D) or NULL: OUT smoothed Cholesky factors (lower triangular), times sqrt(sigma^2) if calibrate
+ *   fmeans (N,D), fchols (N,D,D) or NULL: OUT filtered states (fchols are square-root factors, not triangular)
+ *   scalars: OUT POF_NSCALARS doubles */
+int pof_linear_filtsmooth_f64(pof_stream_t s, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                              const double* x0_mean, const double* x0_chol, const double* H, const double* c,
+                              double* means, double* chols, double* fmeans, double* fchols, int calibrate,
+                              double* scalars, void* ws, size_t ws_bytes);
+
+/* ---- time-sharded (multi-GPU) form of the same pass: three local stages with two exchange points ----------
+ * Rank r owns the contiguous step range [k_lo, k_hi) of the global n steps; H, c are the LOCAL slices
+ * (k_hi-k_lo steps) and means/chols/fmeans/fchols the LOCAL rows t in (k_lo, k_hi] (plus row t = 0 on rank 0:
+ * local row index = t - t_lo with t_lo = k_lo + (k_lo > 0)), i.e. n_loc + (rank==0) rows.
+ *  stage A: fold + up-sweep -> the rank's filtering element `carry_f` (3D^2+2D doubles)
+ *           [exchange: all-gather carry_f; every rank folds the earlier ranks' elements onto x0 with
+ *            pof_filter_apply_chain_f64 to get its incoming state]
+ *  stage B: down-sweep from `state_in` (D + D*D), filter scan, smoother up-sweep -> `carry_s` (2D^2+D),
+ *           `state_end` (D + D*D filtered state at k_hi), `partials` (3 doubles: nll, ssq_ref, ssq_proper sums)
+ *           [exchange: all-gather carry_s and state_end; pof_smooth_apply_chain_f64 gives the rank's seed;
+ *            all-reduce partials -> cscale]
+ *  stage C: smoother down-sweep from `seed` (D + D*D smoothed state at k_hi), smoother scan
+ *           -> means/chols, `partials2` (2 doubles: obj sum, not-close count); the objective term that couples
+ *           the first local state to the previous rank's last state is added by the rank that owns the step. */
+int pof_shard_stage_a_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* H, const double* c, double* carry_f, void* ws, size_t ws_bytes);
+int pof_shard_stage_b_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
+                          double* carry_s, double* state_end, double* partials, void* ws, size_t ws_bytes);
+int pof_shard_stage_c_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,
+                          double* chols, double* partials2, void* ws, size_t ws_bytes);
+/* state <- op(state, elems[0]), op(.., elems[1]), ... (count packed filter elements, earlier first) */
+int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
+                               double* state_out, double* scratch /* >= D+D*D doubles */);
+/* state <- smoothing op(state(later), elems[count-1]), ..., elems[0]  (elements in time order, applied last-first) */
+int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
+                               double* state_out, double* scratch);
+
+/* Final calibration + projection -- replaces pof/solver.py:66-71 (`chol *= sqrt(ssq)`; ys = E0 states):
+ * ymean (N,d) = scale0 * means[:, b*(q+1)],  ychol (N,d,D) = mult * scale0 * chols[:, b*(q+1), :]. */
+int pof_project_f64(pof_stream_t s, int64_t N, int d, int q, double scale0, const double* mult_dev,
+                    const double* means, const double* chols, double* ymean, double* ychol);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

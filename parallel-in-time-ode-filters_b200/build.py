@@ -1,0 +1,69 @@
+"""Builds libpof_b200.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc.
+
+    python parallel-in-time-ode-filters_b200/build.py [--force]
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpof_b200.so")
+SOURCES = ["pof_api.cu", "pof_leaf_d1.cu", "pof_leaf_d2.cu", "pof_leaf_d3.cu", "pof_leaf_d4.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def _headers():
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [
+        os.path.join(inc, f) for f in os.listdir(inc)
+    ]
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_time = _newest(_headers())
+    jobs = []
+    objs = []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        op = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(op)
+        if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr_time):
+            jobs.append((sp, op))
+
+    def run(job):
+        sp, op = job
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", op]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(op + ".log", "w") as fh:
+            fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {sp}:\n{r.stdout}\n{r.stderr}")
+        return op
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(run, jobs))
+    if jobs or force or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print("built", LIB, "(recompiled %d objects)" % len(jobs))
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

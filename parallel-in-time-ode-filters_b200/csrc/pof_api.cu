@@ -1,0 +1,628 @@
+// C ABI (include/pof_b200.h) of the B200-native parallel-in-time IEKS pass, plus the kernels that are not
+// templated on (d, q): the tree sweeps over chunk carries (one warp per associative combine, pof_coop.cuh),
+// the deterministic scalar reductions, the fused vector-field/Jacobian linearisation for the built-in IVPs
+// and the final calibration + projection.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pof_b200.h"
+#include "pof_coop.cuh"
+#include "pof_launch.cuh"
+#include "pof_pipeline.cuh"
+
+namespace pof {
+
+const LeafLaunch* leaf_launch(int d, int q) {
+  switch (d) {
+    case 1: return leaf_launch_d1(q);
+    case 2: return leaf_launch_d2(q);
+    case 3: return leaf_launch_d3(q);
+    case 4: return leaf_launch_d4(q);
+    default: return nullptr;
+  }
+}
+
+constexpr int TREE_WARPS = 4;  // warps (= element pairs) per CTA in the tree kernels
+
+// ------------------------------------------------------------------------------------------------ tree sweeps
+// up:   parent[i] = op(child[2i], child[2i+1])           (copy if the second child is missing)
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+    k_filter_up(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent, long nparent) {
+  extern __shared__ double sm[];
+  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (gw >= nparent) return;
+  Warp w;
+  const int FE = filter_elem_size(D);
+  const double* lc = child + 2 * gw * FE;
+  double* out = parent + gw * FE;
+  if (2 * gw + 1 < nchild)
+    filter_combine(w, D, lc, lc + FE, out, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
+  else
+    coop_copy(w, out, lc, FE);
+}
+// down (exclusive, state form): cin[2i] = pin[i] ; cin[2i+1] = op(state pin[i], cagg[2i])
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+    k_filter_down(int D, const double* __restrict__ pin, long nparent, const double* __restrict__ cagg, long nchild,
+                  double* __restrict__ cin) {
+  extern __shared__ double sm[];
+  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (gw >= nparent) return;
+  Warp w;
+  const int FE = filter_elem_size(D), ST = state_size(D);
+  const double* p = pin + gw * ST;
+  coop_copy(w, cin + 2 * gw * ST, p, ST);
+  if (2 * gw + 1 < nchild)
+    filter_combine(w, D, p, cagg + 2 * gw * FE, cin + (2 * gw + 1) * ST,
+                   sm + (threadIdx.x >> 5) * coop_ws_doubles(D), true);
+}
+// smoother up: parent[i] = op(e1 = later = child[2i+1], e2 = earlier = child[2i])
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+    k_smooth_up(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent, long nparent) {
+  extern __shared__ double sm[];
+  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (gw >= nparent) return;
+  Warp w;
+  const int SE = smooth_elem_size(D);
+  const double* lc = child + 2 * gw * SE;
+  double* out = parent + gw * SE;
+  if (2 * gw + 1 < nchild)
+    smooth_combine(w, D, lc + SE, lc, out, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
+  else
+    coop_copy(w, out, lc, SE);
+}
+// smoother down (exclusive suffix, state form): cin[2i+1] = pin[i] ; cin[2i] = op(state pin[i], cagg[2i+1])
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+    k_smooth_down(int D, const double* __restrict__ pin, long nparent, const double* __restrict__ cagg, long nchild,
+                  double* __restrict__ cin) {
+  extern __shared__ double sm[];
+  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (gw >= nparent) return;
+  Warp w;
+  const int SE = smooth_elem_size(D), ST = state_size(D);
+  const double* p = pin + gw * ST;
+  if (2 * gw + 1 < nchild) {
+    coop_copy(w, cin + (2 * gw + 1) * ST, p, ST);
+    smooth_combine(w, D, p, cagg + (2 * gw + 1) * SE, cin + 2 * gw * ST,
+                   sm + (threadIdx.x >> 5) * coop_ws_doubles(D), true);
+  } else {
+    coop_copy(w, cin + 2 * gw * ST, p, ST);
+  }
+}
+// batched operators (C-ABI test hooks / S3 seam): out[i] = op(e1[i], e2[i])
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+    k_filter_combine_batched(int D, long n, const double* __restrict__ e1, const double* __restrict__ e2,
+                             double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (gw >= n) return;
+  Warp w;
+  const int FE = filter_elem_size(D);
+  filter_combine(w, D, e1 + gw * FE, e2 + gw * FE, out + gw * FE, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
+}
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+    k_smooth_combine_batched(int D, long n, const double* __restrict__ e1, const double* __restrict__ e2,
+                             double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  if (gw >= n) return;
+  Warp w;
+  const int SE = smooth_elem_size(D);
+  smooth_combine(w, D, e1 + gw * SE, e2 + gw * SE, out + gw * SE, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
+}
+// sequential chains over a handful of rank carries (one warp)
+__global__ void __launch_bounds__(32)
+    k_filter_chain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
+                   double* __restrict__ state_out, double* __restrict__ scratch) {
+  extern __shared__ double sm[];
+  Warp w;
+  const int FE = filter_elem_size(D), ST = state_size(D);
+  // ping-pong between state_out and scratch so that the last write lands in state_out
+  const double* cur = state_in;
+  for (int i = 0; i < count; ++i) {
+    double* dst = ((count - 1 - i) % 2 == 0) ? state_out : scratch;
+    filter_combine(w, D, cur, elems + (long)i * FE, dst, sm, true);
+    w.sync();
+    cur = dst;
+  }
+  if (count == 0) coop_copy(w, state_out, state_in, ST);
+}
+__global__ void __launch_bounds__(32)
+    k_smooth_chain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
+                   double* __restrict__ state_out, double* __restrict__ scratch) {
+  extern __shared__ double sm[];
+  Warp w;
+  const int SE = smooth_elem_size(D), ST = state_size(D);
+  const double* cur = state_in;
+  for (int i = 0; i < count; ++i) {
+    double* dst = ((count - 1 - i) % 2 == 0) ? state_out : scratch;
+    smooth_combine(w, D, cur, elems + (long)(count - 1 - i) * SE, dst, sm, true);
+    w.sync();
+    cur = dst;
+  }
+  if (count == 0) coop_copy(w, state_out, state_in, ST);
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+// out[j] = sum_i part[i*ncomp + j], fixed summation order (deterministic), single CTA
+__global__ void __launch_bounds__(256) k_reduce_parts(const double* __restrict__ part, long cnt, int ncomp,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[256];
+  for (int j = 0; j < ncomp; ++j) {
+    double s = 0.0;
+    for (long i = threadIdx.x; i < cnt; i += 256) s += part[i * ncomp + j];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = sh[0];
+    __syncthreads();
+  }
+}
+// scalars from the filter partial sums [nll, s1, s2] over n*d observations
+__global__ void k_finalize_filter(const double* __restrict__ sums, double n, double d, int calibrate,
+                                  double* __restrict__ scal) {
+  const double ssq = sums[1] / n / d;
+  scal[POF_S_NLL] = sums[0];
+  scal[POF_S_SSQ] = ssq;
+  scal[POF_S_SSQ_PROPER] = sums[2] / n / d;
+  scal[POF_S_CSCALE] = calibrate ? sqrt(ssq) : 1.0;
+}
+__global__ void k_finalize_smooth(const double* __restrict__ sums, double* __restrict__ scal) {
+  scal[POF_S_OBJ] = sums[0];
+  scal[POF_S_NOT_CLOSE] = sums[1];
+}
+__global__ void k_pack_state(int D, const double* __restrict__ m, const double* __restrict__ L,
+                             double* __restrict__ st) {
+  for (int i = threadIdx.x; i < D + D * D; i += blockDim.x) st[i] = (i < D) ? m[i] : L[i - D];
+}
+
+// ------------------------------------------------------------------------------------------------ linearise
+struct IvpParams {
+  double p[8];
+};
+// vector field f and Jacobian J (row-major dxd) of the built-in problems, reference pof/ivp.py
+__device__ __forceinline__ bool ivp_eval(int id, const IvpParams& P, const double* y, double* f, double* J) {
+  switch (id) {
+    case POF_IVP_LOGISTIC:
+      f[0] = y[0] * (1.0 - y[0]);
+      J[0] = 1.0 - 2.0 * y[0];
+      return true;
+    case POF_IVP_LOTKAVOLTERRA: {
+      const double a = P.p[0], b = P.p[1], c = P.p[2], dd = P.p[3];
+      f[0] = a * y[0] - b * y[0] * y[1];
+      f[1] = -c * y[1] + dd * y[0] * y[1];
+      J[0] = a - b * y[1]; J[1] = -b * y[0];
+      J[2] = dd * y[1];    J[3] = -c + dd * y[0];
+      return true;
+    }
+    case POF_IVP_VANDERPOL: {
+      const double mu = P.p[0];
+      f[0] = y[1];
+      f[1] = mu * ((1.0 - y[0] * y[0]) * y[1] - y[0]);
+      J[0] = 0.0; J[1] = 1.0;
+      J[2] = mu * (-2.0 * y[0] * y[1] - 1.0); J[3] = mu * (1.0 - y[0] * y[0]);
+      return true;
+    }
+    case POF_IVP_FITZHUGHNAGUMO: {
+      const double a = P.p[0], b = P.p[1], tinv = P.p[2], l = P.p[3];
+      f[0] = y[0] - (y[0] * y[0] * y[0]) / 3.0 - y[1] + l;
+      f[1] = tinv * (y[0] + a - b * y[1]);
+      J[0] = 1.0 - y[0] * y[0]; J[1] = -1.0;
+      J[2] = tinv;              J[3] = -tinv * b;
+      return true;
+    }
+    case POF_IVP_ROBER: {
+      const double k1 = P.p[0], k2 = P.p[1], k3 = P.p[2];
+      f[0] = -k1 * y[0] + k3 * y[1] * y[2];
+      f[1] = k1 * y[0] - k2 * y[1] * y[1] - k3 * y[1] * y[2];
+      f[2] = k2 * y[1] * y[1];
+      J[0] = -k1; J[1] = k3 * y[2];                     J[2] = k3 * y[1];
+      J[3] = k1;  J[4] = -2.0 * k2 * y[1] - k3 * y[2];  J[5] = -k3 * y[1];
+      J[6] = 0.0; J[7] = 2.0 * k2 * y[1];               J[8] = 0.0;
+      return true;
+    }
+    case POF_IVP_RIGIDBODY: {
+      const double p0 = P.p[0], p1 = P.p[1], p2 = P.p[2];
+      f[0] = p0 * y[1] * y[2]; f[1] = p1 * y[0] * y[2]; f[2] = p2 * y[0] * y[1];
+      J[0] = 0.0;       J[1] = p0 * y[2]; J[2] = p0 * y[1];
+      J[3] = p1 * y[2]; J[4] = 0.0;       J[5] = p1 * y[0];
+      J[6] = p2 * y[1]; J[7] = p2 * y[0]; J[8] = 0.0;
+      return true;
+    }
+    case POF_IVP_SEIR: {
+      const double p0 = P.p[0], p1 = P.p[1], p2 = P.p[2], p3 = P.p[3];
+      const double inf = p1 * y[0] * y[2] / p3;
+      f[0] = -inf; f[1] = inf - p0 * y[1]; f[2] = p0 * y[1] - p2 * y[2]; f[3] = p2 * y[2];
+      const double i0 = p1 * y[2] / p3, i2 = p1 * y[0] / p3;
+      J[0] = -i0;  J[1] = 0.0;  J[2] = -i2;  J[3] = 0.0;
+      J[4] = i0;   J[5] = -p0;  J[6] = i2;   J[7] = 0.0;
+      J[8] = 0.0;  J[9] = p0;   J[10] = -p2; J[11] = 0.0;
+      J[12] = 0.0; J[13] = 0.0; J[14] = p2;  J[15] = 0.0;
+      return true;
+    }
+    case POF_IVP_THREEBODY: {
+      const double mu = P.p[0], mp = 1.0 - P.p[0];
+      const double a1 = y[0] + mu, a2 = y[0] - mp, y1 = y[1];
+      const double r1s = a1 * a1 + y1 * y1, r2s = a2 * a2 + y1 * y1;
+      const double r1 = sqrt(r1s), r2 = sqrt(r2s);
+      const double i13 = 1.0 / (r1s * r1), i23 = 1.0 / (r2s * r2);
+      const double i15 = i13 / r1s, i25 = i23 / r2s;
+      f[0] = y[2];
+      f[1] = y[3];
+      f[2] = y[0] + 2.0 * y[3] - mp * a1 * i13 - mu * a2 * i23;
+      f[3] = y1 - 2.0 * y[2] - mp * y1 * i13 - mu * y1 * i23;
+      const double cross = 3.0 * mp * a1 * y1 * i15 + 3.0 * mu * a2 * y1 * i25;
+      J[0] = 0.0; J[1] = 0.0; J[2] = 1.0; J[3] = 0.0;
+      J[4] = 0.0; J[5] = 0.0; J[6] = 0.0; J[7] = 1.0;
+      J[8] = 1.0 - mp * (i13 - 3.0 * a1 * a1 * i15) - mu * (i23 - 3.0 * a2 * a2 * i25);
+      J[9] = cross; J[10] = 0.0; J[11] = 2.0;
+      J[12] = cross;
+      J[13] = 1.0 - mp * (i13 - 3.0 * y1 * y1 * i15) - mu * (i23 - 3.0 * y1 * y1 * i25);
+      J[14] = -2.0; J[15] = 0.0;
+      return true;
+    }
+    case POF_IVP_HENONHEILES: {
+      const double p = P.p[0];
+      f[0] = y[2]; f[1] = y[3];
+      f[2] = -y[0] - 2.0 * p * y[0] * y[1];
+      f[3] = -y[1] - p * (y[0] * y[0] - y[1] * y[1]);
+      J[0] = 0.0; J[1] = 0.0; J[2] = 1.0; J[3] = 0.0;
+      J[4] = 0.0; J[5] = 0.0; J[6] = 0.0; J[7] = 1.0;
+      J[8] = -1.0 - 2.0 * p * y[1]; J[9] = -2.0 * p * y[0];       J[10] = 0.0; J[11] = 0.0;
+      J[12] = -2.0 * p * y[0];      J[13] = -1.0 + 2.0 * p * y[1]; J[14] = 0.0; J[15] = 0.0;
+      return true;
+    }
+    default:
+      return false;
+  }
+}
+// one thread per step k: H_k = E1 - J E0, c_k = J y - f(y) at y = E0 m_{k+1}
+__global__ void __launch_bounds__(256)
+    k_linearize(int ivp_id, IvpParams P, long n, int d, int q, double scale0, double scale1,
+                const double* __restrict__ means_t1, double* __restrict__ H, double* __restrict__ c) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int Q1 = q + 1, D = d * Q1;
+  double y[4], f[4], J[16];
+  for (int b = 0; b < d; ++b) y[b] = scale0 * means_t1[k * D + b * Q1];
+  ivp_eval(ivp_id, P, y, f, J);
+  for (int a = 0; a < d; ++a) {
+    double ca = -f[a];
+    for (int b = 0; b < d; ++b) ca = fma(J[a * d + b], y[b], ca);
+    c[k * d + a] = ca;
+    double* Hr = H + (k * d + a) * D;
+    for (int j = 0; j < D; ++j) Hr[j] = 0.0;
+    for (int b = 0; b < d; ++b) Hr[b * Q1] = -J[a * d + b] * scale0;
+    Hr[a * Q1 + 1] += scale1;
+  }
+}
+// ys = E0 states, with the (second) calibration multiplier of pof/solver.py:66-69 read from device memory
+__global__ void __launch_bounds__(256)
+    k_project(long N, int d, int q, double scale0, const double* __restrict__ mult, const double* __restrict__ means,
+              const double* __restrict__ chols, double* __restrict__ ymean, double* __restrict__ ychol) {
+  const int Q1 = q + 1, D = d * Q1;
+  const long total = N * d * (D + 1);
+  const double mu = mult ? *mult : 1.0;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long row = idx / (D + 1);
+    const int col = (int)(idx - row * (D + 1));
+    const long t = row / d;
+    const int b = (int)(row - t * d);
+    if (col == D) {
+      ymean[row] = scale0 * means[t * D + b * Q1];
+    } else if (ychol) {
+      ychol[row * D + col] = mu * scale0 * chols[(t * D + b * Q1) * D + col];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct WsLayout {
+  TreeLevels tl;
+  long CS, L;
+  int D, FE, SE, ST, NE;
+  size_t o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, total;  // in doubles
+  void build(long n, int d, int q, long chunk_len) {
+    D = d * (q + 1);
+    FE = 3 * D * D + 2 * D;
+    SE = 2 * D * D + D;
+    ST = D * D + D;
+    NE = D + 2 * D * D;
+    L = chunk_len < 1 ? 1 : chunk_len;
+    CS = (n + L - 1) / L;
+    if (CS < 1) CS = 1;
+    tl.build(CS);
+    size_t o = 0;
+    auto take = [&](size_t cnt) {
+      size_t r = o;
+      o += (cnt + 31) & ~(size_t)31;
+      return r;
+    };
+    o_fagg = take((size_t)tl.total * FE);
+    o_fin = take((size_t)tl.total * ST);
+    o_sagg = take((size_t)tl.total * SE);
+    o_sin = take((size_t)tl.total * ST);
+    o_kern = take((size_t)L * NE * CS);
+    o_send = take((size_t)CS * ST);
+    o_part = take((size_t)CS * 3);
+    o_part2 = take((size_t)CS * 2);
+    o_sums = take(16);
+    o_misc = take((size_t)2 * ST + 64);
+    total = o;
+  }
+};
+
+static inline int tree_smem_bytes(int D) { return TREE_WARPS * coop_ws_doubles(D) * (int)sizeof(double); }
+
+template <class K>
+static cudaError_t set_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return cudaSuccess;
+}
+
+#define POF_CK(x)                     \
+  do {                                \
+    cudaError_t e__ = (x);            \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+
+static int make_args(long n, int d, int q, const double* qL_host, const double* H, const double* c,
+                     const WsLayout& wl, LeafArgs& a) {
+  if (q < 1 || q > 5) return POF_E_UNSUPPORTED_DQ;
+  a.n = n;
+  a.L = wl.L;
+  a.CS = wl.CS;
+  a.H = H;
+  a.c = c;
+  for (int i = 0; i < 36; ++i) a.ql.v[i] = 0.0;
+  for (int i = 0; i < (q + 1) * (q + 1); ++i) a.ql.v[i] = qL_host[i];
+  return 0;
+}
+
+// stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
+static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws) {
+  double* fagg = ws + wl.o_fagg;
+  POF_CK(ll->fold(s, a, fagg));
+  const int smem = tree_smem_bytes(wl.D);
+  POF_CK(set_smem(k_filter_up, smem));
+  for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
+    const long np = wl.tl.sz[l + 1];
+    k_filter_up<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+        wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np);
+  }
+  return (int)cudaGetLastError();
+}
+// stage B: filter down-sweep from the root's incoming state (already stored at fin[root]), scan, smoother up-sweep
+static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
+                   double* fmeans, double* fchols) {
+  double* fagg = ws + wl.o_fagg;
+  double* fin = ws + wl.o_fin;
+  double* sagg = ws + wl.o_sagg;
+  const int smem = tree_smem_bytes(wl.D);
+  POF_CK(set_smem(k_filter_down, smem));
+  POF_CK(set_smem(k_smooth_up, smem));
+  for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+    const long np = wl.tl.sz[l];
+    k_filter_down<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+        wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
+        fin + wl.tl.off[l - 1] * wl.ST);
+  }
+  POF_CK(cudaGetLastError());
+  POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+  for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
+    const long np = wl.tl.sz[l + 1];
+    k_smooth_up<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+        wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
+  }
+  k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+  return (int)cudaGetLastError();
+}
+// stage C: smoother down-sweep from the seed (already stored at sin[root]) + smoother scan
+static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
+                   int emit_t0, const double* cscale, double* means, double* chols) {
+  double* sagg = ws + wl.o_sagg;
+  double* sin_ = ws + wl.o_sin;
+  const int smem = tree_smem_bytes(wl.D);
+  POF_CK(set_smem(k_smooth_down, smem));
+  for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+    const long np = wl.tl.sz[l];
+    k_smooth_down<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+        wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
+        sin_ + wl.tl.off[l - 1] * wl.ST);
+  }
+  POF_CK(cudaGetLastError());
+  POF_CK(ll->smooth(s, a, sin_, ws + wl.o_kern, emit_t0, cscale, means, chols, ws + wl.o_part2));
+  k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part2, wl.CS, 2, ws + wl.o_sums + 8);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pof
+
+using namespace pof;
+
+extern "C" {
+
+int pof_supported(int d, int q) { return leaf_launch(d, q) != nullptr ? 1 : 0; }
+
+int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count) {
+  (void)d;
+  (void)q;
+  if (sm_count <= 0) sm_count = 148;
+  const int64_t n = N - 1;
+  const int64_t target = (int64_t)sm_count * 256;  // one chunk per thread, ~8 warps per SM
+  int64_t L = (n + target - 1) / target;
+  if (L < 4) L = 4;
+  return L;
+}
+
+size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
+  WsLayout wl;
+  wl.build(N - 1, d, q, chunk_len);
+  return wl.total * sizeof(double);
+}
+
+int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
+  if (n <= 0) return 0;
+  const int smem = tree_smem_bytes(D);
+  POF_CK(set_smem(k_filter_combine_batched, smem));
+  k_filter_combine_batched<<<(unsigned)((n + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem,
+                             (cudaStream_t)s>>>(D, n, e1, e2, out);
+  return (int)cudaGetLastError();
+}
+int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
+  if (n <= 0) return 0;
+  const int smem = tree_smem_bytes(D);
+  POF_CK(set_smem(k_smooth_combine_batched, smem));
+  k_smooth_combine_batched<<<(unsigned)((n + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem,
+                             (cudaStream_t)s>>>(D, n, e1, e2, out);
+  return (int)cudaGetLastError();
+}
+
+int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
+                          double scale0, double scale1, const double* means_t1, double* H, double* c) {
+  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
+  if (d < 1 || d > 4 || nparams > 8) return POF_E_ARG;
+  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
+  if (dims[ivp_id] != d) return POF_E_ARG;
+  IvpParams P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
+  if (n <= 0) return 0;
+  k_linearize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, scale1, means_t1,
+                                                                        H, c);
+  return (int)cudaGetLastError();
+}
+
+int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                              const double* x0_mean, const double* x0_chol, const double* H, const double* c,
+                              double* means, double* chols, double* fmeans, double* fchols, int calibrate,
+                              double* scalars, void* ws_, size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (N < 2) return POF_E_ARG;
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (!ll) return POF_E_UNSUPPORTED_DQ;
+  WsLayout wl;
+  wl.build(N - 1, d, q, chunk_len);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  LeafArgs a;
+  int rc = make_args(N - 1, d, q, qL_host, H, c, wl, a);
+  if (rc) return rc;
+  rc = stage_a(s, ll, a, wl, ws);
+  if (rc) return rc;
+  // root's incoming state = x0
+  k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
+  if (fmeans) {
+    POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols);
+  if (rc) return rc;
+  k_finalize_filter<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, calibrate, scalars);
+  // terminal smoothing state = filtered state at the last time point
+  POF_CK(cudaMemcpyAsync(ws + wl.o_sin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, ws + wl.o_send + (wl.CS - 1) * wl.ST,
+                         wl.ST * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  rc = stage_c(s, ll, a, wl, ws, 1, scalars + POF_S_CSCALE, means, chols);
+  if (rc) return rc;
+  k_finalize_smooth<<<1, 1, 0, s>>>(ws + wl.o_sums + 8, scalars);
+  return (int)cudaGetLastError();
+}
+
+int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* H, const double* c, double* carry_f, void* ws_, size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (n_loc < 1) return POF_E_ARG;
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (!ll) return POF_E_UNSUPPORTED_DQ;
+  WsLayout wl;
+  wl.build(n_loc, d, q, chunk_len);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  LeafArgs a;
+  int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
+  if (rc) return rc;
+  rc = stage_a(s, ll, a, wl, ws);
+  if (rc) return rc;
+  POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(double),
+                         cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
+                          double* carry_s, double* state_end, double* partials, void* ws_, size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (!ll) return POF_E_UNSUPPORTED_DQ;
+  WsLayout wl;
+  wl.build(n_loc, d, q, chunk_len);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  LeafArgs a;
+  int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
+  if (rc) return rc;
+  POF_CK(cudaMemcpyAsync(ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, state_in, wl.ST * sizeof(double),
+                         cudaMemcpyDeviceToDevice, s));
+  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols);
+  if (rc) return rc;
+  POF_CK(cudaMemcpyAsync(carry_s, ws + wl.o_sagg + wl.tl.off[wl.tl.nlev - 1] * wl.SE, wl.SE * sizeof(double),
+                         cudaMemcpyDeviceToDevice, s));
+  POF_CK(cudaMemcpyAsync(state_end, ws + wl.o_send + (wl.CS - 1) * wl.ST, wl.ST * sizeof(double),
+                         cudaMemcpyDeviceToDevice, s));
+  POF_CK(cudaMemcpyAsync(partials, ws + wl.o_sums, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int pof_shard_stage_c_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,
+                          double* chols, double* partials2, void* ws_, size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  (void)is_last_rank;
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (!ll) return POF_E_UNSUPPORTED_DQ;
+  WsLayout wl;
+  wl.build(n_loc, d, q, chunk_len);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  LeafArgs a;
+  int rc = make_args(n_loc, d, q, qL_host, nullptr, nullptr, wl, a);
+  if (rc) return rc;
+  POF_CK(cudaMemcpyAsync(ws + wl.o_sin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, seed, wl.ST * sizeof(double),
+                         cudaMemcpyDeviceToDevice, s));
+  // local row of state t' is t' - (1 - has_row0): shift the base pointers so that the kernels can index by t'
+  const long shift = has_row0 ? 0 : 1;
+  double* mb = means - shift * wl.D;
+  double* cb = chols ? chols - shift * (long)wl.D * wl.D : nullptr;
+  rc = stage_c(s, ll, a, wl, ws, has_row0, cscale, mb, cb);
+  if (rc) return rc;
+  POF_CK(cudaMemcpyAsync(partials2, ws + wl.o_sums + 8, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
+                               double* state_out, double* scratch) {
+  const int smem = coop_ws_doubles(D) * (int)sizeof(double);
+  POF_CK(set_smem(k_filter_chain, smem));
+  k_filter_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
+  return (int)cudaGetLastError();
+}
+int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
+                               double* state_out, double* scratch) {
+  const int smem = coop_ws_doubles(D) * (int)sizeof(double);
+  POF_CK(set_smem(k_smooth_chain, smem));
+  k_smooth_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
+  return (int)cudaGetLastError();
+}
+
+int pof_project_f64(pof_stream_t s, int64_t N, int d, int q, double scale0, const double* mult_dev,
+                    const double* means, const double* chols, double* ymean, double* ychol) {
+  const long total = (long)N * d * (d * (q + 1) + 1);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  k_project<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(N, d, q, scale0, mult_dev, means, chols, ymean, ychol);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// Launch interface between the (d, q)-templated leaf kernels (compiled in pof_leaf_d*.cu, one translation unit
+// per ODE dimension so that nvcc builds them in parallel) and the C ABI in pof_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pof {
+
+struct QLParam {
+  double v[36];  // (q+1) x (q+1) row-major, q <= 5; lives in the kernel-parameter constant bank
+};
+
+struct LeafArgs {
+  long n;    // local number of steps
+  long L;    // chunk length
+  long CS;   // number of chunks
+  const double* H;
+  const double* c;
+  QLParam ql;
+};
+
+struct LeafLaunch {
+  cudaError_t (*fold)(cudaStream_t, const LeafArgs&, double* fagg);
+  cudaError_t (*scan)(cudaStream_t, const LeafArgs&, const double* fin, double* kern, double* sagg, double* send,
+                      double* part, double* fmeans, double* fchols);
+  cudaError_t (*smooth)(cudaStream_t, const LeafArgs&, const double* sin, const double* kern, int emit_t0,
+                        const double* cscale, double* means, double* chols, double* part2);
+};
+
+// returns nullptr if (d, q) is not compiled in
+const LeafLaunch* leaf_launch(int d, int q);
+const LeafLaunch* leaf_launch_d1(int q);
+const LeafLaunch* leaf_launch_d2(int q);
+const LeafLaunch* leaf_launch_d3(int q);
+const LeafLaunch* leaf_launch_d4(int q);
+
+}  // namespace pof

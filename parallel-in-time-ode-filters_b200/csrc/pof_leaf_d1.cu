@@ -1,0 +1,2 @@
+#include "pof_leaf_kernels.cuh"
+POF_DEFINE_LEAF_D(1)

@@ -1,0 +1,143 @@
+"""ctypes binding of libpof_b200.so (the C ABI declared in include/pof_b200.h).
+
+The product path has NO CPU fallback: importing this module without the built CUDA library raises.
+Device memory, streams and (for time-sharded runs) collectives are torch's; every numerical step of the hot path is
+a kernel of the library.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libpof_b200.so")
+
+S_NLL, S_OBJ, S_SSQ, S_SSQ_PROPER, S_NOT_CLOSE, S_CSCALE, NSCALARS = 0, 1, 2, 3, 4, 5, 8
+
+IVP_IDS = dict(
+    logistic=0, lotkavolterra=1, vanderpol=2, fitzhughnagumo=3, rober=4, rigid_body=5, seir=6, threebody=7,
+    henonheiles=8,
+)
+
+_c_dp = ctypes.c_void_p
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_dbl = ctypes.c_double
+_c_sz = ctypes.c_size_t
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    sig = {
+        "pof_supported": (_c_int, [_c_int, _c_int]),
+        "pof_default_chunk_len": (_c_i64, [_c_i64, _c_int, _c_int, _c_int]),
+        "pof_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_i64]),
+        "pof_filter_combine_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_dp, _c_dp, _c_dp]),
+        "pof_smooth_combine_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_dp, _c_dp, _c_dp]),
+        "pof_linearize_ivp_f64": (
+            _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_dp]),
+        "pof_linear_filtsmooth_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_a_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_b_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_c_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_sz]),
+        "pof_filter_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+LIB = _load()
+EXPORTED = [
+    "pof_supported", "pof_default_chunk_len", "pof_workspace_bytes", "pof_filter_combine_f64",
+    "pof_smooth_combine_f64", "pof_linearize_ivp_f64", "pof_linear_filtsmooth_f64", "pof_shard_stage_a_f64",
+    "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
+    "pof_project_f64",
+]
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc > 0:
+            raise NativeError(f"{what}: CUDA error {rc}")
+        names = {-1: "unsupported (d, q)", -2: "workspace too small", -3: "bad argument", -4: "unknown IVP"}
+        raise NativeError(f"{what}: {names.get(rc, rc)}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise NativeError("pof_b200 kernels need contiguous float64 CUDA tensors (there is no CPU fallback)")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_doubles(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+_SM_COUNT = {}
+
+
+def sm_count(device=None):
+    dev = torch.cuda.current_device() if device is None else device
+    if dev not in _SM_COUNT:
+        _SM_COUNT[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _SM_COUNT[dev]
+
+
+class Workspace:
+    """Caller-owned scratch memory for one problem shape (N, d, q, chunk_len) on one device."""
+
+    _cache = {}
+
+    def __init__(self, N, d, q, chunk_len, device):
+        self.N, self.d, self.q, self.chunk_len = int(N), int(d), int(q), int(chunk_len)
+        self.nbytes = int(LIB.pof_workspace_bytes(self.N, self.d, self.q, self.chunk_len))
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+
+    @classmethod
+    def get(cls, N, d, q, chunk_len, device):
+        key = (int(N), int(d), int(q), int(chunk_len), str(device))
+        ws = cls._cache.get(key)
+        if ws is None:
+            if len(cls._cache) > 4:
+                cls._cache.clear()
+            ws = cls._cache[key] = cls(N, d, q, chunk_len, device)
+        return ws
+
+
+def default_chunk_len(N, d, q, device=None):
+    return int(LIB.pof_default_chunk_len(int(N), int(d), int(q), sm_count(device)))

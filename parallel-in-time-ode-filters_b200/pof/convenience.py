@@ -1,0 +1,69 @@
+"""Problem set-up (reference pof/convenience.py:13-45, 76-92)."""
+import numpy as np
+import torch
+
+from . import initialization as init
+from .observations import NonlinearModel
+from .transitions import (IWP, TransitionModel, nordsieck_preconditioner, nordsieck_scalings,
+                          preconditioned_discretize, preconditioned_discretize_1d, projection_matrix)
+from .utils import MVNSqrt
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pof_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def set_up_solver(*, f, y0, ts, order):
+    """reference convenience.py:13-45.  `dtm` holds ONE (D,D) copy of F and QL (the reference replicates the
+    identical matrices n times); `om.f` carries what the fused linearisation kernel needs."""
+    dev = _device()
+    ts_h = np.asarray(torch.as_tensor(ts, dtype=torch.float64).detach().cpu())
+    y0_h = torch.as_tensor(y0, dtype=torch.float64).detach().cpu()
+    dt = float(ts_h[1] - ts_h[0])  # uniform grid assumed, as in the reference (convenience.py:14-16)
+    d = int(y0_h.shape[0])
+
+    iwp = IWP(num_derivatives=order, wiener_process_dimension=d)
+    F, QL = preconditioned_discretize(iwp)
+    _, qL = preconditioned_discretize_1d(iwp)
+    P, PI = nordsieck_preconditioner(iwp, dt)
+    sv, _ = nordsieck_scalings(iwp, dt)
+    E0 = projection_matrix(iwp, 0) @ P
+    E1 = projection_matrix(iwp, 1) @ P
+
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    E0_t, E1_t = tt(E0), tt(E1)
+
+    def om_f(x):
+        return E1_t.to(x.device) @ x - f(None, E0_t.to(x.device) @ x)
+
+    om_f._pof_lin = dict(
+        builtin=getattr(f, "_pof_builtin", None), f=f, scale0=float(sv[0]), scale1=float(sv[1]) if order >= 1 else 0.0,
+        d=d, q=order, E0=E0_t, E1=E1_t,
+    )
+    om = NonlinearModel(om_f)
+
+    x0 = init.taylor_mode_init(f, y0_h, order)
+    PI_t = tt(PI)
+    x0 = MVNSqrt(PI_t @ x0.mean.to(dev), PI_t @ x0.chol.to(dev))
+
+    return {
+        "f": f, "y0": y0_h, "ts": ts_h, "dtm": TransitionModel(tt(F), tt(QL)), "om": om, "x0": x0,
+        "E0": E0_t, "P": tt(P), "PI": PI_t, "order": order, "iwp": iwp,
+        "_qL": np.ascontiguousarray(qL), "_scale0": float(sv[0]), "_device": dev,
+    }
+
+
+def get_initial_trajectory(setup, method="prior"):
+    """reference convenience.py:76-92 ('coarse' needs sequential_eks_solve + interpolation: not in this tier)"""
+    f, y0, order, ts = setup["f"], setup["y0"], setup["order"], setup["ts"]
+    PI, dev = setup["PI"], setup["_device"]
+    if method == "constant":
+        st = init.constant_init(y0=y0, order=order, ts=ts, f=f)
+        return MVNSqrt((st.mean.to(dev) @ PI.T).contiguous(), st.chol.to(dev))  # PI @ 0 = 0
+    elif method == "prior":
+        st = init.prior_init(f=f, y0=y0, order=order, ts=ts)
+        return MVNSqrt(st.mean.to(dev).contiguous(), st.chol.to(dev).contiguous())
+    else:
+        raise Exception(f"method={method} not found")

@@ -1,0 +1,72 @@
+"""Initial state x0 and initial linearisation trajectories (reference pof/initialization.py).
+
+`taylor_mode_init` replaces the un-vendored `tornadox.init.TaylorMode` (initialization.py:15-22) by nested
+forward-mode jvps: y^(0) = y0, y^(k+1) = d/dt y^(k) = J_{y^(k)}(y) f(y).  One-off host-side set-up (tiny tensors).
+"""
+import numpy as np
+import torch
+
+from .transitions import IWP, nordsieck_preconditioner, preconditioned_discretize
+from .utils import MVNSqrt
+
+
+def _cpu64(y):
+    return torch.as_tensor(y, dtype=torch.float64).detach().cpu()
+
+
+def taylor_derivatives(f, y0, num_derivatives):
+    """rows y^{(k)}(t0), k = 0..q, shape (q+1, d)"""
+    y0 = _cpu64(y0)
+
+    def fy(y):
+        return f(None, y)
+
+    def deriv(k):
+        if k == 0:
+            return lambda y: y
+        prev = deriv(k - 1)
+        return lambda y: torch.func.jvp(prev, (y,), (fy(y),))[1]
+
+    rows = [deriv(k)(y0) for k in range(num_derivatives + 1)]
+    return torch.stack(rows)
+
+
+def taylor_mode_init(f, y0, num_derivatives):
+    """reference initialization.py:15-22: mean = [y1, y1', .., y1^(q), y2, ..], chol = 0"""
+    derivs = taylor_derivatives(f, y0, num_derivatives)  # (q+1, d)
+    m0 = derivs.T.reshape(-1).contiguous()
+    D = m0.shape[0]
+    return MVNSqrt(m0, torch.zeros((D, D), dtype=torch.float64))
+
+
+def constant_init(*, y0, order, ts, f=True):
+    """reference initialization.py:42-56"""
+    y0 = _cpu64(y0)
+    d = y0.shape[-1]
+    N = len(ts)
+    dy0 = _cpu64(f(None, y0)) if f is not None else torch.zeros_like(y0)
+    x0 = torch.cat([y0[:, None], dy0[:, None], torch.zeros((d, order - 1), dtype=torch.float64)], dim=1).reshape(1, -1)
+    traj = x0.repeat(N, 1)
+    D = traj.shape[1]
+    return MVNSqrt(traj, torch.zeros((N, D, D), dtype=torch.float64))
+
+
+def prior_init(*, f, y0, order, ts):
+    """reference initialization.py:75-89, including its quirk: the step sizes are the absolute times ts[1:], and the
+    trajectory is returned in NON-preconditioned coordinates.  Only the means feed the first linearisation."""
+    x0 = taylor_mode_init(f, y0, order)
+    d = int(_cpu64(y0).shape[0])
+    iwp = IWP(num_derivatives=order, wiener_process_dimension=d)
+    F, QL = preconditioned_discretize(iwp)
+    ts = np.asarray(_cpu64(ts))
+    N = len(ts)
+    D = x0.mean.shape[0]
+    means = np.empty((N, D))
+    chols = np.zeros((N, D, D))
+    m0 = x0.mean.numpy()
+    means[0] = m0
+    for k, dt in enumerate(ts[1:]):
+        P, PI = nordsieck_preconditioner(iwp, dt)
+        means[k + 1] = P @ F @ PI @ m0
+        chols[k + 1] = P @ QL
+    return MVNSqrt(torch.from_numpy(means), torch.from_numpy(chols))

@@ -1,0 +1,112 @@
+"""Parallel-in-time square-root filter / smoother (reference pof/parallel_filtsmooth/).
+
+Same entry points and return values as the reference; every one of them runs the CUDA pass
+(pof_linear_filtsmooth_f64: blocked prefix / suffix scans) -- nothing is computed on the host.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+from ..observations import AffineModel
+from ..transitions import IWP, TransitionModel, preconditioned_discretize
+from ..utils import MVNSqrt
+
+
+def _model_dims(dtm: TransitionModel, dom: AffineModel):
+    n, d, D = dom.H.shape
+    if D % d != 0:
+        raise ValueError("state dimension must be d*(q+1)")
+    q = D // d - 1
+    F = dtm.F[0] if dtm.F.dim() == 3 else dtm.F
+    QL = dtm.QL[0] if dtm.QL.dim() == 3 else dtm.QL
+    Fi, QLi = preconditioned_discretize(IWP(num_derivatives=q, wiener_process_dimension=d))
+    Fh, QLh = F.detach().cpu().numpy(), QL.detach().cpu().numpy()
+    if not (np.allclose(Fh, Fi, rtol=0, atol=1e-12) and np.allclose(QLh, QLi, rtol=0, atol=1e-12)):
+        raise NotImplementedError(
+            "the CUDA pass is specialised to the preconditioned IWP transition model of pof.transitions "
+            "(F = I_d (x) flip(pascal), QL = I_d (x) chol(flip(hilbert))); other transition models are out of scope"
+        )
+    if dom.cholR is not None and bool((dom.cholR != 0).any()):
+        raise NotImplementedError("noisy observations (cholR != 0) are out of scope of this tier")
+    return n, d, q, D, np.ascontiguousarray(QLi[: q + 1, : q + 1])
+
+
+def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_len=None, fmeans=None, fchols=None,
+             scalars=None):
+    """One filter+smoother pass on device buffers (the call `solve` makes every iteration)."""
+    N = means_io.shape[0]
+    nat.require_cuda(x0.mean, x0.chol, H, c, means_io, chols, fmeans, fchols)
+    dev = means_io.device
+    if chunk_len is None:
+        chunk_len = nat.default_chunk_len(N, d, q, dev.index)
+    ws = nat.Workspace.get(N, d, q, chunk_len, dev)
+    if scalars is None:
+        scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+    qLh, qLp = nat.host_doubles(qL)
+    rc = nat.LIB.pof_linear_filtsmooth_f64(
+        nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
+        nat.ptr(means_io), nat.ptr(chols), nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)), nat.ptr(scalars),
+        ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+    nat.check(rc, "pof_linear_filtsmooth_f64")
+    return scalars
+
+
+def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None):
+    """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq)"""
+    n, d, q, D, qL = _model_dims(linear_transitions, linear_observations)
+    dev = linear_observations.H.device
+    means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
+    chols = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
+    sc = run_pass(x0, qL, linear_observations.H.contiguous(), linear_observations.b.contiguous(), means, chols, d=d,
+                  q=q, calibrate=False, chunk_len=chunk_len)
+    return MVNSqrt(means, chols), sc[nat.S_NLL], sc[nat.S_OBJ], sc[nat.S_SSQ]
+
+
+def linear_noiseless_filtering(x0, transition_models, observation_models, *, chunk_len=None):
+    """reference parallel_filtsmooth/filter.py:18-47 -> (filtered MVNSqrt, nll, obj, ssq).
+    The filtered chols are square-root factors (chol @ chol.T is the covariance) but not triangular."""
+    n, d, q, D, qL = _model_dims(transition_models, observation_models)
+    dev = observation_models.H.device
+    means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
+    fm = torch.empty((n + 1, D), dtype=torch.float64, device=dev)
+    fc = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
+    sc = run_pass(x0, qL, observation_models.H.contiguous(), observation_models.b.contiguous(), means, None, d=d, q=q,
+                  calibrate=False, chunk_len=chunk_len, fmeans=fm, fchols=fc)
+    # filter objective (reference filter.py:43-45, swapped-argument form), evaluated on the filtered means
+    F = transition_models.F[0] if transition_models.F.dim() == 3 else transition_models.F
+    QL = transition_models.QL[0] if transition_models.QL.dim() == 3 else transition_models.QL
+    r = torch.linalg.solve_triangular(QL, (fm[:-1] - fm[1:] @ F.T).T, upper=False)
+    obj = (r * r).sum()
+    return MVNSqrt(fm, fc), sc[nat.S_NLL], obj, sc[nat.S_SSQ]
+
+
+def _pack(parts):
+    n = parts[0].shape[0]
+    return torch.cat([p.reshape(n, -1) for p in parts], dim=1).contiguous()
+
+
+def sqrt_filtering_operator(elem1, elem2):
+    """reference filter.py:117-142 (batched over the leading axis): elems are tuples (A, b, U, eta, Z)"""
+    n, D = elem1[1].shape
+    e1, e2 = _pack(elem1), _pack(elem2)
+    nat.require_cuda(e1, e2)
+    out = torch.empty_like(e1)
+    nat.check(nat.LIB.pof_filter_combine_f64(nat.stream_ptr(), n, D, nat.ptr(e1), nat.ptr(e2), nat.ptr(out)),
+              "pof_filter_combine_f64")
+    DD = D * D
+    return (out[:, :DD].reshape(n, D, D), out[:, DD:DD + D], out[:, DD + D:2 * DD + D].reshape(n, D, D),
+            out[:, 2 * DD + D:2 * DD + 2 * D], out[:, 2 * DD + 2 * D:].reshape(n, D, D))
+
+
+def sqrt_smoothing_operator(elem1, elem2):
+    """reference smoother.py:53-63 (batched): elems are tuples (g, E, D); elem1 is the LATER element"""
+    n, D = elem1[0].shape
+    e1, e2 = _pack(elem1), _pack(elem2)
+    nat.require_cuda(e1, e2)
+    out = torch.empty_like(e1)
+    nat.check(nat.LIB.pof_smooth_combine_f64(nat.stream_ptr(), n, D, nat.ptr(e1), nat.ptr(e2), nat.ptr(out)),
+              "pof_smooth_combine_f64")
+    DD = D * D
+    return out[:, :D], out[:, D:D + DD].reshape(n, D, D), out[:, D + DD:].reshape(n, D, D)

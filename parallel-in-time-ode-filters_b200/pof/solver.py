@@ -1,0 +1,80 @@
+"""Solver API (reference pof/solver.py:11-96): `solve` and `sequential_eks_solve`, keyword-only, same defaults,
+same `(MVNSqrt(mean (N,d), chol (N,d,D)), info_dict)` results -- as torch CUDA tensors."""
+import ctypes
+
+import torch
+
+from . import _native as nat
+from .convenience import get_initial_trajectory, set_up_solver
+from .convergence_criteria import crit_scalars
+from .parallel_filtsmooth import run_pass
+from .step import linearize_into
+from .utils import MVNSqrt
+
+
+def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, sequential=False, chunk_len=None):
+    """reference solver.py:11-73.  The IEKS loop keeps every array on the device; per iteration the host reads back
+    five scalars (nll, obj, sigma^2, #means not close, NaN state) to evaluate the reference's stopping rule."""
+    setup = set_up_solver(f=f, y0=y0, ts=ts, order=order)
+    x0, om, dev = setup["x0"], setup["om"], setup["_device"]
+    lin = om.f._pof_lin
+    d, q = lin["d"], order
+    states = get_initial_trajectory(setup, method=init)
+
+    means = states.mean.contiguous().clone()
+    N, D = means.shape
+    n = N - 1
+    chols = torch.empty((N, D, D), dtype=torch.float64, device=dev)
+    H = torch.empty((n, d, D), dtype=torch.float64, device=dev)
+    c = torch.empty((n, d), dtype=torch.float64, device=dev)
+    scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+    if sequential:
+        chunk_len = n
+    elif chunk_len is None:
+        chunk_len = nat.default_chunk_len(N, d, q, dev.index)
+
+    nll = obj = ssq = 0.0
+    nll_old = obj_old = 0.0
+    k = 0
+    while True:
+        if k >= 1:
+            converged = crit_scalars(obj, obj_old, nll, nll_old, n_bad)
+            if converged or not (k <= maxiters):
+                break
+        nll_old, obj_old = nll, obj
+        # body: ieks_step (solver.py:48-55); it always calibrates inside the loop (calibrate is not forwarded)
+        linearize_into(lin, means, H, c)
+        run_pass(x0, setup["_qL"], H, c, means, chols, d=d, q=q, calibrate=True, chunk_len=chunk_len, scalars=scalars)
+        sc = scalars.cpu()
+        nll, obj, ssq, n_bad = float(sc[nat.S_NLL]), float(sc[nat.S_OBJ]), float(sc[nat.S_SSQ]), float(
+            sc[nat.S_NOT_CLOSE])
+        k += 1
+
+    info_dict = {
+        "iterations": k, "nll": nll, "obj": obj, "sigma_squared": ssq, "calibrated": False,
+        "sigma_squared_proper": float(sc[nat.S_SSQ_PROPER]),
+    }
+    if calibrate:
+        info_dict["calibrated"] = True
+    # final calibration (the second one, solver.py:66-69) fused with the E0 projection (solver.py:71)
+    ymean = torch.empty((N, d), dtype=torch.float64, device=dev)
+    ychol = torch.empty((N, d, D), dtype=torch.float64, device=dev)
+    mult = scalars[nat.S_CSCALE:nat.S_CSCALE + 1] if calibrate else None
+    rc = nat.LIB.pof_project_f64(nat.stream_ptr(), N, d, q, setup["_scale0"], nat.ptr(mult), nat.ptr(means),
+                                 nat.ptr(chols), nat.ptr(ymean), nat.ptr(ychol))
+    nat.check(rc, "pof_project_f64")
+    return MVNSqrt(ymean, ychol), info_dict
+
+
+def sequential_eks_solve(*, f, y0, ts, order, return_full_states=False, calibrate=True):
+    """reference solver.py:76-96: one extended Kalman filter pass relinearised at the predicted mean, then RTS."""
+    from .sequential_filtsmooth.eks import eks_filtsmooth
+
+    setup = set_up_solver(f=f, y0=y0, ts=ts, order=order)
+    states, nll, obj, ssq = eks_filtsmooth(setup)
+    info_dict = {"nll": nll, "obj": obj, "sigma_squared": ssq, "calibrated": False}
+    if calibrate:
+        states = MVNSqrt(states.mean, float(ssq) ** 0.5 * states.chol)
+        info_dict["calibrated"] = True
+    M = setup["P"] if return_full_states else setup["E0"]
+    return MVNSqrt(states.mean @ M.T, torch.einsum("ij,njk->nik", M, states.chol)), info_dict

@@ -1,0 +1,58 @@
+"""IWP prior in preconditioned coordinates (reference pof/transitions.py).
+
+Host-side, one-off: the discretisation does not depend on dt (transitions.py:37-50), so F and QL are computed once
+and kept un-replicated; the kernels take the (q+1)x(q+1) block qL and know F's Pascal structure at compile time.
+"""
+from typing import NamedTuple
+
+import numpy as np
+import scipy.linalg
+import scipy.special
+import torch
+
+
+class TransitionModel(NamedTuple):
+    """Linear transition model in square-root form: x' | x ~ N(Fx, QL*QLt) (reference transitions.py:15-19)."""
+
+    F: torch.Tensor
+    QL: torch.Tensor
+
+
+class IWP(NamedTuple):
+    wiener_process_dimension: int
+    num_derivatives: int
+
+
+def preconditioned_discretize_1d(iwp: IWP):
+    """reference transitions.py:37-41"""
+    q = iwp.num_derivatives
+    A_1d = np.flip(scipy.linalg.pascal(q + 1, kind="lower", exact=False))
+    Q_1d = np.flip(scipy.linalg.hilbert(q + 1))
+    return np.ascontiguousarray(A_1d), np.linalg.cholesky(Q_1d)
+
+
+def preconditioned_discretize(iwp: IWP):
+    """reference transitions.py:44-50"""
+    A_1d, L_Q1d = preconditioned_discretize_1d(iwp)
+    Id = np.eye(iwp.wiener_process_dimension)
+    return np.kron(Id, A_1d), np.kron(Id, L_Q1d)
+
+
+def nordsieck_scalings(iwp: IWP, dt):
+    q = iwp.num_derivatives
+    powers = np.arange(q, -1, -1)
+    scales = scipy.special.factorial(powers)
+    powers = powers + 0.5
+    return (np.abs(dt) ** powers) / scales, (np.abs(dt) ** (-powers)) * scales
+
+
+def nordsieck_preconditioner(iwp: IWP, dt):
+    """reference transitions.py:53-68"""
+    sv, svi = nordsieck_scalings(iwp, dt)
+    Id = np.eye(iwp.wiener_process_dimension)
+    return np.kron(Id, np.diag(sv)), np.kron(Id, np.diag(svi))
+
+
+def projection_matrix(iwp: IWP, derivative_to_project_onto):
+    """reference transitions.py:80-88"""
+    return np.kron(np.eye(iwp.wiener_process_dimension), np.eye(1, iwp.num_derivatives + 1, derivative_to_project_onto))

@@ -1,0 +1,220 @@
+"""GPU parity tests: the CUDA pass (through the pof façade -> C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): outputs E0*mean rtol 1e-9 (relative to the component's max,
++1e-12); covariances reconstructed from the UNcalibrated Cholesky factors, relative-to-max 1e-7; nll/obj rtol 1e-9;
+sigma^2 (reference formula, QR-sign dependent) rtol 1e-2 and the sign-invariant variant rtol 1e-8.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ivps as oivps  # noqa: E402
+from oracle import pof_oracle as O  # noqa: E402
+
+
+def _cov(L):
+    return L @ np.swapaxes(L, -1, -2)
+
+
+def _pair(name, **kw):
+    import pof.ivp
+
+    return getattr(pof.ivp, name)(**kw), getattr(oivps, name)(**kw)
+
+
+CASES = [
+    ("fitzhughnagumo", {}, 100, 3, None),
+    ("fitzhughnagumo", {}, 100, 3, 7),
+    ("fitzhughnagumo", {}, 1024, 3, 5),
+    ("fitzhughnagumo", {}, 4096, 3, None),
+    ("logistic", {}, 64, 3, 4),
+    ("logistic", {}, 333, 1, 4),
+    ("logistic", {}, 200, 4, 6),
+    ("lotkavolterra", {}, 300, 2, 9),
+    ("vanderpol", {"stiffness_constant": 1.0}, 256, 3, 8),
+    ("rigid_body", {}, 256, 3, 8),
+    ("rober", {"tmax": 10.0}, 128, 2, 8),
+    ("seir", {}, 200, 2, 6),
+    ("threebody", {"tmax": 1.0}, 128, 3, 8),
+    ("henonheiles", {"tmax": 10.0}, 128, 2, 8),
+    ("henonheiles", {"tmax": 10.0}, 200, 5, 8),
+]
+
+
+@pytest.mark.parametrize("name,kw,N,q,L", CASES)
+def test_ieks_step_matches_oracle(native_lib, name, kw, N, q, L):
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], states)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    torch.cuda.synchronize()
+
+    osetup = O.set_up_solver(oivp, ts, q)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    np.testing.assert_allclose(dom.H.cpu().numpy(), odom.H, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(dom.b.cpu().numpy(), odom.b, rtol=1e-12, atol=1e-13)
+    oout, onll, oobj, ossq, ossqp = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom)
+
+    E0 = osetup["E0"]
+    m, Lc = out.mean.cpu().numpy(), out.chol.cpu().numpy()
+    y, yo = m @ E0.T, oout.mean @ E0.T
+    scale = np.abs(yo).max(axis=0)
+    assert (np.abs(y - yo) <= 1e-9 * scale + 1e-12).all(), np.abs(y - yo).max()
+    C, Co = _cov(Lc), _cov(oout.chol)
+    Cy, Cyo = E0 @ C @ E0.T, E0 @ Co @ E0.T
+    assert np.abs(Cy - Cyo).max() <= 1e-7 * np.abs(Cyo).max()
+    assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
+    assert abs(float(nll) - onll) <= 1e-9 * abs(onll) + 1e-9
+    assert abs(float(obj) - oobj) <= 1e-9 * abs(oobj)
+    assert abs(float(ssq) - ossq) <= 1e-2 * abs(ossq)
+    # full internal state, small N only
+    if N <= 512:
+        cs = np.abs(oout.mean).max(axis=0)
+        assert (np.abs(m - oout.mean) <= 1e-9 * cs + 1e-12).all()
+    # smoothed chol is lower triangular like the reference's
+    assert np.abs(np.triu(Lc, 1)).max() == 0.0
+
+
+def _rand_filter_elems(rng, n, D, d):
+    A = rng.standard_normal((n, D, D))
+    b = rng.standard_normal((n, D))
+    U = np.tril(rng.standard_normal((n, D, D)))
+    eta = rng.standard_normal((n, D))
+    Z = np.tril(rng.standard_normal((n, D, D)))
+    # rank-deficient / zero cases like the leaves
+    U[: n // 4, :, D - d:] = 0.0
+    Z[: n // 4, :, d:] = 0.0
+    U[n // 4: n // 4 + 3] = 0.0
+    Z[n // 4 + 3: n // 4 + 6] = 0.0
+    return A, b, U, eta, Z
+
+
+@pytest.mark.parametrize("D,d", [(8, 2), (4, 1), (12, 3), (5, 1), (24, 4)])
+def test_filter_combine_matches_oracle(native_lib, D, d):
+    from pof.parallel_filtsmooth import sqrt_filtering_operator
+
+    rng = np.random.default_rng(0)
+    n = 257
+    e1 = _rand_filter_elems(rng, n, D, d)
+    e2 = _rand_filter_elems(rng, n, D, d)
+    t = lambda e: tuple(torch.as_tensor(x, device="cuda") for x in e)
+    out = [x.cpu().numpy() for x in sqrt_filtering_operator(t(e1), t(e2))]
+    ref = O.sqrt_filtering_operator(e1, e2)
+    for i in (0, 1, 3):
+        np.testing.assert_allclose(out[i], ref[i], rtol=1e-9, atol=1e-9 * np.abs(ref[i]).max())
+    for i in (2, 4):
+        Cg, Cr = _cov(out[i]), _cov(ref[i])
+        np.testing.assert_allclose(Cg, Cr, rtol=0, atol=1e-10 * np.abs(Cr).max())
+
+
+def test_filter_combine_associative(native_lib):
+    from pof.parallel_filtsmooth import sqrt_filtering_operator as op
+
+    rng = np.random.default_rng(1)
+    n, D = 64, 8
+    t = lambda e: tuple(torch.as_tensor(x, device="cuda") for x in e)
+    a, b, c = (t(_rand_filter_elems(rng, n, D, 2)) for _ in range(3))
+    l = [x.cpu().numpy() for x in op(op(a, b), c)]
+    r = [x.cpu().numpy() for x in op(a, op(b, c))]
+    for i in (0, 1, 3):
+        np.testing.assert_allclose(l[i], r[i], rtol=0, atol=1e-9 * max(1.0, np.abs(r[i]).max()))
+    for i in (2, 4):
+        np.testing.assert_allclose(_cov(l[i]), _cov(r[i]), rtol=0, atol=1e-9 * np.abs(_cov(r[i])).max())
+
+
+@pytest.mark.parametrize("D", [8, 4, 12])
+def test_smooth_combine_matches_oracle(native_lib, D):
+    from pof.parallel_filtsmooth import sqrt_smoothing_operator
+
+    rng = np.random.default_rng(2)
+    n = 129
+    mk = lambda: (rng.standard_normal((n, D)), rng.standard_normal((n, D, D)), np.tril(rng.standard_normal((n, D, D))))
+    e1, e2 = mk(), mk()
+    t = lambda e: tuple(torch.as_tensor(x, device="cuda") for x in e)
+    out = [x.cpu().numpy() for x in sqrt_smoothing_operator(t(e1), t(e2))]
+    ref = O.sqrt_smoothing_operator(e1, e2)
+    np.testing.assert_allclose(out[0], ref[0], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(out[1], ref[1], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(_cov(out[2]), _cov(ref[2]), rtol=0, atol=1e-11 * np.abs(_cov(ref[2])).max())
+
+
+SOLVE_CASES = [
+    ("logistic", {}, 16, 3, 9), ("logistic", {}, 64, 3, 12), ("logistic", {}, 32, 2, 10),
+    ("rigid_body", {}, 128, 3, 10), ("vanderpol", {"stiffness_constant": 1.0}, 128, 3, 10),
+    ("fitzhughnagumo", {}, 512, 3, 64), ("henonheiles", {"tmax": 10.0}, 64, 2, 13),
+]
+
+
+@pytest.mark.parametrize("name,kw,N,q,iters", SOLVE_CASES)
+def test_solve_reproduces_published_iterations(native_lib, name, kw, N, q, iters):
+    """Known answers from the reference's published CSVs (tests/golden/published_ieks3.json)."""
+    from pof.solver import solve
+
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    ys, info = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant", maxiters=1000)
+    assert info["iterations"] == iters
+    oys, oinfo = O.solve(oivp, ts, q, init="constant", maxiters=1000)
+    y, yo = ys.mean.cpu().numpy(), oys.mean
+    assert (np.abs(y - yo) <= 1e-9 * np.abs(yo).max(axis=0) + 1e-12).all()
+    # calibrated output covariance: divide out each side's own sigma^2
+    s, so = info["sigma_squared"], oinfo["sigma_squared"]
+    C = _cov(ys.chol.cpu().numpy()) / s**2
+    Co = _cov(oys.chol) / so**2
+    assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
+    assert abs(s - so) <= 1e-2 * abs(so)
+
+
+def test_readme_example(native_lib):
+    """README configuration (BASELINE config 1): FHN, order 3, ts = linspace(0, 100, 100), init='constant'."""
+    import pof.ivp
+    from pof.solver import solve
+
+    ivp = pof.ivp.fitzhughnagumo()
+    ts = torch.linspace(0, 100, 100, dtype=torch.float64)
+    ys, info = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant")
+    assert ys.mean.shape == (100, 2) and ys.chol.shape == (100, 2, 8)
+    assert info["iterations"] == 48
+    oys, oinfo = O.solve(oivps.fitzhughnagumo(), np.linspace(0, 100, 100), 3, init="constant")
+    assert np.abs(ys.mean.cpu().numpy() - oys.mean).max() <= 1e-9 * np.abs(oys.mean).max()
+
+
+def test_user_f_autodiff_path_matches_builtin(native_lib):
+    """A user-supplied f (no built-in tag) goes through torch.func jacobians and must give the same pass."""
+    import pof.ivp
+    from pof.solver import solve
+
+    ivp = pof.ivp.lotkavolterra()
+
+    def f(t, Y):
+        return torch.stack([1.5 * Y[0] - Y[0] * Y[1], -3.0 * Y[1] + Y[0] * Y[1]])
+
+    ts = np.linspace(0, 7, 200)
+    a, ia = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=2, init="constant")
+    b, ib = solve(f=f, y0=ivp.y0, ts=ts, order=2, init="constant")
+    assert ia["iterations"] == ib["iterations"]
+    np.testing.assert_allclose(a.mean.cpu().numpy(), b.mean.cpu().numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_sequential_flag_matches_parallel(native_lib):
+    import pof.ivp
+    from pof.solver import solve
+
+    ivp = pof.ivp.logistic()
+    ts = np.arange(0, 10.5, 0.5)
+    for order in (1, 3):
+        for init in ("constant", "prior"):
+            a, ia = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=order, init=init)
+            b, ib = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=order, init=init, sequential=True)
+            assert a.mean.shape[0] == len(ts)
+            assert ia["iterations"] == ib["iterations"]
+            np.testing.assert_allclose(a.mean.cpu().numpy(), b.mean.cpu().numpy(), rtol=1e-9, atol=1e-11)
