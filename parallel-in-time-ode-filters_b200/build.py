@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpof_b200.so")
-SOURCES = ["pof_api.cu", "pof_leaf_d1.cu", "pof_leaf_d2.cu", "pof_leaf_d3.cu", "pof_leaf_d4.cu"]
+SOURCES = [
+    "pof_api.cu", "pof_leaf_d1.cu", "pof_leaf_d2.cu", "pof_leaf_d3.cu", "pof_leaf_d4.cu",
+    "pof_lane_d1.cu", "pof_lane_d2.cu", "pof_lane_d3.cu", "pof_lane_d4.cu",
+]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

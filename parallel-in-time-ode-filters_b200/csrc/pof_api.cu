@@ -4,6 +4,7 @@
 // and the final calibration + projection.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/pof_b200.h"
 #include "pof_coop.cuh"
@@ -12,7 +13,8 @@
 
 namespace pof {
 
-const LeafLaunch* leaf_launch(int d, int q) {
+// thread-per-chunk reference kernels (pof_leaf.cuh)
+static const LeafLaunch* thread_launch(int d, int q) {
   switch (d) {
     case 1: return leaf_launch_d1(q);
     case 2: return leaf_launch_d2(q);
@@ -20,6 +22,27 @@ const LeafLaunch* leaf_launch(int d, int q) {
     case 4: return leaf_launch_d4(q);
     default: return nullptr;
   }
+}
+// lane-cooperative performance kernels (pof_lane.cuh); D <= 32
+static const LeafLaunch* lane_launch(int d, int q) {
+  if (d * (q + 1) > 32) return nullptr;
+  switch (d) {
+    case 1: return lane_launch_d1(q);
+    case 2: return lane_launch_d2(q);
+    case 3: return lane_launch_d3(q);
+    case 4: return lane_launch_d4(q);
+    default: return nullptr;
+  }
+}
+// POF_B200_LEAF_IMPL=thread selects the reference kernels (debugging / cross-checks); default: lane kernels
+const LeafLaunch* leaf_launch(int d, int q) {
+  const char* e = getenv("POF_B200_LEAF_IMPL");
+  const bool want_thread = e && e[0] == 't';
+  if (!want_thread) {
+    const LeafLaunch* l = lane_launch(d, q);
+    if (l) return l;
+  }
+  return thread_launch(d, q);
 }
 
 constexpr int TREE_WARPS = 4;  // warps (= element pairs) per CTA in the tree kernels
@@ -447,11 +470,11 @@ extern "C" {
 int pof_supported(int d, int q) { return leaf_launch(d, q) != nullptr ? 1 : 0; }
 
 int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count) {
-  (void)d;
-  (void)q;
   if (sm_count <= 0) sm_count = 148;
+  const LeafLaunch* ll = leaf_launch(d, q);
+  const int cpw = ll ? ll->chunks_per_warp : 32;
   const int64_t n = N - 1;
-  const int64_t target = (int64_t)sm_count * 256;  // one chunk per thread, ~8 warps per SM
+  const int64_t target = (int64_t)sm_count * 8 * cpw;  // ~8 resident warps per SM, `cpw` chunks per warp
   int64_t L = (n + target - 1) / target;
   if (L < 4) L = 4;
   return L;

@@ -1,0 +1,2 @@
+#include "pof_lane_kernels.cuh"
+POF_DEFINE_LANE_D(2)

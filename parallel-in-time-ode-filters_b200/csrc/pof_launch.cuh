@@ -24,6 +24,7 @@ struct LeafLaunch {
                       double* part, double* fmeans, double* fchols);
   cudaError_t (*smooth)(cudaStream_t, const LeafArgs&, const double* sin, const double* kern, int emit_t0,
                         const double* cscale, double* means, double* chols, double* part2);
+  int chunks_per_warp;  // 32 for the thread-per-chunk kernels, 32/G for the lane-cooperative ones
 };
 
 // returns nullptr if (d, q) is not compiled in
@@ -32,5 +33,10 @@ const LeafLaunch* leaf_launch_d1(int q);
 const LeafLaunch* leaf_launch_d2(int q);
 const LeafLaunch* leaf_launch_d3(int q);
 const LeafLaunch* leaf_launch_d4(int q);
+// lane-cooperative (performance) path
+const LeafLaunch* lane_launch_d1(int q);
+const LeafLaunch* lane_launch_d2(int q);
+const LeafLaunch* lane_launch_d3(int q);
+const LeafLaunch* lane_launch_d4(int q);
 
 }  // namespace pof

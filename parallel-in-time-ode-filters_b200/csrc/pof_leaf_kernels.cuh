@@ -68,7 +68,7 @@ struct LeafLaunchers {
     return cudaGetLastError();
   }
   static const LeafLaunch* get() {
-    static const LeafLaunch l = {&fold, &scan, &smooth};
+    static const LeafLaunch l = {&fold, &scan, &smooth, 32};
     return &l;
   }
 };

@@ -43,8 +43,15 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["lane", "thread"])
+def leaf_impl(request, monkeypatch):
+    """Both leaf-kernel families: the lane-cooperative performance kernels and the thread-per-chunk reference ones."""
+    monkeypatch.setenv("POF_B200_LEAF_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name,kw,N,q,L", CASES)
-def test_ieks_step_matches_oracle(native_lib, name, kw, N, q, L):
+def test_ieks_step_matches_oracle(native_lib, leaf_impl, name, kw, N, q, L):
     from pof.convenience import get_initial_trajectory, set_up_solver
     from pof.parallel_filtsmooth import linear_filtsmooth
     from pof.step import linearize_at_previous_states
@@ -73,8 +80,13 @@ def test_ieks_step_matches_oracle(native_lib, name, kw, N, q, L):
     Cy, Cyo = E0 @ C @ E0.T, E0 @ Co @ E0.T
     assert np.abs(Cy - Cyo).max() <= 1e-7 * np.abs(Cyo).max()
     assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
-    assert abs(float(nll) - onll) <= 1e-9 * abs(onll) + 1e-9
-    assert abs(float(obj) - oobj) <= 1e-9 * abs(oobj)
+    # nll / obj: rtol 1e-9, widened to the reference's own schedule dependence where that is larger (two valid
+    # association orders of the reference formulas disagree by 3e-9 on nll for logistic order 4, N=200)
+    _, nll2, obj2, _, _ = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom, scan=O.sequential_scan)
+    tol_nll = max(1e-9 * abs(onll) + 1e-9, 10 * abs(nll2 - onll))
+    tol_obj = max(1e-9 * abs(oobj), 10 * abs(obj2 - oobj))
+    assert abs(float(nll) - onll) <= tol_nll
+    assert abs(float(obj) - oobj) <= tol_obj
     assert abs(float(ssq) - ossq) <= 1e-2 * abs(ossq)
     # full internal state, small N only
     if N <= 512:
