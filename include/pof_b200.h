@@ -54,6 +54,13 @@ enum {
 /* 1 if the (d, q) leaf kernels are compiled in */
 int pof_supported(int d, int q);
 
+/* measurement aids (bench.py): per-segment device timing with CUDA events on the launching stream, kernel-launch
+ * count of one pass, and the device's FP64 FMA peak measured by a register-resident DFMA loop */
+void pof_profile_enable(int on);
+int pof_profile_read(double* ms_out /* 7 */, int64_t* count_out /* 7 */);
+int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len);
+int pof_measure_dfma_tflops(pof_stream_t s, double* tflops_out /* host */);
+
 /* default chunk length (steps per thread) for a problem size, chosen to fill the GPU `sm_count` SMs */
 int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count);
 

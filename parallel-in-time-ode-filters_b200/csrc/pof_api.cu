@@ -45,14 +45,14 @@ const LeafLaunch* leaf_launch(int d, int q) {
   return thread_launch(d, q);
 }
 
-constexpr int TREE_WARPS = 4;  // warps (= element pairs) per CTA in the tree kernels
+constexpr int TREE_WARPS = 4;  // max warps (= element pairs) per CTA in the tree kernels; fewer when D is large
 
 // ------------------------------------------------------------------------------------------------ tree sweeps
 // up:   parent[i] = op(child[2i], child[2i+1])           (copy if the second child is missing)
 __global__ void __launch_bounds__(TREE_WARPS * 32)
     k_filter_up(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent, long nparent) {
   extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= nparent) return;
   Warp w;
   const int FE = filter_elem_size(D);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32)
     k_filter_down(int D, const double* __restrict__ pin, long nparent, const double* __restrict__ cagg, long nchild,
                   double* __restrict__ cin) {
   extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= nparent) return;
   Warp w;
   const int FE = filter_elem_size(D), ST = state_size(D);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32)
 __global__ void __launch_bounds__(TREE_WARPS * 32)
     k_smooth_up(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent, long nparent) {
   extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= nparent) return;
   Warp w;
   const int SE = smooth_elem_size(D);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32)
     k_smooth_down(int D, const double* __restrict__ pin, long nparent, const double* __restrict__ cagg, long nchild,
                   double* __restrict__ cin) {
   extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= nparent) return;
   Warp w;
   const int SE = smooth_elem_size(D), ST = state_size(D);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32)
     k_filter_combine_batched(int D, long n, const double* __restrict__ e1, const double* __restrict__ e2,
                              double* __restrict__ out) {
   extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= n) return;
   Warp w;
   const int FE = filter_elem_size(D);
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32)
     k_smooth_combine_batched(int D, long n, const double* __restrict__ e1, const double* __restrict__ e2,
                              double* __restrict__ out) {
   extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= n) return;
   Warp w;
   const int SE = smooth_elem_size(D);
@@ -341,6 +341,22 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// 16 independent FMA chains per thread: saturates the FP64 pipe
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double* __restrict__ sink) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double m = 1.0 - 1e-12, c = 1e-13;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t += a[i];
+  if (t == 123.456) sink[threadIdx.x] = t;
+}
+
 // ------------------------------------------------------------------------------------------------ workspace
 struct WsLayout {
   TreeLevels tl;
@@ -377,7 +393,13 @@ struct WsLayout {
   }
 };
 
-static inline int tree_smem_bytes(int D) { return TREE_WARPS * coop_ws_doubles(D) * (int)sizeof(double); }
+// warps per CTA such that the per-warp shared-memory workspaces fit in 227 KB (0 if even one does not fit)
+static inline int tree_warps(int D) {
+  const long per = (long)coop_ws_doubles(D) * (long)sizeof(double);
+  long w = (227L * 1024L) / per;
+  return (int)(w > TREE_WARPS ? TREE_WARPS : w);
+}
+static inline int tree_smem_bytes(int D) { return tree_warps(D) * coop_ws_doubles(D) * (int)sizeof(double); }
 
 template <class K>
 static cudaError_t set_smem(K kernel, int bytes) {
@@ -385,10 +407,44 @@ static cudaError_t set_smem(K kernel, int bytes) {
   return cudaSuccess;
 }
 
+// ---- optional per-segment device timing (used by bench.py for the roofline numbers): CUDA events recorded on the
+// launching stream around each segment of a pass.  Off by default; global, not thread-safe (a measurement aid).
+enum { SEG_FOLD = 0, SEG_FUP, SEG_FDOWN, SEG_SCAN, SEG_SUP, SEG_SDOWN, SEG_SMOOTH, SEG_COUNT };
+struct Prof {
+  bool on = false;
+  static constexpr int MAXP = 4096;
+  cudaEvent_t ev[MAXP][2];
+  int seg[MAXP];
+  int created = 0, used = 0;
+  double acc[SEG_COUNT] = {0};
+  long cnt[SEG_COUNT] = {0};
+} g_prof;
+struct ProfScope {
+  int idx = -1;
+  cudaStream_t s;
+  ProfScope(int seg, cudaStream_t st) : s(st) {
+    if (!g_prof.on || g_prof.used >= Prof::MAXP) return;
+    idx = g_prof.used++;
+    if (idx >= g_prof.created) {
+      cudaEventCreate(&g_prof.ev[idx][0]);
+      cudaEventCreate(&g_prof.ev[idx][1]);
+      g_prof.created = idx + 1;
+    }
+    g_prof.seg[idx] = seg;
+    cudaEventRecord(g_prof.ev[idx][0], s);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof.ev[idx][1], s);
+  }
+};
+
 #define POF_CK(x)                     \
   do {                                \
     cudaError_t e__ = (x);            \
-    if (e__ != cudaSuccess) return (int)e__; \
+    if (e__ != cudaSuccess) {         \
+      (void)cudaGetLastError();       \
+      return (int)e__;                \
+    }                                 \
   } while (0)
 
 static int make_args(long n, int d, int q, const double* qL_host, const double* H, const double* c,
@@ -407,12 +463,18 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
 // stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
 static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws) {
   double* fagg = ws + wl.o_fagg;
-  POF_CK(ll->fold(s, a, fagg));
+  {
+    ProfScope ps(SEG_FOLD, s);
+    POF_CK(ll->fold(s, a, fagg));
+  }
+  ProfScope ps(SEG_FUP, s);
   const int smem = tree_smem_bytes(wl.D);
+  const int tw = tree_warps(wl.D);
+  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_up, smem));
   for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
     const long np = wl.tl.sz[l + 1];
-    k_filter_up<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+    k_filter_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
         wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np);
   }
   return (int)cudaGetLastError();
@@ -424,19 +486,28 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   double* fin = ws + wl.o_fin;
   double* sagg = ws + wl.o_sagg;
   const int smem = tree_smem_bytes(wl.D);
+  const int tw = tree_warps(wl.D);
+  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_down, smem));
   POF_CK(set_smem(k_smooth_up, smem));
+  {
+  ProfScope ps(SEG_FDOWN, s);
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     const long np = wl.tl.sz[l];
-    k_filter_down<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+    k_filter_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
         wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
         fin + wl.tl.off[l - 1] * wl.ST);
   }
+  }
   POF_CK(cudaGetLastError());
-  POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+  {
+    ProfScope ps(SEG_SCAN, s);
+    POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+  }
+  ProfScope ps(SEG_SUP, s);
   for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
     const long np = wl.tl.sz[l + 1];
-    k_smooth_up<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+    k_smooth_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
         wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
   }
   k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
@@ -448,15 +519,23 @@ static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   double* sagg = ws + wl.o_sagg;
   double* sin_ = ws + wl.o_sin;
   const int smem = tree_smem_bytes(wl.D);
+  const int tw = tree_warps(wl.D);
+  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_smooth_down, smem));
+  {
+  ProfScope ps(SEG_SDOWN, s);
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     const long np = wl.tl.sz[l];
-    k_smooth_down<<<(unsigned)((np + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem, s>>>(
+    k_smooth_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
         wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
         sin_ + wl.tl.off[l - 1] * wl.ST);
   }
+  }
   POF_CK(cudaGetLastError());
-  POF_CK(ll->smooth(s, a, sin_, ws + wl.o_kern, emit_t0, cscale, means, chols, ws + wl.o_part2));
+  {
+    ProfScope ps(SEG_SMOOTH, s);
+    POF_CK(ll->smooth(s, a, sin_, ws + wl.o_kern, emit_t0, cscale, means, chols, ws + wl.o_part2));
+  }
   k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part2, wl.CS, 2, ws + wl.o_sums + 8);
   return (int)cudaGetLastError();
 }
@@ -468,6 +547,71 @@ using namespace pof;
 extern "C" {
 
 int pof_supported(int d, int q) { return leaf_launch(d, q) != nullptr ? 1 : 0; }
+
+void pof_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  for (int i = 0; i < SEG_COUNT; ++i) {
+    g_prof.acc[i] = 0.0;
+    g_prof.cnt[i] = 0;
+  }
+}
+// synchronises the device; ms_out[7] = accumulated milliseconds of [fold, filter_up, filter_down, scan, smooth_up,
+// smooth_down, smooth], count_out[7] = number of timed segments of each kind
+int pof_profile_read(double* ms_out, int64_t* count_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  for (int i = 0; i < g_prof.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]) == cudaSuccess) {
+      g_prof.acc[g_prof.seg[i]] += ms;
+      g_prof.cnt[g_prof.seg[i]] += 1;
+    }
+  }
+  g_prof.used = 0;
+  for (int i = 0; i < SEG_COUNT; ++i) {
+    ms_out[i] = g_prof.acc[i];
+    count_out[i] = g_prof.cnt[i];
+  }
+  return 0;
+}
+// kernels launched by one pof_linear_filtsmooth_f64 call
+int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
+  WsLayout wl;
+  wl.build(N - 1, d, q, chunk_len);
+  return 3 /*leaf*/ + 4 * (int64_t)(wl.tl.nlev - 1) /*tree sweeps*/ + 1 /*pack*/ + 2 /*reduce*/ + 2 /*finalize*/;
+}
+
+// FP64 FMA throughput of this device (TFLOP/s), measured with a register-resident DFMA loop: the roofline
+// denominator for the FP64-bound kernels (MEASURED_PEAKS.json holds no FP64 number)
+int pof_measure_dfma_tflops(pof_stream_t s_, double* tflops_out) {
+  cudaStream_t s = (cudaStream_t)s_;
+  int dev = 0, sms = 0;
+  POF_CK(cudaGetDevice(&dev));
+  POF_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  POF_CK(cudaMalloc(&sink, sizeof(double) * 1024));
+  const int iters = 1 << 14, blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  POF_CK(cudaEventCreate(&e0));
+  POF_CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    POF_CK(cudaEventRecord(e0, s));
+    k_dfma_peak<<<blocks, threads, 0, s>>>(iters, sink);
+    POF_CK(cudaEventRecord(e1, s));
+    POF_CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    POF_CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
 
 int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count) {
   if (sm_count <= 0) sm_count = 148;
@@ -489,17 +633,19 @@ size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
 int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
   if (n <= 0) return 0;
   const int smem = tree_smem_bytes(D);
+  const int tw = tree_warps(D);
+  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_combine_batched, smem));
-  k_filter_combine_batched<<<(unsigned)((n + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem,
-                             (cudaStream_t)s>>>(D, n, e1, e2, out);
+  k_filter_combine_batched<<<(unsigned)((n + tw - 1) / tw), tw * 32, smem, (cudaStream_t)s>>>(D, n, e1, e2, out);
   return (int)cudaGetLastError();
 }
 int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
   if (n <= 0) return 0;
   const int smem = tree_smem_bytes(D);
+  const int tw = tree_warps(D);
+  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_smooth_combine_batched, smem));
-  k_smooth_combine_batched<<<(unsigned)((n + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, smem,
-                             (cudaStream_t)s>>>(D, n, e1, e2, out);
+  k_smooth_combine_batched<<<(unsigned)((n + tw - 1) / tw), tw * 32, smem, (cudaStream_t)s>>>(D, n, e1, e2, out);
   return (int)cudaGetLastError();
 }
 

@@ -32,7 +32,8 @@ struct Lane {
   // of a warp start 2 doubles (mod 16) apart: conflict-free broadcast reads across groups)
   static constexpr int LDM = D + 1;
   static constexpr int BC = ((D + 2 + 1) / 2) * 2;
-  static constexpr int RAW = 2 * BC + 2 * D * LDM + D;
+  static constexpr int VEC = ((D + 1) / 2) * 2;
+  static constexpr int RAW = 2 * BC + 2 * D * LDM + 2 * VEC;
   static constexpr int SM_GROUP = RAW + ((2 - (RAW % 16)) + 16) % 16;
 
   struct Ctx {
@@ -42,7 +43,7 @@ struct Lane {
     double* bc;     // broadcast slots
     double* mat;    // row-exchange matrices
     double* vec;    // gather vector
-    int flip;
+    int flip, vflip;
     double cf[Q1];  // Pascal coefficients of this lane's row of F: (F x)_r = sum_i cf[i] x[blk0 + i]
     double tq[D];   // this lane's row of QL
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
@@ -56,6 +57,7 @@ struct Lane {
     c.mat = sm_group + 2 * BC;
     c.vec = c.mat + 2 * D * LDM;
     c.flip = 0;
+    c.vflip = 0;
     const int rr = (c.r < D) ? c.r : 0;
     c.rb = rr % Q1;
     c.blk0 = rr - c.rb;
@@ -81,23 +83,30 @@ struct Lane {
   // lane `src` publishes n doubles, every lane of the group reads them
   template <int n>
   static __device__ __forceinline__ void bcast(Ctx& c, const double (&x)[n], int src, double (&out)[n]) {
-    double* slot = c.bc + c.flip * BC;
+    double2* slot = reinterpret_cast<double2*>(c.bc + c.flip * BC);
     c.flip ^= 1;
     if (c.r == src) {
 #pragma unroll
-      for (int j = 0; j < n; ++j) slot[j] = x[j];
+      for (int j = 0; j + 1 < n; j += 2) slot[j / 2] = make_double2(x[j], x[j + 1]);
+      if (n % 2) slot[n / 2] = make_double2(x[n - 1], 0.0);
     }
     c.sync();
 #pragma unroll
-    for (int j = 0; j < n; ++j) out[j] = slot[j];
+    for (int j = 0; j + 1 < n; j += 2) {
+      const double2 v = slot[j / 2];
+      out[j] = v.x;
+      out[j + 1] = v.y;
+    }
+    if (n % 2) out[n - 1] = slot[n / 2].x;
   }
   // out[j] = x of lane j
   static __device__ __forceinline__ void allgather(Ctx& c, double x, double (&out)[D]) {
-    c.sync();
-    if (c.r < D) c.vec[c.r] = x;
+    double* v = c.vec + c.vflip * VEC;
+    c.vflip ^= 1;
+    if (c.r < D) v[c.r] = x;
     c.sync();
 #pragma unroll
-    for (int j = 0; j < D; ++j) out[j] = c.vec[j];
+    for (int j = 0; j < D; ++j) out[j] = v[j];
   }
   // publish this lane's row into exchange matrix `which` (row-major, leading dimension LDM)
   static __device__ __forceinline__ double* publish(Ctx& c, int which, const double (&x)[D]) {
@@ -146,6 +155,25 @@ struct Lane {
     }
   }
 
+  // reciprocal and reciprocal square root: hardware seed (2^-22) + two Newton steps (~1 ulp), branch free
+  static __device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+  }
+  static __device__ __forceinline__ double fast_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-hx * r, r, 0.5);
+    return fma(r, e, r);
+  }
+
   // Householder parameters for the row (alpha, x[0..n-1]):  H = I - tp * v v^T,  v = (s, x),  H (alpha,x)^T = (beta,0)
   struct HH {
     double s, tp, beta;
@@ -159,12 +187,13 @@ struct Lane {
     HH h;
     h.nz = sigma > 0.0;
     const double nrm2 = fma(alpha, alpha, sigma);
-    const double nrm = sqrt(nrm2);
+    const double rn = fast_rsqrt(nrm2);  // 1 / norm
+    const double nrm = nrm2 * rn;
     const double beta = (alpha >= 0.0) ? -nrm : nrm;
     const double s = alpha - beta;
     h.beta = h.nz ? beta : alpha;
     h.s = h.nz ? s : 0.0;
-    h.tp = h.nz ? 1.0 / (nrm * fabs(s)) : 0.0;
+    h.tp = h.nz ? rn * fast_rcp(fabs(s)) : 0.0;  // 1 / (norm |s|)
     return h;
   }
 
@@ -183,12 +212,11 @@ struct Lane {
       double w = h.s * t[i];
 #pragma unroll
       for (int j = 0; j < K; ++j) w = fma(c[j], piv[1 + j], w);
-      w *= h.tp;
-      const bool below = cx.r > i;
-      const bool own = cx.r == i;
-      t[i] = own ? h.beta : (below ? fma(-w, h.s, t[i]) : t[i]);
+      // rows above the pivot are untouched (w = 0); the pivot row itself maps to (beta, ~0): its C entries are dead
+      w = (cx.r >= i) ? w * h.tp : 0.0;
+      t[i] = (cx.r == i) ? h.beta : fma(-w, h.s, t[i]);
 #pragma unroll
-      for (int j = 0; j < K; ++j) c[j] = own ? (h.nz ? 0.0 : c[j]) : (below ? fma(-w, piv[1 + j], c[j]) : c[j]);
+      for (int j = 0; j < K; ++j) c[j] = fma(-w, piv[1 + j], c[j]);
       if (PASS) {
         double u = h.s * pt[i];
 #pragma unroll
@@ -214,12 +242,11 @@ struct Lane {
       double w = h.s * x[I];
 #pragma unroll
       for (int j = I + 1; j < D; ++j) w = fma(x[j], piv[j - I], w);
-      w *= h.tp;
-      const bool below = cx.r > I;
-      const bool own = cx.r == I;
-      x[I] = own ? h.beta : (below ? fma(-w, h.s, x[I]) : x[I]);
+      // entries right of the diagonal in the pivot row become ~0 (roundoff); only the lower triangle is ever read
+      w = (cx.r >= I) ? w * h.tp : 0.0;
+      x[I] = (cx.r == I) ? h.beta : fma(-w, h.s, x[I]);
 #pragma unroll
-      for (int j = I + 1; j < D; ++j) x[j] = own ? (h.nz ? 0.0 : x[j]) : (below ? fma(-w, piv[j - I], x[j]) : x[j]);
+      for (int j = I + 1; j < D; ++j) x[j] = fma(-w, piv[j - I], x[j]);
       tria_step<I + 1>(cx, x);
     }
   }
@@ -294,7 +321,7 @@ struct Lane {
       double s = y[a];
 #pragma unroll
       for (int j = 0; j < a; ++j) s = fma(-SL[a][j], z[j], s);
-      z[a] = s / SL[a][a];
+      z[a] = s * fast_rcp(SL[a][a]);
     }
   }
   static __device__ __forceinline__ void load_Hc(const double* __restrict__ H, const double* __restrict__ c, long k,
@@ -437,7 +464,7 @@ struct Lane {
       {
         const double* M = publish(cx, 1, t);
         double inv[D];
-        allgather(cx, 1.0 / pick(t, rc), inv);
+        allgather(cx, fast_rcp(pick(t, rc)), inv);
 #pragma unroll
         for (int j = D - 1; j >= 0; --j) {
           double s = e[j];
@@ -459,11 +486,8 @@ struct Lane {
       if (r < D) {
         double* kp = kern + k * NE;
         kp[r] = g;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          kp[D + r * D + j] = e[j];
-          kp[D + D * D + r * D + j] = uf[j];
-        }
+        store_row(kp + D + r * D, e);
+        store_row(kp + D + D * D + r * D, uf);
       }
       // ---- compose the chunk's smoothing element: acc = acc o kernel_k
       if (k == k0) {
@@ -528,7 +552,7 @@ struct Lane {
         double s = y[a];
 #pragma unroll
         for (int e2 = a + 1; e2 < d; ++e2) s = fma(-SL[e2][a], wv[e2], s);
-        wv[a] = s / SL[a][a];
+        wv[a] = s * fast_rcp(SL[a][a]);
         ww = fma(wv[a], wv[a], ww);
       }
       s1 += ww;
@@ -565,10 +589,46 @@ struct Lane {
     const bool close = fabs(old - m) <= (1e-8 + 1e-13 * fabs(m));
     means[t * D + r] = m;
     if (chols) {
+      double row[D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) chols[(t * D + r) * D + j] = (j <= r) ? cscale * l[j] : 0.0;
+      for (int j = 0; j < D; ++j) row[j] = (j <= r) ? cscale * l[j] : 0.0;
+      store_row(chols + (t * D + r) * D, row);
     }
     return close ? 0.0 : 1.0;
+  }
+  // one matrix row to global memory (128-bit stores when the row length is even)
+  static __device__ __forceinline__ void store_row(double* __restrict__ p, const double (&x)[D]) {
+    if constexpr (D % 2 == 0) {
+      double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+      for (int j = 0; j < D / 2; ++j) p2[j] = make_double2(x[2 * j], x[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) p[j] = x[j];
+    }
+  }
+  static __device__ __forceinline__ void load_kernel(int r, const double* __restrict__ kp, double& g, double (&e)[D],
+                                                     double (&dk)[D]) {
+    const int rc = (r < D) ? r : 0;
+    g = kp[rc];
+    const double2* pe = reinterpret_cast<const double2*>(kp + D + rc * D);
+    const double2* pd = reinterpret_cast<const double2*>(kp + D + D * D + rc * D);
+    if constexpr (D % 2 == 0) {
+#pragma unroll
+      for (int j = 0; j < D / 2; ++j) {
+        const double2 a = pe[j], b = pd[j];
+        e[2 * j] = a.x;
+        e[2 * j + 1] = a.y;
+        dk[2 * j] = b.x;
+        dk[2 * j + 1] = b.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        e[j] = kp[D + rc * D + j];
+        dk[j] = kp[D + D * D + rc * D + j];
+      }
+    }
   }
   static __device__ __forceinline__ void smooth(Ctx& cx, long k0, long k1, bool last, bool emit_t0,
                                                 const double* qLinvdiag, const double* qL,
@@ -587,22 +647,17 @@ struct Lane {
     }
     double obj = 0.0, bad = 0.0;
     if (last) bad += emit(r, k1, m, l, cscale, means, chols);
+    // software pipeline: the backward kernel of step k-1 is in flight while step k is processed
+    double gn = 0.0, en[D], dkn[D];
+    load_kernel(r, kern + (k1 - 1) * NE, gn, en, dkn);
     for (long k = k1 - 1; k >= k0; --k) {
-      const double* kp = kern + k * NE;
-      double g = 0.0, e[D], dk[D];
+      double g = gn, e[D], dk[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        e[j] = 0.0;
-        dk[j] = 0.0;
+        e[j] = en[j];
+        dk[j] = dkn[j];
       }
-      if (r < D) {
-        g = kp[r];
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          e[j] = kp[D + r * D + j];
-          dk[j] = kp[D + D * D + r * D + j];
-        }
-      }
+      if (k > k0) load_kernel(r, kern + (k - 1) * NE, gn, en, dkn);
       const double* ML = publish(cx, 0, l);
       double mv[D];
       allgather(cx, m, mv);

@@ -6,6 +6,9 @@
 namespace pof {
 
 constexpr int LANE_WARPS = 4;
+#ifndef POF_LANE_MINBLOCKS
+#define POF_LANE_MINBLOCKS 1
+#endif
 
 template <int d, int q>
 struct LaneSetup {
@@ -26,8 +29,8 @@ struct LaneSetup {
 };
 
 template <int d, int q>
-__global__ void __launch_bounds__(LANE_WARPS * 32) k_lane_fold(LeafArgs a, double* __restrict__ fagg) {
-  extern __shared__ double sm[];
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS) k_lane_fold(LeafArgs a, double* __restrict__ fagg) {
+  extern __shared__ __align__(16) double sm[];
   using LN = Lane<d, q>;
   const long ch = LaneSetup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
@@ -39,11 +42,11 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) k_lane_fold(LeafArgs a, doubl
 }
 
 template <int d, int q>
-__global__ void __launch_bounds__(LANE_WARPS * 32)
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
     k_lane_scan(LeafArgs a, const double* __restrict__ fin, double* __restrict__ kern, double* __restrict__ sagg,
                 double* __restrict__ send, double* __restrict__ part, double* __restrict__ fmeans,
                 double* __restrict__ fchols) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   using LN = Lane<d, q>;
   const long ch = LaneSetup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
@@ -56,11 +59,11 @@ __global__ void __launch_bounds__(LANE_WARPS * 32)
 }
 
 template <int d, int q>
-__global__ void __launch_bounds__(LANE_WARPS * 32)
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
     k_lane_smooth(LeafArgs a, const double* __restrict__ sin, const double* __restrict__ kern, int emit_t0,
                   const double* __restrict__ cscale, double* __restrict__ means, double* __restrict__ chols,
                   double* __restrict__ part2) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   using LN = Lane<d, q>;
   const long ch = LaneSetup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;

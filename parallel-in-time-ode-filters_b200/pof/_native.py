@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libpof_b200.so")
+LIB_PATH = os.environ.get("POF_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libpof_b200.so")
 
 S_NLL, S_OBJ, S_SSQ, S_SSQ_PROPER, S_NOT_CLOSE, S_CSCALE, NSCALARS = 0, 1, 2, 3, 4, 5, 8
 
@@ -62,6 +62,10 @@ def _load():
         "pof_filter_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_profile_enable": (None, [_c_int]),
+        "pof_profile_read": (_c_int, [_c_dp, _c_dp]),
+        "pof_launches_per_pass": (_c_i64, [_c_i64, _c_int, _c_int, _c_i64]),
+        "pof_measure_dfma_tflops": (_c_int, [_c_dp, _c_dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -75,7 +79,7 @@ EXPORTED = [
     "pof_supported", "pof_default_chunk_len", "pof_workspace_bytes", "pof_filter_combine_f64",
     "pof_smooth_combine_f64", "pof_linearize_ivp_f64", "pof_linear_filtsmooth_f64", "pof_shard_stage_a_f64",
     "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
-    "pof_project_f64",
+    "pof_project_f64", "pof_profile_enable", "pof_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops",
 ]
 
 

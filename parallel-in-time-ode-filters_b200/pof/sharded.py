@@ -1,0 +1,168 @@
+"""Time-sharded (multi-GPU) IEKS pass: one process per GPU, contiguous time shards, two carry exchanges.
+
+Rank r owns steps [k_lo, k_hi) of the n = N-1 global steps and the state rows t in (k_lo, k_hi] (rank 0 also owns
+row 0).  One pass is three local stages of the CUDA library with two exchange points:
+
+    stage A  fold + up-sweep                 -> this shard's filtering element (3D^2+2D doubles)
+      all-gather of the W filtering elements; every rank folds elements 0..r-1 onto x0 (<= W-1 combines, one warp)
+    stage B  down-sweep, filter scan, smoother up-sweep
+                                             -> smoothing element (2D^2+D), filtered end state (D+D^2), 3 partial sums
+      all-gather of [smoothing element | end state | partial sums]; every rank folds the later ranks' elements onto the
+      last rank's end state; the sums give nll / sigma^2 (hence the calibration scale) on every rank identically
+    stage C  smoother down-sweep + smoother scan -> smoothed rows, 2 partial sums (objective, means not close)
+      all-gather of the 2 sums
+
+The exchanged payloads are a few KB, i.e. latency-bound: there is no bulk data-path collective.  The collectives are
+`torch.distributed` (NCCL over NVLink on the GPUs; gloo in the CPU tests, where the stages run in the host simulator
+through the same orchestration code).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _native as nat
+
+
+def shard_bounds(n_steps: int, rank: int, world: int):
+    """contiguous step range [k_lo, k_hi) of `rank`"""
+    return (rank * n_steps) // world, ((rank + 1) * n_steps) // world
+
+
+class CudaBackend:
+    """Stages of libpof_b200.so on the current CUDA device."""
+
+    def __init__(self, d, q, n_loc, chunk_len, qL, device):
+        self.d, self.q, self.n_loc = d, q, n_loc
+        self.device = device
+        self.chunk_len = int(chunk_len or nat.default_chunk_len(n_loc + 1, d, q, device.index))
+        self.ws = nat.Workspace.get(n_loc + 1, d, q, self.chunk_len, device)
+        self.qL, self.qLp = nat.host_doubles(qL)
+        D = d * (q + 1)
+        self.scratch = torch.empty(D + D * D, dtype=torch.float64, device=device)
+
+    def _ws(self):
+        return ctypes.c_void_p(self.ws.buf.data_ptr()), self.ws.nbytes
+
+    def stage_a(self, H, c, carry_f):
+        p, nb = self._ws()
+        nat.check(nat.LIB.pof_shard_stage_a_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
+                                                nat.ptr(H), nat.ptr(c), nat.ptr(carry_f), p, nb), "stage_a")
+
+    def stage_b(self, H, c, state_in, fmeans, fchols, carry_s, state_end, partials):
+        p, nb = self._ws()
+        nat.check(nat.LIB.pof_shard_stage_b_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
+                                                nat.ptr(H), nat.ptr(c), nat.ptr(state_in), nat.ptr(fmeans),
+                                                nat.ptr(fchols), nat.ptr(carry_s), nat.ptr(state_end),
+                                                nat.ptr(partials), p, nb), "stage_b")
+
+    def stage_c(self, seed, is_last, has_row0, cscale, means, chols, partials2):
+        p, nb = self._ws()
+        nat.check(nat.LIB.pof_shard_stage_c_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
+                                                nat.ptr(seed), int(is_last), int(has_row0), nat.ptr(cscale),
+                                                nat.ptr(means), nat.ptr(chols), nat.ptr(partials2), p, nb), "stage_c")
+
+    def filter_chain(self, D, count, state_in, elems, state_out):
+        nat.check(nat.LIB.pof_filter_apply_chain_f64(nat.stream_ptr(), D, count, nat.ptr(state_in), nat.ptr(elems),
+                                                     nat.ptr(state_out), nat.ptr(self.scratch)), "filter_chain")
+
+    def smooth_chain(self, D, count, state_in, elems, state_out):
+        nat.check(nat.LIB.pof_smooth_apply_chain_f64(nat.stream_ptr(), D, count, nat.ptr(state_in), nat.ptr(elems),
+                                                     nat.ptr(state_out), nat.ptr(self.scratch)), "smooth_chain")
+
+
+class ShardedPass:
+    """One linear filter+smoother pass over a time-sharded trajectory (the multi-GPU form of
+    pof.parallel_filtsmooth.linear_filtsmooth; reference pof/parallel_filtsmooth/__init__.py:5-10)."""
+
+    def __init__(self, N, d, q, qL, *, rank=None, world=None, group=None, device=None, chunk_len=None, backend=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.N, self.d, self.q = int(N), int(d), int(q)
+        self.D = D = d * (q + 1)
+        self.n = self.N - 1
+        self.k_lo, self.k_hi = shard_bounds(self.n, self.rank, self.world)
+        self.n_loc = self.k_hi - self.k_lo
+        if self.n_loc < 1:
+            raise ValueError("every rank needs at least one time step")
+        self.has_row0 = self.rank == 0
+        self.rows = self.n_loc + (1 if self.has_row0 else 0)
+        self.FE, self.SE, self.ST = 3 * D * D + 2 * D, 2 * D * D + D, D * D + D
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.backend = backend or CudaBackend(d, q, self.n_loc, chunk_len, qL, self.device)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)
+        self.carry_f, self.gather_f = z(self.FE), z(self.world * self.FE)
+        self.state_in, self.seed = z(self.ST), z(self.ST)
+        self.pay_b, self.gather_b = z(self.SE + self.ST + 3), z(self.world * (self.SE + self.ST + 3))
+        self.pay_c, self.gather_c = z(2), z(self.world * 2)
+        self.cscale = z(1)
+        self.x0_state = z(self.ST)
+
+    def _all_gather(self, out, inp):
+        if self.world == 1:
+            out.copy_(inp)
+        else:
+            dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def run(self, x0_mean, x0_chol, H_loc, c_loc, means_loc, chols_loc, *, calibrate=True, fmeans=None, fchols=None):
+        """H_loc (n_loc,d,D), c_loc (n_loc,d): local linearisation; means_loc (rows,D) in/out; chols_loc (rows,D,D)
+        out or None.  Returns dict(nll, obj, ssq, ssq_proper, not_close) -- identical on every rank."""
+        D, W, r, be = self.D, self.world, self.rank, self.backend
+        FE, SE, ST = self.FE, self.SE, self.ST
+        self.x0_state[:D].copy_(x0_mean)
+        self.x0_state[D:].copy_(x0_chol.reshape(-1))
+        # ---- stage A + exchange 1
+        be.stage_a(H_loc, c_loc, self.carry_f)
+        self._all_gather(self.gather_f, self.carry_f)
+        be.filter_chain(D, r, self.x0_state, self.gather_f, self.state_in)
+        # ---- stage B + exchange 2
+        pb = self.pay_b
+        if fmeans is not None and self.has_row0:
+            fmeans[0].copy_(x0_mean)
+            fchols[0].copy_(x0_chol)
+        shift = 0 if self.has_row0 else 1  # local row of state t' is t' - shift
+        fm = None if fmeans is None else fmeans
+        be.stage_b(H_loc, c_loc, self.state_in, _shifted(fm, shift, D), _shifted(fchols, shift, D * D), pb[:SE],
+                   pb[SE:SE + ST], pb[SE + ST:])
+        self._all_gather(self.gather_b, pb)
+        gb = self.gather_b.view(W, SE + ST + 3)
+        sums = gb[:, SE + ST:].sum(dim=0)  # same order on every rank -> bitwise identical scalars
+        nll = sums[0]
+        ssq = sums[1] / self.n / self.d
+        ssq_proper = sums[2] / self.n / self.d
+        self.cscale.copy_(torch.sqrt(ssq).reshape(1) if calibrate else torch.ones(1, dtype=torch.float64,
+                                                                                   device=self.device))
+        terminal = gb[W - 1, SE:SE + ST].contiguous()
+        later = gb[r + 1:, :SE].contiguous() if r + 1 < W else gb[:0, :SE].contiguous()
+        be.smooth_chain(D, W - 1 - r, terminal, later, self.seed)
+        # ---- stage C + exchange 3
+        be.stage_c(self.seed, r == W - 1, self.has_row0, self.cscale, means_loc, chols_loc, self.pay_c)
+        self._all_gather(self.gather_c, self.pay_c)
+        s2 = self.gather_c.view(W, 2).sum(dim=0)
+        return dict(nll=nll, obj=s2[0], ssq=ssq, ssq_proper=ssq_proper, not_close=s2[1])
+
+
+def _shifted(t, shift, width):
+    """view of `t` whose row index is offset by `shift` rows (the stages index local states by t', rows by t'-shift);
+    row -1 is never touched when shift == 1"""
+    if t is None or shift == 0:
+        return t
+    return _RowShift(t, shift * width)
+
+
+class _RowShift:
+    """pointer-only wrapper: data_ptr() moved back by `back` doubles (used only to pass a base address to the C ABI)"""
+
+    def __init__(self, t, back):
+        self.t, self.back = t, back
+        self.is_cuda, self.dtype = t.is_cuda, t.dtype
+
+    def data_ptr(self):
+        return self.t.data_ptr() - 8 * self.back
+
+    def is_contiguous(self):
+        return self.t.is_contiguous()

@@ -30,7 +30,8 @@ def main():
         H = torch.empty((N - 1, d, D), dtype=torch.float64, device=dev)
         c = torch.empty((N - 1, d), dtype=torch.float64, device=dev)
         sc = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
-        for L in ([None] if len(sys.argv) > 1 else [None]):
+        for L in [int(x) for x in os.environ.get('CHUNK_LENS', '0').split(',')]:
+            L = L or None
             def it():
                 linearize_into(lin, means, H, c)
                 run_pass(setup["x0"], setup["_qL"], H, c, means, chols, d=d, q=q, calibrate=True, chunk_len=L,
@@ -44,7 +45,7 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); it(); e1.record(); torch.cuda.synchronize()
                 tms.append(e0.elapsed_time(e1))
-            print(f"N={N} L={nat.default_chunk_len(N, d, q)} ms/iter={min(tms):.3f} scalars={sc.cpu().numpy()[:5]}", flush=True)
+            print(f"N={N} L={L or nat.default_chunk_len(N, d, q)} ms/iter={min(tms):.3f} scalars={sc.cpu().numpy()[:5]}", flush=True)
 
 
 if __name__ == "__main__":

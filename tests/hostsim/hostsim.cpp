@@ -83,7 +83,159 @@ static int run(long N, long L, const double* qL, const double* x0, const double*
   return 0;
 }
 
+// ---- time-sharded form: the same three stages the CUDA library exposes (pof_shard_stage_{a,b,c}_f64), on the host
+struct HsWs {
+  int d, q, D, FE, SE, ST;
+  long n, L, CS;
+  TreeLevels tl;
+  std::vector<double> fagg, fin, sagg, sin_, kern, send, part, part2, smem, qL;
+};
+template <int d, int q>
+static void hs_a(HsWs& w, const double* H, const double* c, double* carry_f) {
+  using CK = Chunk<d, q>;
+  Warp wp;
+  for (long ch = 0; ch < w.CS; ++ch)
+    CK::fold(ch * w.L, std::min((ch + 1) * w.L, w.n), H, c, w.qL.data(), &w.fagg[ch * w.FE]);
+  for (int l = 0; l + 1 < w.tl.nlev; ++l)
+    for (long i = 0; i < w.tl.sz[l + 1]; ++i) {
+      double* par = &w.fagg[(w.tl.off[l + 1] + i) * w.FE];
+      const double* lc = &w.fagg[(w.tl.off[l] + 2 * i) * w.FE];
+      if (2 * i + 1 < w.tl.sz[l]) filter_combine(wp, w.D, lc, lc + w.FE, par, w.smem.data(), false);
+      else std::memcpy(par, lc, w.FE * sizeof(double));
+    }
+  std::memcpy(carry_f, &w.fagg[w.tl.off[w.tl.nlev - 1] * w.FE], w.FE * sizeof(double));
+}
+template <int d, int q>
+static void hs_b(HsWs& w, const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
+                 double* carry_s, double* state_end, double* partials) {
+  using CK = Chunk<d, q>;
+  Warp wp;
+  const TreeLevels& tl = w.tl;
+  std::memcpy(&w.fin[tl.off[tl.nlev - 1] * w.ST], state_in, w.ST * sizeof(double));
+  for (int l = tl.nlev - 1; l >= 1; --l)
+    for (long i = 0; i < tl.sz[l]; ++i) {
+      const double* pin = &w.fin[(tl.off[l] + i) * w.ST];
+      std::memcpy(&w.fin[(tl.off[l - 1] + 2 * i) * w.ST], pin, w.ST * sizeof(double));
+      if (2 * i + 1 < tl.sz[l - 1])
+        filter_combine(wp, w.D, pin, &w.fagg[(tl.off[l - 1] + 2 * i) * w.FE],
+                       &w.fin[(tl.off[l - 1] + 2 * i + 1) * w.ST], w.smem.data(), true);
+    }
+  for (long ch = 0; ch < w.CS; ++ch)
+    CK::scan(ch * w.L, std::min((ch + 1) * w.L, w.n), H, c, w.qL.data(), &w.fin[ch * w.ST], w.kern.data(), w.CS, ch,
+             &w.sagg[ch * w.SE], &w.send[ch * w.ST], &w.part[ch * 3], fmeans, fchols);
+  for (int l = 0; l + 1 < tl.nlev; ++l)
+    for (long i = 0; i < tl.sz[l + 1]; ++i) {
+      double* par = &w.sagg[(tl.off[l + 1] + i) * w.SE];
+      const double* lc = &w.sagg[(tl.off[l] + 2 * i) * w.SE];
+      if (2 * i + 1 < tl.sz[l]) smooth_combine(wp, w.D, lc + w.SE, lc, par, w.smem.data(), false);
+      else std::memcpy(par, lc, w.SE * sizeof(double));
+    }
+  std::memcpy(carry_s, &w.sagg[tl.off[tl.nlev - 1] * w.SE], w.SE * sizeof(double));
+  std::memcpy(state_end, &w.send[(w.CS - 1) * w.ST], w.ST * sizeof(double));
+  partials[0] = partials[1] = partials[2] = 0.0;
+  for (long ch = 0; ch < w.CS; ++ch)
+    for (int j = 0; j < 3; ++j) partials[j] += w.part[ch * 3 + j];
+}
+template <int d, int q>
+static void hs_c(HsWs& w, const double* seed, int has_row0, double cscale, double* means, double* chols,
+                 double* partials2) {
+  using CK = Chunk<d, q>;
+  Warp wp;
+  const TreeLevels& tl = w.tl;
+  std::memcpy(&w.sin_[tl.off[tl.nlev - 1] * w.ST], seed, w.ST * sizeof(double));
+  for (int l = tl.nlev - 1; l >= 1; --l)
+    for (long i = 0; i < tl.sz[l]; ++i) {
+      const double* pin = &w.sin_[(tl.off[l] + i) * w.ST];
+      if (2 * i + 1 < tl.sz[l - 1]) {
+        std::memcpy(&w.sin_[(tl.off[l - 1] + 2 * i + 1) * w.ST], pin, w.ST * sizeof(double));
+        smooth_combine(wp, w.D, pin, &w.sagg[(tl.off[l - 1] + 2 * i + 1) * w.SE],
+                       &w.sin_[(tl.off[l - 1] + 2 * i) * w.ST], w.smem.data(), true);
+      } else {
+        std::memcpy(&w.sin_[(tl.off[l - 1] + 2 * i) * w.ST], pin, w.ST * sizeof(double));
+      }
+    }
+  const long shift = has_row0 ? 0 : 1;
+  double* mb = means - shift * w.D;
+  double* cb = chols ? chols - shift * (long)w.D * w.D : nullptr;
+  for (long ch = 0; ch < w.CS; ++ch)
+    CK::smooth(ch * w.L, std::min((ch + 1) * w.L, w.n), ch == w.CS - 1, has_row0 != 0, w.qL.data(),
+               &w.sin_[ch * w.ST], w.kern.data(), w.CS, ch, cscale, mb, cb, &w.part2[ch * 2]);
+  partials2[0] = partials2[1] = 0.0;
+  for (long ch = 0; ch < w.CS; ++ch)
+    for (int j = 0; j < 2; ++j) partials2[j] += w.part2[ch * 2 + j];
+}
+
+#define HS_DISPATCH(CALL)                                                                                      \
+  do {                                                                                                         \
+    const int d = w->d, q = w->q;                                                                              \
+    if (d == 1 && q == 1) { CALL(1, 1); } else if (d == 1 && q == 2) { CALL(1, 2); }                           \
+    else if (d == 1 && q == 3) { CALL(1, 3); } else if (d == 2 && q == 2) { CALL(2, 2); }                      \
+    else if (d == 2 && q == 3) { CALL(2, 3); } else if (d == 3 && q == 3) { CALL(3, 3); }                      \
+    else return -1;                                                                                            \
+  } while (0)
+
 extern "C" {
+void* hs_ws_create(int d, int q, long n_loc, long L, const double* qL) {
+  HsWs* w = new HsWs;
+  w->d = d; w->q = q; w->D = d * (q + 1);
+  const int D = w->D;
+  w->FE = 3 * D * D + 2 * D; w->SE = 2 * D * D + D; w->ST = D * D + D;
+  w->n = n_loc; w->L = L; w->CS = (n_loc + L - 1) / L;
+  w->tl.build(w->CS);
+  w->fagg.resize(w->tl.total * w->FE); w->fin.resize(w->tl.total * w->ST);
+  w->sagg.resize(w->tl.total * w->SE); w->sin_.resize(w->tl.total * w->ST);
+  w->kern.resize((size_t)L * (D + 2 * D * D) * w->CS); w->send.resize(w->CS * w->ST);
+  w->part.resize(w->CS * 3); w->part2.resize(w->CS * 2);
+  w->smem.resize(coop_ws_doubles(D));
+  w->qL.assign(qL, qL + (q + 1) * (q + 1));
+  return w;
+}
+void hs_ws_free(void* p) { delete (HsWs*)p; }
+int hs_stage_a(void* p, const double* H, const double* c, double* carry_f) {
+  HsWs* w = (HsWs*)p;
+#define CALL(dd, qq) hs_a<dd, qq>(*w, H, c, carry_f)
+  HS_DISPATCH(CALL);
+#undef CALL
+  return 0;
+}
+int hs_stage_b(void* p, const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
+               double* carry_s, double* state_end, double* partials) {
+  HsWs* w = (HsWs*)p;
+#define CALL(dd, qq) hs_b<dd, qq>(*w, H, c, state_in, fmeans, fchols, carry_s, state_end, partials)
+  HS_DISPATCH(CALL);
+#undef CALL
+  return 0;
+}
+int hs_stage_c(void* p, const double* seed, int has_row0, double cscale, double* means, double* chols,
+               double* partials2) {
+  HsWs* w = (HsWs*)p;
+#define CALL(dd, qq) hs_c<dd, qq>(*w, seed, has_row0, cscale, means, chols, partials2)
+  HS_DISPATCH(CALL);
+#undef CALL
+  return 0;
+}
+int hs_filter_chain(int D, int count, const double* state_in, const double* elems, double* state_out) {
+  std::vector<double> smem(coop_ws_doubles(D)), cur(state_in, state_in + D + D * D), nxt(D + D * D);
+  Warp w;
+  const int FE = 3 * D * D + 2 * D;
+  for (int i = 0; i < count; ++i) {
+    filter_combine(w, D, cur.data(), elems + (long)i * FE, nxt.data(), smem.data(), true);
+    cur.swap(nxt);
+  }
+  std::memcpy(state_out, cur.data(), (D + D * D) * sizeof(double));
+  return 0;
+}
+int hs_smooth_chain(int D, int count, const double* state_in, const double* elems, double* state_out) {
+  std::vector<double> smem(coop_ws_doubles(D)), cur(state_in, state_in + D + D * D), nxt(D + D * D);
+  Warp w;
+  const int SE = 2 * D * D + D;
+  for (int i = 0; i < count; ++i) {
+    smooth_combine(w, D, cur.data(), elems + (long)(count - 1 - i) * SE, nxt.data(), smem.data(), true);
+    cur.swap(nxt);
+  }
+  std::memcpy(state_out, cur.data(), (D + D * D) * sizeof(double));
+  return 0;
+}
 int hs_filter_combine(int D, const double* e1, const double* e2, double* out, int state_mode) {
   std::vector<double> smem(coop_ws_doubles(D));
   Warp w;
