@@ -1,0 +1,50 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, and exports every symbol include/pof_b200.h declares.
+No compute calls here (no GPU in this container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "pof_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pof_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(native_lib):
+    lib = ctypes.CDLL(native_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pof_b200.h but not exported"
+    assert sorted(native_lib.EXPORTED) == names
+
+
+def test_host_only_queries(native_lib):
+    L = native_lib.LIB
+    assert L.pof_supported(2, 3) == 1 and L.pof_supported(1, 1) == 1 and L.pof_supported(4, 5) == 1
+    assert L.pof_supported(5, 3) == 0 and L.pof_supported(2, 9) == 0
+    assert L.pof_default_chunk_len(1 << 20, 2, 3, 148) >= 4
+    nb = L.pof_workspace_bytes(1 << 20, 2, 3, 222)
+    assert 1.1e9 < nb < 1.4e9  # dominated by the per-step backward kernels: n * 136 doubles
+    assert L.pof_launches_per_pass(1 << 20, 2, 3, 222) > 8
+
+
+def test_sass_is_sm100a(native_lib):
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", native_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(monkeypatch):
+    """the product path refuses CPU tensors"""
+    import torch
+    from pof import _native as nat
+
+    with pytest.raises(nat.NativeError):
+        nat.require_cuda(torch.zeros(3, dtype=torch.float64))
