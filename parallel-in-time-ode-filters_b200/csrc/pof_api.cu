@@ -45,6 +45,16 @@ const LeafLaunch* leaf_launch(int d, int q) {
   return thread_launch(d, q);
 }
 
+// register-resident tree sweeps when 2D <= 32 (POF_B200_TREE_IMPL=generic forces the shared-memory kernels)
+static const TreeLaunch* tree_launch(int D) {
+  const char* e = getenv("POF_B200_TREE_IMPL");
+  if (e && e[0] == 'g') return nullptr;
+  const TreeLaunch* t = tree_launch_a(D);
+  if (!t) t = tree_launch_b(D);
+  if (!t) t = tree_launch_c(D);
+  return t;
+}
+
 constexpr int TREE_WARPS = 4;  // max warps (= element pairs) per CTA in the tree kernels; fewer when D is large
 
 // ------------------------------------------------------------------------------------------------ tree sweeps
@@ -472,10 +482,14 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   const int tw = tree_warps(wl.D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_up, smem));
+  const TreeLaunch* tl = tree_launch(wl.D);
   for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
     const long np = wl.tl.sz[l + 1];
-    k_filter_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-        wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np);
+    if (tl)
+      POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE, np));
+    else
+      k_filter_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
+          wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np);
   }
   return (int)cudaGetLastError();
 }
@@ -490,13 +504,18 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_down, smem));
   POF_CK(set_smem(k_smooth_up, smem));
+  const TreeLaunch* tl = tree_launch(wl.D);
   {
   ProfScope ps(SEG_FDOWN, s);
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     const long np = wl.tl.sz[l];
-    k_filter_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-        wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
-        fin + wl.tl.off[l - 1] * wl.ST);
+    if (tl)
+      POF_CK(tl->fdown(s, fin + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], fagg + wl.tl.off[l - 1] * wl.FE,
+                       fin + wl.tl.off[l - 1] * wl.ST, np));
+    else
+      k_filter_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
+          wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
+          fin + wl.tl.off[l - 1] * wl.ST);
   }
   }
   POF_CK(cudaGetLastError());
@@ -507,8 +526,11 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   ProfScope ps(SEG_SUP, s);
   for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
     const long np = wl.tl.sz[l + 1];
-    k_smooth_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-        wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
+    if (tl)
+      POF_CK(tl->sup(s, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE, np));
+    else
+      k_smooth_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
+          wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
   }
   k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
   return (int)cudaGetLastError();
@@ -524,11 +546,16 @@ static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   POF_CK(set_smem(k_smooth_down, smem));
   {
   ProfScope ps(SEG_SDOWN, s);
+  const TreeLaunch* tl = tree_launch(wl.D);
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     const long np = wl.tl.sz[l];
-    k_smooth_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-        wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
-        sin_ + wl.tl.off[l - 1] * wl.ST);
+    if (tl)
+      POF_CK(tl->sdown(s, sin_ + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], sagg + wl.tl.off[l - 1] * wl.SE,
+                       sin_ + wl.tl.off[l - 1] * wl.ST, np));
+    else
+      k_smooth_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
+          wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
+          sin_ + wl.tl.off[l - 1] * wl.ST);
   }
   }
   POF_CK(cudaGetLastError());
@@ -632,6 +659,7 @@ size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
 
 int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
   if (n <= 0) return 0;
+  if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->fcomb((cudaStream_t)s, e1, n, e2, out, n);
   const int smem = tree_smem_bytes(D);
   const int tw = tree_warps(D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
@@ -641,6 +669,7 @@ int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, c
 }
 int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
   if (n <= 0) return 0;
+  if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->scomb((cudaStream_t)s, e1, n, e2, out, n);
   const int smem = tree_smem_bytes(D);
   const int tw = tree_warps(D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;

@@ -39,4 +39,13 @@ const LeafLaunch* lane_launch_d2(int q);
 const LeafLaunch* lane_launch_d3(int q);
 const LeafLaunch* lane_launch_d4(int q);
 
+// register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> generic shared-memory kernels
+struct TreeLaunch {
+  typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
+  Fn fup, fdown, sup, sdown, fcomb, scomb;
+};
+const TreeLaunch* tree_launch_a(int D);
+const TreeLaunch* tree_launch_b(int D);
+const TreeLaunch* tree_launch_c(int D);
+
 }  // namespace pof

@@ -1,0 +1,432 @@
+// Carry level, performance path: the reference's two associative operators with REGISTER-resident rows.
+//
+//   filter operator  (pof/parallel_filtsmooth/filter.py:117-142): G2 = pow2ceil(2D) lanes per combine, lane r owns
+//                    row r of the 2D x 2D array Xi = [[U1^T Z2, I],[Z2, 0]] during its triangularisation; afterwards
+//                    lanes 0..D-1 triangularise [A2 Y | U2] (-> U) while lanes D..2D-1 triangularise
+//                    [A1^T Xi22 | Z1] (-> Z) in the same pivot loop.
+//   smoothing operator (smoother.py:53-63): GS = pow2ceil(D) lanes per combine.
+//
+// Same algebra as pof_coop.cuh (Y = U1 Xi11^{-T}, G = I - Y Xi21^T, ...), same packed element layouts; the generic
+// shared-memory version there remains the fallback for 2D > 32.  Small GEMMs read the second operand's rows from a
+// per-combine shared-memory staging area (published row-wise by the owning lanes).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pof_small.cuh"
+
+namespace pof {
+
+template <int D>
+struct TreeLane {
+  static constexpr int pow2c(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : (x <= 16 ? 16 : 32))); }
+  static constexpr int W2 = 2 * D;
+  static constexpr int G2 = pow2c(W2);     // lanes per filtering combine
+  static constexpr int GS = pow2c(D);      // lanes per smoothing combine
+  static constexpr int LDM = D + 1;
+  static constexpr int MAT = D * LDM;
+  static constexpr int BCW = ((W2 + 2 + 1) / 2) * 2;  // broadcast slot (doubles)
+  // staging: 9 matrices + 2x2 broadcast slots + 2 gather vectors
+  static constexpr int NMAT = 9;
+  static constexpr int VEC = ((W2 + 1) / 2) * 2;
+  static constexpr int RAW = NMAT * MAT + 4 * BCW + 2 * VEC;
+  static constexpr int SM_COMBINE = RAW + ((2 - (RAW % 16)) + 16) % 16;
+  enum { mU1 = 0, mZ2, mA1, mX11, mX21, mX22, mY, mG, mP };
+
+  struct Ctx {
+    int r;  // lane within the combine's group
+    unsigned mask;
+    double* sm;
+    int flip, vflip;
+    __device__ __forceinline__ double* mat(int which) const { return sm + which * MAT; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  };
+  template <int G>
+  static __device__ __forceinline__ void init(Ctx& c, double* sm) {
+    const int lane = threadIdx.x & 31;
+    c.r = lane % G;
+    c.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    c.sm = sm;
+    c.flip = 0;
+    c.vflip = 0;
+  }
+
+  static __device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+  }
+  static __device__ __forceinline__ double fast_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-hx * r, r, 0.5);
+    return fma(r, e, r);
+  }
+  struct HH {
+    double s, tp, beta;
+  };
+  template <int n>
+  static __device__ __forceinline__ HH house(double alpha, const double* x) {
+    double sigma = 0.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) sigma = fma(x[j], x[j], sigma);
+    const bool nz = sigma > 0.0;
+    const double nrm2 = fma(alpha, alpha, sigma);
+    const double rn = fast_rsqrt(nrm2);
+    const double nrm = nrm2 * rn;
+    const double beta = (alpha >= 0.0) ? -nrm : nrm;
+    const double s = alpha - beta;
+    HH h;
+    h.beta = nz ? beta : alpha;
+    h.s = nz ? s : 0.0;
+    h.tp = nz ? rn * fast_rcp(fabs(s)) : 0.0;
+    return h;
+  }
+
+  // lane `src` publishes n doubles into broadcast slot `slot_id` (0/1: two independent streams), all lanes read
+  template <int n>
+  static __device__ __forceinline__ void bcast(Ctx& c, int slot_id, const double (&x)[n], int src, double (&out)[n]) {
+    double2* slot = reinterpret_cast<double2*>(c.sm + NMAT * MAT + (2 * slot_id + c.flip) * BCW);
+    if (c.r == src) {
+#pragma unroll
+      for (int j = 0; j + 1 < n; j += 2) slot[j / 2] = make_double2(x[j], x[j + 1]);
+      if (n % 2) slot[n / 2] = make_double2(x[n - 1], 0.0);
+    }
+    c.sync();
+#pragma unroll
+    for (int j = 0; j + 1 < n; j += 2) {
+      const double2 v = slot[j / 2];
+      out[j] = v.x;
+      out[j + 1] = v.y;
+    }
+    if (n % 2) out[n - 1] = slot[n / 2].x;
+  }
+  // out[j] = x of lane j (j < n)
+  template <int n>
+  static __device__ __forceinline__ void allgather(Ctx& c, double x, double (&out)[n]) {
+    double* v = c.sm + NMAT * MAT + 4 * BCW + c.vflip * VEC;
+    c.vflip ^= 1;
+    if (c.r < n) v[c.r] = x;
+    c.sync();
+#pragma unroll
+    for (int j = 0; j < n; ++j) out[j] = v[j];
+  }
+  // row `row` of matrix `which` <- x   (caller syncs)
+  static __device__ __forceinline__ void put_row(Ctx& c, int which, int row, const double (&x)[D]) {
+    double* M = c.mat(which) + row * LDM;
+#pragma unroll
+    for (int j = 0; j < D; ++j) M[j] = x[j];
+  }
+  // y[c] = sum_k a[k] * M[k][c]   (row vector times staged matrix)
+  static __device__ __forceinline__ void row_times(const Ctx& c, int which, const double (&a)[D], double (&y)[D]) {
+    const double* M = c.mat(which);
+#pragma unroll
+    for (int j = 0; j < D; ++j) y[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) y[j] = fma(a[k], M[k * LDM + j], y[j]);
+    }
+  }
+  // y[c] = sum_k M1[k][col] * M2[k][c]   (column `col` of M1, transposed, times M2)
+  static __device__ __forceinline__ void col_times(const Ctx& c, int which1, int col, int which2, double (&y)[D]) {
+    const double* M1 = c.mat(which1);
+    const double* M2 = c.mat(which2);
+#pragma unroll
+    for (int j = 0; j < D; ++j) y[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double a = M1[k * LDM + col];
+#pragma unroll
+      for (int j = 0; j < D; ++j) y[j] = fma(a, M2[k * LDM + j], y[j]);
+    }
+  }
+  static __device__ __forceinline__ void load_row(const double* __restrict__ p, double (&x)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = p[j];
+  }
+  static __device__ __forceinline__ void store_row_tri(double* __restrict__ p, int row, const double* x) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) p[j] = (j <= row) ? x[j] : 0.0;
+  }
+
+  // one pivot of a right-Householder triangularisation over NC columns; rows over lanes; two independent halves
+  // (rows [0,D) use pivot lane I, rows [D,2D) use pivot lane D+I) when DUAL, else a single matrix whose rows are the
+  // lanes [0, NR)
+  template <int I, int NC, int NPIV, bool DUAL>
+  static __device__ __forceinline__ void tria_step(Ctx& cx, double (&x)[NC]) {
+    if constexpr (I < NPIV && I + 1 < NC) {
+      constexpr int n = NC - I;
+      double mine[n], piv[n];
+#pragma unroll
+      for (int j = I; j < NC; ++j) mine[j - I] = x[j];
+      const bool second = DUAL && cx.r >= D;
+      if (DUAL) {
+        // both halves publish into their own slot; each lane reads its half's slot
+        double2* s0 = reinterpret_cast<double2*>(cx.sm + NMAT * MAT + (0 + cx.flip) * BCW);
+        double2* s1 = reinterpret_cast<double2*>(cx.sm + NMAT * MAT + (2 + cx.flip) * BCW);
+        if (cx.r == I || cx.r == D + I) {
+          double2* s = second ? s1 : s0;
+#pragma unroll
+          for (int j = 0; j + 1 < n; j += 2) s[j / 2] = make_double2(mine[j], mine[j + 1]);
+          if (n % 2) s[n / 2] = make_double2(mine[n - 1], 0.0);
+        }
+        cx.sync();
+        const double2* s = second ? s1 : s0;
+#pragma unroll
+        for (int j = 0; j + 1 < n; j += 2) {
+          const double2 v = s[j / 2];
+          piv[j] = v.x;
+          piv[j + 1] = v.y;
+        }
+        if (n % 2) piv[n - 1] = s[n / 2].x;
+        cx.flip ^= 1;
+      } else {
+        bcast<n>(cx, 0, mine, I, piv);
+        cx.flip ^= 1;
+      }
+      const HH h = house<n - 1>(piv[0], piv + 1);
+      double w = h.s * x[I];
+#pragma unroll
+      for (int j = I + 1; j < NC; ++j) w = fma(x[j], piv[j - I], w);
+      const int rr = second ? cx.r - D : cx.r;
+      w = (rr >= I) ? w * h.tp : 0.0;
+      x[I] = (rr == I) ? h.beta : fma(-w, h.s, x[I]);
+#pragma unroll
+      for (int j = I + 1; j < NC; ++j) x[j] = fma(-w, piv[j - I], x[j]);
+      tria_step<I + 1, NC, NPIV, DUAL>(cx, x);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------- filtering operator
+  // e1: earlier (packed element, or packed state when STATE), e2: later element; out: element, or state when STATE
+  template <bool STATE>
+  static __device__ __forceinline__ void filter_combine(Ctx& cx, const double* __restrict__ e1,
+                                                        const double* __restrict__ e2, double* __restrict__ out) {
+    constexpr int DD = D * D;
+    const int r = cx.r;
+    const bool top = r < D;
+    const bool bot = r >= D && r < W2;
+    const int rr = top ? r : (bot ? r - D : 0);
+    // element pointers
+    const double* A1 = e1;
+    const double* b1 = STATE ? e1 : e1 + DD;
+    const double* U1 = STATE ? e1 + D : e1 + DD + D;
+    const double* n1 = e1 + 2 * DD + D;
+    const double* Z1 = e1 + 2 * DD + 2 * D;
+    const double* A2 = e2;
+    const double* b2 = e2 + DD;
+    const double* U2 = e2 + DD + D;
+    const double* n2 = e2 + 2 * DD + D;
+    const double* Z2 = e2 + 2 * DD + 2 * D;
+
+    // stage U1, Z2 (and A1): lanes [0,D) publish U1 rows, lanes [D,2D) publish Z2 rows
+    double u1[D], z2[D], a1[D];
+    load_row(U1 + rr * D, u1);
+    load_row(Z2 + rr * D, z2);
+    if (top) put_row(cx, mU1, rr, u1);
+    if (bot) put_row(cx, mZ2, rr, z2);
+    if (!STATE) {
+      load_row(A1 + rr * D, a1);
+      if (top) put_row(cx, mA1, rr, a1);
+    }
+    cx.sync();
+    // Xi rows: top r: [ (U1^T Z2)[r,:], e_r ] ; bottom r: [ Z2[r,:], 0 ]
+    double x[W2];
+    {
+      double y[D];
+      col_times(cx, mU1, rr, mZ2, y);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        x[j] = top ? y[j] : (bot ? z2[j] : 0.0);
+        x[D + j] = (top && j == rr) ? 1.0 : 0.0;
+      }
+    }
+    tria_step<0, W2, (STATE ? D : W2), false>(cx, x);
+    // publish Xi11 (lanes top), Xi21 and Xi22 (lanes bottom)
+    {
+      double lo[D], hi[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        lo[j] = x[j];
+        hi[j] = (j <= rr) ? x[D + j] : 0.0;
+      }
+      if (top) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) lo[j] = (j <= rr) ? lo[j] : 0.0;
+        put_row(cx, mX11, rr, lo);
+      }
+      if (bot) {
+        put_row(cx, mX21, rr, lo);
+        if (!STATE) put_row(cx, mX22, rr, hi);
+      }
+    }
+    cx.sync();
+    // Y row r = U1[r,:] Xi11^{-T}  (forward substitution), lanes top (others compute harmlessly on row rr)
+    double y[D];
+    {
+      const double* X11 = cx.mat(mX11);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double acc = u1[j];
+#pragma unroll
+        for (int i = 0; i < j; ++i) acc = fma(-y[i], X11[j * LDM + i], acc);
+        y[j] = acc * fast_rcp(X11[j * LDM + j]);
+      }
+    }
+    if (top) put_row(cx, mY, rr, y);
+    // G row r = e_r - Y[r,:] Xi21^T
+    double g[D];
+    {
+      const double* X21 = cx.mat(mX21);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double acc = (c == rr) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fma(-y[k], X21[c * LDM + k], acc);
+        g[c] = acc;
+      }
+    }
+    if (top) put_row(cx, mG, rr, g);
+    cx.sync();
+    // ---- b = A2 G (b1 + U1 U1^T eta2) + b2
+    double a2[D];
+    load_row(A2 + rr * D, a2);
+    {
+      double v[D], t[D];
+      allgather<D>(cx, top ? n2[rr] : 0.0, v);
+      // (U1^T eta2)[rr]: column rr of U1
+      double s = 0.0;
+      const double* MU = cx.mat(mU1);
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma(MU[k * LDM + rr], v[k], s);
+      allgather<D>(cx, s, t);
+      double t0 = b1[rr];
+#pragma unroll
+      for (int k = 0; k < D; ++k) t0 = fma(u1[k], t[k], t0);
+      allgather<D>(cx, t0, v);
+      double t2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) t2 = fma(g[k], v[k], t2);
+      allgather<D>(cx, t2, t);
+      double bo = b2[rr];
+#pragma unroll
+      for (int k = 0; k < D; ++k) bo = fma(a2[k], t[k], bo);
+      if (top) (STATE ? out : out + DD)[rr] = bo;
+    }
+    // ---- rows for the second triangularisation: top: [A2 Y | U2] -> U ; bottom: [A1^T Xi22 | Z1] -> Z
+    double x2[W2];
+    {
+      double p[D], q2[D];
+      row_times(cx, mY, a2, p);
+      load_row((bot && !STATE) ? Z1 + rr * D : U2 + rr * D, q2);
+      if (!STATE) {
+        double pz[D];
+        col_times(cx, mA1, rr, mX22, pz);
+#pragma unroll
+        for (int j = 0; j < D; ++j) p[j] = bot ? pz[j] : p[j];
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        x2[j] = p[j];
+        x2[D + j] = q2[j];
+      }
+    }
+    if (!STATE) {
+      // ---- A = A2 (G A1)
+      double pr[D], ao[D];
+      row_times(cx, mA1, g, pr);
+      if (top) put_row(cx, mP, rr, pr);
+      cx.sync();
+      row_times(cx, mP, a2, ao);
+      if (top) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) out[rr * D + j] = ao[j];
+      }
+      // ---- eta = A1^T G^T (eta2 - Z2 Z2^T b1) + eta1
+      double v[D], t[D];
+      allgather<D>(cx, top ? b1[rr] : 0.0, v);
+      double s = 0.0;
+      const double* MZ = cx.mat(mZ2);
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma(MZ[k * LDM + rr], v[k], s);  // (Z2^T b1)[rr]
+      allgather<D>(cx, s, t);
+      double s0 = n2[rr];
+#pragma unroll
+      for (int k = 0; k < D; ++k) s0 = fma(-MZ[rr * LDM + k], t[k], s0);  // eta2 - Z2 (Z2^T b1)
+      allgather<D>(cx, s0, v);
+      double s2 = 0.0;
+      const double* MG = cx.mat(mG);
+#pragma unroll
+      for (int k = 0; k < D; ++k) s2 = fma(MG[k * LDM + rr], v[k], s2);  // (G^T s)[rr]
+      allgather<D>(cx, s2, t);
+      double eo = n1[rr];
+      const double* MA = cx.mat(mA1);
+#pragma unroll
+      for (int k = 0; k < D; ++k) eo = fma(MA[k * LDM + rr], t[k], eo);  // (A1^T .)[rr]
+      if (top) out[2 * DD + D + rr] = eo;
+    }
+    tria_step<0, W2, D, !STATE>(cx, x2);
+    if (top) store_row_tri((STATE ? out + D : out + DD + D) + rr * D, rr, x2);
+    if (!STATE && bot) store_row_tri(out + 2 * DD + 2 * D + rr * D, rr, x2);
+  }
+
+  // ------------------------------------------------------------------------------------------- smoothing operator
+  // e1: LATER (packed element, or packed state when STATE), e2: EARLIER element.  GS lanes, lane r owns row r.
+  template <bool STATE>
+  static __device__ __forceinline__ void smooth_combine(Ctx& cx, const double* __restrict__ e1,
+                                                        const double* __restrict__ e2, double* __restrict__ out) {
+    constexpr int DD = D * D;
+    const int r = cx.r;
+    const bool act = r < D;
+    const int rr = act ? r : 0;
+    const double* g1 = e1;
+    const double* E1 = e1 + D;
+    const double* D1 = STATE ? e1 + D : e1 + D + DD;
+    const double* g2 = e2;
+    const double* E2 = e2 + D;
+    const double* D2 = e2 + D + DD;
+    double row[D];
+    load_row(D1 + rr * D, row);
+    if (act) put_row(cx, mU1, rr, row);
+    if (!STATE) {
+      load_row(E1 + rr * D, row);
+      if (act) put_row(cx, mA1, rr, row);
+    }
+    double e2r[D], v[D];
+    load_row(E2 + rr * D, e2r);
+    allgather<D>(cx, act ? g1[rr] : 0.0, v);  // also orders the put_rows before the reads below
+    double go = g2[rr];
+#pragma unroll
+    for (int k = 0; k < D; ++k) go = fma(e2r[k], v[k], go);
+    if (act) out[rr] = go;
+    if (!STATE) {
+      double eo[D];
+      row_times(cx, mA1, e2r, eo);
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) out[D + rr * D + j] = eo[j];
+      }
+    }
+    double x[W2];
+    {
+      double p[D], d2[D];
+      row_times(cx, mU1, e2r, p);
+      load_row(D2 + rr * D, d2);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        x[j] = p[j];
+        x[D + j] = d2[j];
+      }
+    }
+    tria_step<0, W2, D, false>(cx, x);
+    if (act) store_row_tri((STATE ? out + D : out + D + DD) + rr * D, rr, x);
+  }
+};
+
+}  // namespace pof
