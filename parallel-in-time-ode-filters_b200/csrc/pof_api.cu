@@ -372,7 +372,7 @@ struct WsLayout {
   TreeLevels tl;
   long CS, L;
   int D, FE, SE, ST, NE;
-  size_t o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, total;  // in doubles
+  size_t o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, total;  // in doubles
   void build(long n, int d, int q, long chunk_len) {
     D = d * (q + 1);
     FE = 3 * D * D + 2 * D;
@@ -390,6 +390,7 @@ struct WsLayout {
       return r;
     };
     o_fagg = take((size_t)tl.total * FE);
+    o_faggm = take((size_t)CS * FE);
     o_fin = take((size_t)tl.total * ST);
     o_sagg = take((size_t)tl.total * SE);
     o_sin = take((size_t)tl.total * ST);
@@ -473,9 +474,10 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
 // stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
 static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws) {
   double* fagg = ws + wl.o_fagg;
+  const bool pre = ll->has_pre_update && tree_launch(wl.D) != nullptr;
   {
     ProfScope ps(SEG_FOLD, s);
-    POF_CK(ll->fold(s, a, fagg));
+    POF_CK(ll->fold(s, a, fagg, pre ? ws + wl.o_faggm : nullptr));
   }
   ProfScope ps(SEG_FUP, s);
   const int smem = tree_smem_bytes(wl.D);
@@ -519,10 +521,13 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   }
   }
   POF_CK(cudaGetLastError());
+  const bool pre = ll->has_pre_update && tl != nullptr;
   {
     ProfScope ps(SEG_SCAN, s);
-    POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+    POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, pre ? nullptr : sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
   }
+  // chunk-level smoothing elements straight from (incoming state, filtering element before its last update)
+  if (pre) POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
   ProfScope ps(SEG_SUP, s);
   for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
     const long np = wl.tl.sz[l + 1];

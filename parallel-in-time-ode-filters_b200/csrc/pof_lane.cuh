@@ -336,7 +336,8 @@ struct Lane {
 
   // ================================================================== filter phase 1: chunk -> filtering element
   static __device__ __forceinline__ void fold(Ctx& cx, long k0, long k1, const double* __restrict__ H,
-                                              const double* __restrict__ c, double* __restrict__ agg) {
+                                              const double* __restrict__ c, double* __restrict__ agg,
+                                              double* __restrict__ aggm) {
     const int r = cx.r;
     double a[D], uf[D], z[D], b = 0.0, eta = 0.0;
 #pragma unroll
@@ -362,6 +363,18 @@ struct Lane {
 #pragma unroll
       for (int j = 0; j < D; ++j) t[j] = cx.tq[j];
       tpqrt<D, false>(cx, t, cc, nullptr, nullptr);
+      // the element before the chunk's last measurement update (for the chunk-level smoothing element)
+      if (aggm && k == k1 - 1 && r < D) {
+        const int DD = D * D;
+        aggm[DD + r] = b;
+        aggm[2 * DD + D + r] = eta;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          aggm[r * D + j] = a[j];
+          aggm[DD + D + r * D + j] = (j <= r) ? t[j] : 0.0;
+          aggm[2 * DD + 2 * D + r * D + j] = (j <= r) ? z[j] : 0.0;
+        }
+      }
       // update
       double SL[d][d];
       update(cx, t, Hk, SL);
@@ -423,6 +436,7 @@ struct Lane {
   }
 
   // ================================================================== filter phase 3: seeded square-root KF
+  template <bool COMPOSE>
   static __device__ __forceinline__ void scan(Ctx& cx, long k0, long k1, const double* __restrict__ H,
                                               const double* __restrict__ c, const double* __restrict__ state_in,
                                               double* __restrict__ kern, double* __restrict__ sagg,
@@ -489,8 +503,10 @@ struct Lane {
         store_row(kp + D + r * D, e);
         store_row(kp + D + D * D + r * D, uf);
       }
-      // ---- compose the chunk's smoothing element: acc = acc o kernel_k
-      if (k == k0) {
+      // ---- compose the chunk's smoothing element: acc = acc o kernel_k  (skipped when the chunk-level element is
+      //      derived from the filtering element instead, pof_treelane.cuh chunk_kernel)
+      if (!COMPOSE) {
+      } else if (k == k0) {
         ga = g;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -565,13 +581,16 @@ struct Lane {
     // chunk outputs: smoothing element, filtered end state (triangular factor), partial sums
     tria_rows(cx, uf);
     if (r < D) {
-      sagg[r] = ga;
       state_end[r] = m;
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        sagg[D + r * D + j] = ea[j];
-        sagg[D + D * D + r * D + j] = (j <= r) ? da[j] : 0.0;
-        state_end[D + r * D + j] = (j <= r) ? uf[j] : 0.0;
+      for (int j = 0; j < D; ++j) state_end[D + r * D + j] = (j <= r) ? uf[j] : 0.0;
+      if (COMPOSE) {
+        sagg[r] = ga;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          sagg[D + r * D + j] = ea[j];
+          sagg[D + D * D + r * D + j] = (j <= r) ? da[j] : 0.0;
+        }
       }
     }
     if (r == 0) {

@@ -29,7 +29,8 @@ struct LaneSetup {
 };
 
 template <int d, int q>
-__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS) k_lane_fold(LeafArgs a, double* __restrict__ fagg) {
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
+    k_lane_fold(LeafArgs a, double* __restrict__ fagg, double* __restrict__ faggm) {
   extern __shared__ __align__(16) double sm[];
   using LN = Lane<d, q>;
   const long ch = LaneSetup<d, q>::chunk_of_thread();
@@ -38,10 +39,11 @@ __global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS) k_lane_fo
   LN::init_ctx(cx, LaneSetup<d, q>::smem_of_thread(sm), a.ql.v);
   const long k0 = ch * a.L;
   const long k1 = (k0 + a.L < a.n) ? k0 + a.L : a.n;
-  LN::fold(cx, k0, k1, a.H, a.c, fagg + ch * (3 * LN::D * LN::D + 2 * LN::D));
+  constexpr int FE = 3 * LN::D * LN::D + 2 * LN::D;
+  LN::fold(cx, k0, k1, a.H, a.c, fagg + ch * FE, faggm ? faggm + ch * FE : nullptr);
 }
 
-template <int d, int q>
+template <int d, int q, bool COMPOSE>
 __global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
     k_lane_scan(LeafArgs a, const double* __restrict__ fin, double* __restrict__ kern, double* __restrict__ sagg,
                 double* __restrict__ send, double* __restrict__ part, double* __restrict__ fmeans,
@@ -55,7 +57,8 @@ __global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
   constexpr int D = LN::D, SE = 2 * D * D + D, ST = D * D + D;
   const long k0 = ch * a.L;
   const long k1 = (k0 + a.L < a.n) ? k0 + a.L : a.n;
-  LN::scan(cx, k0, k1, a.H, a.c, fin + ch * ST, kern, sagg + ch * SE, send + ch * ST, part + ch * 3, fmeans, fchols);
+  LN::template scan<COMPOSE>(cx, k0, k1, a.H, a.c, fin + ch * ST, kern, COMPOSE ? sagg + ch * SE : nullptr,
+                             send + ch * ST, part + ch * 3, fmeans, fchols);
 }
 
 template <int d, int q>
@@ -83,14 +86,18 @@ __global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
 template <int d, int q>
 struct LaneLaunchers {
   using LS = LaneSetup<d, q>;
-  static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg) {
-    k_lane_fold<d, q><<<LS::grid(a.CS), LANE_WARPS * 32, LS::smem_bytes(), s>>>(a, fagg);
+  static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg, double* faggm) {
+    k_lane_fold<d, q><<<LS::grid(a.CS), LANE_WARPS * 32, LS::smem_bytes(), s>>>(a, fagg, faggm);
     return cudaGetLastError();
   }
   static cudaError_t scan(cudaStream_t s, const LeafArgs& a, const double* fin, double* kern, double* sagg,
                           double* send, double* part, double* fmeans, double* fchols) {
-    k_lane_scan<d, q><<<LS::grid(a.CS), LANE_WARPS * 32, LS::smem_bytes(), s>>>(a, fin, kern, sagg, send, part,
-                                                                                 fmeans, fchols);
+    if (sagg)
+      k_lane_scan<d, q, true><<<LS::grid(a.CS), LANE_WARPS * 32, LS::smem_bytes(), s>>>(a, fin, kern, sagg, send,
+                                                                                         part, fmeans, fchols);
+    else
+      k_lane_scan<d, q, false><<<LS::grid(a.CS), LANE_WARPS * 32, LS::smem_bytes(), s>>>(a, fin, kern, sagg, send,
+                                                                                          part, fmeans, fchols);
     return cudaGetLastError();
   }
   static cudaError_t smooth(cudaStream_t s, const LeafArgs& a, const double* sin, const double* kern, int emit_t0,
@@ -100,7 +107,7 @@ struct LaneLaunchers {
     return cudaGetLastError();
   }
   static const LeafLaunch* get() {
-    static const LeafLaunch l = {&fold, &scan, &smooth, Lane<d, q>::GPW};
+    static const LeafLaunch l = {&fold, &scan, &smooth, Lane<d, q>::GPW, 1};
     return &l;
   }
 };

@@ -19,12 +19,15 @@ struct LeafArgs {
 };
 
 struct LeafLaunch {
-  cudaError_t (*fold)(cudaStream_t, const LeafArgs&, double* fagg);
+  // faggm (may be null): the chunk's filtering element BEFORE its last measurement update (lane kernels only)
+  cudaError_t (*fold)(cudaStream_t, const LeafArgs&, double* fagg, double* faggm);
+  // sagg null: do not compose the chunk's smoothing element inside the scan (lane kernels only)
   cudaError_t (*scan)(cudaStream_t, const LeafArgs&, const double* fin, double* kern, double* sagg, double* send,
                       double* part, double* fmeans, double* fchols);
   cudaError_t (*smooth)(cudaStream_t, const LeafArgs&, const double* sin, const double* kern, int emit_t0,
                         const double* cscale, double* means, double* chols, double* part2);
-  int chunks_per_warp;  // 32 for the thread-per-chunk kernels, 32/G for the lane-cooperative ones
+  int chunks_per_warp;
+  int has_pre_update;  // 1 if fold can emit faggm and scan can skip the composition  // 32 for the thread-per-chunk kernels, 32/G for the lane-cooperative ones
 };
 
 // returns nullptr if (d, q) is not compiled in
@@ -42,7 +45,7 @@ const LeafLaunch* lane_launch_d4(int q);
 // register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> generic shared-memory kernels
 struct TreeLaunch {
   typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
-  Fn fup, fdown, sup, sdown, fcomb, scomb;
+  Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk;
 };
 const TreeLaunch* tree_launch_a(int D);
 const TreeLaunch* tree_launch_b(int D);

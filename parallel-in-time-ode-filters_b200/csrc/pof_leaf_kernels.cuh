@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(LEAF_THREADS)
 template <int d, int q>
 struct LeafLaunchers {
   static unsigned grid(const LeafArgs& a) { return (unsigned)((a.CS + LEAF_THREADS - 1) / LEAF_THREADS); }
-  static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg) {
+  static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg, double* /*faggm*/) {
     k_fold<d, q><<<grid(a), LEAF_THREADS, 0, s>>>(a, fagg);
     return cudaGetLastError();
   }
@@ -68,7 +68,7 @@ struct LeafLaunchers {
     return cudaGetLastError();
   }
   static const LeafLaunch* get() {
-    static const LeafLaunch l = {&fold, &scan, &smooth, 32};
+    static const LeafLaunch l = {&fold, &scan, &smooth, 32, 0};
     return &l;
   }
 };

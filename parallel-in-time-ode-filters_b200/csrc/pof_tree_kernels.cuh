@@ -8,7 +8,7 @@ namespace pof {
 
 constexpr int TL_WARPS = 4;
 
-enum TreeOp { T_FUP = 0, T_FDOWN, T_SUP, T_SDOWN, T_FCOMB, T_SCOMB };
+enum TreeOp { T_FUP = 0, T_FDOWN, T_SUP, T_SDOWN, T_FCOMB, T_SCOMB, T_CHUNKK };
 
 template <int D, int G>
 __device__ __forceinline__ void group_copy(int r, double* __restrict__ dst, const double* __restrict__ src, int n) {
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32)
     k_tree(const double* __restrict__ a, long na, const double* __restrict__ b, double* __restrict__ c, long nb) {
   extern __shared__ __align__(16) double sm[];
   using TL = TreeLane<D>;
-  constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB);
+  constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB || OP == T_CHUNKK);
   constexpr int G = FILT ? TL::G2 : TL::GS;
   constexpr int CPW = 32 / G;
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(TL_WARPS * 32)
     } else {
       group_copy<D, G>(cx.r, c + 2 * i * ST, p, ST);
     }
+  } else if constexpr (OP == T_CHUNKK) {
+    // a = chunk incoming states, b = chunk filtering elements before their last update, c = chunk smoothing elements
+    TL::chunk_kernel(cx, a + i * ST, b + i * FE, c + i * SE);
   } else if constexpr (OP == T_FCOMB) {
     TL::template filter_combine<false>(cx, a + i * FE, b + i * FE, c + i * FE);
   } else {
@@ -66,7 +69,7 @@ struct TreeLaunchers {
   using TL = TreeLane<D>;
   template <int OP>
   static cudaError_t run(cudaStream_t s, const double* a, long na, const double* b, double* c, long nb) {
-    constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB);
+    constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB || OP == T_CHUNKK);
     constexpr int G = FILT ? TL::G2 : TL::GS;
     constexpr int CPW = 32 / G;
     constexpr int smem = TL_WARPS * CPW * TL::SM_COMBINE * (int)sizeof(double);
@@ -80,7 +83,8 @@ struct TreeLaunchers {
     return cudaGetLastError();
   }
   static const TreeLaunch* get() {
-    static const TreeLaunch t = {&run<T_FUP>, &run<T_FDOWN>, &run<T_SUP>, &run<T_SDOWN>, &run<T_FCOMB>, &run<T_SCOMB>};
+    static const TreeLaunch t = {&run<T_FUP>, &run<T_FDOWN>, &run<T_SUP>, &run<T_SDOWN>, &run<T_FCOMB>, &run<T_SCOMB>,
+                                 &run<T_CHUNKK>};
     return &t;
   }
 };

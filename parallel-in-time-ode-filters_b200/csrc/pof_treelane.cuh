@@ -376,6 +376,149 @@ struct TreeLane {
     if (!STATE && bot) store_row_tri(out + 2 * DD + 2 * D + rr * D, rr, x2);
   }
 
+  // ------------------------------------------------------------------------------- chunk-level smoothing element
+  // The smoothing element (g, E, Dm) of a whole chunk (steps s..e), i.e. the composition of its per-step backward
+  // kernels (smoother.py:37-63), obtained directly from the filtered state (m, L) at the chunk start and the chunk's
+  // filtering element taken BEFORE its last measurement update (A, b, U, eta, Z):
+  //    x_s | y_{1:e-1} ~ N(m', Y Y^T),  Y = L Xi11^{-T},  m' = G (m + L L^T eta)      (as in the filtering operator)
+  //    tria([[A Y, U],[Y, 0]]) = [[Phi11, 0],[Phi21, Phi22]],  E = Phi21 Phi11^{-1},  g = m' - E (A m' + b),  Dm = Phi22
+  // One such op per chunk replaces L-1 per-step compositions inside the filter scan.
+  static __device__ __forceinline__ void chunk_kernel(Ctx& cx, const double* __restrict__ st,
+                                                      const double* __restrict__ e2, double* __restrict__ out) {
+    constexpr int DD = D * D;
+    const int r = cx.r;
+    const bool top = r < D;
+    const bool bot = r >= D && r < W2;
+    const int rr = top ? r : (bot ? r - D : 0);
+    const double* b1 = st;
+    const double* U1 = st + D;
+    const double* A2 = e2;
+    const double* b2 = e2 + DD;
+    const double* U2 = e2 + DD + D;
+    const double* n2 = e2 + 2 * DD + D;
+    const double* Z2 = e2 + 2 * DD + 2 * D;
+    double u1[D], z2[D];
+    load_row(U1 + rr * D, u1);
+    load_row(Z2 + rr * D, z2);
+    if (top) put_row(cx, mU1, rr, u1);
+    if (bot) put_row(cx, mZ2, rr, z2);
+    cx.sync();
+    double x[W2];
+    {
+      double y0[D];
+      col_times(cx, mU1, rr, mZ2, y0);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        x[j] = top ? y0[j] : (bot ? z2[j] : 0.0);
+        x[D + j] = (top && j == rr) ? 1.0 : 0.0;
+      }
+    }
+    tria_step<0, W2, D, false>(cx, x);
+    {
+      double lo[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) lo[j] = (top && j > rr) ? 0.0 : x[j];
+      if (top) put_row(cx, mX11, rr, lo);
+      if (bot) put_row(cx, mX21, rr, lo);
+    }
+    cx.sync();
+    double y[D];
+    {
+      const double* X11 = cx.mat(mX11);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double acc = u1[j];
+#pragma unroll
+        for (int i = 0; i < j; ++i) acc = fma(-y[i], X11[j * LDM + i], acc);
+        y[j] = acc * fast_rcp(X11[j * LDM + j]);
+      }
+    }
+    if (top) put_row(cx, mY, rr, y);
+    double g[D];
+    {
+      const double* X21 = cx.mat(mX21);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double acc = (c == rr) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fma(-y[k], X21[c * LDM + k], acc);
+        g[c] = acc;
+      }
+    }
+    cx.sync();
+    double a2[D];
+    load_row(A2 + rr * D, a2);
+    // m' = G (m + L L^T eta)  and  v = A m' + b
+    double mp[D], vf[D];
+    {
+      double v[D], t[D];
+      allgather<D>(cx, top ? n2[rr] : 0.0, v);
+      double s = 0.0;
+      const double* MU = cx.mat(mU1);
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma(MU[k * LDM + rr], v[k], s);
+      allgather<D>(cx, s, t);
+      double t0 = b1[rr];
+#pragma unroll
+      for (int k = 0; k < D; ++k) t0 = fma(u1[k], t[k], t0);
+      allgather<D>(cx, t0, v);
+      double t2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) t2 = fma(g[k], v[k], t2);
+      allgather<D>(cx, t2, mp);
+      double av = b2[rr];
+#pragma unroll
+      for (int k = 0; k < D; ++k) av = fma(a2[k], mp[k], av);
+      allgather<D>(cx, av, vf);
+    }
+    // joint array [[A Y, U],[Y, 0]]
+    double x2[W2];
+    {
+      double p[D], q2[D];
+      row_times(cx, mY, a2, p);
+      load_row(U2 + rr * D, q2);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        x2[j] = top ? p[j] : (bot ? y[j] : 0.0);
+        x2[D + j] = top ? q2[j] : 0.0;
+      }
+    }
+    tria_step<0, W2, W2, false>(cx, x2);
+    {
+      double lo[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) lo[j] = (j <= rr) ? x2[j] : 0.0;
+      cx.sync();
+      if (top) put_row(cx, mX11, rr, lo);
+      cx.sync();
+    }
+    // E row (bottom lanes): e Phi11 = phi21  (backward substitution over the columns)
+    double e[D];
+    {
+      const double* P11 = cx.mat(mX11);
+#pragma unroll
+      for (int j = D - 1; j >= 0; --j) {
+        double acc = x2[j];
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) acc = fma(-e[i], P11[i * LDM + j], acc);
+        e[j] = acc * fast_rcp(P11[j * LDM + j]);
+      }
+    }
+    if (bot) {
+      double go = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        go = (k == rr) ? mp[k] : go;
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) go = fma(-e[k], vf[k], go);
+      out[rr] = go;
+#pragma unroll
+      for (int j = 0; j < D; ++j) out[D + rr * D + j] = e[j];
+      store_row_tri(out + D + DD + rr * D, rr, x2 + D);
+    }
+  }
+
   // ------------------------------------------------------------------------------------------- smoothing operator
   // e1: LATER (packed element, or packed state when STATE), e2: EARLIER element.  GS lanes, lane r owns row r.
   template <bool STATE>
