@@ -206,7 +206,7 @@ def run_native(args):
     import pof.ivp
     from pof import _native as nat
     from pof.convenience import set_up_solver
-    from pof.parallel_filtsmooth import run_pass
+    from pof.parallel_filtsmooth import run_iteration
     from pof.sharded import ShardedPass, shard_bounds
     from pof.step import linearize_into
 
@@ -232,8 +232,9 @@ def run_native(args):
     means0 = row.repeat(rows, 1).contiguous()
     means = means0.clone()
     chols = torch.empty((rows, D_, D_), dtype=torch.float64, device=dev)
-    H = torch.empty((n_loc, d_, D_), dtype=torch.float64, device=dev)
-    c = torch.empty((n_loc, d_), dtype=torch.float64, device=dev)
+    if world > 1:
+        H = torch.empty((n_loc, d_, D_), dtype=torch.float64, device=dev)
+        c = torch.empty((n_loc, d_), dtype=torch.float64, device=dev)
     scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
     t1row = 1 if rank == 0 else 0  # local row of the first linearisation point (state k_lo + 1)
 
@@ -246,11 +247,11 @@ def run_native(args):
 
     if world == 1:
         L = nat.default_chunk_len(N_total, d_, q_, dev.index)
+        L = int(os.environ.get("POF_CHUNK_LEN", L))
         launches = 1 + int(nat.LIB.pof_launches_per_pass(N_total, d_, q_, L))
 
-        def step():
-            linearize()
-            run_pass(x0, qL, H, c, means, chols, d=d_, q=q_, calibrate=True, chunk_len=L, scalars=scalars)
+        def step():  # the fused iteration: linearise (compact, in the workspace) + pass
+            run_iteration(x0, qL, lin, means, chols, calibrate=True, chunk_len=L, scalars=scalars)
             return scalars
     else:
         sp = ShardedPass(N_total, d_, q_, qL, rank=rank, world=world, device=dev)

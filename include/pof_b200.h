@@ -101,6 +101,16 @@ int pof_linear_filtsmooth_f64(pof_stream_t s, int64_t N, int d, int q, int64_t c
                               double* means, double* chols, double* fmeans, double* fchols, int calibrate,
                               double* scalars, void* ws, size_t ws_bytes);
 
+/* One fused IEKS iteration for a built-in IVP -- replaces the body of the reference's while loop,
+ *   pof.step.ieks_step(om, dtm, x0, states)   pof/step.py:33-45   (called from pof/solver.py:48-55):
+ * linearise at means[1:] (fused f / Jacobian, kept in the compact form [J_f | c] inside the workspace: the dense
+ * (n,d,D) H is never materialised), filter + smoother pass, calibration, convergence reductions.
+ * means (N,D): IN previous trajectory, OUT smoothed means; chols (N,D,D) or NULL; scalars as above. */
+int pof_ieks_iteration_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t N, int d, int q,
+                           int64_t chunk_len, const double* qL_host, double scale0, double scale1,
+                           const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
+                           double* scalars, void* ws, size_t ws_bytes);
+
 /* ---- time-sharded (multi-GPU) form of the same pass: three local stages with two exchange points ----------
  * Rank r owns the contiguous step range [k_lo, k_hi) of the global n steps; H, c are the LOCAL slices
  * (k_hi-k_lo steps) and means/chols/fmeans/fchols the LOCAL rows t in (k_lo, k_hi] (plus row t = 0 on rank 0:

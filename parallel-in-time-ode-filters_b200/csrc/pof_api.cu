@@ -331,6 +331,26 @@ __global__ void __launch_bounds__(256)
     Hr[a * Q1 + 1] += scale1;
   }
 }
+// compact linearisation: per step [J_f (d x d) | c (d)] with c = J_f y - f(y); the leaf kernels rebuild H on load
+__global__ void __launch_bounds__(256)
+    k_linearize_compact(int ivp_id, IvpParams P, long n, int d, int q, double scale0,
+                        const double* __restrict__ means_t1, double* __restrict__ Jc) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int Q1 = q + 1, D = d * Q1;
+  double y[4], f[4], J[16];
+  for (int b = 0; b < d; ++b) y[b] = scale0 * means_t1[k * D + b * Q1];
+  ivp_eval(ivp_id, P, y, f, J);
+  double* o = Jc + k * (d * d + d);
+  for (int a = 0; a < d; ++a) {
+    double ca = -f[a];
+    for (int b = 0; b < d; ++b) {
+      ca = fma(J[a * d + b], y[b], ca);
+      o[a * d + b] = J[a * d + b];
+    }
+    o[d * d + a] = ca;
+  }
+}
 // ys = E0 states, with the (second) calibration multiplier of pof/solver.py:66-69 read from device memory
 __global__ void __launch_bounds__(256)
     k_project(long N, int d, int q, double scale0, const double* __restrict__ mult, const double* __restrict__ means,
@@ -372,7 +392,7 @@ struct WsLayout {
   TreeLevels tl;
   long CS, L;
   int D, FE, SE, ST, NE;
-  size_t o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, total;  // in doubles
+  size_t o_lin, o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, total;  // in doubles
   void build(long n, int d, int q, long chunk_len) {
     D = d * (q + 1);
     FE = 3 * D * D + 2 * D;
@@ -389,6 +409,7 @@ struct WsLayout {
       o += (cnt + 31) & ~(size_t)31;
       return r;
     };
+    o_lin = take((size_t)(n > 0 ? n : 1) * (d * D + d));  // linearisation of the fused iteration (compact or dense)
     o_fagg = take((size_t)tl.total * FE);
     o_faggm = take((size_t)CS * FE);
     o_fin = take((size_t)tl.total * ST);
@@ -466,6 +487,8 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   a.CS = wl.CS;
   a.H = H;
   a.c = c;
+  a.Jc = nullptr;
+  a.s0 = a.s1 = 0.0;
   for (int i = 0; i < 36; ++i) a.ql.v[i] = 0.0;
   for (int i = 0; i < (q + 1) * (q + 1); ++i) a.ql.v[i] = qL_host[i];
   return 0;
@@ -611,7 +634,8 @@ int pof_profile_read(double* ms_out, int64_t* count_out) {
 int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  return 3 /*leaf*/ + 4 * (int64_t)(wl.tl.nlev - 1) /*tree sweeps*/ + 1 /*pack*/ + 2 /*reduce*/ + 2 /*finalize*/;
+  return 3 /*leaf*/ + 4 * (int64_t)(wl.tl.nlev - 1) /*tree sweeps*/ + 1 /*chunk smoothing elements*/ + 1 /*pack*/ +
+         2 /*reduce*/ + 2 /*finalize*/;
 }
 
 // FP64 FMA throughput of this device (TFLOP/s), measured with a register-resident DFMA loop: the roofline
@@ -697,6 +721,10 @@ int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host,
   return (int)cudaGetLastError();
 }
 
+static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws, int64_t N,
+                    int d, const double* x0_mean, const double* x0_chol, double* means, double* chols,
+                    double* fmeans, double* fchols, int calibrate, double* scalars);
+
 int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
                               const double* x0_mean, const double* x0_chol, const double* H, const double* c,
                               double* means, double* chols, double* fmeans, double* fchols, int calibrate,
@@ -712,7 +740,53 @@ int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t 
   LeafArgs a;
   int rc = make_args(N - 1, d, q, qL_host, H, c, wl, a);
   if (rc) return rc;
-  rc = stage_a(s, ll, a, wl, ws);
+  return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
+}
+
+int pof_ieks_iteration_f64(pof_stream_t s_, int ivp_id, const double* params_host, int nparams, int64_t N, int d,
+                           int q, int64_t chunk_len, const double* qL_host, double scale0, double scale1,
+                           const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
+                           double* scalars, void* ws_, size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (N < 2) return POF_E_ARG;
+  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
+  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
+  if (dims[ivp_id] != d || nparams > 8) return POF_E_ARG;
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (!ll) return POF_E_UNSUPPORTED_DQ;
+  WsLayout wl;
+  wl.build(N - 1, d, q, chunk_len);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  IvpParams P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
+  const long n = N - 1;
+  const int D = wl.D;
+  double* lin = ws + wl.o_lin;
+  LeafArgs a;
+  int rc;
+  if (ll->has_pre_update) {  // lane kernels: compact linearisation, H rebuilt on load
+    k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, means + D, lin);
+    rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, a);
+    a.Jc = lin;
+    a.s0 = scale0;
+    a.s1 = scale1;
+  } else {
+    k_linearize<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, scale1, means + D, lin,
+                                                            lin + (size_t)n * d * D);
+    rc = make_args(n, d, q, qL_host, lin, lin + (size_t)n * d * D, wl, a);
+  }
+  if (rc) return rc;
+  POF_CK(cudaGetLastError());
+  return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, nullptr, nullptr, calibrate, scalars);
+}
+
+}  // extern "C"
+
+static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws, int64_t N,
+                    int d, const double* x0_mean, const double* x0_chol, double* means, double* chols,
+                    double* fmeans, double* fchols, int calibrate, double* scalars) {
+  int rc = stage_a(s, ll, a, wl, ws);
   if (rc) return rc;
   // root's incoming state = x0
   k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
@@ -731,6 +805,8 @@ int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t 
   k_finalize_smooth<<<1, 1, 0, s>>>(ws + wl.o_sums + 8, scalars);
   return (int)cudaGetLastError();
 }
+
+extern "C" {
 
 int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
                           const double* H, const double* c, double* carry_f, void* ws_, size_t ws_bytes) {

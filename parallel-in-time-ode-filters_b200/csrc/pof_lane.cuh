@@ -324,19 +324,38 @@ struct Lane {
       z[a] = s * fast_rcp(SL[a][a]);
     }
   }
-  static __device__ __forceinline__ void load_Hc(const double* __restrict__ H, const double* __restrict__ c, long k,
-                                                 double (&Hk)[d][D], double (&ck)[d]) {
+  // linearised observation model of step k: dense (H, c) from memory, or rebuilt from the compact form [J_f | c]:
+  // H = E1 - J_f E0 with E0 = s0 e_0^T, E1 = s1 e_1^T per block (reference pof/convenience.py:26-28)
+  struct Lin {
+    const double* __restrict__ H;
+    const double* __restrict__ c;
+    const double* __restrict__ Jc;
+    double s0, s1;
+  };
+  static __device__ __forceinline__ void load_Hc(const Lin& L, long k, double (&Hk)[d][D], double (&ck)[d]) {
+    if (L.Jc) {
+      const double* p = L.Jc + k * (d * d + d);
 #pragma unroll
-    for (int a = 0; a < d; ++a) {
-      ck[a] = __ldg(c + k * d + a);
+      for (int a = 0; a < d; ++a) {
+        ck[a] = __ldg(p + d * d + a);
 #pragma unroll
-      for (int j = 0; j < D; ++j) Hk[a][j] = __ldg(H + (k * d + a) * D + j);
+        for (int j = 0; j < D; ++j) Hk[a][j] = 0.0;
+#pragma unroll
+        for (int b = 0; b < d; ++b) Hk[a][b * Q1] = -__ldg(p + a * d + b) * L.s0;
+        Hk[a][a * Q1 + 1] += L.s1;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < d; ++a) {
+        ck[a] = __ldg(L.c + k * d + a);
+#pragma unroll
+        for (int j = 0; j < D; ++j) Hk[a][j] = __ldg(L.H + (k * d + a) * D + j);
+      }
     }
   }
 
   // ================================================================== filter phase 1: chunk -> filtering element
-  static __device__ __forceinline__ void fold(Ctx& cx, long k0, long k1, const double* __restrict__ H,
-                                              const double* __restrict__ c, double* __restrict__ agg,
+  static __device__ __forceinline__ void fold(Ctx& cx, long k0, long k1, const Lin& lin, double* __restrict__ agg,
                                               double* __restrict__ aggm) {
     const int r = cx.r;
     double a[D], uf[D], z[D], b = 0.0, eta = 0.0;
@@ -348,7 +367,7 @@ struct Lane {
     }
     for (long k = k0; k < k1; ++k) {
       double Hk[d][D], ck[d];
-      load_Hc(H, c, k, Hk, ck);
+      load_Hc(lin, k, Hk, ck);
       // predict
       double t[D], cc[D];
       {
@@ -437,8 +456,8 @@ struct Lane {
 
   // ================================================================== filter phase 3: seeded square-root KF
   template <bool COMPOSE>
-  static __device__ __forceinline__ void scan(Ctx& cx, long k0, long k1, const double* __restrict__ H,
-                                              const double* __restrict__ c, const double* __restrict__ state_in,
+  static __device__ __forceinline__ void scan(Ctx& cx, long k0, long k1, const Lin& lin,
+                                              const double* __restrict__ state_in,
                                               double* __restrict__ kern, double* __restrict__ sagg,
                                               double* __restrict__ state_end, double* __restrict__ part,
                                               double* __restrict__ fmeans, double* __restrict__ fchols) {
@@ -461,7 +480,7 @@ struct Lane {
     double nll = 0.0, s1 = 0.0, s2 = 0.0;
     for (long k = k0; k < k1; ++k) {
       double Hk[d][D], ck[d];
-      load_Hc(H, c, k, Hk, ck);
+      load_Hc(lin, k, Hk, ck);
       // ---- predict + backward kernel: [[F Uf, QL],[Uf, 0]] -> [[T, 0],[Phi21, Phi22~]]
       double t[D], cc[D], e[D];
       {
@@ -602,9 +621,9 @@ struct Lane {
 
   // ================================================================== smoother phase 3: seeded square-root RTS
   static __device__ __forceinline__ double emit(int r, long t, double m, const double (&l)[D], double cscale,
-                                                double* __restrict__ means, double* __restrict__ chols) {
+                                                double old, double* __restrict__ means,
+                                                double* __restrict__ chols) {
     if (r >= D) return 0.0;
-    const double old = means[t * D + r];
     const bool close = fabs(old - m) <= (1e-8 + 1e-13 * fabs(m));
     means[t * D + r] = m;
     if (chols) {
@@ -665,18 +684,25 @@ struct Lane {
       for (int j = 0; j < D; ++j) l[j] = 0.0;
     }
     double obj = 0.0, bad = 0.0;
-    if (last) bad += emit(r, k1, m, l, cscale, means, chols);
-    // software pipeline: the backward kernel of step k-1 is in flight while step k is processed
+    if (last) bad += emit(r, k1, m, l, cscale, means[k1 * D + rc], means, chols);
+    // software pipeline: the backward kernel and the previous mean of step k-1 are in flight while step k is
+    // processed (no dependent global load inside a step)
     double gn = 0.0, en[D], dkn[D];
     load_kernel(r, kern + (k1 - 1) * NE, gn, en, dkn);
+    const bool skip0 = !emit_t0;  // row t = 0 belongs to the previous shard
+    double oldn = (k1 - 1 > 0 || !skip0) ? means[(k1 - 1) * D + rc] : 0.0;
     for (long k = k1 - 1; k >= k0; --k) {
       double g = gn, e[D], dk[D];
+      const double old = oldn;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         e[j] = en[j];
         dk[j] = dkn[j];
       }
-      if (k > k0) load_kernel(r, kern + (k - 1) * NE, gn, en, dkn);
+      if (k > k0) {
+        load_kernel(r, kern + (k - 1) * NE, gn, en, dkn);
+        oldn = (k - 1 > 0 || !skip0) ? means[(k - 1) * D + rc] : 0.0;
+      }
       const double* ML = publish(cx, 0, l);
       double mv[D];
       allgather(cx, m, mv);
@@ -708,7 +734,7 @@ struct Lane {
       m = mn;
 #pragma unroll
       for (int j = 0; j < D; ++j) l[j] = (j <= rc) ? dk[j] : 0.0;
-      if (k > 0 || emit_t0) bad += emit(r, k, m, l, cscale, means, chols);
+      if (k > 0 || emit_t0) bad += emit(r, k, m, l, cscale, old, means, chols);
     }
     // not-close counts are per lane: sum over the group
 #pragma unroll

@@ -6,8 +6,16 @@
 namespace pof {
 
 constexpr int LANE_WARPS = 4;
-#ifndef POF_LANE_MINBLOCKS
-#define POF_LANE_MINBLOCKS 1
+// resident CTAs per SM the compiler must allow.  Measured on B200: forcing more occupancy (168 / 128 registers) makes
+// fold and smooth SLOWER (spills add LSU traffic, and the kernels are bound by shared-memory delivery, not by warps)
+#ifndef POF_FOLD_MINBLOCKS
+#define POF_FOLD_MINBLOCKS 1
+#endif
+#ifndef POF_SCAN_MINBLOCKS
+#define POF_SCAN_MINBLOCKS 1
+#endif
+#ifndef POF_SMOOTH_MINBLOCKS
+#define POF_SMOOTH_MINBLOCKS 2
 #endif
 
 template <int d, int q>
@@ -29,7 +37,7 @@ struct LaneSetup {
 };
 
 template <int d, int q>
-__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_FOLD_MINBLOCKS)
     k_lane_fold(LeafArgs a, double* __restrict__ fagg, double* __restrict__ faggm) {
   extern __shared__ __align__(16) double sm[];
   using LN = Lane<d, q>;
@@ -40,11 +48,12 @@ __global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
   const long k0 = ch * a.L;
   const long k1 = (k0 + a.L < a.n) ? k0 + a.L : a.n;
   constexpr int FE = 3 * LN::D * LN::D + 2 * LN::D;
-  LN::fold(cx, k0, k1, a.H, a.c, fagg + ch * FE, faggm ? faggm + ch * FE : nullptr);
+  const typename LN::Lin lin = {a.H, a.c, a.Jc, a.s0, a.s1};
+  LN::fold(cx, k0, k1, lin, fagg + ch * FE, faggm ? faggm + ch * FE : nullptr);
 }
 
 template <int d, int q, bool COMPOSE>
-__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_SCAN_MINBLOCKS)
     k_lane_scan(LeafArgs a, const double* __restrict__ fin, double* __restrict__ kern, double* __restrict__ sagg,
                 double* __restrict__ send, double* __restrict__ part, double* __restrict__ fmeans,
                 double* __restrict__ fchols) {
@@ -57,12 +66,13 @@ __global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
   constexpr int D = LN::D, SE = 2 * D * D + D, ST = D * D + D;
   const long k0 = ch * a.L;
   const long k1 = (k0 + a.L < a.n) ? k0 + a.L : a.n;
-  LN::template scan<COMPOSE>(cx, k0, k1, a.H, a.c, fin + ch * ST, kern, COMPOSE ? sagg + ch * SE : nullptr,
+  const typename LN::Lin lin = {a.H, a.c, a.Jc, a.s0, a.s1};
+  LN::template scan<COMPOSE>(cx, k0, k1, lin, fin + ch * ST, kern, COMPOSE ? sagg + ch * SE : nullptr,
                              send + ch * ST, part + ch * 3, fmeans, fchols);
 }
 
 template <int d, int q>
-__global__ void __launch_bounds__(LANE_WARPS * 32, POF_LANE_MINBLOCKS)
+__global__ void __launch_bounds__(LANE_WARPS * 32, POF_SMOOTH_MINBLOCKS)
     k_lane_smooth(LeafArgs a, const double* __restrict__ sin, const double* __restrict__ kern, int emit_t0,
                   const double* __restrict__ cscale, double* __restrict__ means, double* __restrict__ chols,
                   double* __restrict__ part2) {

@@ -13,8 +13,10 @@ struct LeafArgs {
   long n;    // local number of steps
   long L;    // chunk length
   long CS;   // number of chunks
-  const double* H;
+  const double* H;  // dense linearisation (n,d,D), (n,d) ...
   const double* c;
+  const double* Jc;  // ... or compact: per step [J_f (d x d) | c (d)], H = E1 - J_f E0 rebuilt on load (Jc != null)
+  double s0, s1;     // Nordsieck scalings: E0 = s0 e_0^T, E1 = s1 e_1^T per block
   QLParam ql;
 };
 

@@ -53,6 +53,29 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
     return scalars
 
 
+def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len=None, scalars=None):
+    """One fused IEKS iteration for a built-in IVP (linearise + pass, `pof_ieks_iteration_f64`): the body of the
+    reference's while loop (pof/solver.py:48-55 -> pof/step.py:33-45).  `lin` is `om.f._pof_lin`."""
+    N = means_io.shape[0]
+    d, q = lin["d"], lin["q"]
+    nat.require_cuda(x0.mean, x0.chol, means_io, chols)
+    dev = means_io.device
+    if chunk_len is None:
+        chunk_len = nat.default_chunk_len(N, d, q, dev.index)
+    ws = nat.Workspace.get(N, d, q, chunk_len, dev)
+    if scalars is None:
+        scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+    ivp_id, params = lin["builtin"]
+    ph, pp = nat.host_doubles(list(params) + [0.0])
+    qLh, qLp = nat.host_doubles(qL)
+    rc = nat.LIB.pof_ieks_iteration_f64(
+        nat.stream_ptr(), ivp_id, pp, len(params), N, d, q, int(chunk_len), qLp, lin["scale0"], lin["scale1"],
+        nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(means_io), nat.ptr(chols), int(bool(calibrate)),
+        nat.ptr(scalars), ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+    nat.check(rc, "pof_ieks_iteration_f64")
+    return scalars
+
+
 def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None):
     """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq)"""
     n, d, q, D, qL = _model_dims(linear_transitions, linear_observations)

@@ -7,7 +7,7 @@ import torch
 from . import _native as nat
 from .convenience import get_initial_trajectory, set_up_solver
 from .convergence_criteria import crit_scalars
-from .parallel_filtsmooth import run_pass
+from .parallel_filtsmooth import run_iteration, run_pass
 from .step import linearize_into
 from .utils import MVNSqrt
 
@@ -25,8 +25,9 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
     N, D = means.shape
     n = N - 1
     chols = torch.empty((N, D, D), dtype=torch.float64, device=dev)
-    H = torch.empty((n, d, D), dtype=torch.float64, device=dev)
-    c = torch.empty((n, d), dtype=torch.float64, device=dev)
+    if lin["builtin"] is None:
+        H = torch.empty((n, d, D), dtype=torch.float64, device=dev)
+        c = torch.empty((n, d), dtype=torch.float64, device=dev)
     scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
     if sequential:
         chunk_len = n
@@ -43,8 +44,12 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
                 break
         nll_old, obj_old = nll, obj
         # body: ieks_step (solver.py:48-55); it always calibrates inside the loop (calibrate is not forwarded)
-        linearize_into(lin, means, H, c)
-        run_pass(x0, setup["_qL"], H, c, means, chols, d=d, q=q, calibrate=True, chunk_len=chunk_len, scalars=scalars)
+        if lin["builtin"] is not None:  # fused f / Jacobian + pass, H never materialised
+            run_iteration(x0, setup["_qL"], lin, means, chols, calibrate=True, chunk_len=chunk_len, scalars=scalars)
+        else:  # user f: autodiff linearisation on the device, then the same pass
+            linearize_into(lin, means, H, c)
+            run_pass(x0, setup["_qL"], H, c, means, chols, d=d, q=q, calibrate=True, chunk_len=chunk_len,
+                     scalars=scalars)
         sc = scalars.cpu()
         nll, obj, ssq, n_bad = float(sc[nat.S_NLL]), float(sc[nat.S_OBJ]), float(sc[nat.S_SSQ]), float(
             sc[nat.S_NOT_CLOSE])
