@@ -30,11 +30,23 @@ D_, d_, q_ = 8, 2, 3
 # algorithmic FLOPs per time step per iteration of the REFERENCE formulas at (D, d) = (8, 2)
 FLOP_STEP = 68.5e3
 # attribution to the dominant kernel (filter scan: seeded square-root filter = one filtering combine per step, the
-# innovation statistics, the smoother-element build and one smoothing combine): C_f + O + E_s + C_s  
-FLOP_STEP_SCAN = 21.4e3 + 3.23e3 + 8.1e3 + 3.9e3
-# algorithmic HBM bytes per step of the scan kernel: read H, c (18 doubles), write the step's backward kernel
-# (g, E, D: 136 doubles)
-BYTES_STEP_SCAN = (18 + 136) * 8.0
+# innovation statistics and the smoother-element build): C_f + O + E_s  
+FLOP_STEP_SCAN = 21.4e3 + 3.23e3 + 8.1e3
+# algorithmic HBM bytes per step of the scan kernel: read the compact linearisation [J_f | c] (6 doubles), write the
+# step's backward kernel (g, E, D: 136 doubles)
+BYTES_STEP_SCAN = (6 + 136) * 8.0
+
+
+def measured_traffic(kernel_prefix):
+    """dram bytes per launch of the scan kernel from the committed ncu --set full capture (profiles/), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        for k, v in t.items():
+            if k.startswith(kernel_prefix):
+                return v["dram_bytes_read"] + v["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
 
 
 def parse():
@@ -344,9 +356,11 @@ def run_native(args):
     scan_tflops = FLOP_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
     iter_tflops = FLOP_STEP * n_loc / (ms_iter * 1e-3) / 1e12
     roofline = {
-        "kernel": "k_lane_scan<2,3> (filter scan: seeded square-root filter + backward kernels + innovation statistics)",
+        "kernel": "k_lane_scan<2,3,false> (filter scan: seeded square-root filter + backward kernels + innovation "
+                  "statistics)",
         "bound": "fp64", "achieved": scan_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": (scan_tflops / fp64_peak) if scan_tflops else None, "traffic": None,
+        "frac": (scan_tflops / fp64_peak) if scan_tflops else None,
+        "traffic": measured_traffic("k_lane_scan") if args.n_time == 2**20 else None,
         "peak_source": "DFMA loop measured in this run (pof_measure_dfma_tflops); nominal 37 TFLOP/s",
         "algorithmic_flop_per_step": FLOP_STEP_SCAN, "avg_launch_ms": scan_ms,
         "share_of_step": scan_ms / ms_iter if ms_iter else None,
@@ -355,7 +369,8 @@ def run_native(args):
     roofline_hbm = {
         "kernel": roofline["kernel"], "bound": "hbm", "achieved": BYTES_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e9,
         "peak": hbm_peak, "unit": "GB/s", "frac": BYTES_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e9 / hbm_peak,
-        "traffic": None, "peak_source": hbm_src,
+        "traffic": measured_traffic("k_lane_scan") if args.n_time == 2**20 else None, "peak_source": hbm_src,
+        "algorithmic_bytes_per_step": BYTES_STEP_SCAN,
     }
     roofline_iter = {
         "scope": "whole IEKS iteration (all kernels of a step)", "bound": "fp64", "achieved": iter_tflops,

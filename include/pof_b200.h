@@ -111,6 +111,17 @@ int pof_ieks_iteration_f64(pof_stream_t s, int ivp_id, const double* params_host
                            const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
                            double* scalars, void* ws, size_t ws_bytes);
 
+/* Sequential extended Kalman smoother for a built-in IVP -- replaces
+ *   pof.sequential_filtsmooth.filtsmooth(x0, dtm, om)   pof/sequential_filtsmooth/__init__.py:5-10
+ * (EKF relinearised at the predicted mean of every step, filter.py:9-30, then RTS, smoother.py:8-28), the numerical
+ * core of pof.solver.sequential_eks_solve (solver.py:76-96).  O(N) span by construction: one thread walks the grid
+ * (baseline / cross-check path).  means (N,D), chols (N,D,D): OUT smoothed, uncalibrated.  scalars[POF_S_NLL] holds
+ * +sum log-likelihood like the reference's sequential path (filter.py:91). */
+int pof_sequential_eks_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t N, int d, int q,
+                           const double* qL_host, double scale0, double scale1, const double* x0_mean,
+                           const double* x0_chol, double* means, double* chols, double* scalars, void* ws,
+                           size_t ws_bytes);
+
 /* ---- time-sharded (multi-GPU) form of the same pass: three local stages with two exchange points ----------
  * Rank r owns the contiguous step range [k_lo, k_hi) of the global n steps; H, c are the LOCAL slices
  * (k_hi-k_lo steps) and means/chols/fmeans/fchols the LOCAL rows t in (k_lo, k_hi] (plus row t = 0 on rank 0:

@@ -8,6 +8,7 @@
 
 #include "../../include/pof_b200.h"
 #include "pof_coop.cuh"
+#include "pof_ivp.cuh"
 #include "pof_launch.cuh"
 #include "pof_pipeline.cuh"
 
@@ -206,111 +207,20 @@ __global__ void k_finalize_smooth(const double* __restrict__ sums, double* __res
   scal[POF_S_OBJ] = sums[0];
   scal[POF_S_NOT_CLOSE] = sums[1];
 }
+__global__ void k_finalize_seq(const double* __restrict__ sums, double n, double d, double* __restrict__ scal) {
+  scal[POF_S_NLL] = -sums[0];
+  scal[POF_S_SSQ] = sums[1] / n / d;
+  scal[POF_S_SSQ_PROPER] = sums[2] / n / d;
+  scal[POF_S_OBJ] = sums[3];
+  scal[POF_S_NOT_CLOSE] = 0.0;
+  scal[POF_S_CSCALE] = 1.0;
+}
 __global__ void k_pack_state(int D, const double* __restrict__ m, const double* __restrict__ L,
                              double* __restrict__ st) {
   for (int i = threadIdx.x; i < D + D * D; i += blockDim.x) st[i] = (i < D) ? m[i] : L[i - D];
 }
 
 // ------------------------------------------------------------------------------------------------ linearise
-struct IvpParams {
-  double p[8];
-};
-// vector field f and Jacobian J (row-major dxd) of the built-in problems, reference pof/ivp.py
-__device__ __forceinline__ bool ivp_eval(int id, const IvpParams& P, const double* y, double* f, double* J) {
-  switch (id) {
-    case POF_IVP_LOGISTIC:
-      f[0] = y[0] * (1.0 - y[0]);
-      J[0] = 1.0 - 2.0 * y[0];
-      return true;
-    case POF_IVP_LOTKAVOLTERRA: {
-      const double a = P.p[0], b = P.p[1], c = P.p[2], dd = P.p[3];
-      f[0] = a * y[0] - b * y[0] * y[1];
-      f[1] = -c * y[1] + dd * y[0] * y[1];
-      J[0] = a - b * y[1]; J[1] = -b * y[0];
-      J[2] = dd * y[1];    J[3] = -c + dd * y[0];
-      return true;
-    }
-    case POF_IVP_VANDERPOL: {
-      const double mu = P.p[0];
-      f[0] = y[1];
-      f[1] = mu * ((1.0 - y[0] * y[0]) * y[1] - y[0]);
-      J[0] = 0.0; J[1] = 1.0;
-      J[2] = mu * (-2.0 * y[0] * y[1] - 1.0); J[3] = mu * (1.0 - y[0] * y[0]);
-      return true;
-    }
-    case POF_IVP_FITZHUGHNAGUMO: {
-      const double a = P.p[0], b = P.p[1], tinv = P.p[2], l = P.p[3];
-      f[0] = y[0] - (y[0] * y[0] * y[0]) / 3.0 - y[1] + l;
-      f[1] = tinv * (y[0] + a - b * y[1]);
-      J[0] = 1.0 - y[0] * y[0]; J[1] = -1.0;
-      J[2] = tinv;              J[3] = -tinv * b;
-      return true;
-    }
-    case POF_IVP_ROBER: {
-      const double k1 = P.p[0], k2 = P.p[1], k3 = P.p[2];
-      f[0] = -k1 * y[0] + k3 * y[1] * y[2];
-      f[1] = k1 * y[0] - k2 * y[1] * y[1] - k3 * y[1] * y[2];
-      f[2] = k2 * y[1] * y[1];
-      J[0] = -k1; J[1] = k3 * y[2];                     J[2] = k3 * y[1];
-      J[3] = k1;  J[4] = -2.0 * k2 * y[1] - k3 * y[2];  J[5] = -k3 * y[1];
-      J[6] = 0.0; J[7] = 2.0 * k2 * y[1];               J[8] = 0.0;
-      return true;
-    }
-    case POF_IVP_RIGIDBODY: {
-      const double p0 = P.p[0], p1 = P.p[1], p2 = P.p[2];
-      f[0] = p0 * y[1] * y[2]; f[1] = p1 * y[0] * y[2]; f[2] = p2 * y[0] * y[1];
-      J[0] = 0.0;       J[1] = p0 * y[2]; J[2] = p0 * y[1];
-      J[3] = p1 * y[2]; J[4] = 0.0;       J[5] = p1 * y[0];
-      J[6] = p2 * y[1]; J[7] = p2 * y[0]; J[8] = 0.0;
-      return true;
-    }
-    case POF_IVP_SEIR: {
-      const double p0 = P.p[0], p1 = P.p[1], p2 = P.p[2], p3 = P.p[3];
-      const double inf = p1 * y[0] * y[2] / p3;
-      f[0] = -inf; f[1] = inf - p0 * y[1]; f[2] = p0 * y[1] - p2 * y[2]; f[3] = p2 * y[2];
-      const double i0 = p1 * y[2] / p3, i2 = p1 * y[0] / p3;
-      J[0] = -i0;  J[1] = 0.0;  J[2] = -i2;  J[3] = 0.0;
-      J[4] = i0;   J[5] = -p0;  J[6] = i2;   J[7] = 0.0;
-      J[8] = 0.0;  J[9] = p0;   J[10] = -p2; J[11] = 0.0;
-      J[12] = 0.0; J[13] = 0.0; J[14] = p2;  J[15] = 0.0;
-      return true;
-    }
-    case POF_IVP_THREEBODY: {
-      const double mu = P.p[0], mp = 1.0 - P.p[0];
-      const double a1 = y[0] + mu, a2 = y[0] - mp, y1 = y[1];
-      const double r1s = a1 * a1 + y1 * y1, r2s = a2 * a2 + y1 * y1;
-      const double r1 = sqrt(r1s), r2 = sqrt(r2s);
-      const double i13 = 1.0 / (r1s * r1), i23 = 1.0 / (r2s * r2);
-      const double i15 = i13 / r1s, i25 = i23 / r2s;
-      f[0] = y[2];
-      f[1] = y[3];
-      f[2] = y[0] + 2.0 * y[3] - mp * a1 * i13 - mu * a2 * i23;
-      f[3] = y1 - 2.0 * y[2] - mp * y1 * i13 - mu * y1 * i23;
-      const double cross = 3.0 * mp * a1 * y1 * i15 + 3.0 * mu * a2 * y1 * i25;
-      J[0] = 0.0; J[1] = 0.0; J[2] = 1.0; J[3] = 0.0;
-      J[4] = 0.0; J[5] = 0.0; J[6] = 0.0; J[7] = 1.0;
-      J[8] = 1.0 - mp * (i13 - 3.0 * a1 * a1 * i15) - mu * (i23 - 3.0 * a2 * a2 * i25);
-      J[9] = cross; J[10] = 0.0; J[11] = 2.0;
-      J[12] = cross;
-      J[13] = 1.0 - mp * (i13 - 3.0 * y1 * y1 * i15) - mu * (i23 - 3.0 * y1 * y1 * i25);
-      J[14] = -2.0; J[15] = 0.0;
-      return true;
-    }
-    case POF_IVP_HENONHEILES: {
-      const double p = P.p[0];
-      f[0] = y[2]; f[1] = y[3];
-      f[2] = -y[0] - 2.0 * p * y[0] * y[1];
-      f[3] = -y[1] - p * (y[0] * y[0] - y[1] * y[1]);
-      J[0] = 0.0; J[1] = 0.0; J[2] = 1.0; J[3] = 0.0;
-      J[4] = 0.0; J[5] = 0.0; J[6] = 0.0; J[7] = 1.0;
-      J[8] = -1.0 - 2.0 * p * y[1]; J[9] = -2.0 * p * y[0];       J[10] = 0.0; J[11] = 0.0;
-      J[12] = -2.0 * p * y[0];      J[13] = -1.0 + 2.0 * p * y[1]; J[14] = 0.0; J[15] = 0.0;
-      return true;
-    }
-    default:
-      return false;
-  }
-}
 // one thread per step k: H_k = E1 - J E0, c_k = J y - f(y) at y = E0 m_{k+1}
 __global__ void __launch_bounds__(256)
     k_linearize(int ivp_id, IvpParams P, long n, int d, int q, double scale0, double scale1,
@@ -807,6 +717,36 @@ static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, con
 }
 
 extern "C" {
+
+int pof_sequential_eks_f64(pof_stream_t s_, int ivp_id, const double* params_host, int nparams, int64_t N, int d,
+                           int q, const double* qL_host, double scale0, double scale1, const double* x0_mean,
+                           const double* x0_chol, double* means, double* chols, double* scalars, void* ws_,
+                           size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (N < 2) return POF_E_ARG;
+  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
+  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
+  if (dims[ivp_id] != d || nparams > 8) return POF_E_ARG;
+  const LeafLaunch* ll = thread_launch(d, q);
+  if (!ll || !ll->seq_eks) return POF_E_UNSUPPORTED_DQ;
+  WsLayout wl;
+  wl.build(N - 1, d, q, N - 1);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  LeafArgs a;
+  int rc = make_args(N - 1, d, q, qL_host, nullptr, nullptr, wl, a);
+  if (rc) return rc;
+  a.s0 = scale0;
+  a.s1 = scale1;
+  double p8[8];
+  for (int i = 0; i < 8; ++i) p8[i] = (i < nparams) ? params_host[i] : 0.0;
+  double* x0 = ws + wl.o_misc;
+  k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, x0);
+  POF_CK(ll->seq_eks(s, a, ivp_id, p8, x0, ws + wl.o_kern, means, chols, ws + wl.o_sums));
+  // scalars: NLL slot holds the reference's `ell` = +sum loglik (sequential path sign, filter.py:91)
+  k_finalize_seq<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, scalars);
+  return (int)cudaGetLastError();
+}
 
 int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
                           const double* H, const double* c, double* carry_f, void* ws_, size_t ws_bytes) {

@@ -83,6 +83,14 @@ struct Lane {
   // lane `src` publishes n doubles, every lane of the group reads them
   template <int n>
   static __device__ __forceinline__ void bcast(Ctx& c, const double (&x)[n], int src, double (&out)[n]) {
+#ifndef POF_BCAST_SMEM
+    // register-to-register broadcast (default; measured 2 % faster than the shared-memory slot on B200: the same
+    // crossbar bandwidth, but no store + barrier on the critical path)
+    const int srclane = ((threadIdx.x & 31) / G) * G + src;
+#pragma unroll
+    for (int j = 0; j < n; ++j) out[j] = __shfl_sync(c.mask, x[j], srclane);
+    return;
+#endif
     double2* slot = reinterpret_cast<double2*>(c.bc + c.flip * BC);
     c.flip ^= 1;
     if (c.r == src) {

@@ -117,7 +117,7 @@ struct LaneLaunchers {
     return cudaGetLastError();
   }
   static const LeafLaunch* get() {
-    static const LeafLaunch l = {&fold, &scan, &smooth, Lane<d, q>::GPW, 1};
+    static const LeafLaunch l = {&fold, &scan, &smooth, nullptr, Lane<d, q>::GPW, 1};
     return &l;
   }
 };

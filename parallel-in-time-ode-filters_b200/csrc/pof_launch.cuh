@@ -28,6 +28,9 @@ struct LeafLaunch {
                       double* part, double* fmeans, double* fchols);
   cudaError_t (*smooth)(cudaStream_t, const LeafArgs&, const double* sin, const double* kern, int emit_t0,
                         const double* cscale, double* means, double* chols, double* part2);
+  // sequential extended Kalman smoother relinearised at the predicted mean (one thread; baseline path), or null
+  cudaError_t (*seq_eks)(cudaStream_t, const LeafArgs&, int ivp_id, const double* params8, const double* x0,
+                         double* kern, double* means, double* chols, double* part);
   int chunks_per_warp;
   int has_pre_update;  // 1 if fold can emit faggm and scan can skip the composition  // 32 for the thread-per-chunk kernels, 32/G for the lane-cooperative ones
 };

@@ -1,6 +1,7 @@
 // Leaf kernels: one thread per time-chunk (see pof_pipeline.cuh / pof_leaf.cuh for the math).
 // Included by pof_leaf_d{1,2,3,4}.cu with POF_LEAF_D defined.
 #pragma once
+#include "pof_ivp.cuh"
 #include "pof_launch.cuh"
 #include "pof_pipeline.cuh"
 
@@ -50,8 +51,26 @@ __global__ void __launch_bounds__(LEAF_THREADS)
                       part2 + ch * 2);
 }
 
+// Sequential EKS (reference pof/sequential_filtsmooth/__init__.py:5-10, filter.py:9-30, smoother.py:8-28): extended
+// Kalman filter relinearised at the PREDICTED mean of every step, then the RTS smoother.  Inherently sequential:
+// one thread walks the whole grid (baseline / cross-check path, not a performance path).
+template <int d, int q>
+__global__ void __launch_bounds__(32)
+    k_seq_eks(LeafArgs a, int ivp_id, IvpParams P, const double* __restrict__ x0, double* __restrict__ kern,
+              double* __restrict__ means, double* __restrict__ chols, double* __restrict__ part) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Chunk<d, q>::seq_eks(a.n, a.s0, a.s1, a.ql.v, ivp_id, P, x0, kern, means, chols, part);
+}
+
 template <int d, int q>
 struct LeafLaunchers {
+  static cudaError_t seq_eks(cudaStream_t s, const LeafArgs& a, int ivp_id, const double* params8, const double* x0,
+                             double* kern, double* means, double* chols, double* part) {
+    IvpParams P;
+    for (int i = 0; i < 8; ++i) P.p[i] = params8[i];
+    k_seq_eks<d, q><<<1, 32, 0, s>>>(a, ivp_id, P, x0, kern, means, chols, part);
+    return cudaGetLastError();
+  }
   static unsigned grid(const LeafArgs& a) { return (unsigned)((a.CS + LEAF_THREADS - 1) / LEAF_THREADS); }
   static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg, double* /*faggm*/) {
     k_fold<d, q><<<grid(a), LEAF_THREADS, 0, s>>>(a, fagg);
@@ -68,7 +87,7 @@ struct LeafLaunchers {
     return cudaGetLastError();
   }
   static const LeafLaunch* get() {
-    static const LeafLaunch l = {&fold, &scan, &smooth, 32, 0};
+    static const LeafLaunch l = {&fold, &scan, &smooth, &seq_eks, 32, 0};
     return &l;
   }
 };

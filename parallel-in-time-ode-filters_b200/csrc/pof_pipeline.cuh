@@ -11,6 +11,7 @@
 // so that the 32 threads of a warp (32 consecutive chunks) access consecutive addresses.
 #pragma once
 #include "pof_coop.cuh"
+#include "pof_ivp.cuh"
 #include "pof_leaf.cuh"
 
 namespace pof {
@@ -156,6 +157,77 @@ struct Chunk {
     }
     part[0] = obj;
     part[1] = nconv;
+  }
+
+  // ---- sequential EKS: extended Kalman filter relinearised at the PREDICTED mean of every step, then RTS
+  //      (reference pof/sequential_filtsmooth/__init__.py:5-10, filter.py:9-30, smoother.py:8-28).  kern: (n, NE)
+  //      time-major scratch.  part: [nll, ssq_ref sum, ssq_proper sum, obj].
+  static POF_HD void seq_eks(long n, double s0, double s1, const double* qL, int ivp_id, const IvpParams& P,
+                             const double* __restrict__ x0, double* __restrict__ kern, double* __restrict__ means,
+                             double* __restrict__ chols, double* __restrict__ part) {
+    constexpr int Q1 = q + 1;
+    typename LF::ScanState st;
+    for (int r = 0; r < D; ++r) {
+      st.m[r] = x0[r];
+      for (int j = 0; j < D; ++j) st.Uf[r][j] = x0[D + r * D + j];
+    }
+    double nll = 0.0, a1 = 0.0, a2 = 0.0;
+    for (long k = 0; k < n; ++k) {
+      double mp[D];
+      for (int i = 0; i < D; ++i) mp[i] = st.m[i];
+      LF::mulF_vec(mp);
+      double y[4], f[4], J[16], Hk[d][D], ck[d];
+      for (int b = 0; b < d; ++b) y[b] = s0 * mp[b * Q1];
+      ivp_eval(ivp_id, P, y, f, J);
+      for (int e = 0; e < d; ++e) {
+        double ce = -f[e];
+        for (int j = 0; j < D; ++j) Hk[e][j] = 0.0;
+        for (int b = 0; b < d; ++b) {
+          ce = fma(J[e * d + b], y[b], ce);
+          Hk[e][b * Q1] = -J[e * d + b] * s0;
+        }
+        Hk[e][e * Q1 + 1] += s1;
+        ck[e] = ce;
+      }
+      typename LF::StepOut o;
+      st.step(Hk, ck, qL, o);
+      nll += o.nll;
+      a1 += o.ssq_ref;
+      a2 += o.ssq_proper;
+      double* kp = kern + k * NE;
+      for (int r = 0; r < D; ++r) {
+        kp[r] = o.g[r];
+        for (int e = 0; e < D; ++e) {
+          kp[D + r * D + e] = o.E[r][e];
+          kp[D + D * D + r * D + e] = o.Dk[r][e];
+        }
+      }
+    }
+    house_rows<D, D, D, 1>(st.Uf);
+    typename LF::SmoothState sm;
+    for (int r = 0; r < D; ++r) {
+      sm.m[r] = st.m[r];
+      for (int j = 0; j < D; ++j) sm.L[r][j] = (j <= r) ? st.Uf[r][j] : 0.0;
+    }
+    double obj = 0.0;
+    emit(n, sm, 1.0, means, chols);
+    for (long k = n - 1; k >= 0; --k) {
+      const double* kp = kern + k * NE;
+      double g[D], E[D][D], Dk[D][D];
+      for (int r = 0; r < D; ++r) {
+        g[r] = kp[r];
+        for (int e = 0; e < D; ++e) {
+          E[r][e] = kp[D + r * D + e];
+          Dk[r][e] = kp[D + D * D + r * D + e];
+        }
+      }
+      obj += sm.step(g, E, Dk, qL);
+      emit(k, sm, 1.0, means, chols);
+    }
+    part[0] = nll;
+    part[1] = a1;
+    part[2] = a2;
+    part[3] = obj;
   }
 
   // write one smoothed state in API layout; returns the number of mean entries that fail

@@ -1,0 +1,70 @@
+"""Turn the ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/summarize_ncu.py <launch_list.csv> <full.ncu-rep> <tag>
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+launches, rep, tag = sys.argv[1:4]
+out_dir = "profiles"
+
+# ---- launch list: per-kernel share of one step
+lines = [l for l in open(launches) if not l.startswith("==")]
+rows = list(csv.DictReader(lines))
+names = [r["Kernel Name"] for r in rows]
+folds = [i for i, n in enumerate(names) if "fold" in n]
+start, end = (folds[-2] - 1, folds[-1] - 1) if len(folds) >= 2 else (0, len(rows))
+agg = collections.OrderedDict()
+for r in rows[start:end]:
+    n = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
+    v = float(r["Metric Value"].replace(",", ""))
+    u = r["Metric Unit"]
+    v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
+    agg.setdefault(n, [0, 0.0])
+    agg[n][0] += 1
+    agg[n][1] += v
+tot = sum(v[1] for v in agg.values())
+with open(f"{out_dir}/{tag}_launch_shares.md", "w") as fh:
+    fh.write(f"# {tag}: kernels of ONE IEKS iteration (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n")
+    fh.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
+    fh.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
+    for n, (c, t) in agg.items():
+        fh.write(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |\n")
+    fh.write(f"| **sum** | {sum(v[0] for v in agg.values())} | {tot:.1f} | 100% |\n")
+
+# ---- full capture: key metrics per kernel
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+hdr, units = rr[0], rr[1]
+idx = {h: i for i, h in enumerate(hdr)}
+want = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+seen = {}
+with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as fh:
+    fh.write(f"# {tag}: ncu --set full --clock-control none, first launch of each kernel\n\n")
+    for r in rr[2:]:
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
+        key = (name, r[idx.get("launch__grid_size", 0)])
+        if name in seen:
+            continue
+        seen[name] = 1
+        fh.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---|---|\n")
+        for w in want:
+            if w in idx:
+                fh.write(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |\n")
+        st = [(h, r[i]) for h, i in idx.items() if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h]
+        st = [(h, float(v.replace(",", ""))) for h, v in st if v not in ("", "n/a")]
+        st.sort(key=lambda x: -x[1])
+        fh.write("\nTop stall reasons (warps stalled per issue-active cycle): " + ", ".join(
+            f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}={v:.2f}"
+            for h, v in st[:6]) + "\n\n")
+print("wrote", f"{out_dir}/{tag}_launch_shares.md", f"{out_dir}/{tag}_ncu_full_summary.md")

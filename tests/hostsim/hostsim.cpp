@@ -236,6 +236,21 @@ int hs_smooth_chain(int D, int count, const double* state_in, const double* elem
   std::memcpy(state_out, cur.data(), (D + D * D) * sizeof(double));
   return 0;
 }
+int hs_seq_eks(int d, int q, long N, const double* qL, double s0, double s1, int ivp_id, const double* params8,
+               const double* x0, double* means, double* chols, double* part) {
+  IvpParams P;
+  for (int i = 0; i < 8; ++i) P.p[i] = params8[i];
+  const int D = d * (q + 1);
+  std::vector<double> kern((size_t)(N - 1) * (D + 2 * D * D));
+#define CASE(dd, qq)                                                                                          \
+  if (d == dd && q == qq) {                                                                                   \
+    Chunk<dd, qq>::seq_eks(N - 1, s0, s1, qL, ivp_id, P, x0, kern.data(), means, chols, part);                \
+    return 0;                                                                                                 \
+  }
+  CASE(1, 1) CASE(1, 3) CASE(2, 3) CASE(3, 2)
+#undef CASE
+  return -1;
+}
 int hs_filter_combine(int D, const double* e1, const double* e2, double* out, int state_mode) {
   std::vector<double> smem(coop_ws_doubles(D));
   Warp w;

@@ -241,3 +241,25 @@ def test_sequential_flag_matches_parallel(native_lib):
             assert a.mean.shape[0] == len(ts)
             assert ia["iterations"] == ib["iterations"]
             np.testing.assert_allclose(a.mean.cpu().numpy(), b.mean.cpu().numpy(), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("name,kw,N,q", [("logistic", {}, 21, 1), ("logistic", {}, 21, 3),
+                                         ("fitzhughnagumo", {}, 300, 3), ("rigid_body", {}, 128, 2)])
+def test_sequential_eks_solve_matches_oracle(native_lib, name, kw, N, q):
+    """reference tests/test_solver.py:22-27 (shape) + numbers against the oracle's restatement of solver.py:76-96"""
+    from pof.solver import sequential_eks_solve
+
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    ys, info = sequential_eks_solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    assert ys.mean.shape[0] == len(ts)
+    oys, oinfo = O.sequential_eks_solve(oivp, ts, q)
+    y, yo = ys.mean.cpu().numpy(), oys.mean
+    assert (np.abs(y - yo) <= 1e-9 * np.abs(yo).max(axis=0) + 1e-12).all()
+    s, so = info["sigma_squared"], oinfo["sigma_squared"]
+    C, Co = _cov(ys.chol.cpu().numpy()) / s, _cov(oys.chol) / so
+    assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
+    assert abs(s - so) <= 1e-2 * abs(so)
+    assert abs(info["nll"] - oinfo["nll"]) <= 1e-9 * abs(oinfo["nll"]) + 1e-9
+    full, _ = sequential_eks_solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, return_full_states=True)
+    assert full.mean.shape == (N, ivp.y0.shape[0] * (q + 1))

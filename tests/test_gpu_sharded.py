@@ -1,0 +1,79 @@
+"""Time-sharded pass on real GPUs (NCCL): sharded == single-GPU pass == oracle.  Needs >= 2 GPUs (skipped otherwise)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, N, q, ret):
+    import torch.distributed as dist
+
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "parallel-in-time-ode-filters_b200")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import pof.ivp
+        from pof.convenience import get_initial_trajectory, set_up_solver
+        from pof.parallel_filtsmooth import linear_filtsmooth
+        from pof.sharded import ShardedPass, shard_bounds
+        from pof.step import linearize_at_previous_states
+
+        ivp = pof.ivp.fitzhughnagumo()
+        ts = np.linspace(0, 100, N)
+        setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+        st = get_initial_trajectory(setup, method="constant")
+        dom = linearize_at_previous_states(setup["om"], st)
+        ref, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom)
+        d, D = 2, 2 * (q + 1)
+        k_lo, k_hi = shard_bounds(N - 1, rank, world)
+        r0 = 0 if rank == 0 else k_lo + 1
+        sp = ShardedPass(N, d, q, setup["_qL"], rank=rank, world=world, device=dev)
+        means = st.mean[r0:k_hi + 1].contiguous().clone()
+        chols = torch.zeros((sp.rows, D, D), dtype=torch.float64, device=dev)
+        res = sp.run(setup["x0"].mean, setup["x0"].chol, dom.H[k_lo:k_hi].contiguous(), dom.b[k_lo:k_hi].contiguous(),
+                     means, chols, calibrate=False)
+        torch.cuda.synchronize()
+        em = float((means - ref.mean[r0:k_hi + 1]).abs().max() / ref.mean.abs().max())
+        cov = lambda L: L @ L.transpose(-1, -2)
+        ec = float((cov(chols) - cov(ref.chol[r0:k_hi + 1])).abs().max() / cov(ref.chol).abs().max())
+        ok = (em < 1e-9 and ec < 1e-9 and abs(float(res["nll"]) - float(nll)) <= 1e-9 * abs(float(nll))
+              and abs(float(res["obj"]) - float(obj)) <= 1e-9 * abs(float(obj))
+              and abs(float(res["ssq"]) - float(ssq)) <= 1e-6 * abs(float(ssq)))
+        ret[rank] = (bool(ok), em, ec, float(res["nll"]), float(nll))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,q", [(4097, 3), (100000, 3)])
+def test_sharded_nccl_matches_single_gpu(native_lib, N, q):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, q, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(600) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for r in range(world):
+        assert ret[r][0], ret[r]
