@@ -206,6 +206,16 @@ def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout clean for the ONE JSON line: libraries (e.g. NCCL's version banner) print to fd 1
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
@@ -400,7 +410,7 @@ def run_native(args):
                                                    zip(["nll", "obj", "ssq", "ssq_proper", "not_close"],
                                                        scalars.cpu().tolist()[:5]))},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
