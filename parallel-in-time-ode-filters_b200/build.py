@@ -15,6 +15,7 @@ SOURCES = [
     "pof_api.cu", "pof_leaf_d1.cu", "pof_leaf_d2.cu", "pof_leaf_d3.cu", "pof_leaf_d4.cu",
     "pof_lane_d1.cu", "pof_lane_d2.cu", "pof_lane_d3.cu", "pof_lane_d4.cu",
     "pof_tree_a.cu", "pof_tree_b.cu", "pof_tree_c.cu",
+    "pof_lane2_d1.cu", "pof_lane2_d2.cu", "pof_lane2_d3.cu", "pof_lane2_d4.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

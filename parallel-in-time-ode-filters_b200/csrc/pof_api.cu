@@ -14,6 +14,16 @@
 
 namespace pof {
 
+// register-resident tree sweeps when 2D <= 32 (POF_B200_TREE_IMPL=generic forces the shared-memory kernels)
+static const TreeLaunch* tree_launch(int D) {
+  const char* e = getenv("POF_B200_TREE_IMPL");
+  if (e && e[0] == 'g') return nullptr;
+  const TreeLaunch* t = tree_launch_a(D);
+  if (!t) t = tree_launch_b(D);
+  if (!t) t = tree_launch_c(D);
+  return t;
+}
+
 // thread-per-chunk reference kernels (pof_leaf.cuh)
 static const LeafLaunch* thread_launch(int d, int q) {
   switch (d) {
@@ -35,25 +45,31 @@ static const LeafLaunch* lane_launch(int d, int q) {
     default: return nullptr;
   }
 }
-// POF_B200_LEAF_IMPL=thread selects the reference kernels (debugging / cross-checks); default: lane kernels
+// two rows per lane (pof_lane2.cuh): the default where instantiated (D <= 16)
+static const LeafLaunch* lane2_launch(int d, int q) {
+  switch (d) {
+    case 1: return lane2_launch_d1(q);
+    case 2: return lane2_launch_d2(q);
+    case 3: return lane2_launch_d3(q);
+    case 4: return lane2_launch_d4(q);
+    default: return nullptr;
+  }
+}
+// POF_B200_LEAF_IMPL = thread | lane1 | lane2 selects a kernel family (debugging / cross-checks); default: lane2
+// where available (and the register-resident tree ops are not disabled), else lane1, else thread
 const LeafLaunch* leaf_launch(int d, int q) {
   const char* e = getenv("POF_B200_LEAF_IMPL");
   const bool want_thread = e && e[0] == 't';
+  const bool want_lane1 = e && e[0] == 'l' && e[1] == 'a' && e[2] == 'n' && e[3] == 'e' && e[4] == '1';
   if (!want_thread) {
+    if (!want_lane1 && tree_launch(d * (q + 1)) != nullptr) {
+      const LeafLaunch* l2 = lane2_launch(d, q);
+      if (l2) return l2;
+    }
     const LeafLaunch* l = lane_launch(d, q);
     if (l) return l;
   }
   return thread_launch(d, q);
-}
-
-// register-resident tree sweeps when 2D <= 32 (POF_B200_TREE_IMPL=generic forces the shared-memory kernels)
-static const TreeLaunch* tree_launch(int D) {
-  const char* e = getenv("POF_B200_TREE_IMPL");
-  if (e && e[0] == 'g') return nullptr;
-  const TreeLaunch* t = tree_launch_a(D);
-  if (!t) t = tree_launch_b(D);
-  if (!t) t = tree_launch_c(D);
-  return t;
 }
 
 constexpr int TREE_WARPS = 4;  // max warps (= element pairs) per CTA in the tree kernels; fewer when D is large

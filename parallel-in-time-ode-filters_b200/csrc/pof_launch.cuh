@@ -46,6 +46,11 @@ const LeafLaunch* lane_launch_d1(int q);
 const LeafLaunch* lane_launch_d2(int q);
 const LeafLaunch* lane_launch_d3(int q);
 const LeafLaunch* lane_launch_d4(int q);
+// two rows per lane (pof_lane2.cuh); null where not instantiated
+const LeafLaunch* lane2_launch_d1(int q);
+const LeafLaunch* lane2_launch_d2(int q);
+const LeafLaunch* lane2_launch_d3(int q);
+const LeafLaunch* lane2_launch_d4(int q);
 
 // register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> generic shared-memory kernels
 struct TreeLaunch {

@@ -43,7 +43,7 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["lane", "thread"])
+@pytest.fixture(params=["lane2", "lane1", "thread"])
 def leaf_impl(request, monkeypatch):
     """Both leaf-kernel families: the lane-cooperative performance kernels and the thread-per-chunk reference ones."""
     monkeypatch.setenv("POF_B200_LEAF_IMPL", request.param)
