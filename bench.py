@@ -366,11 +366,11 @@ def run_native(args):
     scan_tflops = FLOP_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
     iter_tflops = FLOP_STEP * n_loc / (ms_iter * 1e-3) / 1e12
     roofline = {
-        "kernel": "k_lane_scan<2,3,false> (filter scan: seeded square-root filter + backward kernels + innovation "
+        "kernel": "k_lane2_scan<2,3> (filter scan: seeded square-root filter + backward kernels + innovation "
                   "statistics)",
         "bound": "fp64", "achieved": scan_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": (scan_tflops / fp64_peak) if scan_tflops else None,
-        "traffic": measured_traffic("k_lane_scan") if args.n_time == 2**20 else None,
+        "traffic": measured_traffic("k_lane2_scan") if args.n_time == 2**20 else None,
         "peak_source": "DFMA loop measured in this run (pof_measure_dfma_tflops); nominal 37 TFLOP/s",
         "algorithmic_flop_per_step": FLOP_STEP_SCAN, "avg_launch_ms": scan_ms,
         "share_of_step": scan_ms / ms_iter if ms_iter else None,
@@ -379,7 +379,7 @@ def run_native(args):
     roofline_hbm = {
         "kernel": roofline["kernel"], "bound": "hbm", "achieved": BYTES_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e9,
         "peak": hbm_peak, "unit": "GB/s", "frac": BYTES_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e9 / hbm_peak,
-        "traffic": measured_traffic("k_lane_scan") if args.n_time == 2**20 else None, "peak_source": hbm_src,
+        "traffic": measured_traffic("k_lane2_scan") if args.n_time == 2**20 else None, "peak_source": hbm_src,
         "algorithmic_bytes_per_step": BYTES_STEP_SCAN,
     }
     roofline_iter = {

@@ -361,8 +361,7 @@ static inline int tree_smem_bytes(int D) { return tree_warps(D) * coop_ws_double
 
 template <class K>
 static cudaError_t set_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return cudaSuccess;
+  return ensure_smem(kernel, bytes);
 }
 
 // ---- optional per-segment device timing (used by bench.py for the roofline numbers): CUDA events recorded on the

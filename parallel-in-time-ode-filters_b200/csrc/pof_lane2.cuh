@@ -53,7 +53,7 @@ struct Lane2 {
     unsigned mask;
     double* mat;       // 2 exchange matrices
     double* vec;       // 2 gather vectors
-    double* tq;        // this lane's rows of QL: tq[s*D + j]
+    double* tq;        // this lane's rows of QL, lane-minor: tq[(s*D + j)*G] (conflict-free across the group)
     int vflip;
     double cf[R][Q1];  // Pascal coefficients of the owned rows of F
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
@@ -65,7 +65,7 @@ struct Lane2 {
     c.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
     c.mat = sm_group;
     c.vec = sm_group + 2 * D * LDM;
-    c.tq = c.vec + 2 * VEC + c.l * (R * D);
+    c.tq = c.vec + 2 * VEC + c.l;
     c.vflip = 0;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -87,7 +87,7 @@ struct Lane2 {
 #pragma unroll
         for (int b = 0; b < Q1; ++b)
           if (c.rb[s] == b && (j / Q1) * Q1 == c.blk0[s] && (j % Q1) <= b) v = qL[b * Q1 + (j % Q1)];
-        c.tq[s * D + j] = (c.row[s] < D) ? v : 0.0;
+        c.tq[(s * D + j) * G] = (c.row[s] < D) ? v : 0.0;
       }
     }
     c.sync();
@@ -196,7 +196,7 @@ struct Lane2 {
 #pragma unroll
     for (int s = 0; s < R; ++s) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) t[s][j] = c.tq[s * D + j];
+      for (int j = 0; j < D; ++j) t[s][j] = c.tq[(s * D + j) * G];
     }
   }
 

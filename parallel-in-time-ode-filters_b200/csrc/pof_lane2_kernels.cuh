@@ -85,9 +85,7 @@ struct Lane2Launchers {
   using LS = Lane2Setup<d, q>;
   template <class K>
   static cudaError_t prep(K kernel) {
-    if (LS::smem_bytes() > 48 * 1024)
-      return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS::smem_bytes());
-    return cudaSuccess;
+    return ensure_smem(kernel, LS::smem_bytes());
   }
   static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg, double* faggm) {
     if (cudaError_t e = prep(k_lane2_fold<d, q>)) return e;

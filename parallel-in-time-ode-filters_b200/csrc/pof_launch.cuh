@@ -5,6 +5,36 @@
 
 namespace pof {
 
+// Raise a kernel's dynamic shared-memory limit ONCE per (kernel, device): cudaFuncSetAttribute is a driver call of
+// several microseconds, and calling it on every launch made the tiny tree kernels launch-bound.
+struct SmemCache {
+  static constexpr int CAP = 1024;
+  const void* fn[CAP];
+  int dev[CAP], bytes[CAP], n = 0;
+};
+inline SmemCache& smem_cache() {
+  static SmemCache c;
+  return c;
+}
+template <class K>
+inline cudaError_t ensure_smem(K kernel, int bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SmemCache& c = smem_cache();
+  const void* key = (const void*)kernel;
+  for (int i = 0; i < c.n; ++i)
+    if (c.fn[i] == key && c.dev[i] == dev && c.bytes[i] >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && c.n < SmemCache::CAP) {
+    c.fn[c.n] = key;
+    c.dev[c.n] = dev;
+    c.bytes[c.n] = bytes;
+    ++c.n;
+  }
+  return e;
+}
+
 struct QLParam {
   double v[36];  // (q+1) x (q+1) row-major, q <= 5; lives in the kernel-parameter constant bank
 };
