@@ -420,7 +420,9 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
 }
 
 // stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
-static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws) {
+// need_root: the tree's root element is only consumed by the time-sharded form (it is the shard's carry)
+static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
+                   bool need_root) {
   double* fagg = ws + wl.o_fagg;
   const bool pre = ll->has_pre_update && tree_launch(wl.D) != nullptr;
   {
@@ -433,7 +435,7 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_up, smem));
   const TreeLaunch* tl = tree_launch(wl.D);
-  for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
+  for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l) {
     const long np = wl.tl.sz[l + 1];
     if (tl)
       POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE, np));
@@ -445,7 +447,7 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
 }
 // stage B: filter down-sweep from the root's incoming state (already stored at fin[root]), scan, smoother up-sweep
 static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
-                   double* fmeans, double* fchols) {
+                   double* fmeans, double* fchols, bool need_root) {
   double* fagg = ws + wl.o_fagg;
   double* fin = ws + wl.o_fin;
   double* sagg = ws + wl.o_sagg;
@@ -477,7 +479,7 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   // chunk-level smoothing elements straight from (incoming state, filtering element before its last update)
   if (pre) POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
   ProfScope ps(SEG_SUP, s);
-  for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
+  for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l) {
     const long np = wl.tl.sz[l + 1];
     if (tl)
       POF_CK(tl->sup(s, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE, np));
@@ -559,8 +561,10 @@ int pof_profile_read(double* ms_out, int64_t* count_out) {
 int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  return 3 /*leaf*/ + 4 * (int64_t)(wl.tl.nlev - 1) /*tree sweeps*/ + 1 /*chunk smoothing elements*/ + 1 /*pack*/ +
-         2 /*reduce*/ + 2 /*finalize*/;
+  const int64_t downs = 2 * (int64_t)(wl.tl.nlev - 1);
+  const int64_t ups = 2 * (int64_t)(wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0);  // the root combine is skipped on one GPU
+  return 3 /*leaf*/ + downs + ups /*tree sweeps*/ + 1 /*chunk smoothing elements*/ + 1 /*pack*/ + 2 /*reduce*/ +
+         2 /*finalize*/;
 }
 
 // FP64 FMA throughput of this device (TFLOP/s), measured with a register-resident DFMA loop: the roofline
@@ -711,7 +715,7 @@ int pof_ieks_iteration_f64(pof_stream_t s_, int ivp_id, const double* params_hos
 static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws, int64_t N,
                     int d, const double* x0_mean, const double* x0_chol, double* means, double* chols,
                     double* fmeans, double* fchols, int calibrate, double* scalars) {
-  int rc = stage_a(s, ll, a, wl, ws);
+  int rc = stage_a(s, ll, a, wl, ws, false);
   if (rc) return rc;
   // root's incoming state = x0
   k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
@@ -719,7 +723,7 @@ static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, con
     POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
     POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
-  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols);
+  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, false);
   if (rc) return rc;
   k_finalize_filter<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, calibrate, scalars);
   // terminal smoothing state = filtered state at the last time point
@@ -776,7 +780,7 @@ int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
   LeafArgs a;
   int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
   if (rc) return rc;
-  rc = stage_a(s, ll, a, wl, ws);
+  rc = stage_a(s, ll, a, wl, ws, true);
   if (rc) return rc;
   POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(double),
                          cudaMemcpyDeviceToDevice, s));
@@ -798,7 +802,7 @@ int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
   if (rc) return rc;
   POF_CK(cudaMemcpyAsync(ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, state_in, wl.ST * sizeof(double),
                          cudaMemcpyDeviceToDevice, s));
-  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols);
+  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, true);
   if (rc) return rc;
   POF_CK(cudaMemcpyAsync(carry_s, ws + wl.o_sagg + wl.tl.off[wl.tl.nlev - 1] * wl.SE, wl.SE * sizeof(double),
                          cudaMemcpyDeviceToDevice, s));

@@ -265,3 +265,62 @@ def test_sequential_eks_solve_matches_oracle(native_lib, name, kw, N, q):
     assert abs(info["nll"] - oinfo["nll"]) <= 1e-9 * abs(oinfo["nll"]) + 1e-9
     full, _ = sequential_eks_solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, return_full_states=True)
     assert full.mean.shape == (N, ivp.y0.shape[0] * (q + 1))
+
+
+@pytest.mark.parametrize("N,L", [(2, None), (3, None), (5, 1), (9, 100), (33, 4), (257, 8)])
+def test_edge_sizes(native_lib, leaf_impl, N, L):
+    """tiny grids, chunk length 1, chunk longer than the grid, ragged last chunk"""
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+
+    ivp, oivp = _pair("lotkavolterra")
+    ts = np.linspace(0.0, 0.05 * (N - 1), N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=2)
+    st = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], st)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    osetup = O.set_up_solver(oivp, ts, 2)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    oout, onll, oobj, ossq, _ = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom)
+    np.testing.assert_allclose(out.mean.cpu().numpy(), oout.mean, rtol=0, atol=1e-9 * np.abs(oout.mean).max())
+    C, Co = _cov(out.chol.cpu().numpy()), _cov(oout.chol)
+    np.testing.assert_allclose(C, Co, rtol=0, atol=1e-9 * max(np.abs(Co).max(), 1e-300))
+    assert abs(float(nll) - onll) <= 1e-9 * abs(onll) + 1e-9
+    assert abs(float(obj) - oobj) <= 1e-9 * abs(oobj) + 1e-12
+
+
+def test_nan_propagates_and_stops_the_loop(native_lib):
+    """divergence handling of the reference: NaNs propagate, crit() reports convergence so the loop exits
+    (convergence_criteria.py:6,13)"""
+    import pof.ivp
+    from pof.solver import solve
+
+    ivp = pof.ivp.logistic(y0=[float("nan")])
+    ys, info = solve(f=ivp.f, y0=ivp.y0, ts=np.linspace(0, 1, 20), order=2, init="constant", maxiters=50)
+    assert info["iterations"] == 1
+    assert torch.isnan(ys.mean[1:]).any()
+
+
+def test_dense_H_seam_matches_fused_iteration(native_lib):
+    """S3 seam (dense H, c arrays) and the fused built-in-IVP iteration (compact linearisation) give the same pass"""
+    import pof.ivp
+    from pof import _native as nat
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import run_iteration, run_pass
+    from pof.step import linearize_at_previous_states
+
+    ivp = pof.ivp.fitzhughnagumo()
+    ts = np.linspace(0, 100, 5000)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=3)
+    st = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], st)
+    m1, m2 = st.mean.clone(), st.mean.clone()
+    c1, c2 = torch.empty((5000, 8, 8), dtype=torch.float64, device="cuda"), torch.empty((5000, 8, 8), dtype=torch.float64, device="cuda")
+    s1 = run_pass(setup["x0"], setup["_qL"], dom.H, dom.b, m1, c1, d=2, q=3, calibrate=True).clone()
+    s2 = run_iteration(setup["x0"], setup["_qL"], setup["om"].f._pof_lin, m2, c2, calibrate=True).clone()
+    np.testing.assert_allclose(m1.cpu().numpy(), m2.cpu().numpy(), rtol=0, atol=1e-11 * float(m1.abs().max()))
+    np.testing.assert_allclose(s1.cpu().numpy()[:4], s2.cpu().numpy()[:4], rtol=1e-10)
+    np.testing.assert_allclose(_cov(c1.cpu().numpy()), _cov(c2.cpu().numpy()), rtol=0,
+                               atol=1e-10 * float(_cov(c1.cpu().numpy()).max()))
