@@ -141,6 +141,17 @@ int pof_shard_stage_a_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t c
 int pof_shard_stage_b_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
                           const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
                           double* carry_s, double* state_end, double* partials, void* ws, size_t ws_bytes);
+/* the same two stages reading the compact linearisation [J_f | c] (n_loc, d*d+d) written by
+ * pof_linearize_ivp_compact_f64 instead of dense (H, c) */
+int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
+                                  int q, double scale0, const double* means_t1, double* Jc);
+int pof_shard_stage_a_compact_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                                  const double* Jc, double scale0, double scale1, double* carry_f, void* ws,
+                                  size_t ws_bytes);
+int pof_shard_stage_b_compact_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                                  const double* Jc, double scale0, double scale1, const double* state_in,
+                                  double* fmeans, double* fchols, double* carry_s, double* state_end, double* partials,
+                                  void* ws, size_t ws_bytes);
 int pof_shard_stage_c_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
                           const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,
                           double* chols, double* partials2, void* ws, size_t ws_bytes);

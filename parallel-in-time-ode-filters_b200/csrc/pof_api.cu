@@ -654,6 +654,20 @@ static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, con
                     int d, const double* x0_mean, const double* x0_chol, double* means, double* chols,
                     double* fmeans, double* fchols, int calibrate, double* scalars);
 
+int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
+                                  int q, double scale0, const double* means_t1, double* Jc) {
+  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
+  if (d < 1 || d > 4 || nparams > 8) return POF_E_ARG;
+  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
+  if (dims[ivp_id] != d) return POF_E_ARG;
+  IvpParams P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
+  if (n <= 0) return 0;
+  k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, means_t1,
+                                                                                Jc);
+  return (int)cudaGetLastError();
+}
+
 int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
                               const double* x0_mean, const double* x0_chol, const double* H, const double* c,
                               double* means, double* chols, double* fmeans, double* fchols, int calibrate,
@@ -767,9 +781,43 @@ int pof_sequential_eks_f64(pof_stream_t s_, int ivp_id, const double* params_hos
   return (int)cudaGetLastError();
 }
 
+static int shard_a(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                   const double* H, const double* c, const double* Jc, double s0, double s1, double* carry_f,
+                   void* ws_, size_t ws_bytes);
+static int shard_b(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                   const double* H, const double* c, const double* Jc, double s0, double s1, const double* state_in,
+                   double* fmeans, double* fchols, double* carry_s, double* state_end, double* partials, void* ws_,
+                   size_t ws_bytes);
+
 int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
                           const double* H, const double* c, double* carry_f, void* ws_, size_t ws_bytes) {
-  cudaStream_t s = (cudaStream_t)s_;
+  return shard_a((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, carry_f, ws_, ws_bytes);
+}
+int pof_shard_stage_a_compact_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len,
+                                  const double* qL_host, const double* Jc, double scale0, double scale1,
+                                  double* carry_f, void* ws_, size_t ws_bytes) {
+  return shard_a((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1, carry_f, ws_,
+                 ws_bytes);
+}
+int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                          const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
+                          double* carry_s, double* state_end, double* partials, void* ws_, size_t ws_bytes) {
+  return shard_b((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, state_in, fmeans, fchols,
+                 carry_s, state_end, partials, ws_, ws_bytes);
+}
+int pof_shard_stage_b_compact_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len,
+                                  const double* qL_host, const double* Jc, double scale0, double scale1,
+                                  const double* state_in, double* fmeans, double* fchols, double* carry_s,
+                                  double* state_end, double* partials, void* ws_, size_t ws_bytes) {
+  return shard_b((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1, state_in,
+                 fmeans, fchols, carry_s, state_end, partials, ws_, ws_bytes);
+}
+
+}  // extern "C"
+
+static int shard_a(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                   const double* H, const double* c, const double* Jc, double s0, double s1, double* carry_f,
+                   void* ws_, size_t ws_bytes) {
   if (n_loc < 1) return POF_E_ARG;
   const LeafLaunch* ll = leaf_launch(d, q);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
@@ -780,6 +828,12 @@ int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
   LeafArgs a;
   int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
   if (rc) return rc;
+  if (Jc) {
+    if (!ll->has_pre_update) return POF_E_ARG;  // only the lane kernels read the compact form
+    a.Jc = Jc;
+    a.s0 = s0;
+    a.s1 = s1;
+  }
   rc = stage_a(s, ll, a, wl, ws, true);
   if (rc) return rc;
   POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(double),
@@ -787,10 +841,10 @@ int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
   return 0;
 }
 
-int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                          const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
-                          double* carry_s, double* state_end, double* partials, void* ws_, size_t ws_bytes) {
-  cudaStream_t s = (cudaStream_t)s_;
+static int shard_b(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+                   const double* H, const double* c, const double* Jc, double s0, double s1, const double* state_in,
+                   double* fmeans, double* fchols, double* carry_s, double* state_end, double* partials, void* ws_,
+                   size_t ws_bytes) {
   const LeafLaunch* ll = leaf_launch(d, q);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
@@ -800,6 +854,12 @@ int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
   LeafArgs a;
   int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
   if (rc) return rc;
+  if (Jc) {
+    if (!ll->has_pre_update) return POF_E_ARG;
+    a.Jc = Jc;
+    a.s0 = s0;
+    a.s1 = s1;
+  }
   POF_CK(cudaMemcpyAsync(ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, state_in, wl.ST * sizeof(double),
                          cudaMemcpyDeviceToDevice, s));
   rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, true);
@@ -811,6 +871,8 @@ int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
   POF_CK(cudaMemcpyAsync(partials, ws + wl.o_sums, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
+
+extern "C" {
 
 int pof_shard_stage_c_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
                           const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,

@@ -62,6 +62,13 @@ def _load():
         "pof_shard_stage_b_f64": (
             _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
                      _c_dp, _c_dp, _c_sz]),
+        "pof_linearize_ivp_compact_f64": (
+            _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp]),
+        "pof_shard_stage_a_compact_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_b_compact_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_dp, _c_sz]),
         "pof_shard_stage_c_f64": (
             _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp,
                      _c_dp, _c_sz]),
@@ -85,7 +92,8 @@ EXPORTED = [
     "pof_supported", "pof_default_chunk_len", "pof_workspace_bytes", "pof_filter_combine_f64",
     "pof_smooth_combine_f64", "pof_linearize_ivp_f64", "pof_linear_filtsmooth_f64", "pof_ieks_iteration_f64", "pof_sequential_eks_f64",
     "pof_shard_stage_a_f64",
-    "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
+    "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_linearize_ivp_compact_f64",
+    "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
     "pof_project_f64", "pof_profile_enable", "pof_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops",
 ]
 

@@ -47,13 +47,31 @@ class CudaBackend:
     def _ws(self):
         return ctypes.c_void_p(self.ws.buf.data_ptr()), self.ws.nbytes
 
+    def set_compact(self, scale0, scale1):
+        """H arguments of stage_a/b are then the compact linearisation [J_f | c] (c must be None)"""
+        self.scales = (float(scale0), float(scale1))
+
     def stage_a(self, H, c, carry_f):
         p, nb = self._ws()
+        if c is None:
+            s0, s1 = self.scales
+            nat.check(nat.LIB.pof_shard_stage_a_compact_f64(nat.stream_ptr(), self.n_loc, self.d, self.q,
+                                                            self.chunk_len, self.qLp, nat.ptr(H), s0, s1,
+                                                            nat.ptr(carry_f), p, nb), "stage_a")
+            return
         nat.check(nat.LIB.pof_shard_stage_a_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
                                                 nat.ptr(H), nat.ptr(c), nat.ptr(carry_f), p, nb), "stage_a")
 
     def stage_b(self, H, c, state_in, fmeans, fchols, carry_s, state_end, partials):
         p, nb = self._ws()
+        if c is None:
+            s0, s1 = self.scales
+            nat.check(nat.LIB.pof_shard_stage_b_compact_f64(nat.stream_ptr(), self.n_loc, self.d, self.q,
+                                                            self.chunk_len, self.qLp, nat.ptr(H), s0, s1,
+                                                            nat.ptr(state_in), nat.ptr(fmeans), nat.ptr(fchols),
+                                                            nat.ptr(carry_s), nat.ptr(state_end), nat.ptr(partials), p,
+                                                            nb), "stage_b")
+            return
         nat.check(nat.LIB.pof_shard_stage_b_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
                                                 nat.ptr(H), nat.ptr(c), nat.ptr(state_in), nat.ptr(fmeans),
                                                 nat.ptr(fchols), nat.ptr(carry_s), nat.ptr(state_end),

@@ -7,7 +7,7 @@ import torch
 from . import _native as nat
 from .convenience import get_initial_trajectory, set_up_solver
 from .convergence_criteria import crit_scalars
-from .parallel_filtsmooth import run_iteration, run_pass
+from .parallel_filtsmooth import GraphedIteration, run_pass
 from .step import linearize_into
 from .utils import MVNSqrt
 
@@ -37,6 +37,7 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
     nll = obj = ssq = 0.0
     nll_old = obj_old = 0.0
     k = 0
+    fused = None
     while True:
         if k >= 1:
             converged = crit_scalars(obj, obj_old, nll, nll_old, n_bad)
@@ -44,8 +45,13 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
                 break
         nll_old, obj_old = nll, obj
         # body: ieks_step (solver.py:48-55); it always calibrates inside the loop (calibrate is not forwarded)
-        if lin["builtin"] is not None:  # fused f / Jacobian + pass, H never materialised
-            run_iteration(x0, setup["_qL"], lin, means, chols, calibrate=True, chunk_len=chunk_len, scalars=scalars)
+        if lin["builtin"] is not None:  # fused f / Jacobian + pass, H never materialised; graph-replayed
+            if fused is None:
+                fused = GraphedIteration(x0, setup["_qL"], lin, means, chols, scalars, calibrate=True,
+                                         chunk_len=chunk_len)
+            elif fused.graph is None and k >= 1:
+                fused.capture()  # note: capturing runs no kernels; the replay below is iteration k+1
+            fused()
         else:  # user f: autodiff linearisation on the device, then the same pass
             linearize_into(lin, means, H, c)
             run_pass(x0, setup["_qL"], H, c, means, chols, d=d, q=q, calibrate=True, chunk_len=chunk_len,
