@@ -35,8 +35,13 @@ struct Lane2 {
   // per-group shared memory (doubles): two row-exchange matrices, two gather vectors, this group's rows of QL
   static constexpr int LDM = D + 1;
   static constexpr int VEC = ((D + 1) / 2) * 2;
-  static constexpr int RAW = 2 * D * LDM + 2 * VEC + R * G * D;
-  static constexpr int SM_GROUP = RAW + ((2 - (RAW % 16)) + 16) % 16;
+  static constexpr int NJ = d * d + d;                 // compact linearisation of a step: [J_f | c]
+  static constexpr int NJP = ((NJ + 1) / 2) * 2;
+  static constexpr int RAW = 2 * D * LDM + 2 * VEC + R * G * D + 2 * NJP;  // ... + 2 staging slots for [J_f | c]
+  // 64-bit shared accesses are served per half-warp (16 lanes = 16/G groups): the group stride must spread those
+  // groups over the 16 eight-byte banks, i.e. SM_GROUP == G (mod 16) (with odd LDM the rows of a group then fall into
+  // distinct banks as well).  ncu before: 2x excess wavefronts on every STS and on the column reads (stride == 2).
+  static constexpr int SM_GROUP = RAW + (((G % 16) - (RAW % 16)) + 16) % 16;
 
   struct Lin {
     const double* __restrict__ H;
@@ -54,6 +59,7 @@ struct Lane2 {
     double* mat;       // 2 exchange matrices
     double* vec;       // 2 gather vectors
     double* tq;        // this lane's rows of QL, lane-minor: tq[(s*D + j)*G] (conflict-free across the group)
+    double* lbuf;      // 2 x NJP doubles: compact linearisations staged by cp.async (global -> shared, no registers)
     int vflip;
     double cf[R][Q1];  // Pascal coefficients of the owned rows of F
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
@@ -66,6 +72,7 @@ struct Lane2 {
     c.mat = sm_group;
     c.vec = sm_group + 2 * D * LDM;
     c.tq = c.vec + 2 * VEC + c.l;
+    c.lbuf = c.vec + 2 * VEC + R * G * D;
     c.vflip = 0;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -111,15 +118,48 @@ struct Lane2 {
     e = fma(-hx * r, r, 0.5);
     return fma(r, e, r);
   }
+  // sum_j a[j]*b[j] with several independent accumulators: the leaf recursions are bound by dependent-issue latency
+  // ("wait" stalls with 2 warps per scheduler), so every long FMA chain is split and tree-added
+  template <int n>
+  static __device__ __forceinline__ double dotn(const double* a, const double* b) {
+    if constexpr (n <= 0) {
+      return 0.0;
+    } else if constexpr (n < 4) {
+      double s = a[0] * b[0];
+#pragma unroll
+      for (int j = 1; j < n; ++j) s = fma(a[j], b[j], s);
+      return s;
+    } else if constexpr (n < 10) {
+      double s0 = a[0] * b[0], s1 = a[1] * b[1];
+#pragma unroll
+      for (int j = 2; j + 1 < n; j += 2) {
+        s0 = fma(a[j], b[j], s0);
+        s1 = fma(a[j + 1], b[j + 1], s1);
+      }
+      if constexpr (n % 2) s0 = fma(a[n - 1], b[n - 1], s0);
+      return s0 + s1;
+    } else {
+      double s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
+#pragma unroll
+      for (int j = 4; j + 3 < n; j += 4) {
+        s0 = fma(a[j], b[j], s0);
+        s1 = fma(a[j + 1], b[j + 1], s1);
+        s2 = fma(a[j + 2], b[j + 2], s2);
+        s3 = fma(a[j + 3], b[j + 3], s3);
+      }
+      if constexpr (n % 4 >= 1) s0 = fma(a[n - n % 4], b[n - n % 4], s0);
+      if constexpr (n % 4 >= 2) s1 = fma(a[n - n % 4 + 1], b[n - n % 4 + 1], s1);
+      if constexpr (n % 4 >= 3) s2 = fma(a[n - n % 4 + 2], b[n - n % 4 + 2], s2);
+      return (s0 + s1) + (s2 + s3);
+    }
+  }
   struct HH {
     double s, tp, beta;
   };
   // Householder for the row (alpha, x[0..n)):  H = I - tp v v^T, v = (s, x), H (alpha, x)^T = (beta, 0)
   template <int n>
   static __device__ __forceinline__ HH house(double alpha, const double* x) {
-    double sigma = 0.0;
-#pragma unroll
-    for (int j = 0; j < n; ++j) sigma = fma(x[j], x[j], sigma);
+    const double sigma = dotn<n>(x, x);
     const bool nz = sigma > 0.0;
     const double nrm2 = fma(alpha, alpha, sigma);
     const double rn = fast_rsqrt(nrm2);
@@ -131,6 +171,9 @@ struct Lane2 {
     h.s = nz ? s : 0.0;
     h.tp = nz ? rn * fast_rcp(fabs(s)) : 0.0;
     return h;
+  }
+  static __device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
   }
   static __device__ __forceinline__ double bshfl(const Ctx& c, double x, int src) {
     return __shfl_sync(c.mask, x, ((threadIdx.x & 31) / G) * G + src);
@@ -222,9 +265,7 @@ struct Lane2 {
       if constexpr (PASS) {
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-          double u = h.s * pt[s][I];
-#pragma unroll
-          for (int j = 0; j < K; ++j) u = fma(pc[s][J0 + j], piv[1 + j], u);
+          double u = fma(h.s, pt[s][I], dotn<K>(&pc[s][J0], piv + 1));
           u *= h.tp;
           pt[s][I] = fma(-u, h.s, pt[s][I]);
 #pragma unroll
@@ -238,9 +279,7 @@ struct Lane2 {
   static __device__ __forceinline__ void row_update(const Ctx& cx, const HH& h, const double* piv, double (&t)[R][D],
                                                     double (&c)[R][D]) {
     if constexpr (S * G + G - 1 >= I) {  // some row of this slot is at or below the pivot
-      double w = h.s * t[S][I];
-#pragma unroll
-      for (int j = 0; j < K; ++j) w = fma(c[S][J0 + j], piv[1 + j], w);
+      double w = fma(h.s, t[S][I], dotn<K>(&c[S][J0], piv + 1));  // the dot does not wait for the reflector
       w = (cx.row[S] >= I) ? w * h.tp : 0.0;
       t[S][I] = (cx.row[S] == I) ? h.beta : fma(-w, h.s, t[S][I]);
 #pragma unroll
@@ -260,9 +299,7 @@ struct Lane2 {
                                                      double (&x)[R][D]) {
     if constexpr (S * G + G - 1 >= I) {
       constexpr int n = D - J0 - I;
-      double w = h.s * x[S][J0 + I];
-#pragma unroll
-      for (int j = 1; j < n; ++j) w = fma(x[S][J0 + I + j], piv[j], w);
+      double w = fma(h.s, x[S][J0 + I], dotn<n - 1>(&x[S][J0 + I + 1], piv + 1));
       w = (cx.row[S] >= I) ? w * h.tp : 0.0;
       x[S][J0 + I] = (cx.row[S] == I) ? h.beta : fma(-w, h.s, x[S][J0 + I]);
 #pragma unroll
@@ -320,6 +357,58 @@ struct Lane2 {
       o.Hd = L.H + k * d * D;
     }
   }
+  // bring the linearisation of step k into L2 (the load itself sits next to its use: held in registers across the
+  // prediction QR it was spilled right after the load, which exposed the full DRAM latency -- ncu: STL on long_sb)
+  static __device__ __forceinline__ void prefetch_lin(const Lin& L, long k) {
+    if (L.Jc) {
+      const double* p = L.Jc + k * (d * d + d);
+      prefetch_l2(p);
+      prefetch_l2(p + (d * d + d) - 1);
+    } else {
+      prefetch_l2(L.c + k * d);
+      prefetch_l2(L.H + k * d * D);
+      prefetch_l2(L.H + k * d * D + d * D - 1);
+    }
+  }
+  // Asynchronous staging of step k's compact linearisation into slot (k & 1) of the group's shared memory
+  // (cp.async: global -> shared without passing through registers; held in registers one step ahead it cost ~60
+  // registers of pressure and spills, loaded at its use it exposed the DRAM latency once per step).
+  static constexpr int CPD = (G >= 2 && NJ % 2 == 0) ? 2 : 1;  // doubles per copy (16-byte copies need alignment)
+  static __device__ __forceinline__ void stage_lin(const Ctx& cx, const Lin& L, long k, bool valid) {
+    if (L.Jc && valid) {
+      const double* src = L.Jc + k * NJ;
+      double* dst = cx.lbuf + (k & 1) * NJP;
+#pragma unroll
+      for (int i0 = 0; i0 < NJ / CPD; i0 += G) {
+        const int i = i0 + cx.l;
+        if (i < NJ / CPD) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i * CPD);
+          if constexpr (CPD == 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + i * CPD) : "memory");
+          else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + i * CPD) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // step k's linearisation: from the staging slot (waits for all but the most recent cp.async group), or dense
+  static __device__ __forceinline__ void fetch_lin(const Ctx& cx, const Lin& L, long k, LinK& o) {
+    if (L.Jc) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      cx.sync();
+      const double* p = cx.lbuf + (k & 1) * NJP;
+#pragma unroll
+      for (int a = 0; a < d; ++a) {
+        o.c[a] = p[d * d + a];
+#pragma unroll
+        for (int b = 0; b < d; ++b) o.J[a][b] = p[a * d + b];
+      }
+      o.Hd = nullptr;
+    } else {
+      load_lin(L, k, o);
+    }
+  }
   // (H X)[a][col] for a column `col` of a published D-row matrix M
   static __device__ __forceinline__ void H_times_col(const Lin& L, const LinK& lk, const double* M, int col,
                                                      double (&out)[d]) {
@@ -371,9 +460,7 @@ struct Lane2 {
       const HH h = house<D - A - 1>(W[A][A], &W[A][A + 1]);
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        double w = h.s * t[s][A];
-#pragma unroll
-        for (int j = A + 1; j < D; ++j) w = fma(t[s][j], W[A][j], w);
+        double w = fma(h.s, t[s][A], dotn<D - A - 1>(&t[s][A + 1], &W[A][A + 1]));
         w *= h.tp;
         t[s][A] = fma(-w, h.s, t[s][A]);
 #pragma unroll
@@ -381,9 +468,7 @@ struct Lane2 {
       }
 #pragma unroll
       for (int a2 = A + 1; a2 < d; ++a2) {
-        double u = h.s * W[a2][A];
-#pragma unroll
-        for (int j = A + 1; j < D; ++j) u = fma(W[a2][j], W[A][j], u);
+        double u = fma(h.s, W[a2][A], dotn<D - A - 1>(&W[a2][A + 1], &W[A][A + 1]));
         u *= h.tp;
         W[a2][A] = fma(-u, h.s, W[a2][A]);
 #pragma unroll
@@ -429,9 +514,9 @@ struct Lane2 {
   template <bool FIRST>
   static __device__ __forceinline__ void fold_step(Ctx& cx, const Lin& lin, long k, bool emit_pre,
                                                    double (&a)[R][D], double (&b)[R], double (&uf)[R][D],
-                                                   double (&eta)[R], double (&z)[R][D], double* __restrict__ aggm) {
-    LinK lk;
-    load_lin(lin, k, lk);
+                                                   double (&eta)[R], double (&z)[R][D], double* __restrict__ aggm,
+                                                   bool has_next) {
+    stage_lin(cx, lin, k + 1, has_next);
     // ---- predict: A <- F A, b <- F b, T = tria([F Uf, QL])
     double t[R][D];
     {
@@ -472,6 +557,8 @@ struct Lane2 {
     }
     // ---- update
     double SL[d][d];
+    LinK lk;
+    fetch_lin(cx, lin, k, lk);
     const double* MT = publish<0>(cx, 1, t);
     update(cx, lin, lk, MT, t, SL);
     // ---- G = SL^{-1} (H A) (columns over the owned rows' indices), zz = SL^{-1}(H b + c)
@@ -533,8 +620,10 @@ struct Lane2 {
         z[s][j] = 0.0;
       }
     }
-    fold_step<true>(cx, lin, k0, aggm && k0 == k1 - 1, a, b, uf, eta, z, aggm);
-    for (long k = k0 + 1; k < k1; ++k) fold_step<false>(cx, lin, k, aggm && k == k1 - 1, a, b, uf, eta, z, aggm);
+    stage_lin(cx, lin, k0, true);
+    fold_step<true>(cx, lin, k0, aggm && k0 == k1 - 1, a, b, uf, eta, z, aggm, k0 + 1 < k1);
+    for (long k = k0 + 1; k < k1; ++k)
+      fold_step<false>(cx, lin, k, aggm && k == k1 - 1, a, b, uf, eta, z, aggm, k + 1 < k1);
     constexpr int DD = D * D;
 #pragma unroll
     for (int s = 0; s < R; ++s)
@@ -569,9 +658,8 @@ struct Lane2 {
   template <int J0>
   static __device__ __forceinline__ void scan_step(Ctx& cx, const Lin& lin, long k, double (&m)[R], double (&uf)[R][D],
                                                    double* __restrict__ kern, Stats& st, double* __restrict__ fmeans,
-                                                   double* __restrict__ fchols) {
-    LinK lk;
-    load_lin(lin, k, lk);
+                                                   double* __restrict__ fchols, bool has_next) {
+    stage_lin(cx, lin, k + 1, has_next);
     // ---- predict + backward kernel: [[F Uf, QL],[Uf, 0]] -> [[T, 0],[Phi21, Phi22~]]
     double t[R][D], cc[R][D], e[R][D];
     {
@@ -621,16 +709,18 @@ struct Lane2 {
     // ---- Dk = tria(Phi22~) and store the step's backward kernel
     double dk[R][D];
     tria_rows<J0>(cx, uf, dk);
+    {
+      double* kp = kern + k * NE;
 #pragma unroll
-    for (int s = 0; s < R; ++s)
-      if (cx.row[s] < D) {
-        double* kp = kern + k * NE;
-        kp[cx.row[s]] = g[s];
-        store_row(kp + D + cx.row[s] * D, e[s]);
-        store_row(kp + D + D * D + cx.row[s] * D, dk[s]);
-      }
+      for (int s = 0; s < R; ++s)
+        if (cx.row[s] < D) kp[cx.row[s]] = g[s];
+      store_rows_pm(cx, kp + D, e);
+      store_rows_pm(cx, kp + D + D * D, dk);
+    }
     // ---- measurement update
     double SL[d][d], y[d], zz[d];
+    LinK lk;
+    fetch_lin(cx, lin, k, lk);
     update(cx, lin, lk, MT, t, SL);
     H_times_vec(lin, lk, mv, y);
     solveSL(SL, y, zz);
@@ -686,8 +776,9 @@ struct Lane2 {
       for (int j = 0; j < D; ++j) uf[s][j] = ok ? state_in[D + cx.rc[s] * D + j] : 0.0;
     }
     Stats st = {0.0, 0.0, 0.0};
-    scan_step<0>(cx, lin, k0, m, uf, kern, st, fmeans, fchols);
-    for (long k = k0 + 1; k < k1; ++k) scan_step<d>(cx, lin, k, m, uf, kern, st, fmeans, fchols);
+    stage_lin(cx, lin, k0, true);
+    scan_step<0>(cx, lin, k0, m, uf, kern, st, fmeans, fchols, k0 + 1 < k1);
+    for (long k = k0 + 1; k < k1; ++k) scan_step<d>(cx, lin, k, m, uf, kern, st, fmeans, fchols, k + 1 < k1);
     // filtered end state with a lower-triangular factor
     double le[R][D];
     tria_rows<d>(cx, uf, le);
@@ -706,31 +797,64 @@ struct Lane2 {
   }
 
   // ================================================================== smoother phase 3: seeded square-root RTS
-  static __device__ __forceinline__ void load_kernel(const Ctx& cx, const double* __restrict__ kp, double (&g)[R],
-                                                     double (&e)[R][D], double (&dk)[R][D]) {
+  // a step's backward kernel (g | E | Dk), row-contiguous per lane: (g, E rows) and (Dk rows) are loaded separately so
+  // that only (g, E) -- needed first -- is held one step ahead in registers; Dk is loaded at the top of its own step
+  // from L2, where a prefetch issued one step earlier has put it (holding all 2D^2+D doubles of the next step in
+  // registers spilled, and the spill stores then waited for the loads: ncu STL on long_sb, 19 % of the samples)
+  // Matrices of the backward kernels (private to scan -> smooth) are stored PIECE-major: element (r, c) of a D x D
+  // block lives at ((c / PW) * D + r) * PW + c % PW with PW = 2 doubles (one 128-bit access) for even D.  The G lanes
+  // of a group then touch G consecutive 16-byte pieces per instruction (one 64-byte segment per chunk) instead of G
+  // pieces 8 D bytes apart: 8 instead of ~20 L1 tag look-ups and half the L2 sectors per warp access (ncu, r01).
+  static constexpr int PW = (D % 2 == 0) ? 2 : 1;
+  static __device__ __forceinline__ void load_rows(const Ctx& cx, const double* __restrict__ base, double (&x)[R][D]) {
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int rc = cx.rc[s];
-      g[s] = kp[rc];
-      if constexpr (D % 2 == 0) {
-        const double2* pe = reinterpret_cast<const double2*>(kp + D + rc * D);
-        const double2* pd = reinterpret_cast<const double2*>(kp + D + D * D + rc * D);
+      if constexpr (PW == 2) {
+        const double2* pe = reinterpret_cast<const double2*>(base) + rc;
 #pragma unroll
         for (int j = 0; j < D / 2; ++j) {
-          const double2 a = pe[j], b = pd[j];
-          e[s][2 * j] = a.x;
-          e[s][2 * j + 1] = a.y;
-          dk[s][2 * j] = b.x;
-          dk[s][2 * j + 1] = b.y;
+          const double2 a = pe[j * D];
+          x[s][2 * j] = a.x;
+          x[s][2 * j + 1] = a.y;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          e[s][j] = kp[D + rc * D + j];
-          dk[s][j] = kp[D + D * D + rc * D + j];
-        }
+        for (int j = 0; j < D; ++j) x[s][j] = base[j * D + rc];
       }
     }
+  }
+  static __device__ __forceinline__ void store_rows_pm(const Ctx& cx, double* __restrict__ base,
+                                                       const double (&x)[R][D]) {
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+      if (cx.row[s] < D) {
+        const int r = cx.row[s];
+        if constexpr (PW == 2) {
+          double2* pe = reinterpret_cast<double2*>(base) + r;
+#pragma unroll
+          for (int j = 0; j < D / 2; ++j) pe[j * D] = make_double2(x[s][2 * j], x[s][2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < D; ++j) base[j * D + r] = x[s][j];
+        }
+      }
+  }
+  static __device__ __forceinline__ void load_ge(const Ctx& cx, const double* __restrict__ kp, double (&g)[R],
+                                                 double (&e)[R][D]) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) g[s] = kp[cx.rc[s]];
+    load_rows(cx, kp + D, e);
+  }
+  static __device__ __forceinline__ void prefetch_dk(const Ctx& cx, const double* __restrict__ kp) {
+    // the Dk block is D*D contiguous doubles: lane l of the group touches every G-th 64-byte piece of it
+    const double* p = kp + D + D * D;
+#pragma unroll
+    for (int o = 0; o < D * D; o += 8 * G) {
+      const int off = o + 8 * cx.l;
+      if (off < D * D) prefetch_l2(p + off);
+    }
+    if (cx.l == 0) prefetch_l2(p + D * D - 1);
   }
   static __device__ __forceinline__ double emit(const Ctx& cx, long t, const double (&m)[R], const double (&l)[R][D],
                                                 double cscale, const double (&old)[R], double* __restrict__ means,
@@ -771,25 +895,25 @@ struct Lane2 {
       for (int s = 0; s < R; ++s) old[s] = means[k1 * D + cx.rc[s]];
       bad += emit(cx, k1, m, l, cscale, old, means, chols);
     }
-    double gn[R], en[R][D], dkn[R][D];
-    load_kernel(cx, kern + (k1 - 1) * NE, gn, en, dkn);
+    double gn[R], en[R][D];
+    load_ge(cx, kern + (k1 - 1) * NE, gn, en);
+    prefetch_dk(cx, kern + (k1 - 1) * NE);
     const bool skip0 = !emit_t0;
 #pragma unroll
     for (int s = 0; s < R; ++s) oldn[s] = (k1 - 1 > 0 || !skip0) ? means[(k1 - 1) * D + cx.rc[s]] : 0.0;
     for (long k = k1 - 1; k >= k0; --k) {
       double g[R], e[R][D], dk[R][D];
+      load_rows(cx, kern + k * NE + D + D * D, dk);
 #pragma unroll
       for (int s = 0; s < R; ++s) {
         g[s] = gn[s];
         old[s] = oldn[s];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          e[s][j] = en[s][j];
-          dk[s][j] = dkn[s][j];
-        }
+        for (int j = 0; j < D; ++j) e[s][j] = en[s][j];
       }
       if (k > k0) {
-        load_kernel(cx, kern + (k - 1) * NE, gn, en, dkn);
+        prefetch_dk(cx, kern + (k - 1) * NE);
+        load_ge(cx, kern + (k - 1) * NE, gn, en);
 #pragma unroll
         for (int s = 0; s < R; ++s) oldn[s] = (k - 1 > 0 || !skip0) ? means[(k - 1) * D + cx.rc[s]] : 0.0;
       }

@@ -67,14 +67,46 @@ struct TreeLane {
     e = fma(-hx * r, r, 0.5);
     return fma(r, e, r);
   }
+  // multi-accumulator dot product (the combines are latency chains: split every long FMA chain)
+  template <int n>
+  static __device__ __forceinline__ double dotn(const double* a, const double* b) {
+    if constexpr (n <= 0) {
+      return 0.0;
+    } else if constexpr (n < 4) {
+      double s = a[0] * b[0];
+#pragma unroll
+      for (int j = 1; j < n; ++j) s = fma(a[j], b[j], s);
+      return s;
+    } else if constexpr (n < 10) {
+      double s0 = a[0] * b[0], s1 = a[1] * b[1];
+#pragma unroll
+      for (int j = 2; j + 1 < n; j += 2) {
+        s0 = fma(a[j], b[j], s0);
+        s1 = fma(a[j + 1], b[j + 1], s1);
+      }
+      if constexpr (n % 2) s0 = fma(a[n - 1], b[n - 1], s0);
+      return s0 + s1;
+    } else {
+      double s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
+#pragma unroll
+      for (int j = 4; j + 3 < n; j += 4) {
+        s0 = fma(a[j], b[j], s0);
+        s1 = fma(a[j + 1], b[j + 1], s1);
+        s2 = fma(a[j + 2], b[j + 2], s2);
+        s3 = fma(a[j + 3], b[j + 3], s3);
+      }
+      if constexpr (n % 4 >= 1) s0 = fma(a[n - n % 4], b[n - n % 4], s0);
+      if constexpr (n % 4 >= 2) s1 = fma(a[n - n % 4 + 1], b[n - n % 4 + 1], s1);
+      if constexpr (n % 4 >= 3) s2 = fma(a[n - n % 4 + 2], b[n - n % 4 + 2], s2);
+      return (s0 + s1) + (s2 + s3);
+    }
+  }
   struct HH {
     double s, tp, beta;
   };
   template <int n>
   static __device__ __forceinline__ HH house(double alpha, const double* x) {
-    double sigma = 0.0;
-#pragma unroll
-    for (int j = 0; j < n; ++j) sigma = fma(x[j], x[j], sigma);
+    const double sigma = dotn<n>(x, x);
     const bool nz = sigma > 0.0;
     const double nrm2 = fma(alpha, alpha, sigma);
     const double rn = fast_rsqrt(nrm2);
@@ -191,9 +223,7 @@ struct TreeLane {
         cx.flip ^= 1;
       }
       const HH h = house<n - 1>(piv[0], piv + 1);
-      double w = h.s * x[I];
-#pragma unroll
-      for (int j = I + 1; j < NC; ++j) w = fma(x[j], piv[j - I], w);
+      double w = fma(h.s, x[I], dotn<NC - I - 1>(&x[I + 1], piv + 1));  // the dot does not wait for the reflector
       const int rr = second ? cx.r - D : cx.r;
       w = (rr >= I) ? w * h.tp : 0.0;
       x[I] = (rr == I) ? h.beta : fma(-w, h.s, x[I]);
