@@ -31,6 +31,15 @@ struct Lane2 {
   static constexpr int GPW = 32 / G;
   static constexpr int NE = D + 2 * D * D;
   static constexpr int KP = D - d;  // columns of a posterior factor
+  // The information factor Z of a chunk's filtering element only ACCUMULATES: Z Z^T += G_k^T G_k per step, nothing
+  // else in the fold reads it.  So the d new columns of MZ consecutive steps are collected first and absorbed with
+  // ONE triangularisation tria([Z | G_k^T ... G_{k+MZ-1}^T]) (D pivots with MZ*d extra columns) instead of MZ
+  // triangularisations with d extra columns each: the reflector set-up (norm, rsqrt, rcp: as expensive as the row
+  // update when there are only d columns) and the dependent pivot chain shrink by the factor MZ.
+#ifndef POF_FOLD_MZ
+#define POF_FOLD_MZ 4
+#endif
+  static constexpr int MZ = (POF_FOLD_MZ * d <= D) ? POF_FOLD_MZ : (D / d);
   static constexpr double LOG_2PI = 1.8378770664093454835606594728112;
   // per-group shared memory (doubles): two row-exchange matrices, two gather vectors, this group's rows of QL
   static constexpr int LDM = D + 1;
@@ -514,8 +523,8 @@ struct Lane2 {
   template <bool FIRST>
   static __device__ __forceinline__ void fold_step(Ctx& cx, const Lin& lin, long k, bool emit_pre,
                                                    double (&a)[R][D], double (&b)[R], double (&uf)[R][D],
-                                                   double (&eta)[R], double (&z)[R][D], double* __restrict__ aggm,
-                                                   bool has_next) {
+                                                   double (&eta)[R], double (&z)[R][D], double (&gt)[R][D], int slot,
+                                                   double* __restrict__ aggm, bool has_next) {
     stage_lin(cx, lin, k + 1, has_next);
     // ---- predict: A <- F A, b <- F b, T = tria([F Uf, QL])
     double t[R][D];
@@ -592,17 +601,23 @@ struct Lane2 {
 #pragma unroll
       for (int j = 0; j < D; ++j) uf[s][j] = (j < d) ? 0.0 : t[s][j];
     }
-    // ---- Z <- tria([Z, G^T]): d extra columns, kept in columns [D-d, D) of a scratch row array
-    {
-      double gt[R][D];
+    // ---- pending columns of Z: G^T of this step goes to columns [D - (slot+1) d, D - slot d) of gt (flush_z absorbs)
+#pragma unroll
+    for (int sl = 0; sl < MZ; ++sl) {
 #pragma unroll
       for (int s = 0; s < R; ++s) {
 #pragma unroll
-        for (int j = 0; j < D; ++j) gt[s][j] = 0.0;
-#pragma unroll
-        for (int e = 0; e < d; ++e) gt[s][D - d + e] = g[e][s];
+        for (int e = 0; e < d; ++e) gt[s][D - (sl + 1) * d + e] = (sl == slot) ? g[e][s] : gt[s][D - (sl + 1) * d + e];
       }
-      tpqrt<D - d, false>(cx, z, gt, nullptr, nullptr);
+    }
+  }
+  // Z <- tria([Z | pending columns]); pending <- 0
+  static __device__ __forceinline__ void flush_z(Ctx& cx, double (&z)[R][D], double (&gt)[R][D]) {
+    tpqrt<D - MZ * d, false>(cx, z, gt, nullptr, nullptr);
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) gt[s][j] = 0.0;
     }
   }
 
@@ -620,10 +635,26 @@ struct Lane2 {
         z[s][j] = 0.0;
       }
     }
+    double gt[R][D];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) gt[s][j] = 0.0;
+    }
     stage_lin(cx, lin, k0, true);
-    fold_step<true>(cx, lin, k0, aggm && k0 == k1 - 1, a, b, uf, eta, z, aggm, k0 + 1 < k1);
-    for (long k = k0 + 1; k < k1; ++k)
-      fold_step<false>(cx, lin, k, aggm && k == k1 - 1, a, b, uf, eta, z, aggm, k + 1 < k1);
+    fold_step<true>(cx, lin, k0, aggm && k0 == k1 - 1, a, b, uf, eta, z, gt, 0, aggm, k0 + 1 < k1);
+    int slot = 1;
+    for (long k = k0 + 1; k <= k1; ++k) {
+      // one flush site: when MZ steps are pending, before the chunk's last step if it emits the pre-update element
+      // (which must carry the complete Z), and after the last step
+      if (slot == MZ || k == k1 || (k == k1 - 1 && aggm && slot != 0)) {
+        flush_z(cx, z, gt);
+        slot = 0;
+      }
+      if (k == k1) break;
+      fold_step<false>(cx, lin, k, aggm && k == k1 - 1, a, b, uf, eta, z, gt, slot, aggm, k + 1 < k1);
+      ++slot;
+    }
     constexpr int DD = D * D;
 #pragma unroll
     for (int s = 0; s < R; ++s)
@@ -840,21 +871,20 @@ struct Lane2 {
         }
       }
   }
-  static __device__ __forceinline__ void load_ge(const Ctx& cx, const double* __restrict__ kp, double (&g)[R],
-                                                 double (&e)[R][D]) {
+  // L2 prefetch of one step's backward kernel (NE contiguous doubles) and the previous mean of that row, spread over
+  // the group's lanes in 128-byte strides
+  static __device__ __forceinline__ void prefetch_step(const Ctx& cx, const double* __restrict__ kp,
+                                                       const double* __restrict__ mrow) {
 #pragma unroll
-    for (int s = 0; s < R; ++s) g[s] = kp[cx.rc[s]];
-    load_rows(cx, kp + D, e);
-  }
-  static __device__ __forceinline__ void prefetch_dk(const Ctx& cx, const double* __restrict__ kp) {
-    // the Dk block is D*D contiguous doubles: lane l of the group touches every G-th 64-byte piece of it
-    const double* p = kp + D + D * D;
-#pragma unroll
-    for (int o = 0; o < D * D; o += 8 * G) {
-      const int off = o + 8 * cx.l;
-      if (off < D * D) prefetch_l2(p + off);
+    for (int o = 0; o < NE; o += 16 * G) {
+      const int off = o + 16 * cx.l;
+      if (off < NE) prefetch_l2(kp + off);
     }
-    if (cx.l == 0) prefetch_l2(p + D * D - 1);
+    if (cx.l == 0) {
+      prefetch_l2(kp + NE - 1);
+      prefetch_l2(mrow);
+      prefetch_l2(mrow + D - 1);
+    }
   }
   static __device__ __forceinline__ double emit(const Ctx& cx, long t, const double (&m)[R], const double (&l)[R][D],
                                                 double cscale, const double (&old)[R], double* __restrict__ means,
@@ -881,7 +911,7 @@ struct Lane2 {
                                                 const double* __restrict__ seed, const double* __restrict__ kern,
                                                 double cscale, double* __restrict__ means,
                                                 double* __restrict__ chols, double* __restrict__ part) {
-    double m[R], l[R][D], old[R], oldn[R];
+    double m[R], l[R][D], old[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const bool ok = cx.row[s] < D;
@@ -895,28 +925,25 @@ struct Lane2 {
       for (int s = 0; s < R; ++s) old[s] = means[k1 * D + cx.rc[s]];
       bad += emit(cx, k1, m, l, cscale, old, means, chols);
     }
-    double gn[R], en[R][D];
-    load_ge(cx, kern + (k1 - 1) * NE, gn, en);
-    prefetch_dk(cx, kern + (k1 - 1) * NE);
+    // Global loads of a step are issued at its top and hit L2: the whole kernel of step k-1 (and the previous mean of
+    // row k-1) is prefetched into L2 while step k computes.  (Holding the next kernel in registers spilled; mixing
+    // DRAM-latency loads for step k-1 with L2 hits for step k made every consumer wait for the slowest load, because
+    // the few load scoreboards are shared -- ncu: long_scoreboard on the first shuffle of Dk, 33 % of the samples.)
     const bool skip0 = !emit_t0;
-#pragma unroll
-    for (int s = 0; s < R; ++s) oldn[s] = (k1 - 1 > 0 || !skip0) ? means[(k1 - 1) * D + cx.rc[s]] : 0.0;
+    prefetch_step(cx, kern + (k1 - 1) * NE, means + (k1 - 1) * D);
     for (long k = k1 - 1; k >= k0; --k) {
       double g[R], e[R][D], dk[R][D];
-      load_rows(cx, kern + k * NE + D + D * D, dk);
+      {
+        const double* kp = kern + k * NE;
 #pragma unroll
-      for (int s = 0; s < R; ++s) {
-        g[s] = gn[s];
-        old[s] = oldn[s];
-#pragma unroll
-        for (int j = 0; j < D; ++j) e[s][j] = en[s][j];
+        for (int s = 0; s < R; ++s) {
+          g[s] = kp[cx.rc[s]];
+          old[s] = (k > 0 || !skip0) ? means[k * D + cx.rc[s]] : 0.0;
+        }
+        load_rows(cx, kp + D, e);
+        load_rows(cx, kp + D + D * D, dk);
       }
-      if (k > k0) {
-        prefetch_dk(cx, kern + (k - 1) * NE);
-        load_ge(cx, kern + (k - 1) * NE, gn, en);
-#pragma unroll
-        for (int s = 0; s < R; ++s) oldn[s] = (k - 1 > 0 || !skip0) ? means[(k - 1) * D + cx.rc[s]] : 0.0;
-      }
+      if (k > k0) prefetch_step(cx, kern + (k - 1) * NE, means + (k - 1) * D);
       const double* ML = publish<0>(cx, 0, l);
       double mv[D];
       gather(cx, m, mv);
