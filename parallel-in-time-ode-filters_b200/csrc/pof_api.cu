@@ -24,6 +24,19 @@ static const TreeLaunch* tree_launch(int D) {
   return t;
 }
 
+// POF_B200_TREE_SWEEP=1: whole tree sweeps as single cooperative kernels with a grid barrier per level.  Measured on
+// B200 (N = 2^20, 14 levels): 0.51 ms per filter tree against 0.33 ms with one graph-replayed launch per level -- a
+// cooperative-groups grid barrier costs more than a kernel boundary inside a CUDA graph here, so the default stays
+// one launch per level.
+static bool tree_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("POF_B200_TREE_SWEEP");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // thread-per-chunk reference kernels (pof_leaf.cuh)
 static const LeafLaunch* thread_launch(int d, int q) {
   switch (d) {
@@ -419,6 +432,20 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   return 0;
 }
 
+static void fill_sweep(SweepArgs& sa, const WsLayout& wl, double* agg, double* st, int up_levels, int do_down) {
+  sa.nlev = wl.tl.nlev;
+  sa.up_levels = up_levels < 0 ? 0 : up_levels;
+  sa.do_down = do_down;
+  for (int l = 0; l < SweepArgs::MAXL; ++l) {
+    sa.off[l] = l < wl.tl.nlev ? wl.tl.off[l] : 0;
+    sa.sz[l] = l < wl.tl.nlev ? wl.tl.sz[l] : 0;
+  }
+  sa.agg = agg;
+  sa.st = st;
+  sa.root_m = sa.root_L = nullptr;
+  sa.faggm = sa.fin = nullptr;
+}
+
 // stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
 // need_root: the tree's root element is only consumed by the time-sharded form (it is the shard's carry)
 static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
@@ -429,12 +456,21 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     ProfScope ps(SEG_FOLD, s);
     POF_CK(ll->fold(s, a, fagg, pre ? ws + wl.o_faggm : nullptr));
   }
+  const TreeLaunch* tl = tree_launch(wl.D);
+  if (tl && tree_fused()) {
+    // single GPU: the up-sweep runs fused with the down-sweep in stage_b; sharded: up-sweep incl. the root here
+    if (!need_root) return 0;
+    ProfScope ps(SEG_FUP, s);
+    SweepArgs sa;
+    fill_sweep(sa, wl, fagg, ws + wl.o_fin, wl.tl.nlev - 1, 0);
+    POF_CK(tl->fsweep(s, sa));
+    return 0;
+  }
   ProfScope ps(SEG_FUP, s);
   const int smem = tree_smem_bytes(wl.D);
   const int tw = tree_warps(wl.D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_up, smem));
-  const TreeLaunch* tl = tree_launch(wl.D);
   for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l) {
     const long np = wl.tl.sz[l + 1];
     if (tl)
@@ -446,8 +482,10 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   return (int)cudaGetLastError();
 }
 // stage B: filter down-sweep from the root's incoming state (already stored at fin[root]), scan, smoother up-sweep
+// fuse_sdown (single GPU): the smoother's down-sweep runs in the same cooperative kernel as its up-sweep, seeded with
+// the filtered state of the last chunk; stage_c must then be called with skip_down
 static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
-                   double* fmeans, double* fchols, bool need_root) {
+                   double* fmeans, double* fchols, bool need_root, bool fuse_sdown = false) {
   double* fagg = ws + wl.o_fagg;
   double* fin = ws + wl.o_fin;
   double* sagg = ws + wl.o_sagg;
@@ -457,7 +495,13 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   POF_CK(set_smem(k_filter_down, smem));
   POF_CK(set_smem(k_smooth_up, smem));
   const TreeLaunch* tl = tree_launch(wl.D);
-  {
+  const bool fused = tl && tree_fused();
+  if (fused) {
+    ProfScope ps(need_root ? SEG_FDOWN : SEG_FUP, s);
+    SweepArgs sa;
+    fill_sweep(sa, wl, fagg, fin, need_root ? 0 : wl.tl.nlev - 2, 1);
+    POF_CK(tl->fsweep(s, sa));
+  } else {
   ProfScope ps(SEG_FDOWN, s);
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     const long np = wl.tl.sz[l];
@@ -476,6 +520,20 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     ProfScope ps(SEG_SCAN, s);
     POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, pre ? nullptr : sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
   }
+  if (fused && pre) {
+    ProfScope ps(SEG_SUP, s);
+    SweepArgs sa;
+    fill_sweep(sa, wl, sagg, ws + wl.o_sin, need_root ? wl.tl.nlev - 1 : wl.tl.nlev - 2, fuse_sdown ? 1 : 0);
+    sa.faggm = ws + wl.o_faggm;
+    sa.fin = fin;
+    if (fuse_sdown) {
+      sa.root_m = ws + wl.o_send + (wl.CS - 1) * wl.ST;
+      sa.root_L = sa.root_m + wl.D;
+    }
+    POF_CK(tl->ssweep(s, sa));
+    k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+    return (int)cudaGetLastError();
+  }
   // chunk-level smoothing elements straight from (incoming state, filtering element before its last update)
   if (pre) POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
   ProfScope ps(SEG_SUP, s);
@@ -492,16 +550,22 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
 }
 // stage C: smoother down-sweep from the seed (already stored at sin[root]) + smoother scan
 static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
-                   int emit_t0, const double* cscale, double* means, double* chols) {
+                   int emit_t0, const double* cscale, double* means, double* chols, bool skip_down = false) {
   double* sagg = ws + wl.o_sagg;
   double* sin_ = ws + wl.o_sin;
   const int smem = tree_smem_bytes(wl.D);
   const int tw = tree_warps(wl.D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_smooth_down, smem));
-  {
-  ProfScope ps(SEG_SDOWN, s);
   const TreeLaunch* tl = tree_launch(wl.D);
+  if (skip_down) {
+  } else if (tl && tree_fused()) {
+    ProfScope ps(SEG_SDOWN, s);
+    SweepArgs sa;
+    fill_sweep(sa, wl, sagg, sin_, 0, 1);
+    POF_CK(tl->ssweep(s, sa));
+  } else {
+  ProfScope ps(SEG_SDOWN, s);
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     const long np = wl.tl.sz[l];
     if (tl)
@@ -561,6 +625,9 @@ int pof_profile_read(double* ms_out, int64_t* count_out) {
 int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (ll && ll->has_pre_update && tree_launch(wl.D) && tree_fused())
+    return 3 /*leaf*/ + 2 /*cooperative tree sweeps*/ + 1 /*pack*/ + 2 /*reduce*/ + 2 /*finalize*/;
   const int64_t downs = 2 * (int64_t)(wl.tl.nlev - 1);
   const int64_t ups = 2 * (int64_t)(wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0);  // the root combine is skipped on one GPU
   return 3 /*leaf*/ + downs + ups /*tree sweeps*/ + 1 /*chunk smoothing elements*/ + 1 /*pack*/ + 2 /*reduce*/ +
@@ -737,13 +804,15 @@ static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, con
     POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
     POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
-  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, false);
+  const bool fuse_sdown = ll->has_pre_update && tree_launch(wl.D) != nullptr && tree_fused();
+  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, false, fuse_sdown);
   if (rc) return rc;
   k_finalize_filter<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, calibrate, scalars);
   // terminal smoothing state = filtered state at the last time point
-  POF_CK(cudaMemcpyAsync(ws + wl.o_sin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, ws + wl.o_send + (wl.CS - 1) * wl.ST,
-                         wl.ST * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  rc = stage_c(s, ll, a, wl, ws, 1, scalars + POF_S_CSCALE, means, chols);
+  if (!fuse_sdown)
+    POF_CK(cudaMemcpyAsync(ws + wl.o_sin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, ws + wl.o_send + (wl.CS - 1) * wl.ST,
+                           wl.ST * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  rc = stage_c(s, ll, a, wl, ws, 1, scalars + POF_S_CSCALE, means, chols, fuse_sdown);
   if (rc) return rc;
   k_finalize_smooth<<<1, 1, 0, s>>>(ws + wl.o_sums + 8, scalars);
   return (int)cudaGetLastError();

@@ -82,10 +82,30 @@ const LeafLaunch* lane2_launch_d2(int q);
 const LeafLaunch* lane2_launch_d3(int q);
 const LeafLaunch* lane2_launch_d4(int q);
 
+// One whole tree sweep (all levels of an up-sweep and/or a down-sweep) as ONE persistent cooperative kernel with a
+// grid barrier between levels: ~2 us per level instead of a kernel boundary (launch gap, cold instruction cache,
+// drained SMs) per level.
+struct SweepArgs {
+  static constexpr int MAXL = 48;
+  int nlev;          // levels of the tree (level 0 = chunks)
+  int up_levels;     // up-sweep: build levels 1 .. up_levels (0: none)
+  int do_down;       // down-sweep from the root to level 0 afterwards
+  long off[MAXL], sz[MAXL];
+  double* agg;       // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
+  double* st;        // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
+  const double* root_m;  // if non-null: root state <- (root_m, root_L) before the down-sweep
+  const double* root_L;
+  // smoothing sweep only: chunk-level smoothing elements first (if faggm != null): agg[level 0] <- chunk_kernel
+  const double* faggm;   // chunk filtering elements before their last update
+  const double* fin;     // chunk incoming filtered states
+};
+
 // register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> generic shared-memory kernels
 struct TreeLaunch {
   typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
   Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk;
+  typedef cudaError_t (*SweepFn)(cudaStream_t, const SweepArgs&);
+  SweepFn fsweep, ssweep;  // cooperative whole-sweep kernels (filtering / smoothing)
 };
 const TreeLaunch* tree_launch_a(int D);
 const TreeLaunch* tree_launch_b(int D);

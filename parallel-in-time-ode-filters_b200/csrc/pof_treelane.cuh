@@ -277,14 +277,17 @@ struct TreeLane {
         x[D + j] = (top && j == rr) ? 1.0 : 0.0;
       }
     }
-    tria_step<0, W2, (STATE ? D : W2), false>(cx, x);
-    // publish Xi11 (lanes top), Xi21 and Xi22 (lanes bottom)
+    // Only the first D pivots: they give Xi11 and Xi21.  The remaining block B (bottom rows, columns D..2D) is NOT
+    // triangularised: it enters the result only through Z = tria([A1^T Xi22 | Z1]), which depends on Xi22 Xi22^T = B B^T
+    // alone, so B itself serves (D-1 fewer pivots on the latency chain of every up-sweep level).
+    tria_step<0, W2, D, false>(cx, x);
+    // publish Xi11 (lanes top), Xi21 and B (lanes bottom)
     {
       double lo[D], hi[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         lo[j] = x[j];
-        hi[j] = (j <= rr) ? x[D + j] : 0.0;
+        hi[j] = x[D + j];
       }
       if (top) {
 #pragma unroll
