@@ -178,13 +178,28 @@ def set_up_solver(ivp: IVP, ts, order):
     return dict(ivp=ivp, ts=ts, dtm=TransitionModel(F, QL), x0=x0, E0=E0, E1=E1, P=P, PI=PI, order=order, d=d)
 
 
+def coarse_ekf_init(ivp, order, ts, N=10):
+    """pof/initialization.py:103-121: sequential EKS on a coarse grid of N points (full states, calibrated, mapped
+    back with P), then piecewise-constant interpolation idx = floor(ts / coarse_dt) -- absolute times, i.e. t0 = 0 is
+    assumed; JAX clamps out-of-range gather indices."""
+    ts = np.asarray(ts, dtype=float)
+    coarse_ts = np.linspace(ts[0], ts[-1], N)
+    coarse_dt = coarse_ts[1] - coarse_ts[0]
+    out, _ = sequential_eks_solve(ivp, coarse_ts, order, return_full_states=True)
+    idxs = np.clip(np.floor(ts / coarse_dt).astype(int), 0, N - 1)
+    return MVNSqrt(out.mean[idxs], out.chol[idxs])
+
+
 def get_initial_trajectory(setup, method="constant"):
-    """pof/convenience.py:76-92 (only 'constant'; the others are out of tier-1 scope)."""
+    """pof/convenience.py:76-92 ('constant' and 'coarse'; 'prior' is restated on the host side of the product)."""
+    PI = setup["PI"]
+    if method == "coarse":
+        st = coarse_ekf_init(setup["ivp"], setup["order"], setup["ts"], N=100)
+        return MVNSqrt(st.mean @ PI.T, np.einsum("ij,njk->nik", PI, st.chol))
     if method != "constant":
         raise NotImplementedError(method)
     N = len(setup["ts"])
     st = constant_init(setup["ivp"], setup["order"], N)
-    PI = setup["PI"]
     return MVNSqrt(st.mean @ PI.T, np.einsum("ij,njk->nik", PI, st.chol))
 
 

@@ -341,6 +341,41 @@ struct Lane2 {
     }
   }
 
+  // Right-Householder lower-triangularisation of the D x (2D - JS) matrix [x | y(:, JS:D)]; the D x D lower-triangular
+  // result is left in x.  (Smoother: x = E L_{k+1}, y = the UNtriangularised Phi22~ block of the step's joint QR --
+  // only y y^T matters, so the filter scan does not triangularise it.)
+  template <int S, int I, int JS>
+  static __device__ __forceinline__ void tria2_update(const Ctx& cx, const HH& h, const double* piv, double (&x)[R][D],
+                                                      double (&y)[R][D]) {
+    if constexpr (S * G + G - 1 >= I) {
+      constexpr int n1 = D - I, n2 = D - JS;
+      double w = fma(h.s, x[S][I], dotn<n1 - 1>(&x[S][I + 1], piv + 1) + dotn<n2>(&y[S][JS], piv + n1));
+      w = (cx.row[S] >= I) ? w * h.tp : 0.0;
+      x[S][I] = (cx.row[S] == I) ? h.beta : fma(-w, h.s, x[S][I]);
+#pragma unroll
+      for (int j = 1; j < n1; ++j) x[S][I + j] = fma(-w, piv[j], x[S][I + j]);
+#pragma unroll
+      for (int j = 0; j < n2; ++j) y[S][JS + j] = fma(-w, piv[n1 + j], y[S][JS + j]);
+    }
+  }
+  template <int I, int JS>
+  static __device__ __forceinline__ void tria2_step(Ctx& cx, double (&x)[R][D], double (&y)[R][D]) {
+    if constexpr (I < D) {
+      constexpr int n1 = D - I, n2 = D - JS;
+      constexpr int so = I / G;
+      const int lo = I % G;
+      double piv[n1 + n2];
+#pragma unroll
+      for (int j = 0; j < n1; ++j) piv[j] = bshfl(cx, x[so][I + j], lo);
+#pragma unroll
+      for (int j = 0; j < n2; ++j) piv[n1 + j] = bshfl(cx, y[so][JS + j], lo);
+      const HH h = house<n1 + n2 - 1>(piv[0], piv + 1);
+      tria2_update<0, I, JS>(cx, h, piv, x, y);
+      tria2_update<1, I, JS>(cx, h, piv, x, y);
+      tria2_step<I + 1, JS>(cx, x, y);
+    }
+  }
+
   // ---------------------------------------------------------------------------------------------- linearisation access
   struct LinK {  // one step's linearisation, compact or dense
     double J[d][d], c[d];
@@ -737,16 +772,15 @@ struct Lane2 {
       for (int i = 0; i < D; ++i) acc = fma(-e[s][i], mv[i], acc);
       g[s] = acc;
     }
-    // ---- Dk = tria(Phi22~) and store the step's backward kernel
-    double dk[R][D];
-    tria_rows<J0>(cx, uf, dk);
+    // ---- store the step's backward kernel (g | E | Phi22~): the noise factor stays UNtriangularised -- the smoother
+    // only needs Phi22~ Phi22~^T and triangularises [E L | Phi22~] in one go (D - J0 - 1 pivots less per step here)
     {
       double* kp = kern + k * NE;
 #pragma unroll
       for (int s = 0; s < R; ++s)
         if (cx.row[s] < D) kp[cx.row[s]] = g[s];
-      store_rows_pm(cx, kp + D, e);
-      store_rows_pm(cx, kp + D + D * D, dk);
+      store_rows_pm<0>(cx, kp + D, e);
+      store_rows_pm<(J0 / PW) * PW>(cx, kp + D + D * D, uf);
     }
     // ---- measurement update
     double SL[d][d], y[d], zz[d];
@@ -837,24 +871,28 @@ struct Lane2 {
   // of a group then touch G consecutive 16-byte pieces per instruction (one 64-byte segment per chunk) instead of G
   // pieces 8 D bytes apart: 8 instead of ~20 L1 tag look-ups and half the L2 sectors per warp access (ncu, r01).
   static constexpr int PW = (D % 2 == 0) ? 2 : 1;
+  template <int JS = 0>  // columns [JS, D) only (JS a multiple of PW)
   static __device__ __forceinline__ void load_rows(const Ctx& cx, const double* __restrict__ base, double (&x)[R][D]) {
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int rc = cx.rc[s];
+#pragma unroll
+      for (int j = 0; j < JS; ++j) x[s][j] = 0.0;
       if constexpr (PW == 2) {
         const double2* pe = reinterpret_cast<const double2*>(base) + rc;
 #pragma unroll
-        for (int j = 0; j < D / 2; ++j) {
+        for (int j = JS / 2; j < D / 2; ++j) {
           const double2 a = pe[j * D];
           x[s][2 * j] = a.x;
           x[s][2 * j + 1] = a.y;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < D; ++j) x[s][j] = base[j * D + rc];
+        for (int j = JS; j < D; ++j) x[s][j] = base[j * D + rc];
       }
     }
   }
+  template <int JS>
   static __device__ __forceinline__ void store_rows_pm(const Ctx& cx, double* __restrict__ base,
                                                        const double (&x)[R][D]) {
 #pragma unroll
@@ -864,10 +902,10 @@ struct Lane2 {
         if constexpr (PW == 2) {
           double2* pe = reinterpret_cast<double2*>(base) + r;
 #pragma unroll
-          for (int j = 0; j < D / 2; ++j) pe[j * D] = make_double2(x[s][2 * j], x[s][2 * j + 1]);
+          for (int j = JS / 2; j < D / 2; ++j) pe[j * D] = make_double2(x[s][2 * j], x[s][2 * j + 1]);
         } else {
 #pragma unroll
-          for (int j = 0; j < D; ++j) base[j * D + r] = x[s][j];
+          for (int j = JS; j < D; ++j) base[j * D + r] = x[s][j];
         }
       }
   }
@@ -906,6 +944,74 @@ struct Lane2 {
       }
     return bad;
   }
+  template <int JS>
+  static __device__ __forceinline__ void smooth_step(Ctx& cx, long k, bool has_prev, bool emit_t0,
+                                                     const double* qLinvdiag, const double* qL,
+                                                     const double* __restrict__ kern, double cscale,
+                                                     double* __restrict__ means, double* __restrict__ chols,
+                                                     double (&m)[R], double (&l)[R][D], double& obj, double& bad) {
+    double g[R], e[R][D], ph[R][D], old[R];
+    {
+      const double* kp = kern + k * NE;
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        g[s] = kp[cx.rc[s]];
+        old[s] = (k > 0 || emit_t0) ? means[k * D + cx.rc[s]] : 0.0;
+      }
+      load_rows<0>(cx, kp + D, e);
+      load_rows<JS>(cx, kp + D + D * D, ph);
+    }
+    if (has_prev) prefetch_step(cx, kern + (k - 1) * NE, means + (k - 1) * D);
+    const double* ML = publish<0>(cx, 0, l);
+    double mv[D];
+    gather(cx, m, mv);
+    double mn[R], cd[R][D];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      mn[s] = g[s];
+#pragma unroll
+      for (int j = 0; j < D; ++j) cd[s][j] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int s = 0; s < R; ++s) mn[s] = fma(e[s][i], mv[i], mn[s]);
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const double lv = ML[i * LDM + j];
+#pragma unroll
+        for (int s = 0; s < R; ++s) cd[s][j] = fma(e[s][i], lv, cd[s][j]);
+      }
+    }
+    tria2_step<0, JS>(cx, cd, ph);
+    // objective increment |QL^{-1}(m_k - F m_{k+1})|^2 (replicated)
+    double fm[D], rr[D], dr[R];
+#pragma unroll
+    for (int i = 0; i < D; ++i) fm[i] = mv[i];
+    mulF_vec(fm);
+#pragma unroll
+    for (int s = 0; s < R; ++s) dr[s] = mn[s] - pick(fm, cx.rc[s]);
+    gather(cx, dr, rr);
+#pragma unroll
+    for (int b = 0; b < d; ++b) {
+#pragma unroll
+      for (int i = 0; i < Q1; ++i) {
+        double acc = rr[b * Q1 + i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) acc = fma(-qL[i * Q1 + j], rr[b * Q1 + j], acc);
+        acc *= qLinvdiag[i];
+        rr[b * Q1 + i] = acc;
+        obj = fma(acc, acc, obj);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      m[s] = mn[s];
+#pragma unroll
+      for (int j = 0; j < D; ++j) l[s][j] = (j <= cx.rc[s]) ? cd[s][j] : 0.0;
+    }
+    if (k > 0 || emit_t0) bad += emit(cx, k, m, l, cscale, old, means, chols);
+  }
   static __device__ __forceinline__ void smooth(Ctx& cx, long k0, long k1, bool last, bool emit_t0,
                                                 const double* qLinvdiag, const double* qL,
                                                 const double* __restrict__ seed, const double* __restrict__ kern,
@@ -929,71 +1035,11 @@ struct Lane2 {
     // row k-1) is prefetched into L2 while step k computes.  (Holding the next kernel in registers spilled; mixing
     // DRAM-latency loads for step k-1 with L2 hits for step k made every consumer wait for the slowest load, because
     // the few load scoreboards are shared -- ncu: long_scoreboard on the first shuffle of Dk, 33 % of the samples.)
-    const bool skip0 = !emit_t0;
     prefetch_step(cx, kern + (k1 - 1) * NE, means + (k1 - 1) * D);
-    for (long k = k1 - 1; k >= k0; --k) {
-      double g[R], e[R][D], dk[R][D];
-      {
-        const double* kp = kern + k * NE;
-#pragma unroll
-        for (int s = 0; s < R; ++s) {
-          g[s] = kp[cx.rc[s]];
-          old[s] = (k > 0 || !skip0) ? means[k * D + cx.rc[s]] : 0.0;
-        }
-        load_rows(cx, kp + D, e);
-        load_rows(cx, kp + D + D * D, dk);
-      }
-      if (k > k0) prefetch_step(cx, kern + (k - 1) * NE, means + (k - 1) * D);
-      const double* ML = publish<0>(cx, 0, l);
-      double mv[D];
-      gather(cx, m, mv);
-      double mn[R], cd[R][D];
-#pragma unroll
-      for (int s = 0; s < R; ++s) {
-        mn[s] = g[s];
-#pragma unroll
-        for (int j = 0; j < D; ++j) cd[s][j] = 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-#pragma unroll
-        for (int s = 0; s < R; ++s) mn[s] = fma(e[s][i], mv[i], mn[s]);
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          const double lv = ML[i * LDM + j];
-#pragma unroll
-          for (int s = 0; s < R; ++s) cd[s][j] = fma(e[s][i], lv, cd[s][j]);
-        }
-      }
-      tpqrt<0, false>(cx, dk, cd, nullptr, nullptr);
-      // objective increment |QL^{-1}(m_k - F m_{k+1})|^2 (replicated)
-      double fm[D], rr[D], dr[R];
-#pragma unroll
-      for (int i = 0; i < D; ++i) fm[i] = mv[i];
-      mulF_vec(fm);
-#pragma unroll
-      for (int s = 0; s < R; ++s) dr[s] = mn[s] - pick(fm, cx.rc[s]);
-      gather(cx, dr, rr);
-#pragma unroll
-      for (int b = 0; b < d; ++b) {
-#pragma unroll
-        for (int i = 0; i < Q1; ++i) {
-          double acc = rr[b * Q1 + i];
-#pragma unroll
-          for (int j = 0; j < i; ++j) acc = fma(-qL[i * Q1 + j], rr[b * Q1 + j], acc);
-          acc *= qLinvdiag[i];
-          rr[b * Q1 + i] = acc;
-          obj = fma(acc, acc, obj);
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < R; ++s) {
-        m[s] = mn[s];
-#pragma unroll
-        for (int j = 0; j < D; ++j) l[s][j] = (j <= cx.rc[s]) ? dk[s][j] : 0.0;
-      }
-      if (k > 0 || emit_t0) bad += emit(cx, k, m, l, cscale, old, means, chols);
-    }
+    // the noise factor of a step has D - d columns, except for the chunk's first step (full incoming factor)
+    for (long k = k1 - 1; k > k0; --k)
+      smooth_step<(d / PW) * PW>(cx, k, true, emit_t0, qLinvdiag, qL, kern, cscale, means, chols, m, l, obj, bad);
+    smooth_step<0>(cx, k0, false, emit_t0, qLinvdiag, qL, kern, cscale, means, chols, m, l, obj, bad);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) bad += __shfl_xor_sync(cx.mask, bad, o, G);
     if (cx.l == 0) {

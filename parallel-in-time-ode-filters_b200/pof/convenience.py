@@ -56,10 +56,13 @@ def set_up_solver(*, f, y0, ts, order):
 
 
 def get_initial_trajectory(setup, method="prior"):
-    """reference convenience.py:76-92 ('coarse' needs sequential_eks_solve + interpolation: not in this tier)"""
+    """reference convenience.py:76-92"""
     f, y0, order, ts = setup["f"], setup["y0"], setup["order"], setup["ts"]
     PI, dev = setup["PI"], setup["_device"]
-    if method == "constant":
+    if method == "coarse":
+        st = init.coarse_ekf_init(y0=y0, order=order, ts=ts, f=f, N=100)
+        return MVNSqrt((st.mean.to(dev) @ PI.T).contiguous(), torch.einsum("ij,njk->nik", PI, st.chol.to(dev)))
+    elif method == "constant":
         st = init.constant_init(y0=y0, order=order, ts=ts, f=f)
         return MVNSqrt((st.mean.to(dev) @ PI.T).contiguous(), st.chol.to(dev))  # PI @ 0 = 0
     elif method == "prior":

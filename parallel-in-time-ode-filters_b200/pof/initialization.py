@@ -70,3 +70,18 @@ def prior_init(*, f, y0, order, ts):
         means[k + 1] = P @ F @ PI @ m0
         chols[k + 1] = P @ QL
     return MVNSqrt(torch.from_numpy(means), torch.from_numpy(chols))
+
+
+def coarse_ekf_init(*, f, y0, order, ts, N=10):
+    """reference initialization.py:103-121: sequential EKS (GPU kernel `pof_sequential_eks_f64`) on a coarse grid of N
+    points with full states, then piecewise-constant interpolation idx = floor(ts / coarse_dt) (absolute times: the
+    reference assumes t0 = 0; out-of-range indices clamp as in JAX)."""
+    from .solver import sequential_eks_solve
+
+    ts = np.asarray(_cpu64(ts))
+    coarse_ts = np.linspace(ts[0], ts[-1], N)
+    coarse_dt = coarse_ts[1] - coarse_ts[0]
+    out, _ = sequential_eks_solve(f=f, y0=y0, ts=coarse_ts, order=order, return_full_states=True)
+    idxs = np.clip(np.floor(ts / coarse_dt).astype(np.int64), 0, N - 1)
+    idx_t = torch.from_numpy(idxs).to(out.mean.device)
+    return MVNSqrt(out.mean.index_select(0, idx_t), out.chol.index_select(0, idx_t))

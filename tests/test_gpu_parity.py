@@ -267,6 +267,35 @@ def test_sequential_eks_solve_matches_oracle(native_lib, name, kw, N, q):
     assert full.mean.shape == (N, ivp.y0.shape[0] * (q + 1))
 
 
+@pytest.mark.parametrize("name,kw,N,q", [("logistic", {}, 200, 3), ("lotkavolterra", {}, 400, 2),
+                                         ("fitzhughnagumo", {}, 512, 3)])
+def test_coarse_init_matches_oracle(native_lib, name, kw, N, q):
+    """init="coarse" (reference initialization.py:103-121, convenience.py:80-83): sequential EKS on 100 coarse points,
+    piecewise-constant interpolation, then the IEKS loop.  Trajectory and iteration count against the oracle."""
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.solver import solve
+
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    st = get_initial_trajectory(setup, method="coarse")
+    osetup = O.set_up_solver(oivp, ts, q)
+    ost = O.get_initial_trajectory(osetup, method="coarse")
+    m, mo = st.mean.cpu().numpy(), ost.mean
+    assert m.shape == mo.shape
+    # the means seed the first linearisation: compare what the linearisation reads (E0 m) tightly, the full state
+    # relative to each column's scale
+    E0 = osetup["E0"]
+    assert (np.abs(m @ E0.T - mo @ E0.T) <= 1e-9 * np.abs(mo @ E0.T).max(axis=0) + 1e-12).all()
+    assert (np.abs(m - mo) <= 1e-7 * np.abs(mo).max(axis=0) + 1e-12).all()
+    ys, info = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="coarse", maxiters=1000)
+    oys, oinfo = O.solve(oivp, ts, q, init="coarse", maxiters=1000)
+    # long FHN runs stop on the roundoff-sensitive obj/means rule (DESIGN.md section 4): a few iterations either way
+    assert abs(info["iterations"] - oinfo["iterations"]) <= max(1, 0.05 * oinfo["iterations"])
+    y, yo = ys.mean.cpu().numpy(), oys.mean
+    assert (np.abs(y - yo) <= 1e-7 * np.abs(yo).max(axis=0) + 1e-10).all()
+
+
 @pytest.mark.parametrize("N,L", [(2, None), (3, None), (5, 1), (9, 100), (33, 4), (257, 8)])
 def test_edge_sizes(native_lib, leaf_impl, N, L):
     """tiny grids, chunk length 1, chunk longer than the grid, ragged last chunk"""
