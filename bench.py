@@ -33,8 +33,11 @@ FLOP_STEP = 68.5e3
 # innovation statistics and the smoother-element build): C_f + O + E_s  
 FLOP_STEP_SCAN = 21.4e3 + 3.23e3 + 8.1e3
 # algorithmic HBM bytes per step of the scan kernel: read the compact linearisation [J_f | c] (6 doubles), write the
-# step's backward kernel (g, E, D: 136 doubles)
-BYTES_STEP_SCAN = (6 + 136) * 8.0
+# step's backward kernel (g: 8, E: 64, untriangularised noise factor: D x (D-d) = 48 doubles)
+BYTES_STEP_SCAN = (6 + 8 + 64 + 48) * 8.0
+# smoother: read the backward kernel (120 doubles) and the previous mean (8), write the new mean (8) and the calibrated
+# Cholesky factor in the API layout (64)
+BYTES_STEP_SMOOTH = (120 + 8 + 8 + 64) * 8.0
 
 
 def measured_fp64_pipe(kernel_prefix):
@@ -44,6 +47,18 @@ def measured_fp64_pipe(kernel_prefix):
         for k, v in t.items():
             if k.startswith(kernel_prefix):
                 return v["fp64_pipe_pct"] / 100.0
+    except Exception:
+        pass
+    return None
+
+
+def measured_ncu(kernel_prefix, field):
+    """one field of the committed ncu --set full capture of a kernel (profiles/r01_traffic.json), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        for k, v in t.items():
+            if k.startswith(kernel_prefix):
+                return v.get(field)
     except Exception:
         pass
     return None
@@ -64,8 +79,8 @@ def measured_traffic(kernel_prefix):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n-time", type=int, default=2**20, help="time points per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2**15, help="N of the bounded CPU-baseline sample")
@@ -240,7 +255,7 @@ def run_native(args):
     import pof.ivp
     from pof import _native as nat
     from pof.convenience import set_up_solver
-    from pof.parallel_filtsmooth import GraphedIteration, run_iteration
+    from pof.parallel_filtsmooth import GraphedCall, GraphedIteration, run_iteration
     from pof.sharded import ShardedPass, shard_bounds
     from pof.step import linearize_into
 
@@ -294,9 +309,16 @@ def run_native(args):
         L = sp.backend.chunk_len
         launches = 1 + int(nat.LIB.pof_launches_per_pass(n_loc + 1, d_, q_, L)) + 2
 
-        def step():
+        def eager_step():
             linearize()
             return sp.run(x0.mean, x0.chol, Jc, None, means, chols, calibrate=True)
+
+        # the whole sharded iteration (kernels, NCCL all-gathers, the small torch ops between the stages) replayed
+        # from one CUDA graph per rank; POF_BENCH_SHARDED_GRAPH=0 times the eager launches instead
+        fused = GraphedCall(eager_step)
+
+        def step():
+            return fused()
 
     def barrier():
         if world > 1:
@@ -325,8 +347,8 @@ def run_native(args):
     nat.check(nat.LIB.pof_profile_read(seg_ms[0].ctypes.data_as(nat._c_dp), seg_ms[1].ctypes.data_as(nat._c_dp)),
               "profile_read")
     nat.LIB.pof_profile_enable(0)
-    if world == 1:
-        torch.cuda.synchronize()
+    if world == 1 or os.environ.get("POF_BENCH_SHARDED_GRAPH", "1") != "0":
+        barrier()
         fused.capture()
         step()
     clocks = ClockSampler(local)
@@ -367,9 +389,17 @@ def run_native(args):
     nat.check(nat.LIB.pof_measure_dfma_tflops(nat.stream_ptr(), tf.ctypes.data_as(nat._c_dp)), "dfma peak")
     fp64_peak = float(tf[0])
 
-    if rank != 0:
+    def leave():
+        # A process group whose NCCL kernels live in captured CUDA graphs does not tear down reliably (the 2-GPU run
+        # hung in destroy_process_group after printing its line): flush and leave without the teardown.
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     peaks = {}
@@ -395,9 +425,22 @@ def run_native(args):
         "algorithmic_flop_per_step": FLOP_STEP_SCAN, "avg_launch_ms": scan_ms,
         "share_of_step": scan_ms / ms_ref_share if ms_ref_share else None,
         "fp64_pipe_utilisation_ncu": measured_fp64_pipe("k_lane2_scan"),
+        "lsu_pipe_utilisation_ncu": (measured_ncu("k_lane2_scan", "lsu_pipe_pct") or 0) / 100.0 or None,
+        "issue_slot_utilisation_ncu": (measured_ncu("k_lane2_scan", "issue_active_pct") or 0) / 100.0 or None,
         "note": "achieved counts the REFERENCE formulas' flops (SURVEY 8d: one general filtering combine, 21.4 kFLOP, per "
                 "step); the kernel reaches the same result with a ~8x cheaper leaf recursion, so frac can exceed 1 -- the "
                 "executed-instruction view is fp64_pipe_utilisation_ncu (ncu sm__inst_executed_pipe_fp64, profiles/)",
+    }
+    smooth_ms = seg["smooth"]
+    roofline_smooth = {
+        "kernel": "k_lane2_smooth<2,3> (seeded square-root RTS recursion; objective, calibration, convergence count)",
+        "bound": "hbm", "achieved": BYTES_STEP_SMOOTH * n_loc / (smooth_ms * 1e-3) / 1e9 if smooth_ms > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s",
+        "frac": BYTES_STEP_SMOOTH * n_loc / (smooth_ms * 1e-3) / 1e9 / hbm_peak if smooth_ms > 0 else None,
+        "traffic": measured_traffic("k_lane2_smooth") if args.n_time == 2**20 else None, "peak_source": hbm_src,
+        "algorithmic_bytes_per_step": BYTES_STEP_SMOOTH, "avg_launch_ms": smooth_ms,
+        "fp64_pipe_utilisation_ncu": measured_fp64_pipe("k_lane2_smooth"),
+        "lsu_pipe_utilisation_ncu": (measured_ncu("k_lane2_smooth", "lsu_pipe_pct") or 0) / 100.0 or None,
     }
     roofline_hbm = {
         "kernel": roofline["kernel"], "bound": "hbm", "achieved": BYTES_STEP_SCAN * n_loc / (scan_ms * 1e-3) / 1e9,
@@ -427,15 +470,15 @@ def run_native(args):
         "time_steps_per_s": N_total / (ms_iter * 1e-3),
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches * args.steps,
-        "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_iteration": roofline_iter,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_smooth": roofline_smooth,
+        "roofline_iteration": roofline_iter,
         "cpu_baseline": cpu, "clocks": clk,
         "scalars_last": {k: float(v) for k, v in (last.items() if isinstance(last, dict) else
                                                    zip(["nll", "obj", "ssq", "ssq_proper", "not_close"],
                                                        scalars.cpu().tolist()[:5]))},
     }
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":

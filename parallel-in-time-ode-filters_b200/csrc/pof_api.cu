@@ -37,6 +37,36 @@ static bool tree_fused() {
   return v == 1;
 }
 
+// Side stream on which the smoother's up-sweep runs concurrently with the filter scan: its inputs (the chunk-level
+// smoothing elements) only depend on the fold and the filter down-sweep, and its ~14 latency-bound levels fit into
+// the registers / shared memory the scan leaves free on every SM.  One stream + two events per device, created on
+// first use (eagerly, i.e. before any graph capture); fork/join through events, so the pass stays stream-ordered on
+// the caller's stream and is capturable.  POF_B200_OVERLAP=0 disables it.
+struct SideStream {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+static SideStream* side_stream() {
+  static SideStream tab[64];
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("POF_B200_OVERLAP");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& t = tab[dev];
+  if (!t.ok) {
+    if (cudaStreamCreateWithFlags(&t.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    t.ok = true;
+  }
+  return &t;
+}
+
 // thread-per-chunk reference kernels (pof_leaf.cuh)
 static const LeafLaunch* thread_launch(int d, int q) {
   switch (d) {
@@ -206,22 +236,46 @@ __global__ void __launch_bounds__(32)
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
-// out[j] = sum_i part[i*ncomp + j], fixed summation order (deterministic), single CTA
-__global__ void __launch_bounds__(256) k_reduce_parts(const double* __restrict__ part, long cnt, int ncomp,
-                                                      double* __restrict__ out) {
-  __shared__ double sh[256];
-  for (int j = 0; j < ncomp; ++j) {
-    double s = 0.0;
-    for (long i = threadIdx.x; i < cnt; i += 256) s += part[i * ncomp + j];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) out[j] = sh[0];
-    __syncthreads();
+// out[j] = sum_i part[i*NC + j], fixed summation order (deterministic), single CTA of 1024 threads: every thread
+// accumulates its strided share of all NC components with independent loads, then a shuffle tree per warp and one
+// over the 32 warp sums (the first version took 22 us per launch: 3 serial passes of dependent loads by 256 threads)
+template <int NC>
+__global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restrict__ part, long cnt,
+                                                         double* __restrict__ out) {
+  __shared__ double sh[32][NC];
+  double s[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) s[j] = 0.0;
+  for (long i = threadIdx.x; i < cnt; i += 1024) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s[j] += part[i * NC + j];
   }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_down_sync(0xffffffffu, s[j], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) sh[warp][j] = s[j];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      double v = sh[lane][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) out[j] = v;
+    }
+  }
+}
+static inline void reduce_parts(cudaStream_t s, const double* part, long cnt, int ncomp, double* out) {
+  if (ncomp == 2) k_reduce_parts_t<2><<<1, 1024, 0, s>>>(part, cnt, out);
+  else if (ncomp == 3) k_reduce_parts_t<3><<<1, 1024, 0, s>>>(part, cnt, out);
+  else if (ncomp == 4) k_reduce_parts_t<4><<<1, 1024, 0, s>>>(part, cnt, out);
+  else k_reduce_parts_t<5><<<1, 1024, 0, s>>>(part, cnt, out);
 }
 // scalars from the filter partial sums [nll, s1, s2] over n*d observations
 __global__ void k_finalize_filter(const double* __restrict__ sums, double n, double d, int calibrate,
@@ -516,6 +570,27 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   }
   POF_CK(cudaGetLastError());
   const bool pre = ll->has_pre_update && tl != nullptr;
+  SideStream* side = (pre && !fused) ? side_stream() : nullptr;
+  if (side) {
+    // chunk-level smoothing elements, then fork: smoother up-sweep on the side stream || filter scan on s
+    POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
+    POF_CK(cudaEventRecord(side->fork, s));
+    POF_CK(cudaStreamWaitEvent(side->s2, side->fork, 0));
+    {
+      ProfScope ps(SEG_SUP, side->s2);
+      for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l)
+        POF_CK(tl->sup(side->s2, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE,
+                       wl.tl.sz[l + 1]));
+    }
+    POF_CK(cudaEventRecord(side->join, side->s2));
+    {
+      ProfScope ps(SEG_SCAN, s);
+      POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, nullptr, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+    }
+    POF_CK(cudaStreamWaitEvent(s, side->join, 0));
+    reduce_parts(s, ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+    return (int)cudaGetLastError();
+  }
   {
     ProfScope ps(SEG_SCAN, s);
     POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, pre ? nullptr : sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
@@ -531,7 +606,7 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
       sa.root_L = sa.root_m + wl.D;
     }
     POF_CK(tl->ssweep(s, sa));
-    k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+    reduce_parts(s, ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
     return (int)cudaGetLastError();
   }
   // chunk-level smoothing elements straight from (incoming state, filtering element before its last update)
@@ -545,7 +620,7 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
       k_smooth_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
           wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
   }
-  k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+  reduce_parts(s, ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
   return (int)cudaGetLastError();
 }
 // stage C: smoother down-sweep from the seed (already stored at sin[root]) + smoother scan
@@ -582,7 +657,7 @@ static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     ProfScope ps(SEG_SMOOTH, s);
     POF_CK(ll->smooth(s, a, sin_, ws + wl.o_kern, emit_t0, cscale, means, chols, ws + wl.o_part2));
   }
-  k_reduce_parts<<<1, 256, 0, s>>>(ws + wl.o_part2, wl.CS, 2, ws + wl.o_sums + 8);
+  reduce_parts(s, ws + wl.o_part2, wl.CS, 2, ws + wl.o_sums + 8);
   return (int)cudaGetLastError();
 }
 

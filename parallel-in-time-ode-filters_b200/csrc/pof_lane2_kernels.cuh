@@ -96,7 +96,7 @@ struct Lane2Launchers {
   static cudaError_t scan(cudaStream_t s, const LeafArgs& a, const double* fin, double* kern, double* sagg,
                           double* send, double* part, double* fmeans, double* fchols) {
     if (sagg) return cudaErrorInvalidValue;
-    if (cudaError_t e = prep(k_lane2_scan<d, q>)) return e;
+    if (cudaError_t e = ensure_smem(k_lane2_scan<d, q>, LS::smem_bytes(), true)) return e;
     k_lane2_scan<d, q><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes(), s>>>(a, fin, kern, send, part, fmeans,
                                                                                   fchols);
     return cudaGetLastError();

@@ -153,7 +153,7 @@ struct TreeLaunchers {
     constexpr int CPW = 32 / G;
     constexpr int smem = TL_WARPS * CPW * TL::SM_COMBINE * (int)sizeof(double);
     if (nb <= 0) return cudaSuccess;
-    if (cudaError_t e = ensure_smem(k_tree<D, OP>, smem)) return e;
+    if (cudaError_t e = ensure_smem(k_tree<D, OP>, smem, OP == T_SUP)) return e;
     const long per_block = (long)TL_WARPS * CPW;
     k_tree<D, OP><<<(unsigned)((nb + per_block - 1) / per_block), TL_WARPS * 32, smem, s>>>(a, na, b, c, nb);
     return cudaGetLastError();

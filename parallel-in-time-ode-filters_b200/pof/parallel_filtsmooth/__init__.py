@@ -107,6 +107,33 @@ class GraphedIteration:
             self.graph.replay()
 
 
+class GraphedCall:
+    """Any stream-ordered, host-sync-free callable (e.g. one time-sharded iteration: linearise + ShardedPass.run with
+    its NCCL all-gathers) captured once into a CUDA graph and replayed.  `fn` must work on fixed buffers; its return
+    value (device tensors) is kept from the capture and returned by every replay."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.graph = None
+        self.out = None
+
+    def capture(self):
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                self.out = self.fn()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+
+    def __call__(self):
+        if self.graph is None:
+            return self.fn()
+        self.graph.replay()
+        return self.out
+
+
 def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None):
     """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq)"""
     n, d, q, D, qL = _model_dims(linear_transitions, linear_observations)

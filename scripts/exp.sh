@@ -1,4 +1,4 @@
-seg() { python -c "
-import json,sys; j=json.load(open(sys.argv[1])); print(sys.argv[1], round(j['value'],4), round(j['e2e']['value'],3), j['gpu_launches'], {k:round(v,4) for k,v in j['roofline_iteration']['segments_ms'].items()})" $1; }
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest19.log 2>&1; tail -4 gpurun_out/pytest19.log
-timeout 300 python bench.py --no-cpu-baseline > gpurun_out/b_A.json 2>gpurun_out/b_A.err; seg gpurun_out/b_A.json; tail -3 gpurun_out/b_A.err
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest22.log 2>&1; tail -3 gpurun_out/pytest22.log
+timeout 600 python bench.py > gpurun_out/bench10.json 2>gpurun_out/bench10.err; cat gpurun_out/bench10.json | head -c 600; echo; tail -3 gpurun_out/bench10.err
+timeout 300 python scripts/sweep_n.py --graph > gpurun_out/sweep_graph.log 2>&1; tail -15 gpurun_out/sweep_graph.log
+bash scripts/capture_profiles.sh r01f

@@ -1,14 +1,20 @@
 """Turn the ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-    python scripts/summarize_ncu.py <launch_list.csv> <full.ncu-rep> <tag>
+    python scripts/summarize_ncu.py <launch_list.csv> <full.ncu-rep> <tag> [<more.ncu-rep> ...]
+
+Also refreshes profiles/r01_traffic.json (dram bytes, FP64-pipe utilisation and LSU utilisation per kernel), which
+bench.py reads for `roofline.traffic` / `fp64_pipe_utilisation_ncu`.
 """
 import collections
 import csv
+import json
+import os
 import re
 import subprocess
 import sys
 
 launches, rep, tag = sys.argv[1:4]
+more_reps = sys.argv[4:]
 out_dir = "profiles"
 
 # ---- launch list: per-kernel share of one step
@@ -35,11 +41,7 @@ with open(f"{out_dir}/{tag}_launch_shares.md", "w") as fh:
         fh.write(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |\n")
     fh.write(f"| **sum** | {sum(v[0] for v in agg.values())} | {tot:.1f} | 100% |\n")
 
-# ---- full capture: key metrics per kernel
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-hdr, units = rr[0], rr[1]
-idx = {h: i for i, h in enumerate(hdr)}
+# ---- full captures: key metrics per kernel
 want = [
     "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -48,23 +50,53 @@ want = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
+
+
+def num(v, unit=""):
+    x = float(v.replace(",", ""))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1e-3, "usecond": 1e-3, "ms": 1.0,
+             "msecond": 1.0, "ns": 1e-6, "nsecond": 1e-6}.get(unit, 1.0)
+    return x * scale
+
+
+traffic_path = os.path.join(out_dir, "r01_traffic.json")
+try:
+    traffic = json.load(open(traffic_path))
+except Exception:
+    traffic = {}
 seen = {}
 with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as fh:
     fh.write(f"# {tag}: ncu --set full --clock-control none, first launch of each kernel\n\n")
-    for r in rr[2:]:
-        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
-        key = (name, r[idx.get("launch__grid_size", 0)])
-        if name in seen:
-            continue
-        seen[name] = 1
-        fh.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---|---|\n")
-        for w in want:
-            if w in idx:
-                fh.write(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |\n")
-        st = [(h, r[i]) for h, i in idx.items() if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h]
-        st = [(h, float(v.replace(",", ""))) for h, v in st if v not in ("", "n/a")]
-        st.sort(key=lambda x: -x[1])
-        fh.write("\nTop stall reasons (warps stalled per issue-active cycle): " + ", ".join(
-            f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}={v:.2f}"
-            for h, v in st[:6]) + "\n\n")
-print("wrote", f"{out_dir}/{tag}_launch_shares.md", f"{out_dir}/{tag}_ncu_full_summary.md")
+    for one in [rep] + more_reps:
+        raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rr = list(csv.reader(raw.splitlines()))
+        hdr, units = rr[0], rr[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        for r in rr[2:]:
+            name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("pof::", "")
+            if name in seen:
+                continue
+            seen[name] = 1
+            fh.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---|---|\n")
+            for w in want:
+                if w in idx:
+                    fh.write(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |\n")
+            st = [(h, r[i]) for h, i in idx.items()
+                  if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h]
+            st = [(h, float(v.replace(",", ""))) for h, v in st if v not in ("", "n/a")]
+            st.sort(key=lambda x: -x[1])
+            fh.write("\nTop stall reasons (warps stalled per issue-active cycle): " + ", ".join(
+                f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}={v:.2f}"
+                for h, v in st[:6]) + "\n\n")
+            g = lambda m: num(r[idx[m]], units[idx[m]])
+            traffic[name] = {
+                "dram_bytes_read": g("dram__bytes_read.sum"), "dram_bytes_write": g("dram__bytes_write.sum"),
+                "duration_ms_under_ncu": g("gpu__time_duration.sum"),
+                "fp64_pipe_pct": g("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                "lsu_pipe_pct": g("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "registers": g("launch__registers_per_thread"),
+                "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, N=2^20, FHN order 3)",
+            }
+json.dump(traffic, open(traffic_path, "w"), indent=1)
+print("wrote", f"{out_dir}/{tag}_launch_shares.md", f"{out_dir}/{tag}_ncu_full_summary.md", traffic_path)
