@@ -184,3 +184,77 @@ class _RowShift:
 
     def is_contiguous(self):
         return self.t.is_contiguous()
+
+
+def solve_sharded(*, f, y0, ts, order, init="constant", calibrate=True, maxiters=10_000, group=None, chunk_len=None,
+                  graph=True):
+    """The time-sharded form of `pof.solver.solve` (reference solver.py:11-73) for the built-in `pof.ivp` problems: one
+    process per GPU, rank r owns the contiguous rows `rows = slice(r0, k_hi + 1)` of the N grid points.  Every rank
+    runs the same IEKS loop; per iteration it linearises its shard (fused CUDA kernel, compact form), runs
+    `ShardedPass.run` (three stages, three small all-gathers) and evaluates the reference's stopping rule on scalars
+    that are bitwise identical on all ranks -- so all ranks leave the loop in the same iteration without any further
+    exchange.  After the first (eager) iteration the whole iteration is replayed from one CUDA graph per rank.
+
+    Returns (MVNSqrt(mean (rows, d), chol (rows, d, D)) of the local rows, info_dict, rows)."""
+    from .convenience import get_initial_trajectory, set_up_solver
+    from .convergence_criteria import crit_scalars
+    from .parallel_filtsmooth import GraphedCall
+    from .utils import MVNSqrt
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    setup = set_up_solver(f=f, y0=y0, ts=ts, order=order)
+    lin = setup["om"].f._pof_lin
+    if lin["builtin"] is None:
+        raise NotImplementedError("solve_sharded: built-in pof.ivp vector fields only (fused linearisation kernel)")
+    x0, dev = setup["x0"], setup["_device"]
+    d, q = lin["d"], order
+    D = d * (q + 1)
+    N = len(setup["ts"])
+    sp = ShardedPass(N, d, q, setup["_qL"], rank=rank, world=world, group=group, device=dev, chunk_len=chunk_len)
+    sp.backend.set_compact(lin["scale0"], lin["scale1"])
+    r0 = 0 if sp.has_row0 else sp.k_lo + 1
+    rows = slice(r0, sp.k_hi + 1)
+    full = get_initial_trajectory(setup, method=init)
+    means = full.mean[rows].contiguous().clone()
+    del full
+    chols = torch.empty((sp.rows, D, D), dtype=torch.float64, device=dev)
+    Jc = torch.empty((sp.n_loc, d * d + d), dtype=torch.float64, device=dev)
+    t1row = 1 if sp.has_row0 else 0
+    ivp_id, params = lin["builtin"]
+    ph, pp = nat.host_doubles(list(params) + [0.0])
+    out5 = torch.zeros(5, dtype=torch.float64, device=dev)
+
+    def iteration():
+        nat.check(nat.LIB.pof_linearize_ivp_compact_f64(nat.stream_ptr(), ivp_id, pp, len(params), sp.n_loc, d, q,
+                                                        lin["scale0"], nat.ptr(means[t1row:]), nat.ptr(Jc)),
+                  "linearize")
+        res = sp.run(x0.mean, x0.chol, Jc, None, means, chols, calibrate=True)  # the loop always calibrates
+        out5.copy_(torch.stack([res["nll"], res["obj"], res["ssq"], res["ssq_proper"], res["not_close"]]))
+        return out5
+
+    step = GraphedCall(iteration)
+    nll = obj = ssq = ssqp = 0.0
+    nll_old = obj_old = 0.0
+    n_bad = 1.0
+    k = 0
+    while True:
+        if k >= 1:
+            if crit_scalars(obj, obj_old, nll, nll_old, n_bad) or not (k <= maxiters):
+                break
+        nll_old, obj_old = nll, obj
+        if graph and step.graph is None and k >= 1 and dev.type == "cuda":
+            step.capture()
+        sc = step().cpu()
+        nll, obj, ssq, ssqp, n_bad = (float(v) for v in sc)
+        k += 1
+    info = {"iterations": k, "nll": nll, "obj": obj, "sigma_squared": ssq, "calibrated": bool(calibrate),
+            "sigma_squared_proper": ssqp}
+    # final calibration (the second one, solver.py:66-69) fused with the E0 projection (solver.py:71)
+    ymean = torch.empty((sp.rows, d), dtype=torch.float64, device=dev)
+    ychol = torch.empty((sp.rows, d, D), dtype=torch.float64, device=dev)
+    mult = sp.cscale if calibrate else None  # sqrt(sigma^2) of the last pass, identical on every rank
+    nat.check(nat.LIB.pof_project_f64(nat.stream_ptr(), sp.rows, d, q, setup["_scale0"], nat.ptr(mult),
+                                      nat.ptr(means), nat.ptr(chols), nat.ptr(ymean), nat.ptr(ychol)), "project")
+    step.graph = None  # release the captured NCCL work before the caller tears the process group down
+    return MVNSqrt(ymean, ychol), info, rows

@@ -355,3 +355,22 @@ def test_dense_H_seam_matches_fused_iteration(native_lib):
     np.testing.assert_allclose(s1.cpu().numpy()[:4], s2.cpu().numpy()[:4], rtol=1e-10)
     np.testing.assert_allclose(_cov(c1.cpu().numpy()), _cov(c2.cpu().numpy()), rtol=0,
                                atol=1e-10 * float(_cov(c1.cpu().numpy()).max()))
+
+
+def test_solve_sharded_single_rank_matches_solve(native_lib):
+    """pof.sharded.solve_sharded without a process group (world size 1) runs the three shard stages and the
+    graph-replayed loop on one GPU: same iterations and solution as pof.solver.solve"""
+    import pof.ivp
+    from pof.sharded import solve_sharded
+    from pof.solver import solve
+
+    ivp = pof.ivp.lotkavolterra()
+    ts = np.linspace(ivp.t0, ivp.tmax, 3000)
+    ys, info, rows = solve_sharded(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=1000)
+    ref, rinfo = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=1000)
+    assert rows == slice(0, 3000)
+    assert abs(info["iterations"] - rinfo["iterations"]) <= 1
+    y, yr = ys.mean.cpu().numpy(), ref.mean.cpu().numpy()
+    assert (np.abs(y - yr) <= 1e-7 * np.abs(yr).max(axis=0) + 1e-12).all()
+    C, Cr = _cov(ys.chol.cpu().numpy()), _cov(ref.chol.cpu().numpy())
+    assert np.abs(C - Cr).max() <= 1e-6 * np.abs(Cr).max()

@@ -77,3 +77,53 @@ def test_sharded_nccl_matches_single_gpu(native_lib, N, q):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     for r in range(world):
         assert ret[r][0], ret[r]
+
+
+def _solve_worker(rank, world, port, N, q, ret):
+    import torch.distributed as dist
+
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "parallel-in-time-ode-filters_b200")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import pof.ivp
+        from pof.sharded import solve_sharded
+        from pof.solver import solve
+
+        ivp = pof.ivp.lotkavolterra()
+        ts = np.linspace(ivp.t0, ivp.tmax, N)
+        ys, info, rows = solve_sharded(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant", maxiters=1000)
+        ref, rinfo = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant", maxiters=1000)
+        torch.cuda.synchronize()
+        em = float((ys.mean - ref.mean[rows]).abs().max() / ref.mean.abs().max())
+        cov = lambda L: L @ L.transpose(-1, -2)
+        ec = float((cov(ys.chol) - cov(ref.chol[rows])).abs().max() / cov(ref.chol).abs().max())
+        ok = abs(info["iterations"] - rinfo["iterations"]) <= 1 and em < 1e-7 and ec < 1e-6
+        ret[rank] = (bool(ok), info["iterations"], rinfo["iterations"], em, ec)
+    finally:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+
+
+def test_solve_sharded_nccl_matches_single_gpu(native_lib):
+    """the sharded IEKS loop (graph-replayed iterations with NCCL all-gathers) against pof.solver.solve"""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_worker, args=(r, world, port, 20000, 3, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for r in range(world):
+        assert ret[r][0], ret[r]
