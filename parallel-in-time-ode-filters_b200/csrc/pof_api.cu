@@ -488,8 +488,11 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
 
 static void fill_sweep(SweepArgs& sa, const WsLayout& wl, double* agg, double* st, int up_levels, int do_down) {
   sa.nlev = wl.tl.nlev;
-  sa.up_levels = up_levels < 0 ? 0 : up_levels;
-  sa.do_down = do_down;
+  sa.up_begin = 0;
+  sa.up_end = up_levels < 0 ? 0 : up_levels;
+  sa.down_begin = do_down ? wl.tl.nlev - 1 : 0;
+  sa.down_end = 0;
+  sa.block_sync = 0;
   for (int l = 0; l < SweepArgs::MAXL; ++l) {
     sa.off[l] = l < wl.tl.nlev ? wl.tl.off[l] : 0;
     sa.sz[l] = l < wl.tl.nlev ? wl.tl.sz[l] : 0;
@@ -498,6 +501,31 @@ static void fill_sweep(SweepArgs& sa, const WsLayout& wl, double* agg, double* s
   sa.st = st;
   sa.root_m = sa.root_L = nullptr;
   sa.faggm = sa.fin = nullptr;
+}
+// The apex of a tree: the levels whose nodes fit into ONE CTA of the sweep kernel (cap nodes per level).  They run in
+// a single launch with __syncthreads between levels: warm instruction cache and no kernel boundary for the ~4 levels
+// at the top of the up-sweep and of the down-sweep, where a launch costs a full cold-start combine (~10 us) for a
+// handful of nodes.  POF_B200_TREE_APEX=0 disables it.
+static bool apex_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("POF_B200_TREE_APEX");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+// first up-sweep level l (building level l+1) that fits the apex: sz[l+1] <= cap; up_total = number of up levels
+static int apex_up_begin(const WsLayout& wl, int up_total, int cap) {
+  int l = 0;
+  while (l < up_total && wl.tl.sz[l + 1] > cap) ++l;
+  return l;
+}
+// the down-sweep runs l = nlev-1 .. 1 (level l-1 from level l); apex while sz[l] <= cap: returns the level at which the
+// per-level launches take over (apex covers l = nlev-1 .. ret+1)
+static int apex_down_end(const WsLayout& wl, int cap) {
+  int l = wl.tl.nlev - 1;
+  while (l >= 1 && wl.tl.sz[l] <= cap) --l;
+  return l;
 }
 
 // stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
@@ -525,7 +553,21 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   const int tw = tree_warps(wl.D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
   POF_CK(set_smem(k_filter_up, smem));
-  for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l) {
+  const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
+  const int a_up = (tl && apex_enabled()) ? apex_up_begin(wl, up_total, tl->fcap) : up_total;
+  if (tl && a_up < up_total && need_root) {  // sharded: the apex of the up-sweep here (single GPU: in stage_b)
+    SweepArgs sa;
+    fill_sweep(sa, wl, fagg, ws + wl.o_fin, 0, 0);
+    sa.up_begin = a_up;
+    sa.up_end = up_total;
+    sa.block_sync = 1;
+    for (int l = 0; l < a_up; ++l)
+      POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE,
+                     wl.tl.sz[l + 1]));
+    POF_CK(tl->fsweep(s, sa));
+    return (int)cudaGetLastError();
+  }
+  for (int l = 0; l < (tl ? a_up : up_total); ++l) {
     const long np = wl.tl.sz[l + 1];
     if (tl)
       POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE, np));
@@ -557,7 +599,25 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     POF_CK(tl->fsweep(s, sa));
   } else {
   ProfScope ps(SEG_FDOWN, s);
-  for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+  int l_start = wl.tl.nlev - 1;
+  if (tl && apex_enabled()) {
+    // apex: (single GPU) the top of the up-sweep left over by stage_a, then the top of the down-sweep, one CTA
+    const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
+    const int a_up = need_root ? up_total : apex_up_begin(wl, up_total, tl->fcap);
+    const int a_dn = apex_down_end(wl, tl->fcap);
+    if (a_up < up_total || a_dn < wl.tl.nlev - 1) {
+      SweepArgs sa;
+      fill_sweep(sa, wl, fagg, fin, 0, 0);
+      sa.up_begin = a_up;
+      sa.up_end = up_total;
+      sa.down_begin = wl.tl.nlev - 1;
+      sa.down_end = a_dn;
+      sa.block_sync = 1;
+      POF_CK(tl->fsweep(s, sa));
+      l_start = a_dn;
+    }
+  }
+  for (int l = l_start; l >= 1; --l) {
     const long np = wl.tl.sz[l];
     if (tl)
       POF_CK(tl->fdown(s, fin + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], fagg + wl.tl.off[l - 1] * wl.FE,
@@ -578,9 +638,19 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     POF_CK(cudaStreamWaitEvent(side->s2, side->fork, 0));
     {
       ProfScope ps(SEG_SUP, side->s2);
-      for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l)
+      const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
+      const int a_up = apex_enabled() ? apex_up_begin(wl, up_total, tl->scap) : up_total;
+      for (int l = 0; l < a_up; ++l)
         POF_CK(tl->sup(side->s2, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE,
                        wl.tl.sz[l + 1]));
+      if (a_up < up_total) {
+        SweepArgs sa;
+        fill_sweep(sa, wl, sagg, ws + wl.o_sin, 0, 0);
+        sa.up_begin = a_up;
+        sa.up_end = up_total;
+        sa.block_sync = 1;
+        POF_CK(tl->ssweep(side->s2, sa));
+      }
     }
     POF_CK(cudaEventRecord(side->join, side->s2));
     {
@@ -641,7 +711,20 @@ static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     POF_CK(tl->ssweep(s, sa));
   } else {
   ProfScope ps(SEG_SDOWN, s);
-  for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+  int l_start = wl.tl.nlev - 1;
+  if (tl && apex_enabled()) {
+    const int a_dn = apex_down_end(wl, tl->scap);
+    if (a_dn < wl.tl.nlev - 1) {
+      SweepArgs sa;
+      fill_sweep(sa, wl, sagg, sin_, 0, 0);
+      sa.down_begin = wl.tl.nlev - 1;
+      sa.down_end = a_dn;
+      sa.block_sync = 1;
+      POF_CK(tl->ssweep(s, sa));
+      l_start = a_dn;
+    }
+  }
+  for (int l = l_start; l >= 1; --l) {
     const long np = wl.tl.sz[l];
     if (tl)
       POF_CK(tl->sdown(s, sin_ + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], sagg + wl.tl.off[l - 1] * wl.SE,

@@ -193,8 +193,10 @@ struct Lane {
 #pragma unroll
     for (int j = 0; j < n; ++j) sigma = fma(x[j], x[j], sigma);
     HH h;
-    h.nz = sigma > 0.0;
     const double nrm2 = fma(alpha, alpha, sigma);
+    // rsqrt.approx.ftz flushes subnormal inputs to zero (-> inf -> NaN in the Newton step): a row whose squared norm
+    // is below 2^-1000 is treated as already reduced (identity reflector), as a zero tail is
+    h.nz = sigma > 0.0 && nrm2 > 0x1p-1000;
     const double rn = fast_rsqrt(nrm2);  // 1 / norm
     const double nrm = nrm2 * rn;
     const double beta = (alpha >= 0.0) ? -nrm : nrm;

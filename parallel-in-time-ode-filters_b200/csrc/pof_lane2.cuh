@@ -169,8 +169,10 @@ struct Lane2 {
   template <int n>
   static __device__ __forceinline__ HH house(double alpha, const double* x) {
     const double sigma = dotn<n>(x, x);
-    const bool nz = sigma > 0.0;
     const double nrm2 = fma(alpha, alpha, sigma);
+    // rsqrt.approx.ftz flushes subnormal inputs to zero (-> inf -> NaN in the Newton step): a row whose squared norm
+    // is below 2^-1000 is treated as already reduced (identity reflector), as a zero tail is
+    const bool nz = sigma > 0.0 && nrm2 > 0x1p-1000;
     const double rn = fast_rsqrt(nrm2);
     const double nrm = nrm2 * rn;
     const double beta = (alpha >= 0.0) ? -nrm : nrm;

@@ -95,8 +95,10 @@ const LeafLaunch* lane2_launch_d4(int q);
 struct SweepArgs {
   static constexpr int MAXL = 48;
   int nlev;          // levels of the tree (level 0 = chunks)
-  int up_levels;     // up-sweep: build levels 1 .. up_levels (0: none)
-  int do_down;       // down-sweep from the root to level 0 afterwards
+  int up_begin, up_end;      // up-sweep: for l in [up_begin, up_end): level l+1 <- pairs of level l
+  int down_begin, down_end;  // down-sweep: for l = down_begin; l > down_end; --l: level l-1 <- level l
+  int block_sync;    // 1: launched as ONE CTA, levels separated by __syncthreads (the apex of the tree: levels with
+                     // at most one CTA's worth of nodes); 0: cooperative launch, grid barrier per level
   long off[MAXL], sz[MAXL];
   double* agg;       // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
   double* st;        // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
@@ -112,7 +114,8 @@ struct TreeLaunch {
   typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
   Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk;
   typedef cudaError_t (*SweepFn)(cudaStream_t, const SweepArgs&);
-  SweepFn fsweep, ssweep;  // cooperative whole-sweep kernels (filtering / smoothing)
+  SweepFn fsweep, ssweep;  // whole-sweep kernels (filtering / smoothing): cooperative, or one CTA for the apex
+  int fcap, scap;          // nodes one CTA of the sweep kernel processes per level (filtering / smoothing)
 };
 const TreeLaunch* tree_launch_a(int D);
 const TreeLaunch* tree_launch_b(int D);

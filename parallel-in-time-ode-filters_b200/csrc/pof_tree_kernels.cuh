@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_sweep(const SweepArgs A)
       const long ng = (long)gridDim.x * TL_WARPS * CPW2;
       for (long i = ((long)blockIdx.x * TL_WARPS + warp) * CPW2 + lane / G2; i < A.sz[0]; i += ng)
         TL::chunk_kernel(cx, A.fin + i * ST, A.faggm + i * FE, A.agg + i * SE);
-      grid.sync();
+      if (A.block_sync) __syncthreads(); else grid.sync();
     }
   }
   constexpr int CPW = 32 / G;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_sweep(const SweepArgs A)
   const long g0 = ((long)blockIdx.x * TL_WARPS + warp) * CPW + lane / G;
   const long ng = (long)gridDim.x * TL_WARPS * CPW;
   // ---- up-sweep
-  for (int l = 0; l < A.up_levels; ++l) {
+  for (int l = A.up_begin; l < A.up_end; ++l) {
     const double* ch = A.agg + A.off[l] * EL;
     double* pa = A.agg + A.off[l + 1] * EL;
     const long na = A.sz[l], nb = A.sz[l + 1];
@@ -110,17 +110,19 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_sweep(const SweepArgs A)
         group_copy<D, G>(cx.r, pa + i * EL, lc, EL);
       }
     }
-    grid.sync();
+    if (A.block_sync) __syncthreads(); else grid.sync();
   }
-  if (!A.do_down) return;
+  if (A.down_begin <= A.down_end) return;
   // ---- root state
   if (A.root_m && g0 == 0) {
     double* r = A.st + A.off[A.nlev - 1] * ST;
     for (int i = cx.r; i < ST; i += G) r[i] = (i < D) ? A.root_m[i] : A.root_L[i - D];
   }
-  if (A.root_m) grid.sync();
+  if (A.root_m) {
+    if (A.block_sync) __syncthreads(); else grid.sync();
+  }
   // ---- down-sweep (state form)
-  for (int l = A.nlev - 1; l >= 1; --l) {
+  for (int l = A.down_begin; l > A.down_end; --l) {
     const double* ps = A.st + A.off[l] * ST;
     const double* el = A.agg + A.off[l - 1] * EL;
     double* cs = A.st + A.off[l - 1] * ST;
@@ -139,7 +141,9 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_sweep(const SweepArgs A)
         }
       }
     }
-    if (l > 1) grid.sync();
+    if (l > A.down_end + 1) {
+      if (A.block_sync) __syncthreads(); else grid.sync();
+    }
   }
 }
 
@@ -178,9 +182,13 @@ struct TreeLaunchers {
       if (per_sm < 1) return cudaErrorLaunchOutOfResources;
       max_grid[dev] = per_sm * sms;
     }
+    if (A.block_sync) {  // the apex: one CTA, plain launch
+      k_tree_sweep<D, FILT><<<1, TL_WARPS * 32, smem, s>>>(A);
+      return cudaGetLastError();
+    }
     long widest = 1;
-    if (A.up_levels > 0) widest = A.sz[1];
-    if (A.do_down && A.nlev >= 2 && A.sz[1] > widest) widest = A.sz[1];
+    if (A.up_end > A.up_begin) widest = A.sz[A.up_begin + 1];
+    if (A.down_begin > A.down_end && A.sz[A.down_end + 1] > widest) widest = A.sz[A.down_end + 1];
     long blocks = (widest + (long)TL_WARPS * (32 / G) - 1) / ((long)TL_WARPS * (32 / G));
     if (!FILT && A.faggm) {
       const long b2 = (A.sz[0] + (long)TL_WARPS * CPWmin - 1) / ((long)TL_WARPS * CPWmin);
@@ -195,7 +203,8 @@ struct TreeLaunchers {
   }
   static const TreeLaunch* get() {
     static const TreeLaunch t = {&run<T_FUP>, &run<T_FDOWN>, &run<T_SUP>, &run<T_SDOWN>, &run<T_FCOMB>, &run<T_SCOMB>,
-                                 &run<T_CHUNKK>, &sweep<true>, &sweep<false>};
+                                 &run<T_CHUNKK>, &sweep<true>, &sweep<false>,
+                                 TL_WARPS * (32 / TL::G2), TL_WARPS * (32 / TL::GS)};
     return &t;
   }
 };

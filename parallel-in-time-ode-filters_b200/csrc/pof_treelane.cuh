@@ -107,8 +107,8 @@ struct TreeLane {
   template <int n>
   static __device__ __forceinline__ HH house(double alpha, const double* x) {
     const double sigma = dotn<n>(x, x);
-    const bool nz = sigma > 0.0;
     const double nrm2 = fma(alpha, alpha, sigma);
+    const bool nz = sigma > 0.0 && nrm2 > 0x1p-1000;  // see pof_lane2.cuh: subnormal norms would turn into NaN
     const double rn = fast_rsqrt(nrm2);
     const double nrm = nrm2 * rn;
     const double beta = (alpha >= 0.0) ? -nrm : nrm;
