@@ -364,7 +364,7 @@ def test_solve_sharded_single_rank_matches_solve(native_lib):
     from pof.sharded import solve_sharded
     from pof.solver import solve
 
-    ivp = pof.ivp.lotkavolterra()
+    ivp = pof.ivp.rigid_body()
     ts = np.linspace(ivp.t0, ivp.tmax, 3000)
     ys, info, rows = solve_sharded(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=1000)
     ref, rinfo = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=1000)

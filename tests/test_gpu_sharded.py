@@ -12,22 +12,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+    """rendezvous file for the file:// init method (a probed-free TCP port was taken again before rank 0 listened on it
+    once, which cost a 300 s hang on the GPU box)"""
+    import tempfile
+
+    fd, path = tempfile.mkstemp(prefix="pof_rdzv_")
+    os.close(fd)
+    os.unlink(path)
+    return path
 
 
 def _worker(rank, world, port, N, q, ret):
     import torch.distributed as dist
 
     sys.path[:0] = [ROOT, os.path.join(ROOT, "parallel-in-time-ode-filters_b200")]
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", init_method=f"file://{port}", rank=rank, world_size=world, device_id=dev)
     try:
         import pof.ivp
         from pof.convenience import get_initial_trajectory, set_up_solver
@@ -73,7 +74,10 @@ def test_sharded_nccl_matches_single_gpu(native_lib, N, q):
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, N, q, ret)) for r in range(world)]
     [p.start() for p in procs]
-    [p.join(600) for p in procs]
+    [p.join(180) for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     for r in range(world):
         assert ret[r][0], ret[r]
@@ -83,17 +87,17 @@ def _solve_worker(rank, world, port, N, q, ret):
     import torch.distributed as dist
 
     sys.path[:0] = [ROOT, os.path.join(ROOT, "parallel-in-time-ode-filters_b200")]
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", init_method=f"file://{port}", rank=rank, world_size=world, device_id=dev)
     try:
         import pof.ivp
         from pof.sharded import solve_sharded
         from pof.solver import solve
 
-        ivp = pof.ivp.lotkavolterra()
+        # rigid body: 10 iterations at every N (Lotka-Volterra at N ~ 2e4 sits at the edge of the IEKS's divergence:
+        # there the iteration count depends on the association order of the scan, cf. profiles/r01_work_precision_*)
+        ivp = pof.ivp.rigid_body()
         ts = np.linspace(ivp.t0, ivp.tmax, N)
         ys, info, rows = solve_sharded(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant", maxiters=1000)
         ref, rinfo = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant", maxiters=1000)
@@ -103,9 +107,12 @@ def _solve_worker(rank, world, port, N, q, ret):
         ec = float((cov(ys.chol) - cov(ref.chol[rows])).abs().max() / cov(ref.chol).abs().max())
         ok = abs(info["iterations"] - rinfo["iterations"]) <= 1 and em < 1e-7 and ec < 1e-6
         ret[rank] = (bool(ok), info["iterations"], rinfo["iterations"], em, ec)
-    finally:
         torch.cuda.synchronize()
-        dist.destroy_process_group()
+        # leave without tearing the process group down: NCCL kernels captured in CUDA graphs made
+        # destroy_process_group hang once (bench.py leaves the same way)
+        os._exit(0)
+    finally:
+        pass
 
 
 def test_solve_sharded_nccl_matches_single_gpu(native_lib):
@@ -120,7 +127,7 @@ def test_solve_sharded_nccl_matches_single_gpu(native_lib):
     port = _free_port()
     procs = [ctx.Process(target=_solve_worker, args=(r, world, port, 20000, 3, ret)) for r in range(world)]
     [p.start() for p in procs]
-    [p.join(300) for p in procs]
+    [p.join(180) for p in procs]
     for p in procs:
         if p.is_alive():
             p.kill()
