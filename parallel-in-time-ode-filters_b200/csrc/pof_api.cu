@@ -786,9 +786,20 @@ int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
   const LeafLaunch* ll = leaf_launch(d, q);
   if (ll && ll->has_pre_update && tree_launch(wl.D) && tree_fused())
     return 3 /*leaf*/ + 2 /*cooperative tree sweeps*/ + 1 /*pack*/ + 2 /*reduce*/ + 2 /*finalize*/;
-  const int64_t downs = 2 * (int64_t)(wl.tl.nlev - 1);
-  const int64_t ups = 2 * (int64_t)(wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0);  // the root combine is skipped on one GPU
-  return 3 /*leaf*/ + downs + ups /*tree sweeps*/ + 1 /*chunk smoothing elements*/ + 1 /*pack*/ + 2 /*reduce*/ +
+  const int up_total = wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0;  // the root combine is skipped on one GPU
+  const int down_total = wl.tl.nlev - 1;
+  const TreeLaunch* tl = tree_launch(wl.D);
+  int64_t tree = 2 * (int64_t)(up_total + down_total);
+  if (tl && apex_enabled()) {  // the top levels of each sweep run in one single-CTA launch (stage_a / stage_b / stage_c)
+    const int fu = apex_up_begin(wl, up_total, tl->fcap), fd = apex_down_end(wl, tl->fcap);
+    const int su = apex_up_begin(wl, up_total, tl->scap), sd = apex_down_end(wl, tl->scap);
+    // the smoother's up-sweep has its apex only on the side-stream path (two-rows-per-lane leaves, overlap enabled)
+    const bool sup_apex = ll && ll->has_pre_update && side_stream() != nullptr;
+    tree = fu + fd + ((fu < up_total || fd < down_total) ? 1 : 0)  // filter: per-level ups and downs, one apex
+           + (sup_apex ? su + ((su < up_total) ? 1 : 0) : up_total) + sd + ((sd < down_total) ? 1 : 0);
+  }
+  const int64_t chunkk = (ll && ll->has_pre_update && tl) ? 1 : 0;
+  return 3 /*leaf*/ + tree /*tree sweeps*/ + chunkk /*chunk smoothing elements*/ + 1 /*pack*/ + 2 /*reduce*/ +
          2 /*finalize*/;
 }
 
