@@ -144,7 +144,21 @@ def henonheiles(t0=0.0, tmax=100.0, y0=None, p=None):
     )
 
 
+def lorenz96(t0=0.0, tmax=10.0, y0=None, d=16, forcing=8.0):
+    """Not in pof/ivp.py: the larger-state problem of BASELINE config 5: Lorenz-96,
+    f_i = (y_{i+1} - y_{i-2}) y_{i-1} - y_i + F (cyclic), y0_i = F + 0.01 sin(i)."""
+    if y0 is None:
+        y0 = [forcing + 0.01 * np.sin(i) for i in range(d)]
+    d = len(y0)
+    return _make(
+        "lorenz96",
+        lambda y: [(y[(i + 1) % d] - y[(i - 2) % d]) * y[(i - 1) % d] - y[i] + forcing for i in range(d)],
+        y0, t0, tmax,
+    )
+
+
 ALL = dict(
     logistic=logistic, lotkavolterra=lotkavolterra, vanderpol=vanderpol, fitzhughnagumo=fitzhughnagumo,
     rober=rober, rigid_body=rigid_body, seir=seir, threebody=threebody, henonheiles=henonheiles,
+    lorenz96=lorenz96,
 )

@@ -1,10 +1,13 @@
 // Host simulator (TEST INFRASTRUCTURE ONLY): runs the exact per-thread / per-warp device code of
 // parallel-in-time-ode-filters_b200/csrc on the CPU, with the same chunking, tree schedule and memory layout the
 // CUDA kernels use, so the math can be checked against the oracle without a GPU.  Never loaded by the product.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "pof_pipeline.cuh"
+#include "pof_tile.cuh"
 
 using namespace pof;
 
@@ -271,5 +274,126 @@ int hs_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const d
   CASE(1, 1) CASE(1, 2) CASE(1, 3) CASE(1, 4) CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(3, 3) CASE(4, 2) CASE(4, 3)
 #undef CASE
   return -1;
+}
+}
+
+// ---- large-state ("tile") family: CTA-cooperative device code of pof_tile.cuh, executed by a one-thread team whose
+// iteration order inside every Team::each is selectable (0 forward, 1 reverse, 2 permuted): identical results under
+// all orders <=> the iterations of every each() are independent <=> the CUDA kernels are race-free (pof_tile.cuh).
+static int run_tile(int d, int q, long N, long L, const double* qL, const double* x0, const double* H, const double* c,
+                    const double* Jc, double s0, double s1, const double* R, double* means, double* chols,
+                    double* fmeans, double* fchols, int calibrate, double* scalars, int order) {
+  Team::order() = order;
+  Team t;
+  const int D = d * (q + 1);
+  const long n = N - 1;
+  const long CS = (n + L - 1) / L;
+  const int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D, NE = D + 2 * D * D;
+  TreeLevels tl;
+  tl.build(CS);
+  std::vector<double> fagg(tl.total * FE), faggm(CS * FE), fin(tl.total * ST), sagg(tl.total * SE), sin_(tl.total * ST);
+  std::vector<double> kern((size_t)n * NE), send(CS * ST), part(CS * 3), part2(CS * 2);
+  std::vector<double> smem(std::max({tile_fold_smem_doubles(D, d), tile_scan_smem_doubles(D, d),
+                                     tile_smooth_smem_doubles(D, d), tile_tree_smem_doubles(D)}));
+  // poison the shared memory so that reads of never-written entries show up as NaN
+  auto poison = [&]() { std::fill(smem.begin(), smem.end(), std::nan("")); };
+  const TileLin lin = {H, c, Jc, R, s0, s1};
+  for (long ch = 0; ch < CS; ++ch) {
+    poison();
+    tile_fold(t, d, q, qL, lin, ch * L, std::min((ch + 1) * L, n), &fagg[ch * FE], &faggm[ch * FE], smem.data());
+  }
+  for (int l = 0; l + 1 < tl.nlev; ++l)
+    for (long i = 0; i < tl.sz[l + 1]; ++i) {
+      double* par = &fagg[(tl.off[l + 1] + i) * FE];
+      const double* lc = &fagg[(tl.off[l] + 2 * i) * FE];
+      poison();
+      if (2 * i + 1 < tl.sz[l]) tile_filter_combine(t, D, lc, lc + FE, par, smem.data(), false);
+      else std::memcpy(par, lc, FE * sizeof(double));
+    }
+  std::memcpy(&fin[(tl.off[tl.nlev - 1]) * ST], x0, ST * sizeof(double));
+  for (int l = tl.nlev - 1; l >= 1; --l)
+    for (long i = 0; i < tl.sz[l]; ++i) {
+      const double* pin = &fin[(tl.off[l] + i) * ST];
+      std::memcpy(&fin[(tl.off[l - 1] + 2 * i) * ST], pin, ST * sizeof(double));
+      poison();
+      if (2 * i + 1 < tl.sz[l - 1])
+        tile_filter_combine(t, D, pin, &fagg[(tl.off[l - 1] + 2 * i) * FE], &fin[(tl.off[l - 1] + 2 * i + 1) * ST],
+                            smem.data(), true);
+    }
+  if (fmeans) {
+    std::memcpy(fmeans, x0, D * sizeof(double));
+    std::memcpy(fchols, x0 + D, D * D * sizeof(double));
+  }
+  for (long ch = 0; ch < CS; ++ch) {
+    poison();
+    tile_chunk_kernel(t, D, &fin[ch * ST], &faggm[ch * FE], &sagg[ch * SE], smem.data());
+    poison();
+    tile_scan(t, d, q, qL, lin, ch * L, std::min((ch + 1) * L, n), &fin[ch * ST], kern.data(), &send[ch * ST],
+              &part[ch * 3], fmeans, fchols, smem.data());
+  }
+  double nll = 0, a1 = 0, a2 = 0;
+  for (long ch = 0; ch < CS; ++ch) { nll += part[ch * 3]; a1 += part[ch * 3 + 1]; a2 += part[ch * 3 + 2]; }
+  const double ssq = a1 / n / d, ssqp = a2 / n / d;
+  for (int l = 0; l + 1 < tl.nlev; ++l)
+    for (long i = 0; i < tl.sz[l + 1]; ++i) {
+      double* par = &sagg[(tl.off[l + 1] + i) * SE];
+      const double* lc = &sagg[(tl.off[l] + 2 * i) * SE];
+      poison();
+      if (2 * i + 1 < tl.sz[l]) tile_smooth_combine(t, D, lc + SE, lc, par, smem.data(), false);
+      else std::memcpy(par, lc, SE * sizeof(double));
+    }
+  std::memcpy(&sin_[(tl.off[tl.nlev - 1]) * ST], &send[(CS - 1) * ST], ST * sizeof(double));
+  for (int l = tl.nlev - 1; l >= 1; --l)
+    for (long i = 0; i < tl.sz[l]; ++i) {
+      const double* pin = &sin_[(tl.off[l] + i) * ST];
+      if (2 * i + 1 < tl.sz[l - 1]) {
+        std::memcpy(&sin_[(tl.off[l - 1] + 2 * i + 1) * ST], pin, ST * sizeof(double));
+        poison();
+        tile_smooth_combine(t, D, pin, &sagg[(tl.off[l - 1] + 2 * i + 1) * SE], &sin_[(tl.off[l - 1] + 2 * i) * ST],
+                            smem.data(), true);
+      } else {
+        std::memcpy(&sin_[(tl.off[l - 1] + 2 * i) * ST], pin, ST * sizeof(double));
+      }
+    }
+  const double cscale = calibrate ? sqrt(ssq) : 1.0;
+  for (long ch = 0; ch < CS; ++ch) {
+    poison();
+    tile_smooth(t, d, q, qL, ch * L, std::min((ch + 1) * L, n), ch == CS - 1, true, &sin_[ch * ST], kern.data(), cscale,
+                means, chols, &part2[ch * 2], smem.data());
+  }
+  double obj = 0, bad = 0;
+  for (long ch = 0; ch < CS; ++ch) { obj += part2[ch * 2]; bad += part2[ch * 2 + 1]; }
+  scalars[0] = nll; scalars[1] = obj; scalars[2] = ssq; scalars[3] = ssqp; scalars[4] = bad;
+  Team::order() = 0;
+  return 0;
+}
+
+extern "C" {
+int hs_tile_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const double* x0, const double* H,
+                              const double* c, const double* Jc, double s0, double s1, const double* R, double* means,
+                              double* chols, double* fmeans, double* fchols, int calibrate, double* scalars,
+                              int order) {
+  return run_tile(d, q, N, L, qL, x0, H, c, Jc, s0, s1, R, means, chols, fmeans, fchols, calibrate, scalars, order);
+}
+int hs_tile_filter_combine(int D, const double* e1, const double* e2, double* out, int state_mode, int order) {
+  std::vector<double> smem(tile_tree_smem_doubles(D), std::nan(""));
+  Team::order() = order;
+  Team t;
+  tile_filter_combine(t, D, e1, e2, out, smem.data(), state_mode != 0);
+  Team::order() = 0;
+  return 0;
+}
+int hs_tile_smooth_combine(int D, const double* e1, const double* e2, double* out, int state_mode, int order) {
+  std::vector<double> smem(tile_tree_smem_doubles(D), std::nan(""));
+  Team::order() = order;
+  Team t;
+  tile_smooth_combine(t, D, e1, e2, out, smem.data(), state_mode != 0);
+  Team::order() = 0;
+  return 0;
+}
+int hs_tile_smem_bytes(int D, int d, int which) {
+  const int v[4] = {tile_fold_smem_doubles(D, d), tile_scan_smem_doubles(D, d), tile_smooth_smem_doubles(D, d),
+                    tile_tree_smem_doubles(D)};
+  return v[which & 3] * (int)sizeof(double);
 }
 }
