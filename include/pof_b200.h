@@ -101,6 +101,19 @@ int pof_linear_filtsmooth_f64(pof_stream_t s, int64_t N, int d, int q, int64_t c
                               double* means, double* chols, double* fmeans, double* fchols, int calibrate,
                               double* scalars, void* ws, size_t ws_bytes);
 
+/* The same pass with observation noise: cholR (n,d,d) lower-triangular factors of the observation covariances
+ * (reference AffineModel.cholR, pof/observations.py:23-33; used by the reference's regularised iterations,
+ * pof/observations.py:43-83).  cholR == NULL is the noiseless case.  Served by the large-state ("tile") kernels for any
+ * (d, q) they support (pof_supported_tile); chunk_len from pof_default_chunk_len_tile. */
+int pof_linear_filtsmooth_noisy_f64(pof_stream_t s, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                                    const double* x0_mean, const double* x0_chol, const double* H, const double* c,
+                                    const double* cholR, double* means, double* chols, double* fmeans, double* fchols,
+                                    int calibrate, double* scalars, void* ws, size_t ws_bytes);
+/* 1 if the CTA-per-chunk large-state kernels support (d, q) (any d, 1 <= q <= 5, D = d (q+1) limited by the 227 KB of
+ * shared memory per CTA: D <= 64 at d = 16); their default chunk length (one chunk per resident CTA) */
+int pof_supported_tile(int d, int q);
+int64_t pof_default_chunk_len_tile(int64_t N, int d, int q, int sm_count);
+
 /* One fused IEKS iteration for a built-in IVP -- replaces the body of the reference's while loop,
  *   pof.step.ieks_step(om, dtm, x0, states)   pof/step.py:33-45   (called from pof/solver.py:48-55):
  * linearise at means[1:] (fused f / Jacobian, kept in the compact form [J_f | c] inside the workspace: the dense

@@ -16,6 +16,7 @@ SOURCES = [
     "pof_lane_d1.cu", "pof_lane_d2.cu", "pof_lane_d3.cu", "pof_lane_d4.cu",
     "pof_tree_a.cu", "pof_tree_b.cu", "pof_tree_c.cu",
     "pof_lane2_d1.cu", "pof_lane2_d2.cu", "pof_lane2_d3.cu", "pof_lane2_d4.cu",
+    "pof_tile.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -38,6 +39,13 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     hdr_time = _newest(_headers())
+    # up to date: the library is newer than every source and header (the object directory does not travel to the GPU
+    # box, the library does -- no recompilation there)
+    src_time = max([hdr_time] + [os.path.getmtime(os.path.join(CSRC, s)) for s in SOURCES])
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= src_time:
+        if verbose:
+            print("up to date:", LIB)
+        return LIB
     jobs = []
     objs = []
     for src in SOURCES:

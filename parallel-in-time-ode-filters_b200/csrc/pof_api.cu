@@ -17,7 +17,7 @@ namespace pof {
 // register-resident tree sweeps when 2D <= 32 (POF_B200_TREE_IMPL=generic forces the shared-memory kernels)
 static const TreeLaunch* tree_launch(int D) {
   const char* e = getenv("POF_B200_TREE_IMPL");
-  if (e && e[0] == 'g') return nullptr;
+  if (e && (e[0] == 'g' || e[0] == 't')) return nullptr;  // generic (warp, shared memory) / tile (CTA per node)
   const TreeLaunch* t = tree_launch_a(D);
   if (!t) t = tree_launch_b(D);
   if (!t) t = tree_launch_c(D);
@@ -102,6 +102,8 @@ static const LeafLaunch* lane2_launch(int d, int q) {
 // where available (and the register-resident tree ops are not disabled), else lane1, else thread
 const LeafLaunch* leaf_launch(int d, int q) {
   const char* e = getenv("POF_B200_LEAF_IMPL");
+  const bool want_tile = e && e[0] == 't' && e[1] == 'i';
+  if (want_tile) return tile_supported(d, q) ? tile_leaf_launch() : nullptr;
   const bool want_thread = e && e[0] == 't';
   const bool want_lane1 = e && e[0] == 'l' && e[1] == 'a' && e[2] == 'n' && e[3] == 'e' && e[4] == '1';
   if (!want_thread) {
@@ -112,7 +114,9 @@ const LeafLaunch* leaf_launch(int d, int q) {
     const LeafLaunch* l = lane_launch(d, q);
     if (l) return l;
   }
-  return thread_launch(d, q);
+  if (const LeafLaunch* l = thread_launch(d, q)) return l;
+  // anything the (d, q)-templated families do not cover: the large-state tile family (D limited by shared memory)
+  return tile_supported(d, q) ? tile_leaf_launch() : nullptr;
 }
 
 constexpr int TREE_WARPS = 4;  // max warps (= element pairs) per CTA in the tree kernels; fewer when D is large
@@ -344,6 +348,25 @@ __global__ void __launch_bounds__(256)
     o[d * d + a] = ca;
   }
 }
+// Lorenz-96 (POF_IVP_LORENZ96; the larger-state problem of BASELINE config 5, not in the reference's ivp.py):
+//   f_a = (y_{a+1} - y_{a-2}) y_{a-1} - y_a + F (cyclic), 4 <= d.  One thread per (step, component): row a of the
+// Jacobian has the three entries d f_a / d y_{a+1} = y_{a-1}, d f_a / d y_{a-2} = -y_{a-1}, d f_a / d y_{a-1} =
+// y_{a+1} - y_{a-2} and -1 on the diagonal.  dense != 0: H (n,d,D), c (n,d); else compact [J_f | c] per step.
+__global__ void __launch_bounds__(256)
+    k_linearize_l96(double forcing, long n, int d, int q, double scale0, double scale1, int dense,
+                    const double* __restrict__ means_t1, double* __restrict__ H, double* __restrict__ c,
+                    double* __restrict__ Jc) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * d) return;
+  l96_linearize_row(forcing, idx / d, (int)(idx % d), d, q, scale0, scale1, dense, means_t1, H, c, Jc);
+}
+// built-in problem ids and the ODE dimension each one accepts
+static bool ivp_dim_ok(int ivp_id, int d) {
+  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
+  if (ivp_id == POF_IVP_LORENZ96) return d >= 4 && d <= 64;
+  return ivp_id >= 0 && ivp_id <= POF_IVP_HENONHEILES && dims[ivp_id] == d;
+}
+
 // ys = E0 states, with the (second) calibration multiplier of pof/solver.py:66-69 read from device memory
 __global__ void __launch_bounds__(256)
     k_project(long N, int d, int q, double scale0, const double* __restrict__ mult, const double* __restrict__ means,
@@ -425,6 +448,15 @@ static inline int tree_warps(int D) {
   return (int)(w > TREE_WARPS ? TREE_WARPS : w);
 }
 static inline int tree_smem_bytes(int D) { return tree_warps(D) * coop_ws_doubles(D) * (int)sizeof(double); }
+// Which carry-level kernels serve a pass when no register-resident TreeLaunch exists for D: the warp-per-combine
+// shared-memory kernels above, or the CTA-per-node tile kernels (pof_tile.cu).  The tile leaves need the chunk-level
+// smoothing op, which only the register-resident and the tile trees have; POF_B200_TREE_IMPL=tile forces the tile tree.
+static bool use_tile_tree(int D, const LeafLaunch* ll) {
+  const char* e = getenv("POF_B200_TREE_IMPL");
+  if (e && e[0] == 't') return tile_tree_supported(D);
+  if (tree_launch(D) != nullptr) return false;
+  return (ll && ll->is_tile) || tree_warps(D) < 1;
+}
 
 template <class K>
 static cudaError_t set_smem(K kernel, int bytes) {
@@ -480,6 +512,9 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   a.H = H;
   a.c = c;
   a.Jc = nullptr;
+  a.R = nullptr;
+  a.d = d;
+  a.q = q;
   a.s0 = a.s1 = 0.0;
   for (int i = 0; i < 36; ++i) a.ql.v[i] = 0.0;
   for (int i = 0; i < (q + 1) * (q + 1); ++i) a.ql.v[i] = qL_host[i];
@@ -533,7 +568,8 @@ static int apex_down_end(const WsLayout& wl, int cap) {
 static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
                    bool need_root) {
   double* fagg = ws + wl.o_fagg;
-  const bool pre = ll->has_pre_update && tree_launch(wl.D) != nullptr;
+  const bool tile = use_tile_tree(wl.D, ll);
+  const bool pre = ll->has_pre_update && (tree_launch(wl.D) != nullptr || tile);
   {
     ProfScope ps(SEG_FOLD, s);
     POF_CK(ll->fold(s, a, fagg, pre ? ws + wl.o_faggm : nullptr));
@@ -551,8 +587,10 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   ProfScope ps(SEG_FUP, s);
   const int smem = tree_smem_bytes(wl.D);
   const int tw = tree_warps(wl.D);
-  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-  POF_CK(set_smem(k_filter_up, smem));
+  if (!tl && !tile) {
+    if (tw < 1) return POF_E_UNSUPPORTED_DQ;
+    POF_CK(set_smem(k_filter_up, smem));
+  }
   const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
   const int a_up = (tl && apex_enabled()) ? apex_up_begin(wl, up_total, tl->fcap) : up_total;
   if (tl && a_up < up_total && need_root) {  // sharded: the apex of the up-sweep here (single GPU: in stage_b)
@@ -571,6 +609,8 @@ static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     const long np = wl.tl.sz[l + 1];
     if (tl)
       POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE, np));
+    else if (tile)
+      POF_CK(tile_fup(s, wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np));
     else
       k_filter_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
           wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np);
@@ -587,10 +627,13 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   double* sagg = ws + wl.o_sagg;
   const int smem = tree_smem_bytes(wl.D);
   const int tw = tree_warps(wl.D);
-  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-  POF_CK(set_smem(k_filter_down, smem));
-  POF_CK(set_smem(k_smooth_up, smem));
   const TreeLaunch* tl = tree_launch(wl.D);
+  const bool tile = use_tile_tree(wl.D, ll);
+  if (!tl && !tile) {
+    if (tw < 1) return POF_E_UNSUPPORTED_DQ;
+    POF_CK(set_smem(k_filter_down, smem));
+    POF_CK(set_smem(k_smooth_up, smem));
+  }
   const bool fused = tl && tree_fused();
   if (fused) {
     ProfScope ps(need_root ? SEG_FDOWN : SEG_FUP, s);
@@ -622,6 +665,9 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     if (tl)
       POF_CK(tl->fdown(s, fin + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], fagg + wl.tl.off[l - 1] * wl.FE,
                        fin + wl.tl.off[l - 1] * wl.ST, np));
+    else if (tile)
+      POF_CK(tile_fdown(s, wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
+                        fin + wl.tl.off[l - 1] * wl.ST));
     else
       k_filter_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
           wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
@@ -629,8 +675,8 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   }
   }
   POF_CK(cudaGetLastError());
-  const bool pre = ll->has_pre_update && tl != nullptr;
-  SideStream* side = (pre && !fused) ? side_stream() : nullptr;
+  const bool pre = ll->has_pre_update && (tl != nullptr || tile);
+  SideStream* side = (pre && !fused && tl) ? side_stream() : nullptr;
   if (side) {
     // chunk-level smoothing elements, then fork: smoother up-sweep on the side stream || filter scan on s
     POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
@@ -680,12 +726,19 @@ static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     return (int)cudaGetLastError();
   }
   // chunk-level smoothing elements straight from (incoming state, filtering element before its last update)
-  if (pre) POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
+  if (pre) {
+    if (tl)
+      POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
+    else
+      POF_CK(tile_chunkk(s, wl.D, fin, ws + wl.o_faggm, sagg, wl.CS));
+  }
   ProfScope ps(SEG_SUP, s);
   for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l) {
     const long np = wl.tl.sz[l + 1];
     if (tl)
       POF_CK(tl->sup(s, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE, np));
+    else if (tile)
+      POF_CK(tile_sup(s, wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np));
     else
       k_smooth_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
           wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
@@ -700,9 +753,12 @@ static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
   double* sin_ = ws + wl.o_sin;
   const int smem = tree_smem_bytes(wl.D);
   const int tw = tree_warps(wl.D);
-  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-  POF_CK(set_smem(k_smooth_down, smem));
   const TreeLaunch* tl = tree_launch(wl.D);
+  const bool tile = use_tile_tree(wl.D, ll);
+  if (!tl && !tile) {
+    if (tw < 1) return POF_E_UNSUPPORTED_DQ;
+    POF_CK(set_smem(k_smooth_down, smem));
+  }
   if (skip_down) {
   } else if (tl && tree_fused()) {
     ProfScope ps(SEG_SDOWN, s);
@@ -729,6 +785,9 @@ static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, cons
     if (tl)
       POF_CK(tl->sdown(s, sin_ + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], sagg + wl.tl.off[l - 1] * wl.SE,
                        sin_ + wl.tl.off[l - 1] * wl.ST, np));
+    else if (tile)
+      POF_CK(tile_sdown(s, wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
+                        sin_ + wl.tl.off[l - 1] * wl.ST));
     else
       k_smooth_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
           wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
@@ -798,7 +857,7 @@ int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
     tree = fu + fd + ((fu < up_total || fd < down_total) ? 1 : 0)  // filter: per-level ups and downs, one apex
            + (sup_apex ? su + ((su < up_total) ? 1 : 0) : up_total) + sd + ((sd < down_total) ? 1 : 0);
   }
-  const int64_t chunkk = (ll && ll->has_pre_update && tl) ? 1 : 0;
+  const int64_t chunkk = (ll && ll->has_pre_update && (tl || use_tile_tree(wl.D, ll))) ? 1 : 0;
   return 3 /*leaf*/ + tree /*tree sweeps*/ + chunkk /*chunk smoothing elements*/ + 1 /*pack*/ + 2 /*reduce*/ +
          2 /*finalize*/;
 }
@@ -839,10 +898,20 @@ int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count) {
   const LeafLaunch* ll = leaf_launch(d, q);
   const int cpw = ll ? ll->chunks_per_warp : 32;
   const int64_t n = N - 1;
-  const int64_t target = (int64_t)sm_count * 8 * cpw;  // ~8 resident warps per SM, `cpw` chunks per warp
+  // ~8 resident warps per SM, `cpw` chunks per warp; tile family: one chunk per resident CTA
+  const int64_t target = (ll && ll->is_tile) ? (int64_t)sm_count * tile_ctas_per_sm(d, q) : (int64_t)sm_count * 8 * cpw;
   int64_t L = (n + target - 1) / target;
   if (L < 4) L = 4;
   return L;
+}
+
+int pof_supported_tile(int d, int q) { return tile_supported(d, q) ? 1 : 0; }
+int64_t pof_default_chunk_len_tile(int64_t N, int d, int q, int sm_count) {
+  if (sm_count <= 0) sm_count = 148;
+  const int64_t n = N - 1;
+  const int64_t target = (int64_t)sm_count * tile_ctas_per_sm(d, q);
+  int64_t L = (n + target - 1) / target;
+  return L < 4 ? 4 : L;
 }
 
 size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
@@ -854,6 +923,7 @@ size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
 int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
   if (n <= 0) return 0;
   if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->fcomb((cudaStream_t)s, e1, n, e2, out, n);
+  if (use_tile_tree(D, nullptr)) return (int)tile_fcomb((cudaStream_t)s, D, n, e1, e2, out);
   const int smem = tree_smem_bytes(D);
   const int tw = tree_warps(D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
@@ -864,6 +934,7 @@ int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, c
 int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
   if (n <= 0) return 0;
   if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->scomb((cudaStream_t)s, e1, n, e2, out, n);
+  if (use_tile_tree(D, nullptr)) return (int)tile_scomb((cudaStream_t)s, D, n, e1, e2, out);
   const int smem = tree_smem_bytes(D);
   const int tw = tree_warps(D);
   if (tw < 1) return POF_E_UNSUPPORTED_DQ;
@@ -874,13 +945,16 @@ int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, c
 
 int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
                           double scale0, double scale1, const double* means_t1, double* H, double* c) {
-  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
-  if (d < 1 || d > 4 || nparams > 8) return POF_E_ARG;
-  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
-  if (dims[ivp_id] != d) return POF_E_ARG;
+  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
+  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
   IvpParams P;
   for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
   if (n <= 0) return 0;
+  if (ivp_id == POF_IVP_LORENZ96) {
+    k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, (cudaStream_t)s>>>(P.p[0], n, d, q, scale0, scale1, 1,
+                                                                                  means_t1, H, c, nullptr);
+    return (int)cudaGetLastError();
+  }
   k_linearize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, scale1, means_t1,
                                                                         H, c);
   return (int)cudaGetLastError();
@@ -892,13 +966,16 @@ static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, con
 
 int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
                                   int q, double scale0, const double* means_t1, double* Jc) {
-  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
-  if (d < 1 || d > 4 || nparams > 8) return POF_E_ARG;
-  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
-  if (dims[ivp_id] != d) return POF_E_ARG;
+  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
+  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
   IvpParams P;
   for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
   if (n <= 0) return 0;
+  if (ivp_id == POF_IVP_LORENZ96) {
+    k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, (cudaStream_t)s>>>(P.p[0], n, d, q, scale0, 0.0, 0,
+                                                                                  means_t1, nullptr, nullptr, Jc);
+    return (int)cudaGetLastError();
+  }
   k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, means_t1,
                                                                                 Jc);
   return (int)cudaGetLastError();
@@ -922,15 +999,34 @@ int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t 
   return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
 }
 
+// general observation noise: always the tile family (the only leaves that carry the D-column posterior factor)
+int pof_linear_filtsmooth_noisy_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                                    const double* x0_mean, const double* x0_chol, const double* H, const double* c,
+                                    const double* cholR, double* means, double* chols, double* fmeans, double* fchols,
+                                    int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (N < 2) return POF_E_ARG;
+  if (!tile_supported(d, q)) return POF_E_UNSUPPORTED_DQ;
+  const LeafLaunch* ll = tile_leaf_launch();
+  WsLayout wl;
+  wl.build(N - 1, d, q, chunk_len);
+  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  double* ws = (double*)ws_;
+  LeafArgs a;
+  int rc = make_args(N - 1, d, q, qL_host, H, c, wl, a);
+  if (rc) return rc;
+  a.R = cholR;
+  return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
+}
+
 int pof_ieks_iteration_f64(pof_stream_t s_, int ivp_id, const double* params_host, int nparams, int64_t N, int d,
                            int q, int64_t chunk_len, const double* qL_host, double scale0, double scale1,
                            const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
                            double* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
-  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
-  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
-  if (dims[ivp_id] != d || nparams > 8) return POF_E_ARG;
+  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
+  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
   const LeafLaunch* ll = leaf_launch(d, q);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
@@ -944,7 +1040,15 @@ int pof_ieks_iteration_f64(pof_stream_t s_, int ivp_id, const double* params_hos
   double* lin = ws + wl.o_lin;
   LeafArgs a;
   int rc;
-  if (ll->has_pre_update) {  // lane kernels: compact linearisation, H rebuilt on load
+  if (ivp_id == POF_IVP_LORENZ96) {
+    if (!ll->has_pre_update) return POF_E_UNSUPPORTED_DQ;  // only the tile (and lane) leaves rebuild H from [J_f | c]
+    k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, s>>>(P.p[0], n, d, q, scale0, 0.0, 0, means + D,
+                                                                    nullptr, nullptr, lin);
+    rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, a);
+    a.Jc = lin;
+    a.s0 = scale0;
+    a.s1 = scale1;
+  } else if (ll->has_pre_update) {  // lane kernels: compact linearisation, H rebuilt on load
     k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, means + D, lin);
     rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, a);
     a.Jc = lin;
@@ -1140,6 +1244,8 @@ int pof_shard_stage_c_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t 
 
 int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
                                double* state_out, double* scratch) {
+  if (use_tile_tree(D, nullptr))
+    return (int)tile_fchain((cudaStream_t)s, D, count, state_in, elems, state_out, scratch);
   const int smem = coop_ws_doubles(D) * (int)sizeof(double);
   POF_CK(set_smem(k_filter_chain, smem));
   k_filter_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
@@ -1147,6 +1253,8 @@ int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* s
 }
 int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
                                double* state_out, double* scratch) {
+  if (use_tile_tree(D, nullptr))
+    return (int)tile_schain((cudaStream_t)s, D, count, state_in, elems, state_out, scratch);
   const int smem = coop_ws_doubles(D) * (int)sizeof(double);
   POF_CK(set_smem(k_smooth_chain, smem));
   k_smooth_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);

@@ -106,4 +106,38 @@ POF_HD bool ivp_eval(int id, const IvpParams& P, const double* y, double* f, dou
   }
 }
 
+
+// Lorenz-96 (POF_IVP_LORENZ96), one (step k, component a) of the linearisation H_k = E1 - J_f E0, c_k = J_f y - f(y) at
+// y = E0 m_{k+1}:  f_a = (y_{a+1} - y_{a-2}) y_{a-1} - y_a + F (cyclic, d >= 4).  dense != 0: row a of H (n,d,D) and c
+// (n,d); else row a of the compact form [J_f (d x d) | c (d)] per step.  Shared by the kernel and the host simulator.
+POF_HD void l96_linearize_row(double forcing, long k, int a, int d, int q, double scale0, double scale1, int dense,
+                              const double* means_t1, double* H, double* c, double* Jc) {
+  const int Q1 = q + 1, D = d * Q1;
+  const int ip1 = (a + 1) % d, im1 = (a + d - 1) % d, im2 = (a + d - 2) % d;
+  const double* m = means_t1 + k * D;
+  const double ya = scale0 * m[a * Q1], yp1 = scale0 * m[ip1 * Q1], ym1 = scale0 * m[im1 * Q1],
+               ym2 = scale0 * m[im2 * Q1];
+  const double f = (yp1 - ym2) * ym1 - ya + forcing;
+  const double jp1 = ym1, jm2 = -ym1, jm1 = yp1 - ym2, ja = -1.0;
+  const double ca = jp1 * yp1 + jm2 * ym2 + jm1 * ym1 + ja * ya - f;
+  if (dense) {
+    double* Hr = H + (k * d + a) * D;
+    for (int j = 0; j < D; ++j) Hr[j] = 0.0;
+    Hr[ip1 * Q1] = -jp1 * scale0;
+    Hr[im2 * Q1] = -jm2 * scale0;
+    Hr[im1 * Q1] = -jm1 * scale0;
+    Hr[a * Q1] = -ja * scale0;
+    Hr[a * Q1 + 1] += scale1;
+    c[k * d + a] = ca;
+  } else {
+    double* o = Jc + k * ((long)d * d + d);
+    for (int b = 0; b < d; ++b) o[a * d + b] = 0.0;
+    o[a * d + ip1] = jp1;
+    o[a * d + im2] = jm2;
+    o[a * d + im1] = jm1;
+    o[a * d + a] = ja;
+    o[(long)d * d + a] = ca;
+  }
+}
+
 }  // namespace pof

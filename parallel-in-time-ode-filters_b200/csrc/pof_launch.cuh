@@ -55,6 +55,8 @@ struct LeafArgs {
   const double* Jc;  // ... or compact: per step [J_f (d x d) | c (d)], H = E1 - J_f E0 rebuilt on load (Jc != null)
   double s0, s1;     // Nordsieck scalings: E0 = s0 e_0^T, E1 = s1 e_1^T per block
   QLParam ql;
+  int d, q;          // runtime dimensions (the tile family is not templated on them)
+  const double* R;   // observation-noise factors cholR (n,d,d), or null = noiseless (tile family only)
 };
 
 struct LeafLaunch {
@@ -70,6 +72,7 @@ struct LeafLaunch {
                          double* kern, double* means, double* chols, double* part);
   int chunks_per_warp;
   int has_pre_update;  // 1 if fold can emit faggm and scan can skip the composition  // 32 for the thread-per-chunk kernels, 32/G for the lane-cooperative ones
+  int is_tile;         // 1 for the CTA-per-chunk large-state family (pof_tile.cu): chunks_per_warp is 0 there
 };
 
 // returns nullptr if (d, q) is not compiled in
@@ -88,6 +91,25 @@ const LeafLaunch* lane2_launch_d1(int q);
 const LeafLaunch* lane2_launch_d2(int q);
 const LeafLaunch* lane2_launch_d3(int q);
 const LeafLaunch* lane2_launch_d4(int q);
+
+// large-state family (pof_tile.cu): CTA per chunk / per tree node, runtime (d, q); D limited by shared memory
+bool tile_supported(int d, int q);
+bool tile_tree_supported(int D);
+int tile_ctas_per_sm(int d, int q);
+const LeafLaunch* tile_leaf_launch();
+cudaError_t tile_fup(cudaStream_t, int D, const double* child, long nchild, double* parent, long nparent);
+cudaError_t tile_fdown(cudaStream_t, int D, const double* pin, long nparent, const double* cagg, long nchild,
+                       double* cin);
+cudaError_t tile_sup(cudaStream_t, int D, const double* child, long nchild, double* parent, long nparent);
+cudaError_t tile_sdown(cudaStream_t, int D, const double* pin, long nparent, const double* cagg, long nchild,
+                       double* cin);
+cudaError_t tile_chunkk(cudaStream_t, int D, const double* fin, const double* faggm, double* sagg, long CS);
+cudaError_t tile_fcomb(cudaStream_t, int D, long n, const double* e1, const double* e2, double* out);
+cudaError_t tile_scomb(cudaStream_t, int D, long n, const double* e1, const double* e2, double* out);
+cudaError_t tile_fchain(cudaStream_t, int D, int count, const double* state_in, const double* elems,
+                        double* state_out, double* scratch);
+cudaError_t tile_schain(cudaStream_t, int D, int count, const double* state_in, const double* elems,
+                        double* state_out, double* scratch);
 
 // One whole tree sweep (all levels of an up-sweep and/or a down-sweep) as ONE persistent cooperative kernel with a
 // grid barrier between levels: ~2 us per level instead of a kernel boundary (launch gap, cold instruction cache,

@@ -621,8 +621,8 @@ struct TileTreeWs {
 
 // e1: earlier element (packed filtering element, or packed state (m, L) if state_mode), e2: later element.
 // out: packed filtering element, or packed state if state_mode.  out must not alias e1 / e2.
-POF_TDEV void tile_filter_combine(const Team& t, int D, const double* __restrict__ e1, const double* __restrict__ e2,
-                                  double* __restrict__ out, double* smem, bool state_mode) {
+POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const double* e2,
+                                  double* out, double* smem, bool state_mode) {
   TileTreeWs s(smem, D);
   const int DD = D * D, ldx = s.ldx;
   const double* A1 = state_mode ? nullptr : e1;
@@ -765,8 +765,8 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* __restrict
 
 // e1: LATER element (packed smoothing element [g | E | Dm], or packed state if state_mode), e2: EARLIER element.
 // g = E2 g1 + g2 ; E = E2 E1 ; Dm = tria([E2 D1, D2])   (smoother.py:53-63)
-POF_TDEV void tile_smooth_combine(const Team& t, int D, const double* __restrict__ e1, const double* __restrict__ e2,
-                                  double* __restrict__ out, double* smem, bool state_mode) {
+POF_TDEV void tile_smooth_combine(const Team& t, int D, const double* e1, const double* e2,
+                                  double* out, double* smem, bool state_mode) {
   TileTreeWs s(smem, D);
   const int DD = D * D, ldx = s.ldx;
   const double* g1 = e1;
@@ -808,8 +808,8 @@ POF_TDEV void tile_smooth_combine(const Team& t, int D, const double* __restrict
 // chunk's filtering element e2 = (A, b, U, eta, Z) taken before its last measurement update (see pof_treelane.cuh):
 //   Xi = tria([[L^T Z, I],[Z, 0]]),  Y = L Xi11^{-T},  G = I - Y Xi21^T,  m' = G (m + L L^T eta)
 //   tria([[A Y, U],[Y, 0]]) = [[Phi11, 0],[Phi21, Phi22]],  E = Phi21 Phi11^{-1},  g = m' - E (A m' + b),  Dm = Phi22
-POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* __restrict__ st, const double* __restrict__ e2,
-                                double* __restrict__ out, double* smem) {
+POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const double* e2,
+                                double* out, double* smem) {
   TileTreeWs s(smem, D);
   const int DD = D * D, ldx = s.ldx;
   const double* m1 = st;

@@ -19,7 +19,7 @@ S_NLL, S_OBJ, S_SSQ, S_SSQ_PROPER, S_NOT_CLOSE, S_CSCALE, NSCALARS = 0, 1, 2, 3,
 
 IVP_IDS = dict(
     logistic=0, lotkavolterra=1, vanderpol=2, fitzhughnagumo=3, rober=4, rigid_body=5, seir=6, threebody=7,
-    henonheiles=8,
+    henonheiles=8, lorenz96=9,
 )
 
 _c_dp = ctypes.c_void_p
@@ -51,6 +51,11 @@ def _load():
         "pof_linear_filtsmooth_f64": (
             _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
                      _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_linear_filtsmooth_noisy_f64": (
+            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_supported_tile": (_c_int, [_c_int, _c_int]),
+        "pof_default_chunk_len_tile": (_c_i64, [_c_i64, _c_int, _c_int, _c_int]),
         "pof_ieks_iteration_f64": (
             _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
                      _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
@@ -95,6 +100,7 @@ EXPORTED = [
     "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_linearize_ivp_compact_f64",
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
     "pof_project_f64", "pof_profile_enable", "pof_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops",
+    "pof_linear_filtsmooth_noisy_f64", "pof_supported_tile", "pof_default_chunk_len_tile",
 ]
 
 
@@ -160,3 +166,8 @@ class Workspace:
 
 def default_chunk_len(N, d, q, device=None):
     return int(LIB.pof_default_chunk_len(int(N), int(d), int(q), sm_count(device)))
+
+
+def default_chunk_len_tile(N, d, q, device=None):
+    """chunk length for the large-state (CTA-per-chunk) kernels, which also serve noisy observations"""
+    return int(LIB.pof_default_chunk_len_tile(int(N), int(d), int(q), sm_count(device)))

@@ -157,3 +157,17 @@ def henonheiles(t0=0.0, tmax=100.0, y0=None, p=None):
         )
 
     return InitialValueProblem(f=_tag(f, "henonheiles", (p,)), t0=t0, tmax=tmax, y0=y0)
+
+
+def lorenz96(t0=0.0, tmax=10.0, y0=None, d=16, forcing=8.0):
+    """Not in the reference's ivp.py: the larger-state problem of BASELINE config 5.  Lorenz-96,
+    f_i = (y_{i+1} - y_{i-2}) y_{i-1} - y_i + F (cyclic indices), y0_i = F + 0.01 sin(i); d >= 4."""
+    if y0 is None:
+        y0 = forcing + 0.01 * torch.sin(torch.arange(d, dtype=torch.float64))
+    y0 = _t(y0)
+    forcing = float(forcing)
+
+    def f(_, y, forcing=forcing):
+        return (torch.roll(y, -1, -1) - torch.roll(y, 2, -1)) * torch.roll(y, 1, -1) - y + forcing
+
+    return InitialValueProblem(f=_tag(f, "lorenz96", (forcing,)), t0=t0, tmax=tmax, y0=y0)

@@ -28,23 +28,36 @@ def _model_dims(dtm: TransitionModel, dom: AffineModel):
             "the CUDA pass is specialised to the preconditioned IWP transition model of pof.transitions "
             "(F = I_d (x) flip(pascal), QL = I_d (x) chol(flip(hilbert))); other transition models are out of scope"
         )
-    if dom.cholR is not None and bool((dom.cholR != 0).any()):
-        raise NotImplementedError("noisy observations (cholR != 0) are out of scope of this tier")
     return n, d, q, D, np.ascontiguousarray(QLi[: q + 1, : q + 1])
 
 
+def _noise(dom: AffineModel):
+    """cholR as a contiguous (n,d,d) tensor if the observations are noisy, else None (reference observations.py:23-33)"""
+    if dom.cholR is None or not bool((dom.cholR != 0).any()):
+        return None
+    return dom.cholR.contiguous()
+
+
 def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_len=None, fmeans=None, fchols=None,
-             scalars=None):
-    """One filter+smoother pass on device buffers (the call `solve` makes every iteration)."""
+             scalars=None, cholR=None):
+    """One filter+smoother pass on device buffers (the call `solve` makes every iteration).  cholR (n,d,d): noisy
+    observations, served by the large-state kernels (`pof_linear_filtsmooth_noisy_f64`)."""
     N = means_io.shape[0]
-    nat.require_cuda(x0.mean, x0.chol, H, c, means_io, chols, fmeans, fchols)
+    nat.require_cuda(x0.mean, x0.chol, H, c, means_io, chols, fmeans, fchols, cholR)
     dev = means_io.device
     if chunk_len is None:
-        chunk_len = nat.default_chunk_len(N, d, q, dev.index)
+        chunk_len = (nat.default_chunk_len_tile if cholR is not None else nat.default_chunk_len)(N, d, q, dev.index)
     ws = nat.Workspace.get(N, d, q, chunk_len, dev)
     if scalars is None:
         scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
     qLh, qLp = nat.host_doubles(qL)
+    if cholR is not None:
+        rc = nat.LIB.pof_linear_filtsmooth_noisy_f64(
+            nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
+            nat.ptr(cholR), nat.ptr(means_io), nat.ptr(chols), nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)),
+            nat.ptr(scalars), ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+        nat.check(rc, "pof_linear_filtsmooth_noisy_f64")
+        return scalars
     rc = nat.LIB.pof_linear_filtsmooth_f64(
         nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
         nat.ptr(means_io), nat.ptr(chols), nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)), nat.ptr(scalars),
@@ -141,7 +154,7 @@ def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=
     means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
     chols = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
     sc = run_pass(x0, qL, linear_observations.H.contiguous(), linear_observations.b.contiguous(), means, chols, d=d,
-                  q=q, calibrate=False, chunk_len=chunk_len)
+                  q=q, calibrate=False, chunk_len=chunk_len, cholR=_noise(linear_observations))
     return MVNSqrt(means, chols), sc[nat.S_NLL], sc[nat.S_OBJ], sc[nat.S_SSQ]
 
 
@@ -154,7 +167,7 @@ def linear_noiseless_filtering(x0, transition_models, observation_models, *, chu
     fm = torch.empty((n + 1, D), dtype=torch.float64, device=dev)
     fc = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
     sc = run_pass(x0, qL, observation_models.H.contiguous(), observation_models.b.contiguous(), means, None, d=d, q=q,
-                  calibrate=False, chunk_len=chunk_len, fmeans=fm, fchols=fc)
+                  calibrate=False, chunk_len=chunk_len, fmeans=fm, fchols=fc, cholR=_noise(observation_models))
     # filter objective (reference filter.py:43-45, swapped-argument form), evaluated on the filtered means
     F = transition_models.F[0] if transition_models.F.dim() == 3 else transition_models.F
     QL = transition_models.QL[0] if transition_models.QL.dim() == 3 else transition_models.QL

@@ -391,6 +391,16 @@ int hs_tile_smooth_combine(int D, const double* e1, const double* e2, double* ou
   Team::order() = 0;
   return 0;
 }
+// Lorenz-96 linearisation (the body of k_linearize_l96): dense (H, c) and compact [J_f | c]
+int hs_linearize_l96(double forcing, long n, int d, int q, double s0, double s1, const double* means_t1, double* H,
+                     double* c, double* Jc) {
+  for (long k = 0; k < n; ++k)
+    for (int a = 0; a < d; ++a) {
+      l96_linearize_row(forcing, k, a, d, q, s0, s1, 1, means_t1, H, c, nullptr);
+      l96_linearize_row(forcing, k, a, d, q, s0, 0.0, 0, means_t1, nullptr, nullptr, Jc);
+    }
+  return 0;
+}
 int hs_tile_smem_bytes(int D, int d, int which) {
   const int v[4] = {tile_fold_smem_doubles(D, d), tile_scan_smem_doubles(D, d), tile_smooth_smem_doubles(D, d),
                     tile_tree_smem_doubles(D)};

@@ -27,7 +27,10 @@ def test_header_symbols_exported(native_lib):
 def test_host_only_queries(native_lib):
     L = native_lib.LIB
     assert L.pof_supported(2, 3) == 1 and L.pof_supported(1, 1) == 1 and L.pof_supported(4, 5) == 1
-    assert L.pof_supported(5, 3) == 0 and L.pof_supported(2, 9) == 0
+    # beyond the (d <= 4)-templated families: the large-state tile kernels, limited by shared memory (D <= 64 at d = 16)
+    assert L.pof_supported(5, 3) == 1 and L.pof_supported(16, 3) == 1 and L.pof_supported_tile(2, 3) == 1
+    assert L.pof_supported(16, 4) == 0 and L.pof_supported(2, 9) == 0 and L.pof_supported_tile(32, 3) == 0
+    assert L.pof_default_chunk_len(1 << 18, 16, 3, 148) == ((1 << 18) - 1 + 147) // 148  # one chunk per SM
     assert L.pof_default_chunk_len(1 << 20, 2, 3, 148) >= 4
     nb = L.pof_workspace_bytes(1 << 20, 2, 3, 222)
     assert 1.1e9 < nb < 1.4e9  # dominated by the per-step backward kernels: n * 136 doubles

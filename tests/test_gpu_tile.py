@@ -1,0 +1,204 @@
+"""GPU parity tests of the large-state ("tile") kernels (csrc/pof_tile.cu{,h}): CTA-per-chunk leaf recursions and
+CTA-per-node tree operators for runtime (d, q) -- the path that serves D > 24 (BASELINE config 5: Lorenz-96, d = 16,
+q = 3, D = 64) and noisy observations (cholR != 0).  Same tolerances as tests/test_gpu_parity.py (north_star: outputs
+1e-9, covariances 1e-7).  The identical device code runs on the host in tests/test_hostsim_tile.py."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ivps as oivps  # noqa: E402
+from oracle import pof_oracle as O  # noqa: E402
+
+
+def _cov(L):
+    return L @ np.swapaxes(L, -1, -2)
+
+
+def _pair(name, **kw):
+    import pof.ivp
+
+    return getattr(pof.ivp, name)(**kw), getattr(oivps, name)(**kw)
+
+
+def _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=False):
+    oout, onll, oobj, ossq, _ = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom)
+    oout2, nll2, obj2, _, _ = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom, scan=O.sequential_scan)
+    E0 = osetup["E0"]
+    m, Lc = out.mean.cpu().numpy(), out.chol.cpu().numpy()
+    assert np.isfinite(m).all() and np.isfinite(Lc).all()
+    y, yo = m @ E0.T, oout.mean @ E0.T
+    scale = np.abs(yo).max(axis=0)
+    band = np.abs(oout2.mean @ E0.T - yo).max(axis=0)
+    tol_y = np.maximum(1e-9 * scale + 1e-12, 10 * band)
+    assert (np.abs(y - yo) <= tol_y).all(), (np.abs(y - yo).max(axis=0), tol_y)
+    C, Co = _cov(Lc), _cov(oout.chol)
+    assert np.abs(E0 @ C @ E0.T - E0 @ Co @ E0.T).max() <= 1e-7 * np.abs(E0 @ Co @ E0.T).max()
+    assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
+    assert abs(float(nll) - onll) <= max(1e-9 * abs(onll) + 1e-9, 10 * abs(nll2 - onll))
+    assert abs(float(obj) - oobj) <= max(1e-9 * abs(oobj), 10 * abs(obj2 - oobj))
+    if not noisy:  # the reference's sigma^2 formula depends on QR sign conventions (utils.py:110-112)
+        assert abs(float(ssq) - ossq) <= 1e-2 * abs(ossq)
+    if N <= 512:
+        cs = np.abs(oout.mean).max(axis=0)
+        band_m = np.abs(oout2.mean - oout.mean).max(axis=0)
+        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, 10 * band_m)).all()
+    assert np.abs(np.triu(Lc, 1)).max() == 0.0
+
+
+SMALL = [
+    ("fitzhughnagumo", {}, 100, 3, None), ("fitzhughnagumo", {}, 100, 3, 7), ("fitzhughnagumo", {}, 4096, 3, None),
+    ("logistic", {}, 333, 1, 4), ("rigid_body", {}, 256, 3, 8), ("henonheiles", {"tmax": 10.0}, 200, 5, 8),
+    ("lotkavolterra", {}, 300, 2, 1),
+]
+
+
+@pytest.mark.parametrize("tree", ["lane", "tile"])
+@pytest.mark.parametrize("name,kw,N,q,L", SMALL)
+def test_tile_family_on_the_reference_problems(native_lib, monkeypatch, tree, name, kw, N, q, L):
+    """the tile leaves (and, with tree = tile, the CTA-per-node tree operators) forced onto the small-state problems"""
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+
+    monkeypatch.setenv("POF_B200_LEAF_IMPL", "tile")
+    if tree == "tile":
+        monkeypatch.setenv("POF_B200_TREE_IMPL", "tile")
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], states)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    torch.cuda.synchronize()
+    osetup = O.set_up_solver(oivp, ts, q)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    _check_pass(out, nll, obj, ssq, osetup, odom, N)
+
+
+@pytest.mark.parametrize("name,kw,N,q,L", [("fitzhughnagumo", {}, 100, 3, 7), ("rigid_body", {}, 300, 2, None),
+                                            ("lorenz96", {"tmax": 1.0, "d": 8}, 60, 2, 7)])
+def test_noisy_observations_match_oracle(native_lib, name, kw, N, q, L):
+    """cholR != 0 through the reference's own seam linear_filtsmooth(x0, dtm, AffineModel(H, b, cholR))"""
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.observations import AffineModel
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], states)
+    d = int(ivp.y0.shape[0])
+    rng = np.random.default_rng(1)
+    R = np.tril(0.05 * rng.standard_normal((N - 1, d, d))) + 0.1 * np.eye(d)
+    dom = AffineModel(dom.H, dom.b, torch.as_tensor(R, device=dom.H.device))
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    torch.cuda.synchronize()
+    osetup = O.set_up_solver(oivp, ts, q)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    odom = O.AffineModel(odom.H, odom.b, R)
+    _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=True)
+
+
+@pytest.mark.parametrize("N,L", [(40, 6), (150, None)])
+def test_lorenz96_d16_q3_pass_matches_oracle(native_lib, N, L):
+    """BASELINE config 5's state size (D = 64) on a grid the oracle finishes in seconds"""
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+
+    assert native_lib.LIB.pof_supported(16, 3) == 1
+    ivp, oivp = _pair("lorenz96", tmax=1.0)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=3)
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], states)  # fused k_linearize_l96
+    osetup = O.set_up_solver(oivp, ts, 3)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    np.testing.assert_allclose(setup["x0"].mean.cpu().numpy(), osetup["x0"].mean, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(dom.H.cpu().numpy(), odom.H, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(dom.b.cpu().numpy(), odom.b, rtol=1e-12, atol=1e-12)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    torch.cuda.synchronize()
+    _check_pass(out, nll, obj, ssq, osetup, odom, N)
+
+
+def test_lorenz96_fused_iteration_equals_dense_pass(native_lib):
+    """pof_ieks_iteration_f64 (compact [J_f | c] linearisation inside the workspace) == linearise + dense pass"""
+    import pof.ivp
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth, run_iteration
+    from pof.step import linearize_at_previous_states
+
+    ivp = pof.ivp.lorenz96(tmax=2.0)
+    N = 700
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=3)
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], states)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom)
+    means = states.mean.contiguous().clone()
+    chols = torch.empty((N, 64, 64), dtype=torch.float64, device=means.device)
+    sc = run_iteration(setup["x0"], setup["_qL"], setup["om"].f._pof_lin, means, chols, calibrate=False)
+    torch.cuda.synchronize()
+    scale = out.mean.abs().max().item()
+    assert (means - out.mean).abs().max().item() <= 1e-11 * scale
+    C, C2 = out.chol @ out.chol.transpose(-1, -2), chols @ chols.transpose(-1, -2)
+    assert (C - C2).abs().max().item() <= 1e-10 * C.abs().max().item()
+    assert abs(float(sc[native_lib.S_NLL]) - float(nll)) <= 1e-10 * abs(float(nll))
+    assert abs(float(sc[native_lib.S_OBJ]) - float(obj)) <= 1e-10 * abs(float(obj))
+
+
+def test_lorenz96_solve_converges_to_the_ode_solution(native_lib):
+    """the whole IEKS loop at D = 64 (graph-replayed fused iterations on the tile kernels) against SciPy DOP853"""
+    from scipy.integrate import solve_ivp
+
+    import pof.ivp
+    from pof.solver import solve
+
+    ivp = pof.ivp.lorenz96(tmax=1.0)
+    N = 2049
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    ys, info = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=200)
+    torch.cuda.synchronize()
+    assert 2 <= info["iterations"] < 200 and np.isfinite(info["obj"])
+    y0 = ivp.y0.numpy()
+    rhs = lambda t, y: (np.roll(y, -1) - np.roll(y, 2)) * np.roll(y, 1) - y + 8.0
+    ref = solve_ivp(rhs, (0.0, 1.0), y0, method="DOP853", rtol=1e-12, atol=1e-12, t_eval=ts).y.T
+    err = np.abs(ys.mean.cpu().numpy() - ref).max()
+    assert err < 1e-6, err
+    assert tuple(ys.chol.shape) == (N, 16, 64)
+
+
+@pytest.mark.parametrize("D", [40, 64])
+def test_large_state_operators_match_oracle(native_lib, D):
+    """the S3 operators at state sizes only the tile tree kernels serve"""
+    from pof.parallel_filtsmooth import sqrt_filtering_operator, sqrt_smoothing_operator
+
+    rng = np.random.default_rng(D)
+    n = 9
+    e = lambda: (rng.standard_normal((n, D, D)) / np.sqrt(D), rng.standard_normal((n, D)),
+                 np.tril(rng.standard_normal((n, D, D))) / np.sqrt(D), rng.standard_normal((n, D)),
+                 np.tril(rng.standard_normal((n, D, D))) / np.sqrt(D))
+    e1, e2 = e(), e()
+    t = lambda x: tuple(torch.as_tensor(a, device="cuda") for a in x)
+    out = [x.cpu().numpy() for x in sqrt_filtering_operator(t(e1), t(e2))]
+    ref = O.sqrt_filtering_operator(e1, e2)
+    for i in (0, 1, 3):
+        np.testing.assert_allclose(out[i], ref[i], rtol=0, atol=1e-9 * np.abs(ref[i]).max())
+    for i in (2, 4):
+        np.testing.assert_allclose(_cov(out[i]), _cov(ref[i]), rtol=0, atol=1e-9 * np.abs(_cov(ref[i])).max())
+    s = lambda: (rng.standard_normal((n, D)), rng.standard_normal((n, D, D)) / np.sqrt(D),
+                 np.tril(rng.standard_normal((n, D, D))))
+    s1, s2 = s(), s()
+    out = [x.cpu().numpy() for x in sqrt_smoothing_operator(t(s1), t(s2))]
+    ref = O.sqrt_smoothing_operator(s1, s2)
+    for i in (0, 1):
+        np.testing.assert_allclose(out[i], ref[i], rtol=0, atol=1e-9 * np.abs(ref[i]).max())
+    np.testing.assert_allclose(_cov(out[2]), _cov(ref[2]), rtol=0, atol=1e-9 * np.abs(_cov(ref[2])).max())
