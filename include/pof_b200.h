@@ -101,14 +101,21 @@ int pof_linear_filtsmooth_f64(pof_stream_t s, int64_t N, int d, int q, int64_t c
                               double* means, double* chols, double* fmeans, double* fchols, int calibrate,
                               double* scalars, void* ws, size_t ws_bytes);
 
-/* The same pass with observation noise: cholR (n,d,d) lower-triangular factors of the observation covariances
- * (reference AffineModel.cholR, pof/observations.py:23-33; used by the reference's regularised iterations,
- * pof/observations.py:43-83).  cholR == NULL is the noiseless case.  Served by the large-state ("tile") kernels for any
- * (d, q) they support (pof_supported_tile); chunk_len from pof_default_chunk_len_tile. */
-int pof_linear_filtsmooth_noisy_f64(pof_stream_t s, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
-                                    const double* x0_mean, const double* x0_chol, const double* H, const double* c,
-                                    const double* cholR, double* means, double* chols, double* fmeans, double* fchols,
-                                    int calibrate, double* scalars, void* ws, size_t ws_bytes);
+/* The same pass for a GENERAL linear-Gaussian model -- the full argument range of the reference's seam
+ *   linear_filtsmooth(x0, TransitionModel(F (n,D,D), QL (n,D,D)), AffineModel(H (n,d,D), b (n,d), cholR (n,d,d)))
+ *   pof/parallel_filtsmooth/__init__.py:5-10, pof/transitions.py:15-19, pof/observations.py:23-33:
+ *   F, QL  : per-step dense transition matrices and lower-triangular process-noise factors, e.g. the reference's
+ *            non-preconditioned models on a non-uniform grid (pof/transitions.py:71-99, pof/convenience.py:48-73);
+ *            both NULL = the preconditioned IWP given by qL_host (then qL_host must not be NULL)
+ *   cholR  : lower-triangular factors of the observation covariances (the reference's regularised iterations,
+ *            pof/observations.py:43-83); NULL = noiseless
+ * D = d (q+1).  Served by the large-state ("tile") kernels for any (d, q) they support (pof_supported_tile);
+ * chunk_len from pof_default_chunk_len_tile, workspace from pof_workspace_bytes. */
+int pof_linear_filtsmooth_general_f64(pof_stream_t s, int64_t N, int d, int q, int64_t chunk_len,
+                                      const double* qL_host, const double* F, const double* QL, const double* x0_mean,
+                                      const double* x0_chol, const double* H, const double* c, const double* cholR,
+                                      double* means, double* chols, double* fmeans, double* fchols, int calibrate,
+                                      double* scalars, void* ws, size_t ws_bytes);
 /* 1 if the CTA-per-chunk large-state kernels support (d, q) (any d, 1 <= q <= 5, D = d (q+1) limited by the 227 KB of
  * shared memory per CTA: D <= 64 at d = 16); their default chunk length (one chunk per resident CTA) */
 int pof_supported_tile(int d, int q);

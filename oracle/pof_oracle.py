@@ -101,10 +101,15 @@ def whiten(m, cholP):
     return solve_lower(cholP, m, trans=True)
 
 
+def _mv(F, m):
+    """rows of m times F^T; F is one (D,D) matrix or the reference's per-step stack (n,D,D) (vmapped models)."""
+    return m @ F.T if F.ndim == 2 else np.einsum("nij,nj->ni", F, m)
+
+
 def objective_function_value(mnext, m, F, QL):
-    """pof/utils.py:97-101 (batched over leading axis; F, QL are single (D,D))."""
-    r = mnext - m @ F.T
-    Lb = np.broadcast_to(QL, r.shape[:-1] + QL.shape)
+    """pof/utils.py:97-101 (batched over leading axis; F, QL are single (D,D) or per-step (n,D,D))."""
+    r = mnext - _mv(F, m)
+    Lb = np.broadcast_to(QL, r.shape[:-1] + QL.shape[-2:])
     w = solve_lower(Lb, r)
     return np.sum(w * w, -1)
 
@@ -285,7 +290,7 @@ def _T(x):
 def get_filter_elements(F, QL, H, c, cholR, ms, Ls):
     """filter.py:50-81 `_get_element`, batched over the leading axis."""
     n, ny, nx = H.shape
-    m1 = ms @ F.T
+    m1 = _mv(F, ms)
     N1_ = tria(np.concatenate([F @ Ls, np.broadcast_to(QL, (n, nx, nx))], axis=-1))
     Psi_ = np.concatenate(
         [np.concatenate([H @ N1_, cholR], axis=-1), np.concatenate([N1_, np.zeros((n, nx, ny))], axis=-1)], axis=-2
@@ -339,7 +344,7 @@ def sqrt_filtering_operator(elem1, elem2):
 def _get_obs(F, QL, H, c, cholR, m, cholP):
     """filter.py:84-93, batched."""
     n, ny, nx = H.shape
-    predicted_mean = m @ F.T
+    predicted_mean = _mv(F, m)
     predicted_chol = tria(np.concatenate([F @ cholP, np.broadcast_to(QL, (n, nx, nx))], axis=-1))
     obs_mean = np.einsum("nij,nj->ni", H, predicted_mean) + c
     obs_chol = tria(np.concatenate([H @ predicted_chol, cholR], axis=-1))
@@ -387,7 +392,7 @@ def _sqrt_associative_params(F, QL, m, chol_P):
     Dm = Tria_Phi[:, nx:, nx:]
     # smoother.py:48: E = solve(Phi11.T, Phi21.T).T  (general solve; Phi11 is triangular)
     E = _T(solve_lower(Phi11, _T(Phi21), trans=True))
-    g = m - np.einsum("nij,nj->ni", E, m @ F.T)
+    g = m - np.einsum("nij,nj->ni", E, _mv(F, m))
     return g, E, Dm
 
 

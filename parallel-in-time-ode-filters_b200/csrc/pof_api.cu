@@ -513,6 +513,8 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   a.c = c;
   a.Jc = nullptr;
   a.R = nullptr;
+  a.F = nullptr;
+  a.QLd = nullptr;
   a.d = d;
   a.q = q;
   a.s0 = a.s1 = 0.0;
@@ -999,13 +1001,17 @@ int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t 
   return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
 }
 
-// general observation noise: always the tile family (the only leaves that carry the D-column posterior factor)
-int pof_linear_filtsmooth_noisy_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
-                                    const double* x0_mean, const double* x0_chol, const double* H, const double* c,
-                                    const double* cholR, double* means, double* chols, double* fmeans, double* fchols,
-                                    int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
+// general linear-Gaussian model: always the tile family (the only leaves that carry the D-column posterior factor and
+// read dense per-step transition models)
+int pof_linear_filtsmooth_general_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len,
+                                      const double* qL_host, const double* F, const double* QL, const double* x0_mean,
+                                      const double* x0_chol, const double* H, const double* c, const double* cholR,
+                                      double* means, double* chols, double* fmeans, double* fchols, int calibrate,
+                                      double* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
+  if ((F == nullptr) != (QL == nullptr)) return POF_E_ARG;
+  if (!F && !qL_host) return POF_E_ARG;
   if (!tile_supported(d, q)) return POF_E_UNSUPPORTED_DQ;
   const LeafLaunch* ll = tile_leaf_launch();
   WsLayout wl;
@@ -1013,9 +1019,12 @@ int pof_linear_filtsmooth_noisy_f64(pof_stream_t s_, int64_t N, int d, int q, in
   if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
   double* ws = (double*)ws_;
   LeafArgs a;
-  int rc = make_args(N - 1, d, q, qL_host, H, c, wl, a);
+  double ql_dummy[36] = {0.0};
+  int rc = make_args(N - 1, d, q, qL_host ? qL_host : ql_dummy, H, c, wl, a);
   if (rc) return rc;
   a.R = cholR;
+  a.F = F;
+  a.QLd = QL;
   return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
 }
 

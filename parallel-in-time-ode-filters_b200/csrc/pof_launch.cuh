@@ -57,6 +57,8 @@ struct LeafArgs {
   QLParam ql;
   int d, q;          // runtime dimensions (the tile family is not templated on them)
   const double* R;   // observation-noise factors cholR (n,d,d), or null = noiseless (tile family only)
+  const double* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
+  const double* QLd; // preconditioned IWP described by ql (tile family only)
 };
 
 struct LeafLaunch {

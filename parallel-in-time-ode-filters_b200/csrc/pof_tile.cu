@@ -18,6 +18,8 @@ static __device__ __forceinline__ TileLin make_lin(const LeafArgs& a) {
   lin.R = a.R;
   lin.s0 = a.s0;
   lin.s1 = a.s1;
+  lin.F = a.F;
+  lin.QL = a.QLd;
   return lin;
 }
 
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   const long k1 = (k0 + a.L < a.n) ? k0 + a.L : a.n;
   const double cs = cscale ? *cscale : 1.0;
   Team t;
-  tile_smooth(t, a.d, a.q, a.ql.v, k0, k1, ch == a.CS - 1, emit_t0 != 0, sin + ch * ST, kern, cs, means, chols,
+  tile_smooth(t, a.d, a.q, a.ql.v, make_lin(a), k0, k1, ch == a.CS - 1, emit_t0 != 0, sin + ch * ST, kern, cs, means, chols,
               part2 + ch * 2, sm);
 }
 

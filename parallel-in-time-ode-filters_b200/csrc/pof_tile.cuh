@@ -127,6 +127,11 @@ struct TileModel {
   int d, q, Q1, D;
   const double* cf;  // Q1 x Q1: cf[i][j] = binom(q-i, j-i) for j >= i (row i of flip(pascal)), else 0
   const double* ql;  // Q1 x Q1 lower triangular
+  // general transition model of the current step (the reference's per-step TransitionModel(F, QL), e.g. the
+  // non-preconditioned / non-uniform-grid models of pof/transitions.py:71-99): dense D x D in global memory, or null =
+  // the preconditioned IWP above
+  const double* Fd;
+  const double* Qd;
 };
 constexpr int TILE_MODEL_DOUBLES = 2 * 36;
 
@@ -139,6 +144,8 @@ POF_TDEV void tile_model_init(const Team& t, TileModel& md, int d, int q, const 
   double* ql = smem + 36;
   md.cf = cf;
   md.ql = ql;
+  md.Fd = nullptr;
+  md.Qd = nullptr;
   const int Q1 = q + 1;
   t.each(Q1 * Q1, [&](int idx) {
     const int i = idx / Q1, j = idx - i * Q1;
@@ -155,12 +162,17 @@ POF_TDEV void tile_model_init(const Team& t, TileModel& md, int d, int q, const 
 // (F X)(r, c) for X given by an accessor: row r = b*Q1 + i  <-  sum_{j >= i} cf[i][j] X(b*Q1 + j, c)
 template <class FX>
 POF_TDEV double tile_F_row(const TileModel& md, int r, FX x) {
-  const int b = r / md.Q1, i = r - b * md.Q1;
   double s = 0.0;
+  if (md.Fd) {
+    for (int j = 0; j < md.D; ++j) s = fma(md.Fd[r * md.D + j], x(j), s);
+    return s;
+  }
+  const int b = r / md.Q1, i = r - b * md.Q1;
   for (int j = i; j < md.Q1; ++j) s = fma(md.cf[i * md.Q1 + j], x(b * md.Q1 + j), s);
   return s;
 }
 POF_TDEV double tile_QL(const TileModel& md, int r, int c) {
+  if (md.Qd) return (c <= r) ? md.Qd[r * md.D + c] : 0.0;
   const int br = r / md.Q1, bc = c / md.Q1;
   const int i = r - br * md.Q1, j = c - bc * md.Q1;
   return (br == bc && j <= i) ? md.ql[i * md.Q1 + j] : 0.0;
@@ -174,7 +186,13 @@ struct TileLin {
   const double* Jc;  // (n, d*d + d) or null
   const double* R;   // (n, d, d) or null (noiseless)
   double s0, s1;
+  const double* F;   // general per-step transition matrices (n, D, D) and noise factors (lower), or null = IWP
+  const double* QL;
 };
+POF_TDEV void tile_set_step_model(TileModel& md, const TileLin& lin, long k) {
+  md.Fd = lin.F ? lin.F + k * md.D * md.D : nullptr;
+  md.Qd = lin.QL ? lin.QL + k * md.D * md.D : nullptr;
+}
 POF_TDEV void tile_stage_lin(const Team& t, const TileModel& md, const TileLin& lin, long k, double* Hs, double* cs,
                              double* Rs) {
   const int d = md.d, D = md.D, Q1 = md.Q1;
@@ -299,15 +317,33 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
   });
   for (long k = k0; k < k1; ++k) {
     tile_stage_lin(t, md, lin, k, Hs, v.cs, v.Rs);
-    // predict: A <- F A, b <- F b (one thread per column: in place, rows ascending within a block), [QL | F Uf]
-    t.each(D + 1, [&](int c) {
-      for (int r = 0; r < D; ++r) {
+    tile_set_step_model(md, lin, k);
+    // predict: A <- F A, b <- F b, [QL | F Uf]
+    if (md.Fd) {  // dense F: out of place through PW (free until the next each)
+      t.each(D * (D + 1), [&](int idx) {
+        const int r = idx / (D + 1), c = idx - r * (D + 1);
         if (c < D)
-          A[r * lda + c] = tile_F_row(md, r, [&](int j) { return A[j * lda + c]; });
+          PW[r * ldp + c] = tile_F_row(md, r, [&](int j) { return A[j * lda + c]; });
         else
-          b[r] = tile_F_row(md, r, [&](int j) { return b[j]; });
-      }
-    });
+          v.v2[r] = tile_F_row(md, r, [&](int j) { return b[j]; });
+      });
+      t.each(D * (D + 1), [&](int idx) {
+        const int r = idx / (D + 1), c = idx - r * (D + 1);
+        if (c < D)
+          A[r * lda + c] = PW[r * ldp + c];
+        else
+          b[r] = v.v2[r];
+      });
+    } else {  // IWP: one thread per column, in place, rows ascending (row r only reads rows >= r of its block)
+      t.each(D + 1, [&](int c) {
+        for (int r = 0; r < D; ++r) {
+          if (c < D)
+            A[r * lda + c] = tile_F_row(md, r, [&](int j) { return A[j * lda + c]; });
+          else
+            b[r] = tile_F_row(md, r, [&](int j) { return b[j]; });
+        }
+      });
+    }
     t.each(D * D, [&](int idx) {
       const int r = idx / D, c = idx - r * D;
       PW[r * ldp + c] = tile_QL(md, r, c);
@@ -401,6 +437,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
   });
   for (long k = k0; k < k1; ++k) {
     tile_stage_lin(t, md, lin, k, Hs, v.cs, v.Rs);
+    tile_set_step_model(md, lin, k);
     t.each(D * D, [&](int idx) {
       const int r = idx / D, c = idx - r * D;
       PW[r * ldp + c] = tile_QL(md, r, c);
@@ -498,7 +535,8 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
 // ---------------------------------------------------------------------------------------------------------------
 // seed: packed smoothed state (m, L lower) at time k1.  Writes the smoothed states t in [k0, k1) (and t = n when
 // `last`) in API layout, factors scaled by cscale (pof/step.py:42-44).  part: [obj, #mean entries not close].
-POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, long k0, long k1, bool last,
+POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, const TileLin& lin, long k0, long k1,
+                          bool last,
                           bool emit_t0, const double* __restrict__ seed, const double* __restrict__ kern,
                           double cscale, double* __restrict__ means, double* __restrict__ chols,
                           double* __restrict__ part, double* smem) {
@@ -544,6 +582,7 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, l
   if (last) emit(k1);
   for (long k = k1 - 1; k >= k0; --k) {
     const double* kp = kern + k * NE;
+    tile_set_step_model(md, lin, k);
     t.each(D * D, [&](int idx) {
       const int r = idx / D, c = idx - r * D;
       Es[r * lde + c] = kp[D + idx];
@@ -569,12 +608,24 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, l
     // per block of the block-diagonal QL; new state
     t.each(d, [&](int b) {
       double o = 0.0;
-      for (int i = 0; i < Q1; ++i) {
-        double s = mn[b * Q1 + i] - fm[b * Q1 + i];
-        for (int j = 0; j < i; ++j) s = fma(-md.ql[i * Q1 + j], rs[b * Q1 + j], s);
-        s /= md.ql[i * Q1 + i];
-        rs[b * Q1 + i] = s;
-        o = fma(s, s, o);
+      if (md.Qd) {  // dense QL: one forward substitution over the whole state (iteration 0), nothing for the others
+        if (b == 0) {
+          for (int i = 0; i < D; ++i) {
+            double s = mn[i] - fm[i];
+            for (int j = 0; j < i; ++j) s = fma(-md.Qd[i * D + j], rs[j], s);
+            s /= md.Qd[i * D + i];
+            rs[i] = s;
+            o = fma(s, s, o);
+          }
+        }
+      } else {
+        for (int i = 0; i < Q1; ++i) {
+          double s = mn[b * Q1 + i] - fm[b * Q1 + i];
+          for (int j = 0; j < i; ++j) s = fma(-md.ql[i * Q1 + j], rs[b * Q1 + j], s);
+          s /= md.ql[i * Q1 + i];
+          rs[b * Q1 + i] = s;
+          o = fma(s, s, o);
+        }
       }
       v.w[b] = o;
     });

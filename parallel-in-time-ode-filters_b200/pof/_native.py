@@ -51,9 +51,9 @@ def _load():
         "pof_linear_filtsmooth_f64": (
             _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
                      _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
-        "pof_linear_filtsmooth_noisy_f64": (
+        "pof_linear_filtsmooth_general_f64": (
             _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
-                     _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+                     _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
         "pof_supported_tile": (_c_int, [_c_int, _c_int]),
         "pof_default_chunk_len_tile": (_c_i64, [_c_i64, _c_int, _c_int, _c_int]),
         "pof_ieks_iteration_f64": (
@@ -100,7 +100,7 @@ EXPORTED = [
     "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_linearize_ivp_compact_f64",
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
     "pof_project_f64", "pof_profile_enable", "pof_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops",
-    "pof_linear_filtsmooth_noisy_f64", "pof_supported_tile", "pof_default_chunk_len_tile",
+    "pof_linear_filtsmooth_general_f64", "pof_supported_tile", "pof_default_chunk_len_tile",
 ]
 
 

@@ -4,7 +4,7 @@ import torch
 
 from . import initialization as init
 from .observations import NonlinearModel
-from .transitions import (IWP, TransitionModel, nordsieck_preconditioner, nordsieck_scalings,
+from .transitions import (IWP, TransitionModel, discretize_transitions, nordsieck_preconditioner, nordsieck_scalings,
                           preconditioned_discretize, preconditioned_discretize_1d, projection_matrix)
 from .utils import MVNSqrt
 
@@ -52,6 +52,33 @@ def set_up_solver(*, f, y0, ts, order):
         "f": f, "y0": y0_h, "ts": ts_h, "dtm": TransitionModel(tt(F), tt(QL)), "om": om, "x0": x0,
         "E0": E0_t, "P": tt(P), "PI": PI_t, "order": order, "iwp": iwp,
         "_qL": np.ascontiguousarray(qL), "_scale0": float(sv[0]), "_device": dev,
+    }
+
+
+def set_up_solver_no_precond(*, f, y0, ts, order):
+    """reference convenience.py:48-73: non-preconditioned coordinates, one dense transition model per step -- valid on
+    NON-uniform grids.  `dtm` holds (n,D,D) stacks; `linear_filtsmooth` / `ieks_step` route them to the general pass."""
+    dev = _device()
+    ts_h = np.asarray(torch.as_tensor(ts, dtype=torch.float64).detach().cpu())
+    y0_h = torch.as_tensor(y0, dtype=torch.float64).detach().cpu()
+    d = int(y0_h.shape[0])
+    iwp = IWP(num_derivatives=order, wiener_process_dimension=d)
+    dtm = discretize_transitions(iwp, times=ts_h, device=dev)
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    E0_t, E1_t = tt(projection_matrix(iwp, 0)), tt(projection_matrix(iwp, 1))
+
+    def om_f(x):
+        return E1_t.to(x.device) @ x - f(None, E0_t.to(x.device) @ x)
+
+    om_f._pof_lin = dict(builtin=getattr(f, "_pof_builtin", None), f=f, scale0=1.0, scale1=1.0, d=d, q=order,
+                         E0=E0_t, E1=E1_t)
+    x0 = init.taylor_mode_init(f, y0_h, order)
+    x0 = MVNSqrt(x0.mean.to(dev), x0.chol.to(dev))
+    eye = torch.eye(d * (order + 1), dtype=torch.float64, device=dev)
+    _, qL = preconditioned_discretize_1d(iwp)
+    return {
+        "f": f, "y0": y0_h, "ts": ts_h, "dtm": dtm, "om": NonlinearModel(om_f), "x0": x0, "E0": E0_t, "P": eye,
+        "PI": eye, "order": order, "iwp": iwp, "_qL": np.ascontiguousarray(qL), "_scale0": 1.0, "_device": dev,
     }
 
 

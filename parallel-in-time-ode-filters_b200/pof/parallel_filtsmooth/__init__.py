@@ -15,20 +15,27 @@ from ..utils import MVNSqrt
 
 
 def _model_dims(dtm: TransitionModel, dom: AffineModel):
+    """-> (n, d, q, D, qL, dense): dense = None for the preconditioned IWP of pof.transitions (the specialised kernels),
+    else contiguous per-step (F (n,D,D), QL (n,D,D)) for the general kernels (`pof_linear_filtsmooth_general_f64`)."""
     n, d, D = dom.H.shape
     if D % d != 0:
         raise ValueError("state dimension must be d*(q+1)")
     q = D // d - 1
-    F = dtm.F[0] if dtm.F.dim() == 3 else dtm.F
-    QL = dtm.QL[0] if dtm.QL.dim() == 3 else dtm.QL
     Fi, QLi = preconditioned_discretize(IWP(num_derivatives=q, wiener_process_dimension=d))
-    Fh, QLh = F.detach().cpu().numpy(), QL.detach().cpu().numpy()
-    if not (np.allclose(Fh, Fi, rtol=0, atol=1e-12) and np.allclose(QLh, QLi, rtol=0, atol=1e-12)):
-        raise NotImplementedError(
-            "the CUDA pass is specialised to the preconditioned IWP transition model of pof.transitions "
-            "(F = I_d (x) flip(pascal), QL = I_d (x) chol(flip(hilbert))); other transition models are out of scope"
-        )
-    return n, d, q, D, np.ascontiguousarray(QLi[: q + 1, : q + 1])
+    qL = np.ascontiguousarray(QLi[: q + 1, : q + 1])
+
+    def is_const(M, ref):
+        M0 = M[0] if M.dim() == 3 else M
+        if not np.allclose(M0.detach().cpu().numpy(), ref, rtol=0, atol=1e-12):
+            return False
+        return M.dim() == 2 or bool((M == M0).all())
+
+    if is_const(dtm.F, Fi) and is_const(dtm.QL, QLi):
+        return n, d, q, D, qL, None
+    if not bool((torch.triu(dtm.QL, 1) == 0).all()):
+        raise ValueError("QL must be lower triangular (a Cholesky factor of the process-noise covariance)")
+    rep = lambda M: (M if M.dim() == 3 else M.unsqueeze(0).expand(n, D, D)).contiguous()
+    return n, d, q, D, qL, (rep(dtm.F), rep(dtm.QL))
 
 
 def _noise(dom: AffineModel):
@@ -39,24 +46,28 @@ def _noise(dom: AffineModel):
 
 
 def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_len=None, fmeans=None, fchols=None,
-             scalars=None, cholR=None):
+             scalars=None, cholR=None, dense=None):
     """One filter+smoother pass on device buffers (the call `solve` makes every iteration).  cholR (n,d,d): noisy
-    observations, served by the large-state kernels (`pof_linear_filtsmooth_noisy_f64`)."""
+    observations; dense = (F (n,D,D), QL (n,D,D)): general per-step transition models -- both served by the
+    large-state kernels (`pof_linear_filtsmooth_general_f64`)."""
     N = means_io.shape[0]
-    nat.require_cuda(x0.mean, x0.chol, H, c, means_io, chols, fmeans, fchols, cholR)
+    general = cholR is not None or dense is not None
+    Fd, QLd = dense if dense is not None else (None, None)
+    nat.require_cuda(x0.mean, x0.chol, H, c, means_io, chols, fmeans, fchols, cholR, Fd, QLd)
     dev = means_io.device
     if chunk_len is None:
-        chunk_len = (nat.default_chunk_len_tile if cholR is not None else nat.default_chunk_len)(N, d, q, dev.index)
+        chunk_len = (nat.default_chunk_len_tile if general else nat.default_chunk_len)(N, d, q, dev.index)
     ws = nat.Workspace.get(N, d, q, chunk_len, dev)
     if scalars is None:
         scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
     qLh, qLp = nat.host_doubles(qL)
-    if cholR is not None:
-        rc = nat.LIB.pof_linear_filtsmooth_noisy_f64(
-            nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
-            nat.ptr(cholR), nat.ptr(means_io), nat.ptr(chols), nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)),
-            nat.ptr(scalars), ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
-        nat.check(rc, "pof_linear_filtsmooth_noisy_f64")
+    if general:
+        rc = nat.LIB.pof_linear_filtsmooth_general_f64(
+            nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(Fd), nat.ptr(QLd), nat.ptr(x0.mean),
+            nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c), nat.ptr(cholR), nat.ptr(means_io), nat.ptr(chols),
+            nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)), nat.ptr(scalars),
+            ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+        nat.check(rc, "pof_linear_filtsmooth_general_f64")
         return scalars
     rc = nat.LIB.pof_linear_filtsmooth_f64(
         nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
@@ -149,29 +160,30 @@ class GraphedCall:
 
 def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None):
     """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq)"""
-    n, d, q, D, qL = _model_dims(linear_transitions, linear_observations)
+    n, d, q, D, qL, dense = _model_dims(linear_transitions, linear_observations)
     dev = linear_observations.H.device
     means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
     chols = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
     sc = run_pass(x0, qL, linear_observations.H.contiguous(), linear_observations.b.contiguous(), means, chols, d=d,
-                  q=q, calibrate=False, chunk_len=chunk_len, cholR=_noise(linear_observations))
+                  q=q, calibrate=False, chunk_len=chunk_len, cholR=_noise(linear_observations), dense=dense)
     return MVNSqrt(means, chols), sc[nat.S_NLL], sc[nat.S_OBJ], sc[nat.S_SSQ]
 
 
 def linear_noiseless_filtering(x0, transition_models, observation_models, *, chunk_len=None):
     """reference parallel_filtsmooth/filter.py:18-47 -> (filtered MVNSqrt, nll, obj, ssq).
     The filtered chols are square-root factors (chol @ chol.T is the covariance) but not triangular."""
-    n, d, q, D, qL = _model_dims(transition_models, observation_models)
+    n, d, q, D, qL, dense = _model_dims(transition_models, observation_models)
     dev = observation_models.H.device
     means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
     fm = torch.empty((n + 1, D), dtype=torch.float64, device=dev)
     fc = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
     sc = run_pass(x0, qL, observation_models.H.contiguous(), observation_models.b.contiguous(), means, None, d=d, q=q,
-                  calibrate=False, chunk_len=chunk_len, fmeans=fm, fchols=fc, cholR=_noise(observation_models))
+                  calibrate=False, chunk_len=chunk_len, fmeans=fm, fchols=fc, cholR=_noise(observation_models),
+                  dense=dense)
     # filter objective (reference filter.py:43-45, swapped-argument form), evaluated on the filtered means
-    F = transition_models.F[0] if transition_models.F.dim() == 3 else transition_models.F
-    QL = transition_models.QL[0] if transition_models.QL.dim() == 3 else transition_models.QL
-    r = torch.linalg.solve_triangular(QL, (fm[:-1] - fm[1:] @ F.T).T, upper=False)
+    F, QL = transition_models.F, transition_models.QL
+    Fm = fm[1:] @ F.T if F.dim() == 2 else torch.einsum("nij,nj->ni", F, fm[1:])
+    r = torch.linalg.solve_triangular(QL, (fm[:-1] - Fm).unsqueeze(-1), upper=False)
     obj = (r * r).sum()
     return MVNSqrt(fm, fc), sc[nat.S_NLL], obj, sc[nat.S_SSQ]
 

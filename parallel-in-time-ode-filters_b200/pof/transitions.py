@@ -56,3 +56,32 @@ def nordsieck_preconditioner(iwp: IWP, dt):
 def projection_matrix(iwp: IWP, derivative_to_project_onto):
     """reference transitions.py:80-88"""
     return np.kron(np.eye(iwp.wiener_process_dimension), np.eye(1, iwp.num_derivatives + 1, derivative_to_project_onto))
+
+
+def non_preconditioned_discretize(iwp: IWP, dt):
+    """reference transitions.py:71-77: (P F PI, P QL) for one step size"""
+    P, PI = nordsieck_preconditioner(iwp, dt)
+    F, QL = preconditioned_discretize(iwp)
+    return P @ F @ PI, P @ QL
+
+
+def get_transition_model(iwp: IWP, dt):
+    """reference transitions.py:91-93 (numpy arrays; `discretize_transitions` stacks them on the device)"""
+    return TransitionModel(*non_preconditioned_discretize(iwp, dt))
+
+
+def discretize_transitions(iwp: IWP, times=None, steps=None, device=None):
+    """reference transitions.py:96-100: per-step models for arbitrary (non-uniform) grids,
+    TransitionModel(F (n,D,D), QL (n,D,D)) -- the input of the general pass `pof_linear_filtsmooth_general_f64`."""
+    if steps is None:
+        times = np.asarray(times, dtype=np.float64)
+        steps = times[1:] - times[:-1]
+    F0, QL0 = preconditioned_discretize(iwp)
+    sv = np.stack([nordsieck_scalings(iwp, dt)[0] for dt in steps])    # (n, q+1)
+    svi = np.stack([nordsieck_scalings(iwp, dt)[1] for dt in steps])
+    d = iwp.wiener_process_dimension
+    Pd, PId = np.tile(sv, (1, d)), np.tile(svi, (1, d))                  # diagonals of P_k, PI_k: (n, D)
+    Fs = Pd[:, :, None] * F0[None] * PId[:, None, :]
+    QLs = Pd[:, :, None] * QL0[None]
+    tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
+    return TransitionModel(tt(Fs), tt(QLs))

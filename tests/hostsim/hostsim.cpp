@@ -281,8 +281,9 @@ int hs_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const d
 // iteration order inside every Team::each is selectable (0 forward, 1 reverse, 2 permuted): identical results under
 // all orders <=> the iterations of every each() are independent <=> the CUDA kernels are race-free (pof_tile.cuh).
 static int run_tile(int d, int q, long N, long L, const double* qL, const double* x0, const double* H, const double* c,
-                    const double* Jc, double s0, double s1, const double* R, double* means, double* chols,
-                    double* fmeans, double* fchols, int calibrate, double* scalars, int order) {
+                    const double* Jc, double s0, double s1, const double* R, const double* Fd, const double* Qd,
+                    double* means, double* chols, double* fmeans, double* fchols, int calibrate, double* scalars,
+                    int order) {
   Team::order() = order;
   Team t;
   const int D = d * (q + 1);
@@ -297,7 +298,7 @@ static int run_tile(int d, int q, long N, long L, const double* qL, const double
                                      tile_smooth_smem_doubles(D, d), tile_tree_smem_doubles(D)}));
   // poison the shared memory so that reads of never-written entries show up as NaN
   auto poison = [&]() { std::fill(smem.begin(), smem.end(), std::nan("")); };
-  const TileLin lin = {H, c, Jc, R, s0, s1};
+  const TileLin lin = {H, c, Jc, R, s0, s1, Fd, Qd};
   for (long ch = 0; ch < CS; ++ch) {
     poison();
     tile_fold(t, d, q, qL, lin, ch * L, std::min((ch + 1) * L, n), &fagg[ch * FE], &faggm[ch * FE], smem.data());
@@ -358,7 +359,7 @@ static int run_tile(int d, int q, long N, long L, const double* qL, const double
   const double cscale = calibrate ? sqrt(ssq) : 1.0;
   for (long ch = 0; ch < CS; ++ch) {
     poison();
-    tile_smooth(t, d, q, qL, ch * L, std::min((ch + 1) * L, n), ch == CS - 1, true, &sin_[ch * ST], kern.data(), cscale,
+    tile_smooth(t, d, q, qL, lin, ch * L, std::min((ch + 1) * L, n), ch == CS - 1, true, &sin_[ch * ST], kern.data(), cscale,
                 means, chols, &part2[ch * 2], smem.data());
   }
   double obj = 0, bad = 0;
@@ -370,10 +371,11 @@ static int run_tile(int d, int q, long N, long L, const double* qL, const double
 
 extern "C" {
 int hs_tile_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const double* x0, const double* H,
-                              const double* c, const double* Jc, double s0, double s1, const double* R, double* means,
-                              double* chols, double* fmeans, double* fchols, int calibrate, double* scalars,
-                              int order) {
-  return run_tile(d, q, N, L, qL, x0, H, c, Jc, s0, s1, R, means, chols, fmeans, fchols, calibrate, scalars, order);
+                              const double* c, const double* Jc, double s0, double s1, const double* R,
+                              const double* Fd, const double* Qd, double* means, double* chols, double* fmeans,
+                              double* fchols, int calibrate, double* scalars, int order) {
+  return run_tile(d, q, N, L, qL, x0, H, c, Jc, s0, s1, R, Fd, Qd, means, chols, fmeans, fchols, calibrate, scalars,
+                  order);
 }
 int hs_tile_filter_combine(int D, const double* e1, const double* e2, double* out, int state_mode, int order) {
   std::vector<double> smem(tile_tree_smem_doubles(D), std::nan(""));

@@ -202,3 +202,48 @@ def test_large_state_operators_match_oracle(native_lib, D):
     for i in (0, 1):
         np.testing.assert_allclose(out[i], ref[i], rtol=0, atol=1e-9 * np.abs(ref[i]).max())
     np.testing.assert_allclose(_cov(out[2]), _cov(ref[2]), rtol=0, atol=1e-9 * np.abs(_cov(ref[2])).max())
+
+
+@pytest.mark.parametrize("name,q,N,noisy", [("fitzhughnagumo", 2, 300, False), ("rigid_body", 3, 200, True)])
+def test_nonuniform_grid_general_transition_models(native_lib, name, q, N, noisy):
+    """the reference's non-preconditioned per-step models (set_up_solver_no_precond, convenience.py:48-73) on a
+    NON-uniform grid, through ieks_step's pieces: fused linearisation + linear_filtsmooth with (n,D,D) F / QL stacks"""
+    from pof.convenience import set_up_solver_no_precond
+    from pof.initialization import constant_init
+    from pof.observations import AffineModel
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+    from pof.utils import MVNSqrt
+
+    ivp, oivp = _pair(name)
+    d = int(ivp.y0.shape[0])
+    D = d * (q + 1)
+    ts = ivp.t0 + (ivp.tmax - ivp.t0) * 0.3 * np.linspace(0, 1, N) ** 1.5
+    setup = set_up_solver_no_precond(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    st = constant_init(y0=ivp.y0, order=q, ts=ts, f=ivp.f)
+    dev = setup["_device"]
+    states = MVNSqrt(st.mean.to(dev).contiguous(), st.chol.to(dev))
+    dom = linearize_at_previous_states(setup["om"], states)
+    R = None
+    if noisy:
+        rng = np.random.default_rng(2)
+        R = np.tril(0.05 * rng.standard_normal((N - 1, d, d))) + 0.1 * np.eye(d)
+        dom = AffineModel(dom.H, dom.b, torch.as_tensor(R, device=dev))
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom)
+    torch.cuda.synchronize()
+
+    F0, QL0 = O.preconditioned_discretize(d, q)
+    Fs, QLs = np.empty((N - 1, D, D)), np.empty((N - 1, D, D))
+    for k, dt in enumerate(np.diff(ts)):
+        Pk, PIk = O.nordsieck_preconditioner(d, q, dt)
+        Fs[k], QLs[k] = Pk @ F0 @ PIk, Pk @ QL0
+    np.testing.assert_allclose(setup["dtm"].F.cpu().numpy(), Fs, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(setup["dtm"].QL.cpu().numpy(), QLs, rtol=1e-13, atol=0)
+    osetup = dict(ivp=oivp, ts=ts, dtm=O.TransitionModel(Fs, QLs), x0=O.taylor_mode_init(oivp, q),
+                  E0=O.projection_matrix(d, q, 0), E1=O.projection_matrix(d, q, 1), order=q, d=d)
+    ost = O.constant_init(oivp, q, N)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    np.testing.assert_allclose(dom.H.cpu().numpy(), odom.H, rtol=1e-13, atol=1e-13)
+    if noisy:
+        odom = O.AffineModel(odom.H, odom.b, R)
+    _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=noisy)

@@ -48,7 +48,7 @@ def _problem(name, kw, N, q, noisy):
     return setup, st, dom
 
 
-def _run(lib, setup, st, dom, q, L, order=0, noisy=False, compact=None):
+def _run(lib, setup, st, dom, q, L, order=0, noisy=False, compact=None, dense_model=None):
     d = setup["d"]
     D = d * (q + 1)
     N = st.mean.shape[0]
@@ -61,8 +61,9 @@ def _run(lib, setup, st, dom, q, L, order=0, noisy=False, compact=None):
     Jc, s0, s1 = (None, 0.0, 0.0) if compact is None else compact
     rc = lib.hs_tile_linear_filtsmooth(
         d, q, ctypes.c_long(N), ctypes.c_long(L), _p(qL), _p(x0), None if Jc is not None else _p(H),
-        None if Jc is not None else _p(c), _p(Jc), ctypes.c_double(s0), ctypes.c_double(s1), _p(R), _p(means),
-        _p(chols), _p(fm), _p(fc), 0, _p(sc), order)
+        None if Jc is not None else _p(c), _p(Jc), ctypes.c_double(s0), ctypes.c_double(s1), _p(R),
+        None if dense_model is None else _p(dense_model[0]), None if dense_model is None else _p(dense_model[1]),
+        _p(means), _p(chols), _p(fm), _p(fc), 0, _p(sc), order)
     assert rc == 0
     return means, chols, fm, fc, sc
 
@@ -151,3 +152,38 @@ def test_tile_shared_memory_fits_config5(lib):
     """d = 16, q = 3 (D = 64): every tile kernel's dynamic shared memory fits the 227 KB a B200 CTA can have"""
     for which in range(4):
         assert lib.hs_tile_smem_bytes(64, 16, which) <= 227 * 1024
+
+
+@pytest.mark.parametrize("name,q,N,L,noisy", [("fitzhughnagumo", 2, 60, 7, False), ("rigid_body", 3, 45, 4, True)])
+def test_tile_general_transition_models_nonuniform_grid(lib, name, q, N, L, noisy):
+    """per-step dense (F_k, QL_k): the reference's non-preconditioned models on a NON-uniform grid
+    (pof/transitions.py:71-99 `non_preconditioned_discretize`, pof/convenience.py:48-73 `set_up_solver_no_precond`)"""
+    ivp = getattr(ivps, name)()
+    d = ivp.y0.shape[0]
+    D = d * (q + 1)
+    ts = ivp.t0 + (ivp.tmax - ivp.t0) * 0.3 * np.linspace(0, 1, N) ** 1.5
+    F0, QL0 = O.preconditioned_discretize(d, q)
+    Fs, QLs = np.empty((N - 1, D, D)), np.empty((N - 1, D, D))
+    for k, dt in enumerate(np.diff(ts)):
+        Pk, PIk = O.nordsieck_preconditioner(d, q, dt)
+        Fs[k], QLs[k] = Pk @ F0 @ PIk, Pk @ QL0
+    E0, E1 = O.projection_matrix(d, q, 0), O.projection_matrix(d, q, 1)
+    x0 = O.taylor_mode_init(ivp, q)
+    st = O.constant_init(ivp, q, N)
+    setup = dict(ivp=ivp, ts=ts, dtm=O.TransitionModel(Fs, QLs), x0=x0, E0=E0, E1=E1, order=q, d=d)
+    dom = O.linearize_at(setup, st.mean[1:])
+    if noisy:
+        rng = np.random.default_rng(2)
+        dom = O.AffineModel(dom.H, dom.b, np.tril(0.05 * rng.standard_normal((N - 1, d, d))) + 0.1 * np.eye(d))
+    res = [_run(lib, setup, st, dom, q, L, order, noisy, dense_model=(Fs, QLs)) for order in (0, 1, 2)]
+    means, chols, fm, fc, sc = res[0]
+    filt, nll, _, ssq, ssqp = O.linear_noiseless_filtering(x0, setup["dtm"], dom)
+    out, obj = O.smoothing(setup["dtm"], filt)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(fm, filt.mean) <= 1e-9 and rel(means, out.mean) <= 1e-9
+    assert rel(_cov(fc), _cov(filt.chol)) <= 1e-9 and rel(_cov(chols), _cov(out.chol)) <= 1e-9
+    assert abs(sc[0] - nll) <= 1e-9 * abs(nll) and abs(sc[1] - obj) <= 1e-9 * abs(obj)
+    assert abs(sc[3] - ssqp) <= 1e-9 * ssqp
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert np.array_equal(a, b, equal_nan=True)
