@@ -1108,10 +1108,11 @@ int pof_sequential_eks_f64(pof_stream_t s_, int ivp_id, const double* params_hos
                            size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
-  if (ivp_id < 0 || ivp_id > POF_IVP_HENONHEILES) return POF_E_IVP;
-  static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
-  if (dims[ivp_id] != d || nparams > 8) return POF_E_ARG;
-  const LeafLaunch* ll = thread_launch(d, q);
+  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
+  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
+  // one thread (d <= 4 templates) or, for larger states / POF_B200_LEAF_IMPL=tile, one CTA of the tile family
+  const LeafLaunch* ll = leaf_launch(d, q);
+  if (!ll || !ll->is_tile) ll = thread_launch(d, q);
   if (!ll || !ll->seq_eks) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, N - 1);

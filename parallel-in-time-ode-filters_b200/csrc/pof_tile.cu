@@ -65,6 +65,16 @@ __global__ void __launch_bounds__(TILE_THREADS)
               part2 + ch * 2, sm);
 }
 
+// sequential EKS: ONE CTA walks the whole grid (inherently sequential baseline path of the reference)
+__global__ void __launch_bounds__(TILE_THREADS)
+    k_tile_seq_eks(LeafArgs a, TileEks eks, const double* __restrict__ x0, double* __restrict__ kern,
+                   double* __restrict__ state_end, double* __restrict__ means, double* __restrict__ chols,
+                   double* __restrict__ sums) {
+  extern __shared__ __align__(16) double sm[];
+  Team t;
+  tile_seq_eks(t, a.d, a.q, a.ql.v, make_lin(a), eks, a.n, x0, kern, state_end, means, chols, sums, sm);
+}
+
 // ------------------------------------------------------------------------------------------------ tree sweeps
 // same node conventions as the warp kernels in pof_api.cu (k_filter_up, ...), one CTA per parent node
 __global__ void __launch_bounds__(TILE_THREADS)
@@ -222,8 +232,24 @@ static cudaError_t tl_smooth(cudaStream_t s, const LeafArgs& a, const double* si
   k_tile_smooth<<<(unsigned)a.CS, TILE_THREADS, sb, s>>>(a, sin, kern, emit_t0, cscale, means, chols, part2);
   return cudaGetLastError();
 }
+// kern: (n, NE) scratch; part: >= 5 doubles [sum -loglik, ssq_ref, ssq_proper, obj, -]; the D + D^2 doubles behind
+// the packed x0 are used as scratch for the filtered end state
+static cudaError_t tl_seq_eks(cudaStream_t s, const LeafArgs& a, int ivp_id, const double* params8, const double* x0,
+                              double* kern, double* means, double* chols, double* part) {
+  const int D = a.d * (a.q + 1);
+  int dbl = tile_scan_smem_doubles(D, a.d);
+  if (tile_smooth_smem_doubles(D, a.d) > dbl) dbl = tile_smooth_smem_doubles(D, a.d);
+  const int sb = bytes(dbl);
+  if (cudaError_t e = ensure_smem(k_tile_seq_eks, sb)) return e;
+  TileEks eks;
+  eks.ivp_id = ivp_id;
+  for (int i = 0; i < 8; ++i) eks.P.p[i] = params8[i];
+  double* state_end = const_cast<double*>(x0) + (D + D * D);
+  k_tile_seq_eks<<<1, TILE_THREADS, sb, s>>>(a, eks, x0, kern, state_end, means, chols, part);
+  return cudaGetLastError();
+}
 const LeafLaunch* tile_leaf_launch() {
-  static const LeafLaunch l = {&tl_fold, &tl_scan, &tl_smooth, nullptr, 0, 1, 1};
+  static const LeafLaunch l = {&tl_fold, &tl_scan, &tl_smooth, &tl_seq_eks, 0, 1, 1};
   return &l;
 }
 

@@ -22,6 +22,7 @@
 // Observation noise: `R` (the reference's cholR, observations.py:23-33) may be non-zero here -- the posterior factor
 // then has D instead of D-d non-zero columns; R == nullptr is the noiseless ODE-solver case (step.py:12-22).
 #pragma once
+#include "pof_ivp.cuh"
 #include "pof_small.cuh"
 
 namespace pof {
@@ -192,6 +193,37 @@ struct TileLin {
 POF_TDEV void tile_set_step_model(TileModel& md, const TileLin& lin, long k) {
   md.Fd = lin.F ? lin.F + k * md.D * md.D : nullptr;
   md.Qd = lin.QL ? lin.QL + k * md.D * md.D : nullptr;
+}
+// Sequential EKS (reference pof/sequential_filtsmooth/filter.py:9-30): the observation model is relinearised at the
+// PREDICTED mean of every step, inside the kernel, for a built-in vector field.
+struct TileEks {
+  int ivp_id;
+  IvpParams P;
+};
+// Hs, cs <- linearisation of x -> E1 x - f(E0 x) at the predicted mean mp; Rs <- 0
+POF_TDEV void tile_stage_lin_eks(const Team& t, const TileModel& md, const TileEks& eks, double s0, double s1,
+                                 const double* mp, double* Hs, double* cs, double* Rs) {
+  const int d = md.d, D = md.D, Q1 = md.Q1;
+  t.each(d, [&](int a) {
+    for (int e = 0; e < d; ++e) Rs[a * d + e] = 0.0;
+    if (eks.ivp_id == POF_IVP_LORENZ96) {
+      l96_linearize_row(eks.P.p[0], 0, a, d, md.q, s0, s1, 1, mp, Hs, cs, nullptr);
+    } else if (a == 0) {  // d <= 4: one iteration evaluates the whole field and Jacobian
+      double y[4], f[4], J[16];
+      for (int b = 0; b < d; ++b) y[b] = s0 * mp[b * Q1];
+      ivp_eval(eks.ivp_id, eks.P, y, f, J);
+      for (int r = 0; r < d; ++r) {
+        double ce = -f[r];
+        for (int j = 0; j < D; ++j) Hs[r * D + j] = 0.0;
+        for (int b = 0; b < d; ++b) {
+          ce = fma(J[r * d + b], y[b], ce);
+          Hs[r * D + b * Q1] = -J[r * d + b] * s0;
+        }
+        Hs[r * D + r * Q1 + 1] += s1;
+        cs[r] = ce;
+      }
+    }
+  });
 }
 POF_TDEV void tile_stage_lin(const Team& t, const TileModel& md, const TileLin& lin, long k, double* Hs, double* cs,
                              double* Rs) {
@@ -413,7 +445,7 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
 POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, const TileLin& lin, long k0, long k1,
                         const double* __restrict__ state_in, double* __restrict__ kern,
                         double* __restrict__ state_end, double* __restrict__ part, double* __restrict__ fmeans,
-                        double* __restrict__ fchols, double* smem) {
+                        double* __restrict__ fchols, double* smem, const TileEks* eks = nullptr) {
   TileModel md;
   tile_model_init(t, md, d, q, ql_param, smem);
   const int D = md.D, DD = D * D, NE = D + 2 * DD;
@@ -436,7 +468,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
     if (idx < 3) v.acc[idx] = 0.0;
   });
   for (long k = k0; k < k1; ++k) {
-    tile_stage_lin(t, md, lin, k, Hs, v.cs, v.Rs);
+    if (!eks) tile_stage_lin(t, md, lin, k, Hs, v.cs, v.Rs);
     tile_set_step_model(md, lin, k);
     t.each(D * D, [&](int idx) {
       const int r = idx / D, c = idx - r * D;
@@ -446,6 +478,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       PW[(D + r) * ldp + D + c] = X[(long)(d + r) * ldx + d + c];
       if (c == 0) mp[r] = tile_F_row(md, r, [&](int j) { return m[j]; });
     });
+    if (eks) tile_stage_lin_eks(t, md, *eks, lin.s0, lin.s1, mp, Hs, v.cs, v.Rs);
     tile_tria(t, PW, 2 * D, 2 * D, ldp, D, D, v.diag);
     // E = Phi21 T^{-1} (row-wise back substitution, in place), then g = m - E (F m)
     t.each(D, [&](int r) {
@@ -647,6 +680,17 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
     part[0] = v.acc[0];
     part[1] = nb;
   });
+}
+
+// Sequential extended Kalman smoother on ONE CTA (reference pof/sequential_filtsmooth/__init__.py:5-10): the filter
+// relinearised at every predicted mean over the whole grid, then the RTS recursion.  x0: packed (m, L).  kern: (n, NE)
+// scratch, state_end: D + D^2 scratch.  sums: [sum -loglik, ssq_ref sum, ssq_proper sum, obj, (unused count)].
+POF_TDEV void tile_seq_eks(const Team& t, int d, int q, const double* ql_param, const TileLin& lin, const TileEks& eks,
+                           long n, const double* __restrict__ x0, double* __restrict__ kern,
+                           double* __restrict__ state_end, double* __restrict__ means, double* __restrict__ chols,
+                           double* __restrict__ sums, double* smem) {
+  tile_scan(t, d, q, ql_param, lin, 0, n, x0, kern, state_end, sums, nullptr, nullptr, smem, &eks);
+  tile_smooth(t, d, q, ql_param, lin, 0, n, true, true, state_end, kern, 1.0, means, chols, sums + 3, smem);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -393,6 +393,21 @@ int hs_tile_smooth_combine(int D, const double* e1, const double* e2, double* ou
   Team::order() = 0;
   return 0;
 }
+int hs_tile_seq_eks(int d, int q, long N, const double* qL, double s0, double s1, int ivp_id, const double* params8,
+                    const double* x0, double* means, double* chols, double* sums, int order) {
+  Team::order() = order;
+  Team t;
+  const int D = d * (q + 1);
+  TileEks eks;
+  eks.ivp_id = ivp_id;
+  for (int i = 0; i < 8; ++i) eks.P.p[i] = params8[i];
+  const TileLin lin = {nullptr, nullptr, nullptr, nullptr, s0, s1, nullptr, nullptr};
+  std::vector<double> kern((size_t)(N - 1) * (D + 2 * D * D)), send(D + D * D);
+  std::vector<double> smem(std::max(tile_scan_smem_doubles(D, d), tile_smooth_smem_doubles(D, d)), std::nan(""));
+  tile_seq_eks(t, d, q, qL, lin, eks, N - 1, x0, kern.data(), send.data(), means, chols, sums, smem.data());
+  Team::order() = 0;
+  return 0;
+}
 // Lorenz-96 linearisation (the body of k_linearize_l96): dense (H, c) and compact [J_f | c]
 int hs_linearize_l96(double forcing, long n, int d, int q, double s0, double s1, const double* means_t1, double* H,
                      double* c, double* Jc) {

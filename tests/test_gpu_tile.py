@@ -247,3 +247,26 @@ def test_nonuniform_grid_general_transition_models(native_lib, name, q, N, noisy
     if noisy:
         odom = O.AffineModel(odom.H, odom.b, R)
     _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=noisy)
+
+
+@pytest.mark.parametrize("name,kw,N,q,force", [("fitzhughnagumo", {}, 300, 3, True), ("logistic", {}, 21, 1, True),
+                                               ("lorenz96", {"tmax": 0.5}, 40, 3, False)])
+def test_tile_sequential_eks_solve_matches_oracle(native_lib, monkeypatch, name, kw, N, q, force):
+    """sequential_eks_solve on ONE CTA of the tile family (k_tile_seq_eks): forced onto small problems, and the only
+    path for d = 16"""
+    from pof.solver import sequential_eks_solve
+
+    if force:
+        monkeypatch.setenv("POF_B200_LEAF_IMPL", "tile")
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    ys, info = sequential_eks_solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    oys, oinfo = O.sequential_eks_solve(oivp, ts, q)
+    y, yo = ys.mean.cpu().numpy(), oys.mean
+    assert (np.abs(y - yo) <= 1e-9 * np.abs(yo).max(axis=0) + 1e-12).all()
+    s, so = info["sigma_squared"], oinfo["sigma_squared"]
+    C, Co = _cov(ys.chol.cpu().numpy()) / s, _cov(oys.chol) / so
+    assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
+    d = int(ivp.y0.shape[0])
+    assert abs(s - so) <= (5e-2 if d <= 4 else 1e-1) * abs(so)  # QR-sign dependent formula (utils.py:110-112)
+    assert abs(info["nll"] - oinfo["nll"]) <= 1e-9 * abs(oinfo["nll"]) + 1e-9
