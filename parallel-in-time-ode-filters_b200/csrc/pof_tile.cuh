@@ -66,6 +66,22 @@ struct Team {
 #endif
 };
 
+// init + sum_{k in [lo, hi)} a(k) b(k) with four independent FMA chains (a dependent DFMA issues every ~8 cycles on
+// B200, and a CTA of 8 warps cannot hide that by itself)
+template <class FA, class FB>
+POF_TDEV double tile_dot(int lo, int hi, double init, FA a, FB b) {
+  double s0 = init, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = lo;
+  for (; k + 3 < hi; k += 4) {
+    s0 = fma(a(k), b(k), s0);
+    s1 = fma(a(k + 1), b(k + 1), s1);
+    s2 = fma(a(k + 2), b(k + 2), s2);
+    s3 = fma(a(k + 3), b(k + 3), s3);
+  }
+  for (; k < hi; ++k) s0 = fma(a(k), b(k), s0);
+  return (s0 + s1) + (s2 + s3);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Right-Householder lower-triangularisation of M (R x C, leading dimension ld), pivots 0..npiv-1, LAPACK sign
 // convention (beta = -sign(alpha) norm), Q never formed (replaces the reference's tria(), pof/utils.py:33-41).
@@ -165,11 +181,11 @@ template <class FX>
 POF_TDEV double tile_F_row(const TileModel& md, int r, FX x) {
   double s = 0.0;
   if (md.Fd) {
-    for (int j = 0; j < md.D; ++j) s = fma(md.Fd[r * md.D + j], x(j), s);
+    s = tile_dot(0, md.D, s, [&](int j) { return md.Fd[r * md.D + j]; }, [&](int j) { return x(j); });
     return s;
   }
   const int b = r / md.Q1, i = r - b * md.Q1;
-  for (int j = i; j < md.Q1; ++j) s = fma(md.cf[i * md.Q1 + j], x(b * md.Q1 + j), s);
+  s = tile_dot(i, md.Q1, s, [&](int j) { return md.cf[i * md.Q1 + j]; }, [&](int j) { return x(b * md.Q1 + j); });
   return s;
 }
 POF_TDEV double tile_QL(const TileModel& md, int r, int c) {
@@ -264,7 +280,7 @@ POF_TDEV void tile_update_factor(const Team& t, const TileModel& md, const doubl
     double v = 0.0;
     if (r < d) {
       if (j < D) {
-        for (int i = j; i < D; ++i) v = fma(Hs[r * D + i], T[(long)i * ldT + j], v);
+        v = tile_dot(j, D, v, [&](int i) { return Hs[r * D + i]; }, [&](int i) { return T[(long)i * ldT + j]; });
       } else {
         v = Rs[r * d + (j - D)];
       }
@@ -395,32 +411,32 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
       });
     }
     tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag);
-    // G = SL^{-1} (H A) (d x D) and z = SL^{-1} (H b + c) in column D: one thread per column
+    // G = SL^{-1} (H A) (d x D) and z = SL^{-1} (H b + c) in column D: products, then one thread per column solves
+    t.each(d * (D + 1), [&](int idx) {
+      const int a = idx / (D + 1), j = idx - a * (D + 1);
+      G[a * ldg + j] = (j < D) ? tile_dot(0, D, 0.0, [&](int i) { return Hs[a * D + i]; },
+                                          [&](int i) { return A[i * lda + j]; })
+                               : tile_dot(0, D, v.cs[a], [&](int i) { return Hs[a * D + i]; },
+                                          [&](int i) { return b[i]; });
+    });
     t.each(D + 1, [&](int j) {
       for (int a = 0; a < d; ++a) {
-        double s = (j < D) ? 0.0 : v.cs[a];
-        if (j < D) {
-          for (int i = 0; i < D; ++i) s = fma(Hs[a * D + i], A[i * lda + j], s);
-        } else {
-          for (int i = 0; i < D; ++i) s = fma(Hs[a * D + i], b[i], s);
-        }
-        for (int e = 0; e < a; ++e) s = fma(-X[(long)a * ldx + e], G[e * ldg + j], s);
+        const double s = tile_dot(0, a, G[a * ldg + j], [&](int e) { return -X[(long)a * ldx + e]; },
+                                  [&](int e) { return G[e * ldg + j]; });
         G[a * ldg + j] = s / X[(long)a * ldx + a];
       }
     });
     // A <- A - Kbar G ; b <- b - Kbar z ; eta <- eta - G^T z ; [Z | G^T]
-    t.each(D, [&](int i) {
-      double bi = b[i], ei = eta[i];
-      for (int a = 0; a < d; ++a) {
-        const double kb = X[(long)(d + i) * ldx + a];
-        const double za = G[a * ldg + D];
-        bi = fma(-kb, za, bi);
-        ei = fma(-G[a * ldg + i], za, ei);
-        for (int j = 0; j < D; ++j) A[i * lda + j] = fma(-kb, G[a * ldg + j], A[i * lda + j]);
-        ZG[i * ldz + D + a] = G[a * ldg + i];
+    t.each(D * D, [&](int idx) {
+      const int i = idx / D, j = idx - i * D;
+      A[i * lda + j] = tile_dot(0, d, A[i * lda + j], [&](int a) { return -X[(long)(d + i) * ldx + a]; },
+                                [&](int a) { return G[a * ldg + j]; });
+      if (j < d) ZG[i * ldz + D + j] = G[j * ldg + i];
+      if (j == 0) {
+        b[i] = tile_dot(0, d, b[i], [&](int a) { return -X[(long)(d + i) * ldx + a]; },
+                        [&](int a) { return G[a * ldg + D]; });
+        eta[i] = tile_dot(0, d, eta[i], [&](int a) { return -G[a * ldg + i]; }, [&](int a) { return G[a * ldg + D]; });
       }
-      b[i] = bi;
-      eta[i] = ei;
     });
     tile_tria(t, ZG, D, D + d, ldz, D, D, v.diag);
   }
@@ -486,7 +502,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       double gr = m[r];
       for (int j = D - 1; j >= 0; --j) {
         double s = e[j];
-        for (int i = j + 1; i < D; ++i) s = fma(-e[i], PW[(long)i * ldp + j], s);
+        s = tile_dot(j + 1, D, s, [&](int i) { return -e[i]; }, [&](int i) { return PW[(long)i * ldp + j]; });
         s /= PW[(long)j * ldp + j];
         e[j] = s;
         gr = fma(-s, mp[j], gr);
@@ -514,7 +530,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
     tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag);
     t.each(d, [&](int a) {
       double s = v.cs[a];
-      for (int i = 0; i < D; ++i) s = fma(Hs[a * D + i], mp[i], s);
+      s = tile_dot(0, D, s, [&](int i) { return Hs[a * D + i]; }, [&](int i) { return mp[i]; });
       v.y[a] = s;
     });
     // innovation statistics: nll = -log N(y; 0, SL SL^T) (pof/utils.py:22-30), ssq_ref = |SL^{-T} y|^2 (utils.py:110-112
@@ -523,7 +539,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       double zz = 0.0, lg = 0.0, ww = 0.0;
       for (int a = 0; a < d; ++a) {
         double s = v.y[a];
-        for (int e = 0; e < a; ++e) s = fma(-X[(long)a * ldx + e], v.z[e], s);
+        s = tile_dot(0, a, s, [&](int e) { return -X[(long)a * ldx + e]; }, [&](int e) { return v.z[e]; });
         s /= X[(long)a * ldx + a];
         v.z[a] = s;
         zz = fma(s, s, zz);
@@ -531,7 +547,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       }
       for (int a = d - 1; a >= 0; --a) {
         double s = v.y[a];
-        for (int e = a + 1; e < d; ++e) s = fma(-X[(long)e * ldx + a], v.w[e], s);
+        s = tile_dot(a + 1, d, s, [&](int e) { return -X[(long)e * ldx + a]; }, [&](int e) { return v.w[e]; });
         s /= X[(long)a * ldx + a];
         v.w[a] = s;
         ww = fma(s, s, ww);
@@ -542,7 +558,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
     });
     t.each(D, [&](int i) {
       double s = mp[i];
-      for (int a = 0; a < d; ++a) s = fma(-X[(long)(d + i) * ldx + a], v.z[a], s);
+      s = tile_dot(0, d, s, [&](int a) { return -X[(long)(d + i) * ldx + a]; }, [&](int a) { return v.z[a]; });
       m[i] = s;
     });
     if (fmeans) {
@@ -627,12 +643,12 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
       if (idx < DD) {
         const int a = idx / D, j = idx - a * D;
         double s = 0.0;
-        for (int i = j; i < D; ++i) s = fma(Es[a * lde + i], Ls[i * lde + j], s);
+        s = tile_dot(j, D, s, [&](int i) { return Es[a * lde + i]; }, [&](int i) { return Ls[i * lde + j]; });
         SW[a * lds + D + j] = s;
       } else {
         const int a = idx - DD;
         double s = kp[a];
-        for (int i = 0; i < D; ++i) s = fma(Es[a * lde + i], m[i], s);
+        s = tile_dot(0, D, s, [&](int i) { return Es[a * lde + i]; }, [&](int i) { return m[i]; });
         mn[a] = s;
       }
     });
@@ -645,7 +661,7 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
         if (b == 0) {
           for (int i = 0; i < D; ++i) {
             double s = mn[i] - fm[i];
-            for (int j = 0; j < i; ++j) s = fma(-md.Qd[i * D + j], rs[j], s);
+            s = tile_dot(0, i, s, [&](int j) { return -md.Qd[i * D + j]; }, [&](int j) { return rs[j]; });
             s /= md.Qd[i * D + i];
             rs[i] = s;
             o = fma(s, s, o);
@@ -654,7 +670,7 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
       } else {
         for (int i = 0; i < Q1; ++i) {
           double s = mn[b * Q1 + i] - fm[b * Q1 + i];
-          for (int j = 0; j < i; ++j) s = fma(-md.ql[i * Q1 + j], rs[b * Q1 + j], s);
+          s = tile_dot(0, i, s, [&](int j) { return -md.ql[i * Q1 + j]; }, [&](int j) { return rs[b * Q1 + j]; });
           s /= md.ql[i * Q1 + i];
           rs[b * Q1 + i] = s;
           o = fma(s, s, o);
@@ -736,7 +752,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
     double v = 0.0;
-    for (int k = 0; k < D; ++k) v = fma(U1[k * D + r], Z2[k * D + c], v);
+    v = tile_dot(0, D, v, [&](int k) { return U1[k * D + r]; }, [&](int k) { return Z2[k * D + c]; });
     Xi[r * ldx + c] = v;
     Xi[r * ldx + D + c] = (r == c) ? 1.0 : 0.0;
     Xi[(D + r) * ldx + c] = Z2[idx];
@@ -748,7 +764,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
   t.each(D, [&](int r) {
     for (int j = 0; j < D; ++j) {
       double acc = U1[r * D + j];
-      for (int i = 0; i < j; ++i) acc = fma(-Y[r * ldx + i], Xi[j * ldx + i], acc);
+      acc = tile_dot(0, j, acc, [&](int i) { return -Y[r * ldx + i]; }, [&](int i) { return Xi[j * ldx + i]; });
       Y[r * ldx + j] = acc / Xi[j * ldx + j];
     }
   });
@@ -758,17 +774,17 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
     if (idx < DD) {
       const int r = idx / D, c = idx - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(Y[r * ldx + k], Xi[(D + c) * ldx + k], v);
+      v = tile_dot(0, D, v, [&](int k) { return Y[r * ldx + k]; }, [&](int k) { return Xi[(D + c) * ldx + k]; });
       G[r * ldx + c] = ((r == c) ? 1.0 : 0.0) - v;
     } else if (idx < DD + D) {
       const int i = idx - DD;
       double acc = 0.0;
-      for (int k = 0; k < D; ++k) acc = fma(U1[k * D + i], n2[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return U1[k * D + i]; }, [&](int k) { return n2[k]; });
       s.t1[i] = acc;
     } else {
       const int i = idx - DD - D;
       double acc = 0.0;
-      for (int k = 0; k < D; ++k) acc = fma(Z2[k * D + i], b1[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return Z2[k * D + i]; }, [&](int k) { return b1[k]; });
       s.t3[i] = acc;
     }
   });
@@ -776,12 +792,12 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
   t.each(2 * D, [&](int idx) {
     if (idx < D) {
       double acc = b1[idx];
-      for (int k = 0; k < D; ++k) acc = fma(U1[idx * D + k], s.t1[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return U1[idx * D + k]; }, [&](int k) { return s.t1[k]; });
       s.t0[idx] = acc;
     } else {
       const int i = idx - D;
       double acc = n2[i];
-      for (int k = 0; k < D; ++k) acc = fma(-Z2[i * D + k], s.t3[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return -Z2[i * D + k]; }, [&](int k) { return s.t3[k]; });
       s.t2[i] = acc;
     }
   });
@@ -791,19 +807,19 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
     if (idx0 < 2 * D) {
       if (idx0 < D) {
         double acc = 0.0;
-        for (int k = 0; k < D; ++k) acc = fma(G[idx0 * ldx + k], s.t0[k], acc);
+        acc = tile_dot(0, D, acc, [&](int k) { return G[idx0 * ldx + k]; }, [&](int k) { return s.t0[k]; });
         s.t1[idx0] = acc;
       } else {
         const int i = idx0 - D;
         double acc = 0.0;
-        for (int k = 0; k < D; ++k) acc = fma(G[k * ldx + i], s.t2[k], acc);
+        acc = tile_dot(0, D, acc, [&](int k) { return G[k * ldx + i]; }, [&](int k) { return s.t2[k]; });
         s.t3[i] = acc;
       }
     } else {
       const int idx = idx0 - 2 * D;
       const int r = idx / D, c = idx - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(G[r * ldx + k], A1[k * D + c], v);
+      v = tile_dot(0, D, v, [&](int k) { return G[r * ldx + k]; }, [&](int k) { return A1[k * D + c]; });
       P[r * ldx + c] = v;
     }
   });
@@ -812,18 +828,18 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
   t.each((state_mode ? 0 : DD + D) + D, [&](int idx0) {
     if (idx0 < D) {
       double acc = b2[idx0];
-      for (int k = 0; k < D; ++k) acc = fma(A2[idx0 * D + k], s.t1[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return A2[idx0 * D + k]; }, [&](int k) { return s.t1[k]; });
       ob[idx0] = acc;
     } else if (idx0 < 2 * D) {
       const int i = idx0 - D;
       double acc = n1[i];
-      for (int k = 0; k < D; ++k) acc = fma(A1[k * D + i], s.t3[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return A1[k * D + i]; }, [&](int k) { return s.t3[k]; });
       out[2 * DD + D + i] = acc;
     } else {
       const int idx = idx0 - 2 * D;
       const int r = idx / D, c = idx - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(A2[r * D + k], P[k * ldx + c], v);
+      v = tile_dot(0, D, v, [&](int k) { return A2[r * D + k]; }, [&](int k) { return P[k * ldx + c]; });
       out[idx] = v;
     }
   });
@@ -831,7 +847,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
     double v = 0.0;
-    for (int k = 0; k < D; ++k) v = fma(A2[r * D + k], Y[k * ldx + c], v);
+    v = tile_dot(0, D, v, [&](int k) { return A2[r * D + k]; }, [&](int k) { return Y[k * ldx + c]; });
     W[r * ldx + c] = v;
     W[r * ldx + D + c] = U2[idx];
   });
@@ -846,7 +862,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
     double v = 0.0;
-    for (int k = c; k < D; ++k) v = fma(A1[k * D + r], Xi[(D + k) * ldx + D + c], v);
+    v = tile_dot(c, D, v, [&](int k) { return A1[k * D + r]; }, [&](int k) { return Xi[(D + k) * ldx + D + c]; });
     W[r * ldx + c] = v;
     W[r * ldx + D + c] = Z1[idx];
   });
@@ -875,19 +891,19 @@ POF_TDEV void tile_smooth_combine(const Team& t, int D, const double* e1, const 
     if (idx0 < DD) {
       const int r = idx0 / D, c = idx0 - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(E2[r * D + k], D1[k * D + c], v);
+      v = tile_dot(0, D, v, [&](int k) { return E2[r * D + k]; }, [&](int k) { return D1[k * D + c]; });
       W[r * ldx + c] = v;
       W[r * ldx + D + c] = D2[idx0];
     } else if (idx0 < DD + D) {
       const int i = idx0 - DD;
       double acc = g2[i];
-      for (int k = 0; k < D; ++k) acc = fma(E2[i * D + k], g1[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return E2[i * D + k]; }, [&](int k) { return g1[k]; });
       out[i] = acc;
     } else {
       const int idx = idx0 - DD - D;
       const int r = idx / D, c = idx - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(E2[r * D + k], E1[k * D + c], v);
+      v = tile_dot(0, D, v, [&](int k) { return E2[r * D + k]; }, [&](int k) { return E1[k * D + c]; });
       out[D + idx] = v;
     }
   });
@@ -920,7 +936,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
     if (idx < DD) {
       const int r = idx / D, c = idx - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(L1[k * D + r], Z2[k * D + c], v);
+      v = tile_dot(0, D, v, [&](int k) { return L1[k * D + r]; }, [&](int k) { return Z2[k * D + c]; });
       Xi[r * ldx + c] = v;
       Xi[r * ldx + D + c] = (r == c) ? 1.0 : 0.0;
       Xi[(D + r) * ldx + c] = Z2[idx];
@@ -928,7 +944,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
     } else {
       const int i = idx - DD;
       double acc = 0.0;
-      for (int k = 0; k < D; ++k) acc = fma(L1[k * D + i], n2[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return L1[k * D + i]; }, [&](int k) { return n2[k]; });
       s.t1[i] = acc;  // L^T eta
     }
   });
@@ -940,13 +956,13 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
       const int r = idx;
       for (int j = 0; j < D; ++j) {
         double acc = L1[r * D + j];
-        for (int i = 0; i < j; ++i) acc = fma(-Y[r * ldx + i], Xi[j * ldx + i], acc);
+        acc = tile_dot(0, j, acc, [&](int i) { return -Y[r * ldx + i]; }, [&](int i) { return Xi[j * ldx + i]; });
         Y[r * ldx + j] = acc / Xi[j * ldx + j];
       }
     } else {
       const int i = idx - D;
       double acc = m1[i];
-      for (int k = 0; k < D; ++k) acc = fma(L1[i * D + k], s.t1[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return L1[i * D + k]; }, [&](int k) { return s.t1[k]; });
       s.t0[i] = acc;
     }
   });
@@ -955,13 +971,13 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
     double v = 0.0;
-    for (int k = 0; k < D; ++k) v = fma(Y[r * ldx + k], Xi[(D + c) * ldx + k], v);
+    v = tile_dot(0, D, v, [&](int k) { return Y[r * ldx + k]; }, [&](int k) { return Xi[(D + c) * ldx + k]; });
     G[r * ldx + c] = ((r == c) ? 1.0 : 0.0) - v;
   });
   // m' = G t0 -> t2
   t.each(D, [&](int i) {
     double acc = 0.0;
-    for (int k = 0; k < D; ++k) acc = fma(G[i * ldx + k], s.t0[k], acc);
+    acc = tile_dot(0, D, acc, [&](int k) { return G[i * ldx + k]; }, [&](int k) { return s.t0[k]; });
     s.t2[i] = acc;
   });
   // v = A m' + b -> t3 ;  Phi = [[A Y, U],[Y, 0]] overwrites Xi (dead now)
@@ -969,7 +985,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
     if (idx < DD) {
       const int r = idx / D, c = idx - r * D;
       double v = 0.0;
-      for (int k = 0; k < D; ++k) v = fma(A2[r * D + k], Y[k * ldx + c], v);
+      v = tile_dot(0, D, v, [&](int k) { return A2[r * D + k]; }, [&](int k) { return Y[k * ldx + c]; });
       Xi[r * ldx + c] = v;
       Xi[r * ldx + D + c] = U2[idx];
       Xi[(D + r) * ldx + c] = Y[r * ldx + c];
@@ -977,7 +993,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
     } else {
       const int i = idx - DD;
       double acc = b2[i];
-      for (int k = 0; k < D; ++k) acc = fma(A2[i * D + k], s.t2[k], acc);
+      acc = tile_dot(0, D, acc, [&](int k) { return A2[i * D + k]; }, [&](int k) { return s.t2[k]; });
       s.t3[i] = acc;
     }
   });
@@ -988,7 +1004,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
     double gr = s.t2[r];
     for (int j = D - 1; j >= 0; --j) {
       double acc = e[j];
-      for (int i = j + 1; i < D; ++i) acc = fma(-e[i], Xi[(long)i * ldx + j], acc);
+      acc = tile_dot(j + 1, D, acc, [&](int i) { return -e[i]; }, [&](int i) { return Xi[(long)i * ldx + j]; });
       acc /= Xi[(long)j * ldx + j];
       e[j] = acc;
       gr = fma(-acc, s.t3[j], gr);
