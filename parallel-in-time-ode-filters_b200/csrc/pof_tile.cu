@@ -23,7 +23,7 @@ static __device__ __forceinline__ TileLin make_lin(const LeafArgs& a) {
   return lin;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_fold(LeafArgs a, double* __restrict__ fagg, double* __restrict__ faggm) {
   extern __shared__ __align__(16) double sm[];
   const long ch = blockIdx.x;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   tile_fold(t, a.d, a.q, a.ql.v, make_lin(a), k0, k1, fagg + ch * FE, faggm ? faggm + ch * FE : nullptr, sm);
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_scan(LeafArgs a, const double* __restrict__ fin, double* __restrict__ kern, double* __restrict__ send,
                 double* __restrict__ part, double* __restrict__ fmeans, double* __restrict__ fchols) {
   extern __shared__ __align__(16) double sm[];
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
             fchols, sm);
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_smooth(LeafArgs a, const double* __restrict__ sin, const double* __restrict__ kern, int emit_t0,
                   const double* __restrict__ cscale, double* __restrict__ means, double* __restrict__ chols,
                   double* __restrict__ part2) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
 }
 
 // sequential EKS: ONE CTA walks the whole grid (inherently sequential baseline path of the reference)
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_seq_eks(LeafArgs a, TileEks eks, const double* __restrict__ x0, double* __restrict__ kern,
                    double* __restrict__ state_end, double* __restrict__ means, double* __restrict__ chols,
                    double* __restrict__ sums) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
 
 // ------------------------------------------------------------------------------------------------ tree sweeps
 // same node conventions as the warp kernels in pof_api.cu (k_filter_up, ...), one CTA per parent node
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_fup(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent) {
   extern __shared__ __align__(16) double sm[];
   const long i = blockIdx.x;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   else
     t.each((int)FE, [&](int j) { out[j] = lc[j]; });
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_fdown(int D, const double* __restrict__ pin, const double* __restrict__ cagg, long nchild,
                  double* __restrict__ cin) {
   extern __shared__ __align__(16) double sm[];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   t.each((int)ST, [&](int j) { c0[j] = p[j]; });
   if (2 * i + 1 < nchild) tile_filter_combine(t, D, p, cagg + 2 * i * FE, cin + (2 * i + 1) * ST, sm, true);
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_sup(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent) {
   extern __shared__ __align__(16) double sm[];
   const long i = blockIdx.x;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   else
     t.each((int)SE, [&](int j) { out[j] = lc[j]; });
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_sdown(int D, const double* __restrict__ pin, const double* __restrict__ cagg, long nchild,
                  double* __restrict__ cin) {
   extern __shared__ __align__(16) double sm[];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
     t.each((int)ST, [&](int j) { c0[j] = p[j]; });
   }
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_chunkk(int D, const double* __restrict__ fin, const double* __restrict__ faggm, double* __restrict__ sagg) {
   extern __shared__ __align__(16) double sm[];
   const long i = blockIdx.x;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   Team t;
   tile_chunk_kernel(t, D, fin + i * ST, faggm + i * FE, sagg + i * SE, sm);
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_fcomb(int D, const double* __restrict__ e1, const double* __restrict__ e2, double* __restrict__ out) {
   extern __shared__ __align__(16) double sm[];
   const long i = blockIdx.x;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   Team t;
   tile_filter_combine(t, D, e1 + i * FE, e2 + i * FE, out + i * FE, sm, false);
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_scomb(int D, const double* __restrict__ e1, const double* __restrict__ e2, double* __restrict__ out) {
   extern __shared__ __align__(16) double sm[];
   const long i = blockIdx.x;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   tile_smooth_combine(t, D, e1 + i * SE, e2 + i * SE, out + i * SE, sm, false);
 }
 // sequential chains over a handful of rank carries (one CTA); ping-pong so that the last write lands in state_out
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_fchain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
                   double* __restrict__ state_out, double* __restrict__ scratch) {
   extern __shared__ __align__(16) double sm[];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(TILE_THREADS)
   }
   if (count == 0) t.each((int)ST, [&](int j) { state_out[j] = state_in[j]; });
 }
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
     k_tile_schain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
                   double* __restrict__ state_out, double* __restrict__ scratch) {
   extern __shared__ __align__(16) double sm[];

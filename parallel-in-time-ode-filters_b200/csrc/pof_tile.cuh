@@ -22,6 +22,8 @@
 // Observation noise: `R` (the reference's cholR, observations.py:23-33) may be non-zero here -- the posterior factor
 // then has D instead of D-d non-zero columns; R == nullptr is the noiseless ODE-solver case (step.py:12-22).
 #pragma once
+#include <vector>
+
 #include "pof_ivp.cuh"
 #include "pof_small.cuh"
 
@@ -29,8 +31,11 @@ namespace pof {
 
 #if defined(__CUDACC__)
 #define POF_TDEV __host__ __device__ __forceinline__
+// the Householder sweeps are called from many places and are large once unrolled: real functions, compiled once
+#define POF_TFUNC __host__ __device__ __noinline__
 #else
 #define POF_TDEV inline
+#define POF_TFUNC inline
 #endif
 
 struct Team {
@@ -42,7 +47,9 @@ struct Team {
     for (int i = tid; i < n; i += nt) f(i);
     __syncthreads();
   }
+  __device__ __forceinline__ int threads() const { return nt; }
 #else
+  int threads() const { return 1 << 20; }
   // host simulator: one "thread" runs all iterations; the order is selectable to expose cross-iteration dependences
   static int& order() {
     static int o = 0;
@@ -93,7 +100,7 @@ POF_TDEV double tile_dot(int lo, int hi, double init, FA a, FB b) {
 // thread 0 only records beta.  The diagonal is written back at the end; the eliminated entries of the pivot rows
 // keep stale values (never referenced afterwards: only the lower triangle / the non-pivot rows are meaningful).
 // ---------------------------------------------------------------------------------------------------------------
-POF_TDEV void tile_tria(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag) {
+POF_TFUNC void tile_tria_smem(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag) {
   for (int i = 0; i < npiv; ++i) {
     const int js = c0 >= 0 ? c0 : i + 1;
     t.each(R - i, [&](int rr) {
@@ -135,6 +142,136 @@ POF_TDEV void tile_tria(const Team& t, double* M, int R, int C, int ld, int npiv
     });
   }
   t.each(npiv, [&](int i) { M[(long)i * ld + i] = diag[i]; });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same triangularisation with the rows held in REGISTERS for the whole sweep (the shared-memory version re-reads
+// and re-writes the trailing matrix for every pivot: 8 shared-memory wavefronts per column and pivot; here a pivot
+// costs one broadcast read of the pivot row per column).  Thread r owns row r for all pivots: `regs.at(r)` is the
+// thread's register file on the device (iteration r of every each() below runs on thread r because R <= #threads) and
+// a per-iteration array in the host simulator.  KT >= C - cb columns per row (cb = c0 in pentagonal mode, else 0) are
+// kept, zero-padded, all loops fully unrolled so that nothing is indexed dynamically.  The pivot row travels through a
+// double-buffered broadcast array pb (2 x KT doubles of shared memory): the owner of row i+1 publishes it at the end of
+// pivot i, so there is still ONE barrier per pivot.
+// ---------------------------------------------------------------------------------------------------------------
+template <int KT>
+struct RowRegs {
+#if defined(__CUDA_ARCH__)
+  double v[KT];
+  __device__ __forceinline__ explicit RowRegs(int) {}
+  __device__ __forceinline__ double* at(int) { return v; }
+#else
+  std::vector<double> store;
+  explicit RowRegs(int rows) : store((size_t)rows * KT) {}
+  double* at(int i) { return &store[(size_t)i * KT]; }
+#endif
+};
+
+// PENTA: the pivot column i lives in shared memory (left, already triangular block), the registers hold columns
+// [c0, C).  Plain (!PENTA): the registers hold columns [i, C) of the CURRENT pivot i -- after every pivot the finished
+// column i is written to shared memory and the register file shifts left by one (compile-time indices only: a
+// `rv[i]` with a runtime i would send the whole array to local memory).
+template <int KT, bool PENTA>
+POF_TFUNC void tile_tria_reg(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag,
+                            double* pb) {
+  const int cb = PENTA ? c0 : 0;
+  const int K = C - cb;
+  RowRegs<KT> regs(R);
+  t.each(R, [&](int r) {
+    double* rv = regs.at(r);
+    const double* row = M + (long)r * ld + cb;
+    POF_UNROLL_N(KT)
+    for (int j = 0; j < KT; ++j) rv[j] = (j < K) ? row[j] : 0.0;
+    if (r == 0) {
+      POF_UNROLL_N(KT)
+      for (int j = 0; j < KT; ++j) pb[j] = rv[j];
+    }
+  });
+  for (int i = 0; i < npiv; ++i) {
+    const double* p = pb + (i & 1) * KT;
+    double* pn = pb + ((i + 1) & 1) * KT;
+    // all R iterations, not R - i: iteration r must stay on thread r, whose registers hold row r (regs.at takes the
+    // iteration index of the enclosing each(), never a derived row number)
+    t.each(R, [&](int r) {
+      if (r < i) return;
+      double* rv = regs.at(r);
+      constexpr int J0 = PENTA ? 0 : 1;  // first register column of the part to eliminate (columns >= K hold zeros)
+      double s[4] = {0.0, 0.0, 0.0, 0.0}, dt[4] = {0.0, 0.0, 0.0, 0.0};
+      POF_UNROLL_N(KT)
+      for (int j = J0; j < KT; ++j) {
+        const double pj = p[j];
+        s[j & 3] = fma(pj, pj, s[j & 3]);
+        dt[j & 3] = fma(rv[j], pj, dt[j & 3]);
+      }
+      const double alpha = PENTA ? M[(long)i * ld + i] : p[0];
+      const double rowi = PENTA ? M[(long)r * ld + i] : rv[0];
+      const double sigma = (s[0] + s[1]) + (s[2] + s[3]);
+      double newi = rowi;
+      if (sigma > 0.0) {
+        const double nrm = sqrt(fma(alpha, alpha, sigma));
+        const double beta = (alpha >= 0.0) ? -nrm : nrm;
+        if (r == i) {
+          diag[i] = beta;
+        } else {
+          const double tau = (beta - alpha) / beta;
+          const double scale = 1.0 / (alpha - beta);
+          const double w = tau * fma(scale, (dt[0] + dt[1]) + (dt[2] + dt[3]), rowi);
+          const double ws = w * scale;
+          newi = rowi - w;
+          POF_UNROLL_N(KT)
+          for (int j = J0; j < KT; ++j) rv[j] = fma(-ws, p[j], rv[j]);
+        }
+      } else if (r == i) {  // nothing to eliminate: identity (also keeps all-zero rows free of NaN)
+        diag[i] = alpha;
+      }
+      if (r > i) M[(long)r * ld + i] = newi;  // column i is final now
+      if (!PENTA) {  // shift: register column 0 becomes column i + 1
+        POF_UNROLL_N(KT)
+        for (int j = 0; j + 1 < KT; ++j) rv[j] = rv[j + 1];
+        rv[KT - 1] = 0.0;
+      }
+      if (r == i + 1) {  // publish the next pivot row
+        POF_UNROLL_N(KT)
+        for (int j = 0; j < KT; ++j) pn[j] = rv[j];
+      }
+    });
+  }
+  // columns right of the pivots: only the non-pivot rows carry meaningful values there
+  const int cs = PENTA ? cb : npiv;
+  t.each(R, [&](int r) {
+    if (r < npiv) return;
+    const double* rv = regs.at(r);
+    double* row = M + (long)r * ld + cs;
+    POF_UNROLL_N(KT)
+    for (int j = 0; j < KT; ++j)
+      if (cs + j < C) row[j] = rv[j];
+  });
+  t.each(npiv, [&](int i) { M[(long)i * ld + i] = diag[i]; });
+}
+
+// pb: 2 x TILE_PB_COLS doubles of shared memory for the register version (used when the row span fits)
+constexpr int TILE_PB_COLS = 64;
+POF_TDEV void tile_tria(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag, double* pb) {
+  const int K = C - (c0 >= 0 ? c0 : 0);
+  if (pb != nullptr && R <= t.threads() && K <= TILE_PB_COLS) {
+    if (c0 >= 0) {
+      if (K <= 16)
+        tile_tria_reg<16, true>(t, M, R, C, ld, npiv, c0, diag, pb);
+      else if (K <= 32)
+        tile_tria_reg<32, true>(t, M, R, C, ld, npiv, c0, diag, pb);
+      else
+        tile_tria_reg<64, true>(t, M, R, C, ld, npiv, c0, diag, pb);
+    } else {
+      if (K <= 16)
+        tile_tria_reg<16, false>(t, M, R, C, ld, npiv, c0, diag, pb);
+      else if (K <= 32)
+        tile_tria_reg<32, false>(t, M, R, C, ld, npiv, c0, diag, pb);
+      else
+        tile_tria_reg<64, false>(t, M, R, C, ld, npiv, c0, diag, pb);
+    }
+  } else {
+    tile_tria_smem(t, M, R, C, ld, npiv, c0, diag);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -273,7 +410,7 @@ POF_TDEV void tile_stage_lin(const Team& t, const TileModel& md, const TileLin& 
 // Uf = X[d:, d:d+D] (its last d columns are zero when R == 0).
 // ---------------------------------------------------------------------------------------------------------------
 POF_TDEV void tile_update_factor(const Team& t, const TileModel& md, const double* T, int ldT, const double* Hs,
-                                 const double* Rs, bool noisy, double* X, double* diag) {
+                                 const double* Rs, bool noisy, double* X, double* diag, double* pb) {
   const int d = md.d, D = md.D, ldx = D + d + 1, W = D + d;
   t.each((d + D) * W, [&](int idx) {
     const int r = idx / W, j = idx - r * W;
@@ -289,13 +426,13 @@ POF_TDEV void tile_update_factor(const Team& t, const TileModel& md, const doubl
     }
     X[(long)r * ldx + j] = v;
   });
-  tile_tria(t, X, d + D, noisy ? W : D, ldx, d, -1, diag);
+  tile_tria(t, X, d + D, noisy ? W : D, ldx, d, -1, diag, pb);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory layouts (in doubles) of the three leaf kernels
 // ---------------------------------------------------------------------------------------------------------------
-POF_TDEV int tile_vec_doubles(int D, int d) { return 8 * D + 4 * d + d * d + 16; }
+POF_TDEV int tile_vec_doubles(int D, int d) { return 8 * D + 4 * d + d * d + 16 + 2 * TILE_PB_COLS; }
 POF_TDEV int tile_fold_smem_doubles(int D, int d) {
   return TILE_MODEL_DOUBLES + D * (2 * D + 1) + (D + d) * (D + d + 1) + D * (D + 1) + D * (D + d + 1) +
          d * (D + 1) + d * D + tile_vec_doubles(D, d);
@@ -306,7 +443,9 @@ POF_TDEV int tile_scan_smem_doubles(int D, int d) {
 POF_TDEV int tile_smooth_smem_doubles(int D, int d) {
   return TILE_MODEL_DOUBLES + D * (2 * D + 1) + 2 * D * (D + 1) + tile_vec_doubles(D, d);
 }
-POF_TDEV int tile_tree_smem_doubles(int D) { return 2 * D * (2 * D + 1) + D * (2 * D + 1) + 10 * D + 16; }
+POF_TDEV int tile_tree_smem_doubles(int D) {
+  return 2 * D * (2 * D + 1) + D * (2 * D + 1) + 10 * D + 16 + 2 * TILE_PB_COLS;
+}
 
 // small vectors common to the leaf kernels
 struct TileVecs {
@@ -315,6 +454,7 @@ struct TileVecs {
   double *cs, *y, *z, *w;     // d each
   double *Rs;                 // d x d
   double *acc;                // 16 scalars
+  double *pb;                 // 2 x TILE_PB_COLS: pivot-row broadcast buffers of tile_tria_reg
   POF_TDEV void init(double* base, int D, int d) {
     v0 = base;
     v1 = v0 + D;
@@ -327,6 +467,7 @@ struct TileVecs {
     w = z + d;
     Rs = w + d;
     acc = Rs + d * d;
+    pb = acc + 16;
   }
 };
 
@@ -397,7 +538,7 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
       PW[r * ldp + c] = tile_QL(md, r, c);
       PW[r * ldp + D + c] = tile_F_row(md, r, [&](int j) { return X[(long)(d + j) * ldx + d + c]; });
     });
-    tile_tria(t, PW, D, 2 * D, ldp, D, D, v.diag);
+    tile_tria(t, PW, D, 2 * D, ldp, D, D, v.diag, v.pb);
     if (aggm && k == k1 - 1) {
       t.each(D * D, [&](int idx) {
         const int r = idx / D, c = idx - r * D;
@@ -410,7 +551,7 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
         }
       });
     }
-    tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag);
+    tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag, v.pb);
     // G = SL^{-1} (H A) (d x D) and z = SL^{-1} (H b + c) in column D: products, then one thread per column solves
     t.each(d * (D + 1), [&](int idx) {
       const int a = idx / (D + 1), j = idx - a * (D + 1);
@@ -438,7 +579,7 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
         eta[i] = tile_dot(0, d, eta[i], [&](int a) { return -G[a * ldg + i]; }, [&](int a) { return G[a * ldg + D]; });
       }
     });
-    tile_tria(t, ZG, D, D + d, ldz, D, D, v.diag);
+    tile_tria(t, ZG, D, D + d, ldz, D, D, v.diag, v.pb);
   }
   t.each(D * D, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
@@ -495,7 +636,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       if (c == 0) mp[r] = tile_F_row(md, r, [&](int j) { return m[j]; });
     });
     if (eks) tile_stage_lin_eks(t, md, *eks, lin.s0, lin.s1, mp, Hs, v.cs, v.Rs);
-    tile_tria(t, PW, 2 * D, 2 * D, ldp, D, D, v.diag);
+    tile_tria(t, PW, 2 * D, 2 * D, ldp, D, D, v.diag, v.pb);
     // E = Phi21 T^{-1} (row-wise back substitution, in place), then g = m - E (F m)
     t.each(D, [&](int r) {
       double* e = PW + (long)(D + r) * ldp;
@@ -510,7 +651,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       g[r] = gr;
     });
     // Dk = tria(Phi22~)
-    tile_tria(t, PW + (long)D * ldp + D, D, D, ldp, D, -1, v.diag);
+    tile_tria(t, PW + (long)D * ldp + D, D, D, ldp, D, -1, v.diag, v.pb);
     {
       double* kp = kern + k * NE;
       t.each(NE, [&](int idx) {
@@ -527,7 +668,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
         kp[idx] = val;
       });
     }
-    tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag);
+    tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag, v.pb);
     t.each(d, [&](int a) {
       double s = v.cs[a];
       s = tile_dot(0, D, s, [&](int i) { return Hs[a * D + i]; }, [&](int i) { return mp[i]; });
@@ -570,7 +711,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
     }
   }
   // the end state goes to the smoother tree as (m, L) with L lower triangular
-  tile_tria(t, X + (long)d * ldx + d, D, D, ldx, D, -1, v.diag);
+  tile_tria(t, X + (long)d * ldx + d, D, D, ldx, D, -1, v.diag, v.pb);
   t.each(D * D, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
     state_end[D + idx] = (c <= r) ? X[(long)(d + r) * ldx + d + c] : 0.0;
@@ -652,7 +793,7 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
         mn[a] = s;
       }
     });
-    tile_tria(t, SW, D, 2 * D, lds, D, D, v.diag);
+    tile_tria(t, SW, D, 2 * D, lds, D, D, v.diag, v.pb);
     // objective increment |QL^{-1}(m_k - F m_{k+1})|^2 (reference's swapped-argument form, smoother.py:20): one thread
     // per block of the block-diagonal QL; new state
     t.each(d, [&](int b) {
@@ -716,7 +857,7 @@ POF_TDEV void tile_seq_eks(const Team& t, int d, int q, const double* ql_param, 
 //   eta = A1^T G^T (eta2 - Z2 Z2^T b1) + eta1                                                   Z = tria([A1^T Xi22, Z1])
 // ---------------------------------------------------------------------------------------------------------------
 struct TileTreeWs {
-  double *Xi, *W, *t0, *t1, *t2, *t3, *diag;
+  double *Xi, *W, *t0, *t1, *t2, *t3, *diag, *pb;
   int ldx;
   POF_TDEV TileTreeWs(double* smem, int D) {
     ldx = 2 * D + 1;
@@ -727,6 +868,7 @@ struct TileTreeWs {
     t2 = t1 + D;
     t3 = t2 + D;
     diag = t3 + D;
+    pb = diag + 6 * D + 16;
   }
 };
 
@@ -758,7 +900,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
     Xi[(D + r) * ldx + c] = Z2[idx];
     Xi[(D + r) * ldx + D + c] = 0.0;
   });
-  tile_tria(t, Xi, 2 * D, 2 * D, ldx, state_mode ? D : 2 * D, -1, s.diag);
+  tile_tria(t, Xi, 2 * D, 2 * D, ldx, state_mode ? D : 2 * D, -1, s.diag, s.pb);
   // Y = U1 Xi11^{-T} (row r solves y Xi11^T = u_r), kept in the dead upper-right block of Xi
   double* Y = Xi + D;  // Y(r, j) = Y[r * ldx + j]
   t.each(D, [&](int r) {
@@ -851,7 +993,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
     W[r * ldx + c] = v;
     W[r * ldx + D + c] = U2[idx];
   });
-  tile_tria(t, W, D, 2 * D, ldx, D, -1, s.diag);
+  tile_tria(t, W, D, 2 * D, ldx, D, -1, s.diag, s.pb);
   double* oU = state_mode ? out + D : out + DD + D;
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
@@ -866,7 +1008,7 @@ POF_TDEV void tile_filter_combine(const Team& t, int D, const double* e1, const 
     W[r * ldx + c] = v;
     W[r * ldx + D + c] = Z1[idx];
   });
-  tile_tria(t, W, D, 2 * D, ldx, D, -1, s.diag);
+  tile_tria(t, W, D, 2 * D, ldx, D, -1, s.diag, s.pb);
   double* oZ = out + 2 * DD + 2 * D;
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
@@ -907,7 +1049,7 @@ POF_TDEV void tile_smooth_combine(const Team& t, int D, const double* e1, const 
       out[D + idx] = v;
     }
   });
-  tile_tria(t, W, D, 2 * D, ldx, D, -1, s.diag);
+  tile_tria(t, W, D, 2 * D, ldx, D, -1, s.diag, s.pb);
   double* oD = state_mode ? out + D : out + D + DD;
   t.each(DD, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
@@ -948,7 +1090,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
       s.t1[i] = acc;  // L^T eta
     }
   });
-  tile_tria(t, Xi, 2 * D, 2 * D, ldx, D, -1, s.diag);
+  tile_tria(t, Xi, 2 * D, 2 * D, ldx, D, -1, s.diag, s.pb);
   // Y = L Xi11^{-T} in W[:, 0:D];  t0 = m + L t1
   double* Y = W;
   t.each(2 * D, [&](int idx) {
@@ -997,7 +1139,7 @@ POF_TDEV void tile_chunk_kernel(const Team& t, int D, const double* st, const do
       s.t3[i] = acc;
     }
   });
-  tile_tria(t, Xi, 2 * D, 2 * D, ldx, 2 * D, -1, s.diag);
+  tile_tria(t, Xi, 2 * D, 2 * D, ldx, 2 * D, -1, s.diag, s.pb);
   // E = Phi21 Phi11^{-1} (row-wise back substitution, in place); g = m' - E v; outputs
   t.each(D, [&](int r) {
     double* e = Xi + (long)(D + r) * ldx;
