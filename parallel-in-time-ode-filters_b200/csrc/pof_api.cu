@@ -515,6 +515,10 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   a.R = nullptr;
   a.F = nullptr;
   a.QLd = nullptr;
+  {
+    const char* e = getenv("POF_B200_TILE_SWEEP");
+    a.tile_reg = (e && e[0] == 'r') ? 1 : 0;
+  }
   a.d = d;
   a.q = q;
   a.s0 = a.s1 = 0.0;

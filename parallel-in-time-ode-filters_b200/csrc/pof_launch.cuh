@@ -59,6 +59,7 @@ struct LeafArgs {
   const double* R;   // observation-noise factors cholR (n,d,d), or null = noiseless (tile family only)
   const double* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
   const double* QLd; // preconditioned IWP described by ql (tile family only)
+  int tile_reg;      // tile family: register-resident Householder sweeps (POF_B200_TILE_SWEEP=reg), default shared memory
 };
 
 struct LeafLaunch {

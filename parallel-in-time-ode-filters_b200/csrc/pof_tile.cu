@@ -20,6 +20,7 @@ static __device__ __forceinline__ TileLin make_lin(const LeafArgs& a) {
   lin.s1 = a.s1;
   lin.F = a.F;
   lin.QL = a.QLd;
+  lin.reg_sweeps = a.tile_reg;
   return lin;
 }
 

@@ -48,8 +48,62 @@ struct Team {
     __syncthreads();
   }
   __device__ __forceinline__ int threads() const { return nt; }
+  // n rows x H cooperating threads per row (H a power of two <= 32, n * H <= #threads, so thread tid IS (row tid / H,
+  // part tid % H) in every call).  stage1(row, part) returns two partial sums; they are added over the H parts of a
+  // row (xor butterfly: all H threads get bitwise the same totals); stage2(row, part, totals) finishes.  Barrier.
+  // Everything a stage-2 body reads that another part's stage 2 writes must travel through the three sum channels.
+  template <int H, class S1, class S2>
+  __device__ __forceinline__ void each_group(int n, S1&& s1, S2&& s2) const {
+    const bool active = tid < n * H;
+    const int r = tid / H, h = tid % H;
+    double a = 0.0, b = 0.0, c = 0.0;
+    if (active) s1(r, h, a, b, c);
+#pragma unroll
+    for (int o = 1; o < H; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (active) s2(r, h, a, b, c);
+    __syncthreads();
+  }
 #else
-  int threads() const { return 1 << 20; }
+  int threads() const { return 256; }  // the CTA size of the kernels (TILE_THREADS): same dispatch decisions as the device
+  template <int H, class S1, class S2>
+  void each_group(int n, S1&& s1, S2&& s2) const {
+    auto row = [&](int r) {
+      double a[H], b[H], c[H];
+      for (int h = 0; h < H; ++h) {
+        a[h] = b[h] = c[h] = 0.0;
+        s1(r, h, a[h], b[h], c[h]);
+      }
+      for (int o = 1; o < H; o <<= 1) {  // the same butterfly as the shuffles
+        double na[H], nb[H], nc[H];
+        for (int h = 0; h < H; ++h) {
+          na[h] = a[h] + a[h ^ o];
+          nb[h] = b[h] + b[h ^ o];
+          nc[h] = c[h] + c[h ^ o];
+        }
+        for (int h = 0; h < H; ++h) {
+          a[h] = na[h];
+          b[h] = nb[h];
+          c[h] = nc[h];
+        }
+      }
+      // stage 2 of one part must not depend on stage 2 of another one: forward / reverse with the iteration order
+      if (order() == 0) {
+        for (int h = 0; h < H; ++h) s2(r, h, a[h], b[h], c[h]);
+      } else {
+        for (int h = H - 1; h >= 0; --h) s2(r, h, a[h], b[h], c[h]);
+      }
+    };
+    const int o = order();
+    if (o == 0) {
+      for (int r = 0; r < n; ++r) row(r);
+    } else {
+      for (int r = n - 1; r >= 0; --r) row(r);
+    }
+  }
   // host simulator: one "thread" runs all iterations; the order is selectable to expose cross-iteration dependences
   static int& order() {
     static int o = 0;
@@ -88,6 +142,8 @@ POF_TDEV double tile_dot(int lo, int hi, double init, FA a, FB b) {
   for (; k < hi; ++k) s0 = fma(a(k), b(k), s0);
   return (s0 + s1) + (s2 + s3);
 }
+
+constexpr int TILE_PB_COLS_ = 128;  // columns of one pivot-row broadcast buffer (register sweeps)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Right-Householder lower-triangularisation of M (R x C, leading dimension ld), pivots 0..npiv-1, LAPACK sign
@@ -147,13 +203,61 @@ POF_TFUNC void tile_tria_smem(const Team& t, double* M, int R, int C, int ld, in
 // ---------------------------------------------------------------------------------------------------------------
 // The same triangularisation with the rows held in REGISTERS for the whole sweep (the shared-memory version re-reads
 // and re-writes the trailing matrix for every pivot: 8 shared-memory wavefronts per column and pivot; here a pivot
-// costs one broadcast read of the pivot row per column).  Thread r owns row r for all pivots: `regs.at(r)` is the
-// thread's register file on the device (iteration r of every each() below runs on thread r because R <= #threads) and
-// a per-iteration array in the host simulator.  KT >= C - cb columns per row (cb = c0 in pentagonal mode, else 0) are
-// kept, zero-padded, all loops fully unrolled so that nothing is indexed dynamically.  The pivot row travels through a
-// double-buffered broadcast array pb (2 x KT doubles of shared memory): the owner of row i+1 publishes it at the end of
-// pivot i, so there is still ONE barrier per pivot.
+// costs one broadcast read of the pivot row per column).  `regs.at(it)` is the executing thread's register file on
+// the device (iteration `it` of every each() / each_group() below runs on thread `it`, because the iteration counts
+// do not exceed the thread count) and a per-iteration array in the host simulator; it must be called with the
+// iteration index of the enclosing each, never with a derived row number.  All loops over the registers are fully
+// unrolled so that nothing is indexed dynamically.  The pivot row travels through a double-buffered broadcast array
+// pb (2 x TILE_PB_COLS doubles of shared memory): the owners of row i+1 publish it at the end of pivot i, so there is
+// still ONE barrier per pivot.  The reflector is H = I - tp v v^T, v = (alpha - beta, tail), tp = 1 / (norm |v_0|),
+// derived with the hardware reciprocal / reciprocal-square-root approximations plus two Newton steps, as in the
+// register-resident leaf kernels (pof_lane2.cuh): the fp64 division / square-root subroutine calls made ptxas spill
+// the rows around them.
 // ---------------------------------------------------------------------------------------------------------------
+POF_TDEV double tile_fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / x;
+#endif
+}
+POF_TDEV double tile_fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-hx * r, r, 0.5);
+  return fma(r, e, r);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+// (beta, v0 = alpha - beta, tp) of the reflector for a row with head alpha and squared tail norm sigma; ok = false if
+// there is nothing to eliminate (zero tail; the approximations flush subnormals: squared norms below 2^-1000 count as
+// zero) -- then the reflector is the identity and beta = alpha
+struct TileHouse {
+  double beta, v0, tp;
+  bool ok;
+};
+POF_TDEV TileHouse tile_house(double alpha, double sigma) {
+  TileHouse h;
+  const double nrm2 = fma(alpha, alpha, sigma);
+  h.ok = sigma > 0.0 && nrm2 > 0x1p-1000;
+  const double rn = tile_fast_rsqrt(h.ok ? nrm2 : 1.0);
+  const double nrm = nrm2 * rn;
+  h.beta = h.ok ? ((alpha >= 0.0) ? -nrm : nrm) : alpha;
+  h.v0 = alpha - h.beta;
+  h.tp = h.ok ? rn * tile_fast_rcp(fabs(h.v0)) : 0.0;
+  return h;
+}
+
 template <int KT>
 struct RowRegs {
 #if defined(__CUDA_ARCH__)
@@ -162,116 +266,178 @@ struct RowRegs {
   __device__ __forceinline__ double* at(int) { return v; }
 #else
   std::vector<double> store;
-  explicit RowRegs(int rows) : store((size_t)rows * KT) {}
-  double* at(int i) { return &store[(size_t)i * KT]; }
+  explicit RowRegs(int its) : store((size_t)its * KT) {}
+  double* at(int it) { return &store[(size_t)it * KT]; }
 #endif
 };
 
-// PENTA: the pivot column i lives in shared memory (left, already triangular block), the registers hold columns
-// [c0, C).  Plain (!PENTA): the registers hold columns [i, C) of the CURRENT pivot i -- after every pivot the finished
-// column i is written to shared memory and the register file shifts left by one (compile-time indices only: a
-// `rv[i]` with a runtime i would send the whole array to local memory).
-template <int KT, bool PENTA>
-POF_TFUNC void tile_tria_reg(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag,
-                            double* pb) {
-  const int cb = PENTA ? c0 : 0;
-  const int K = C - cb;
+// Pentagonal mode ([T | C], T lower triangular in shared memory, C = columns [c0, C) in registers), H threads per
+// row: thread (r, h) keeps columns [h KT, (h+1) KT) of C.  R H <= #threads, C - c0 <= KT H.
+template <int KT, int H>
+POF_TFUNC void tile_tria_regp(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag,
+                              double* pb) {
+  const int K = C - c0;
+  RowRegs<KT> regs(R * H);
+  t.each(R * H, [&](int it) {
+    const int r = it / H, h = it % H;
+    double* rv = regs.at(it);
+    const double* row = M + (long)r * ld + c0 + h * KT;
+    POF_UNROLL_N(KT)
+    for (int j = 0; j < KT; ++j) rv[j] = (h * KT + j < K) ? row[j] : 0.0;
+    if (r == 0) {
+      POF_UNROLL_N(KT)
+      for (int j = 0; j < KT; ++j) pb[h * KT + j] = rv[j];
+    }
+  });
+  for (int i = 0; i < npiv; ++i) {
+    const double* p = pb + (i & 1) * TILE_PB_COLS_;
+    double* pn = pb + ((i + 1) & 1) * TILE_PB_COLS_;
+    t.template each_group<H>(
+        R,
+        // partial squared norm of the pivot row, partial dot product; part 0 also contributes the row's entry in the
+        // pivot column (it is rewritten by part 0 in stage 2, so the other parts must not read it there)
+        [&](int r, int h, double& sg, double& dt, double& ri) {
+          if (r < i) return;
+          if (h == 0) ri = M[(long)r * ld + i];
+          const double* rv = regs.at(r * H + h);
+          const double* ph = p + h * KT;
+          double s[4] = {0.0, 0.0, 0.0, 0.0}, d[4] = {0.0, 0.0, 0.0, 0.0};
+          POF_UNROLL_N(KT)
+          for (int j = 0; j < KT; ++j) {
+            const double pj = ph[j];
+            s[j & 3] = fma(pj, pj, s[j & 3]);
+            d[j & 3] = fma(rv[j], pj, d[j & 3]);
+          }
+          sg = (s[0] + s[1]) + (s[2] + s[3]);
+          dt = (d[0] + d[1]) + (d[2] + d[3]);
+        },
+        [&](int r, int h, double sigma, double dot, double rowi) {
+          if (r < i) return;
+          double* rv = regs.at(r * H + h);
+          const double* ph = p + h * KT;
+          const TileHouse hh = tile_house(M[(long)i * ld + i], sigma);
+          if (r == i) {
+            if (h == 0) diag[i] = hh.beta;
+            return;
+          }
+          const double ws = hh.tp * fma(hh.v0, rowi, dot);
+          if (h == 0) M[(long)r * ld + i] = fma(-ws, hh.v0, rowi);  // column i is final now
+          POF_UNROLL_N(KT)
+          for (int j = 0; j < KT; ++j) rv[j] = fma(-ws, ph[j], rv[j]);
+          if (r == i + 1) {  // publish the next pivot row
+            POF_UNROLL_N(KT)
+            for (int j = 0; j < KT; ++j) pn[h * KT + j] = rv[j];
+          }
+        });
+  }
+  // columns right of the triangular block: only the non-pivot rows carry meaningful values there
+  t.each(R * H, [&](int it) {
+    const int r = it / H, h = it % H;
+    if (r < npiv) return;
+    const double* rv = regs.at(it);
+    double* row = M + (long)r * ld + c0 + h * KT;
+    POF_UNROLL_N(KT)
+    for (int j = 0; j < KT; ++j)
+      if (h * KT + j < K) row[j] = rv[j];
+  });
+  t.each(npiv, [&](int i) { M[(long)i * ld + i] = diag[i]; });
+}
+
+// Plain mode, one thread per row: the registers hold columns [i, C) of the CURRENT pivot i -- after every pivot the
+// finished column i is written to shared memory and the register file shifts left by one (compile-time indices only:
+// a `rv[i]` with a runtime i would send the whole array to local memory).  R <= #threads, C <= KT.
+template <int KT>
+POF_TFUNC void tile_tria_reg1(const Team& t, double* M, int R, int C, int ld, int npiv, double* diag, double* pb) {
   RowRegs<KT> regs(R);
   t.each(R, [&](int r) {
     double* rv = regs.at(r);
-    const double* row = M + (long)r * ld + cb;
+    const double* row = M + (long)r * ld;
     POF_UNROLL_N(KT)
-    for (int j = 0; j < KT; ++j) rv[j] = (j < K) ? row[j] : 0.0;
+    for (int j = 0; j < KT; ++j) rv[j] = (j < C) ? row[j] : 0.0;
     if (r == 0) {
       POF_UNROLL_N(KT)
       for (int j = 0; j < KT; ++j) pb[j] = rv[j];
     }
   });
   for (int i = 0; i < npiv; ++i) {
-    const double* p = pb + (i & 1) * KT;
-    double* pn = pb + ((i + 1) & 1) * KT;
-    // all R iterations, not R - i: iteration r must stay on thread r, whose registers hold row r (regs.at takes the
-    // iteration index of the enclosing each(), never a derived row number)
+    const double* p = pb + (i & 1) * TILE_PB_COLS_;
+    double* pn = pb + ((i + 1) & 1) * TILE_PB_COLS_;
+    // all R iterations, not R - i: iteration r must stay on thread r, whose registers hold row r
     t.each(R, [&](int r) {
       if (r < i) return;
       double* rv = regs.at(r);
-      constexpr int J0 = PENTA ? 0 : 1;  // first register column of the part to eliminate (columns >= K hold zeros)
-      double s[4] = {0.0, 0.0, 0.0, 0.0}, dt[4] = {0.0, 0.0, 0.0, 0.0};
+      double s[4] = {0.0, 0.0, 0.0, 0.0}, d[4] = {0.0, 0.0, 0.0, 0.0};
       POF_UNROLL_N(KT)
-      for (int j = J0; j < KT; ++j) {
+      for (int j = 1; j < KT; ++j) {  // columns beyond C hold zeros
         const double pj = p[j];
         s[j & 3] = fma(pj, pj, s[j & 3]);
-        dt[j & 3] = fma(rv[j], pj, dt[j & 3]);
+        d[j & 3] = fma(rv[j], pj, d[j & 3]);
       }
-      const double alpha = PENTA ? M[(long)i * ld + i] : p[0];
-      const double rowi = PENTA ? M[(long)r * ld + i] : rv[0];
-      const double sigma = (s[0] + s[1]) + (s[2] + s[3]);
-      double newi = rowi;
-      if (sigma > 0.0) {
-        const double nrm = sqrt(fma(alpha, alpha, sigma));
-        const double beta = (alpha >= 0.0) ? -nrm : nrm;
-        if (r == i) {
-          diag[i] = beta;
-        } else {
-          const double tau = (beta - alpha) / beta;
-          const double scale = 1.0 / (alpha - beta);
-          const double w = tau * fma(scale, (dt[0] + dt[1]) + (dt[2] + dt[3]), rowi);
-          const double ws = w * scale;
-          newi = rowi - w;
-          POF_UNROLL_N(KT)
-          for (int j = J0; j < KT; ++j) rv[j] = fma(-ws, p[j], rv[j]);
-        }
-      } else if (r == i) {  // nothing to eliminate: identity (also keeps all-zero rows free of NaN)
-        diag[i] = alpha;
+      const TileHouse hh = tile_house(p[0], (s[0] + s[1]) + (s[2] + s[3]));
+      if (r == i) {
+        diag[i] = hh.beta;
+        return;
       }
-      if (r > i) M[(long)r * ld + i] = newi;  // column i is final now
-      if (!PENTA) {  // shift: register column 0 becomes column i + 1
-        POF_UNROLL_N(KT)
-        for (int j = 0; j + 1 < KT; ++j) rv[j] = rv[j + 1];
-        rv[KT - 1] = 0.0;
-      }
+      const double rowi = rv[0];
+      const double ws = hh.tp * fma(hh.v0, rowi, (d[0] + d[1]) + (d[2] + d[3]));
+      M[(long)r * ld + i] = fma(-ws, hh.v0, rowi);  // column i is final now
+      POF_UNROLL_N(KT)
+      for (int j = 1; j < KT; ++j) rv[j - 1] = fma(-ws, p[j], rv[j]);  // update and shift left by one
+      rv[KT - 1] = 0.0;
       if (r == i + 1) {  // publish the next pivot row
         POF_UNROLL_N(KT)
         for (int j = 0; j < KT; ++j) pn[j] = rv[j];
       }
     });
   }
-  // columns right of the pivots: only the non-pivot rows carry meaningful values there
-  const int cs = PENTA ? cb : npiv;
   t.each(R, [&](int r) {
     if (r < npiv) return;
     const double* rv = regs.at(r);
-    double* row = M + (long)r * ld + cs;
+    double* row = M + (long)r * ld + npiv;
     POF_UNROLL_N(KT)
     for (int j = 0; j < KT; ++j)
-      if (cs + j < C) row[j] = rv[j];
+      if (npiv + j < C) row[j] = rv[j];
   });
   t.each(npiv, [&](int i) { M[(long)i * ld + i] = diag[i]; });
 }
 
-// pb: 2 x TILE_PB_COLS doubles of shared memory for the register version (used when the row span fits)
-constexpr int TILE_PB_COLS = 64;
+// pb: 2 x TILE_PB_COLS doubles of shared memory for the register sweeps, or null to force the shared-memory sweep.
+// Pentagonal sweeps: H = 4, 2 or 1 threads per row (as many as fit the CTA), up to 32 columns per thread; plain sweeps:
+// one thread per row, up to 32 columns.  Everything else (the 2D x 2D arrays of the tree operators and the plain sweeps
+// at D = 64) runs the shared-memory sweep.
 POF_TDEV void tile_tria(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag, double* pb) {
-  const int K = C - (c0 >= 0 ? c0 : 0);
-  if (pb != nullptr && R <= t.threads() && K <= TILE_PB_COLS) {
-    if (c0 >= 0) {
-      if (K <= 16)
-        tile_tria_reg<16, true>(t, M, R, C, ld, npiv, c0, diag, pb);
-      else if (K <= 32)
-        tile_tria_reg<32, true>(t, M, R, C, ld, npiv, c0, diag, pb);
-      else
-        tile_tria_reg<64, true>(t, M, R, C, ld, npiv, c0, diag, pb);
-    } else {
-      if (K <= 16)
-        tile_tria_reg<16, false>(t, M, R, C, ld, npiv, c0, diag, pb);
-      else if (K <= 32)
-        tile_tria_reg<32, false>(t, M, R, C, ld, npiv, c0, diag, pb);
-      else
-        tile_tria_reg<64, false>(t, M, R, C, ld, npiv, c0, diag, pb);
+  const int nt = t.threads();
+  if (pb != nullptr && c0 >= 0) {
+    const int K = C - c0;
+    const int H = (R * 4 <= nt && K > 32) ? 4 : ((R * 2 <= nt && K > 16) ? 2 : 1);
+    const int per = (K + H - 1) / H;
+    if (R * H <= nt && per <= 32) {
+      if (H == 4) {
+        if (per <= 16)
+          tile_tria_regp<16, 4>(t, M, R, C, ld, npiv, c0, diag, pb);
+        else
+          tile_tria_regp<32, 4>(t, M, R, C, ld, npiv, c0, diag, pb);
+      } else if (H == 2) {
+        if (per <= 16)
+          tile_tria_regp<16, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
+        else
+          tile_tria_regp<32, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
+      } else {
+        if (per <= 16)
+          tile_tria_regp<16, 1>(t, M, R, C, ld, npiv, c0, diag, pb);
+        else
+          tile_tria_regp<32, 1>(t, M, R, C, ld, npiv, c0, diag, pb);
+      }
+      return;
     }
-  } else {
-    tile_tria_smem(t, M, R, C, ld, npiv, c0, diag);
+  } else if (pb != nullptr && R <= nt && C <= 32) {
+    if (C <= 16)
+      tile_tria_reg1<16>(t, M, R, C, ld, npiv, diag, pb);
+    else
+      tile_tria_reg1<32>(t, M, R, C, ld, npiv, diag, pb);
+    return;
   }
+  tile_tria_smem(t, M, R, C, ld, npiv, c0, diag);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -342,6 +508,8 @@ struct TileLin {
   double s0, s1;
   const double* F;   // general per-step transition matrices (n, D, D) and noise factors (lower), or null = IWP
   const double* QL;
+  int reg_sweeps;    // != 0: Householder sweeps with register-resident rows where they apply (tile_tria), else the
+                     // shared-memory sweep everywhere (default until the register sweeps have been timed on a B200)
 };
 POF_TDEV void tile_set_step_model(TileModel& md, const TileLin& lin, long k) {
   md.Fd = lin.F ? lin.F + k * md.D * md.D : nullptr;
@@ -432,7 +600,7 @@ POF_TDEV void tile_update_factor(const Team& t, const TileModel& md, const doubl
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory layouts (in doubles) of the three leaf kernels
 // ---------------------------------------------------------------------------------------------------------------
-POF_TDEV int tile_vec_doubles(int D, int d) { return 8 * D + 4 * d + d * d + 16 + 2 * TILE_PB_COLS; }
+POF_TDEV int tile_vec_doubles(int D, int d) { return 8 * D + 4 * d + d * d + 16 + 2 * TILE_PB_COLS_; }
 POF_TDEV int tile_fold_smem_doubles(int D, int d) {
   return TILE_MODEL_DOUBLES + D * (2 * D + 1) + (D + d) * (D + d + 1) + D * (D + 1) + D * (D + d + 1) +
          d * (D + 1) + d * D + tile_vec_doubles(D, d);
@@ -443,9 +611,7 @@ POF_TDEV int tile_scan_smem_doubles(int D, int d) {
 POF_TDEV int tile_smooth_smem_doubles(int D, int d) {
   return TILE_MODEL_DOUBLES + D * (2 * D + 1) + 2 * D * (D + 1) + tile_vec_doubles(D, d);
 }
-POF_TDEV int tile_tree_smem_doubles(int D) {
-  return 2 * D * (2 * D + 1) + D * (2 * D + 1) + 10 * D + 16 + 2 * TILE_PB_COLS;
-}
+POF_TDEV int tile_tree_smem_doubles(int D) { return 2 * D * (2 * D + 1) + D * (2 * D + 1) + 10 * D + 16; }
 
 // small vectors common to the leaf kernels
 struct TileVecs {
@@ -490,6 +656,7 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
   double* Hs = G + d * ldg;                  // d x D
   TileVecs v;
   v.init(Hs + d * D, D, d);
+  if (!lin.reg_sweeps) v.pb = nullptr;
   double* b = v.v0;
   double* eta = v.v1;
   const bool noisy = lin.R != nullptr;
@@ -612,6 +779,7 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
   double* Hs = X + (D + d) * ldx;
   TileVecs v;
   v.init(Hs + d * D, D, d);
+  if (!lin.reg_sweeps) v.pb = nullptr;
   double* m = v.v0;
   double* mp = v.v1;
   double* g = v.v2;
@@ -739,6 +907,7 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
   double* Ls = Es + D * lde;               // D x D (lower)
   TileVecs v;
   v.init(Ls + D * lde, D, d);
+  if (!lin.reg_sweeps) v.pb = nullptr;
   double* m = v.v0;
   double* mn = v.v1;
   double* fm = v.v2;
@@ -868,7 +1037,7 @@ struct TileTreeWs {
     t2 = t1 + D;
     t3 = t2 + D;
     diag = t3 + D;
-    pb = diag + 6 * D + 16;
+    pb = nullptr;  // the tree operators always run the shared-memory sweep (2D columns; a few hundred nodes per pass)
   }
 };
 

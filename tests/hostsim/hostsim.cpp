@@ -283,7 +283,7 @@ int hs_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const d
 static int run_tile(int d, int q, long N, long L, const double* qL, const double* x0, const double* H, const double* c,
                     const double* Jc, double s0, double s1, const double* R, const double* Fd, const double* Qd,
                     double* means, double* chols, double* fmeans, double* fchols, int calibrate, double* scalars,
-                    int order) {
+                    int order, int reg_sweeps) {
   Team::order() = order;
   Team t;
   const int D = d * (q + 1);
@@ -298,7 +298,7 @@ static int run_tile(int d, int q, long N, long L, const double* qL, const double
                                      tile_smooth_smem_doubles(D, d), tile_tree_smem_doubles(D)}));
   // poison the shared memory so that reads of never-written entries show up as NaN
   auto poison = [&]() { std::fill(smem.begin(), smem.end(), std::nan("")); };
-  const TileLin lin = {H, c, Jc, R, s0, s1, Fd, Qd};
+  const TileLin lin = {H, c, Jc, R, s0, s1, Fd, Qd, reg_sweeps};
   for (long ch = 0; ch < CS; ++ch) {
     poison();
     tile_fold(t, d, q, qL, lin, ch * L, std::min((ch + 1) * L, n), &fagg[ch * FE], &faggm[ch * FE], smem.data());
@@ -373,9 +373,9 @@ extern "C" {
 int hs_tile_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const double* x0, const double* H,
                               const double* c, const double* Jc, double s0, double s1, const double* R,
                               const double* Fd, const double* Qd, double* means, double* chols, double* fmeans,
-                              double* fchols, int calibrate, double* scalars, int order) {
+                              double* fchols, int calibrate, double* scalars, int order, int reg_sweeps) {
   return run_tile(d, q, N, L, qL, x0, H, c, Jc, s0, s1, R, Fd, Qd, means, chols, fmeans, fchols, calibrate, scalars,
-                  order);
+                  order, reg_sweeps);
 }
 int hs_tile_filter_combine(int D, const double* e1, const double* e2, double* out, int state_mode, int order) {
   std::vector<double> smem(tile_tree_smem_doubles(D), std::nan(""));
@@ -394,14 +394,14 @@ int hs_tile_smooth_combine(int D, const double* e1, const double* e2, double* ou
   return 0;
 }
 int hs_tile_seq_eks(int d, int q, long N, const double* qL, double s0, double s1, int ivp_id, const double* params8,
-                    const double* x0, double* means, double* chols, double* sums, int order) {
+                    const double* x0, double* means, double* chols, double* sums, int order, int reg_sweeps) {
   Team::order() = order;
   Team t;
   const int D = d * (q + 1);
   TileEks eks;
   eks.ivp_id = ivp_id;
   for (int i = 0; i < 8; ++i) eks.P.p[i] = params8[i];
-  const TileLin lin = {nullptr, nullptr, nullptr, nullptr, s0, s1, nullptr, nullptr};
+  const TileLin lin = {nullptr, nullptr, nullptr, nullptr, s0, s1, nullptr, nullptr, reg_sweeps};
   std::vector<double> kern((size_t)(N - 1) * (D + 2 * D * D)), send(D + D * D);
   std::vector<double> smem(std::max(tile_scan_smem_doubles(D, d), tile_smooth_smem_doubles(D, d)), std::nan(""));
   tile_seq_eks(t, d, q, qL, lin, eks, N - 1, x0, kern.data(), send.data(), means, chols, sums, smem.data());
@@ -416,6 +416,15 @@ int hs_linearize_l96(double forcing, long n, int d, int q, double s0, double s1,
       l96_linearize_row(forcing, k, a, d, q, s0, s1, 1, means_t1, H, c, nullptr);
       l96_linearize_row(forcing, k, a, d, q, s0, 0.0, 0, means_t1, nullptr, nullptr, Jc);
     }
+  return 0;
+}
+// one Householder sweep (register or shared-memory version) on a caller-supplied array: unit test hook
+int hs_tile_tria(double* M, int R, int C, int ld, int npiv, int c0, int use_reg, int order) {
+  std::vector<double> diag(4 * (R + C) + 16), pb(2 * TILE_PB_COLS_);
+  Team::order() = order;
+  Team t;
+  tile_tria(t, M, R, C, ld, npiv, c0, diag.data(), use_reg ? pb.data() : nullptr);
+  Team::order() = 0;
   return 0;
 }
 int hs_tile_smem_bytes(int D, int d, int which) {

@@ -270,3 +270,28 @@ def test_tile_sequential_eks_solve_matches_oracle(native_lib, monkeypatch, name,
     d = int(ivp.y0.shape[0])
     assert abs(s - so) <= (5e-2 if d <= 4 else 1e-1) * abs(so)  # QR-sign dependent formula (utils.py:110-112)
     assert abs(info["nll"] - oinfo["nll"]) <= 1e-9 * abs(oinfo["nll"]) + 1e-9
+
+
+# ---- last on purpose: the opt-in register-resident Householder sweeps (POF_B200_TILE_SWEEP=reg).  The
+# default (shared-memory sweeps) is what every test above ran.
+@pytest.mark.parametrize("name,kw,N,q,L", [("fitzhughnagumo", {}, 100, 3, 7), ("rigid_body", {}, 256, 3, 8),
+                                            ("lorenz96", {"tmax": 1.0, "d": 8}, 90, 2, 7),
+                                            ("lorenz96", {"tmax": 1.0}, 40, 3, 6)])
+def test_tile_register_sweeps_match_oracle(native_lib, monkeypatch, name, kw, N, q, L):
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.step import linearize_at_previous_states
+
+    monkeypatch.setenv("POF_B200_LEAF_IMPL", "tile")
+    monkeypatch.setenv("POF_B200_TILE_SWEEP", "reg")
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_at_previous_states(setup["om"], states)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    torch.cuda.synchronize()
+    osetup = O.set_up_solver(oivp, ts, q)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    _check_pass(out, nll, obj, ssq, osetup, odom, N)

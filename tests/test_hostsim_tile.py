@@ -48,7 +48,7 @@ def _problem(name, kw, N, q, noisy):
     return setup, st, dom
 
 
-def _run(lib, setup, st, dom, q, L, order=0, noisy=False, compact=None, dense_model=None):
+def _run(lib, setup, st, dom, q, L, order=0, noisy=False, compact=None, dense_model=None, reg=1):
     d = setup["d"]
     D = d * (q + 1)
     N = st.mean.shape[0]
@@ -63,7 +63,7 @@ def _run(lib, setup, st, dom, q, L, order=0, noisy=False, compact=None, dense_mo
         d, q, ctypes.c_long(N), ctypes.c_long(L), _p(qL), _p(x0), None if Jc is not None else _p(H),
         None if Jc is not None else _p(c), _p(Jc), ctypes.c_double(s0), ctypes.c_double(s1), _p(R),
         None if dense_model is None else _p(dense_model[0]), None if dense_model is None else _p(dense_model[1]),
-        _p(means), _p(chols), _p(fm), _p(fc), 0, _p(sc), order)
+        _p(means), _p(chols), _p(fm), _p(fc), 0, _p(sc), order, reg)
     assert rc == 0
     return means, chols, fm, fc, sc
 
@@ -97,6 +97,12 @@ def test_tile_pass_matches_oracle_and_is_order_independent(lib, name, kw, N, q, 
         again = _run(lib, setup, st, dom, q, L, order, noisy)
         for a, b in zip((means, chols, fm, fc, sc), again):
             assert np.array_equal(a, b, equal_nan=True), f"iteration order {order} changes the result: race"
+    # the default configuration of the kernels: shared-memory Householder sweeps everywhere (the run above used the
+    # register-resident sweeps); same results up to rounding, and order-independent as well
+    smem = [_run(lib, setup, st, dom, q, L, order, noisy, reg=0) for order in (0, 1)]
+    for a, b in zip(smem[0], smem[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert rel(smem[0][0], means) <= 1e-10 and rel(_cov(smem[0][1]), _cov(chols)) <= 1e-10
 
 
 def test_tile_lorenz96_compact_linearisation(lib):
@@ -210,13 +216,17 @@ def test_tile_sequential_eks_matches_oracle(lib, name, kw, params, N, q):
     p8 = np.zeros(8)
     p8[: len(params)] = params
     out, ell, obj, ssq = O.sequential_eks(setup)
-    res = []
-    for order in (0, 1, 2):
+    def run(order, reg):
         means, chols, sums = np.zeros((N, D)), np.zeros((N, D, D)), np.zeros(8)
         assert lib.hs_tile_seq_eks(d, q, ctypes.c_long(N), _p(qL), ctypes.c_double(s0), ctypes.c_double(s1),
-                                   IVP_IDS[name], _p(p8), _p(x0), _p(means), _p(chols), _p(sums), order) == 0
-        res.append((means, chols, sums[:4].copy()))
+                                   IVP_IDS[name], _p(p8), _p(x0), _p(means), _p(chols), _p(sums), order, reg) == 0
+        return means, chols, sums[:4].copy()
+
+    res = [run(order, 1) for order in (0, 1, 2)]  # register-resident sweeps
     means, chols, sums = res[0]
+    m0, c0, _ = run(0, 0)  # shared-memory sweeps (the kernels' default)
+    assert np.abs(m0 - means).max() <= 1e-10 * np.abs(means).max()
+    assert np.abs(_cov(c0) - _cov(chols)).max() <= 1e-10 * np.abs(_cov(chols)).max()
     rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
     assert rel(means, out.mean) <= 1e-9
     assert rel(_cov(chols), _cov(out.chol)) <= 1e-9
@@ -227,3 +237,31 @@ def test_tile_sequential_eks_matches_oracle(lib, name, kw, params, N, q):
     for other in res[1:]:
         for a, b in zip(res[0], other):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("R,C,npiv,c0", [
+    (32, 32, 8, -1), (24, 24, 24, -1), (80, 64, 16, -1), (10, 10, 2, -1),          # plain: one thread per row, shifting
+    (48, 48, 24, 24), (24, 48, 24, 24), (36, 60, 18, 18),                          # pentagonal, 2 threads per row
+    (128, 128, 64, 64), (64, 128, 64, 64), (64, 80, 64, 64), (24, 32, 24, 24),     # D = 64: scan (H=2), fold/smooth (H=4)
+])
+def test_register_sweeps_equal_shared_memory_sweep(lib, R, C, npiv, c0):
+    """tile_tria_regp / tile_tria_reg1 (rows in registers, pivot row broadcast) against tile_tria_smem on random
+    arrays, under all iteration orders (each_group's stage 2 runs the parts of a row forward / backward)"""
+    def run(use_reg, order):
+        rng = np.random.default_rng(7)
+        ld = C + 1
+        M = rng.standard_normal((R, ld))
+        if c0 >= 0:
+            for r in range(min(R, c0)):
+                M[r, r + 1:c0] = 0.0
+        assert lib.hs_tile_tria(_p(M), R, C, ld, npiv, c0, use_reg, order) == 0
+        out = M[:, :C].copy()
+        for r in range(min(R, npiv)):
+            out[r, r + 1:] = 0.0  # eliminated entries of the pivot rows are dead
+        return out
+
+    ref = run(0, 0)
+    res = [run(1, o) for o in (0, 1, 2)]
+    assert np.abs(res[0] - ref).max() <= 1e-13 * np.abs(ref).max()
+    for x in res[1:]:
+        assert np.array_equal(res[0], x)
