@@ -32,7 +32,7 @@ namespace pof {
 #if defined(__CUDACC__)
 #define POF_TDEV __host__ __device__ __forceinline__
 // the Householder sweeps are called from many places and are large once unrolled: real functions, compiled once
-#define POF_TFUNC __host__ __device__ __noinline__
+#define POF_TFUNC __host__ __device__ __forceinline__
 #else
 #define POF_TDEV inline
 #define POF_TFUNC inline
@@ -402,32 +402,22 @@ POF_TFUNC void tile_tria_reg1(const Team& t, double* M, int R, int C, int ld, in
 }
 
 // pb: 2 x TILE_PB_COLS doubles of shared memory for the register sweeps, or null to force the shared-memory sweep.
-// Pentagonal sweeps: H = 4, 2 or 1 threads per row (as many as fit the CTA), up to 32 columns per thread; plain sweeps:
-// one thread per row, up to 32 columns.  Everything else (the 2D x 2D arrays of the tree operators and the plain sweeps
+// Pentagonal sweeps: two threads per row, up to 32 columns per thread; plain sweeps: one thread per row, up to 32
+// columns.  Everything else (the 2D x 2D arrays of the tree operators and the plain sweeps
 // at D = 64) runs the shared-memory sweep.
 POF_TDEV void tile_tria(const Team& t, double* M, int R, int C, int ld, int npiv, int c0, double* diag, double* pb) {
   const int nt = t.threads();
   if (pb != nullptr && c0 >= 0) {
+    // two threads per row, 8 / 16 / 32 columns each (few instantiations on purpose: with six of them inlined into one
+    // kernel ptxas kept the register files of some in local memory)
     const int K = C - c0;
-    const int H = (R * 4 <= nt && K > 32) ? 4 : ((R * 2 <= nt && K > 16) ? 2 : 1);
-    const int per = (K + H - 1) / H;
-    if (R * H <= nt && per <= 32) {
-      if (H == 4) {
-        if (per <= 16)
-          tile_tria_regp<16, 4>(t, M, R, C, ld, npiv, c0, diag, pb);
-        else
-          tile_tria_regp<32, 4>(t, M, R, C, ld, npiv, c0, diag, pb);
-      } else if (H == 2) {
-        if (per <= 16)
-          tile_tria_regp<16, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
-        else
-          tile_tria_regp<32, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
-      } else {
-        if (per <= 16)
-          tile_tria_regp<16, 1>(t, M, R, C, ld, npiv, c0, diag, pb);
-        else
-          tile_tria_regp<32, 1>(t, M, R, C, ld, npiv, c0, diag, pb);
-      }
+    if (R * 2 <= nt && K <= 64) {
+      if (K <= 16)
+        tile_tria_regp<8, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
+      else if (K <= 32)
+        tile_tria_regp<16, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
+      else
+        tile_tria_regp<32, 2>(t, M, R, C, ld, npiv, c0, diag, pb);
       return;
     }
   } else if (pb != nullptr && R <= nt && C <= 32) {
@@ -577,8 +567,8 @@ POF_TDEV void tile_stage_lin(const Team& t, const TileModel& md, const TileLin& 
 // first d rows are triangularised.  Afterwards  SL = X[0:d, 0:d] (lower),  Kbar = X[d:, 0:d],  posterior factor
 // Uf = X[d:, d:d+D] (its last d columns are zero when R == 0).
 // ---------------------------------------------------------------------------------------------------------------
-POF_TDEV void tile_update_factor(const Team& t, const TileModel& md, const double* T, int ldT, const double* Hs,
-                                 const double* Rs, bool noisy, double* X, double* diag, double* pb) {
+POF_TDEV void tile_update_build(const Team& t, const TileModel& md, const double* T, int ldT, const double* Hs,
+                                const double* Rs, double* X) {
   const int d = md.d, D = md.D, ldx = D + d + 1, W = D + d;
   t.each((d + D) * W, [&](int idx) {
     const int r = idx / W, j = idx - r * W;
@@ -594,8 +584,24 @@ POF_TDEV void tile_update_factor(const Team& t, const TileModel& md, const doubl
     }
     X[(long)r * ldx + j] = v;
   });
-  tile_tria(t, X, d + D, noisy ? W : D, ldx, d, -1, diag, pb);
 }
+// One Householder sweep request.  The leaf recursions below are written as loops over PHASES: every phase does its
+// element-wise / GEMM-like work and may leave one sweep request, which is executed at the single tile_tria call site at
+// the bottom of the loop -- so each kernel contains ONE inlined copy of the sweeps (register allocation is then global
+// and the sweeps are not squeezed into whatever registers a caller leaves free across a call).
+struct TileSweep {
+  double* M;
+  int R, C, ld, npiv, c0;
+  POF_TDEV void none() { M = nullptr; }
+  POF_TDEV void set(double* M_, int R_, int C_, int ld_, int npiv_, int c0_) {
+    M = M_;
+    R = R_;
+    C = C_;
+    ld = ld_;
+    npiv = npiv_;
+    c0 = c0_;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory layouts (in doubles) of the three leaf kernels
@@ -672,6 +678,10 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
     }
   });
   for (long k = k0; k < k1; ++k) {
+   for (int ph = 0; ph < 3; ++ph) {
+    TileSweep sw;
+    sw.none();
+    if (ph == 0) {
     tile_stage_lin(t, md, lin, k, Hs, v.cs, v.Rs);
     tile_set_step_model(md, lin, k);
     // predict: A <- F A, b <- F b, [QL | F Uf]
@@ -705,7 +715,8 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
       PW[r * ldp + c] = tile_QL(md, r, c);
       PW[r * ldp + D + c] = tile_F_row(md, r, [&](int j) { return X[(long)(d + j) * ldx + d + c]; });
     });
-    tile_tria(t, PW, D, 2 * D, ldp, D, D, v.diag, v.pb);
+    sw.set(PW, D, 2 * D, ldp, D, D);
+    } else if (ph == 1) {
     if (aggm && k == k1 - 1) {
       t.each(D * D, [&](int idx) {
         const int r = idx / D, c = idx - r * D;
@@ -718,7 +729,9 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
         }
       });
     }
-    tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag, v.pb);
+    tile_update_build(t, md, PW, ldp, Hs, v.Rs, X);
+    sw.set(X, d + D, noisy ? D + d : D, ldx, d, -1);
+    } else {
     // G = SL^{-1} (H A) (d x D) and z = SL^{-1} (H b + c) in column D: products, then one thread per column solves
     t.each(d * (D + 1), [&](int idx) {
       const int a = idx / (D + 1), j = idx - a * (D + 1);
@@ -746,7 +759,10 @@ POF_TDEV void tile_fold(const Team& t, int d, int q, const double* ql_param, con
         eta[i] = tile_dot(0, d, eta[i], [&](int a) { return -G[a * ldg + i]; }, [&](int a) { return G[a * ldg + D]; });
       }
     });
-    tile_tria(t, ZG, D, D + d, ldz, D, D, v.diag, v.pb);
+    sw.set(ZG, D, D + d, ldz, D, D);
+    }
+    if (sw.M) tile_tria(t, sw.M, sw.R, sw.C, sw.ld, sw.npiv, sw.c0, v.diag, v.pb);
+   }
   }
   t.each(D * D, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
@@ -792,7 +808,15 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
     if (c == 0) m[r] = state_in[r];
     if (idx < 3) v.acc[idx] = 0.0;
   });
-  for (long k = k0; k < k1; ++k) {
+  // k == k1 is the epilogue: the end state goes to the smoother tree as (m, L) with L lower triangular
+  for (long k = k0; k <= k1; ++k) {
+   const int nph = (k < k1) ? 4 : 1;
+   for (int ph = 0; ph < nph; ++ph) {
+    TileSweep sw;
+    sw.none();
+    if (k == k1) {
+      sw.set(X + (long)d * ldx + d, D, D, ldx, D, -1);
+    } else if (ph == 0) {
     if (!eks) tile_stage_lin(t, md, lin, k, Hs, v.cs, v.Rs);
     tile_set_step_model(md, lin, k);
     t.each(D * D, [&](int idx) {
@@ -804,7 +828,8 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       if (c == 0) mp[r] = tile_F_row(md, r, [&](int j) { return m[j]; });
     });
     if (eks) tile_stage_lin_eks(t, md, *eks, lin.s0, lin.s1, mp, Hs, v.cs, v.Rs);
-    tile_tria(t, PW, 2 * D, 2 * D, ldp, D, D, v.diag, v.pb);
+    sw.set(PW, 2 * D, 2 * D, ldp, D, D);
+    } else if (ph == 1) {
     // E = Phi21 T^{-1} (row-wise back substitution, in place), then g = m - E (F m)
     t.each(D, [&](int r) {
       double* e = PW + (long)(D + r) * ldp;
@@ -819,7 +844,8 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
       g[r] = gr;
     });
     // Dk = tria(Phi22~)
-    tile_tria(t, PW + (long)D * ldp + D, D, D, ldp, D, -1, v.diag, v.pb);
+    sw.set(PW + (long)D * ldp + D, D, D, ldp, D, -1);
+    } else if (ph == 2) {
     {
       double* kp = kern + k * NE;
       t.each(NE, [&](int idx) {
@@ -836,7 +862,9 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
         kp[idx] = val;
       });
     }
-    tile_update_factor(t, md, PW, ldp, Hs, v.Rs, noisy, X, v.diag, v.pb);
+    tile_update_build(t, md, PW, ldp, Hs, v.Rs, X);
+    sw.set(X, d + D, noisy ? D + d : D, ldx, d, -1);
+    } else {
     t.each(d, [&](int a) {
       double s = v.cs[a];
       s = tile_dot(0, D, s, [&](int i) { return Hs[a * D + i]; }, [&](int i) { return mp[i]; });
@@ -877,9 +905,10 @@ POF_TDEV void tile_scan(const Team& t, int d, int q, const double* ql_param, con
         if (c == 0) fmeans[(k + 1) * D + r] = m[r];
       });
     }
+    }
+    if (sw.M) tile_tria(t, sw.M, sw.R, sw.C, sw.ld, sw.npiv, sw.c0, v.diag, v.pb);
+   }
   }
-  // the end state goes to the smoother tree as (m, L) with L lower triangular
-  tile_tria(t, X + (long)d * ldx + d, D, D, ldx, D, -1, v.diag, v.pb);
   t.each(D * D, [&](int idx) {
     const int r = idx / D, c = idx - r * D;
     state_end[D + idx] = (c <= r) ? X[(long)(d + r) * ldx + d + c] : 0.0;
@@ -940,8 +969,12 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
   };
   if (last) emit(k1);
   for (long k = k1 - 1; k >= k0; --k) {
+   for (int ph = 0; ph < 2; ++ph) {
+    TileSweep sw;
+    sw.none();
     const double* kp = kern + k * NE;
     tile_set_step_model(md, lin, k);
+    if (ph == 0) {
     t.each(D * D, [&](int idx) {
       const int r = idx / D, c = idx - r * D;
       Es[r * lde + c] = kp[D + idx];
@@ -962,7 +995,8 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
         mn[a] = s;
       }
     });
-    tile_tria(t, SW, D, 2 * D, lds, D, D, v.diag, v.pb);
+    sw.set(SW, D, 2 * D, lds, D, D);
+    } else {
     // objective increment |QL^{-1}(m_k - F m_{k+1})|^2 (reference's swapped-argument form, smoother.py:20): one thread
     // per block of the block-diagonal QL; new state
     t.each(d, [&](int b) {
@@ -999,6 +1033,9 @@ POF_TDEV void tile_smooth(const Team& t, int d, int q, const double* ql_param, c
       }
     });
     if (k > 0 || emit_t0) emit(k);
+    }
+    if (sw.M) tile_tria(t, sw.M, sw.R, sw.C, sw.ld, sw.npiv, sw.c0, v.diag, v.pb);
+   }
   }
   t.each(1, [&](int) {
     double nb = 0.0;

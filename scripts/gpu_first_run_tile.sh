@@ -8,7 +8,7 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_tile.py -m gpu -x -q > gpurun_out/${TAG}_tile_tests.log 2>&1
 echo "tile tests exit $?"; tail -n 3 gpurun_out/${TAG}_tile_tests.log
-for e in 12 15 18; do
+for e in 12 15 18; do  # run the whole script again with POF_B200_TILE_SWEEP=reg exported for the A/B
   timeout 300 python scripts/bench_config5.py --log2n $e --steps 2 --warmup 1 > gpurun_out/${TAG}_config5_n$e.json \
       2> gpurun_out/${TAG}_config5_n$e.err
   echo "config5 2^$e exit $?"; tail -c 600 gpurun_out/${TAG}_config5_n$e.json
