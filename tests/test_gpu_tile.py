@@ -105,13 +105,16 @@ def test_noisy_observations_match_oracle(native_lib, name, kw, N, q, L):
     _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=True)
 
 
+@pytest.mark.parametrize("sweep", ["smem", "reg"])
 @pytest.mark.parametrize("N,L", [(40, 6), (150, None)])
-def test_lorenz96_d16_q3_pass_matches_oracle(native_lib, N, L):
-    """BASELINE config 5's state size (D = 64) on a grid the oracle finishes in seconds"""
+def test_lorenz96_d16_q3_pass_matches_oracle(native_lib, monkeypatch, N, L, sweep):
+    """BASELINE config 5's state size (D = 64) on a grid the oracle finishes in seconds; both Householder sweep
+    implementations (shared memory = default, register-resident = opt-in)"""
     from pof.convenience import get_initial_trajectory, set_up_solver
     from pof.parallel_filtsmooth import linear_filtsmooth
     from pof.step import linearize_at_previous_states
 
+    monkeypatch.setenv("POF_B200_TILE_SWEEP", sweep)
     assert native_lib.LIB.pof_supported(16, 3) == 1
     ivp, oivp = _pair("lorenz96", tmax=1.0)
     ts = np.linspace(ivp.t0, ivp.tmax, N)
