@@ -24,6 +24,19 @@ NVCC_FLAGS = [
 ]
 
 
+HASH = LIB + ".srchash"
+
+
+def _source_digest():
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in sorted(_headers() + [os.path.join(CSRC, s) for s in SOURCES]):
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
+    return h.hexdigest()
+
+
 def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
@@ -39,10 +52,10 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     hdr_time = _newest(_headers())
-    # up to date: the library is newer than every source and header (the object directory does not travel to the GPU
-    # box, the library does -- no recompilation there)
-    src_time = max([hdr_time] + [os.path.getmtime(os.path.join(CSRC, s)) for s in SOURCES])
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= src_time:
+    # up to date: the library was built from exactly these sources (content hash in a sidecar file; file times do not
+    # survive the copy to the GPU box reliably, and the object directory does not travel -- the library does)
+    digest = _source_digest()
+    if not force and os.path.exists(LIB) and os.path.exists(HASH) and open(HASH).read().strip() == digest:
         if verbose:
             print("up to date:", LIB)
         return LIB
@@ -73,6 +86,8 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(HASH, "w") as fh:
+        fh.write(digest + "\n")
     if verbose:
         print("built", LIB, "(recompiled %d objects)" % len(jobs))
     return LIB
