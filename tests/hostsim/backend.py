@@ -21,6 +21,15 @@ def load():
                                ctypes.c_void_p, ctypes.c_void_p]
     lib.hs_filter_chain.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.hs_smooth_chain.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    # the same entry points on the large-state ("tile") family
+    lib.hs_tile_ws_create.restype = ctypes.c_void_p
+    lib.hs_tile_ws_create.argtypes = lib.hs_ws_create.argtypes
+    lib.hs_tile_ws_free.argtypes = [ctypes.c_void_p]
+    lib.hs_tile_stage_a.argtypes = lib.hs_stage_a.argtypes
+    lib.hs_tile_stage_b.argtypes = lib.hs_stage_b.argtypes
+    lib.hs_tile_stage_c.argtypes = lib.hs_stage_c.argtypes
+    lib.hs_tile_filter_chain.argtypes = lib.hs_filter_chain.argtypes
+    lib.hs_tile_smooth_chain.argtypes = lib.hs_smooth_chain.argtypes
     return lib
 
 
@@ -29,10 +38,18 @@ def _p(t):
 
 
 class HostBackend:
-    def __init__(self, d, q, n_loc, chunk_len, qL):
-        self.lib = load()
+    def __init__(self, d, q, n_loc, chunk_len, qL, family="thread"):
+        lib = load()
         self.qL = np.ascontiguousarray(qL, dtype=np.float64)
-        self.ws = self.lib.hs_ws_create(d, q, n_loc, chunk_len, self.qL.ctypes.data_as(ctypes.c_void_p))
+        if family == "tile":  # CTA-per-chunk / CTA-per-node device code (csrc/pof_tile.cuh), any (d, q)
+            class _Tile:
+                hs_stage_a, hs_stage_b, hs_stage_c = lib.hs_tile_stage_a, lib.hs_tile_stage_b, lib.hs_tile_stage_c
+                hs_filter_chain, hs_smooth_chain = lib.hs_tile_filter_chain, lib.hs_tile_smooth_chain
+            self.lib = _Tile
+            self.ws = lib.hs_tile_ws_create(d, q, n_loc, chunk_len, self.qL.ctypes.data_as(ctypes.c_void_p))
+        else:
+            self.lib = lib
+            self.ws = lib.hs_ws_create(d, q, n_loc, chunk_len, self.qL.ctypes.data_as(ctypes.c_void_p))
         assert self.ws
 
     def stage_a(self, H, c, carry_f):

@@ -433,3 +433,134 @@ int hs_tile_smem_bytes(int D, int d, int which) {
   return v[which & 3] * (int)sizeof(double);
 }
 }
+
+// ---- time-sharded form on the tile family: the three stages of pof_shard_stage_{a,b,c}_f64 when the leaves are the
+// CTA-per-chunk kernels and the tree is the CTA-per-node one (runtime d, q)
+struct HsTileWs {
+  int d, q, D, FE, SE, ST, NE;
+  long n, L, CS;
+  TreeLevels tl;
+  std::vector<double> fagg, faggm, fin, sagg, sin_, kern, send, part, part2, smem, qL;
+};
+extern "C" {
+void* hs_tile_ws_create(int d, int q, long n_loc, long L, const double* qL) {
+  HsTileWs* w = new HsTileWs;
+  w->d = d; w->q = q; w->D = d * (q + 1);
+  const int D = w->D;
+  w->FE = 3 * D * D + 2 * D; w->SE = 2 * D * D + D; w->ST = D * D + D; w->NE = D + 2 * D * D;
+  w->n = n_loc; w->L = L; w->CS = (n_loc + L - 1) / L;
+  w->tl.build(w->CS);
+  w->fagg.resize(w->tl.total * w->FE); w->faggm.resize(w->CS * w->FE); w->fin.resize(w->tl.total * w->ST);
+  w->sagg.resize(w->tl.total * w->SE); w->sin_.resize(w->tl.total * w->ST);
+  w->kern.resize((size_t)n_loc * w->NE); w->send.resize(w->CS * w->ST);
+  w->part.resize(w->CS * 3); w->part2.resize(w->CS * 2);
+  w->smem.resize(std::max({tile_fold_smem_doubles(D, d), tile_scan_smem_doubles(D, d), tile_smooth_smem_doubles(D, d),
+                           tile_tree_smem_doubles(D)}));
+  w->qL.assign(qL, qL + (q + 1) * (q + 1));
+  return w;
+}
+void hs_tile_ws_free(void* p) { delete (HsTileWs*)p; }
+int hs_tile_stage_a(void* p, const double* H, const double* c, double* carry_f) {
+  HsTileWs& w = *(HsTileWs*)p;
+  Team t;
+  const TileLin lin = {H, c, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, 1};
+  for (long ch = 0; ch < w.CS; ++ch)
+    tile_fold(t, w.d, w.q, w.qL.data(), lin, ch * w.L, std::min((ch + 1) * w.L, w.n), &w.fagg[ch * w.FE],
+              &w.faggm[ch * w.FE], w.smem.data());
+  for (int l = 0; l + 1 < w.tl.nlev; ++l)
+    for (long i = 0; i < w.tl.sz[l + 1]; ++i) {
+      double* par = &w.fagg[(w.tl.off[l + 1] + i) * w.FE];
+      const double* lc = &w.fagg[(w.tl.off[l] + 2 * i) * w.FE];
+      if (2 * i + 1 < w.tl.sz[l]) tile_filter_combine(t, w.D, lc, lc + w.FE, par, w.smem.data(), false);
+      else std::memcpy(par, lc, w.FE * sizeof(double));
+    }
+  std::memcpy(carry_f, &w.fagg[w.tl.off[w.tl.nlev - 1] * w.FE], w.FE * sizeof(double));
+  return 0;
+}
+int hs_tile_stage_b(void* p, const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
+                    double* carry_s, double* state_end, double* partials) {
+  HsTileWs& w = *(HsTileWs*)p;
+  Team t;
+  const TreeLevels& tl = w.tl;
+  const TileLin lin = {H, c, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, 1};
+  std::memcpy(&w.fin[tl.off[tl.nlev - 1] * w.ST], state_in, w.ST * sizeof(double));
+  for (int l = tl.nlev - 1; l >= 1; --l)
+    for (long i = 0; i < tl.sz[l]; ++i) {
+      const double* pin = &w.fin[(tl.off[l] + i) * w.ST];
+      std::memcpy(&w.fin[(tl.off[l - 1] + 2 * i) * w.ST], pin, w.ST * sizeof(double));
+      if (2 * i + 1 < tl.sz[l - 1])
+        tile_filter_combine(t, w.D, pin, &w.fagg[(tl.off[l - 1] + 2 * i) * w.FE],
+                            &w.fin[(tl.off[l - 1] + 2 * i + 1) * w.ST], w.smem.data(), true);
+    }
+  for (long ch = 0; ch < w.CS; ++ch) {
+    tile_chunk_kernel(t, w.D, &w.fin[ch * w.ST], &w.faggm[ch * w.FE], &w.sagg[ch * w.SE], w.smem.data());
+    tile_scan(t, w.d, w.q, w.qL.data(), lin, ch * w.L, std::min((ch + 1) * w.L, w.n), &w.fin[ch * w.ST], w.kern.data(),
+              &w.send[ch * w.ST], &w.part[ch * 3], fmeans, fchols, w.smem.data());
+  }
+  for (int l = 0; l + 1 < tl.nlev; ++l)
+    for (long i = 0; i < tl.sz[l + 1]; ++i) {
+      double* par = &w.sagg[(tl.off[l + 1] + i) * w.SE];
+      const double* lc = &w.sagg[(tl.off[l] + 2 * i) * w.SE];
+      if (2 * i + 1 < tl.sz[l]) tile_smooth_combine(t, w.D, lc + w.SE, lc, par, w.smem.data(), false);
+      else std::memcpy(par, lc, w.SE * sizeof(double));
+    }
+  std::memcpy(carry_s, &w.sagg[tl.off[tl.nlev - 1] * w.SE], w.SE * sizeof(double));
+  std::memcpy(state_end, &w.send[(w.CS - 1) * w.ST], w.ST * sizeof(double));
+  partials[0] = partials[1] = partials[2] = 0.0;
+  for (long ch = 0; ch < w.CS; ++ch)
+    for (int j = 0; j < 3; ++j) partials[j] += w.part[ch * 3 + j];
+  return 0;
+}
+int hs_tile_stage_c(void* p, const double* seed, int has_row0, double cscale, double* means, double* chols,
+                    double* partials2) {
+  HsTileWs& w = *(HsTileWs*)p;
+  Team t;
+  const TreeLevels& tl = w.tl;
+  const TileLin lin = {nullptr, nullptr, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, 1};
+  std::memcpy(&w.sin_[tl.off[tl.nlev - 1] * w.ST], seed, w.ST * sizeof(double));
+  for (int l = tl.nlev - 1; l >= 1; --l)
+    for (long i = 0; i < tl.sz[l]; ++i) {
+      const double* pin = &w.sin_[(tl.off[l] + i) * w.ST];
+      if (2 * i + 1 < tl.sz[l - 1]) {
+        std::memcpy(&w.sin_[(tl.off[l - 1] + 2 * i + 1) * w.ST], pin, w.ST * sizeof(double));
+        tile_smooth_combine(t, w.D, pin, &w.sagg[(tl.off[l - 1] + 2 * i + 1) * w.SE],
+                            &w.sin_[(tl.off[l - 1] + 2 * i) * w.ST], w.smem.data(), true);
+      } else {
+        std::memcpy(&w.sin_[(tl.off[l - 1] + 2 * i) * w.ST], pin, w.ST * sizeof(double));
+      }
+    }
+  const long shift = has_row0 ? 0 : 1;
+  double* mb = means - shift * w.D;
+  double* cb = chols ? chols - shift * (long)w.D * w.D : nullptr;
+  for (long ch = 0; ch < w.CS; ++ch)
+    tile_smooth(t, w.d, w.q, w.qL.data(), lin, ch * w.L, std::min((ch + 1) * w.L, w.n), ch == w.CS - 1, has_row0 != 0,
+                &w.sin_[ch * w.ST], w.kern.data(), cscale, mb, cb, &w.part2[ch * 2], w.smem.data());
+  partials2[0] = partials2[1] = 0.0;
+  for (long ch = 0; ch < w.CS; ++ch)
+    for (int j = 0; j < 2; ++j) partials2[j] += w.part2[ch * 2 + j];
+  return 0;
+}
+// the bodies of k_tile_fchain / k_tile_schain
+int hs_tile_filter_chain(int D, int count, const double* state_in, const double* elems, double* state_out) {
+  std::vector<double> smem(tile_tree_smem_doubles(D)), cur(state_in, state_in + D + D * D), nxt(D + D * D);
+  Team t;
+  const int FE = 3 * D * D + 2 * D;
+  for (int i = 0; i < count; ++i) {
+    tile_filter_combine(t, D, cur.data(), elems + (long)i * FE, nxt.data(), smem.data(), true);
+    cur.swap(nxt);
+  }
+  std::memcpy(state_out, cur.data(), (D + D * D) * sizeof(double));
+  return 0;
+}
+int hs_tile_smooth_chain(int D, int count, const double* state_in, const double* elems, double* state_out) {
+  std::vector<double> smem(tile_tree_smem_doubles(D)), cur(state_in, state_in + D + D * D), nxt(D + D * D);
+  Team t;
+  const int SE = 2 * D * D + D;
+  for (int i = 0; i < count; ++i) {
+    tile_smooth_combine(t, D, cur.data(), elems + (long)(count - 1 - i) * SE, nxt.data(), smem.data(), true);
+    cur.swap(nxt);
+  }
+  std::memcpy(state_out, cur.data(), (D + D * D) * sizeof(double));
+  return 0;
+}
+}

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N, q, L, name, ret):
+def _worker(rank, world, port, N, q, L, name, ret, family="thread", kw=None):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "parallel-in-time-ode-filters_b200"), os.path.join(ROOT, "tests", "hostsim")]
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -31,7 +31,7 @@ def _worker(rank, world, port, N, q, L, name, ret):
         from oracle import ivps, pof_oracle as O
         from pof.sharded import ShardedPass, shard_bounds
 
-        ivp = getattr(ivps, name)()
+        ivp = getattr(ivps, name)(**(kw or {}))
         ts = np.linspace(ivp.t0, ivp.tmax, N)
         setup = O.set_up_solver(ivp, ts, q)
         st = O.get_initial_trajectory(setup)
@@ -40,7 +40,7 @@ def _worker(rank, world, port, N, q, L, name, ret):
         D = d * (q + 1)
         _, qL = O.preconditioned_discretize_1d(q)
         k_lo, k_hi = shard_bounds(N - 1, rank, world)
-        be = HostBackend(d, q, k_hi - k_lo, L, qL)
+        be = HostBackend(d, q, k_hi - k_lo, L, qL, family=family)
         sp = ShardedPass(N, d, q, qL, rank=rank, world=world, device=torch.device("cpu"), backend=be)
         r0 = 0 if rank == 0 else k_lo + 1
         H = torch.from_numpy(np.ascontiguousarray(dom.H[k_lo:k_hi]))
@@ -68,6 +68,22 @@ def test_sharded_pass_matches_oracle(native_lib, world, N, q, L, name):
     ret = ctx.Manager().dict()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, N, q, L, name, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for r in range(world):
+        assert ret[r][0], ret[r]
+
+
+@pytest.mark.parametrize("world,N,q,L,name,kw", [(2, 120, 3, 7, "fitzhughnagumo", {}),
+                                                (3, 70, 2, 5, "lorenz96", {"tmax": 1.0, "d": 8})])
+def test_sharded_pass_on_the_tile_family(native_lib, world, N, q, L, name, kw):
+    """the same orchestration with the large-state kernels' device code behind the three stages (D = 24 for the
+    Lorenz-96 case: beyond the (d <= 4)-templated families)"""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, q, L, name, ret, "tile", kw)) for r in range(world)]
     [p.start() for p in procs]
     [p.join(300) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
