@@ -17,7 +17,12 @@
 // such bodies; nothing outside a body reads memory.  So the code is race-free iff the iterations of each single
 // `each` are independent of each other -- which the host simulator (tests/hostsim) checks by executing them in
 // forward, reverse and shuffled order (the results must be bitwise identical) besides checking the math against the
-// oracle.  Control flow around `each` only depends on CTA-uniform values.
+// oracle.  Control flow around `each` only depends on CTA-uniform values.  (`Team::each_group` is the one extension:
+// H threads per row exchange partial sums through shuffles between a stage 1 and a stage 2; see there.)
+//
+// Code shape.  The leaf recursions are loops over PHASES; a phase does its element-wise / GEMM-like work and leaves at
+// most one Householder-sweep request, executed at ONE inlined call site at the bottom of the loop.  This is what lets
+// ptxas keep the register-resident sweeps in registers (DESIGN.md 2.4 lists what did not work).
 //
 // Observation noise: `R` (the reference's cholR, observations.py:23-33) may be non-zero here -- the posterior factor
 // then has D instead of D-d non-zero columns; R == nullptr is the noiseless ODE-solver case (step.py:12-22).
@@ -31,7 +36,7 @@ namespace pof {
 
 #if defined(__CUDACC__)
 #define POF_TDEV __host__ __device__ __forceinline__
-// the Householder sweeps are called from many places and are large once unrolled: real functions, compiled once
+// the Householder sweeps: inlined, one call site per leaf kernel (see "Code shape" above)
 #define POF_TFUNC __host__ __device__ __forceinline__
 #else
 #define POF_TDEV inline
