@@ -275,6 +275,20 @@ def test_tile_sequential_eks_solve_matches_oracle(native_lib, monkeypatch, name,
     assert abs(info["nll"] - oinfo["nll"]) <= 1e-9 * abs(oinfo["nll"]) + 1e-9
 
 
+def test_lorenz96_sequential_solve_equals_parallel(native_lib):
+    """solve(sequential=True): the whole grid as ONE chunk of the tile kernels (no tree) against the chunked run"""
+    import pof.ivp
+    from pof.solver import solve
+
+    ivp = pof.ivp.lorenz96(tmax=0.5, d=8)
+    ts = np.linspace(ivp.t0, ivp.tmax, 300)
+    a, ia = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=100)
+    b, ib = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=100, sequential=True)
+    torch.cuda.synchronize()
+    assert abs(ia["iterations"] - ib["iterations"]) <= 1
+    assert (a.mean - b.mean).abs().max().item() <= 1e-8 * a.mean.abs().max().item()
+
+
 # ---- last on purpose: the opt-in register-resident Householder sweeps (POF_B200_TILE_SWEEP=reg, DESIGN.md 2.4).  The
 # default (shared-memory sweeps) is what every test above ran.
 @pytest.mark.parametrize("name,kw,N,q,L", [("fitzhughnagumo", {}, 100, 3, 7), ("rigid_body", {}, 256, 3, 8),
