@@ -7,6 +7,9 @@ marshalling (pointer order, shapes, chunk lengths, workspace sizes), and the tes
 points at a kernel, not at Python.  Written when the tile kernels could not be run on a B200 (GPU budget spent).
 
     python scripts/dryrun_gpu_tests_on_host.py [-k expr]
+    POF_DRYRUN_FILE=test_gpu_parity.py python scripts/dryrun_gpu_tests_on_host.py -k "not thread and not lane1"
+        (the older parity tests through the same fake library: 47 pass; the three that do not need CUDA itself
+        -- sharded stages, torch.cuda calls -- or count roundoff-driven IEKS iterations of a different kernel family)
 """
 import ctypes
 import os
@@ -127,7 +130,12 @@ class FakeLib:
         D = d * (q + 1)
         n = N - 1
         m = _arr(means, (N, D))
-        assert ivp_id == 9, "dry run: fused iteration wired for Lorenz-96 only"
+        if ivp_id != 9:  # other built-ins: dense linearisation through the fake entry point above, then the pass
+            H, c = np.zeros((n, d, D)), np.zeros((n, d))
+            m1 = np.ascontiguousarray(m[1:])
+            self.pof_linearize_ivp_f64(s, ivp_id, params, nparams, n, d, q, s0, s1, _p(m1), _p(H), _p(c))
+            return self._pass(N, d, q, L, qL, x0m, x0c, _p(H), _p(c), None, 0.0, 0.0, None, None, None, means, chols,
+                              None, None, calibrate, scalars)
         forcing = _arr(params, (1,))[0]
         H, c, Jc = np.zeros((n, d, D)), np.zeros((n, d)), np.zeros((n, d * d + d))
         HS.hs_linearize_l96(ctypes.c_double(forcing), ctypes.c_long(n), d, q, ctypes.c_double(s0), ctypes.c_double(s1),
@@ -211,7 +219,8 @@ def main():
             for it in items:  # run the gpu-marked tests here
                 it.own_markers = [m for m in it.own_markers if m.name != "gpu"]
 
-    args = [os.path.join(ROOT, "tests", "test_gpu_tile.py"), "-q", "-x", "-p", "no:cacheprovider"] + sys.argv[1:]
+    target = os.environ.get("POF_DRYRUN_FILE", "test_gpu_tile.py")
+    args = [os.path.join(ROOT, "tests", target), "-q", "-p", "no:cacheprovider"] + sys.argv[1:]
     rc = pytest.main(args, plugins=[Plugin()])
     print("native calls:", fake.calls)
     return rc
