@@ -182,6 +182,16 @@ int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* s
 int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
                                double* state_out, double* scratch);
 
+/* Initial linearisation trajectory init="prior" (the default of pof.solver.solve) -- replaces
+ *   pof.initialization.prior_init   pof/initialization.py:66-89  (get_initial_trajectory, convenience.py:88-90):
+ * row 0 = x0 = (m0, 0); row k >= 1 = one prediction of x0 over the step size ts[k] (the ABSOLUTE time: the reference
+ * passes steps = ts[1:]) with the non-preconditioned IWP model, in non-preconditioned coordinates:
+ *   means[k] = P_k F PI_k m0,  chols[k] = tria([0, P_k QL]) = -P_k QL (LAPACK sign convention).
+ * ts (N) device, m0 (D) device (the Taylor-mode initial mean, NOT preconditioned), qL_host as above;
+ * means (N,D) out; chols (N,D,D) out or NULL (only the means feed the first linearisation). */
+int pof_prior_init_f64(pof_stream_t s, int64_t N, int d, int q, const double* qL_host, const double* ts,
+                       const double* m0, double* means, double* chols);
+
 /* Final calibration + projection -- replaces pof/solver.py:66-71 (`chol *= sqrt(ssq)`; ys = E0 states):
  * ymean (N,d) = scale0 * means[:, b*(q+1)],  ychol (N,d,D) = mult * scale0 * chols[:, b*(q+1), :]. */
 int pof_project_f64(pof_stream_t s, int64_t N, int d, int q, double scale0, const double* mult_dev,

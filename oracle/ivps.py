@@ -43,7 +43,7 @@ def _make(name, exprs_fn, y0, t0, tmax):
                 cur = cur.jacobian(sp.Matrix(ys)) * fvec
         return np.array(rows, dtype=np.float64)
 
-    return IVP(name=name, f=f, jac=jacf, y0=y0, t0=float(t0), tmax=float(tmax), taylor=taylor)
+    return IVP(name=name, f=f, jac=jacf, y0=y0, t0=float(t0), tmax=float(tmax), taylor=taylor, exprs=tuple(exprs))
 
 
 def logistic(t0=0.0, tmax=10.0, y0=None):

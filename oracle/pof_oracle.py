@@ -52,6 +52,7 @@ class IVP(NamedTuple):
     t0: float
     tmax: float
     taylor: Callable  # taylor(order) -> (order+1, d) derivatives y^{(k)}(t0)
+    exprs: tuple = None  # the SymPy right-hand sides in the symbols y0..y{d-1} (oracle/threaded.py vectorises them)
 
     @property
     def t_span(self):
@@ -195,9 +196,39 @@ def coarse_ekf_init(ivp, order, ts, N=10):
     return MVNSqrt(out.mean[idxs], out.chol[idxs])
 
 
+def prior_init(ivp: IVP, order, ts):
+    """pof/initialization.py:75-89 (`prior_init` -> `_prior_init`, :66-72): every row k >= 1 is ONE prediction of x0
+    with the non-preconditioned model of step size ts[k] -- the ABSOLUTE time, not a grid spacing -- (quirk Q6:
+    `discretize_transitions(iwp, steps=ts[1:])`, transitions.py:71-77, 91-99):
+        mean_k = (P_k F PI_k) m0,   chol_k = tria([(P_k F PI_k) L0, P_k QL])   (sequential_filtsmooth/filter.py:60-67)
+    and row 0 is x0 itself.  The result is in NON-preconditioned coordinates (convenience.py:88-90 applies no PI)."""
+    ts = np.asarray(ts, dtype=np.float64)
+    x0 = taylor_mode_init(ivp, order)
+    d = ivp.y0.shape[0]
+    F, QL = preconditioned_discretize(d, order)
+    steps = ts[1:]
+    n = steps.shape[0]
+    D = x0.mean.shape[0]
+    Fk = np.empty((n, D, D))
+    QLk = np.empty((n, D, D))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k in range(n):
+            P, PI = nordsieck_preconditioner(d, order, steps[k])
+            Fk[k] = P @ F @ PI
+            QLk[k] = P @ QL
+        means = np.einsum("nij,j->ni", Fk, x0.mean)
+        finite = np.isfinite(QLk).all(axis=(1, 2)) & np.isfinite(Fk).all(axis=(1, 2))
+        chols = np.full((n, D, D), np.nan)
+        if finite.any():
+            chols[finite] = tria(np.concatenate([Fk[finite] @ x0.chol, QLk[finite]], axis=-1))
+    return MVNSqrt(np.concatenate([x0.mean[None], means]), np.concatenate([x0.chol[None], chols]))
+
+
 def get_initial_trajectory(setup, method="constant"):
-    """pof/convenience.py:76-92 ('constant' and 'coarse'; 'prior' is restated on the host side of the product)."""
+    """pof/convenience.py:76-92."""
     PI = setup["PI"]
+    if method == "prior":
+        return prior_init(setup["ivp"], setup["order"], setup["ts"])
     if method == "coarse":
         st = coarse_ekf_init(setup["ivp"], setup["order"], setup["ts"], N=100)
         return MVNSqrt(st.mean @ PI.T, np.einsum("ij,njk->nik", PI, st.chol))

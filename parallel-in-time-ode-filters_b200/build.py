@@ -59,13 +59,19 @@ def build(force=False, verbose=False):
         if verbose:
             print("up to date:", LIB)
         return LIB
+    # object files are reused only if they were compiled with exactly these flags (a sidecar file per build directory)
+    # and are newer than every source / header; otherwise everything is recompiled
+    flags_file = os.path.join(OBJ, "nvcc_flags.txt")
+    flags_now = " ".join(NVCC_FLAGS)
+    flags_same = os.path.exists(flags_file) and open(flags_file).read().strip() == flags_now
     jobs = []
     objs = []
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(op)
-        if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr_time):
+        if (force or not flags_same or not os.path.exists(op)
+                or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr_time)):
             jobs.append((sp, op))
 
     def run(job):
@@ -81,7 +87,10 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
-    if jobs or force or not os.path.exists(LIB):
+    with open(flags_file, "w") as fh:
+        fh.write(flags_now + "\n")
+    # the digest differs from the library's (or there is no library): always relink
+    if True:
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -387,6 +387,44 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// init="prior" (reference pof/initialization.py:66-89): row k >= 1 is ONE prediction of x0 = (m0, 0) over the step size
+// ts[k] with the non-preconditioned model P_k F PI_k, P_k QL (transitions.py:53-77):
+//   mean_k = P_k F (PI_k m0),  chol_k = tria([0, P_k QL]) = -P_k QL  (LAPACK's sign convention; the factor is
+// lower triangular already), row 0 = x0.  One thread per (row, state component); the literal P F PI product is kept
+// (ts[k] = 0 gives NaN exactly like the reference's 0 * inf).
+__global__ void __launch_bounds__(256)
+    k_prior_init(long N, int d, int q, const double* __restrict__ ts, const double* __restrict__ m0, QLParam ql,
+                 double* __restrict__ means, double* __restrict__ chols) {
+  const int Q1 = q + 1, D = d * Q1;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * D) return;
+  const long k = idx / D;
+  const int r = (int)(idx - k * D), blk = r / Q1, i = r - blk * Q1;
+  if (k == 0) {
+    means[r] = m0[r];
+    if (chols)
+      for (int c = 0; c < D; ++c) chols[(long)r * D + c] = 0.0;
+    return;
+  }
+  const double t = fabs(ts[k]);
+  double fact[6];
+  fact[0] = 1.0;
+  for (int p = 1; p <= q; ++p) fact[p] = fact[p - 1] * p;
+  // sv_j = t^(q-j+1/2) / (q-j)!,  svi_j = t^-(q-j+1/2) (q-j)!
+  double acc = 0.0;
+  for (int j = i; j < Q1; ++j) {
+    const double svi = pow(t, -((double)(q - j) + 0.5)) * fact[q - j];
+    acc = fma(binom(q - i, j - i), svi * m0[blk * Q1 + j], acc);
+  }
+  const double sv = pow(t, (double)(q - i) + 0.5) / fact[q - i];
+  means[k * D + r] = sv * acc;
+  if (chols) {
+    double* row = chols + (k * D + r) * D;
+    for (int c = 0; c < D; ++c) row[c] = 0.0;
+    for (int j = 0; j <= i; ++j) row[blk * Q1 + j] = -sv * ql.v[i * Q1 + j];
+  }
+}
+
 // 16 independent FMA chains per thread: saturates the FP64 pipe
 __global__ void __launch_bounds__(256) k_dfma_peak(int iters, double* __restrict__ sink) {
   double a[16];
@@ -1272,6 +1310,16 @@ int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* s
   const int smem = coop_ws_doubles(D) * (int)sizeof(double);
   POF_CK(set_smem(k_smooth_chain, smem));
   k_smooth_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
+  return (int)cudaGetLastError();
+}
+
+int pof_prior_init_f64(pof_stream_t s, int64_t N, int d, int q, const double* qL_host, const double* ts,
+                       const double* m0, double* means, double* chols) {
+  if (N < 1 || d < 1 || q < 1 || q > 5) return POF_E_ARG;
+  QLParam ql;
+  for (int i = 0; i < 36; ++i) ql.v[i] = (i < (q + 1) * (q + 1)) ? qL_host[i] : 0.0;
+  const long total = (long)N * d * (q + 1);
+  k_prior_init<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)s>>>(N, d, q, ts, m0, ql, means, chols);
   return (int)cudaGetLastError();
 }
 

@@ -80,6 +80,7 @@ def _load():
         "pof_filter_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_prior_init_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_profile_enable": (None, [_c_int]),
         "pof_profile_read": (_c_int, [_c_dp, _c_dp]),
         "pof_launches_per_pass": (_c_i64, [_c_i64, _c_int, _c_int, _c_i64]),
@@ -100,7 +101,7 @@ EXPORTED = [
     "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_linearize_ivp_compact_f64",
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
     "pof_project_f64", "pof_profile_enable", "pof_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops",
-    "pof_linear_filtsmooth_general_f64", "pof_supported_tile", "pof_default_chunk_len_tile",
+    "pof_linear_filtsmooth_general_f64", "pof_supported_tile", "pof_default_chunk_len_tile", "pof_prior_init_f64",
 ]
 
 
@@ -144,23 +145,37 @@ def sm_count(device=None):
 
 
 class Workspace:
-    """Caller-owned scratch memory for one problem shape (N, d, q, chunk_len) on one device."""
+    """Caller-owned scratch memory for one problem shape (N, d, q, chunk_len) on one device.
+
+    Ownership rules (a pass writes GBs into this buffer, so a dangling pointer is silent corruption):
+      * anything that bakes `buf.data_ptr()` into a CUDA graph (GraphedIteration, GraphedCall users) or keeps using it
+        across calls (CudaBackend) OWNS its Workspace object -- create it with `Workspace(...)` and keep the reference;
+      * `Workspace.get` is a small per-(shape, device, stream) cache for one-off eager calls.  Two passes on different
+        streams never share a buffer; eviction only drops the cache's own reference (torch's stream-ordered caching
+        allocator keeps the memory valid for kernels already queued on the stream that used it).
+    """
 
     _cache = {}
+    _CACHE_MAX = 4
 
     def __init__(self, N, d, q, chunk_len, device):
         self.N, self.d, self.q, self.chunk_len = int(N), int(d), int(q), int(chunk_len)
         self.nbytes = int(LIB.pof_workspace_bytes(self.N, self.d, self.q, self.chunk_len))
         self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
 
+    def matches(self, N, d, q, chunk_len):
+        return (self.N, self.d, self.q, self.chunk_len) == (int(N), int(d), int(q), int(chunk_len))
+
     @classmethod
     def get(cls, N, d, q, chunk_len, device):
-        key = (int(N), int(d), int(q), int(chunk_len), str(device))
-        ws = cls._cache.get(key)
+        stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+        key = (int(N), int(d), int(q), int(chunk_len), str(device), int(stream))
+        ws = cls._cache.pop(key, None)
         if ws is None:
-            if len(cls._cache) > 4:
-                cls._cache.clear()
-            ws = cls._cache[key] = cls(N, d, q, chunk_len, device)
+            while len(cls._cache) >= cls._CACHE_MAX:
+                cls._cache.pop(next(iter(cls._cache)))  # least recently used; holders keep their own reference
+            ws = cls(N, d, q, chunk_len, device)
+        cls._cache[key] = ws  # most recently used last
         return ws
 
 

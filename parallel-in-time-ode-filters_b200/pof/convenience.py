@@ -44,14 +44,14 @@ def set_up_solver(*, f, y0, ts, order):
     )
     om = NonlinearModel(om_f)
 
-    x0 = init.taylor_mode_init(f, y0_h, order)
+    x0_raw = init.taylor_mode_init(f, y0_h, order)
     PI_t = tt(PI)
-    x0 = MVNSqrt(PI_t @ x0.mean.to(dev), PI_t @ x0.chol.to(dev))
+    x0 = MVNSqrt(PI_t @ x0_raw.mean.to(dev), PI_t @ x0_raw.chol.to(dev))
 
     return {
         "f": f, "y0": y0_h, "ts": ts_h, "dtm": TransitionModel(tt(F), tt(QL)), "om": om, "x0": x0,
         "E0": E0_t, "P": tt(P), "PI": PI_t, "order": order, "iwp": iwp,
-        "_qL": np.ascontiguousarray(qL), "_scale0": float(sv[0]), "_device": dev,
+        "_qL": np.ascontiguousarray(qL), "_scale0": float(sv[0]), "_device": dev, "_x0_raw": x0_raw,
     }
 
 
@@ -82,18 +82,24 @@ def set_up_solver_no_precond(*, f, y0, ts, order):
     }
 
 
-def get_initial_trajectory(setup, method="prior"):
-    """reference convenience.py:76-92"""
+def get_initial_trajectory(setup, method="prior", *, means_only=False):
+    """reference convenience.py:76-92.  Everything is built on the device; `means_only` (used by `solve`: only the
+    means feed the first linearisation) skips the (N,D,D) Cholesky factors (`chol` is then None)."""
     f, y0, order, ts = setup["f"], setup["y0"], setup["order"], setup["ts"]
     PI, dev = setup["PI"], setup["_device"]
     if method == "coarse":
         st = init.coarse_ekf_init(y0=y0, order=order, ts=ts, f=f, N=100)
-        return MVNSqrt((st.mean.to(dev) @ PI.T).contiguous(), torch.einsum("ij,njk->nik", PI, st.chol.to(dev)))
+        chol = None if means_only else torch.einsum("ij,njk->nik", PI, st.chol.to(dev))
+        return MVNSqrt((st.mean.to(dev) @ PI.T).contiguous(), chol)
     elif method == "constant":
-        st = init.constant_init(y0=y0, order=order, ts=ts, f=f)
-        return MVNSqrt((st.mean.to(dev) @ PI.T).contiguous(), st.chol.to(dev))  # PI @ 0 = 0
+        N = len(ts)
+        row = init.constant_init(y0=y0, order=order, ts=ts[:1], f=f).mean.to(dev)  # (1, D): every row is the same
+        means = (row @ PI.T).expand(N, -1).contiguous()
+        D = means.shape[1]
+        chol = None if means_only else torch.zeros((N, D, D), dtype=torch.float64, device=dev)  # PI @ 0 = 0
+        return MVNSqrt(means, chol)
     elif method == "prior":
-        st = init.prior_init(f=f, y0=y0, order=order, ts=ts)
-        return MVNSqrt(st.mean.to(dev).contiguous(), st.chol.to(dev).contiguous())
+        return init.prior_init(f=f, y0=y0, order=order, ts=ts, device=dev, means_only=means_only,
+                               x0=setup.get("_x0_raw"))
     else:
         raise Exception(f"method={method} not found")

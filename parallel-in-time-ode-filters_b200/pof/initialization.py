@@ -6,7 +6,7 @@ forward-mode jvps: y^(0) = y0, y^(k+1) = d/dt y^(k) = J_{y^(k)}(y) f(y).  One-of
 import numpy as np
 import torch
 
-from .transitions import IWP, nordsieck_preconditioner, preconditioned_discretize
+from .transitions import IWP
 from .utils import MVNSqrt
 
 
@@ -51,25 +51,33 @@ def constant_init(*, y0, order, ts, f=True):
     return MVNSqrt(traj, torch.zeros((N, D, D), dtype=torch.float64))
 
 
-def prior_init(*, f, y0, order, ts):
-    """reference initialization.py:75-89, including its quirk: the step sizes are the absolute times ts[1:], and the
-    trajectory is returned in NON-preconditioned coordinates.  Only the means feed the first linearisation."""
-    x0 = taylor_mode_init(f, y0, order)
+def prior_init(*, f, y0, order, ts, device=None, means_only=False, x0=None):
+    """reference initialization.py:66-89, including its quirk: the step sizes are the absolute times ts[1:], and the
+    trajectory is returned in NON-preconditioned coordinates.  Row k is closed form (one prediction of x0 = (m0, 0)),
+    evaluated by the CUDA kernel `pof_prior_init_f64` (one thread per row entry); only the means feed the first
+    linearisation, so `solve` asks for `means_only`."""
+    import ctypes  # noqa: F401
+
+    from . import _native as nat
+    from .transitions import preconditioned_discretize_1d
+
+    if x0 is None:  # (set_up_solver has computed it already: `setup["_x0_raw"]`)
+        x0 = taylor_mode_init(f, y0, order)
     d = int(_cpu64(y0).shape[0])
     iwp = IWP(num_derivatives=order, wiener_process_dimension=d)
-    F, QL = preconditioned_discretize(iwp)
-    ts = np.asarray(_cpu64(ts))
-    N = len(ts)
+    _, qL = preconditioned_discretize_1d(iwp)
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    ts_d = torch.as_tensor(np.asarray(_cpu64(ts)), dtype=torch.float64).to(dev).contiguous()
+    N = ts_d.shape[0]
     D = x0.mean.shape[0]
-    means = np.empty((N, D))
-    chols = np.zeros((N, D, D))
-    m0 = x0.mean.numpy()
-    means[0] = m0
-    for k, dt in enumerate(ts[1:]):
-        P, PI = nordsieck_preconditioner(iwp, dt)
-        means[k + 1] = P @ F @ PI @ m0
-        chols[k + 1] = P @ QL
-    return MVNSqrt(torch.from_numpy(means), torch.from_numpy(chols))
+    m0 = x0.mean.to(dev).contiguous()
+    means = torch.empty((N, D), dtype=torch.float64, device=dev)
+    chols = None if means_only else torch.empty((N, D, D), dtype=torch.float64, device=dev)
+    qLh, qLp = nat.host_doubles(qL)
+    nat.require_cuda(ts_d, m0, means, chols)
+    nat.check(nat.LIB.pof_prior_init_f64(nat.stream_ptr(), N, d, order, qLp, nat.ptr(ts_d), nat.ptr(m0),
+                                         nat.ptr(means), nat.ptr(chols)), "pof_prior_init_f64")
+    return MVNSqrt(means, chols)
 
 
 def coarse_ekf_init(*, f, y0, order, ts, N=10):

@@ -46,7 +46,7 @@ def _noise(dom: AffineModel):
 
 
 def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_len=None, fmeans=None, fchols=None,
-             scalars=None, cholR=None, dense=None):
+             scalars=None, cholR=None, dense=None, ws=None):
     """One filter+smoother pass on device buffers (the call `solve` makes every iteration).  cholR (n,d,d): noisy
     observations; dense = (F (n,D,D), QL (n,D,D)): general per-step transition models -- both served by the
     large-state kernels (`pof_linear_filtsmooth_general_f64`)."""
@@ -57,7 +57,10 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
     dev = means_io.device
     if chunk_len is None:
         chunk_len = (nat.default_chunk_len_tile if general else nat.default_chunk_len)(N, d, q, dev.index)
-    ws = nat.Workspace.get(N, d, q, chunk_len, dev)
+    if ws is None:
+        ws = nat.Workspace.get(N, d, q, chunk_len, dev)
+    elif not ws.matches(N, d, q, chunk_len):
+        raise nat.NativeError("workspace was created for a different problem shape")
     if scalars is None:
         scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
     qLh, qLp = nat.host_doubles(qL)
@@ -77,7 +80,7 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
     return scalars
 
 
-def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len=None, scalars=None):
+def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len=None, scalars=None, ws=None):
     """One fused IEKS iteration for a built-in IVP (linearise + pass, `pof_ieks_iteration_f64`): the body of the
     reference's while loop (pof/solver.py:48-55 -> pof/step.py:33-45).  `lin` is `om.f._pof_lin`."""
     N = means_io.shape[0]
@@ -86,7 +89,10 @@ def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len
     dev = means_io.device
     if chunk_len is None:
         chunk_len = nat.default_chunk_len(N, d, q, dev.index)
-    ws = nat.Workspace.get(N, d, q, chunk_len, dev)
+    if ws is None:
+        ws = nat.Workspace.get(N, d, q, chunk_len, dev)
+    elif not ws.matches(N, d, q, chunk_len):
+        raise nat.NativeError("workspace was created for a different problem shape")
     if scalars is None:
         scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
     ivp_id, params = lin["builtin"]
@@ -107,7 +113,12 @@ class GraphedIteration:
 
     def __init__(self, x0, qL, lin, means, chols, scalars, *, calibrate=True, chunk_len=None):
         self.args = (x0, qL, lin, means, chols)
-        self.kw = dict(calibrate=calibrate, chunk_len=chunk_len, scalars=scalars)
+        N, dev = means.shape[0], means.device
+        if chunk_len is None:
+            chunk_len = nat.default_chunk_len(N, lin["d"], lin["q"], dev.index)
+        # the graph bakes the workspace address in: this object owns the workspace for as long as it lives
+        self.ws = nat.Workspace(N, lin["d"], lin["q"], chunk_len, dev)
+        self.kw = dict(calibrate=calibrate, chunk_len=chunk_len, scalars=scalars, ws=self.ws)
         self.graph = None
 
     def _eager(self):
@@ -158,14 +169,18 @@ class GraphedCall:
         return self.out
 
 
-def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None):
-    """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq)"""
+def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None, info=None):
+    """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq).
+    `info` (optional dict) receives the pass's full scalar vector (`info["scalars"]`, indices `_native.S_*`, e.g. the
+    QR-sign-invariant sigma^2 `S_SSQ_PROPER` that the reference does not return)."""
     n, d, q, D, qL, dense = _model_dims(linear_transitions, linear_observations)
     dev = linear_observations.H.device
     means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
     chols = torch.empty((n + 1, D, D), dtype=torch.float64, device=dev)
     sc = run_pass(x0, qL, linear_observations.H.contiguous(), linear_observations.b.contiguous(), means, chols, d=d,
                   q=q, calibrate=False, chunk_len=chunk_len, cholR=_noise(linear_observations), dense=dense)
+    if info is not None:
+        info["scalars"] = sc
     return MVNSqrt(means, chols), sc[nat.S_NLL], sc[nat.S_OBJ], sc[nat.S_SSQ]
 
 

@@ -39,7 +39,7 @@ class CudaBackend:
         self.d, self.q, self.n_loc = d, q, n_loc
         self.device = device
         self.chunk_len = int(chunk_len or nat.default_chunk_len(n_loc + 1, d, q, device.index))
-        self.ws = nat.Workspace.get(n_loc + 1, d, q, self.chunk_len, device)
+        self.ws = nat.Workspace(n_loc + 1, d, q, self.chunk_len, device)  # owned: graph replays bake its address in
         self.qL, self.qLp = nat.host_doubles(qL)
         D = d * (q + 1)
         self.scratch = torch.empty(D + D * D, dtype=torch.float64, device=device)
@@ -215,7 +215,7 @@ def solve_sharded(*, f, y0, ts, order, init="constant", calibrate=True, maxiters
     sp.backend.set_compact(lin["scale0"], lin["scale1"])
     r0 = 0 if sp.has_row0 else sp.k_lo + 1
     rows = slice(r0, sp.k_hi + 1)
-    full = get_initial_trajectory(setup, method=init)
+    full = get_initial_trajectory(setup, method=init, means_only=True)
     means = full.mean[rows].contiguous().clone()
     del full
     chols = torch.empty((sp.rows, D, D), dtype=torch.float64, device=dev)

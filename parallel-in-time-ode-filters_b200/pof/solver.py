@@ -19,9 +19,9 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
     x0, om, dev = setup["x0"], setup["om"], setup["_device"]
     lin = om.f._pof_lin
     d, q = lin["d"], order
-    states = get_initial_trajectory(setup, method=init)
+    states = get_initial_trajectory(setup, method=init, means_only=True)
 
-    means = states.mean.contiguous().clone()
+    means = states.mean.contiguous()
     N, D = means.shape
     n = N - 1
     chols = torch.empty((N, D, D), dtype=torch.float64, device=dev)
@@ -61,6 +61,10 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
             sc[nat.S_NOT_CLOSE])
         k += 1
 
+    if sequential:
+        # the reference's sequential pass returns ell = +sum log-likelihood where the parallel one returns the
+        # negative sum (quirk Q7: sequential_filtsmooth/filter.py:91 vs parallel_filtsmooth/filter.py:101)
+        nll = -nll
     info_dict = {
         "iterations": k, "nll": nll, "obj": obj, "sigma_squared": ssq, "calibrated": False,
         "sigma_squared_proper": float(sc[nat.S_SSQ_PROPER]),

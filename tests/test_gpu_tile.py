@@ -22,9 +22,18 @@ def _pair(name, **kw):
     return getattr(pof.ivp, name)(**kw), getattr(oivps, name)(**kw)
 
 
+_INFO = {}  # linear_filtsmooth(..., info=_INFO) leaves the pass's scalar vector here (sigma^2 proper is not returned)
+
+
 def _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=False, full_state=True):
-    oout, onll, oobj, ossq, _ = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom)
-    oout2, nll2, obj2, _, _ = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom, scan=O.sequential_scan)
+    oout, onll, oobj, ossq, ossqp = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom)
+    oout2, nll2, obj2, _, ossqp2 = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom, scan=O.sequential_scan)
+    # sign-invariant sigma^2: 1e-8, with the oracle's own schedule band capped at 1e-6
+    from pof import _native as nat
+
+    ssqp = float(_INFO["scalars"][nat.S_SSQ_PROPER])
+    assert abs(ssqp - ossqp) <= max(1e-8 * abs(ossqp), min(10 * abs(ossqp2 - ossqp), 1e-6 * abs(ossqp))), (
+        ssqp, ossqp, ossqp2)
     E0 = osetup["E0"]
     m, Lc = out.mean.cpu().numpy(), out.chol.cpu().numpy()
     assert np.isfinite(m).all() and np.isfinite(Lc).all()
@@ -73,7 +82,7 @@ def test_tile_family_on_the_reference_problems(native_lib, monkeypatch, tree, na
     setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
     states = get_initial_trajectory(setup, method="constant")
     dom = linearize_at_previous_states(setup["om"], states)
-    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L, info=_INFO)
     torch.cuda.synchronize()
     osetup = O.set_up_solver(oivp, ts, q)
     ost = O.get_initial_trajectory(osetup)
@@ -99,7 +108,7 @@ def test_noisy_observations_match_oracle(native_lib, name, kw, N, q, L):
     rng = np.random.default_rng(1)
     R = np.tril(0.05 * rng.standard_normal((N - 1, d, d))) + 0.1 * np.eye(d)
     dom = AffineModel(dom.H, dom.b, torch.as_tensor(R, device=dom.H.device))
-    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L, info=_INFO)
     torch.cuda.synchronize()
     osetup = O.set_up_solver(oivp, ts, q)
     ost = O.get_initial_trajectory(osetup)
@@ -130,7 +139,7 @@ def test_lorenz96_d16_q3_pass_matches_oracle(native_lib, monkeypatch, N, L, swee
     np.testing.assert_allclose(setup["x0"].mean.cpu().numpy(), osetup["x0"].mean, rtol=1e-11, atol=1e-11)
     np.testing.assert_allclose(dom.H.cpu().numpy(), odom.H, rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(dom.b.cpu().numpy(), odom.b, rtol=1e-12, atol=1e-12)
-    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L, info=_INFO)
     torch.cuda.synchronize()
     _check_pass(out, nll, obj, ssq, osetup, odom, N)
 
@@ -148,7 +157,7 @@ def test_lorenz96_fused_iteration_equals_dense_pass(native_lib):
     setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=3)
     states = get_initial_trajectory(setup, method="constant")
     dom = linearize_at_previous_states(setup["om"], states)
-    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, info=_INFO)
     means = states.mean.contiguous().clone()
     chols = torch.empty((N, 64, 64), dtype=torch.float64, device=means.device)
     sc = run_iteration(setup["x0"], setup["_qL"], setup["om"].f._pof_lin, means, chols, calibrate=False)
@@ -235,7 +244,7 @@ def test_nonuniform_grid_general_transition_models(native_lib, name, q, N, noisy
         rng = np.random.default_rng(2)
         R = np.tril(0.05 * rng.standard_normal((N - 1, d, d))) + 0.1 * np.eye(d)
         dom = AffineModel(dom.H, dom.b, torch.as_tensor(R, device=dev))
-    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, info=_INFO)
     torch.cuda.synchronize()
 
     F0, QL0 = O.preconditioned_discretize(d, q)
@@ -311,7 +320,7 @@ def test_tile_register_sweeps_match_oracle(native_lib, monkeypatch, name, kw, N,
     setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
     states = get_initial_trajectory(setup, method="constant")
     dom = linearize_at_previous_states(setup["om"], states)
-    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L)
+    out, nll, obj, ssq = linear_filtsmooth(setup["x0"], setup["dtm"], dom, chunk_len=L, info=_INFO)
     torch.cuda.synchronize()
     osetup = O.set_up_solver(oivp, ts, q)
     ost = O.get_initial_trajectory(osetup)
