@@ -5,6 +5,10 @@
  * Conventions: all pointers are DEVICE pointers unless stated "host"; fp64, row-major, contiguous, caller-owned;
  * nothing is allocated inside (the caller passes a workspace); every call is stream-ordered and does not
  * synchronise; return value 0 = ok, >0 = cudaError_t, <0 = argument error (POF_E_*).
+ * No environment variables are read and there is no library-global mutable state: kernel-family choices are the
+ * explicit `flags` argument, and the only resources a pass needs beyond the workspace (a side stream + two events
+ * for the concurrent smoother up-sweep, optional timing events) live in a caller-owned context (pof_ctx_t).  Calls
+ * with distinct workspaces and distinct contexts (or ctx = NULL) are re-entrant from different host threads.
  *
  * Shapes: N time points, n = N-1 steps, ODE dimension d, IWP order q, state dimension D = d*(q+1), state
  * ordering [y1, y1', .., y1^(q), y2, ..] (reference pof/transitions.py:80-88).
@@ -19,6 +23,14 @@ extern "C" {
 #endif
 
 typedef void* pof_stream_t; /* cudaStream_t */
+typedef struct pof_ctx pof_ctx_t; /* opaque: side stream + events of one (concurrently running) pass */
+
+/* flags (bitwise or) */
+#define POF_F_FAMILY_TILE 1u    /* use the large-state kernels (one CTA per chunk / tree node) even where the
+                                   register-resident d <= 4, D <= 16 family exists (cross-checks, tests) */
+#define POF_F_TILE_SMEM_QR 2u   /* large-state kernels: shared-memory Householder sweeps instead of the register-
+                                   resident ones (A/B measurement; slower on B200) */
+#define POF_F_TREE_PER_LEVEL 4u /* one kernel launch per tree level instead of the dataflow sweeps (A/B measurement) */
 
 #define POF_E_UNSUPPORTED_DQ (-1) /* (d, q) combination not compiled in */
 #define POF_E_WORKSPACE (-2)      /* workspace too small */
@@ -37,6 +49,18 @@ enum {
   POF_NSCALARS = 8
 };
 
+/* segments of a pass for the optional device timing of a context */
+enum {
+  POF_SEG_FOLD = 0, /* filter phase 1: chunk -> filtering element                                   */
+  POF_SEG_FUP,      /* filter up-sweep incl. root (time-sharded stage A only)                        */
+  POF_SEG_FTREE,    /* filter tree: up-sweep + down-sweep on one GPU, down-sweep in sharded stage B  */
+  POF_SEG_SCAN,     /* filter phase 3: seeded square-root filter + backward kernels + statistics     */
+  POF_SEG_SUP,      /* chunk smoothing elements + smoother up-sweep (side stream, concurrent to scan)*/
+  POF_SEG_SDOWN,    /* smoother down-sweep                                                           */
+  POF_SEG_SMOOTH,   /* smoother phase 3: seeded square-root RTS recursion, objective, calibration    */
+  POF_SEG_COUNT
+};
+
 /* built-in vector fields (reference pof/ivp.py) for the fused f / Jacobian evaluation */
 enum {
   POF_IVP_LOGISTIC = 0,      /* ivp.py:7-14    params: none                     */
@@ -51,20 +75,29 @@ enum {
   POF_IVP_LORENZ96 = 9       /* synthetic larger-state problem (BASELINE config 5), params: forcing */
 };
 
-/* 1 if the (d, q) leaf kernels are compiled in */
+/* 1 if some kernel family serves (d, q); 1 if the large-state (CTA-per-chunk) family does (any d, 1 <= q <= 5,
+ * D = d (q+1) limited by the 227 KB of shared memory per CTA: D <= 64 at d = 16) */
 int pof_supported(int d, int q);
+int pof_supported_tile(int d, int q);
 
-/* measurement aids (bench.py): per-segment device timing with CUDA events on the launching stream, kernel-launch
- * count of one pass, and the device's FP64 FMA peak measured by a register-resident DFMA loop */
-void pof_profile_enable(int on);
-int pof_profile_read(double* ms_out /* 7 */, int64_t* count_out /* 7 */);
-int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len);
+/* Execution context (optional; NULL is valid everywhere and means: everything in line on the caller's stream).
+ * With a context the smoother's up-sweep of a pass runs on the context's side stream concurrently with the filter
+ * scan (fork / join through events: the pass stays stream-ordered on `s` and can be captured into a CUDA graph).
+ * Create it on the device the passes run on; one context per concurrently running pass. */
+int pof_ctx_create(pof_ctx_t** out);
+void pof_ctx_destroy(pof_ctx_t* ctx);
+/* measurement aid (bench.py): per-segment device time, CUDA events on the launching streams around each segment */
+void pof_ctx_profile_enable(pof_ctx_t* ctx, int on);
+int pof_ctx_profile_read(pof_ctx_t* ctx, double* ms_out /* POF_SEG_COUNT */, int64_t* count_out /* POF_SEG_COUNT */);
+
+/* kernel-launch count of one pass; the device's FP64 FMA peak measured by a register-resident DFMA loop */
+int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len, uint32_t flags);
 int pof_measure_dfma_tflops(pof_stream_t s, double* tflops_out /* host */);
 
-/* default chunk length (steps per thread) for a problem size, chosen to fill the GPU `sm_count` SMs */
-int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count);
+/* default chunk length (steps per chunk) for a problem size: fills the `sm_count` SMs with one wave of chunks */
+int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count, uint32_t flags);
 
-/* workspace bytes needed by pof_linear_filtsmooth_f64 / pof_ieks_* for the given chunk length */
+/* workspace bytes needed by pof_linear_filtsmooth_f64 / pof_ieks_* / pof_shard_* for the given chunk length */
 size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len);
 
 /* Batched associative operators on packed elements -- the reference's
@@ -73,8 +106,10 @@ size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len);
  * Packed layouts per element (doubles): filter [A D*D | b D | U D*D | eta D | Z D*D], smoother [g D | E D*D | D D*D].
  * e1, e2, out: (n, elem) arrays.  elem1 = earlier in time for the filter; for the smoother the reference calls the
  * operator on the reversed sequence, so elem1 = LATER in time.  One warp per element pair. */
-int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out);
-int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out);
+int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out,
+                           uint32_t flags);
+int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out,
+                           uint32_t flags);
 
 /* Fused linearisation for the built-in IVPs -- replaces vmap(linearize)(om, states[1:])
  *   pof/step.py:12-22, pof/observations.py:35-40 with om = E1 x - f(E0 x) (pof/convenience.py:26-28):
@@ -96,7 +131,8 @@ int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host,
  *   chols (N,D,D) or NULL: OUT smoothed Cholesky factors (lower triangular), times sqrt(sigma^2) if calibrate
  *   fmeans (N,D), fchols (N,D,D) or NULL: OUT filtered states (fchols are square-root factors, not triangular)
  *   scalars: OUT POF_NSCALARS doubles */
-int pof_linear_filtsmooth_f64(pof_stream_t s, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+int pof_linear_filtsmooth_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                              int64_t chunk_len, const double* qL_host,
                               const double* x0_mean, const double* x0_chol, const double* H, const double* c,
                               double* means, double* chols, double* fmeans, double* fchols, int calibrate,
                               double* scalars, void* ws, size_t ws_bytes);
@@ -110,24 +146,20 @@ int pof_linear_filtsmooth_f64(pof_stream_t s, int64_t N, int d, int q, int64_t c
  *   cholR  : lower-triangular factors of the observation covariances (the reference's regularised iterations,
  *            pof/observations.py:43-83); NULL = noiseless
  * D = d (q+1).  Served by the large-state ("tile") kernels for any (d, q) they support (pof_supported_tile);
- * chunk_len from pof_default_chunk_len_tile, workspace from pof_workspace_bytes. */
-int pof_linear_filtsmooth_general_f64(pof_stream_t s, int64_t N, int d, int q, int64_t chunk_len,
+ * chunk_len from pof_default_chunk_len(.., POF_F_FAMILY_TILE), workspace from pof_workspace_bytes. */
+int pof_linear_filtsmooth_general_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                                      int64_t chunk_len,
                                       const double* qL_host, const double* F, const double* QL, const double* x0_mean,
                                       const double* x0_chol, const double* H, const double* c, const double* cholR,
                                       double* means, double* chols, double* fmeans, double* fchols, int calibrate,
                                       double* scalars, void* ws, size_t ws_bytes);
-/* 1 if the CTA-per-chunk large-state kernels support (d, q) (any d, 1 <= q <= 5, D = d (q+1) limited by the 227 KB of
- * shared memory per CTA: D <= 64 at d = 16); their default chunk length (one chunk per resident CTA) */
-int pof_supported_tile(int d, int q);
-int64_t pof_default_chunk_len_tile(int64_t N, int d, int q, int sm_count);
-
 /* One fused IEKS iteration for a built-in IVP -- replaces the body of the reference's while loop,
  *   pof.step.ieks_step(om, dtm, x0, states)   pof/step.py:33-45   (called from pof/solver.py:48-55):
  * linearise at means[1:] (fused f / Jacobian, kept in the compact form [J_f | c] inside the workspace: the dense
  * (n,d,D) H is never materialised), filter + smoother pass, calibration, convergence reductions.
  * means (N,D): IN previous trajectory, OUT smoothed means; chols (N,D,D) or NULL; scalars as above. */
-int pof_ieks_iteration_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t N, int d, int q,
-                           int64_t chunk_len, const double* qL_host, double scale0, double scale1,
+int pof_ieks_iteration_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                           int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host, double scale0, double scale1,
                            const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
                            double* scalars, void* ws, size_t ws_bytes);
 
@@ -137,7 +169,8 @@ int pof_ieks_iteration_f64(pof_stream_t s, int ivp_id, const double* params_host
  * core of pof.solver.sequential_eks_solve (solver.py:76-96).  O(N) span by construction: one thread walks the grid
  * (baseline / cross-check path).  means (N,D), chols (N,D,D): OUT smoothed, uncalibrated.  scalars[POF_S_NLL] holds
  * +sum log-likelihood like the reference's sequential path (filter.py:91). */
-int pof_sequential_eks_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t N, int d, int q,
+int pof_sequential_eks_f64(pof_stream_t s, uint32_t flags, int ivp_id, const double* params_host, int nparams,
+                           int64_t N, int d, int q,
                            const double* qL_host, double scale0, double scale1, const double* x0_mean,
                            const double* x0_chol, double* means, double* chols, double* scalars, void* ws,
                            size_t ws_bytes);
@@ -156,30 +189,37 @@ int pof_sequential_eks_f64(pof_stream_t s, int ivp_id, const double* params_host
  *  stage C: smoother down-sweep from `seed` (D + D*D smoothed state at k_hi), smoother scan
  *           -> means/chols, `partials2` (2 doubles: obj sum, not-close count); the objective term that couples
  *           the first local state to the previous rank's last state is added by the rank that owns the step. */
-int pof_shard_stage_a_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+int pof_shard_stage_a_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host,
                           const double* H, const double* c, double* carry_f, void* ws, size_t ws_bytes);
-int pof_shard_stage_b_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+int pof_shard_stage_b_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host,
                           const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
                           double* carry_s, double* state_end, double* partials, void* ws, size_t ws_bytes);
 /* the same two stages reading the compact linearisation [J_f | c] (n_loc, d*d+d) written by
  * pof_linearize_ivp_compact_f64 instead of dense (H, c) */
 int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
                                   int q, double scale0, const double* means_t1, double* Jc);
-int pof_shard_stage_a_compact_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+int pof_shard_stage_a_compact_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host,
                                   const double* Jc, double scale0, double scale1, double* carry_f, void* ws,
                                   size_t ws_bytes);
-int pof_shard_stage_b_compact_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+int pof_shard_stage_b_compact_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host,
                                   const double* Jc, double scale0, double scale1, const double* state_in,
                                   double* fmeans, double* fchols, double* carry_s, double* state_end, double* partials,
                                   void* ws, size_t ws_bytes);
-int pof_shard_stage_c_f64(pof_stream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
+int pof_shard_stage_c_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host,
                           const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,
                           double* chols, double* partials2, void* ws, size_t ws_bytes);
 /* state <- op(state, elems[0]), op(.., elems[1]), ... (count packed filter elements, earlier first) */
-int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
+int pof_filter_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
+                               const double* elems,
                                double* state_out, double* scratch /* >= D+D*D doubles */);
 /* state <- smoothing op(state(later), elems[count-1]), ..., elems[0]  (elements in time order, applied last-first) */
-int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
+int pof_smooth_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
+                               const double* elems,
                                double* state_out, double* scratch);
 
 /* Initial linearisation trajectory init="prior" (the default of pof.solver.solve) -- replaces

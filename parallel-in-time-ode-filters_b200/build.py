@@ -12,8 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpof_b200.so")
 SOURCES = [
-    "pof_api.cu", "pof_leaf_d1.cu", "pof_leaf_d2.cu", "pof_leaf_d3.cu", "pof_leaf_d4.cu",
-    "pof_lane_d1.cu", "pof_lane_d2.cu", "pof_lane_d3.cu", "pof_lane_d4.cu",
+    "pof_api.cu", "pof_seq_d1.cu", "pof_seq_d2.cu", "pof_seq_d3.cu", "pof_seq_d4.cu",
     "pof_tree_a.cu", "pof_tree_b.cu", "pof_tree_c.cu",
     "pof_lane2_d1.cu", "pof_lane2_d2.cu", "pof_lane2_d3.cu", "pof_lane2_d4.cu",
     "pof_tile.cu",

@@ -1,10 +1,18 @@
-// C ABI (include/pof_b200.h) of the B200-native parallel-in-time IEKS pass, plus the kernels that are not
-// templated on (d, q): the tree sweeps over chunk carries (one warp per associative combine, pof_coop.cuh),
-// the deterministic scalar reductions, the fused vector-field/Jacobian linearisation for the built-in IVPs
-// and the final calibration + projection.
+// C ABI (include/pof_b200.h) of the B200-native parallel-in-time IEKS pass, plus the kernels that are not templated on
+// (d, q): deterministic scalar reductions, the fused vector-field/Jacobian linearisation for the built-in IVPs, the
+// prior initial trajectory, the final calibration + projection, and the orchestration of one pass:
+//
+//   fold (leaf)  ->  filter tree (ONE dataflow launch: up-sweep + down-sweep)  ->  scan (leaf)  ||  smoother up-sweep
+//   (side stream of the caller's context)  ->  smoother down-sweep (one dataflow launch)  ->  smooth (leaf)
+//
+// Kernel families: `lane2` (pof_lane2.cuh: G lanes per chunk, two rows per lane; d <= 4, D <= 16) with the
+// register-resident tree operators (pof_treelane.cuh), and `tile` (pof_tile.cuh: one CTA per chunk / tree node; any
+// (d, q) whose tiles fit shared memory, observation noise, general per-step models).  There is no other path.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "../../include/pof_b200.h"
 #include "pof_coop.cuh"
@@ -12,83 +20,32 @@
 #include "pof_launch.cuh"
 #include "pof_pipeline.cuh"
 
+// caller-owned execution context: the side stream on which the smoother's up-sweep runs concurrently with the filter
+// scan (fork/join through events, so a pass stays stream-ordered on the caller's stream and is capturable), and the
+// optional per-segment timing state.  One context per concurrently running pass; no library-global state.
+struct pof_ctx {
+  int dev = 0;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  // ---- per-segment device timing (bench.py): CUDA events recorded on the launching stream around each segment
+  static constexpr int MAXP = 4096;
+  bool prof_on = false;
+  cudaEvent_t ev[MAXP][2];
+  int seg[MAXP];
+  int created = 0, used = 0;
+  double acc[POF_SEG_COUNT] = {0};
+  long cnt[POF_SEG_COUNT] = {0};
+};
+
 namespace pof {
 
-// register-resident tree sweeps when 2D <= 32 (POF_B200_TREE_IMPL=generic forces the shared-memory kernels)
 static const TreeLaunch* tree_launch(int D) {
-  const char* e = getenv("POF_B200_TREE_IMPL");
-  if (e && (e[0] == 'g' || e[0] == 't')) return nullptr;  // generic (warp, shared memory) / tile (CTA per node)
   const TreeLaunch* t = tree_launch_a(D);
   if (!t) t = tree_launch_b(D);
   if (!t) t = tree_launch_c(D);
   return t;
 }
-
-// POF_B200_TREE_SWEEP=1: whole tree sweeps as single cooperative kernels with a grid barrier per level.  Measured on
-// B200 (N = 2^20, 14 levels): 0.51 ms per filter tree against 0.33 ms with one graph-replayed launch per level -- a
-// cooperative-groups grid barrier costs more than a kernel boundary inside a CUDA graph here, so the default stays
-// one launch per level.
-static bool tree_fused() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("POF_B200_TREE_SWEEP");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-// Side stream on which the smoother's up-sweep runs concurrently with the filter scan: its inputs (the chunk-level
-// smoothing elements) only depend on the fold and the filter down-sweep, and its ~14 latency-bound levels fit into
-// the registers / shared memory the scan leaves free on every SM.  One stream + two events per device, created on
-// first use (eagerly, i.e. before any graph capture); fork/join through events, so the pass stays stream-ordered on
-// the caller's stream and is capturable.  POF_B200_OVERLAP=0 disables it.
-struct SideStream {
-  cudaStream_t s2 = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  bool ok = false;
-};
-static SideStream* side_stream() {
-  static SideStream tab[64];
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("POF_B200_OVERLAP");
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStream& t = tab[dev];
-  if (!t.ok) {
-    if (cudaStreamCreateWithFlags(&t.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    t.ok = true;
-  }
-  return &t;
-}
-
-// thread-per-chunk reference kernels (pof_leaf.cuh)
-static const LeafLaunch* thread_launch(int d, int q) {
-  switch (d) {
-    case 1: return leaf_launch_d1(q);
-    case 2: return leaf_launch_d2(q);
-    case 3: return leaf_launch_d3(q);
-    case 4: return leaf_launch_d4(q);
-    default: return nullptr;
-  }
-}
-// lane-cooperative performance kernels (pof_lane.cuh); D <= 32
-static const LeafLaunch* lane_launch(int d, int q) {
-  if (d * (q + 1) > 32) return nullptr;
-  switch (d) {
-    case 1: return lane_launch_d1(q);
-    case 2: return lane_launch_d2(q);
-    case 3: return lane_launch_d3(q);
-    case 4: return lane_launch_d4(q);
-    default: return nullptr;
-  }
-}
-// two rows per lane (pof_lane2.cuh): the default where instantiated (D <= 16)
+// two rows per lane (pof_lane2.cuh): instantiated for d <= 4, D <= 16
 static const LeafLaunch* lane2_launch(int d, int q) {
   switch (d) {
     case 1: return lane2_launch_d1(q);
@@ -98,114 +55,30 @@ static const LeafLaunch* lane2_launch(int d, int q) {
     default: return nullptr;
   }
 }
-// POF_B200_LEAF_IMPL = thread | lane1 | lane2 selects a kernel family (debugging / cross-checks); default: lane2
-// where available (and the register-resident tree ops are not disabled), else lane1, else thread
-const LeafLaunch* leaf_launch(int d, int q) {
-  const char* e = getenv("POF_B200_LEAF_IMPL");
-  const bool want_tile = e && e[0] == 't' && e[1] == 'i';
-  if (want_tile) return tile_supported(d, q) ? tile_leaf_launch() : nullptr;
-  const bool want_thread = e && e[0] == 't';
-  const bool want_lane1 = e && e[0] == 'l' && e[1] == 'a' && e[2] == 'n' && e[3] == 'e' && e[4] == '1';
-  if (!want_thread) {
-    if (!want_lane1 && tree_launch(d * (q + 1)) != nullptr) {
-      const LeafLaunch* l2 = lane2_launch(d, q);
-      if (l2) return l2;
-    }
-    const LeafLaunch* l = lane_launch(d, q);
-    if (l) return l;
+// one-thread sequential EKS (pof_seq_kernels.cuh), d <= 4
+static const LeafLaunch* seq_launch(int d, int q) {
+  switch (d) {
+    case 1: return seq_launch_d1(q);
+    case 2: return seq_launch_d2(q);
+    case 3: return seq_launch_d3(q);
+    case 4: return seq_launch_d4(q);
+    default: return nullptr;
   }
-  if (const LeafLaunch* l = thread_launch(d, q)) return l;
-  // anything the (d, q)-templated families do not cover: the large-state tile family (D limited by shared memory)
+}
+// the kernel family that serves (d, q): lane2 where instantiated, else (or when POF_F_FAMILY_TILE asks for it) tile
+static const LeafLaunch* leaf_launch(int d, int q, unsigned flags) {
+  if (!(flags & POF_F_FAMILY_TILE)) {
+    if (const LeafLaunch* l2 = lane2_launch(d, q)) return l2;
+  }
   return tile_supported(d, q) ? tile_leaf_launch() : nullptr;
 }
+// tree operators that go with a leaf family: register-resident (with the lane2 leaves) or CTA-per-node tiles
+static const TreeLaunch* tree_for(const LeafLaunch* ll, int D, unsigned flags) {
+  if (ll->is_tile || (flags & POF_F_FAMILY_TILE)) return nullptr;
+  return tree_launch(D);
+}
 
-constexpr int TREE_WARPS = 4;  // max warps (= element pairs) per CTA in the tree kernels; fewer when D is large
-
-// ------------------------------------------------------------------------------------------------ tree sweeps
-// up:   parent[i] = op(child[2i], child[2i+1])           (copy if the second child is missing)
-__global__ void __launch_bounds__(TREE_WARPS * 32)
-    k_filter_up(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent, long nparent) {
-  extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= nparent) return;
-  Warp w;
-  const int FE = filter_elem_size(D);
-  const double* lc = child + 2 * gw * FE;
-  double* out = parent + gw * FE;
-  if (2 * gw + 1 < nchild)
-    filter_combine(w, D, lc, lc + FE, out, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
-  else
-    coop_copy(w, out, lc, FE);
-}
-// down (exclusive, state form): cin[2i] = pin[i] ; cin[2i+1] = op(state pin[i], cagg[2i])
-__global__ void __launch_bounds__(TREE_WARPS * 32)
-    k_filter_down(int D, const double* __restrict__ pin, long nparent, const double* __restrict__ cagg, long nchild,
-                  double* __restrict__ cin) {
-  extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= nparent) return;
-  Warp w;
-  const int FE = filter_elem_size(D), ST = state_size(D);
-  const double* p = pin + gw * ST;
-  coop_copy(w, cin + 2 * gw * ST, p, ST);
-  if (2 * gw + 1 < nchild)
-    filter_combine(w, D, p, cagg + 2 * gw * FE, cin + (2 * gw + 1) * ST,
-                   sm + (threadIdx.x >> 5) * coop_ws_doubles(D), true);
-}
-// smoother up: parent[i] = op(e1 = later = child[2i+1], e2 = earlier = child[2i])
-__global__ void __launch_bounds__(TREE_WARPS * 32)
-    k_smooth_up(int D, const double* __restrict__ child, long nchild, double* __restrict__ parent, long nparent) {
-  extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= nparent) return;
-  Warp w;
-  const int SE = smooth_elem_size(D);
-  const double* lc = child + 2 * gw * SE;
-  double* out = parent + gw * SE;
-  if (2 * gw + 1 < nchild)
-    smooth_combine(w, D, lc + SE, lc, out, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
-  else
-    coop_copy(w, out, lc, SE);
-}
-// smoother down (exclusive suffix, state form): cin[2i+1] = pin[i] ; cin[2i] = op(state pin[i], cagg[2i+1])
-__global__ void __launch_bounds__(TREE_WARPS * 32)
-    k_smooth_down(int D, const double* __restrict__ pin, long nparent, const double* __restrict__ cagg, long nchild,
-                  double* __restrict__ cin) {
-  extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= nparent) return;
-  Warp w;
-  const int SE = smooth_elem_size(D), ST = state_size(D);
-  const double* p = pin + gw * ST;
-  if (2 * gw + 1 < nchild) {
-    coop_copy(w, cin + (2 * gw + 1) * ST, p, ST);
-    smooth_combine(w, D, p, cagg + (2 * gw + 1) * SE, cin + 2 * gw * ST,
-                   sm + (threadIdx.x >> 5) * coop_ws_doubles(D), true);
-  } else {
-    coop_copy(w, cin + 2 * gw * ST, p, ST);
-  }
-}
-// batched operators (C-ABI test hooks / S3 seam): out[i] = op(e1[i], e2[i])
-__global__ void __launch_bounds__(TREE_WARPS * 32)
-    k_filter_combine_batched(int D, long n, const double* __restrict__ e1, const double* __restrict__ e2,
-                             double* __restrict__ out) {
-  extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= n) return;
-  Warp w;
-  const int FE = filter_elem_size(D);
-  filter_combine(w, D, e1 + gw * FE, e2 + gw * FE, out + gw * FE, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
-}
-__global__ void __launch_bounds__(TREE_WARPS * 32)
-    k_smooth_combine_batched(int D, long n, const double* __restrict__ e1, const double* __restrict__ e2,
-                             double* __restrict__ out) {
-  extern __shared__ double sm[];
-  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= n) return;
-  Warp w;
-  const int SE = smooth_elem_size(D);
-  smooth_combine(w, D, e1 + gw * SE, e2 + gw * SE, out + gw * SE, sm + (threadIdx.x >> 5) * coop_ws_doubles(D), false);
-}
+// ------------------------------------------------------------------------------------------------ rank-carry chains
 // sequential chains over a handful of rank carries (one warp)
 __global__ void __launch_bounds__(32)
     k_filter_chain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
@@ -239,13 +112,16 @@ __global__ void __launch_bounds__(32)
   if (count == 0) coop_copy(w, state_out, state_in, ST);
 }
 
+
 // ------------------------------------------------------------------------------------------------ reductions
 // out[j] = sum_i part[i*NC + j], fixed summation order (deterministic), single CTA of 1024 threads: every thread
 // accumulates its strided share of all NC components with independent loads, then a shuffle tree per warp and one
-// over the 32 warp sums (the first version took 22 us per launch: 3 serial passes of dependent loads by 256 threads)
-template <int NC>
+// over the 32 warp sums.  The scalars of the pass are finalised by the same launch (MODE 1: filter statistics,
+// MODE 2: smoother statistics, MODE 0: sums only).
+template <int NC, int MODE>
 __global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restrict__ part, long cnt,
-                                                         double* __restrict__ out) {
+                                                         double* __restrict__ out, double n, double d, int calibrate,
+                                                         double* __restrict__ scal) {
   __shared__ double sh[32][NC];
   double s[NC];
 #pragma unroll
@@ -266,33 +142,29 @@ __global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restric
   }
   __syncthreads();
   if (warp == 0) {
+    double v[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      double v = sh[lane][j];
+      v[j] = sh[lane][j];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) out[j] = v;
+      for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_down_sync(0xffffffffu, v[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) out[j] = v[j];
+      if (MODE == 1 && scal) {  // [nll, s1, s2] over n*d observations (filter.py:96-114)
+        const double ssq = v[1] / n / d;
+        scal[POF_S_NLL] = v[0];
+        scal[POF_S_SSQ] = ssq;
+        scal[POF_S_SSQ_PROPER] = v[2 < NC ? 2 : 0] / n / d;
+        scal[POF_S_CSCALE] = calibrate ? sqrt(ssq) : 1.0;
+      }
+      if (MODE == 2 && scal) {  // [obj, #means not close]
+        scal[POF_S_OBJ] = v[0];
+        scal[POF_S_NOT_CLOSE] = v[1];
+      }
     }
   }
-}
-static inline void reduce_parts(cudaStream_t s, const double* part, long cnt, int ncomp, double* out) {
-  if (ncomp == 2) k_reduce_parts_t<2><<<1, 1024, 0, s>>>(part, cnt, out);
-  else if (ncomp == 3) k_reduce_parts_t<3><<<1, 1024, 0, s>>>(part, cnt, out);
-  else if (ncomp == 4) k_reduce_parts_t<4><<<1, 1024, 0, s>>>(part, cnt, out);
-  else k_reduce_parts_t<5><<<1, 1024, 0, s>>>(part, cnt, out);
-}
-// scalars from the filter partial sums [nll, s1, s2] over n*d observations
-__global__ void k_finalize_filter(const double* __restrict__ sums, double n, double d, int calibrate,
-                                  double* __restrict__ scal) {
-  const double ssq = sums[1] / n / d;
-  scal[POF_S_NLL] = sums[0];
-  scal[POF_S_SSQ] = ssq;
-  scal[POF_S_SSQ_PROPER] = sums[2] / n / d;
-  scal[POF_S_CSCALE] = calibrate ? sqrt(ssq) : 1.0;
-}
-__global__ void k_finalize_smooth(const double* __restrict__ sums, double* __restrict__ scal) {
-  scal[POF_S_OBJ] = sums[0];
-  scal[POF_S_NOT_CLOSE] = sums[1];
 }
 __global__ void k_finalize_seq(const double* __restrict__ sums, double n, double d, double* __restrict__ scal) {
   scal[POF_S_NLL] = -sums[0];
@@ -446,7 +318,9 @@ struct WsLayout {
   TreeLevels tl;
   long CS, L;
   int D, FE, SE, ST, NE;
-  size_t o_lin, o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, total;  // in doubles
+  size_t o_lin, o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, o_flags,
+      total;  // in doubles
+  size_t flag_words;  // 32-bit words of the dataflow flag area (zeroed at the start of every stage)
   void build(long n, int d, int q, long chunk_len) {
     D = d * (q + 1);
     FE = 3 * D * D + 2 * D;
@@ -475,60 +349,31 @@ struct WsLayout {
     o_part2 = take((size_t)CS * 2);
     o_sums = take(16);
     o_misc = take((size_t)2 * ST + 64);
+    flag_words = 4 * (size_t)tl.total + 64;  // [tickets (3 x 16 words) | f_up | f_dn | s_up | s_dn]
+    o_flags = take((flag_words + 1) / 2);
     total = o;
   }
+  unsigned* ticket(double* ws, int which) const { return (unsigned*)(ws + o_flags) + 16 * which; }
+  unsigned* flags(double* ws, int which) const { return (unsigned*)(ws + o_flags) + 64 + (size_t)which * tl.total; }
 };
 
-// warps per CTA such that the per-warp shared-memory workspaces fit in 227 KB (0 if even one does not fit)
-static inline int tree_warps(int D) {
-  const long per = (long)coop_ws_doubles(D) * (long)sizeof(double);
-  long w = (227L * 1024L) / per;
-  return (int)(w > TREE_WARPS ? TREE_WARPS : w);
-}
-static inline int tree_smem_bytes(int D) { return tree_warps(D) * coop_ws_doubles(D) * (int)sizeof(double); }
-// Which carry-level kernels serve a pass when no register-resident TreeLaunch exists for D: the warp-per-combine
-// shared-memory kernels above, or the CTA-per-node tile kernels (pof_tile.cu).  The tile leaves need the chunk-level
-// smoothing op, which only the register-resident and the tile trees have; POF_B200_TREE_IMPL=tile forces the tile tree.
-static bool use_tile_tree(int D, const LeafLaunch* ll) {
-  const char* e = getenv("POF_B200_TREE_IMPL");
-  if (e && e[0] == 't') return tile_tree_supported(D);
-  if (tree_launch(D) != nullptr) return false;
-  return (ll && ll->is_tile) || tree_warps(D) < 1;
-}
-
-template <class K>
-static cudaError_t set_smem(K kernel, int bytes) {
-  return ensure_smem(kernel, bytes);
-}
-
-// ---- optional per-segment device timing (used by bench.py for the roofline numbers): CUDA events recorded on the
-// launching stream around each segment of a pass.  Off by default; global, not thread-safe (a measurement aid).
-enum { SEG_FOLD = 0, SEG_FUP, SEG_FDOWN, SEG_SCAN, SEG_SUP, SEG_SDOWN, SEG_SMOOTH, SEG_COUNT };
-struct Prof {
-  bool on = false;
-  static constexpr int MAXP = 4096;
-  cudaEvent_t ev[MAXP][2];
-  int seg[MAXP];
-  int created = 0, used = 0;
-  double acc[SEG_COUNT] = {0};
-  long cnt[SEG_COUNT] = {0};
-} g_prof;
 struct ProfScope {
+  pof_ctx* c;
   int idx = -1;
   cudaStream_t s;
-  ProfScope(int seg, cudaStream_t st) : s(st) {
-    if (!g_prof.on || g_prof.used >= Prof::MAXP) return;
-    idx = g_prof.used++;
-    if (idx >= g_prof.created) {
-      cudaEventCreate(&g_prof.ev[idx][0]);
-      cudaEventCreate(&g_prof.ev[idx][1]);
-      g_prof.created = idx + 1;
+  ProfScope(pof_ctx* ctx, int seg, cudaStream_t st) : c(ctx), s(st) {
+    if (!c || !c->prof_on || c->used >= pof_ctx::MAXP) return;
+    idx = c->used++;
+    if (idx >= c->created) {
+      cudaEventCreate(&c->ev[idx][0]);
+      cudaEventCreate(&c->ev[idx][1]);
+      c->created = idx + 1;
     }
-    g_prof.seg[idx] = seg;
-    cudaEventRecord(g_prof.ev[idx][0], s);
+    c->seg[idx] = seg;
+    cudaEventRecord(c->ev[idx][0], s);
   }
   ~ProfScope() {
-    if (idx >= 0) cudaEventRecord(g_prof.ev[idx][1], s);
+    if (idx >= 0) cudaEventRecord(c->ev[idx][1], s);
   }
 };
 
@@ -542,7 +387,7 @@ struct ProfScope {
   } while (0)
 
 static int make_args(long n, int d, int q, const double* qL_host, const double* H, const double* c,
-                     const WsLayout& wl, LeafArgs& a) {
+                     const WsLayout& wl, unsigned flags, LeafArgs& a) {
   if (q < 1 || q > 5) return POF_E_UNSUPPORTED_DQ;
   a.n = n;
   a.L = wl.L;
@@ -553,10 +398,7 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   a.R = nullptr;
   a.F = nullptr;
   a.QLd = nullptr;
-  {
-    const char* e = getenv("POF_B200_TILE_SWEEP");
-    a.tile_reg = (e && e[0] == 'r') ? 1 : 0;
-  }
+  a.tile_reg = (flags & POF_F_TILE_SMEM_QR) ? 0 : 1;
   a.d = d;
   a.q = q;
   a.s0 = a.s1 = 0.0;
@@ -565,286 +407,233 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
   return 0;
 }
 
-static void fill_sweep(SweepArgs& sa, const WsLayout& wl, double* agg, double* st, int up_levels, int do_down) {
-  sa.nlev = wl.tl.nlev;
-  sa.up_begin = 0;
-  sa.up_end = up_levels < 0 ? 0 : up_levels;
-  sa.down_begin = do_down ? wl.tl.nlev - 1 : 0;
-  sa.down_end = 0;
-  sa.block_sync = 0;
-  for (int l = 0; l < SweepArgs::MAXL; ++l) {
-    sa.off[l] = l < wl.tl.nlev ? wl.tl.off[l] : 0;
-    sa.sz[l] = l < wl.tl.nlev ? wl.tl.sz[l] : 0;
+// ---- dataflow sweeps (FlowArgs, pof_launch.cuh)
+static void flow_begin(FlowArgs& fa, const WsLayout& wl, double* agg, double* st, unsigned* f_up, unsigned* f_dn,
+                       unsigned* ticket) {
+  fa.nlev = wl.tl.nlev;
+  for (int l = 0; l < FlowArgs::MAXL; ++l) {
+    fa.off[l] = l < wl.tl.nlev ? wl.tl.off[l] : 0;
+    fa.sz[l] = l < wl.tl.nlev ? wl.tl.sz[l] : 0;
   }
-  sa.agg = agg;
-  sa.st = st;
-  sa.root_m = sa.root_L = nullptr;
-  sa.faggm = sa.fin = nullptr;
+  fa.nseg = 0;
+  fa.up_lo = 1;
+  fa.up_hi = 0;
+  fa.agg = agg;
+  fa.st = st;
+  fa.root_m = fa.root_L = nullptr;
+  fa.flag_up = f_up;
+  fa.flag_dn = f_dn;
+  fa.ticket = ticket;
 }
-// The apex of a tree: the levels whose nodes fit into ONE CTA of the sweep kernel (cap nodes per level).  They run in
-// a single launch with __syncthreads between levels: warm instruction cache and no kernel boundary for the ~4 levels
-// at the top of the up-sweep and of the down-sweep, where a launch costs a full cold-start combine (~10 us) for a
-// handful of nodes.  POF_B200_TREE_APEX=0 disables it.
-static bool apex_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("POF_B200_TREE_APEX");
-    v = (e && e[0] == '0') ? 0 : 1;
+// up-sweep: build levels 1 .. top from their children
+static void flow_up(FlowArgs& fa, const WsLayout& wl, int top) {
+  if (top < 1) return;
+  fa.up_lo = 1;
+  fa.up_hi = top;
+  for (int l = 1; l <= top; ++l) {
+    fa.seg_kind[fa.nseg] = FlowArgs::UP;
+    fa.seg_level[fa.nseg] = l;
+    fa.seg_count[fa.nseg] = wl.tl.sz[l];
+    ++fa.nseg;
   }
-  return v == 1;
 }
-// first up-sweep level l (building level l+1) that fits the apex: sz[l+1] <= cap; up_total = number of up levels
-static int apex_up_begin(const WsLayout& wl, int up_total, int cap) {
-  int l = 0;
-  while (l < up_total && wl.tl.sz[l + 1] > cap) ++l;
-  return l;
+// down-sweep from the root state (root_m, root_L): states of all nodes, level nlev-1 .. 0
+static void flow_down(FlowArgs& fa, const WsLayout& wl, const double* root_m, const double* root_L) {
+  fa.root_m = root_m;
+  fa.root_L = root_L;
+  fa.seg_kind[fa.nseg] = FlowArgs::ROOT;
+  fa.seg_level[fa.nseg] = wl.tl.nlev - 1;
+  fa.seg_count[fa.nseg] = 1;
+  ++fa.nseg;
+  for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+    fa.seg_kind[fa.nseg] = FlowArgs::DOWN;
+    fa.seg_level[fa.nseg] = l;
+    fa.seg_count[fa.nseg] = wl.tl.sz[l];
+    ++fa.nseg;
+  }
 }
-// the down-sweep runs l = nlev-1 .. 1 (level l-1 from level l); apex while sz[l] <= cap: returns the level at which the
-// per-level launches take over (apex covers l = nlev-1 .. ret+1)
-static int apex_down_end(const WsLayout& wl, int cap) {
-  int l = wl.tl.nlev - 1;
-  while (l >= 1 && wl.tl.sz[l] <= cap) --l;
-  return l;
+static int zero_flags(cudaStream_t s, const WsLayout& wl, double* ws) {
+  POF_CK(cudaMemsetAsync(ws + wl.o_flags, 0, wl.flag_words * sizeof(unsigned), s));
+  return 0;
 }
 
-// stage A: fold + filter up-sweep.  The rank's element ends at the tree root.
-// need_root: the tree's root element is only consumed by the time-sharded form (it is the shard's carry)
-static int stage_a(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
-                   bool need_root) {
+enum { TK_FILTER = 0, TK_SUP = 1, TK_SDOWN = 2 };
+enum { FL_FUP = 0, FL_FDN = 1, FL_SUP = 2, FL_SDN = 3 };
+
+// stage A: fold (+ in the time-sharded form, need_root: the filter up-sweep whose root is the shard's carry element;
+// on one GPU the up-sweep runs in the same dataflow launch as the down-sweep, in stage B)
+static int stage_a(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
+                   const WsLayout& wl, double* ws, bool need_root) {
   double* fagg = ws + wl.o_fagg;
-  const bool tile = use_tile_tree(wl.D, ll);
-  const bool pre = ll->has_pre_update && (tree_launch(wl.D) != nullptr || tile);
   {
-    ProfScope ps(SEG_FOLD, s);
-    POF_CK(ll->fold(s, a, fagg, pre ? ws + wl.o_faggm : nullptr));
+    ProfScope ps(ctx, POF_SEG_FOLD, s);
+    POF_CK(ll->fold(s, a, fagg, ws + wl.o_faggm));
   }
-  const TreeLaunch* tl = tree_launch(wl.D);
-  if (tl && tree_fused()) {
-    // single GPU: the up-sweep runs fused with the down-sweep in stage_b; sharded: up-sweep incl. the root here
-    if (!need_root) return 0;
-    ProfScope ps(SEG_FUP, s);
-    SweepArgs sa;
-    fill_sweep(sa, wl, fagg, ws + wl.o_fin, wl.tl.nlev - 1, 0);
-    POF_CK(tl->fsweep(s, sa));
+  if (!need_root) return 0;
+  const TreeLaunch* tl = tree_for(ll, wl.D, flags);
+  ProfScope ps(ctx, POF_SEG_FUP, s);
+  if (tl && !(flags & POF_F_TREE_PER_LEVEL)) {
+    FlowArgs fa;
+    flow_begin(fa, wl, fagg, ws + wl.o_fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
+    flow_up(fa, wl, wl.tl.nlev - 1);
+    if (fa.nseg) POF_CK(tl->fflow(s, fa));
     return 0;
   }
-  ProfScope ps(SEG_FUP, s);
-  const int smem = tree_smem_bytes(wl.D);
-  const int tw = tree_warps(wl.D);
-  if (!tl && !tile) {
-    if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-    POF_CK(set_smem(k_filter_up, smem));
-  }
-  const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
-  const int a_up = (tl && apex_enabled()) ? apex_up_begin(wl, up_total, tl->fcap) : up_total;
-  if (tl && a_up < up_total && need_root) {  // sharded: the apex of the up-sweep here (single GPU: in stage_b)
-    SweepArgs sa;
-    fill_sweep(sa, wl, fagg, ws + wl.o_fin, 0, 0);
-    sa.up_begin = a_up;
-    sa.up_end = up_total;
-    sa.block_sync = 1;
-    for (int l = 0; l < a_up; ++l)
-      POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE,
-                     wl.tl.sz[l + 1]));
-    POF_CK(tl->fsweep(s, sa));
-    return (int)cudaGetLastError();
-  }
-  for (int l = 0; l < (tl ? a_up : up_total); ++l) {
+  for (int l = 0; l + 1 < wl.tl.nlev; ++l) {
     const long np = wl.tl.sz[l + 1];
     if (tl)
       POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE, np));
-    else if (tile)
-      POF_CK(tile_fup(s, wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np));
     else
-      k_filter_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-          wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np);
+      POF_CK(tile_fup(s, wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np));
   }
   return (int)cudaGetLastError();
 }
-// stage B: filter down-sweep from the root's incoming state (already stored at fin[root]), scan, smoother up-sweep
-// fuse_sdown (single GPU): the smoother's down-sweep runs in the same cooperative kernel as its up-sweep, seeded with
-// the filtered state of the last chunk; stage_c must then be called with skip_down
-static int stage_b(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
-                   double* fmeans, double* fchols, bool need_root, bool fuse_sdown = false) {
+
+// stage B: filter tree (single GPU: up-sweep + down-sweep; sharded: down-sweep only) from the root's incoming state
+// (root_m, root_L), then the filter scan on `s` while the chunk-level smoothing elements and the smoother's up-sweep
+// run on the context's side stream (their inputs only depend on the fold and the filter tree), join, filter scalars.
+static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
+                   const WsLayout& wl, double* ws, const double* root_m, const double* root_L, double* fmeans,
+                   double* fchols, bool need_root, double n_obs_total, int calibrate, double* scalars) {
   double* fagg = ws + wl.o_fagg;
   double* fin = ws + wl.o_fin;
   double* sagg = ws + wl.o_sagg;
-  const int smem = tree_smem_bytes(wl.D);
-  const int tw = tree_warps(wl.D);
-  const TreeLaunch* tl = tree_launch(wl.D);
-  const bool tile = use_tile_tree(wl.D, ll);
-  if (!tl && !tile) {
-    if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-    POF_CK(set_smem(k_filter_down, smem));
-    POF_CK(set_smem(k_smooth_up, smem));
-  }
-  const bool fused = tl && tree_fused();
-  if (fused) {
-    ProfScope ps(need_root ? SEG_FDOWN : SEG_FUP, s);
-    SweepArgs sa;
-    fill_sweep(sa, wl, fagg, fin, need_root ? 0 : wl.tl.nlev - 2, 1);
-    POF_CK(tl->fsweep(s, sa));
-  } else {
-  ProfScope ps(SEG_FDOWN, s);
-  int l_start = wl.tl.nlev - 1;
-  if (tl && apex_enabled()) {
-    // apex: (single GPU) the top of the up-sweep left over by stage_a, then the top of the down-sweep, one CTA
-    const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
-    const int a_up = need_root ? up_total : apex_up_begin(wl, up_total, tl->fcap);
-    const int a_dn = apex_down_end(wl, tl->fcap);
-    if (a_up < up_total || a_dn < wl.tl.nlev - 1) {
-      SweepArgs sa;
-      fill_sweep(sa, wl, fagg, fin, 0, 0);
-      sa.up_begin = a_up;
-      sa.up_end = up_total;
-      sa.down_begin = wl.tl.nlev - 1;
-      sa.down_end = a_dn;
-      sa.block_sync = 1;
-      POF_CK(tl->fsweep(s, sa));
-      l_start = a_dn;
-    }
-  }
-  for (int l = l_start; l >= 1; --l) {
-    const long np = wl.tl.sz[l];
-    if (tl)
-      POF_CK(tl->fdown(s, fin + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], fagg + wl.tl.off[l - 1] * wl.FE,
-                       fin + wl.tl.off[l - 1] * wl.ST, np));
-    else if (tile)
-      POF_CK(tile_fdown(s, wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
-                        fin + wl.tl.off[l - 1] * wl.ST));
-    else
-      k_filter_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-          wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
-          fin + wl.tl.off[l - 1] * wl.ST);
-  }
-  }
-  POF_CK(cudaGetLastError());
-  const bool pre = ll->has_pre_update && (tl != nullptr || tile);
-  SideStream* side = (pre && !fused && tl) ? side_stream() : nullptr;
-  if (side) {
-    // chunk-level smoothing elements, then fork: smoother up-sweep on the side stream || filter scan on s
-    POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
-    POF_CK(cudaEventRecord(side->fork, s));
-    POF_CK(cudaStreamWaitEvent(side->s2, side->fork, 0));
-    {
-      ProfScope ps(SEG_SUP, side->s2);
-      const int up_total = wl.tl.nlev - 1 - (need_root ? 0 : 1);
-      const int a_up = apex_enabled() ? apex_up_begin(wl, up_total, tl->scap) : up_total;
-      for (int l = 0; l < a_up; ++l)
-        POF_CK(tl->sup(side->s2, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE,
-                       wl.tl.sz[l + 1]));
-      if (a_up < up_total) {
-        SweepArgs sa;
-        fill_sweep(sa, wl, sagg, ws + wl.o_sin, 0, 0);
-        sa.up_begin = a_up;
-        sa.up_end = up_total;
-        sa.block_sync = 1;
-        POF_CK(tl->ssweep(side->s2, sa));
+  const TreeLaunch* tl = tree_for(ll, wl.D, flags);
+  const bool per_level = !tl || (flags & POF_F_TREE_PER_LEVEL);
+  const int up_top = wl.tl.nlev - 1 - (need_root ? 0 : 1);  // the root element is only consumed by the sharded form
+  {
+    ProfScope ps(ctx, POF_SEG_FTREE, s);
+    if (!per_level) {
+      FlowArgs fa;
+      flow_begin(fa, wl, fagg, fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
+      if (!need_root) flow_up(fa, wl, up_top);
+      flow_down(fa, wl, root_m, root_L);
+      POF_CK(tl->fflow(s, fa));
+    } else {
+      if (!need_root)
+        for (int l = 0; l < up_top; ++l) {
+          const long np = wl.tl.sz[l + 1];
+          if (tl)
+            POF_CK(tl->fup(s, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], nullptr, fagg + wl.tl.off[l + 1] * wl.FE, np));
+          else
+            POF_CK(tile_fup(s, wl.D, fagg + wl.tl.off[l] * wl.FE, wl.tl.sz[l], fagg + wl.tl.off[l + 1] * wl.FE, np));
+        }
+      k_pack_state<<<1, 128, 0, s>>>(wl.D, root_m, root_L, fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
+      for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+        const long np = wl.tl.sz[l];
+        if (tl)
+          POF_CK(tl->fdown(s, fin + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], fagg + wl.tl.off[l - 1] * wl.FE,
+                           fin + wl.tl.off[l - 1] * wl.ST, np));
+        else
+          POF_CK(tile_fdown(s, wl.D, fin + wl.tl.off[l] * wl.ST, np, fagg + wl.tl.off[l - 1] * wl.FE, wl.tl.sz[l - 1],
+                            fin + wl.tl.off[l - 1] * wl.ST));
       }
     }
-    POF_CK(cudaEventRecord(side->join, side->s2));
-    {
-      ProfScope ps(SEG_SCAN, s);
-      POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, nullptr, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+  }
+  POF_CK(cudaGetLastError());
+  // chunk-level smoothing elements straight from (incoming state, filtering element before its last update), then
+  // the smoother's up-sweep: on the side stream if the caller gave a context, else in line after the scan
+  auto smoother_up = [&](cudaStream_t st) -> int {
+    ProfScope ps(ctx, POF_SEG_SUP, st);
+    if (tl)
+      POF_CK(tl->chunkk(st, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
+    else
+      POF_CK(tile_chunkk(st, wl.D, fin, ws + wl.o_faggm, sagg, wl.CS));
+    if (!per_level) {
+      FlowArgs fa;
+      flow_begin(fa, wl, sagg, ws + wl.o_sin, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SUP));
+      flow_up(fa, wl, up_top);
+      if (fa.nseg) POF_CK(tl->sflow(st, fa));
+      return 0;
     }
-    POF_CK(cudaStreamWaitEvent(s, side->join, 0));
-    reduce_parts(s, ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+    for (int l = 0; l < up_top; ++l) {
+      const long np = wl.tl.sz[l + 1];
+      if (tl)
+        POF_CK(tl->sup(st, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE, np));
+      else
+        POF_CK(tile_sup(st, wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np));
+    }
     return (int)cudaGetLastError();
+  };
+  const bool side = ctx && ctx->s2 && tl;
+  if (side) {
+    POF_CK(cudaEventRecord(ctx->fork, s));
+    POF_CK(cudaStreamWaitEvent(ctx->s2, ctx->fork, 0));
+    if (int rc = smoother_up(ctx->s2)) return rc;
+    POF_CK(cudaEventRecord(ctx->join, ctx->s2));
   }
   {
-    ProfScope ps(SEG_SCAN, s);
-    POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, pre ? nullptr : sagg, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
+    ProfScope ps(ctx, POF_SEG_SCAN, s);
+    POF_CK(ll->scan(s, a, fin, ws + wl.o_kern, nullptr, ws + wl.o_send, ws + wl.o_part, fmeans, fchols));
   }
-  if (fused && pre) {
-    ProfScope ps(SEG_SUP, s);
-    SweepArgs sa;
-    fill_sweep(sa, wl, sagg, ws + wl.o_sin, need_root ? wl.tl.nlev - 1 : wl.tl.nlev - 2, fuse_sdown ? 1 : 0);
-    sa.faggm = ws + wl.o_faggm;
-    sa.fin = fin;
-    if (fuse_sdown) {
-      sa.root_m = ws + wl.o_send + (wl.CS - 1) * wl.ST;
-      sa.root_L = sa.root_m + wl.D;
-    }
-    POF_CK(tl->ssweep(s, sa));
-    reduce_parts(s, ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
-    return (int)cudaGetLastError();
-  }
-  // chunk-level smoothing elements straight from (incoming state, filtering element before its last update)
-  if (pre) {
-    if (tl)
-      POF_CK(tl->chunkk(s, fin, wl.CS, ws + wl.o_faggm, sagg, wl.CS));
-    else
-      POF_CK(tile_chunkk(s, wl.D, fin, ws + wl.o_faggm, sagg, wl.CS));
-  }
-  ProfScope ps(SEG_SUP, s);
-  for (int l = 0; l + 1 < wl.tl.nlev - (need_root ? 0 : 1); ++l) {
-    const long np = wl.tl.sz[l + 1];
-    if (tl)
-      POF_CK(tl->sup(s, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], nullptr, sagg + wl.tl.off[l + 1] * wl.SE, np));
-    else if (tile)
-      POF_CK(tile_sup(s, wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np));
-    else
-      k_smooth_up<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-          wl.D, sagg + wl.tl.off[l] * wl.SE, wl.tl.sz[l], sagg + wl.tl.off[l + 1] * wl.SE, np);
-  }
-  reduce_parts(s, ws + wl.o_part, wl.CS, 3, ws + wl.o_sums);
+  if (side)
+    POF_CK(cudaStreamWaitEvent(s, ctx->join, 0));
+  else if (int rc = smoother_up(s))
+    return rc;
+  k_reduce_parts_t<3, 1><<<1, 1024, 0, s>>>(ws + wl.o_part, wl.CS, ws + wl.o_sums, n_obs_total, (double)a.d, calibrate,
+                                            scalars);
   return (int)cudaGetLastError();
 }
-// stage C: smoother down-sweep from the seed (already stored at sin[root]) + smoother scan
-static int stage_c(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws,
-                   int emit_t0, const double* cscale, double* means, double* chols, bool skip_down = false) {
+
+// stage C: smoother down-sweep from the seed (root_m, root_L) + smoother scan + smoother scalars
+static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
+                   const WsLayout& wl, double* ws, const double* root_m, const double* root_L, int emit_t0,
+                   const double* cscale, double* means, double* chols, double* scalars) {
   double* sagg = ws + wl.o_sagg;
   double* sin_ = ws + wl.o_sin;
-  const int smem = tree_smem_bytes(wl.D);
-  const int tw = tree_warps(wl.D);
-  const TreeLaunch* tl = tree_launch(wl.D);
-  const bool tile = use_tile_tree(wl.D, ll);
-  if (!tl && !tile) {
-    if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-    POF_CK(set_smem(k_smooth_down, smem));
-  }
-  if (skip_down) {
-  } else if (tl && tree_fused()) {
-    ProfScope ps(SEG_SDOWN, s);
-    SweepArgs sa;
-    fill_sweep(sa, wl, sagg, sin_, 0, 1);
-    POF_CK(tl->ssweep(s, sa));
-  } else {
-  ProfScope ps(SEG_SDOWN, s);
-  int l_start = wl.tl.nlev - 1;
-  if (tl && apex_enabled()) {
-    const int a_dn = apex_down_end(wl, tl->scap);
-    if (a_dn < wl.tl.nlev - 1) {
-      SweepArgs sa;
-      fill_sweep(sa, wl, sagg, sin_, 0, 0);
-      sa.down_begin = wl.tl.nlev - 1;
-      sa.down_end = a_dn;
-      sa.block_sync = 1;
-      POF_CK(tl->ssweep(s, sa));
-      l_start = a_dn;
+  const TreeLaunch* tl = tree_for(ll, wl.D, flags);
+  const bool per_level = !tl || (flags & POF_F_TREE_PER_LEVEL);
+  {
+    ProfScope ps(ctx, POF_SEG_SDOWN, s);
+    if (!per_level) {
+      FlowArgs fa;
+      flow_begin(fa, wl, sagg, sin_, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SDOWN));
+      flow_down(fa, wl, root_m, root_L);
+      POF_CK(tl->sflow(s, fa));
+    } else {
+      k_pack_state<<<1, 128, 0, s>>>(wl.D, root_m, root_L, sin_ + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
+      for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+        const long np = wl.tl.sz[l];
+        if (tl)
+          POF_CK(tl->sdown(s, sin_ + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], sagg + wl.tl.off[l - 1] * wl.SE,
+                           sin_ + wl.tl.off[l - 1] * wl.ST, np));
+        else
+          POF_CK(tile_sdown(s, wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
+                            sin_ + wl.tl.off[l - 1] * wl.ST));
+      }
     }
-  }
-  for (int l = l_start; l >= 1; --l) {
-    const long np = wl.tl.sz[l];
-    if (tl)
-      POF_CK(tl->sdown(s, sin_ + wl.tl.off[l] * wl.ST, wl.tl.sz[l - 1], sagg + wl.tl.off[l - 1] * wl.SE,
-                       sin_ + wl.tl.off[l - 1] * wl.ST, np));
-    else if (tile)
-      POF_CK(tile_sdown(s, wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
-                        sin_ + wl.tl.off[l - 1] * wl.ST));
-    else
-      k_smooth_down<<<(unsigned)((np + tw - 1) / tw), tw * 32, smem, s>>>(
-          wl.D, sin_ + wl.tl.off[l] * wl.ST, np, sagg + wl.tl.off[l - 1] * wl.SE, wl.tl.sz[l - 1],
-          sin_ + wl.tl.off[l - 1] * wl.ST);
-  }
   }
   POF_CK(cudaGetLastError());
   {
-    ProfScope ps(SEG_SMOOTH, s);
+    ProfScope ps(ctx, POF_SEG_SMOOTH, s);
     POF_CK(ll->smooth(s, a, sin_, ws + wl.o_kern, emit_t0, cscale, means, chols, ws + wl.o_part2));
   }
-  reduce_parts(s, ws + wl.o_part2, wl.CS, 2, ws + wl.o_sums + 8);
+  k_reduce_parts_t<2, 2><<<1, 1024, 0, s>>>(ws + wl.o_part2, wl.CS, ws + wl.o_sums + 8, 0.0, 0.0, 0, scalars);
   return (int)cudaGetLastError();
+}
+
+static int run_pass(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
+                    const WsLayout& wl, double* ws, int64_t N, const double* x0_mean, const double* x0_chol,
+                    double* means, double* chols, double* fmeans, double* fchols, int calibrate, double* scalars) {
+  if (int rc = zero_flags(s, wl, ws)) return rc;
+  if (int rc = stage_a(s, ctx, flags, ll, a, wl, ws, false)) return rc;
+  if (fmeans) {
+    POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  if (int rc = stage_b(s, ctx, flags, ll, a, wl, ws, x0_mean, x0_chol, fmeans, fchols, false, (double)(N - 1), calibrate,
+                       scalars))
+    return rc;
+  // terminal smoothing state = filtered state at the last time point
+  const double* term = ws + wl.o_send + (wl.CS - 1) * wl.ST;
+  return stage_c(s, ctx, flags, ll, a, wl, ws, term, term + wl.D, 1, scalars + POF_S_CSCALE, means, chols, scalars);
+}
+
+static int fill_params(int ivp_id, const double* params_host, int nparams, int d, IvpParams& P) {
+  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
+  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
+  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
+  return 0;
 }
 
 }  // namespace pof
@@ -853,57 +642,80 @@ using namespace pof;
 
 extern "C" {
 
-int pof_supported(int d, int q) { return leaf_launch(d, q) != nullptr ? 1 : 0; }
+int pof_supported(int d, int q) { return leaf_launch(d, q, 0) != nullptr ? 1 : 0; }
+int pof_supported_tile(int d, int q) { return tile_supported(d, q) ? 1 : 0; }
 
-void pof_profile_enable(int on) {
-  g_prof.on = on != 0;
-  g_prof.used = 0;
-  for (int i = 0; i < SEG_COUNT; ++i) {
-    g_prof.acc[i] = 0.0;
-    g_prof.cnt[i] = 0;
+// ---- context
+int pof_ctx_create(pof_ctx_t** out) {
+  if (!out) return POF_E_ARG;
+  pof_ctx* c = new pof_ctx();
+  cudaError_t e = cudaGetDevice(&c->dev);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete c;
+    return (int)e;
+  }
+  *out = c;
+  return 0;
+}
+void pof_ctx_destroy(pof_ctx_t* c) {
+  if (!c) return;
+  for (int i = 0; i < c->created; ++i) {
+    cudaEventDestroy(c->ev[i][0]);
+    cudaEventDestroy(c->ev[i][1]);
+  }
+  if (c->fork) cudaEventDestroy(c->fork);
+  if (c->join) cudaEventDestroy(c->join);
+  if (c->s2) cudaStreamDestroy(c->s2);
+  delete c;
+}
+void pof_ctx_profile_enable(pof_ctx_t* c, int on) {
+  if (!c) return;
+  c->prof_on = on != 0;
+  c->used = 0;
+  for (int i = 0; i < POF_SEG_COUNT; ++i) {
+    c->acc[i] = 0.0;
+    c->cnt[i] = 0;
   }
 }
-// synchronises the device; ms_out[7] = accumulated milliseconds of [fold, filter_up, filter_down, scan, smooth_up,
-// smooth_down, smooth], count_out[7] = number of timed segments of each kind
-int pof_profile_read(double* ms_out, int64_t* count_out) {
+// synchronises the device; ms_out[POF_SEG_COUNT] = accumulated milliseconds per segment kind, count_out = #segments
+int pof_ctx_profile_read(pof_ctx_t* c, double* ms_out, int64_t* count_out) {
+  if (!c) return POF_E_ARG;
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return (int)e;
-  for (int i = 0; i < g_prof.used; ++i) {
+  for (int i = 0; i < c->used; ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]) == cudaSuccess) {
-      g_prof.acc[g_prof.seg[i]] += ms;
-      g_prof.cnt[g_prof.seg[i]] += 1;
+    if (cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1]) == cudaSuccess) {
+      c->acc[c->seg[i]] += ms;
+      c->cnt[c->seg[i]] += 1;
     }
   }
-  g_prof.used = 0;
-  for (int i = 0; i < SEG_COUNT; ++i) {
-    ms_out[i] = g_prof.acc[i];
-    count_out[i] = g_prof.cnt[i];
+  c->used = 0;
+  for (int i = 0; i < POF_SEG_COUNT; ++i) {
+    ms_out[i] = c->acc[i];
+    count_out[i] = c->cnt[i];
   }
   return 0;
 }
-// kernels launched by one pof_linear_filtsmooth_f64 call
-int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len) {
+
+// kernels launched by one pof_linear_filtsmooth_f64 call (memset / memcpy nodes not counted)
+int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len, uint32_t flags) {
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  const LeafLaunch* ll = leaf_launch(d, q);
-  if (ll && ll->has_pre_update && tree_launch(wl.D) && tree_fused())
-    return 3 /*leaf*/ + 2 /*cooperative tree sweeps*/ + 1 /*pack*/ + 2 /*reduce*/ + 2 /*finalize*/;
+  const LeafLaunch* ll = leaf_launch(d, q, flags);
+  if (!ll) return 0;
+  const TreeLaunch* tl = tree_for(ll, wl.D, flags);
+  const int64_t leaf = 3, chunkk = 1, reduce = 2;
+  if (tl && !(flags & POF_F_TREE_PER_LEVEL)) {
+    const int64_t sup = wl.tl.nlev >= 3 ? 1 : 0;  // the smoother's up-sweep has no level to build below three levels
+    return leaf + chunkk + reduce + 1 /*filter tree*/ + sup + 1 /*smoother down-sweep*/;
+  }
   const int up_total = wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0;  // the root combine is skipped on one GPU
   const int down_total = wl.tl.nlev - 1;
-  const TreeLaunch* tl = tree_launch(wl.D);
-  int64_t tree = 2 * (int64_t)(up_total + down_total);
-  if (tl && apex_enabled()) {  // the top levels of each sweep run in one single-CTA launch (stage_a / stage_b / stage_c)
-    const int fu = apex_up_begin(wl, up_total, tl->fcap), fd = apex_down_end(wl, tl->fcap);
-    const int su = apex_up_begin(wl, up_total, tl->scap), sd = apex_down_end(wl, tl->scap);
-    // the smoother's up-sweep has its apex only on the side-stream path (two-rows-per-lane leaves, overlap enabled)
-    const bool sup_apex = ll && ll->has_pre_update && side_stream() != nullptr;
-    tree = fu + fd + ((fu < up_total || fd < down_total) ? 1 : 0)  // filter: per-level ups and downs, one apex
-           + (sup_apex ? su + ((su < up_total) ? 1 : 0) : up_total) + sd + ((sd < down_total) ? 1 : 0);
-  }
-  const int64_t chunkk = (ll && ll->has_pre_update && (tl || use_tile_tree(wl.D, ll))) ? 1 : 0;
-  return 3 /*leaf*/ + tree /*tree sweeps*/ + chunkk /*chunk smoothing elements*/ + 1 /*pack*/ + 2 /*reduce*/ +
-         2 /*finalize*/;
+  return leaf + chunkk + reduce + 2 /*pack*/ + 2 * (int64_t)(up_total + down_total);
 }
 
 // FP64 FMA throughput of this device (TFLOP/s), measured with a register-resident DFMA loop: the roofline
@@ -937,25 +749,16 @@ int pof_measure_dfma_tflops(pof_stream_t s_, double* tflops_out) {
   return 0;
 }
 
-int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count) {
+int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count, uint32_t flags) {
   if (sm_count <= 0) sm_count = 148;
-  const LeafLaunch* ll = leaf_launch(d, q);
-  const int cpw = ll ? ll->chunks_per_warp : 32;
+  const LeafLaunch* ll = leaf_launch(d, q, flags);
   const int64_t n = N - 1;
-  // ~8 resident warps per SM, `cpw` chunks per warp; tile family: one chunk per resident CTA
-  const int64_t target = (ll && ll->is_tile) ? (int64_t)sm_count * tile_ctas_per_sm(d, q) : (int64_t)sm_count * 8 * cpw;
+  // lane2: ~8 resident warps per SM, chunks_per_warp chunks per warp; tile family: one chunk per resident CTA
+  const int64_t target = (!ll || ll->is_tile) ? (int64_t)sm_count * tile_ctas_per_sm(d, q)
+                                               : (int64_t)sm_count * 8 * ll->chunks_per_warp;
   int64_t L = (n + target - 1) / target;
   if (L < 4) L = 4;
   return L;
-}
-
-int pof_supported_tile(int d, int q) { return tile_supported(d, q) ? 1 : 0; }
-int64_t pof_default_chunk_len_tile(int64_t N, int d, int q, int sm_count) {
-  if (sm_count <= 0) sm_count = 148;
-  const int64_t n = N - 1;
-  const int64_t target = (int64_t)sm_count * tile_ctas_per_sm(d, q);
-  int64_t L = (n + target - 1) / target;
-  return L < 4 ? 4 : L;
 }
 
 size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
@@ -964,35 +767,27 @@ size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
   return wl.total * sizeof(double);
 }
 
-int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
+int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out,
+                           uint32_t flags) {
   if (n <= 0) return 0;
-  if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->fcomb((cudaStream_t)s, e1, n, e2, out, n);
-  if (use_tile_tree(D, nullptr)) return (int)tile_fcomb((cudaStream_t)s, D, n, e1, e2, out);
-  const int smem = tree_smem_bytes(D);
-  const int tw = tree_warps(D);
-  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-  POF_CK(set_smem(k_filter_combine_batched, smem));
-  k_filter_combine_batched<<<(unsigned)((n + tw - 1) / tw), tw * 32, smem, (cudaStream_t)s>>>(D, n, e1, e2, out);
-  return (int)cudaGetLastError();
+  if (!(flags & POF_F_FAMILY_TILE))
+    if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->fcomb((cudaStream_t)s, e1, n, e2, out, n);
+  if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
+  return (int)tile_fcomb((cudaStream_t)s, D, n, e1, e2, out);
 }
-int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out) {
+int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out,
+                           uint32_t flags) {
   if (n <= 0) return 0;
-  if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->scomb((cudaStream_t)s, e1, n, e2, out, n);
-  if (use_tile_tree(D, nullptr)) return (int)tile_scomb((cudaStream_t)s, D, n, e1, e2, out);
-  const int smem = tree_smem_bytes(D);
-  const int tw = tree_warps(D);
-  if (tw < 1) return POF_E_UNSUPPORTED_DQ;
-  POF_CK(set_smem(k_smooth_combine_batched, smem));
-  k_smooth_combine_batched<<<(unsigned)((n + tw - 1) / tw), tw * 32, smem, (cudaStream_t)s>>>(D, n, e1, e2, out);
-  return (int)cudaGetLastError();
+  if (!(flags & POF_F_FAMILY_TILE))
+    if (const TreeLaunch* tl = tree_launch(D)) return (int)tl->scomb((cudaStream_t)s, e1, n, e2, out, n);
+  if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
+  return (int)tile_scomb((cudaStream_t)s, D, n, e1, e2, out);
 }
 
 int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
                           double scale0, double scale1, const double* means_t1, double* H, double* c) {
-  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
-  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
   IvpParams P;
-  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
+  if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
   if (n <= 0) return 0;
   if (ivp_id == POF_IVP_LORENZ96) {
     k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, (cudaStream_t)s>>>(P.p[0], n, d, q, scale0, scale1, 1,
@@ -1004,16 +799,10 @@ int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host,
   return (int)cudaGetLastError();
 }
 
-static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws, int64_t N,
-                    int d, const double* x0_mean, const double* x0_chol, double* means, double* chols,
-                    double* fmeans, double* fchols, int calibrate, double* scalars);
-
 int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
                                   int q, double scale0, const double* means_t1, double* Jc) {
-  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
-  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
   IvpParams P;
-  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
+  if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
   if (n <= 0) return 0;
   if (ivp_id == POF_IVP_LORENZ96) {
     k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, (cudaStream_t)s>>>(P.p[0], n, d, q, scale0, 0.0, 0,
@@ -1025,239 +814,154 @@ int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* para
   return (int)cudaGetLastError();
 }
 
-int pof_linear_filtsmooth_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
-                              const double* x0_mean, const double* x0_chol, const double* H, const double* c,
-                              double* means, double* chols, double* fmeans, double* fchols, int calibrate,
-                              double* scalars, void* ws_, size_t ws_bytes) {
+int pof_linear_filtsmooth_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                              int64_t chunk_len, const double* qL_host, const double* x0_mean, const double* x0_chol,
+                              const double* H, const double* c, double* means, double* chols, double* fmeans,
+                              double* fchols, int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
-  const LeafLaunch* ll = leaf_launch(d, q);
+  const LeafLaunch* ll = leaf_launch(d, q, flags);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
   if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
   LeafArgs a;
-  int rc = make_args(N - 1, d, q, qL_host, H, c, wl, a);
-  if (rc) return rc;
-  return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
+  if (int rc = make_args(N - 1, d, q, qL_host, H, c, wl, flags, a)) return rc;
+  return run_pass(s, ctx, flags, ll, a, wl, (double*)ws_, N, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate,
+                  scalars);
 }
 
 // general linear-Gaussian model: always the tile family (the only leaves that carry the D-column posterior factor and
 // read dense per-step transition models)
-int pof_linear_filtsmooth_general_f64(pof_stream_t s_, int64_t N, int d, int q, int64_t chunk_len,
-                                      const double* qL_host, const double* F, const double* QL, const double* x0_mean,
-                                      const double* x0_chol, const double* H, const double* c, const double* cholR,
-                                      double* means, double* chols, double* fmeans, double* fchols, int calibrate,
-                                      double* scalars, void* ws_, size_t ws_bytes) {
+int pof_linear_filtsmooth_general_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                                      int64_t chunk_len, const double* qL_host, const double* F, const double* QL,
+                                      const double* x0_mean, const double* x0_chol, const double* H, const double* c,
+                                      const double* cholR, double* means, double* chols, double* fmeans, double* fchols,
+                                      int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
   if ((F == nullptr) != (QL == nullptr)) return POF_E_ARG;
   if (!F && !qL_host) return POF_E_ARG;
   if (!tile_supported(d, q)) return POF_E_UNSUPPORTED_DQ;
+  flags |= POF_F_FAMILY_TILE;
   const LeafLaunch* ll = tile_leaf_launch();
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
   if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
   LeafArgs a;
   double ql_dummy[36] = {0.0};
-  int rc = make_args(N - 1, d, q, qL_host ? qL_host : ql_dummy, H, c, wl, a);
-  if (rc) return rc;
+  if (int rc = make_args(N - 1, d, q, qL_host ? qL_host : ql_dummy, H, c, wl, flags, a)) return rc;
   a.R = cholR;
   a.F = F;
   a.QLd = QL;
-  return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate, scalars);
+  return run_pass(s, ctx, flags, ll, a, wl, (double*)ws_, N, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate,
+                  scalars);
 }
 
-int pof_ieks_iteration_f64(pof_stream_t s_, int ivp_id, const double* params_host, int nparams, int64_t N, int d,
-                           int q, int64_t chunk_len, const double* qL_host, double scale0, double scale1,
-                           const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
-                           double* scalars, void* ws_, size_t ws_bytes) {
+int pof_ieks_iteration_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                           int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                           double scale0, double scale1, const double* x0_mean, const double* x0_chol, double* means,
+                           double* chols, int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
-  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
-  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
-  const LeafLaunch* ll = leaf_launch(d, q);
+  IvpParams P;
+  if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
+  const LeafLaunch* ll = leaf_launch(d, q, flags);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
   if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
   double* ws = (double*)ws_;
-  IvpParams P;
-  for (int i = 0; i < 8; ++i) P.p[i] = (i < nparams) ? params_host[i] : 0.0;
   const long n = N - 1;
   const int D = wl.D;
   double* lin = ws + wl.o_lin;
-  LeafArgs a;
-  int rc;
-  if (ivp_id == POF_IVP_LORENZ96) {
-    if (!ll->has_pre_update) return POF_E_UNSUPPORTED_DQ;  // only the tile (and lane) leaves rebuild H from [J_f | c]
+  // compact linearisation [J_f | c] per step; both kernel families rebuild H = E1 - J_f E0 on load
+  if (ivp_id == POF_IVP_LORENZ96)
     k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, s>>>(P.p[0], n, d, q, scale0, 0.0, 0, means + D,
                                                                     nullptr, nullptr, lin);
-    rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, a);
-    a.Jc = lin;
-    a.s0 = scale0;
-    a.s1 = scale1;
-  } else if (ll->has_pre_update) {  // lane kernels: compact linearisation, H rebuilt on load
+  else
     k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, means + D, lin);
-    rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, a);
-    a.Jc = lin;
-    a.s0 = scale0;
-    a.s1 = scale1;
-  } else {
-    k_linearize<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, scale1, means + D, lin,
-                                                            lin + (size_t)n * d * D);
-    rc = make_args(n, d, q, qL_host, lin, lin + (size_t)n * d * D, wl, a);
-  }
-  if (rc) return rc;
   POF_CK(cudaGetLastError());
-  return run_pass(s, ll, a, wl, ws, N, d, x0_mean, x0_chol, means, chols, nullptr, nullptr, calibrate, scalars);
+  LeafArgs a;
+  if (int rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, flags, a)) return rc;
+  a.Jc = lin;
+  a.s0 = scale0;
+  a.s1 = scale1;
+  return run_pass(s, ctx, flags, ll, a, wl, ws, N, x0_mean, x0_chol, means, chols, nullptr, nullptr, calibrate,
+                  scalars);
 }
 
-}  // extern "C"
-
-static int run_pass(cudaStream_t s, const LeafLaunch* ll, const LeafArgs& a, const WsLayout& wl, double* ws, int64_t N,
-                    int d, const double* x0_mean, const double* x0_chol, double* means, double* chols,
-                    double* fmeans, double* fchols, int calibrate, double* scalars) {
-  int rc = stage_a(s, ll, a, wl, ws, false);
-  if (rc) return rc;
-  // root's incoming state = x0
-  k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
-  if (fmeans) {
-    POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  }
-  const bool fuse_sdown = ll->has_pre_update && tree_launch(wl.D) != nullptr && tree_fused();
-  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, false, fuse_sdown);
-  if (rc) return rc;
-  k_finalize_filter<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, calibrate, scalars);
-  // terminal smoothing state = filtered state at the last time point
-  if (!fuse_sdown)
-    POF_CK(cudaMemcpyAsync(ws + wl.o_sin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, ws + wl.o_send + (wl.CS - 1) * wl.ST,
-                           wl.ST * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  rc = stage_c(s, ll, a, wl, ws, 1, scalars + POF_S_CSCALE, means, chols, fuse_sdown);
-  if (rc) return rc;
-  k_finalize_smooth<<<1, 1, 0, s>>>(ws + wl.o_sums + 8, scalars);
-  return (int)cudaGetLastError();
-}
-
-extern "C" {
-
-int pof_sequential_eks_f64(pof_stream_t s_, int ivp_id, const double* params_host, int nparams, int64_t N, int d,
-                           int q, const double* qL_host, double scale0, double scale1, const double* x0_mean,
-                           const double* x0_chol, double* means, double* chols, double* scalars, void* ws_,
-                           size_t ws_bytes) {
+int pof_sequential_eks_f64(pof_stream_t s_, uint32_t flags, int ivp_id, const double* params_host, int nparams,
+                           int64_t N, int d, int q, const double* qL_host, double scale0, double scale1,
+                           const double* x0_mean, const double* x0_chol, double* means, double* chols, double* scalars,
+                           void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
-  if (ivp_id < 0 || ivp_id > POF_IVP_LORENZ96) return POF_E_IVP;
-  if (nparams > 8 || !ivp_dim_ok(ivp_id, d)) return POF_E_ARG;
-  // one thread (d <= 4 templates) or, for larger states / POF_B200_LEAF_IMPL=tile, one CTA of the tile family
-  const LeafLaunch* ll = leaf_launch(d, q);
-  if (!ll || !ll->is_tile) ll = thread_launch(d, q);
+  IvpParams P;
+  if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
+  // one thread (d <= 4 templates) or, for larger states / POF_F_FAMILY_TILE, one CTA of the tile family
+  const LeafLaunch* ll = (flags & POF_F_FAMILY_TILE) ? nullptr : seq_launch(d, q);
+  if (!ll && tile_supported(d, q)) ll = tile_leaf_launch();
   if (!ll || !ll->seq_eks) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, N - 1);
   if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
   double* ws = (double*)ws_;
   LeafArgs a;
-  int rc = make_args(N - 1, d, q, qL_host, nullptr, nullptr, wl, a);
-  if (rc) return rc;
+  if (int rc = make_args(N - 1, d, q, qL_host, nullptr, nullptr, wl, flags, a)) return rc;
   a.s0 = scale0;
   a.s1 = scale1;
-  double p8[8];
-  for (int i = 0; i < 8; ++i) p8[i] = (i < nparams) ? params_host[i] : 0.0;
   double* x0 = ws + wl.o_misc;
   k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, x0);
-  POF_CK(ll->seq_eks(s, a, ivp_id, p8, x0, ws + wl.o_kern, means, chols, ws + wl.o_sums));
+  POF_CK(ll->seq_eks(s, a, ivp_id, P.p, x0, ws + wl.o_kern, means, chols, ws + wl.o_sums));
   // scalars: NLL slot holds the reference's `ell` = +sum loglik (sequential path sign, filter.py:91)
   k_finalize_seq<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, scalars);
   return (int)cudaGetLastError();
 }
 
-static int shard_a(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                   const double* H, const double* c, const double* Jc, double s0, double s1, double* carry_f,
-                   void* ws_, size_t ws_bytes);
-static int shard_b(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                   const double* H, const double* c, const double* Jc, double s0, double s1, const double* state_in,
-                   double* fmeans, double* fchols, double* carry_s, double* state_end, double* partials, void* ws_,
-                   size_t ws_bytes);
-
-int pof_shard_stage_a_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                          const double* H, const double* c, double* carry_f, void* ws_, size_t ws_bytes) {
-  return shard_a((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, carry_f, ws_, ws_bytes);
-}
-int pof_shard_stage_a_compact_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len,
-                                  const double* qL_host, const double* Jc, double scale0, double scale1,
-                                  double* carry_f, void* ws_, size_t ws_bytes) {
-  return shard_a((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1, carry_f, ws_,
-                 ws_bytes);
-}
-int pof_shard_stage_b_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                          const double* H, const double* c, const double* state_in, double* fmeans, double* fchols,
-                          double* carry_s, double* state_end, double* partials, void* ws_, size_t ws_bytes) {
-  return shard_b((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, state_in, fmeans, fchols,
-                 carry_s, state_end, partials, ws_, ws_bytes);
-}
-int pof_shard_stage_b_compact_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len,
-                                  const double* qL_host, const double* Jc, double scale0, double scale1,
-                                  const double* state_in, double* fmeans, double* fchols, double* carry_s,
-                                  double* state_end, double* partials, void* ws_, size_t ws_bytes) {
-  return shard_b((cudaStream_t)s_, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1, state_in,
-                 fmeans, fchols, carry_s, state_end, partials, ws_, ws_bytes);
-}
-
-}  // extern "C"
-
-static int shard_a(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                   const double* H, const double* c, const double* Jc, double s0, double s1, double* carry_f,
-                   void* ws_, size_t ws_bytes) {
+// ---- time-sharded stages
+static int shard_setup(int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host, const double* H,
+                       const double* c, const double* Jc, double s0, double s1, uint32_t flags, size_t ws_bytes,
+                       const LeafLaunch*& ll, WsLayout& wl, LeafArgs& a) {
   if (n_loc < 1) return POF_E_ARG;
-  const LeafLaunch* ll = leaf_launch(d, q);
+  ll = leaf_launch(d, q, flags);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
-  WsLayout wl;
   wl.build(n_loc, d, q, chunk_len);
   if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
-  LeafArgs a;
-  int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
-  if (rc) return rc;
+  if (int rc = make_args(n_loc, d, q, qL_host, H, c, wl, flags, a)) return rc;
   if (Jc) {
-    if (!ll->has_pre_update) return POF_E_ARG;  // only the lane kernels read the compact form
     a.Jc = Jc;
     a.s0 = s0;
     a.s1 = s1;
   }
-  rc = stage_a(s, ll, a, wl, ws, true);
-  if (rc) return rc;
+  return 0;
+}
+static int shard_a(cudaStream_t s, pof_ctx* ctx, uint32_t flags, int64_t n_loc, int d, int q, int64_t chunk_len,
+                   const double* qL_host, const double* H, const double* c, const double* Jc, double s0, double s1,
+                   double* carry_f, void* ws_, size_t ws_bytes) {
+  const LeafLaunch* ll;
+  WsLayout wl;
+  LeafArgs a;
+  if (int rc = shard_setup(n_loc, d, q, chunk_len, qL_host, H, c, Jc, s0, s1, flags, ws_bytes, ll, wl, a)) return rc;
+  double* ws = (double*)ws_;
+  if (int rc = zero_flags(s, wl, ws)) return rc;
+  if (int rc = stage_a(s, ctx, flags, ll, a, wl, ws, true)) return rc;
   POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(double),
                          cudaMemcpyDeviceToDevice, s));
   return 0;
 }
-
-static int shard_b(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                   const double* H, const double* c, const double* Jc, double s0, double s1, const double* state_in,
-                   double* fmeans, double* fchols, double* carry_s, double* state_end, double* partials, void* ws_,
-                   size_t ws_bytes) {
-  const LeafLaunch* ll = leaf_launch(d, q);
-  if (!ll) return POF_E_UNSUPPORTED_DQ;
+static int shard_b(cudaStream_t s, pof_ctx* ctx, uint32_t flags, int64_t n_loc, int d, int q, int64_t chunk_len,
+                   const double* qL_host, const double* H, const double* c, const double* Jc, double s0, double s1,
+                   const double* state_in, double* fmeans, double* fchols, double* carry_s, double* state_end,
+                   double* partials, void* ws_, size_t ws_bytes) {
+  const LeafLaunch* ll;
   WsLayout wl;
-  wl.build(n_loc, d, q, chunk_len);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
   LeafArgs a;
-  int rc = make_args(n_loc, d, q, qL_host, H, c, wl, a);
-  if (rc) return rc;
-  if (Jc) {
-    if (!ll->has_pre_update) return POF_E_ARG;
-    a.Jc = Jc;
-    a.s0 = s0;
-    a.s1 = s1;
-  }
-  POF_CK(cudaMemcpyAsync(ws + wl.o_fin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, state_in, wl.ST * sizeof(double),
-                         cudaMemcpyDeviceToDevice, s));
-  rc = stage_b(s, ll, a, wl, ws, fmeans, fchols, true);
-  if (rc) return rc;
+  if (int rc = shard_setup(n_loc, d, q, chunk_len, qL_host, H, c, Jc, s0, s1, flags, ws_bytes, ll, wl, a)) return rc;
+  double* ws = (double*)ws_;
+  if (int rc = zero_flags(s, wl, ws)) return rc;
+  if (int rc = stage_b(s, ctx, flags, ll, a, wl, ws, state_in, state_in + wl.D, fmeans, fchols, true, 1.0, 0, nullptr))
+    return rc;
   POF_CK(cudaMemcpyAsync(carry_s, ws + wl.o_sagg + wl.tl.off[wl.tl.nlev - 1] * wl.SE, wl.SE * sizeof(double),
                          cudaMemcpyDeviceToDevice, s));
   POF_CK(cudaMemcpyAsync(state_end, ws + wl.o_send + (wl.CS - 1) * wl.ST, wl.ST * sizeof(double),
@@ -1266,49 +970,75 @@ static int shard_b(cudaStream_t s, int64_t n_loc, int d, int q, int64_t chunk_le
   return 0;
 }
 
-extern "C" {
+int pof_shard_stage_a_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const double* H, const double* c, double* carry_f,
+                          void* ws_, size_t ws_bytes) {
+  return shard_a((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, carry_f, ws_,
+                 ws_bytes);
+}
+int pof_shard_stage_a_compact_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host, const double* Jc, double scale0,
+                                  double scale1, double* carry_f, void* ws_, size_t ws_bytes) {
+  return shard_a((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1,
+                 carry_f, ws_, ws_bytes);
+}
+int pof_shard_stage_b_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const double* H, const double* c,
+                          const double* state_in, double* fmeans, double* fchols, double* carry_s, double* state_end,
+                          double* partials, void* ws_, size_t ws_bytes) {
+  return shard_b((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, state_in,
+                 fmeans, fchols, carry_s, state_end, partials, ws_, ws_bytes);
+}
+int pof_shard_stage_b_compact_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host, const double* Jc, double scale0,
+                                  double scale1, const double* state_in, double* fmeans, double* fchols,
+                                  double* carry_s, double* state_end, double* partials, void* ws_, size_t ws_bytes) {
+  return shard_b((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1,
+                 state_in, fmeans, fchols, carry_s, state_end, partials, ws_, ws_bytes);
+}
 
-int pof_shard_stage_c_f64(pof_stream_t s_, int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host,
-                          const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,
-                          double* chols, double* partials2, void* ws_, size_t ws_bytes) {
+int pof_shard_stage_c_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const double* seed, int is_last_rank, int has_row0,
+                          const double* cscale, double* means, double* chols, double* partials2, void* ws_,
+                          size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   (void)is_last_rank;
-  const LeafLaunch* ll = leaf_launch(d, q);
-  if (!ll) return POF_E_UNSUPPORTED_DQ;
+  const LeafLaunch* ll;
   WsLayout wl;
-  wl.build(n_loc, d, q, chunk_len);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
   LeafArgs a;
-  int rc = make_args(n_loc, d, q, qL_host, nullptr, nullptr, wl, a);
-  if (rc) return rc;
-  POF_CK(cudaMemcpyAsync(ws + wl.o_sin + wl.tl.off[wl.tl.nlev - 1] * wl.ST, seed, wl.ST * sizeof(double),
-                         cudaMemcpyDeviceToDevice, s));
+  if (int rc = shard_setup(n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, nullptr, 0.0, 0.0, flags, ws_bytes, ll,
+                           wl, a))
+    return rc;
+  double* ws = (double*)ws_;
+  if (int rc = zero_flags(s, wl, ws)) return rc;
   // local row of state t' is t' - (1 - has_row0): shift the base pointers so that the kernels can index by t'
   const long shift = has_row0 ? 0 : 1;
   double* mb = means - shift * wl.D;
   double* cb = chols ? chols - shift * (long)wl.D * wl.D : nullptr;
-  rc = stage_c(s, ll, a, wl, ws, has_row0, cscale, mb, cb);
-  if (rc) return rc;
+  if (int rc = stage_c(s, ctx, flags, ll, a, wl, ws, seed, seed + wl.D, has_row0, cscale, mb, cb, nullptr)) return rc;
   POF_CK(cudaMemcpyAsync(partials2, ws + wl.o_sums + 8, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
-int pof_filter_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
-                               double* state_out, double* scratch) {
-  if (use_tile_tree(D, nullptr))
+int pof_filter_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
+                               const double* elems, double* state_out, double* scratch) {
+  if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) {
+    if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
     return (int)tile_fchain((cudaStream_t)s, D, count, state_in, elems, state_out, scratch);
+  }
   const int smem = coop_ws_doubles(D) * (int)sizeof(double);
-  POF_CK(set_smem(k_filter_chain, smem));
+  POF_CK(ensure_smem(k_filter_chain, smem));
   k_filter_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
   return (int)cudaGetLastError();
 }
-int pof_smooth_apply_chain_f64(pof_stream_t s, int D, int count, const double* state_in, const double* elems,
-                               double* state_out, double* scratch) {
-  if (use_tile_tree(D, nullptr))
+int pof_smooth_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
+                               const double* elems, double* state_out, double* scratch) {
+  if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) {
+    if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
     return (int)tile_schain((cudaStream_t)s, D, count, state_in, elems, state_out, scratch);
+  }
   const int smem = coop_ws_doubles(D) * (int)sizeof(double);
-  POF_CK(set_smem(k_smooth_chain, smem));
+  POF_CK(ensure_smem(k_smooth_chain, smem));
   k_smooth_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
   return (int)cudaGetLastError();
 }

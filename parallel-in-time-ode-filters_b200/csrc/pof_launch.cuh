@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 namespace pof {
 
 // Raise a kernel's dynamic shared-memory limit ONCE per (kernel, device): cudaFuncSetAttribute is a driver call of
@@ -16,6 +18,10 @@ inline SmemCache& smem_cache() {
   static SmemCache c;
   return c;
 }
+inline std::mutex& smem_cache_mutex() {
+  static std::mutex m;
+  return m;
+}
 // max_carveout: prefer the largest shared-memory carve-out for this kernel.  Kernels of different sweeps co-reside
 // on an SM (the smoother's up-sweep runs next to the filter scan) only if the carve-out chosen for the resident one
 // leaves room for the other; kernels that run alone keep the default (a larger L1 is worth ~3 % to them).
@@ -24,6 +30,7 @@ inline cudaError_t ensure_smem(K kernel, int bytes, bool max_carveout = false) {
   if (bytes <= 48 * 1024 && !max_carveout) return cudaSuccess;
   int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(smem_cache_mutex());
   SmemCache& c = smem_cache();
   const void* key = (const void*)kernel;
   for (int i = 0; i < c.n; ++i)
@@ -59,7 +66,7 @@ struct LeafArgs {
   const double* R;   // observation-noise factors cholR (n,d,d), or null = noiseless (tile family only)
   const double* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
   const double* QLd; // preconditioned IWP described by ql (tile family only)
-  int tile_reg;      // tile family: register-resident Householder sweeps (POF_B200_TILE_SWEEP=reg), default shared memory
+  int tile_reg;      // tile family: register-resident Householder sweeps (default; 0 with POF_F_TILE_SMEM_QR)
 };
 
 struct LeafLaunch {
@@ -73,22 +80,16 @@ struct LeafLaunch {
   // sequential extended Kalman smoother relinearised at the predicted mean (one thread; baseline path), or null
   cudaError_t (*seq_eks)(cudaStream_t, const LeafArgs&, int ivp_id, const double* params8, const double* x0,
                          double* kern, double* means, double* chols, double* part);
-  int chunks_per_warp;
-  int has_pre_update;  // 1 if fold can emit faggm and scan can skip the composition  // 32 for the thread-per-chunk kernels, 32/G for the lane-cooperative ones
-  int is_tile;         // 1 for the CTA-per-chunk large-state family (pof_tile.cu): chunks_per_warp is 0 there
+  int chunks_per_warp;  // 32 / G for the lane-cooperative kernels
+  int has_pre_update;   // 1 if fold emits faggm (the chunk's element before its last update); both families do
+  int is_tile;          // 1 for the CTA-per-chunk large-state family (pof_tile.cu): chunks_per_warp is 0 there
 };
 
-// returns nullptr if (d, q) is not compiled in
-const LeafLaunch* leaf_launch(int d, int q);
-const LeafLaunch* leaf_launch_d1(int q);
-const LeafLaunch* leaf_launch_d2(int q);
-const LeafLaunch* leaf_launch_d3(int q);
-const LeafLaunch* leaf_launch_d4(int q);
-// lane-cooperative (performance) path
-const LeafLaunch* lane_launch_d1(int q);
-const LeafLaunch* lane_launch_d2(int q);
-const LeafLaunch* lane_launch_d3(int q);
-const LeafLaunch* lane_launch_d4(int q);
+// one-thread sequential EKS (pof_seq_kernels.cuh): only `seq_eks` is set; nullptr if q is not compiled in
+const LeafLaunch* seq_launch_d1(int q);
+const LeafLaunch* seq_launch_d2(int q);
+const LeafLaunch* seq_launch_d3(int q);
+const LeafLaunch* seq_launch_d4(int q);
 // two rows per lane (pof_lane2.cuh); null where not instantiated
 const LeafLaunch* lane2_launch_d1(int q);
 const LeafLaunch* lane2_launch_d2(int q);
@@ -114,33 +115,41 @@ cudaError_t tile_fchain(cudaStream_t, int D, int count, const double* state_in, 
 cudaError_t tile_schain(cudaStream_t, int D, int count, const double* state_in, const double* elems,
                         double* state_out, double* scratch);
 
-// One whole tree sweep (all levels of an up-sweep and/or a down-sweep) as ONE persistent cooperative kernel with a
-// grid barrier between levels: ~2 us per level instead of a kernel boundary (launch gap, cold instruction cache,
-// drained SMs) per level.
-struct SweepArgs {
-  static constexpr int MAXL = 48;
-  int nlev;          // levels of the tree (level 0 = chunks)
-  int up_begin, up_end;      // up-sweep: for l in [up_begin, up_end): level l+1 <- pairs of level l
-  int down_begin, down_end;  // down-sweep: for l = down_begin; l > down_end; --l: level l-1 <- level l
-  int block_sync;    // 1: launched as ONE CTA, levels separated by __syncthreads (the apex of the tree: levels with
-                     // at most one CTA's worth of nodes); 0: cooperative launch, grid barrier per level
+// One whole tree sweep (an up-sweep and/or a down-sweep over the chunk carries) as ONE kernel without level barriers:
+// a DATAFLOW schedule.  Work items (one associative combine each) are numbered in level order; every warp draws the
+// next ticket from an atomic counter, waits until the flags of the nodes its items depend on are set (acquire loads),
+// computes, and publishes its own nodes' flags (release).  An item only depends on items with SMALLER numbers, and
+// those tickets are held by warps that are already running, so the schedule cannot deadlock whatever the residency.
+// Compared with one launch per level (~10 us per level: launch gap + cold instruction cache + one combine's latency)
+// a level costs one warm combine plus an L2 round trip for the flag.
+struct FlowArgs {
+  static constexpr int MAXL = 40;
+  enum Kind { UP = 0, ROOT = 1, DOWN = 2 };
+  int nlev;                 // levels of the tree (level 0 = chunks)
   long off[MAXL], sz[MAXL];
-  double* agg;       // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
-  double* st;        // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
-  const double* root_m;  // if non-null: root state <- (root_m, root_L) before the down-sweep
+  int nseg;                 // segments in execution order: segment j has seg_count[j] independent items
+  int seg_kind[2 * MAXL + 2];
+  int seg_level[2 * MAXL + 2];  // UP: the level that is built (from level - 1); DOWN: the level whose states are known
+  long seg_count[2 * MAXL + 2];
+  long seg_begin[2 * MAXL + 3];  // filled by the launcher: item offsets, every segment padded to whole tickets (a
+                                 // ticket never straddles two segments: its items must not depend on each other)
+  int up_lo, up_hi;         // levels built by UP segments of THIS launch (their flags are waited for); elements of
+                            // any other level were complete before the launch
+  double* agg;              // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
+  double* st;               // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
+  const double* root_m;     // state of the root node for the down-sweep (ROOT item): mean (D), factor (D x D)
   const double* root_L;
-  // smoothing sweep only: chunk-level smoothing elements first (if faggm != null): agg[level 0] <- chunk_kernel
-  const double* faggm;   // chunk filtering elements before their last update
-  const double* fin;     // chunk incoming filtered states
+  unsigned* flag_up;        // per node: element complete   } zeroed by a stream-ordered memset before the launch
+  unsigned* flag_dn;        // per node: state complete     }
+  unsigned* ticket;         // the ticket counter           }
 };
 
 // register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> generic shared-memory kernels
 struct TreeLaunch {
   typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
   Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk;
-  typedef cudaError_t (*SweepFn)(cudaStream_t, const SweepArgs&);
-  SweepFn fsweep, ssweep;  // whole-sweep kernels (filtering / smoothing): cooperative, or one CTA for the apex
-  int fcap, scap;          // nodes one CTA of the sweep kernel processes per level (filtering / smoothing)
+  typedef cudaError_t (*FlowFn)(cudaStream_t, const FlowArgs&);
+  FlowFn fflow, sflow;     // whole-sweep dataflow kernels (filtering / smoothing)
 };
 const TreeLaunch* tree_launch_a(int D);
 const TreeLaunch* tree_launch_b(int D);

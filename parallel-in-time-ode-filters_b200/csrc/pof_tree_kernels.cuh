@@ -1,8 +1,6 @@
 // Tree-sweep kernels over chunk carries with the register-resident combines of pof_treelane.cuh.
 // One group of lanes per tree node; `which` selects the sweep.
 #pragma once
-#include <cooperative_groups.h>
-
 #include "pof_launch.cuh"
 #include "pof_treelane.cuh"
 
@@ -12,9 +10,10 @@ constexpr int TL_WARPS = 4;
 
 enum TreeOp { T_FUP = 0, T_FDOWN, T_SUP, T_SDOWN, T_FCOMB, T_SCOMB, T_CHUNKK };
 
+// (L2 loads: inside a dataflow sweep the source was written by another SM during the SAME kernel)
 template <int D, int G>
-__device__ __forceinline__ void group_copy(int r, double* __restrict__ dst, const double* __restrict__ src, int n) {
-  for (int i = r; i < n; i += G) dst[i] = src[i];
+__device__ __forceinline__ void group_copy(int r, double* dst, const double* src, int n) {
+  for (int i = r; i < n; i += G) dst[i] = __ldcg(src + i);
 }
 
 // a, b, c, na, nb follow the generic kernels in pof_api.cu:
@@ -67,83 +66,110 @@ __global__ void __launch_bounds__(TL_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Whole sweep in one cooperative kernel.  Every group of G lanes walks the nodes of the current level with a grid
-// stride; levels are separated by grid barriers (all CTAs are co-resident: cooperative launch).
+// Whole sweep as one dataflow kernel (FlowArgs, pof_launch.cuh): tickets in level order, per-node ready flags.
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int D, bool FILT>
-__global__ void __launch_bounds__(TL_WARPS * 32) k_tree_sweep(const SweepArgs A) {
+__global__ void __launch_bounds__(TL_WARPS * 32) k_tree_flow(const FlowArgs A) {
   extern __shared__ __align__(16) double sm[];
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
   using TL = TreeLane<D>;
   constexpr int G = FILT ? TL::G2 : TL::GS;
-  constexpr int G2 = TL::G2;  // the chunk-level op always uses the filtering group width
+  constexpr int CPW = 32 / G;
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
   constexpr int EL = FILT ? FE : SE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if constexpr (!FILT) {
-    if (A.faggm) {  // chunk-level smoothing elements (pof_treelane.cuh: chunk_kernel), G2 lanes per chunk
-      constexpr int CPW2 = 32 / G2;
-      typename TL::Ctx cx;
-      TL::template init<G2>(cx, sm + (warp * CPW2 + lane / G2) * TL::SM_COMBINE);
-      const long ng = (long)gridDim.x * TL_WARPS * CPW2;
-      for (long i = ((long)blockIdx.x * TL_WARPS + warp) * CPW2 + lane / G2; i < A.sz[0]; i += ng)
-        TL::chunk_kernel(cx, A.fin + i * ST, A.faggm + i * FE, A.agg + i * SE);
-      if (A.block_sync) __syncthreads(); else grid.sync();
-    }
-  }
-  constexpr int CPW = 32 / G;
   typename TL::Ctx cx;
   TL::template init<G>(cx, sm + (warp * CPW + lane / G) * TL::SM_COMBINE);
-  const long g0 = ((long)blockIdx.x * TL_WARPS + warp) * CPW + lane / G;
-  const long ng = (long)gridDim.x * TL_WARPS * CPW;
-  // ---- up-sweep
-  for (int l = A.up_begin; l < A.up_end; ++l) {
-    const double* ch = A.agg + A.off[l] * EL;
-    double* pa = A.agg + A.off[l + 1] * EL;
-    const long na = A.sz[l], nb = A.sz[l + 1];
-    for (long i = g0; i < nb; i += ng) {
-      const double* lc = ch + 2 * i * EL;
-      if (2 * i + 1 < na) {
-        if constexpr (FILT) TL::template filter_combine<false>(cx, lc, lc + EL, pa + i * EL);
-        else TL::template smooth_combine<false>(cx, lc + EL, lc, pa + i * EL);
-      } else {
-        group_copy<D, G>(cx.r, pa + i * EL, lc, EL);
-      }
+  const long total = A.seg_begin[A.nseg];
+  while (true) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(A.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const long first = (long)t * CPW;
+    if (first >= total) break;
+    const long item = first + lane / G;
+    // decode: segment, level, index within the segment (segments are padded to whole tickets: dead items at the end)
+    int kind = FlowArgs::ROOT, lev = 0;
+    long i = 0;
+    bool live = false;
+    {
+      int sgm = 0;
+      while (sgm + 1 < A.nseg && item >= A.seg_begin[sgm + 1]) ++sgm;
+      kind = A.seg_kind[sgm];
+      lev = A.seg_level[sgm];
+      i = item - A.seg_begin[sgm];
+      live = i < A.seg_count[sgm];
     }
-    if (A.block_sync) __syncthreads(); else grid.sync();
-  }
-  if (A.down_begin <= A.down_end) return;
-  // ---- root state
-  if (A.root_m && g0 == 0) {
-    double* r = A.st + A.off[A.nlev - 1] * ST;
-    for (int i = cx.r; i < ST; i += G) r[i] = (i < D) ? A.root_m[i] : A.root_L[i - D];
-  }
-  if (A.root_m) {
-    if (A.block_sync) __syncthreads(); else grid.sync();
-  }
-  // ---- down-sweep (state form)
-  for (int l = A.down_begin; l > A.down_end; --l) {
-    const double* ps = A.st + A.off[l] * ST;
-    const double* el = A.agg + A.off[l - 1] * EL;
-    double* cs = A.st + A.off[l - 1] * ST;
-    const long na = A.sz[l - 1], nb = A.sz[l];
-    for (long i = g0; i < nb; i += ng) {
-      const double* p = ps + i * ST;
-      if constexpr (FILT) {
-        group_copy<D, G>(cx.r, cs + 2 * i * ST, p, ST);
-        if (2 * i + 1 < na) TL::template filter_combine<true>(cx, p, el + 2 * i * EL, cs + (2 * i + 1) * ST);
-      } else {
-        if (2 * i + 1 < na) {
-          group_copy<D, G>(cx.r, cs + (2 * i + 1) * ST, p, ST);
-          TL::template smooth_combine<true>(cx, p, el + (2 * i + 1) * EL, cs + 2 * i * ST);
+    // dependencies (at most two flags)
+    const unsigned* dep0 = nullptr;
+    const unsigned* dep1 = nullptr;
+    if (live && kind == FlowArgs::UP) {
+      if (lev - 1 >= A.up_lo && lev - 1 <= A.up_hi) {
+        dep0 = A.flag_up + A.off[lev - 1] + 2 * i;
+        if (2 * i + 1 < A.sz[lev - 1]) dep1 = dep0 + 1;
+      }
+    } else if (live && kind == FlowArgs::DOWN) {
+      dep0 = A.flag_dn + A.off[lev] + i;
+      const long e = FILT ? 2 * i : 2 * i + 1;  // the child element the combine reads
+      if (2 * i + 1 < A.sz[lev - 1] && lev - 1 >= A.up_lo && lev - 1 <= A.up_hi) dep1 = A.flag_up + A.off[lev - 1] + e;
+    }
+    while (true) {
+      const bool ok = (!dep0 || ld_acquire(dep0) != 0u) && (!dep1 || ld_acquire(dep1) != 0u);
+      if (__all_sync(0xffffffffu, ok)) break;
+      __nanosleep(64);
+    }
+    __syncwarp();
+    if (live) {
+      if (kind == FlowArgs::UP) {
+        const double* lc = A.agg + (A.off[lev - 1] + 2 * i) * EL;
+        double* pa = A.agg + (A.off[lev] + i) * EL;
+        if (2 * i + 1 < A.sz[lev - 1]) {
+          if constexpr (FILT) TL::template filter_combine<false>(cx, lc, lc + EL, pa);
+          else TL::template smooth_combine<false>(cx, lc + EL, lc, pa);
         } else {
+          group_copy<D, G>(cx.r, pa, lc, EL);
+        }
+        __threadfence();
+        cx.sync();
+        if (cx.r == 0) st_release(A.flag_up + A.off[lev] + i, 1u);
+      } else if (kind == FlowArgs::ROOT) {
+        double* r = A.st + A.off[A.nlev - 1] * ST;
+        for (int j = cx.r; j < ST; j += G) r[j] = (j < D) ? __ldcg(A.root_m + j) : __ldcg(A.root_L + (j - D));
+        __threadfence();
+        cx.sync();
+        if (cx.r == 0) st_release(A.flag_dn + A.off[A.nlev - 1], 1u);
+      } else {
+        const double* p = A.st + (A.off[lev] + i) * ST;
+        const double* el = A.agg + A.off[lev - 1] * EL;
+        double* cs = A.st + A.off[lev - 1] * ST;
+        const bool two = 2 * i + 1 < A.sz[lev - 1];
+        if constexpr (FILT) {
           group_copy<D, G>(cx.r, cs + 2 * i * ST, p, ST);
+          if (two) TL::template filter_combine<true>(cx, p, el + 2 * i * EL, cs + (2 * i + 1) * ST);
+        } else {
+          if (two) {
+            group_copy<D, G>(cx.r, cs + (2 * i + 1) * ST, p, ST);
+            TL::template smooth_combine<true>(cx, p, el + (2 * i + 1) * EL, cs + 2 * i * ST);
+          } else {
+            group_copy<D, G>(cx.r, cs + 2 * i * ST, p, ST);
+          }
+        }
+        __threadfence();
+        cx.sync();
+        if (cx.r == 0) {
+          st_release(A.flag_dn + A.off[lev - 1] + 2 * i, 1u);
+          if (two) st_release(A.flag_dn + A.off[lev - 1] + 2 * i + 1, 1u);
         }
       }
     }
-    if (l > A.down_end + 1) {
-      if (A.block_sync) __syncthreads(); else grid.sync();
-    }
+    __syncwarp();
   }
 }
 
@@ -162,15 +188,14 @@ struct TreeLaunchers {
     k_tree<D, OP><<<(unsigned)((nb + per_block - 1) / per_block), TL_WARPS * 32, smem, s>>>(a, na, b, c, nb);
     return cudaGetLastError();
   }
-  // cooperative whole-sweep launch; the grid is the smaller of "all CTAs co-resident" and "one group per node of the
-  // widest level"
+  // dataflow whole-sweep launch: persistent grid (enough warps for the widest level, at most what is resident)
   template <bool FILT>
-  static cudaError_t sweep(cudaStream_t s, const SweepArgs& A) {
+  static cudaError_t flow(cudaStream_t s, const FlowArgs& A) {
     constexpr int G = FILT ? TL::G2 : TL::GS;
-    constexpr int CPWmin = 32 / TL::G2;  // the chunk-level prologue of the smoothing sweep uses G2 lanes per item
-    constexpr int smem = TL_WARPS * (32 / G) * TL::SM_COMBINE * (int)sizeof(double);
-    auto kern = k_tree_sweep<D, FILT>;
-    if (cudaError_t e = ensure_smem(kern, smem)) return e;
+    constexpr int CPW = 32 / G;
+    constexpr int smem = TL_WARPS * CPW * TL::SM_COMBINE * (int)sizeof(double);
+    auto kern = k_tree_flow<D, FILT>;
+    if (cudaError_t e = ensure_smem(kern, smem, !FILT)) return e;
     static int max_grid[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -182,29 +207,23 @@ struct TreeLaunchers {
       if (per_sm < 1) return cudaErrorLaunchOutOfResources;
       max_grid[dev] = per_sm * sms;
     }
-    if (A.block_sync) {  // the apex: one CTA, plain launch
-      k_tree_sweep<D, FILT><<<1, TL_WARPS * 32, smem, s>>>(A);
-      return cudaGetLastError();
-    }
+    FlowArgs a = A;
     long widest = 1;
-    if (A.up_end > A.up_begin) widest = A.sz[A.up_begin + 1];
-    if (A.down_begin > A.down_end && A.sz[A.down_end + 1] > widest) widest = A.sz[A.down_end + 1];
-    long blocks = (widest + (long)TL_WARPS * (32 / G) - 1) / ((long)TL_WARPS * (32 / G));
-    if (!FILT && A.faggm) {
-      const long b2 = (A.sz[0] + (long)TL_WARPS * CPWmin - 1) / ((long)TL_WARPS * CPWmin);
-      if (b2 > blocks) blocks = b2;
+    a.seg_begin[0] = 0;
+    for (int j = 0; j < a.nseg; ++j) {
+      const long n = a.seg_count[j];
+      if (n > widest) widest = n;
+      a.seg_begin[j + 1] = a.seg_begin[j] + (n + CPW - 1) / CPW * CPW;
     }
+    long blocks = (widest + (long)TL_WARPS * CPW - 1) / ((long)TL_WARPS * CPW);
     if (blocks < 1) blocks = 1;
     if (blocks > max_grid[dev]) blocks = max_grid[dev];
-    SweepArgs a = A;
-    void* params[] = {(void*)&a};
-    return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3(TL_WARPS * 32), params,
-                                       (size_t)smem, s);
+    k_tree_flow<D, FILT><<<(unsigned)blocks, TL_WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
   }
   static const TreeLaunch* get() {
     static const TreeLaunch t = {&run<T_FUP>, &run<T_FDOWN>, &run<T_SUP>, &run<T_SDOWN>, &run<T_FCOMB>, &run<T_SCOMB>,
-                                 &run<T_CHUNKK>, &sweep<true>, &sweep<false>,
-                                 TL_WARPS * (32 / TL::G2), TL_WARPS * (32 / TL::GS)};
+                                 &run<T_CHUNKK>, &flow<true>, &flow<false>};
     return &t;
   }
 };

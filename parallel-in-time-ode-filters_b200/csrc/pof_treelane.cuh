@@ -178,9 +178,23 @@ struct TreeLane {
       for (int j = 0; j < D; ++j) y[j] = fma(a, M2[k * LDM + j], y[j]);
     }
   }
-  static __device__ __forceinline__ void load_row(const double* __restrict__ p, double (&x)[D]) {
+  // Operand loads go to L2 (ld.global.cg): inside a dataflow sweep (k_tree_flow) the operands were written by other
+  // SMs during the SAME kernel, and a node's first/last cache line can be shared with its neighbour's, so a line
+  // cached in L1 by an earlier read may be stale.  (Per-level launches read L2-resident data anyway.)
+  static __device__ __forceinline__ double ldg(const double* p) { return __ldcg(p); }
+  static __device__ __forceinline__ void load_row(const double* p, double (&x)[D]) {
+    if constexpr (D % 2 == 0) {
+      const double2* p2 = reinterpret_cast<const double2*>(p);
 #pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = p[j];
+      for (int j = 0; j < D / 2; ++j) {
+        const double2 v = __ldcg(p2 + j);
+        x[2 * j] = v.x;
+        x[2 * j + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) x[j] = __ldcg(p + j);
+    }
   }
   static __device__ __forceinline__ void store_row_tri(double* __restrict__ p, int row, const double* x) {
 #pragma unroll
@@ -255,14 +269,22 @@ struct TreeLane {
     const double* n2 = e2 + 2 * DD + D;
     const double* Z2 = e2 + 2 * DD + 2 * D;
 
-    // stage U1, Z2 (and A1): lanes [0,D) publish U1 rows, lanes [D,2D) publish Z2 rows
-    double u1[D], z2[D], a1[D];
+    // ALL global operands are loaded here, in one round of independent loads: every later load would sit behind a
+    // __syncwarp (a memory barrier the compiler cannot hoist loads across) and cost its own L2 round trip (~0.4 us)
+    // on the dependent chain of the sweep -- five such round trips per combine before this was hoisted.
+    double u1[D], z2[D], a1[D], a2[D], q2[D];
     load_row(U1 + rr * D, u1);
     load_row(Z2 + rr * D, z2);
+    if (!STATE) load_row(A1 + rr * D, a1);
+    load_row(A2 + rr * D, a2);
+    load_row((bot && !STATE) ? Z1 + rr * D : U2 + rr * D, q2);
+    const double b1r = ldg(b1 + rr), n2r = ldg(n2 + rr), b2r = ldg(b2 + rr);
+    double n1r = 0.0;
+    if (!STATE) n1r = ldg(n1 + rr);
+    // stage U1, Z2 (and A1): lanes [0,D) publish U1 rows, lanes [D,2D) publish Z2 rows
     if (top) put_row(cx, mU1, rr, u1);
     if (bot) put_row(cx, mZ2, rr, z2);
     if (!STATE) {
-      load_row(A1 + rr * D, a1);
       if (top) put_row(cx, mA1, rr, a1);
     }
     cx.sync();
@@ -328,18 +350,16 @@ struct TreeLane {
     if (top) put_row(cx, mG, rr, g);
     cx.sync();
     // ---- b = A2 G (b1 + U1 U1^T eta2) + b2
-    double a2[D];
-    load_row(A2 + rr * D, a2);
     {
       double v[D], t[D];
-      allgather<D>(cx, top ? n2[rr] : 0.0, v);
+      allgather<D>(cx, top ? n2r : 0.0, v);
       // (U1^T eta2)[rr]: column rr of U1
       double s = 0.0;
       const double* MU = cx.mat(mU1);
 #pragma unroll
       for (int k = 0; k < D; ++k) s = fma(MU[k * LDM + rr], v[k], s);
       allgather<D>(cx, s, t);
-      double t0 = b1[rr];
+      double t0 = b1r;
 #pragma unroll
       for (int k = 0; k < D; ++k) t0 = fma(u1[k], t[k], t0);
       allgather<D>(cx, t0, v);
@@ -347,7 +367,7 @@ struct TreeLane {
 #pragma unroll
       for (int k = 0; k < D; ++k) t2 = fma(g[k], v[k], t2);
       allgather<D>(cx, t2, t);
-      double bo = b2[rr];
+      double bo = b2r;
 #pragma unroll
       for (int k = 0; k < D; ++k) bo = fma(a2[k], t[k], bo);
       if (top) (STATE ? out : out + DD)[rr] = bo;
@@ -355,9 +375,8 @@ struct TreeLane {
     // ---- rows for the second triangularisation: top: [A2 Y | U2] -> U ; bottom: [A1^T Xi22 | Z1] -> Z
     double x2[W2];
     {
-      double p[D], q2[D];
+      double p[D];
       row_times(cx, mY, a2, p);
-      load_row((bot && !STATE) ? Z1 + rr * D : U2 + rr * D, q2);
       if (!STATE) {
         double pz[D];
         col_times(cx, mA1, rr, mX22, pz);
@@ -383,13 +402,13 @@ struct TreeLane {
       }
       // ---- eta = A1^T G^T (eta2 - Z2 Z2^T b1) + eta1
       double v[D], t[D];
-      allgather<D>(cx, top ? b1[rr] : 0.0, v);
+      allgather<D>(cx, top ? b1r : 0.0, v);
       double s = 0.0;
       const double* MZ = cx.mat(mZ2);
 #pragma unroll
       for (int k = 0; k < D; ++k) s = fma(MZ[k * LDM + rr], v[k], s);  // (Z2^T b1)[rr]
       allgather<D>(cx, s, t);
-      double s0 = n2[rr];
+      double s0 = n2r;
 #pragma unroll
       for (int k = 0; k < D; ++k) s0 = fma(-MZ[rr * LDM + k], t[k], s0);  // eta2 - Z2 (Z2^T b1)
       allgather<D>(cx, s0, v);
@@ -398,7 +417,7 @@ struct TreeLane {
 #pragma unroll
       for (int k = 0; k < D; ++k) s2 = fma(MG[k * LDM + rr], v[k], s2);  // (G^T s)[rr]
       allgather<D>(cx, s2, t);
-      double eo = n1[rr];
+      double eo = n1r;
       const double* MA = cx.mat(mA1);
 #pragma unroll
       for (int k = 0; k < D; ++k) eo = fma(MA[k * LDM + rr], t[k], eo);  // (A1^T .)[rr]
@@ -430,9 +449,12 @@ struct TreeLane {
     const double* U2 = e2 + DD + D;
     const double* n2 = e2 + 2 * DD + D;
     const double* Z2 = e2 + 2 * DD + 2 * D;
-    double u1[D], z2[D];
+    double u1[D], z2[D], a2[D], q2[D];
     load_row(U1 + rr * D, u1);
     load_row(Z2 + rr * D, z2);
+    load_row(A2 + rr * D, a2);
+    load_row(U2 + rr * D, q2);
+    const double b1r = ldg(b1 + rr), n2r = ldg(n2 + rr), b2r = ldg(b2 + rr);
     if (top) put_row(cx, mU1, rr, u1);
     if (bot) put_row(cx, mZ2, rr, z2);
     cx.sync();
@@ -479,19 +501,17 @@ struct TreeLane {
       }
     }
     cx.sync();
-    double a2[D];
-    load_row(A2 + rr * D, a2);
     // m' = G (m + L L^T eta)  and  v = A m' + b
     double mp[D], vf[D];
     {
       double v[D], t[D];
-      allgather<D>(cx, top ? n2[rr] : 0.0, v);
+      allgather<D>(cx, top ? n2r : 0.0, v);
       double s = 0.0;
       const double* MU = cx.mat(mU1);
 #pragma unroll
       for (int k = 0; k < D; ++k) s = fma(MU[k * LDM + rr], v[k], s);
       allgather<D>(cx, s, t);
-      double t0 = b1[rr];
+      double t0 = b1r;
 #pragma unroll
       for (int k = 0; k < D; ++k) t0 = fma(u1[k], t[k], t0);
       allgather<D>(cx, t0, v);
@@ -499,7 +519,7 @@ struct TreeLane {
 #pragma unroll
       for (int k = 0; k < D; ++k) t2 = fma(g[k], v[k], t2);
       allgather<D>(cx, t2, mp);
-      double av = b2[rr];
+      double av = b2r;
 #pragma unroll
       for (int k = 0; k < D; ++k) av = fma(a2[k], mp[k], av);
       allgather<D>(cx, av, vf);
@@ -507,9 +527,8 @@ struct TreeLane {
     // joint array [[A Y, U],[Y, 0]]
     double x2[W2];
     {
-      double p[D], q2[D];
+      double p[D];
       row_times(cx, mY, a2, p);
-      load_row(U2 + rr * D, q2);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         x2[j] = top ? p[j] : (bot ? y[j] : 0.0);
@@ -567,17 +586,18 @@ struct TreeLane {
     const double* g2 = e2;
     const double* E2 = e2 + D;
     const double* D2 = e2 + D + DD;
-    double row[D];
+    double row[D], row1[D], e2r[D], d2[D], v[D];
     load_row(D1 + rr * D, row);
+    if (!STATE) load_row(E1 + rr * D, row1);
+    load_row(E2 + rr * D, e2r);
+    load_row(D2 + rr * D, d2);
+    const double g1r = ldg(g1 + rr), g2r = ldg(g2 + rr);
     if (act) put_row(cx, mU1, rr, row);
     if (!STATE) {
-      load_row(E1 + rr * D, row);
-      if (act) put_row(cx, mA1, rr, row);
+      if (act) put_row(cx, mA1, rr, row1);
     }
-    double e2r[D], v[D];
-    load_row(E2 + rr * D, e2r);
-    allgather<D>(cx, act ? g1[rr] : 0.0, v);  // also orders the put_rows before the reads below
-    double go = g2[rr];
+    allgather<D>(cx, act ? g1r : 0.0, v);  // also orders the put_rows before the reads below
+    double go = g2r;
 #pragma unroll
     for (int k = 0; k < D; ++k) go = fma(e2r[k], v[k], go);
     if (act) out[rr] = go;
@@ -591,9 +611,8 @@ struct TreeLane {
     }
     double x[W2];
     {
-      double p[D], d2[D];
+      double p[D];
       row_times(cx, mU1, e2r, p);
-      load_row(D2 + rr * D, d2);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         x[j] = p[j];

@@ -40,51 +40,56 @@ def _load():
             "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback."
         )
     lib = ctypes.CDLL(LIB_PATH)
+    U = ctypes.c_uint32
     sig = {
         "pof_supported": (_c_int, [_c_int, _c_int]),
-        "pof_default_chunk_len": (_c_i64, [_c_i64, _c_int, _c_int, _c_int]),
+        "pof_supported_tile": (_c_int, [_c_int, _c_int]),
+        "pof_ctx_create": (_c_int, [ctypes.POINTER(ctypes.c_void_p)]),
+        "pof_ctx_destroy": (None, [_c_dp]),
+        "pof_ctx_profile_enable": (None, [_c_dp, _c_int]),
+        "pof_ctx_profile_read": (_c_int, [_c_dp, _c_dp, _c_dp]),
+        "pof_launches_per_pass": (_c_i64, [_c_i64, _c_int, _c_int, _c_i64, U]),
+        "pof_measure_dfma_tflops": (_c_int, [_c_dp, _c_dp]),
+        "pof_default_chunk_len": (_c_i64, [_c_i64, _c_int, _c_int, _c_int, U]),
         "pof_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_i64]),
-        "pof_filter_combine_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_dp, _c_dp, _c_dp]),
-        "pof_smooth_combine_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_dp, _c_dp, _c_dp]),
+        "pof_filter_combine_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_dp, _c_dp, _c_dp, U]),
+        "pof_smooth_combine_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_dp, _c_dp, _c_dp, U]),
         "pof_linearize_ivp_f64": (
             _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_dp]),
-        "pof_linear_filtsmooth_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
-                     _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
-        "pof_linear_filtsmooth_general_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
-                     _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
-        "pof_supported_tile": (_c_int, [_c_int, _c_int]),
-        "pof_default_chunk_len_tile": (_c_i64, [_c_i64, _c_int, _c_int, _c_int]),
-        "pof_ieks_iteration_f64": (
-            _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
-                     _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
-        "pof_sequential_eks_f64": (
-            _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_dp,
-                     _c_dp, _c_dp, _c_dp, _c_sz]),
-        "pof_shard_stage_a_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
-        "pof_shard_stage_b_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
-                     _c_dp, _c_dp, _c_sz]),
         "pof_linearize_ivp_compact_f64": (
             _c_int, [_c_dp, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp]),
-        "pof_shard_stage_a_compact_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_sz]),
-        "pof_shard_stage_b_compact_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp,
+        # (stream, ctx, flags, N, d, q, chunk_len, qL, x0m, x0c, H, c, means, chols, fmeans, fchols, calibrate,
+        #  scalars, ws, ws_bytes)
+        "pof_linear_filtsmooth_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_linear_filtsmooth_general_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_ieks_iteration_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dbl, _c_dbl,
+                     _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_sequential_eks_f64": (
+            _c_int, [_c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_a_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_b_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
                      _c_dp, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_stage_a_compact_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
+                     _c_sz]),
+        "pof_shard_stage_b_compact_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
         "pof_shard_stage_c_f64": (
-            _c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp,
-                     _c_dp, _c_sz]),
-        "pof_filter_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
-        "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
+            _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_int, _c_int, _c_dp, _c_dp,
+                     _c_dp, _c_dp, _c_dp, _c_sz]),
+        "pof_filter_apply_chain_f64": (_c_int, [_c_dp, U, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, U, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_prior_init_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
-        "pof_profile_enable": (None, [_c_int]),
-        "pof_profile_read": (_c_int, [_c_dp, _c_dp]),
-        "pof_launches_per_pass": (_c_i64, [_c_i64, _c_int, _c_int, _c_i64]),
-        "pof_measure_dfma_tflops": (_c_int, [_c_dp, _c_dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -95,14 +100,25 @@ def _load():
 
 LIB = _load()
 EXPORTED = [
-    "pof_supported", "pof_default_chunk_len", "pof_workspace_bytes", "pof_filter_combine_f64",
-    "pof_smooth_combine_f64", "pof_linearize_ivp_f64", "pof_linear_filtsmooth_f64", "pof_ieks_iteration_f64", "pof_sequential_eks_f64",
-    "pof_shard_stage_a_f64",
-    "pof_shard_stage_b_f64", "pof_shard_stage_c_f64", "pof_linearize_ivp_compact_f64",
-    "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64",
-    "pof_project_f64", "pof_profile_enable", "pof_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops",
-    "pof_linear_filtsmooth_general_f64", "pof_supported_tile", "pof_default_chunk_len_tile", "pof_prior_init_f64",
+    "pof_supported", "pof_supported_tile", "pof_ctx_create", "pof_ctx_destroy", "pof_ctx_profile_enable",
+    "pof_ctx_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops", "pof_default_chunk_len",
+    "pof_workspace_bytes", "pof_filter_combine_f64", "pof_smooth_combine_f64", "pof_linearize_ivp_f64",
+    "pof_linearize_ivp_compact_f64", "pof_linear_filtsmooth_f64", "pof_linear_filtsmooth_general_f64",
+    "pof_ieks_iteration_f64", "pof_sequential_eks_f64", "pof_shard_stage_a_f64", "pof_shard_stage_b_f64",
+    "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_shard_stage_c_f64",
+    "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64", "pof_project_f64", "pof_prior_init_f64",
 ]
+
+# kernel-family flags of the C ABI (include/pof_b200.h).  DEFAULT_FLAGS is what the facade passes; tests / scripts may
+# change it (e.g. F_FAMILY_TILE to run the large-state kernels on small problems) -- the library itself holds no
+# switches and reads no environment variables.
+F_FAMILY_TILE, F_TILE_SMEM_QR, F_TREE_PER_LEVEL = 1, 2, 4
+DEFAULT_FLAGS = int(os.environ.get("POF_B200_FLAGS", "0"))
+SEGMENTS = ["fold", "filter_up_sharded", "filter_tree", "scan", "smooth_up_side_stream", "smooth_down", "smooth"]
+
+
+def flags(extra=0):
+    return ctypes.c_uint32(int(DEFAULT_FLAGS) | int(extra))
 
 
 def check(rc, what):
@@ -144,6 +160,41 @@ def sm_count(device=None):
     return _SM_COUNT[dev]
 
 
+class Context:
+    """Caller-owned execution context of the C ABI (pof_ctx_t): the side stream on which a pass runs the smoother's
+    up-sweep concurrently with the filter scan, plus optional per-segment timing."""
+
+    def __init__(self, device=None):
+        self._p = ctypes.c_void_p()
+        if device is not None and torch.cuda.is_available():
+            with torch.cuda.device(device):
+                check(LIB.pof_ctx_create(ctypes.byref(self._p)), "pof_ctx_create")
+        else:
+            check(LIB.pof_ctx_create(ctypes.byref(self._p)), "pof_ctx_create")
+
+    @property
+    def ptr(self):
+        return self._p
+
+    def profile_enable(self, on=True):
+        LIB.pof_ctx_profile_enable(self._p, int(bool(on)))
+
+    def profile_read(self):
+        """-> dict segment name -> (accumulated ms, count); synchronises the device"""
+        ms = (ctypes.c_double * len(SEGMENTS))()
+        cnt = (ctypes.c_int64 * len(SEGMENTS))()
+        check(LIB.pof_ctx_profile_read(self._p, ms, cnt), "pof_ctx_profile_read")
+        return {nm: (ms[i], cnt[i]) for i, nm in enumerate(SEGMENTS)}
+
+    def __del__(self):
+        try:
+            if self._p:
+                LIB.pof_ctx_destroy(self._p)
+                self._p = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
 class Workspace:
     """Caller-owned scratch memory for one problem shape (N, d, q, chunk_len) on one device.
 
@@ -162,6 +213,11 @@ class Workspace:
         self.N, self.d, self.q, self.chunk_len = int(N), int(d), int(q), int(chunk_len)
         self.nbytes = int(LIB.pof_workspace_bytes(self.N, self.d, self.q, self.chunk_len))
         self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.ctx = Context(device)  # side stream + events of the passes that use this workspace
+
+    @property
+    def ws_ptr(self):
+        return ctypes.c_void_p(self.buf.data_ptr())
 
     def matches(self, N, d, q, chunk_len):
         return (self.N, self.d, self.q, self.chunk_len) == (int(N), int(d), int(q), int(chunk_len))
@@ -179,10 +235,10 @@ class Workspace:
         return ws
 
 
-def default_chunk_len(N, d, q, device=None):
-    return int(LIB.pof_default_chunk_len(int(N), int(d), int(q), sm_count(device)))
+def default_chunk_len(N, d, q, device=None, extra_flags=0):
+    return int(LIB.pof_default_chunk_len(int(N), int(d), int(q), sm_count(device), flags(extra_flags)))
 
 
 def default_chunk_len_tile(N, d, q, device=None):
     """chunk length for the large-state (CTA-per-chunk) kernels, which also serve noisy observations"""
-    return int(LIB.pof_default_chunk_len_tile(int(N), int(d), int(q), sm_count(device)))
+    return default_chunk_len(N, d, q, device, F_FAMILY_TILE)

@@ -66,16 +66,16 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
     qLh, qLp = nat.host_doubles(qL)
     if general:
         rc = nat.LIB.pof_linear_filtsmooth_general_f64(
-            nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(Fd), nat.ptr(QLd), nat.ptr(x0.mean),
+            nat.stream_ptr(), ws.ctx.ptr, nat.flags(), N, d, q, int(chunk_len), qLp, nat.ptr(Fd), nat.ptr(QLd), nat.ptr(x0.mean),
             nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c), nat.ptr(cholR), nat.ptr(means_io), nat.ptr(chols),
             nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)), nat.ptr(scalars),
-            ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+            ws.ws_ptr, ws.nbytes)
         nat.check(rc, "pof_linear_filtsmooth_general_f64")
         return scalars
     rc = nat.LIB.pof_linear_filtsmooth_f64(
-        nat.stream_ptr(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
+        nat.stream_ptr(), ws.ctx.ptr, nat.flags(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
         nat.ptr(means_io), nat.ptr(chols), nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)), nat.ptr(scalars),
-        ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+        ws.ws_ptr, ws.nbytes)
     nat.check(rc, "pof_linear_filtsmooth_f64")
     return scalars
 
@@ -99,9 +99,9 @@ def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len
     ph, pp = nat.host_doubles(list(params) + [0.0])
     qLh, qLp = nat.host_doubles(qL)
     rc = nat.LIB.pof_ieks_iteration_f64(
-        nat.stream_ptr(), ivp_id, pp, len(params), N, d, q, int(chunk_len), qLp, lin["scale0"], lin["scale1"],
+        nat.stream_ptr(), ws.ctx.ptr, nat.flags(), ivp_id, pp, len(params), N, d, q, int(chunk_len), qLp, lin["scale0"], lin["scale1"],
         nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(means_io), nat.ptr(chols), int(bool(calibrate)),
-        nat.ptr(scalars), ctypes.c_void_p(ws.buf.data_ptr()), ws.nbytes)
+        nat.ptr(scalars), ws.ws_ptr, ws.nbytes)
     nat.check(rc, "pof_ieks_iteration_f64")
     return scalars
 
@@ -214,7 +214,8 @@ def sqrt_filtering_operator(elem1, elem2):
     e1, e2 = _pack(elem1), _pack(elem2)
     nat.require_cuda(e1, e2)
     out = torch.empty_like(e1)
-    nat.check(nat.LIB.pof_filter_combine_f64(nat.stream_ptr(), n, D, nat.ptr(e1), nat.ptr(e2), nat.ptr(out)),
+    nat.check(nat.LIB.pof_filter_combine_f64(nat.stream_ptr(), n, D, nat.ptr(e1), nat.ptr(e2), nat.ptr(out),
+                                             nat.flags()),
               "pof_filter_combine_f64")
     DD = D * D
     return (out[:, :DD].reshape(n, D, D), out[:, DD:DD + D], out[:, DD + D:2 * DD + D].reshape(n, D, D),
@@ -227,7 +228,8 @@ def sqrt_smoothing_operator(elem1, elem2):
     e1, e2 = _pack(elem1), _pack(elem2)
     nat.require_cuda(e1, e2)
     out = torch.empty_like(e1)
-    nat.check(nat.LIB.pof_smooth_combine_f64(nat.stream_ptr(), n, D, nat.ptr(e1), nat.ptr(e2), nat.ptr(out)),
+    nat.check(nat.LIB.pof_smooth_combine_f64(nat.stream_ptr(), n, D, nat.ptr(e1), nat.ptr(e2), nat.ptr(out),
+                                             nat.flags()),
               "pof_smooth_combine_f64")
     DD = D * D
     return out[:, :D], out[:, D:D + DD].reshape(n, D, D), out[:, D + DD:].reshape(n, D, D)

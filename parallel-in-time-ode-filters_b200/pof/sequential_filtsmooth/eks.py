@@ -29,9 +29,8 @@ def eks_filtsmooth(setup):
     ph, pp = nat.host_doubles(list(params) + [0.0])
     qLh, qLp = nat.host_doubles(setup["_qL"])
     rc = nat.LIB.pof_sequential_eks_f64(
-        nat.stream_ptr(), ivp_id, pp, len(params), N, d, q, qLp, lin["scale0"], lin["scale1"], nat.ptr(x0.mean),
-        nat.ptr(x0.chol), nat.ptr(means), nat.ptr(chols), nat.ptr(scalars), ctypes.c_void_p(ws.buf.data_ptr()),
-        ws.nbytes)
+        nat.stream_ptr(), nat.flags(), ivp_id, pp, len(params), N, d, q, qLp, lin["scale0"], lin["scale1"],
+        nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(means), nat.ptr(chols), nat.ptr(scalars), ws.ws_ptr, ws.nbytes)
     nat.check(rc, "pof_sequential_eks_f64")
     sc = scalars.cpu()
     return MVNSqrt(means, chols), float(sc[nat.S_NLL]), float(sc[nat.S_OBJ]), float(sc[nat.S_SSQ])

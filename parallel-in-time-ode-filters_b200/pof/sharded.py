@@ -45,7 +45,7 @@ class CudaBackend:
         self.scratch = torch.empty(D + D * D, dtype=torch.float64, device=device)
 
     def _ws(self):
-        return ctypes.c_void_p(self.ws.buf.data_ptr()), self.ws.nbytes
+        return self.ws.ws_ptr, self.ws.nbytes
 
     def set_compact(self, scale0, scale1):
         """H arguments of stage_a/b are then the compact linearisation [J_f | c] (c must be None)"""
@@ -55,40 +55,40 @@ class CudaBackend:
         p, nb = self._ws()
         if c is None:
             s0, s1 = self.scales
-            nat.check(nat.LIB.pof_shard_stage_a_compact_f64(nat.stream_ptr(), self.n_loc, self.d, self.q,
+            nat.check(nat.LIB.pof_shard_stage_a_compact_f64(nat.stream_ptr(), self.ws.ctx.ptr, nat.flags(), self.n_loc, self.d, self.q,
                                                             self.chunk_len, self.qLp, nat.ptr(H), s0, s1,
                                                             nat.ptr(carry_f), p, nb), "stage_a")
             return
-        nat.check(nat.LIB.pof_shard_stage_a_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
+        nat.check(nat.LIB.pof_shard_stage_a_f64(nat.stream_ptr(), self.ws.ctx.ptr, nat.flags(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
                                                 nat.ptr(H), nat.ptr(c), nat.ptr(carry_f), p, nb), "stage_a")
 
     def stage_b(self, H, c, state_in, fmeans, fchols, carry_s, state_end, partials):
         p, nb = self._ws()
         if c is None:
             s0, s1 = self.scales
-            nat.check(nat.LIB.pof_shard_stage_b_compact_f64(nat.stream_ptr(), self.n_loc, self.d, self.q,
+            nat.check(nat.LIB.pof_shard_stage_b_compact_f64(nat.stream_ptr(), self.ws.ctx.ptr, nat.flags(), self.n_loc, self.d, self.q,
                                                             self.chunk_len, self.qLp, nat.ptr(H), s0, s1,
                                                             nat.ptr(state_in), nat.ptr(fmeans), nat.ptr(fchols),
                                                             nat.ptr(carry_s), nat.ptr(state_end), nat.ptr(partials), p,
                                                             nb), "stage_b")
             return
-        nat.check(nat.LIB.pof_shard_stage_b_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
+        nat.check(nat.LIB.pof_shard_stage_b_f64(nat.stream_ptr(), self.ws.ctx.ptr, nat.flags(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
                                                 nat.ptr(H), nat.ptr(c), nat.ptr(state_in), nat.ptr(fmeans),
                                                 nat.ptr(fchols), nat.ptr(carry_s), nat.ptr(state_end),
                                                 nat.ptr(partials), p, nb), "stage_b")
 
     def stage_c(self, seed, is_last, has_row0, cscale, means, chols, partials2):
         p, nb = self._ws()
-        nat.check(nat.LIB.pof_shard_stage_c_f64(nat.stream_ptr(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
+        nat.check(nat.LIB.pof_shard_stage_c_f64(nat.stream_ptr(), self.ws.ctx.ptr, nat.flags(), self.n_loc, self.d, self.q, self.chunk_len, self.qLp,
                                                 nat.ptr(seed), int(is_last), int(has_row0), nat.ptr(cscale),
                                                 nat.ptr(means), nat.ptr(chols), nat.ptr(partials2), p, nb), "stage_c")
 
     def filter_chain(self, D, count, state_in, elems, state_out):
-        nat.check(nat.LIB.pof_filter_apply_chain_f64(nat.stream_ptr(), D, count, nat.ptr(state_in), nat.ptr(elems),
+        nat.check(nat.LIB.pof_filter_apply_chain_f64(nat.stream_ptr(), nat.flags(), D, count, nat.ptr(state_in), nat.ptr(elems),
                                                      nat.ptr(state_out), nat.ptr(self.scratch)), "filter_chain")
 
     def smooth_chain(self, D, count, state_in, elems, state_out):
-        nat.check(nat.LIB.pof_smooth_apply_chain_f64(nat.stream_ptr(), D, count, nat.ptr(state_in), nat.ptr(elems),
+        nat.check(nat.LIB.pof_smooth_apply_chain_f64(nat.stream_ptr(), nat.flags(), D, count, nat.ptr(state_in), nat.ptr(elems),
                                                      nat.ptr(state_out), nat.ptr(self.scratch)), "smooth_chain")
 
 

@@ -39,7 +39,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--d", type=int, default=16)
     ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--flags", type=int, default=0, help="2 = shared-memory Householder sweeps (A/B)")
     a = ap.parse_args()
+    nat.DEFAULT_FLAGS = a.flags
     torch.cuda.set_device(0)
     d, q = a.d, a.order
     D = d * (q + 1)
@@ -47,14 +49,16 @@ def main():
     ivp = pof.ivp.lorenz96(d=d, tmax=10.0)
     ts = np.linspace(ivp.t0, ivp.tmax, N)
     setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
-    st = get_initial_trajectory(setup, method="constant")
+    st = get_initial_trajectory(setup, method="constant", means_only=True)
     lin = setup["om"].f._pof_lin
     means0 = st.mean.contiguous()
     means = means0.clone()
     chols = torch.empty((N, D, D), dtype=torch.float64, device=means.device)
     sc = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=means.device)
     L = nat.default_chunk_len(N, d, q)
-    it = lambda: run_iteration(setup["x0"], setup["_qL"], lin, means, chols, calibrate=True, scalars=sc, chunk_len=L)
+    ws = nat.Workspace(N, d, q, L, means.device)
+    it = lambda: run_iteration(setup["x0"], setup["_qL"], lin, means, chols, calibrate=True, scalars=sc, chunk_len=L,
+                               ws=ws)
     for _ in range(max(a.warmup, 1)):
         it()
     torch.cuda.synchronize()
@@ -66,23 +70,20 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     # per-segment device times (CUDA events inside the library)
-    nat.LIB.pof_profile_enable(1)
+    ws.ctx.profile_enable(True)
     it()
-    seg = (ctypes.c_double * 7)()
-    cnt = (ctypes.c_int64 * 7)()
-    nat.LIB.pof_profile_read(seg, cnt)
-    nat.LIB.pof_profile_enable(0)
+    segd = ws.ctx.profile_read()
+    ws.ctx.profile_enable(False)
     peak = ctypes.c_double(0.0)
     nat.LIB.pof_measure_dfma_tflops(nat.stream_ptr(), ctypes.byref(peak))
     flops = flop_step(D, d) * N
     achieved = flops / (ms * 1e-3) / 1e12
-    names = ["fold", "filter_up", "filter_down", "scan", "smooth_up", "smooth_down", "smooth"]
     out = {
         "metric": "ms per IEKS iteration (fp64)", "value": ms, "unit": "ms", "n_gpus": 1, "steps": a.steps,
         "warmup": a.warmup, "higher_is_better": False, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"BASELINE config 5: Lorenz-96 d={d} order={q} (D={D}), N=2^{a.log2n}, constant init",
                    "chunk_len": L, "kernels": "tile (CTA per chunk, shared-memory tiles)"},
-        "segments_ms": {n: seg[i] for i, n in enumerate(names)},
+        "segments_ms": {k: v[0] for k, v in segd.items()},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                      "frac": achieved / peak.value if peak.value else None,
                      "note": "reference-formula FLOPs (SURVEY 8d); the leaf recursions execute ~8x fewer"},

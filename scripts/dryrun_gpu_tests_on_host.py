@@ -40,9 +40,10 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(P)
 
 
-def _env_reg():
-    e = os.environ.get("POF_B200_TILE_SWEEP", "")
-    return 1 if e[:1] == "r" else 0
+def _reg(flags):
+    """register-resident Householder sweeps unless POF_F_TILE_SMEM_QR (2) is set"""
+    f = flags.value if hasattr(flags, "value") else int(flags)
+    return 0 if (f & 2) else 1
 
 
 class FakeLib:
@@ -58,7 +59,8 @@ class FakeLib:
     def _count(self, name):
         self.calls[name] = self.calls.get(name, 0) + 1
 
-    def _pass(self, N, d, q, L, qL, x0m, x0c, H, c, Jc, s0, s1, R, F, QL, means, chols, fm, fc, calibrate, scalars):
+    def _pass(self, N, d, q, L, qL, x0m, x0c, H, c, Jc, s0, s1, R, F, QL, means, chols, fm, fc, calibrate, scalars,
+              flags=0):
         D = d * (q + 1)
         n = N - 1
         qLa = np.ascontiguousarray(_arr(qL, (q + 1, q + 1))) if qL else np.zeros((q + 1, q + 1))
@@ -66,7 +68,7 @@ class FakeLib:
         sc = np.zeros(8)
         rc = HS.hs_tile_linear_filtsmooth(
             d, q, ctypes.c_long(N), ctypes.c_long(int(L)), _p(qLa), _p(x0), H, c, Jc, ctypes.c_double(s0),
-            ctypes.c_double(s1), R, F, QL, means, chols, fm, fc, int(calibrate), _p(sc), 0, _env_reg())
+            ctypes.c_double(s1), R, F, QL, means, chols, fm, fc, int(calibrate), _p(sc), 0, _reg(flags))
         out = _arr(scalars, (8,))
         nll, obj, ssq, ssqp, bad = sc[:5]
         out[:] = 0.0
@@ -75,19 +77,19 @@ class FakeLib:
         assert n >= 1
         return rc
 
-    def pof_linear_filtsmooth_f64(self, s, N, d, q, L, qL, x0m, x0c, H, c, means, chols, fm, fc, calibrate, scalars, ws,
-                                  ws_bytes):
+    def pof_linear_filtsmooth_f64(self, s, ctx, flags, N, d, q, L, qL, x0m, x0c, H, c, means, chols, fm, fc, calibrate,
+                                  scalars, ws, ws_bytes):
         self._count("pof_linear_filtsmooth_f64")
         assert ws_bytes >= self.real.pof_workspace_bytes(N, d, q, L)
         return self._pass(N, d, q, L, qL, x0m, x0c, H, c, None, 0.0, 0.0, None, None, None, means, chols, fm, fc,
-                          calibrate, scalars)
+                          calibrate, scalars, flags)
 
-    def pof_linear_filtsmooth_general_f64(self, s, N, d, q, L, qL, F, QL, x0m, x0c, H, c, R, means, chols, fm, fc,
-                                          calibrate, scalars, ws, ws_bytes):
+    def pof_linear_filtsmooth_general_f64(self, s, ctx, flags, N, d, q, L, qL, F, QL, x0m, x0c, H, c, R, means, chols,
+                                          fm, fc, calibrate, scalars, ws, ws_bytes):
         self._count("pof_linear_filtsmooth_general_f64")
         assert ws_bytes >= self.real.pof_workspace_bytes(N, d, q, L)
         return self._pass(N, d, q, L, qL, x0m, x0c, H, c, None, 0.0, 0.0, R, F, QL, means, chols, fm, fc, calibrate,
-                          scalars)
+                          scalars, flags)
 
     def pof_linearize_ivp_f64(self, s, ivp_id, params, nparams, n, d, q, s0, s1, means_t1, H, c):
         self._count("pof_linearize_ivp_f64")
@@ -124,8 +126,8 @@ class FakeLib:
             ca[k] = J @ y - f
         return 0
 
-    def pof_ieks_iteration_f64(self, s, ivp_id, params, nparams, N, d, q, L, qL, s0, s1, x0m, x0c, means, chols,
-                               calibrate, scalars, ws, ws_bytes):
+    def pof_ieks_iteration_f64(self, s, ctx, flags, ivp_id, params, nparams, N, d, q, L, qL, s0, s1, x0m, x0c, means,
+                               chols, calibrate, scalars, ws, ws_bytes):
         self._count("pof_ieks_iteration_f64")
         D = d * (q + 1)
         n = N - 1
@@ -135,16 +137,16 @@ class FakeLib:
             m1 = np.ascontiguousarray(m[1:])
             self.pof_linearize_ivp_f64(s, ivp_id, params, nparams, n, d, q, s0, s1, _p(m1), _p(H), _p(c))
             return self._pass(N, d, q, L, qL, x0m, x0c, _p(H), _p(c), None, 0.0, 0.0, None, None, None, means, chols,
-                              None, None, calibrate, scalars)
+                              None, None, calibrate, scalars, flags)
         forcing = _arr(params, (1,))[0]
         H, c, Jc = np.zeros((n, d, D)), np.zeros((n, d)), np.zeros((n, d * d + d))
         HS.hs_linearize_l96(ctypes.c_double(forcing), ctypes.c_long(n), d, q, ctypes.c_double(s0), ctypes.c_double(s1),
                             _p(np.ascontiguousarray(m[1:])), _p(H), _p(c), _p(Jc))
         return self._pass(N, d, q, L, qL, x0m, x0c, None, None, _p(Jc), s0, s1, None, None, None, means, chols, None,
-                          None, calibrate, scalars)
+                          None, calibrate, scalars, flags)
 
-    def pof_sequential_eks_f64(self, s, ivp_id, params, nparams, N, d, q, qL, s0, s1, x0m, x0c, means, chols, scalars,
-                               ws, ws_bytes):
+    def pof_sequential_eks_f64(self, s, flags, ivp_id, params, nparams, N, d, q, qL, s0, s1, x0m, x0c, means, chols,
+                               scalars, ws, ws_bytes):
         self._count("pof_sequential_eks_f64")
         D = d * (q + 1)
         p8 = np.zeros(8)
@@ -153,12 +155,21 @@ class FakeLib:
         qLa = np.ascontiguousarray(_arr(qL, (q + 1, q + 1)))
         sums = np.zeros(8)
         rc = HS.hs_tile_seq_eks(d, q, ctypes.c_long(N), _p(qLa), ctypes.c_double(s0), ctypes.c_double(s1), ivp_id,
-                                _p(p8), _p(x0), means, chols, _p(sums), 0, _env_reg())
+                                _p(p8), _p(x0), means, chols, _p(sums), 0, _reg(flags))
         out = _arr(scalars, (8,))
         out[:] = 0.0
         out[0], out[1], out[2], out[3] = -sums[0], sums[3], sums[1] / (N - 1) / d, sums[2] / (N - 1) / d
         out[5] = 1.0
         return rc
+
+    def pof_ctx_create(self, out):
+        return 0
+
+    def pof_ctx_destroy(self, c):
+        return None
+
+    def pof_prior_init_f64(self, s, N, d, q, qL, ts, m0, means, chols):
+        raise NotImplementedError("prior init has no host simulation")
 
     def pof_project_f64(self, s, N, d, q, scale0, mult, means, chols, ymean, ychol):
         self._count("pof_project_f64")
@@ -171,7 +182,7 @@ class FakeLib:
             yc[:] = mu * scale0 * L[:, 0::Q1, :]
         return 0
 
-    def pof_filter_combine_f64(self, s, n, D, e1, e2, out):
+    def pof_filter_combine_f64(self, s, n, D, e1, e2, out, flags=0):
         self._count("pof_filter_combine_f64")
         FE = 3 * D * D + 2 * D
         a, b, o = _arr(e1, (n, FE)), _arr(e2, (n, FE)), _arr(out, (n, FE))
@@ -180,7 +191,7 @@ class FakeLib:
                                       _p(o[i]), 0, 0)
         return 0
 
-    def pof_smooth_combine_f64(self, s, n, D, e1, e2, out):
+    def pof_smooth_combine_f64(self, s, n, D, e1, e2, out, flags=0):
         self._count("pof_smooth_combine_f64")
         SE = 2 * D * D + D
         a, b, o = _arr(e1, (n, SE)), _arr(e2, (n, SE)), _arr(out, (n, SE))

@@ -30,11 +30,16 @@ def test_host_only_queries(native_lib):
     # beyond the (d <= 4)-templated families: the large-state tile kernels, limited by shared memory (D <= 64 at d = 16)
     assert L.pof_supported(5, 3) == 1 and L.pof_supported(16, 3) == 1 and L.pof_supported_tile(2, 3) == 1
     assert L.pof_supported(16, 4) == 0 and L.pof_supported(2, 9) == 0 and L.pof_supported_tile(32, 3) == 0
-    assert L.pof_default_chunk_len(1 << 18, 16, 3, 148) == ((1 << 18) - 1 + 147) // 148  # one chunk per SM
-    assert L.pof_default_chunk_len(1 << 20, 2, 3, 148) >= 4
+    assert L.pof_default_chunk_len(1 << 18, 16, 3, 148, 0) == ((1 << 18) - 1 + 147) // 148  # one chunk per SM
+    assert L.pof_default_chunk_len(1 << 20, 2, 3, 148, 0) >= 4
     nb = L.pof_workspace_bytes(1 << 20, 2, 3, 222)
     assert 1.1e9 < nb < 1.4e9  # dominated by the per-step backward kernels: n * 136 doubles
-    assert L.pof_launches_per_pass(1 << 20, 2, 3, 222) > 8
+    # dataflow tree sweeps: 3 leaf kernels + chunk elements + 3 tree launches + 2 reductions; one launch per tree level
+    # (flag POF_F_TREE_PER_LEVEL, kept for A/B measurements) needs ~6x as many
+    assert L.pof_launches_per_pass(1 << 20, 2, 3, 222, 0) == 9
+    assert L.pof_launches_per_pass(1 << 20, 2, 3, 222, 4) > 40
+    # the forced large-state family fills the GPU with one chunk per resident CTA
+    assert L.pof_default_chunk_len(1 << 20, 2, 3, 148, 1) > L.pof_default_chunk_len(1 << 20, 2, 3, 148, 0)
 
 
 def test_sass_is_sm100a(native_lib):
@@ -42,6 +47,13 @@ def test_sass_is_sm100a(native_lib):
 
     out = subprocess.run(["cuobjdump", "-lelf", native_lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_library_reads_no_environment(native_lib):
+    """kernel-family choices are explicit `flags` arguments of the C ABI: the library imports no getenv"""
+    csrc = os.path.join(ROOT, "parallel-in-time-ode-filters_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):  # (the statically linked CUDA runtime imports getenv itself: check OUR sources)
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
 
 
 def test_no_cpu_fallback(monkeypatch):

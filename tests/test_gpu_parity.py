@@ -43,10 +43,12 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["lane2", "lane1", "thread"])
-def leaf_impl(request, monkeypatch):
-    """Both leaf-kernel families: the lane-cooperative performance kernels and the thread-per-chunk reference ones."""
-    monkeypatch.setenv("POF_B200_LEAF_IMPL", request.param)
+@pytest.fixture(params=["lane2", "tile"])
+def leaf_impl(request, monkeypatch, native_lib):
+    """Both kernel families: the register-resident lane-cooperative kernels (default for d <= 4, D <= 16) and the
+    large-state CTA-per-chunk kernels forced onto the same problems (explicit ABI flag POF_F_FAMILY_TILE)."""
+    if request.param == "tile":
+        monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_FAMILY_TILE)
     return request.param
 
 

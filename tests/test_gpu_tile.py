@@ -66,17 +66,14 @@ SMALL = [
 ]
 
 
-@pytest.mark.parametrize("tree", ["lane", "tile"])
 @pytest.mark.parametrize("name,kw,N,q,L", SMALL)
-def test_tile_family_on_the_reference_problems(native_lib, monkeypatch, tree, name, kw, N, q, L):
-    """the tile leaves (and, with tree = tile, the CTA-per-node tree operators) forced onto the small-state problems"""
+def test_tile_family_on_the_reference_problems(native_lib, monkeypatch, name, kw, N, q, L):
+    """the tile leaves and CTA-per-node tree operators forced onto the small-state problems (POF_F_FAMILY_TILE)"""
     from pof.convenience import get_initial_trajectory, set_up_solver
     from pof.parallel_filtsmooth import linear_filtsmooth
     from pof.step import linearize_at_previous_states
 
-    monkeypatch.setenv("POF_B200_LEAF_IMPL", "tile")
-    if tree == "tile":
-        monkeypatch.setenv("POF_B200_TREE_IMPL", "tile")
+    monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_FAMILY_TILE)
     ivp, oivp = _pair(name, **kw)
     ts = np.linspace(ivp.t0, ivp.tmax, N)
     setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
@@ -121,12 +118,13 @@ def test_noisy_observations_match_oracle(native_lib, name, kw, N, q, L):
 @pytest.mark.parametrize("N,L", [(40, 6), (150, None)])
 def test_lorenz96_d16_q3_pass_matches_oracle(native_lib, monkeypatch, N, L, sweep):
     """BASELINE config 5's state size (D = 64) on a grid the oracle finishes in seconds; both Householder sweep
-    implementations (shared memory = default, register-resident = opt-in)"""
+    implementations (register-resident = default, shared memory = flag POF_F_TILE_SMEM_QR)"""
     from pof.convenience import get_initial_trajectory, set_up_solver
     from pof.parallel_filtsmooth import linear_filtsmooth
     from pof.step import linearize_at_previous_states
 
-    monkeypatch.setenv("POF_B200_TILE_SWEEP", sweep)
+    if sweep == "smem":
+        monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_TILE_SMEM_QR)
     assert native_lib.LIB.pof_supported(16, 3) == 1
     ivp, oivp = _pair("lorenz96", tmax=1.0)
     ts = np.linspace(ivp.t0, ivp.tmax, N)
@@ -274,7 +272,7 @@ def test_tile_sequential_eks_solve_matches_oracle(native_lib, monkeypatch, name,
     from pof.solver import sequential_eks_solve
 
     if force:
-        monkeypatch.setenv("POF_B200_LEAF_IMPL", "tile")
+        monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_FAMILY_TILE)
     ivp, oivp = _pair(name, **kw)
     ts = np.linspace(ivp.t0, ivp.tmax, N)
     ys, info = sequential_eks_solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
@@ -303,18 +301,17 @@ def test_lorenz96_sequential_solve_equals_parallel(native_lib):
     assert (a.mean - b.mean).abs().max().item() <= 1e-8 * a.mean.abs().max().item()
 
 
-# ---- last on purpose: the opt-in register-resident Householder sweeps (POF_B200_TILE_SWEEP=reg).  The
-# default (shared-memory sweeps) is what every test above ran.
+# ---- the shared-memory Householder sweeps (flag POF_F_TILE_SMEM_QR; the register-resident sweeps are the default and
+# are what every test above ran)
 @pytest.mark.parametrize("name,kw,N,q,L", [("fitzhughnagumo", {}, 100, 3, 7), ("rigid_body", {}, 256, 3, 8),
                                             ("lorenz96", {"tmax": 1.0, "d": 8}, 90, 2, 7),
                                             ("lorenz96", {"tmax": 1.0}, 40, 3, 6)])
-def test_tile_register_sweeps_match_oracle(native_lib, monkeypatch, name, kw, N, q, L):
+def test_tile_shared_memory_sweeps_match_oracle(native_lib, monkeypatch, name, kw, N, q, L):
     from pof.convenience import get_initial_trajectory, set_up_solver
     from pof.parallel_filtsmooth import linear_filtsmooth
     from pof.step import linearize_at_previous_states
 
-    monkeypatch.setenv("POF_B200_LEAF_IMPL", "tile")
-    monkeypatch.setenv("POF_B200_TILE_SWEEP", "reg")
+    monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_FAMILY_TILE | native_lib.F_TILE_SMEM_QR)
     ivp, oivp = _pair(name, **kw)
     ts = np.linspace(ivp.t0, ivp.tmax, N)
     setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
