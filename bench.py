@@ -363,13 +363,15 @@ def run_native(args):
                                                             lin["scale0"], nat.ptr(means[t1row:]), nat.ptr(Jc)),
                       "linearize")
             res = sp.run(x0.mean, x0.chol, Jc, None, means, chols, calibrate=calibrate)
+            if "scalars" in res:
+                return res["scalars"]
             out5[:5].copy_(torch.stack([res["nll"], res["obj"], res["ssq"], res["ssq_proper"], res["not_close"]]))
             return out5
 
         fused = GraphedCall(eager)
         L = sp.backend.chunk_len
-        # linearise + the kernels of a pass + the separate up-sweep launch of stage A + the two carry-chain kernels
-        launches = 1 + int(nat.LIB.pof_launches_per_pass(n_loc + 1, d_, q_, L, nat.flags())) + 1 + 2
+        # linearise + the kernels of a pass + the separate up-sweep launch of stage A + the three exchange kernels
+        launches = 1 + int(nat.LIB.pof_launches_per_pass(n_loc + 1, d_, q_, L, nat.flags())) + 1 + 3
         return (lambda: fused()), fused, L, launches, sp.backend.ws.ctx
 
     def barrier():

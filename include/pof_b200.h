@@ -213,6 +213,25 @@ int pof_shard_stage_c_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_
                           int64_t chunk_len, const double* qL_host,
                           const double* seed, int is_last_rank, int has_row0, const double* cscale, double* means,
                           double* chols, double* partials2, void* ws, size_t ws_bytes);
+/* What a rank does with the all-gathered carries, ONE launch per exchange (register-resident family, D <= 16;
+ * pof_shard_exchange_supported tells; otherwise use the chain entry points below):
+ *  filter  : gathered = world payloads of `stride` doubles whose first 3D^2+2D doubles are carry_f of each rank;
+ *            state_in (D + D*D) <- x0 combined with the carries of ranks 0 .. rank-1 (filter.py:117-142, state form)
+ *  smoother: gathered payload of a rank = [carry_s (2D^2+D) | state_end (D+D*D) | partials (3)];
+ *            sums the partials in rank order (bitwise identical on all ranks) -> scalars[NLL, SSQ, SSQ_PROPER,
+ *            CSCALE] and *cscale = sqrt(sigma^2) (1 if !calibrate), sigma^2 = sum / n_steps_total / d;
+ *            seed (D + D*D) <- the last rank's end state combined with the carries of ranks world-1 .. rank+1
+ *  scalars : gathered = world pairs (obj, not-close count) -> scalars[OBJ], scalars[NOT_CLOSE]
+ * scratch: D + D*D doubles. */
+int pof_shard_exchange_supported(int D, uint32_t flags);
+int pof_shard_exchange_filter_f64(pof_stream_t s, uint32_t flags, int D, int rank, int world, const double* gathered,
+                                  int64_t stride, const double* x0_mean, const double* x0_chol, double* state_in,
+                                  double* scratch);
+int pof_shard_exchange_smooth_f64(pof_stream_t s, uint32_t flags, int D, int d, int rank, int world,
+                                  int64_t n_steps_total, int calibrate, const double* gathered, int64_t stride,
+                                  double* seed, double* scratch, double* cscale, double* scalars);
+int pof_shard_exchange_scalars_f64(pof_stream_t s, int world, const double* gathered, double* scalars);
+
 /* state <- op(state, elems[0]), op(.., elems[1]), ... (count packed filter elements, earlier first) */
 int pof_filter_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
                                const double* elems,

@@ -318,7 +318,7 @@ struct WsLayout {
   TreeLevels tl;
   long CS, L;
   int D, FE, SE, ST, NE;
-  size_t o_lin, o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_kern, o_send, o_part, o_part2, o_sums, o_misc, o_flags,
+  size_t o_lin, o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_sx, o_kern, o_send, o_part, o_part2, o_sums, o_misc, o_flags,
       total;  // in doubles
   size_t flag_words;  // 32-bit words of the dataflow flag area (zeroed at the start of every stage)
   void build(long n, int d, int q, long chunk_len) {
@@ -343,6 +343,7 @@ struct WsLayout {
     o_fin = take((size_t)tl.total * ST);
     o_sagg = take((size_t)tl.total * SE);
     o_sin = take((size_t)tl.total * ST);
+    o_sx = take((size_t)tl.total * SE);  // per node: smoothing aggregate of everything later (element-form down-sweep)
     o_kern = take((size_t)L * NE * CS);
     o_send = take((size_t)CS * ST);
     o_part = take((size_t)CS * 3);
@@ -420,6 +421,7 @@ static void flow_begin(FlowArgs& fa, const WsLayout& wl, double* agg, double* st
   fa.up_hi = 0;
   fa.agg = agg;
   fa.st = st;
+  fa.sx = nullptr;
   fa.root_m = fa.root_L = nullptr;
   fa.flag_up = f_up;
   fa.flag_dn = f_dn;
@@ -447,6 +449,21 @@ static void flow_down(FlowArgs& fa, const WsLayout& wl, const double* root_m, co
   ++fa.nseg;
   for (int l = wl.tl.nlev - 1; l >= 1; --l) {
     fa.seg_kind[fa.nseg] = FlowArgs::DOWN;
+    fa.seg_level[fa.nseg] = l;
+    fa.seg_count[fa.nseg] = wl.tl.sz[l];
+    ++fa.nseg;
+  }
+}
+// smoother only: element-form down-sweep -- per node the aggregate of all LATER nodes (identity at the root)
+static void flow_down_elem(FlowArgs& fa, const WsLayout& wl, double* sx) {
+  fa.sx = sx;
+  fa.root_m = fa.root_L = nullptr;
+  fa.seg_kind[fa.nseg] = FlowArgs::ROOT;
+  fa.seg_level[fa.nseg] = wl.tl.nlev - 1;
+  fa.seg_count[fa.nseg] = 1;
+  ++fa.nseg;
+  for (int l = wl.tl.nlev - 1; l >= 1; --l) {
+    fa.seg_kind[fa.nseg] = FlowArgs::DOWN_E;
     fa.seg_level[fa.nseg] = l;
     fa.seg_count[fa.nseg] = wl.tl.sz[l];
     ++fa.nseg;
@@ -540,10 +557,14 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
     else
       POF_CK(tile_chunkk(st, wl.D, fin, ws + wl.o_faggm, sagg, wl.CS));
     if (!per_level) {
+      // The smoothing elements do not depend on the terminal state, so the WHOLE suffix scan runs here in ELEMENT
+      // form -- up-sweep, then down-sweep giving every chunk the aggregate of all later chunks -- concurrently with
+      // the filter scan; once the terminal state exists, ONE state-form combine per chunk remains (stage C).
       FlowArgs fa;
       flow_begin(fa, wl, sagg, ws + wl.o_sin, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SUP));
       flow_up(fa, wl, up_top);
-      if (fa.nseg) POF_CK(tl->sflow(st, fa));
+      flow_down_elem(fa, wl, ws + wl.o_sx);
+      POF_CK(tl->sflow(st, fa));
       return 0;
     }
     for (int l = 0; l < up_top; ++l) {
@@ -586,10 +607,8 @@ static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
   {
     ProfScope ps(ctx, POF_SEG_SDOWN, s);
     if (!per_level) {
-      FlowArgs fa;
-      flow_begin(fa, wl, sagg, sin_, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SDOWN));
-      flow_down(fa, wl, root_m, root_L);
-      POF_CK(tl->sflow(s, fa));
+      // seeds of all chunks at once: (terminal state) combined with the chunk's "everything later" aggregate
+      POF_CK(tl->sseed(s, root_m, 1, ws + wl.o_sx, sin_, wl.CS));
     } else {
       k_pack_state<<<1, 128, 0, s>>>(wl.D, root_m, root_L, sin_ + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
       for (int l = wl.tl.nlev - 1; l >= 1; --l) {
@@ -709,10 +728,8 @@ int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len, uint32
   if (!ll) return 0;
   const TreeLaunch* tl = tree_for(ll, wl.D, flags);
   const int64_t leaf = 3, chunkk = 1, reduce = 2;
-  if (tl && !(flags & POF_F_TREE_PER_LEVEL)) {
-    const int64_t sup = wl.tl.nlev >= 3 ? 1 : 0;  // the smoother's up-sweep has no level to build below three levels
-    return leaf + chunkk + reduce + 1 /*filter tree*/ + sup + 1 /*smoother down-sweep*/;
-  }
+  if (tl && !(flags & POF_F_TREE_PER_LEVEL))
+    return leaf + chunkk + reduce + 1 /*filter tree*/ + 1 /*smoother suffix scan, element form*/ + 1 /*chunk seeds*/;
   const int up_total = wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0;  // the root combine is skipped on one GPU
   const int down_total = wl.tl.nlev - 1;
   return leaf + chunkk + reduce + 2 /*pack*/ + 2 * (int64_t)(up_total + down_total);
@@ -1018,6 +1035,60 @@ int pof_shard_stage_c_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64
   if (int rc = stage_c(s, ctx, flags, ll, a, wl, ws, seed, seed + wl.D, has_row0, cscale, mb, cb, nullptr)) return rc;
   POF_CK(cudaMemcpyAsync(partials2, ws + wl.o_sums + 8, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   return 0;
+}
+
+// ---- fused rank-carry exchanges (register-resident family; else the caller uses the chain entry points below)
+int pof_shard_exchange_supported(int D, uint32_t flags) {
+  return (!(flags & POF_F_FAMILY_TILE) && tree_launch(D) != nullptr) ? 1 : 0;
+}
+int pof_shard_exchange_filter_f64(pof_stream_t s, uint32_t flags, int D, int rank, int world, const double* gathered,
+                                  int64_t stride, const double* x0_mean, const double* x0_chol, double* state_in,
+                                  double* scratch) {
+  if (!pof_shard_exchange_supported(D, flags)) return POF_E_UNSUPPORTED_DQ;
+  if (rank < 0 || rank >= world) return POF_E_ARG;
+  ExchangeArgs A = {};
+  A.rank = rank;
+  A.world = world;
+  A.gathered = gathered;
+  A.stride = stride;
+  A.x0_mean = x0_mean;
+  A.x0_chol = x0_chol;
+  A.state_out = state_in;
+  A.scratch = scratch;
+  return (int)tree_launch(D)->fexchange((cudaStream_t)s, A);
+}
+int pof_shard_exchange_smooth_f64(pof_stream_t s, uint32_t flags, int D, int d, int rank, int world,
+                                  int64_t n_steps_total, int calibrate, const double* gathered, int64_t stride,
+                                  double* seed, double* scratch, double* cscale, double* scalars) {
+  if (!pof_shard_exchange_supported(D, flags)) return POF_E_UNSUPPORTED_DQ;
+  if (rank < 0 || rank >= world || !cscale) return POF_E_ARG;
+  ExchangeArgs A = {};
+  A.rank = rank;
+  A.world = world;
+  A.gathered = gathered;
+  A.stride = stride;
+  A.state_out = seed;
+  A.scratch = scratch;
+  A.n_obs = (double)n_steps_total;
+  A.d_obs = (double)d;
+  A.calibrate = calibrate;
+  A.cscale = cscale;
+  A.scalars = scalars;
+  return (int)tree_launch(D)->sexchange((cudaStream_t)s, A);
+}
+// scalars[POF_S_OBJ], scalars[POF_S_NOT_CLOSE] <- sums over the ranks' (obj, not-close) pairs, in rank order
+__global__ void k_exchange_sums2(int world, const double* __restrict__ gathered, double* __restrict__ scalars) {
+  double a = 0.0, b = 0.0;
+  for (int r = 0; r < world; ++r) {
+    a += gathered[2 * r];
+    b += gathered[2 * r + 1];
+  }
+  scalars[POF_S_OBJ] = a;
+  scalars[POF_S_NOT_CLOSE] = b;
+}
+int pof_shard_exchange_scalars_f64(pof_stream_t s, int world, const double* gathered, double* scalars) {
+  k_exchange_sums2<<<1, 1, 0, (cudaStream_t)s>>>(world, gathered, scalars);
+  return (int)cudaGetLastError();
 }
 
 int pof_filter_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,

@@ -124,7 +124,7 @@ cudaError_t tile_schain(cudaStream_t, int D, int count, const double* state_in, 
 // a level costs one warm combine plus an L2 round trip for the flag.
 struct FlowArgs {
   static constexpr int MAXL = 40;
-  enum Kind { UP = 0, ROOT = 1, DOWN = 2 };
+  enum Kind { UP = 0, ROOT = 1, DOWN = 2, DOWN_E = 3 };
   int nlev;                 // levels of the tree (level 0 = chunks)
   long off[MAXL], sz[MAXL];
   int nseg;                 // segments in execution order: segment j has seg_count[j] independent items
@@ -137,19 +137,37 @@ struct FlowArgs {
                             // any other level were complete before the launch
   double* agg;              // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
   double* st;               // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
-  const double* root_m;     // state of the root node for the down-sweep (ROOT item): mean (D), factor (D x D)
-  const double* root_L;
+  double* sx;               // smoother, element-form down-sweep (DOWN_E): per node the aggregate of everything LATER
+  const double* root_m;     // state of the root node for the down-sweep (ROOT item): mean (D), factor (D x D);
+  const double* root_L;     // null with DOWN_E segments: the root's "later" aggregate is the identity element
   unsigned* flag_up;        // per node: element complete   } zeroed by a stream-ordered memset before the launch
   unsigned* flag_dn;        // per node: state complete     }
   unsigned* ticket;         // the ticket counter           }
 };
 
-// register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> generic shared-memory kernels
+struct ExchangeArgs {
+  int rank, world;
+  const double* gathered;   // world payloads, `stride` doubles each
+  long stride;
+  const double* x0_mean;    // filter: initial state
+  const double* x0_chol;
+  double* state_out;        // D + D*D: incoming filtered state / smoothing seed of this rank
+  double* scratch;          // D + D*D
+  // smoother exchange only
+  double n_obs, d_obs;      // total number of observations n and their dimension d (sigma^2 = sum / n / d)
+  int calibrate;
+  double* cscale;           // out: sqrt(sigma^2) or 1
+  double* scalars;          // out: POF scalars vector (nll, ssq, ssq_proper, cscale slots), or null
+};
+
+// register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> CTA-per-node tile kernels
 struct TreeLaunch {
   typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
-  Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk;
+  Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk, sseed;
   typedef cudaError_t (*FlowFn)(cudaStream_t, const FlowArgs&);
   FlowFn fflow, sflow;     // whole-sweep dataflow kernels (filtering / smoothing)
+  typedef cudaError_t (*ExchangeFn)(cudaStream_t, const ExchangeArgs&);
+  ExchangeFn fexchange, sexchange;  // rank-carry exchanges of the time-sharded pass (pof_tree_kernels.cuh)
 };
 const TreeLaunch* tree_launch_a(int D);
 const TreeLaunch* tree_launch_b(int D);

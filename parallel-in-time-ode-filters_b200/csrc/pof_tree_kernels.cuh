@@ -8,7 +8,7 @@ namespace pof {
 
 constexpr int TL_WARPS = 4;
 
-enum TreeOp { T_FUP = 0, T_FDOWN, T_SUP, T_SDOWN, T_FCOMB, T_SCOMB, T_CHUNKK };
+enum TreeOp { T_FUP = 0, T_FDOWN, T_SUP, T_SDOWN, T_FCOMB, T_SCOMB, T_CHUNKK, T_SSEED };
 
 // (L2 loads: inside a dataflow sweep the source was written by another SM during the SAME kernel)
 template <int D, int G>
@@ -21,20 +21,26 @@ __device__ __forceinline__ void group_copy(int r, double* dst, const double* src
 //  T_FDOWN : a = parent states, nb = #parents, b = children elems, na = #children, c = children states
 //  T_SUP / T_SDOWN: same with smoothing elements
 //  T_FCOMB / T_SCOMB: c[i] = op(a[i], b[i]), nb = count
-template <int D, int OP>
-__global__ void __launch_bounds__(TL_WARPS * 32)
+//  T_CHUNKK: a = chunk incoming states, b = chunk filtering elements before their last update, c = chunk smoothing elems
+//  T_SSEED : a = ONE terminal state (D + D^2), b = per-chunk exclusive-suffix smoothing elements (the aggregate of all
+//            LATER chunks), c = per-chunk seeds: c[i] = state-form op(a, b[i])   (nb chunks)
+// WARPS: warps per CTA (2 for the kernels that run on the side stream next to the resident filter-scan CTAs: with
+// two warps any register count fits into what those leave free)
+template <int D, int OP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
     k_tree(const double* __restrict__ a, long na, const double* __restrict__ b, double* __restrict__ c, long nb) {
   extern __shared__ __align__(16) double sm[];
   using TL = TreeLane<D>;
   constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB || OP == T_CHUNKK);
   constexpr int G = FILT ? TL::G2 : TL::GS;
   constexpr int CPW = 32 / G;
+  constexpr int SMC = FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S;
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long i = ((long)blockIdx.x * TL_WARPS + warp) * CPW + lane / G;
+  const long i = ((long)blockIdx.x * WARPS + warp) * CPW + lane / G;
   if (i >= nb) return;
   typename TL::Ctx cx;
-  TL::template init<G>(cx, sm + (warp * CPW + lane / G) * TL::SM_COMBINE);
+  TL::template init<G>(cx, sm + (warp * CPW + lane / G) * SMC, FILT ? TL::NMAT : TL::NMAT_S);
   if constexpr (OP == T_FUP) {
     const double* lc = a + 2 * i * FE;
     if (2 * i + 1 < na) TL::template filter_combine<false>(cx, lc, lc + FE, c + i * FE);
@@ -58,6 +64,8 @@ __global__ void __launch_bounds__(TL_WARPS * 32)
   } else if constexpr (OP == T_CHUNKK) {
     // a = chunk incoming states, b = chunk filtering elements before their last update, c = chunk smoothing elements
     TL::chunk_kernel(cx, a + i * ST, b + i * FE, c + i * SE);
+  } else if constexpr (OP == T_SSEED) {
+    TL::template smooth_combine<true>(cx, a, b + i * SE, c + i * ST);
   } else if constexpr (OP == T_FCOMB) {
     TL::template filter_combine<false>(cx, a + i * FE, b + i * FE, c + i * FE);
   } else {
@@ -76,17 +84,18 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int D, bool FILT>
-__global__ void __launch_bounds__(TL_WARPS * 32) k_tree_flow(const FlowArgs A) {
+template <int D, bool FILT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
   extern __shared__ __align__(16) double sm[];
   using TL = TreeLane<D>;
   constexpr int G = FILT ? TL::G2 : TL::GS;
   constexpr int CPW = 32 / G;
+  constexpr int SMC = FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S;
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
   constexpr int EL = FILT ? FE : SE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typename TL::Ctx cx;
-  TL::template init<G>(cx, sm + (warp * CPW + lane / G) * TL::SM_COMBINE);
+  TL::template init<G>(cx, sm + (warp * CPW + lane / G) * SMC, FILT ? TL::NMAT : TL::NMAT_S);
   const long total = A.seg_begin[A.nseg];
   while (true) {
     unsigned t = 0;
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_flow(const FlowArgs A) {
         dep0 = A.flag_up + A.off[lev - 1] + 2 * i;
         if (2 * i + 1 < A.sz[lev - 1]) dep1 = dep0 + 1;
       }
-    } else if (live && kind == FlowArgs::DOWN) {
+    } else if (live && (kind == FlowArgs::DOWN || kind == FlowArgs::DOWN_E)) {
       dep0 = A.flag_dn + A.off[lev] + i;
       const long e = FILT ? 2 * i : 2 * i + 1;  // the child element the combine reads
       if (2 * i + 1 < A.sz[lev - 1] && lev - 1 >= A.up_lo && lev - 1 <= A.up_hi) dep1 = A.flag_up + A.off[lev - 1] + e;
@@ -140,11 +149,38 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_flow(const FlowArgs A) {
         cx.sync();
         if (cx.r == 0) st_release(A.flag_up + A.off[lev] + i, 1u);
       } else if (kind == FlowArgs::ROOT) {
-        double* r = A.st + A.off[A.nlev - 1] * ST;
-        for (int j = cx.r; j < ST; j += G) r[j] = (j < D) ? __ldcg(A.root_m + j) : __ldcg(A.root_L + (j - D));
+        if (A.root_m) {
+          double* r = A.st + A.off[A.nlev - 1] * ST;
+          for (int j = cx.r; j < ST; j += G) r[j] = (j < D) ? __ldcg(A.root_m + j) : __ldcg(A.root_L + (j - D));
+        } else if constexpr (!FILT) {
+          // element-form down-sweep of the smoother: nothing lies later than the root -> the identity element
+          // (g = 0, E = I, D = 0); combining it with any element returns that element exactly
+          double* r = A.sx + A.off[A.nlev - 1] * SE;
+          for (int j = cx.r; j < SE; j += G) r[j] = (j >= D && j < D + D * D && (j - D) / D == (j - D) % D) ? 1.0 : 0.0;
+        }
         __threadfence();
         cx.sync();
         if (cx.r == 0) st_release(A.flag_dn + A.off[A.nlev - 1], 1u);
+      } else if (kind == FlowArgs::DOWN_E) {
+        if constexpr (!FILT) {
+          // exclusive-suffix ELEMENTS: X(right child) = X(parent); X(left child) = op(later = X(parent), right child)
+          const double* px = A.sx + (A.off[lev] + i) * SE;
+          const double* el = A.agg + A.off[lev - 1] * SE;
+          double* cxs = A.sx + A.off[lev - 1] * SE;
+          const bool two = 2 * i + 1 < A.sz[lev - 1];
+          if (two) {
+            group_copy<D, G>(cx.r, cxs + (2 * i + 1) * SE, px, SE);
+            TL::template smooth_combine<false>(cx, px, el + (2 * i + 1) * SE, cxs + 2 * i * SE);
+          } else {
+            group_copy<D, G>(cx.r, cxs + 2 * i * SE, px, SE);
+          }
+          __threadfence();
+          cx.sync();
+          if (cx.r == 0) {
+            st_release(A.flag_dn + A.off[lev - 1] + 2 * i, 1u);
+            if (two) st_release(A.flag_dn + A.off[lev - 1] + 2 * i + 1, 1u);
+          }
+        }
       } else {
         const double* p = A.st + (A.off[lev] + i) * ST;
         const double* el = A.agg + A.off[lev - 1] * EL;
@@ -173,6 +209,76 @@ __global__ void __launch_bounds__(TL_WARPS * 32) k_tree_flow(const FlowArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Rank-carry exchanges of the time-sharded pass (pof/sharded.py): what every rank does with the all-gathered carries,
+// ONE launch of one lane group per exchange (register-resident state-form combines, ~3 us each), including the
+// scalar bookkeeping that used to be ~25 small torch kernels per iteration.
+//   filter  : state_in = x0 (+) carry_0 (+) ... (+) carry_{rank-1}           (filter.py:117-142 in state form)
+//   smoother: sums of the ranks' partial statistics in rank order (bitwise identical on every rank) -> nll, sigma^2,
+//             calibration scale; seed = terminal state (last rank's end state) combined with the later ranks'
+//             smoothing carries W-1 .. rank+1                                 (smoother.py:53-63 in state form)
+template <int D, bool FILT>
+__global__ void __launch_bounds__(32) k_exchange(const ExchangeArgs A) {
+  extern __shared__ __align__(16) double sm[];
+  using TL = TreeLane<D>;
+  constexpr int G = FILT ? TL::G2 : TL::GS;
+  constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
+  const int lane = threadIdx.x & 31;
+  if (lane >= G) return;
+  typename TL::Ctx cx;
+  TL::template init<G>(cx, sm, FILT ? TL::NMAT : TL::NMAT_S);
+  if constexpr (FILT) {
+    // pack x0 into the scratch/state ping-pong so that the last combine writes state_out
+    const int count = A.rank;
+    double* bufs[2] = {A.state_out, A.scratch};
+    int cur = count & 1;  // after `count` flips the result sits in bufs[0]
+    for (int j = cx.r; j < ST; j += G) bufs[cur][j] = (j < D) ? __ldcg(A.x0_mean + j) : __ldcg(A.x0_chol + (j - D));
+    __threadfence();
+    cx.sync();
+    for (int i = 0; i < count; ++i) {
+      TL::template filter_combine<true>(cx, bufs[cur], A.gathered + (long)i * A.stride, bufs[cur ^ 1]);
+      __threadfence();
+      cx.sync();
+      cur ^= 1;
+    }
+  } else {
+    // gathered payload of rank r: [smoothing carry SE | filtered end state ST | nll, s1, s2 partial sums]
+    const int W = A.world;
+    if (cx.r == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int r = 0; r < W; ++r) {
+        const double* p = A.gathered + (long)r * A.stride + SE + ST;
+        s0 += __ldcg(p);
+        s1 += __ldcg(p + 1);
+        s2 += __ldcg(p + 2);
+      }
+      const double ssq = s1 / A.n_obs / A.d_obs;
+      const double cs = A.calibrate ? sqrt(ssq) : 1.0;
+      *A.cscale = cs;
+      if (A.scalars) {
+        A.scalars[0] = s0;                       // POF_S_NLL
+        A.scalars[2] = ssq;                      // POF_S_SSQ
+        A.scalars[3] = s2 / A.n_obs / A.d_obs;   // POF_S_SSQ_PROPER
+        A.scalars[5] = cs;                       // POF_S_CSCALE
+      }
+    }
+    const int count = W - 1 - A.rank;
+    double* bufs[2] = {A.state_out, A.scratch};
+    int cur = count & 1;
+    const double* term = A.gathered + (long)(W - 1) * A.stride + SE;
+    for (int j = cx.r; j < ST; j += G) bufs[cur][j] = __ldcg(term + j);
+    __threadfence();
+    cx.sync();
+    for (int i = 0; i < count; ++i) {  // later carries first: W-1, W-2, .., rank+1
+      const double* el = A.gathered + (long)(W - 1 - i) * A.stride;
+      TL::template smooth_combine<true>(cx, bufs[cur], el, bufs[cur ^ 1]);
+      __threadfence();
+      cx.sync();
+      cur ^= 1;
+    }
+  }
+}
+
 template <int D>
 struct TreeLaunchers {
   using TL = TreeLane<D>;
@@ -181,11 +287,13 @@ struct TreeLaunchers {
     constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB || OP == T_CHUNKK);
     constexpr int G = FILT ? TL::G2 : TL::GS;
     constexpr int CPW = 32 / G;
-    constexpr int smem = TL_WARPS * CPW * TL::SM_COMBINE * (int)sizeof(double);
+    // the ops that run on the side stream (next to the resident CTAs of the filter scan) use two-warp CTAs
+    constexpr int WARPS = (OP == T_CHUNKK || OP == T_SUP) ? 2 : TL_WARPS;
+    constexpr int smem = WARPS * CPW * (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(double);
     if (nb <= 0) return cudaSuccess;
-    if (cudaError_t e = ensure_smem(k_tree<D, OP>, smem, OP == T_SUP)) return e;
-    const long per_block = (long)TL_WARPS * CPW;
-    k_tree<D, OP><<<(unsigned)((nb + per_block - 1) / per_block), TL_WARPS * 32, smem, s>>>(a, na, b, c, nb);
+    if (cudaError_t e = ensure_smem(k_tree<D, OP, WARPS>, smem, WARPS == 2)) return e;
+    const long per_block = (long)WARPS * CPW;
+    k_tree<D, OP, WARPS><<<(unsigned)((nb + per_block - 1) / per_block), WARPS * 32, smem, s>>>(a, na, b, c, nb);
     return cudaGetLastError();
   }
   // dataflow whole-sweep launch: persistent grid (enough warps for the widest level, at most what is resident)
@@ -193,8 +301,9 @@ struct TreeLaunchers {
   static cudaError_t flow(cudaStream_t s, const FlowArgs& A) {
     constexpr int G = FILT ? TL::G2 : TL::GS;
     constexpr int CPW = 32 / G;
-    constexpr int smem = TL_WARPS * CPW * TL::SM_COMBINE * (int)sizeof(double);
-    auto kern = k_tree_flow<D, FILT>;
+    constexpr int WARPS = FILT ? TL_WARPS : 2;  // smoother sweeps run next to the filter scan's resident CTAs
+    constexpr int smem = WARPS * CPW * (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(double);
+    auto kern = k_tree_flow<D, FILT, WARPS>;
     if (cudaError_t e = ensure_smem(kern, smem, !FILT)) return e;
     static int max_grid[64] = {0};
     int dev = 0;
@@ -202,7 +311,7 @@ struct TreeLaunchers {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (max_grid[dev] == 0) {
       int per_sm = 0, sms = 0;
-      if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TL_WARPS * 32, smem)) return e;
+      if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem)) return e;
       if (cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) return e;
       if (per_sm < 1) return cudaErrorLaunchOutOfResources;
       max_grid[dev] = per_sm * sms;
@@ -215,15 +324,23 @@ struct TreeLaunchers {
       if (n > widest) widest = n;
       a.seg_begin[j + 1] = a.seg_begin[j] + (n + CPW - 1) / CPW * CPW;
     }
-    long blocks = (widest + (long)TL_WARPS * CPW - 1) / ((long)TL_WARPS * CPW);
+    long blocks = (widest + (long)WARPS * CPW - 1) / ((long)WARPS * CPW);
     if (blocks < 1) blocks = 1;
     if (blocks > max_grid[dev]) blocks = max_grid[dev];
-    k_tree_flow<D, FILT><<<(unsigned)blocks, TL_WARPS * 32, smem, s>>>(a);
+    k_tree_flow<D, FILT, WARPS><<<(unsigned)blocks, WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+  }
+  template <bool FILT>
+  static cudaError_t exchange(cudaStream_t s, const ExchangeArgs& A) {
+    constexpr int smem = (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(double);
+    if (cudaError_t e = ensure_smem(k_exchange<D, FILT>, smem)) return e;
+    k_exchange<D, FILT><<<1, 32, smem, s>>>(A);
     return cudaGetLastError();
   }
   static const TreeLaunch* get() {
     static const TreeLaunch t = {&run<T_FUP>, &run<T_FDOWN>, &run<T_SUP>, &run<T_SDOWN>, &run<T_FCOMB>, &run<T_SCOMB>,
-                                 &run<T_CHUNKK>, &flow<true>, &flow<false>};
+                                 &run<T_CHUNKK>, &run<T_SSEED>, &flow<true>, &flow<false>, &exchange<true>,
+                                 &exchange<false>};
     return &t;
   }
 };

@@ -31,18 +31,26 @@ struct TreeLane {
   static constexpr int RAW = NMAT * MAT + 4 * BCW + 2 * VEC;
   static constexpr int SM_COMBINE = RAW + ((2 - (RAW % 16)) + 16) % 16;
   enum { mU1 = 0, mZ2, mA1, mX11, mX21, mX22, mY, mG, mP };
+  // the smoothing operator stages only two matrices (D1, E1): a quarter of the shared memory, so that the smoother's
+  // sweeps fit next to the two resident CTAs of the filter scan they run concurrently with (pof_api.cu, stage B)
+  static constexpr int NMAT_S = 2;
+  static constexpr int RAW_S = NMAT_S * MAT + 4 * BCW + 2 * VEC;
+  static constexpr int SM_COMBINE_S = RAW_S + ((2 - (RAW_S % 16)) + 16) % 16;
+  enum { sD1 = 0, sE1 = 1 };
 
   struct Ctx {
     int r;  // lane within the combine's group
     unsigned mask;
     double* sm;
+    int nmat;  // matrices staged ahead of the broadcast slots (NMAT, or NMAT_S for the smoothing operator)
     int flip, vflip;
     __device__ __forceinline__ double* mat(int which) const { return sm + which * MAT; }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
   };
   template <int G>
-  static __device__ __forceinline__ void init(Ctx& c, double* sm) {
+  static __device__ __forceinline__ void init(Ctx& c, double* sm, int nmat = NMAT) {
     const int lane = threadIdx.x & 31;
+    c.nmat = nmat;
     c.r = lane % G;
     c.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
     c.sm = sm;
@@ -123,7 +131,7 @@ struct TreeLane {
   // lane `src` publishes n doubles into broadcast slot `slot_id` (0/1: two independent streams), all lanes read
   template <int n>
   static __device__ __forceinline__ void bcast(Ctx& c, int slot_id, const double (&x)[n], int src, double (&out)[n]) {
-    double2* slot = reinterpret_cast<double2*>(c.sm + NMAT * MAT + (2 * slot_id + c.flip) * BCW);
+    double2* slot = reinterpret_cast<double2*>(c.sm + c.nmat * MAT + (2 * slot_id + c.flip) * BCW);
     if (c.r == src) {
 #pragma unroll
       for (int j = 0; j + 1 < n; j += 2) slot[j / 2] = make_double2(x[j], x[j + 1]);
@@ -141,7 +149,7 @@ struct TreeLane {
   // out[j] = x of lane j (j < n)
   template <int n>
   static __device__ __forceinline__ void allgather(Ctx& c, double x, double (&out)[n]) {
-    double* v = c.sm + NMAT * MAT + 4 * BCW + c.vflip * VEC;
+    double* v = c.sm + c.nmat * MAT + 4 * BCW + c.vflip * VEC;
     c.vflip ^= 1;
     if (c.r < n) v[c.r] = x;
     c.sync();
@@ -214,8 +222,8 @@ struct TreeLane {
       const bool second = DUAL && cx.r >= D;
       if (DUAL) {
         // both halves publish into their own slot; each lane reads its half's slot
-        double2* s0 = reinterpret_cast<double2*>(cx.sm + NMAT * MAT + (0 + cx.flip) * BCW);
-        double2* s1 = reinterpret_cast<double2*>(cx.sm + NMAT * MAT + (2 + cx.flip) * BCW);
+        double2* s0 = reinterpret_cast<double2*>(cx.sm + cx.nmat * MAT + (0 + cx.flip) * BCW);
+        double2* s1 = reinterpret_cast<double2*>(cx.sm + cx.nmat * MAT + (2 + cx.flip) * BCW);
         if (cx.r == I || cx.r == D + I) {
           double2* s = second ? s1 : s0;
 #pragma unroll
@@ -592,9 +600,9 @@ struct TreeLane {
     load_row(E2 + rr * D, e2r);
     load_row(D2 + rr * D, d2);
     const double g1r = ldg(g1 + rr), g2r = ldg(g2 + rr);
-    if (act) put_row(cx, mU1, rr, row);
+    if (act) put_row(cx, sD1, rr, row);
     if (!STATE) {
-      if (act) put_row(cx, mA1, rr, row1);
+      if (act) put_row(cx, sE1, rr, row1);
     }
     allgather<D>(cx, act ? g1r : 0.0, v);  // also orders the put_rows before the reads below
     double go = g2r;
@@ -603,7 +611,7 @@ struct TreeLane {
     if (act) out[rr] = go;
     if (!STATE) {
       double eo[D];
-      row_times(cx, mA1, e2r, eo);
+      row_times(cx, sE1, e2r, eo);
       if (act) {
 #pragma unroll
         for (int j = 0; j < D; ++j) out[D + rr * D + j] = eo[j];
@@ -612,7 +620,7 @@ struct TreeLane {
     double x[W2];
     {
       double p[D];
-      row_times(cx, mU1, e2r, p);
+      row_times(cx, sD1, e2r, p);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         x[j] = p[j];

@@ -86,6 +86,13 @@ def _load():
         "pof_shard_stage_c_f64": (
             _c_int, [_c_dp, _c_dp, U, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dp, _c_int, _c_int, _c_dp, _c_dp,
                      _c_dp, _c_dp, _c_dp, _c_sz]),
+        "pof_shard_exchange_supported": (_c_int, [_c_int, U]),
+        "pof_shard_exchange_filter_f64": (
+            _c_int, [_c_dp, U, _c_int, _c_int, _c_int, _c_dp, _c_i64, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_shard_exchange_smooth_f64": (
+            _c_int, [_c_dp, U, _c_int, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_dp, _c_i64, _c_dp, _c_dp, _c_dp,
+                     _c_dp]),
+        "pof_shard_exchange_scalars_f64": (_c_int, [_c_dp, _c_int, _c_dp, _c_dp]),
         "pof_filter_apply_chain_f64": (_c_int, [_c_dp, U, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, U, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
@@ -107,6 +114,8 @@ EXPORTED = [
     "pof_ieks_iteration_f64", "pof_sequential_eks_f64", "pof_shard_stage_a_f64", "pof_shard_stage_b_f64",
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_shard_stage_c_f64",
     "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64", "pof_project_f64", "pof_prior_init_f64",
+    "pof_shard_exchange_supported", "pof_shard_exchange_filter_f64", "pof_shard_exchange_smooth_f64",
+    "pof_shard_exchange_scalars_f64",
 ]
 
 # kernel-family flags of the C ABI (include/pof_b200.h).  DEFAULT_FLAGS is what the facade passes; tests / scripts may

@@ -83,6 +83,27 @@ class CudaBackend:
                                                 nat.ptr(seed), int(is_last), int(has_row0), nat.ptr(cscale),
                                                 nat.ptr(means), nat.ptr(chols), nat.ptr(partials2), p, nb), "stage_c")
 
+    # ---- fused exchanges (one launch each: carry fold + scalar bookkeeping), register-resident family only
+    @property
+    def fused_exchange(self):
+        D = self.d * (self.q + 1)
+        return bool(nat.LIB.pof_shard_exchange_supported(D, nat.flags()))
+
+    def exchange_filter(self, D, rank, world, gathered, stride, x0_mean, x0_chol, state_in):
+        nat.check(nat.LIB.pof_shard_exchange_filter_f64(nat.stream_ptr(), nat.flags(), D, rank, world,
+                                                        nat.ptr(gathered), stride, nat.ptr(x0_mean), nat.ptr(x0_chol),
+                                                        nat.ptr(state_in), nat.ptr(self.scratch)), "exchange_filter")
+
+    def exchange_smooth(self, D, d, rank, world, n_total, calibrate, gathered, stride, seed, cscale, scalars):
+        nat.check(nat.LIB.pof_shard_exchange_smooth_f64(nat.stream_ptr(), nat.flags(), D, d, rank, world, n_total,
+                                                        int(bool(calibrate)), nat.ptr(gathered), stride, nat.ptr(seed),
+                                                        nat.ptr(self.scratch), nat.ptr(cscale), nat.ptr(scalars)),
+                  "exchange_smooth")
+
+    def exchange_scalars(self, world, gathered, scalars):
+        nat.check(nat.LIB.pof_shard_exchange_scalars_f64(nat.stream_ptr(), world, nat.ptr(gathered),
+                                                         nat.ptr(scalars)), "exchange_scalars")
+
     def filter_chain(self, D, count, state_in, elems, state_out):
         nat.check(nat.LIB.pof_filter_apply_chain_f64(nat.stream_ptr(), nat.flags(), D, count, nat.ptr(state_in), nat.ptr(elems),
                                                      nat.ptr(state_out), nat.ptr(self.scratch)), "filter_chain")
@@ -119,6 +140,7 @@ class ShardedPass:
         self.pay_c, self.gather_c = z(2), z(self.world * 2)
         self.cscale = z(1)
         self.x0_state = z(self.ST)
+        self.scalars = z(nat.NSCALARS)
 
     def _all_gather(self, out, inp):
         if self.world == 1:
@@ -131,6 +153,8 @@ class ShardedPass:
         out or None.  Returns dict(nll, obj, ssq, ssq_proper, not_close) -- identical on every rank."""
         D, W, r, be = self.D, self.world, self.rank, self.backend
         FE, SE, ST = self.FE, self.SE, self.ST
+        if getattr(be, "fused_exchange", False):
+            return self._run_fused(x0_mean, x0_chol, H_loc, c_loc, means_loc, chols_loc, calibrate, fmeans, fchols)
         self.x0_state[:D].copy_(x0_mean)
         self.x0_state[D:].copy_(x0_chol.reshape(-1))
         # ---- stage A + exchange 1
@@ -162,6 +186,55 @@ class ShardedPass:
         self._all_gather(self.gather_c, self.pay_c)
         s2 = self.gather_c.view(W, 2).sum(dim=0)
         return dict(nll=nll, obj=s2[0], ssq=ssq, ssq_proper=ssq_proper, not_close=s2[1])
+
+
+def _run_fused(self, x0_mean, x0_chol, H_loc, c_loc, means_loc, chols_loc, calibrate, fmeans, fchols):
+    """the same pass with ONE kernel per exchange (carry fold + scalar bookkeeping, `pof_shard_exchange_*`): per pass
+    three stage calls, three all-gathers and three exchange kernels -- no other device work.  Written as phases so
+    that a test can drive several "virtual ranks" in lockstep on one GPU (tests/test_gpu_sharded.py)."""
+    st = (x0_mean, x0_chol, H_loc, c_loc, means_loc, chols_loc, calibrate, fmeans, fchols)
+    self.phase_a(st)
+    self._all_gather(self.gather_f, self.carry_f)
+    self.phase_b(st)
+    self._all_gather(self.gather_b, self.pay_b)
+    self.phase_c(st)
+    self._all_gather(self.gather_c, self.pay_c)
+    return self.phase_d()
+
+
+def _phase_a(self, st):
+    self.backend.stage_a(st[2], st[3], self.carry_f)
+
+
+def _phase_b(self, st):
+    x0_mean, x0_chol, H_loc, c_loc, _, _, _, fmeans, fchols = st
+    D, SE, ST, pb = self.D, self.SE, self.ST, self.pay_b
+    self.backend.exchange_filter(D, self.rank, self.world, self.gather_f, self.FE, x0_mean, x0_chol, self.state_in)
+    if fmeans is not None and self.has_row0:
+        fmeans[0].copy_(x0_mean)
+        fchols[0].copy_(x0_chol)
+    shift = 0 if self.has_row0 else 1
+    self.backend.stage_b(H_loc, c_loc, self.state_in, _shifted(fmeans, shift, D), _shifted(fchols, shift, D * D),
+                         pb[:SE], pb[SE:SE + ST], pb[SE + ST:])
+
+
+def _phase_c(self, st):
+    means_loc, chols_loc, calibrate = st[4], st[5], st[6]
+    D, SE, ST, W, r = self.D, self.SE, self.ST, self.world, self.rank
+    self.backend.exchange_smooth(D, self.d, r, W, self.n, calibrate, self.gather_b, SE + ST + 3, self.seed,
+                                 self.cscale, self.scalars)
+    self.backend.stage_c(self.seed, r == W - 1, self.has_row0, self.cscale, means_loc, chols_loc, self.pay_c)
+
+
+def _phase_d(self):
+    sc = self.scalars
+    self.backend.exchange_scalars(self.world, self.gather_c, sc)
+    return dict(nll=sc[nat.S_NLL], obj=sc[nat.S_OBJ], ssq=sc[nat.S_SSQ], ssq_proper=sc[nat.S_SSQ_PROPER],
+                not_close=sc[nat.S_NOT_CLOSE], scalars=sc)
+
+
+ShardedPass.phase_a, ShardedPass.phase_b, ShardedPass.phase_c, ShardedPass.phase_d = _phase_a, _phase_b, _phase_c, _phase_d
+ShardedPass._run_fused = _run_fused
 
 
 def _shifted(t, shift, width):
@@ -230,6 +303,8 @@ def solve_sharded(*, f, y0, ts, order, init="constant", calibrate=True, maxiters
                                                         lin["scale0"], nat.ptr(means[t1row:]), nat.ptr(Jc)),
                   "linearize")
         res = sp.run(x0.mean, x0.chol, Jc, None, means, chols, calibrate=True)  # the loop always calibrates
+        if "scalars" in res:
+            return res["scalars"]  # (nll, obj, ssq, ssq_proper, not_close, ...): written by the exchange kernels
         out5.copy_(torch.stack([res["nll"], res["obj"], res["ssq"], res["ssq_proper"], res["not_close"]]))
         return out5
 
@@ -246,7 +321,7 @@ def solve_sharded(*, f, y0, ts, order, init="constant", calibrate=True, maxiters
         if graph and step.graph is None and k >= 1 and dev.type == "cuda":
             step.capture()
         sc = step().cpu()
-        nll, obj, ssq, ssqp, n_bad = (float(v) for v in sc)
+        nll, obj, ssq, ssqp, n_bad = (float(v) for v in sc[:5])
         k += 1
     info = {"iterations": k, "nll": nll, "obj": obj, "sigma_squared": ssq, "calibrated": bool(calibrate),
             "sigma_squared_proper": ssqp}

@@ -134,3 +134,84 @@ def test_solve_sharded_nccl_matches_single_gpu(native_lib):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     for r in range(world):
         assert ret[r][0], ret[r]
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+@pytest.mark.parametrize("name,N,q,compact", [("fitzhughnagumo", 3001, 3, True), ("rigid_body", 1200, 2, False),
+                                              ("logistic", 257, 1, True)])
+def test_virtual_ranks_on_one_gpu_match_oracle(native_lib, world, name, N, q, compact):
+    """The whole time-sharded pass -- three stages per rank, the fused exchange kernels (carry fold + scalar
+    bookkeeping) -- with `world` VIRTUAL ranks driven in lockstep on ONE GPU: the all-gathers are concatenations.
+    Everything but NCCL itself is the multi-GPU code path, so a single-GPU lease still checks it against the oracle
+    (outputs 1e-9, covariances 1e-7, nll / obj 1e-9, sign-invariant sigma^2 1e-8)."""
+    import pof.ivp
+    from pof import _native as nat
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.sharded import ShardedPass
+    from pof.step import linearize_at_previous_states
+
+    from oracle import ivps as oivps
+    from oracle import pof_oracle as O
+
+    ivp, oivp = getattr(pof.ivp, name)(), getattr(oivps, name)()
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=ts, order=q)
+    st = get_initial_trajectory(setup, method="constant")
+    lin = setup["om"].f._pof_lin
+    d = lin["d"]
+    D = d * (q + 1)
+    dev = st.mean.device
+    dom = linearize_at_previous_states(setup["om"], st)
+    sps, states = [], []
+    for r in range(world):
+        sp = ShardedPass(N, d, q, setup["_qL"], rank=r, world=world, device=dev)
+        assert sp.backend.fused_exchange
+        r0 = 0 if r == 0 else sp.k_lo + 1
+        means = st.mean[r0:sp.k_hi + 1].contiguous().clone()
+        chols = torch.zeros((sp.rows, D, D), dtype=torch.float64, device=dev)
+        if compact:
+            sp.backend.set_compact(lin["scale0"], lin["scale1"])
+            Jc = torch.empty((sp.n_loc, d * d + d), dtype=torch.float64, device=dev)
+            ivp_id, params = lin["builtin"]
+            ph, pp = nat.host_doubles(list(params) + [0.0])
+            nat.check(nat.LIB.pof_linearize_ivp_compact_f64(nat.stream_ptr(), ivp_id, pp, len(params), sp.n_loc, d, q,
+                                                            lin["scale0"], nat.ptr(st.mean[sp.k_lo + 1:sp.k_hi + 1]
+                                                                                   .contiguous()), nat.ptr(Jc)), "lin")
+            H, c = Jc, None
+        else:
+            H, c = dom.H[sp.k_lo:sp.k_hi].contiguous(), dom.b[sp.k_lo:sp.k_hi].contiguous()
+        sps.append(sp)
+        states.append((setup["x0"].mean, setup["x0"].chol, H, c, means, chols, False, None, None))
+    for sp, s in zip(sps, states):
+        sp.phase_a(s)
+    gf = torch.cat([sp.carry_f for sp in sps])
+    for sp, s in zip(sps, states):
+        sp.gather_f.copy_(gf)
+        sp.phase_b(s)
+    gb = torch.cat([sp.pay_b for sp in sps])
+    for sp, s in zip(sps, states):
+        sp.gather_b.copy_(gb)
+        sp.phase_c(s)
+    gc = torch.cat([sp.pay_c for sp in sps])
+    res = []
+    for sp in sps:
+        sp.gather_c.copy_(gc)
+        res.append({k: float(v) for k, v in sp.phase_d().items() if k != "scalars"})
+    torch.cuda.synchronize()
+    assert all(r == res[0] for r in res), res  # bitwise identical scalars on every rank
+
+    osetup = O.set_up_solver(oivp, ts, q)
+    ost = O.get_initial_trajectory(osetup)
+    odom = O.linearize_at(osetup, ost.mean[1:])
+    oout, onll, oobj, ossq, ossqp = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom)
+    m = torch.cat([s[4] for s in states]).cpu().numpy()
+    Lc = torch.cat([s[5] for s in states]).cpu().numpy()
+    assert m.shape == oout.mean.shape
+    E0 = osetup["E0"]
+    y, yo = m @ E0.T, oout.mean @ E0.T
+    assert (np.abs(y - yo) <= 1e-9 * np.abs(yo).max(axis=0) + 1e-12).all()
+    C, Co = Lc @ np.swapaxes(Lc, -1, -2), oout.chol @ np.swapaxes(oout.chol, -1, -2)
+    assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
+    r = res[0]
+    assert abs(r["nll"] - onll) <= 1e-9 * abs(onll) + 1e-9 and abs(r["obj"] - oobj) <= 1e-9 * abs(oobj)
+    assert abs(r["ssq_proper"] - ossqp) <= 1e-8 * abs(ossqp) and abs(r["ssq"] - ossq) <= 1e-2 * abs(ossq)
