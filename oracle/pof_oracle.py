@@ -619,3 +619,44 @@ def sequential_eks_solve(ivp: IVP, ts, order, return_full_states=False, calibrat
         info["calibrated"] = True
     M = setup["P"] if return_full_states else setup["E0"]
     return MVNSqrt(states.mean @ M.T, np.einsum("ij,njk->nik", M, states.chol)), info
+
+
+# --------------------------------------------------------------------------------------
+# regularised iteration  (pof/iterators.py:53-112)
+# --------------------------------------------------------------------------------------
+def qpm_ieks_iterator(setup, init_traj: MVNSqrt, reg_start=1e20, reg_final=1e-20, steps=40, tau_start=None,
+                      tau_final=None, scan=associative_scan):
+    """iterators.py:53-112 `_qpm_ieks_iterator`: quadratic-penalty IEKS.  Observation noise R = (reg / n)^2 I with
+    cholR = reg / n * I (n = dtm.F.shape[0] transitions), reg and the tolerance tau shrink geometrically each time the
+    stage has converged.  Yields (states, nll, obj, reg)."""
+    x0, dtm = setup["x0"], setup["dtm"]
+    dom = linearize_at(setup, init_traj.mean[1:])
+    n, d = dom.b.shape
+    reg_fact = (reg_final / reg_start) ** (1 / steps)
+    if tau_start is None:
+        tau_start, tau_final = 1e5, 1e-5
+    tau_fact = (tau_final / tau_start) ** (1 / steps)
+    reg, tau = reg_start, tau_start
+    eye = np.broadcast_to(np.eye(d), (n, d, d))
+
+    def fs(dom, reg):
+        out, nll, obj, _, _ = linear_filtsmooth(x0, dtm, AffineModel(dom.H, dom.b, reg * eye / n), scan=scan)
+        return out, nll, obj
+
+    states, nll, obj = fs(dom, reg)
+    yield states, nll, obj, reg
+    while True:
+        nll_old, obj_old, states_old = nll, obj, states
+        dom = linearize_at(setup, states.mean[1:])
+        states, nll, obj = fs(dom, reg)
+        yield states, nll, obj, reg
+        if crit(obj, obj_old, nll, nll_old, states.mean, states_old.mean, rtol=tau, atol=tau):
+            reg *= reg_fact
+            tau *= tau_fact
+            if reg == 0:
+                break
+            elif reg < reg_final:
+                reg = 0.0
+                tau = min(tau_final, 1e-5)
+        if np.isnan(nll) or np.isnan(obj):
+            break

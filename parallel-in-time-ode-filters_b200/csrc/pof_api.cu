@@ -469,6 +469,11 @@ static void flow_down_elem(FlowArgs& fa, const WsLayout& wl, double* sx) {
     ++fa.nseg;
   }
 }
+// Element-form suffix scan of the smoother (its whole tree work runs concurrently with the filter scan, one state
+// combine per chunk remains afterwards) pays when the filter scan is long enough to hide it: 2 x log2(#chunks)
+// general smoothing combines against log2(#chunks) cheaper state-form ones after the scan.  Measured on B200 (FHN,
+// D = 8): break-even at ~40 steps per chunk (N ~ 2^18.5); below that the state-form down-sweep stays.
+static bool elem_suffix(const WsLayout& wl) { return wl.L >= 48; }
 static int zero_flags(cudaStream_t s, const WsLayout& wl, double* ws) {
   POF_CK(cudaMemsetAsync(ws + wl.o_flags, 0, wl.flag_words * sizeof(unsigned), s));
   return 0;
@@ -563,8 +568,8 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
       FlowArgs fa;
       flow_begin(fa, wl, sagg, ws + wl.o_sin, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SUP));
       flow_up(fa, wl, up_top);
-      flow_down_elem(fa, wl, ws + wl.o_sx);
-      POF_CK(tl->sflow(st, fa));
+      if (elem_suffix(wl)) flow_down_elem(fa, wl, ws + wl.o_sx);
+      if (fa.nseg) POF_CK(tl->sflow(st, fa));
       return 0;
     }
     for (int l = 0; l < up_top; ++l) {
@@ -607,8 +612,15 @@ static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
   {
     ProfScope ps(ctx, POF_SEG_SDOWN, s);
     if (!per_level) {
-      // seeds of all chunks at once: (terminal state) combined with the chunk's "everything later" aggregate
-      POF_CK(tl->sseed(s, root_m, 1, ws + wl.o_sx, sin_, wl.CS));
+      if (elem_suffix(wl)) {
+        // seeds of all chunks at once: (terminal state) combined with the chunk's "everything later" aggregate
+        POF_CK(tl->sseed(s, root_m, 1, ws + wl.o_sx, sin_, wl.CS));
+      } else {
+        FlowArgs fa;
+        flow_begin(fa, wl, sagg, sin_, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SDOWN));
+        flow_down(fa, wl, root_m, root_L);
+        POF_CK(tl->sflow(s, fa));
+      }
     } else {
       k_pack_state<<<1, 128, 0, s>>>(wl.D, root_m, root_L, sin_ + wl.tl.off[wl.tl.nlev - 1] * wl.ST);
       for (int l = wl.tl.nlev - 1; l >= 1; --l) {
@@ -728,8 +740,11 @@ int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len, uint32
   if (!ll) return 0;
   const TreeLaunch* tl = tree_for(ll, wl.D, flags);
   const int64_t leaf = 3, chunkk = 1, reduce = 2;
-  if (tl && !(flags & POF_F_TREE_PER_LEVEL))
-    return leaf + chunkk + reduce + 1 /*filter tree*/ + 1 /*smoother suffix scan, element form*/ + 1 /*chunk seeds*/;
+  if (tl && !(flags & POF_F_TREE_PER_LEVEL)) {
+    // smoother: element-form suffix scan (1) + chunk seeds (1), or up-sweep (1 if it has a level to build) + down-sweep
+    const int64_t sm = elem_suffix(wl) ? 2 : ((wl.tl.nlev >= 3 ? 1 : 0) + 1);
+    return leaf + chunkk + reduce + 1 /*filter tree*/ + sm;
+  }
   const int up_total = wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0;  // the root combine is skipped on one GPU
   const int down_total = wl.tl.nlev - 1;
   return leaf + chunkk + reduce + 2 /*pack*/ + 2 * (int64_t)(up_total + down_total);

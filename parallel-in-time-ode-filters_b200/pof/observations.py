@@ -28,3 +28,39 @@ def linearize(f, x):
     F_x = torch.func.jacfwd(f)(m)
     cholR = torch.zeros((res.shape[0], res.shape[0]), dtype=m.dtype, device=m.device)
     return AffineModel(F_x, res - F_x @ m, cholR)
+
+
+def linearize_ek0(f, x):
+    """reference observations.py:52-63: zeroth-order linearisation, H = E1 (no Jacobian of the vector field)"""
+    m = x.mean
+    res = f(m)
+    d = res.shape[0]
+    q = m.shape[0] // d - 1
+    E1 = torch.kron(torch.eye(d, dtype=m.dtype, device=m.device),
+                    torch.eye(1, q + 1, 1, dtype=m.dtype, device=m.device))
+    return AffineModel(E1, res - E1 @ m, torch.zeros((d, d), dtype=m.dtype, device=m.device))
+
+
+def uncertain_linearize(f, x):
+    """reference observations.py:43-49 (marked WIP upstream): cholR = tria(F_m chol)"""
+    m, CL = x.mean, x.chol
+    res = f(m)
+    F_m = torch.func.jacfwd(f)(m)
+    cholR = torch.linalg.qr((F_m @ CL).T, mode="r").R.T
+    return AffineModel(F_m, res - F_m @ m, cholR)
+
+
+def linearize_regularized(f, x, l):
+    """reference observations.py:66-83 (Levenberg-Marquardt regularisation): the EK1 model stacked with a pseudo-
+    observation x ~ N(m, I / l); observation dimension d + D.  Kept with the reference's exact (work-in-progress)
+    offset convention `full_b = [res, -m]`.  Host-/autodiff-side helper: the CUDA pass takes observations of dimension d."""
+    m = x.mean
+    res = f(m)
+    F_x = torch.func.jacfwd(f)(m)
+    d, D = res.shape[0], m.shape[0]
+    z = lambda *s: torch.zeros(*s, dtype=m.dtype, device=m.device)
+    eye = torch.eye(D, dtype=m.dtype, device=m.device)
+    full_b = torch.cat([res, -m])
+    full_H = torch.cat([F_x, eye], dim=0)
+    full_cholR = torch.cat([torch.cat([z(d, d), z(d, D)], dim=1), torch.cat([z(D, d), eye / l ** 0.5], dim=1)], dim=0)
+    return AffineModel(full_H, full_b, full_cholR)

@@ -261,9 +261,10 @@ class _RowShift:
 
 def solve_sharded(*, f, y0, ts, order, init="constant", calibrate=True, maxiters=10_000, group=None, chunk_len=None,
                   graph=True):
-    """The time-sharded form of `pof.solver.solve` (reference solver.py:11-73) for the built-in `pof.ivp` problems: one
+    """The time-sharded form of `pof.solver.solve` (reference solver.py:11-73): one
     process per GPU, rank r owns the contiguous rows `rows = slice(r0, k_hi + 1)` of the N grid points.  Every rank
-    runs the same IEKS loop; per iteration it linearises its shard (fused CUDA kernel, compact form), runs
+    runs the same IEKS loop; per iteration it linearises its shard (built-in `pof.ivp` problems: fused CUDA kernel,
+    compact form; any other `f`: torch.func autodiff on the device, dense (H, c)), runs
     `ShardedPass.run` (three stages, three small all-gathers) and evaluates the reference's stopping rule on scalars
     that are bitwise identical on all ranks -- so all ranks leave the loop in the same iteration without any further
     exchange.  After the first (eager) iteration the whole iteration is replayed from one CUDA graph per rank.
@@ -278,31 +279,44 @@ def solve_sharded(*, f, y0, ts, order, init="constant", calibrate=True, maxiters
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     setup = set_up_solver(f=f, y0=y0, ts=ts, order=order)
     lin = setup["om"].f._pof_lin
-    if lin["builtin"] is None:
-        raise NotImplementedError("solve_sharded: built-in pof.ivp vector fields only (fused linearisation kernel)")
+    builtin = lin["builtin"] is not None
     x0, dev = setup["x0"], setup["_device"]
     d, q = lin["d"], order
     D = d * (q + 1)
     N = len(setup["ts"])
     sp = ShardedPass(N, d, q, setup["_qL"], rank=rank, world=world, group=group, device=dev, chunk_len=chunk_len)
-    sp.backend.set_compact(lin["scale0"], lin["scale1"])
+    if builtin:
+        sp.backend.set_compact(lin["scale0"], lin["scale1"])
     r0 = 0 if sp.has_row0 else sp.k_lo + 1
     rows = slice(r0, sp.k_hi + 1)
     full = get_initial_trajectory(setup, method=init, means_only=True)
     means = full.mean[rows].contiguous().clone()
     del full
     chols = torch.empty((sp.rows, D, D), dtype=torch.float64, device=dev)
-    Jc = torch.empty((sp.n_loc, d * d + d), dtype=torch.float64, device=dev)
     t1row = 1 if sp.has_row0 else 0
-    ivp_id, params = lin["builtin"]
-    ph, pp = nat.host_doubles(list(params) + [0.0])
     out5 = torch.zeros(5, dtype=torch.float64, device=dev)
+    if builtin:
+        Jc = torch.empty((sp.n_loc, d * d + d), dtype=torch.float64, device=dev)
+        ivp_id, params = lin["builtin"]
+        ph, pp = nat.host_doubles(list(params) + [0.0])
+    else:
+        from .step import linearize_into
+
+        H = torch.empty((sp.n_loc, d, D), dtype=torch.float64, device=dev)
+        c = torch.empty((sp.n_loc, d), dtype=torch.float64, device=dev)
+        graph = False  # autodiff of a user function is not captured into a CUDA graph
 
     def iteration():
-        nat.check(nat.LIB.pof_linearize_ivp_compact_f64(nat.stream_ptr(), ivp_id, pp, len(params), sp.n_loc, d, q,
-                                                        lin["scale0"], nat.ptr(means[t1row:]), nat.ptr(Jc)),
-                  "linearize")
-        res = sp.run(x0.mean, x0.chol, Jc, None, means, chols, calibrate=True)  # the loop always calibrates
+        if builtin:
+            nat.check(nat.LIB.pof_linearize_ivp_compact_f64(nat.stream_ptr(), ivp_id, pp, len(params), sp.n_loc, d, q,
+                                                            lin["scale0"], nat.ptr(means[t1row:]), nat.ptr(Jc)),
+                      "linearize")
+            res = sp.run(x0.mean, x0.chol, Jc, None, means, chols, calibrate=True)  # the loop always calibrates
+        else:
+            # linearize_into linearises at rows 1.. of what it is given: prepend one (unused) row on ranks > 0
+            pts = means if sp.has_row0 else torch.cat([means[:1], means])
+            linearize_into(lin, pts, H, c)
+            res = sp.run(x0.mean, x0.chol, H, c, means, chols, calibrate=True)
         if "scalars" in res:
             return res["scalars"]  # (nll, obj, ssq, ssq_proper, not_close, ...): written by the exchange kernels
         out5.copy_(torch.stack([res["nll"], res["obj"], res["ssq"], res["ssq_proper"], res["not_close"]]))

@@ -36,7 +36,7 @@ def test_host_only_queries(native_lib):
     assert 1.1e9 < nb < 1.4e9  # dominated by the per-step backward kernels: n * 136 doubles
     # dataflow tree sweeps: 3 leaf kernels + chunk elements + 3 tree launches + 2 reductions; one launch per tree level
     # (flag POF_F_TREE_PER_LEVEL, kept for A/B measurements) needs ~6x as many
-    assert L.pof_launches_per_pass(1 << 20, 2, 3, 222, 0) == 9
+    assert L.pof_launches_per_pass(1 << 20, 2, 3, 222, 0) == 9 and L.pof_launches_per_pass(1 << 14, 2, 3, 4, 0) == 9
     assert L.pof_launches_per_pass(1 << 20, 2, 3, 222, 4) > 40
     # the forced large-state family fills the GPU with one chunk per resident CTA
     assert L.pof_default_chunk_len(1 << 20, 2, 3, 148, 1) > L.pof_default_chunk_len(1 << 20, 2, 3, 148, 0)

@@ -323,3 +323,33 @@ def test_tile_shared_memory_sweeps_match_oracle(native_lib, monkeypatch, name, k
     ost = O.get_initial_trajectory(osetup)
     odom = O.linearize_at(osetup, ost.mean[1:])
     _check_pass(out, nll, obj, ssq, osetup, odom, N)
+
+
+@pytest.mark.parametrize("name,kw,N,q", [("logistic", {}, 60, 2), ("lotkavolterra", {}, 120, 3)])
+def test_qpm_iterator_matches_oracle(native_lib, name, kw, N, q):
+    """The reference's regularised iteration (quadratic-penalty IEKS, iterators.py:53-112): observation noise
+    (reg / n) I driven from 1e20 to 0 -- every stage a pass of the noisy-observation CUDA kernels.  In lockstep with the
+    oracle restatement: same regularisation schedule (the stage switches depend on the stopping rule), nll / obj per
+    iterate, and the final trajectory (= the plain IEKS solution)."""
+    from pof.convenience import get_initial_trajectory
+    from pof.iterators import qpm_ieks_iterator
+    from pof.solver import solve
+
+    ivp, oivp = _pair(name, **kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    it, setup = qpm_ieks_iterator(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant")
+    osetup = O.set_up_solver(oivp, ts, q)
+    oit = O.qpm_ieks_iterator(osetup, O.get_initial_trajectory(osetup))
+    k = 0
+    for (st, nll, obj, reg), (ost, onll, oobj, oreg) in zip(it, oit):
+        assert reg == oreg, (k, reg, oreg)
+        assert abs(float(nll) - onll) <= 1e-7 * abs(onll) + 1e-7, (k, float(nll), onll)
+        assert abs(float(obj) - oobj) <= 1e-7 * abs(oobj) + 1e-9, (k, float(obj), oobj)
+        k += 1
+        assert k < 400
+    assert reg == 0.0 and k > 40
+    E0 = osetup["E0"]
+    y, yo = st.mean.cpu().numpy() @ E0.T, ost.mean @ E0.T
+    assert (np.abs(y - yo) <= 1e-9 * np.abs(yo).max(axis=0) + 1e-12).all()
+    ys, info = solve(f=ivp.f, y0=ivp.y0, ts=ts, order=q, init="constant")
+    assert (np.abs(y - ys.mean.cpu().numpy()) <= 1e-7 * np.abs(yo).max(axis=0)).all()
