@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--e2e-solve", action="store_true", help="also time a full solve() host -> host at N = 2^19")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f32: the optional fp32 mode (single GPU), reported separately; no parity gate applies")
     a = ap.parse_args()
     if a.log2n is None:
         a.log2n = int(np.log2(a.n_time)) if a.n_time else (22 if a.scaling == "strong" else 20)
@@ -316,6 +318,9 @@ def run_native(args):
     N_total = n_total_of(args, world)
     n = N_total - 1
     ivp = pof.ivp.fitzhughnagumo()
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    if tdt != torch.float64 and world > 1:
+        raise SystemExit("--dtype f32: single GPU only")
 
     def make_problem(n_tot):
         """(setup, constant-init means of this rank's rows, k_lo, k_hi)"""
@@ -332,7 +337,11 @@ def run_native(args):
             row[b * (q_ + 1)] = y0[b]
             row[b * (q_ + 1) + 1] = f0[b]
         row = setup["PI"] @ row
-        return setup, row.repeat(rows, 1).contiguous(), k_lo, k_hi
+        if tdt != torch.float64:
+            from pof.utils import MVNSqrt
+
+            setup = dict(setup, x0=MVNSqrt(setup["x0"].mean.to(tdt), setup["x0"].chol.to(tdt)))
+        return setup, row.repeat(rows, 1).to(tdt).contiguous(), k_lo, k_hi
 
     def make_step(setup, means, chols, k_lo, k_hi, n_tot, calibrate=True):
         """-> (step callable returning the 5 scalars as a device tensor, graph object, chunk_len, launches, ctx)"""
@@ -340,7 +349,7 @@ def run_native(args):
         x0, qL = setup["x0"], setup["_qL"]
         n_loc = k_hi - k_lo
         if world == 1:
-            scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+            scalars = torch.zeros(nat.NSCALARS, dtype=tdt, device=dev)
             fused = GraphedIteration(x0, qL, lin, means, chols, scalars, calibrate=calibrate)
             L = fused.ws.chunk_len
             launches = 1 + int(nat.LIB.pof_launches_per_pass(n_tot, d_, q_, L, nat.flags()))
@@ -412,7 +421,7 @@ def run_native(args):
     n_loc = k_hi - k_lo
     rows = means0.shape[0]
     means = means0.clone()
-    chols = torch.empty((rows, D_, D_), dtype=torch.float64, device=dev)
+    chols = torch.empty((rows, D_, D_), dtype=tdt, device=dev)
     step, fused, L, launches, ctx = make_step(setup, means, chols, k_lo, k_hi, N_total)
 
     its_to_converge = None
@@ -447,17 +456,18 @@ def run_native(args):
 
     # ---- end to end through the public call with HOST buffers: H2D of the previous trajectory means from pinned
     # memory, the iteration, D2H of the projected solution means E0 m (N,d) and the scalars
-    h_means = torch.empty((rows, D_), dtype=torch.float64).pin_memory()
+    h_means = torch.empty((rows, D_), dtype=tdt).pin_memory()
     h_means.copy_(means.cpu())
-    h_y = torch.empty((rows, d_), dtype=torch.float64).pin_memory()
-    h_sc = torch.empty(nat.NSCALARS, dtype=torch.float64).pin_memory()
-    ymean = torch.empty((rows, d_), dtype=torch.float64, device=dev)
+    h_y = torch.empty((rows, d_), dtype=tdt).pin_memory()
+    h_sc = torch.empty(nat.NSCALARS, dtype=tdt).pin_memory()
+    ymean = torch.empty((rows, d_), dtype=tdt, device=dev)
+    esz = 8 if tdt == torch.float64 else 4
 
     def e2e_step():
         means.copy_(h_means, non_blocking=True)
         sc = step()
-        nat.check(nat.LIB.pof_project_f64(nat.stream_ptr(), rows, d_, q_, setup["_scale0"], None, nat.ptr(means), None,
-                                          nat.ptr(ymean), None), "project")
+        nat.check(nat.fn("pof_project", tdt)(nat.stream_ptr(), rows, d_, q_, setup["_scale0"], None, nat.ptr(means),
+                                             None, nat.ptr(ymean), None), "project")
         h_y.copy_(ymean, non_blocking=True)
         h_sc.copy_(sc, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -465,13 +475,13 @@ def run_native(args):
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, max(3, args.steps // 2))
-    h2d = rows * D_ * 8
-    d2h = rows * d_ * 8 + nat.NSCALARS * 8
+    h2d = rows * D_ * esz
+    d2h = rows * d_ * esz + nat.NSCALARS * esz
 
     # ---- parity of the path that was just timed, against the CPU oracle, at a size the oracle finishes in seconds
     # (N_total = 2^15, same sharding, ONE uncalibrated pass from the constant trajectory); max over ranks
     parity = None
-    if not args.no_parity:
+    if not args.no_parity and tdt == torch.float64:
         parity = parity_check(torch, dist, nat, make_problem, make_step, rank, world, dev)
 
     # ---- FP64 peak of this device (no FP64 figure in MEASURED_PEAKS.json)
@@ -568,7 +578,7 @@ def run_native(args):
     }
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.dtype == "f64":
         cores = os.cpu_count() or 1
         n_cpu = min(N_total, 2 ** 20)
         ms_c, k_run, w_run, _ = oracle_iterations(n_cpu, cores, 1, 0, budget_s=120.0)
@@ -582,9 +592,10 @@ def run_native(args):
     if its_to_converge is not None:
         cfg["iterations_to_converge_before_timing"] = its_to_converge
     line = {
-        "metric": METRIC, "value": ms_iter, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_iter, "higher_is_better": False, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": cfg,
+        "metric": METRIC if args.dtype == "f64" else "ms per IEKS iteration (fp32: optional mode, reported separately)",
+        "value": ms_iter, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_iter, "higher_is_better": False, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": cfg,
         "time_steps_per_s": N_total / (ms_iter * 1e-3),
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,

@@ -256,6 +256,60 @@ int pof_prior_init_f64(pof_stream_t s, int64_t N, int d, int q, const double* qL
 int pof_project_f64(pof_stream_t s, int64_t N, int d, int q, double scale0, const double* mult_dev,
                     const double* means, const double* chols, double* ymean, double* ychol);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Optional fp32 mode (BASELINE north_star: "an optional fp32 mode reported separately"; the reference runs in fp32
+ * unless JAX_ENABLE_X64 is set).  The register-resident kernel family (d <= 4, D <= 16) compiled with the scalar type
+ * float: same entry points with the suffix _f32, same argument lists and semantics; every DEVICE array is float,
+ * host-side arguments (qL_host, params_host, scalings) stay double, the workspace is sized by
+ * pof_workspace_bytes_f32.  Not available in fp32: the large-state tile kernels (flags & POF_F_FAMILY_TILE, noisy
+ * observations, general transition models, Lorenz-96), the sequential EKS.  Accuracy: the disagreement between
+ * association orders grows like N^3; profiles/r02_fp32_accuracy.md lists where 1e-4 on the outputs holds. */
+size_t pof_workspace_bytes_f32(int64_t N, int d, int q, int64_t chunk_len);
+int pof_filter_combine_f32(pof_stream_t s, int64_t n, int D, const float* e1, const float* e2, float* out,
+                           uint32_t flags);
+int pof_smooth_combine_f32(pof_stream_t s, int64_t n, int D, const float* e1, const float* e2, float* out,
+                           uint32_t flags);
+int pof_linearize_ivp_f32(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
+                          double scale0, double scale1, const float* means_t1, float* H, float* c);
+int pof_linearize_ivp_compact_f32(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
+                                  int q, double scale0, const float* means_t1, float* Jc);
+int pof_linear_filtsmooth_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                              int64_t chunk_len, const double* qL_host, const float* x0_mean, const float* x0_chol,
+                              const float* H, const float* c, float* means, float* chols, float* fmeans, float* fchols,
+                              int calibrate, float* scalars, void* ws, size_t ws_bytes);
+int pof_ieks_iteration_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                           int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                           double scale0, double scale1, const float* x0_mean, const float* x0_chol, float* means,
+                           float* chols, int calibrate, float* scalars, void* ws, size_t ws_bytes);
+int pof_shard_stage_a_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const float* H, const float* c, float* carry_f,
+                          void* ws, size_t ws_bytes);
+int pof_shard_stage_b_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const float* H, const float* c,
+                          const float* state_in, float* fmeans, float* fchols, float* carry_s, float* state_end,
+                          float* partials, void* ws, size_t ws_bytes);
+int pof_shard_stage_a_compact_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host, const float* Jc, double scale0,
+                                  double scale1, float* carry_f, void* ws, size_t ws_bytes);
+int pof_shard_stage_b_compact_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host, const float* Jc, double scale0,
+                                  double scale1, const float* state_in, float* fmeans, float* fchols, float* carry_s,
+                                  float* state_end, float* partials, void* ws, size_t ws_bytes);
+int pof_shard_stage_c_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const float* seed, int is_last_rank, int has_row0,
+                          const float* cscale, float* means, float* chols, float* partials2, void* ws, size_t ws_bytes);
+int pof_shard_exchange_filter_f32(pof_stream_t s, uint32_t flags, int D, int rank, int world, const float* gathered,
+                                  int64_t stride, const float* x0_mean, const float* x0_chol, float* state_in,
+                                  float* scratch);
+int pof_shard_exchange_smooth_f32(pof_stream_t s, uint32_t flags, int D, int d, int rank, int world,
+                                  int64_t n_steps_total, int calibrate, const float* gathered, int64_t stride,
+                                  float* seed, float* scratch, float* cscale, float* scalars);
+int pof_shard_exchange_scalars_f32(pof_stream_t s, int world, const float* gathered, float* scalars);
+int pof_prior_init_f32(pof_stream_t s, int64_t N, int d, int q, const double* qL_host, const float* ts,
+                       const float* m0, float* means, float* chols);
+int pof_project_f32(pof_stream_t s, int64_t N, int d, int q, double scale0, const float* mult_dev, const float* means,
+                    const float* chols, float* ymean, float* ychol);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,9 @@ SOURCES = [
     "pof_tree_a.cu", "pof_tree_b.cu", "pof_tree_c.cu",
     "pof_lane2_d1.cu", "pof_lane2_d2.cu", "pof_lane2_d3.cu", "pof_lane2_d4.cu",
     "pof_tile.cu",
+    # the optional fp32 mode: the same register-resident sources compiled with the scalar type float (pof_real.cuh)
+    "pof_api_f32.cu", "pof_lane2_d1_f32.cu", "pof_lane2_d2_f32.cu", "pof_lane2_d3_f32.cu", "pof_lane2_d4_f32.cu",
+    "pof_tree_a_f32.cu", "pof_tree_b_f32.cu", "pof_tree_c_f32.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

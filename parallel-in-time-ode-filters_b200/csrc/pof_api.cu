@@ -15,29 +15,17 @@
 #include <mutex>
 
 #include "../../include/pof_b200.h"
-#include "pof_coop.cuh"
+#include "pof_ctx.h"
 #include "pof_ivp.cuh"
 #include "pof_launch.cuh"
+#include "pof_tree_levels.cuh"
+#ifndef POF_F32
+#include "pof_coop.cuh"
 #include "pof_pipeline.cuh"
+#endif
 
-// caller-owned execution context: the side stream on which the smoother's up-sweep runs concurrently with the filter
-// scan (fork/join through events, so a pass stays stream-ordered on the caller's stream and is capturable), and the
-// optional per-segment timing state.  One context per concurrently running pass; no library-global state.
-struct pof_ctx {
-  int dev = 0;
-  cudaStream_t s2 = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  // ---- per-segment device timing (bench.py): CUDA events recorded on the launching stream around each segment
-  static constexpr int MAXP = 4096;
-  bool prof_on = false;
-  cudaEvent_t ev[MAXP][2];
-  int seg[MAXP];
-  int created = 0, used = 0;
-  double acc[POF_SEG_COUNT] = {0};
-  long cnt[POF_SEG_COUNT] = {0};
-};
-
-namespace pof {
+namespace POF_NS {
+using namespace pof;  // IvpParams, ivp_eval, TreeLevels (fp64-only helpers shared by both builds)
 
 static const TreeLaunch* tree_launch(int D) {
   const TreeLaunch* t = tree_launch_a(D);
@@ -55,6 +43,7 @@ static const LeafLaunch* lane2_launch(int d, int q) {
     default: return nullptr;
   }
 }
+#ifndef POF_F32
 // one-thread sequential EKS (pof_seq_kernels.cuh), d <= 4
 static const LeafLaunch* seq_launch(int d, int q) {
   switch (d) {
@@ -65,6 +54,7 @@ static const LeafLaunch* seq_launch(int d, int q) {
     default: return nullptr;
   }
 }
+#endif  // !POF_F32
 // the kernel family that serves (d, q): lane2 where instantiated, else (or when POF_F_FAMILY_TILE asks for it) tile
 static const LeafLaunch* leaf_launch(int d, int q, unsigned flags) {
   if (!(flags & POF_F_FAMILY_TILE)) {
@@ -78,18 +68,19 @@ static const TreeLaunch* tree_for(const LeafLaunch* ll, int D, unsigned flags) {
   return tree_launch(D);
 }
 
+#ifndef POF_F32
 // ------------------------------------------------------------------------------------------------ rank-carry chains
 // sequential chains over a handful of rank carries (one warp)
 __global__ void __launch_bounds__(32)
-    k_filter_chain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
-                   double* __restrict__ state_out, double* __restrict__ scratch) {
-  extern __shared__ double sm[];
+    k_filter_chain(int D, int count, const real* __restrict__ state_in, const real* __restrict__ elems,
+                   real* __restrict__ state_out, real* __restrict__ scratch) {
+  extern __shared__ real sm[];
   Warp w;
   const int FE = filter_elem_size(D), ST = state_size(D);
   // ping-pong between state_out and scratch so that the last write lands in state_out
-  const double* cur = state_in;
+  const real* cur = state_in;
   for (int i = 0; i < count; ++i) {
-    double* dst = ((count - 1 - i) % 2 == 0) ? state_out : scratch;
+    real* dst = ((count - 1 - i) % 2 == 0) ? state_out : scratch;
     filter_combine(w, D, cur, elems + (long)i * FE, dst, sm, true);
     w.sync();
     cur = dst;
@@ -97,14 +88,14 @@ __global__ void __launch_bounds__(32)
   if (count == 0) coop_copy(w, state_out, state_in, ST);
 }
 __global__ void __launch_bounds__(32)
-    k_smooth_chain(int D, int count, const double* __restrict__ state_in, const double* __restrict__ elems,
-                   double* __restrict__ state_out, double* __restrict__ scratch) {
-  extern __shared__ double sm[];
+    k_smooth_chain(int D, int count, const real* __restrict__ state_in, const real* __restrict__ elems,
+                   real* __restrict__ state_out, real* __restrict__ scratch) {
+  extern __shared__ real sm[];
   Warp w;
   const int SE = smooth_elem_size(D), ST = state_size(D);
-  const double* cur = state_in;
+  const real* cur = state_in;
   for (int i = 0; i < count; ++i) {
-    double* dst = ((count - 1 - i) % 2 == 0) ? state_out : scratch;
+    real* dst = ((count - 1 - i) % 2 == 0) ? state_out : scratch;
     smooth_combine(w, D, cur, elems + (long)(count - 1 - i) * SE, dst, sm, true);
     w.sync();
     cur = dst;
@@ -113,17 +104,18 @@ __global__ void __launch_bounds__(32)
 }
 
 
+#endif  // !POF_F32
 // ------------------------------------------------------------------------------------------------ reductions
 // out[j] = sum_i part[i*NC + j], fixed summation order (deterministic), single CTA of 1024 threads: every thread
 // accumulates its strided share of all NC components with independent loads, then a shuffle tree per warp and one
 // over the 32 warp sums.  The scalars of the pass are finalised by the same launch (MODE 1: filter statistics,
 // MODE 2: smoother statistics, MODE 0: sums only).
 template <int NC, int MODE>
-__global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restrict__ part, long cnt,
-                                                         double* __restrict__ out, double n, double d, int calibrate,
-                                                         double* __restrict__ scal) {
-  __shared__ double sh[32][NC];
-  double s[NC];
+__global__ void __launch_bounds__(1024) k_reduce_parts_t(const real* __restrict__ part, long cnt,
+                                                         real* __restrict__ out, real n, real d, int calibrate,
+                                                         real* __restrict__ scal) {
+  __shared__ real sh[32][NC];
+  real s[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) s[j] = 0.0;
   for (long i = threadIdx.x; i < cnt; i += 1024) {
@@ -142,7 +134,7 @@ __global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restric
   }
   __syncthreads();
   if (warp == 0) {
-    double v[NC];
+    real v[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       v[j] = sh[lane][j];
@@ -153,7 +145,7 @@ __global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restric
 #pragma unroll
       for (int j = 0; j < NC; ++j) out[j] = v[j];
       if (MODE == 1 && scal) {  // [nll, s1, s2] over n*d observations (filter.py:96-114)
-        const double ssq = v[1] / n / d;
+        const real ssq = v[1] / n / d;
         scal[POF_S_NLL] = v[0];
         scal[POF_S_SSQ] = ssq;
         scal[POF_S_SSQ_PROPER] = v[2 < NC ? 2 : 0] / n / d;
@@ -166,7 +158,8 @@ __global__ void __launch_bounds__(1024) k_reduce_parts_t(const double* __restric
     }
   }
 }
-__global__ void k_finalize_seq(const double* __restrict__ sums, double n, double d, double* __restrict__ scal) {
+#ifndef POF_F32
+__global__ void k_finalize_seq(const real* __restrict__ sums, real n, real d, real* __restrict__ scal) {
   scal[POF_S_NLL] = -sums[0];
   scal[POF_S_SSQ] = sums[1] / n / d;
   scal[POF_S_SSQ_PROPER] = sums[2] / n / d;
@@ -174,8 +167,9 @@ __global__ void k_finalize_seq(const double* __restrict__ sums, double n, double
   scal[POF_S_NOT_CLOSE] = 0.0;
   scal[POF_S_CSCALE] = 1.0;
 }
-__global__ void k_pack_state(int D, const double* __restrict__ m, const double* __restrict__ L,
-                             double* __restrict__ st) {
+#endif  // !POF_F32
+__global__ void k_pack_state(int D, const real* __restrict__ m, const real* __restrict__ L,
+                             real* __restrict__ st) {
   for (int i = threadIdx.x; i < D + D * D; i += blockDim.x) st[i] = (i < D) ? m[i] : L[i - D];
 }
 
@@ -183,69 +177,75 @@ __global__ void k_pack_state(int D, const double* __restrict__ m, const double* 
 // one thread per step k: H_k = E1 - J E0, c_k = J y - f(y) at y = E0 m_{k+1}
 __global__ void __launch_bounds__(256)
     k_linearize(int ivp_id, IvpParams P, long n, int d, int q, double scale0, double scale1,
-                const double* __restrict__ means_t1, double* __restrict__ H, double* __restrict__ c) {
+                const real* __restrict__ means_t1, real* __restrict__ H, real* __restrict__ c) {
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int Q1 = q + 1, D = d * Q1;
   double y[4], f[4], J[16];
-  for (int b = 0; b < d; ++b) y[b] = scale0 * means_t1[k * D + b * Q1];
+  for (int b = 0; b < d; ++b) y[b] = scale0 * (double)means_t1[k * D + b * Q1];
   ivp_eval(ivp_id, P, y, f, J);
   for (int a = 0; a < d; ++a) {
     double ca = -f[a];
     for (int b = 0; b < d; ++b) ca = fma(J[a * d + b], y[b], ca);
-    c[k * d + a] = ca;
-    double* Hr = H + (k * d + a) * D;
+    c[k * d + a] = (real)ca;
+    real* Hr = H + (k * d + a) * D;
     for (int j = 0; j < D; ++j) Hr[j] = 0.0;
-    for (int b = 0; b < d; ++b) Hr[b * Q1] = -J[a * d + b] * scale0;
-    Hr[a * Q1 + 1] += scale1;
+    for (int b = 0; b < d; ++b) Hr[b * Q1] = (real)(-J[a * d + b] * scale0);
+    Hr[a * Q1 + 1] += (real)scale1;
   }
 }
 // compact linearisation: per step [J_f (d x d) | c (d)] with c = J_f y - f(y); the leaf kernels rebuild H on load
 __global__ void __launch_bounds__(256)
     k_linearize_compact(int ivp_id, IvpParams P, long n, int d, int q, double scale0,
-                        const double* __restrict__ means_t1, double* __restrict__ Jc) {
+                        const real* __restrict__ means_t1, real* __restrict__ Jc) {
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int Q1 = q + 1, D = d * Q1;
   double y[4], f[4], J[16];
-  for (int b = 0; b < d; ++b) y[b] = scale0 * means_t1[k * D + b * Q1];
+  for (int b = 0; b < d; ++b) y[b] = scale0 * (double)means_t1[k * D + b * Q1];
   ivp_eval(ivp_id, P, y, f, J);
-  double* o = Jc + k * (d * d + d);
+  real* o = Jc + k * (d * d + d);
   for (int a = 0; a < d; ++a) {
     double ca = -f[a];
     for (int b = 0; b < d; ++b) {
       ca = fma(J[a * d + b], y[b], ca);
-      o[a * d + b] = J[a * d + b];
+      o[a * d + b] = (real)J[a * d + b];
     }
-    o[d * d + a] = ca;
+    o[d * d + a] = (real)ca;
   }
 }
+#ifndef POF_F32
 // Lorenz-96 (POF_IVP_LORENZ96; the larger-state problem of BASELINE config 5, not in the reference's ivp.py):
 //   f_a = (y_{a+1} - y_{a-2}) y_{a-1} - y_a + F (cyclic), 4 <= d.  One thread per (step, component): row a of the
 // Jacobian has the three entries d f_a / d y_{a+1} = y_{a-1}, d f_a / d y_{a-2} = -y_{a-1}, d f_a / d y_{a-1} =
 // y_{a+1} - y_{a-2} and -1 on the diagonal.  dense != 0: H (n,d,D), c (n,d); else compact [J_f | c] per step.
 __global__ void __launch_bounds__(256)
-    k_linearize_l96(double forcing, long n, int d, int q, double scale0, double scale1, int dense,
-                    const double* __restrict__ means_t1, double* __restrict__ H, double* __restrict__ c,
-                    double* __restrict__ Jc) {
+    k_linearize_l96(real forcing, long n, int d, int q, double scale0, double scale1, int dense,
+                    const real* __restrict__ means_t1, real* __restrict__ H, real* __restrict__ c,
+                    real* __restrict__ Jc) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * d) return;
   l96_linearize_row(forcing, idx / d, (int)(idx % d), d, q, scale0, scale1, dense, means_t1, H, c, Jc);
 }
+#endif  // !POF_F32
 // built-in problem ids and the ODE dimension each one accepts
 static bool ivp_dim_ok(int ivp_id, int d) {
   static const int dims[] = {1, 2, 2, 2, 3, 3, 4, 4, 4};
+#ifndef POF_F32
   if (ivp_id == POF_IVP_LORENZ96) return d >= 4 && d <= 64;
+#else
+  if (ivp_id == POF_IVP_LORENZ96) return false;  // large states: the fp64-only tile family
+#endif
   return ivp_id >= 0 && ivp_id <= POF_IVP_HENONHEILES && dims[ivp_id] == d;
 }
 
 // ys = E0 states, with the (second) calibration multiplier of pof/solver.py:66-69 read from device memory
 __global__ void __launch_bounds__(256)
-    k_project(long N, int d, int q, double scale0, const double* __restrict__ mult, const double* __restrict__ means,
-              const double* __restrict__ chols, double* __restrict__ ymean, double* __restrict__ ychol) {
+    k_project(long N, int d, int q, double scale0, const real* __restrict__ mult, const real* __restrict__ means,
+              const real* __restrict__ chols, real* __restrict__ ymean, real* __restrict__ ychol) {
   const int Q1 = q + 1, D = d * Q1;
   const long total = N * d * (D + 1);
-  const double mu = mult ? *mult : 1.0;
+  const real mu = mult ? *mult : 1.0;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const long row = idx / (D + 1);
     const int col = (int)(idx - row * (D + 1));
@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(256)
 // lower triangular already), row 0 = x0.  One thread per (row, state component); the literal P F PI product is kept
 // (ts[k] = 0 gives NaN exactly like the reference's 0 * inf).
 __global__ void __launch_bounds__(256)
-    k_prior_init(long N, int d, int q, const double* __restrict__ ts, const double* __restrict__ m0, QLParam ql,
-                 double* __restrict__ means, double* __restrict__ chols) {
+    k_prior_init(long N, int d, int q, const real* __restrict__ ts, const real* __restrict__ m0, QLParam ql,
+                 real* __restrict__ means, real* __restrict__ chols) {
   const int Q1 = q + 1, D = d * Q1;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * D) return;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256)
       for (int c = 0; c < D; ++c) chols[(long)r * D + c] = 0.0;
     return;
   }
-  const double t = fabs(ts[k]);
+  const double t = fabs((double)ts[k]);  // (evaluated in double whatever the storage type: a one-off set-up kernel)
   double fact[6];
   fact[0] = 1.0;
   for (int p = 1; p <= q; ++p) fact[p] = fact[p - 1] * p;
@@ -286,33 +286,35 @@ __global__ void __launch_bounds__(256)
   double acc = 0.0;
   for (int j = i; j < Q1; ++j) {
     const double svi = pow(t, -((double)(q - j) + 0.5)) * fact[q - j];
-    acc = fma(binom(q - i, j - i), svi * m0[blk * Q1 + j], acc);
+    acc = fma((double)binom(q - i, j - i), svi * (double)m0[blk * Q1 + j], acc);
   }
   const double sv = pow(t, (double)(q - i) + 0.5) / fact[q - i];
-  means[k * D + r] = sv * acc;
+  means[k * D + r] = (real)(sv * acc);
   if (chols) {
-    double* row = chols + (k * D + r) * D;
+    real* row = chols + (k * D + r) * D;
     for (int c = 0; c < D; ++c) row[c] = 0.0;
-    for (int j = 0; j <= i; ++j) row[blk * Q1 + j] = -sv * ql.v[i * Q1 + j];
+    for (int j = 0; j <= i; ++j) row[blk * Q1 + j] = (real)(-sv * (double)ql.v[i * Q1 + j]);
   }
 }
 
+#ifndef POF_F32
 // 16 independent FMA chains per thread: saturates the FP64 pipe
-__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double* __restrict__ sink) {
-  double a[16];
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, real* __restrict__ sink) {
+  real a[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
-  const double m = 1.0 - 1e-12, c = 1e-13;
+  const real m = 1.0 - 1e-12, c = 1e-13;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
   }
-  double t = 0.0;
+  real t = 0.0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) t += a[i];
   if (t == 123.456) sink[threadIdx.x] = t;
 }
 
+#endif  // !POF_F32
 // ------------------------------------------------------------------------------------------------ workspace
 struct WsLayout {
   TreeLevels tl;
@@ -354,8 +356,8 @@ struct WsLayout {
     o_flags = take((flag_words + 1) / 2);
     total = o;
   }
-  unsigned* ticket(double* ws, int which) const { return (unsigned*)(ws + o_flags) + 16 * which; }
-  unsigned* flags(double* ws, int which) const { return (unsigned*)(ws + o_flags) + 64 + (size_t)which * tl.total; }
+  unsigned* ticket(real* ws, int which) const { return (unsigned*)(ws + o_flags) + 16 * which; }
+  unsigned* flags(real* ws, int which) const { return (unsigned*)(ws + o_flags) + 64 + (size_t)which * tl.total; }
 };
 
 struct ProfScope {
@@ -387,7 +389,7 @@ struct ProfScope {
     }                                 \
   } while (0)
 
-static int make_args(long n, int d, int q, const double* qL_host, const double* H, const double* c,
+static int make_args(long n, int d, int q, const double* qL_host, const real* H, const real* c,
                      const WsLayout& wl, unsigned flags, LeafArgs& a) {
   if (q < 1 || q > 5) return POF_E_UNSUPPORTED_DQ;
   a.n = n;
@@ -409,7 +411,7 @@ static int make_args(long n, int d, int q, const double* qL_host, const double* 
 }
 
 // ---- dataflow sweeps (FlowArgs, pof_launch.cuh)
-static void flow_begin(FlowArgs& fa, const WsLayout& wl, double* agg, double* st, unsigned* f_up, unsigned* f_dn,
+static void flow_begin(FlowArgs& fa, const WsLayout& wl, real* agg, real* st, unsigned* f_up, unsigned* f_dn,
                        unsigned* ticket) {
   fa.nlev = wl.tl.nlev;
   for (int l = 0; l < FlowArgs::MAXL; ++l) {
@@ -440,7 +442,7 @@ static void flow_up(FlowArgs& fa, const WsLayout& wl, int top) {
   }
 }
 // down-sweep from the root state (root_m, root_L): states of all nodes, level nlev-1 .. 0
-static void flow_down(FlowArgs& fa, const WsLayout& wl, const double* root_m, const double* root_L) {
+static void flow_down(FlowArgs& fa, const WsLayout& wl, const real* root_m, const real* root_L) {
   fa.root_m = root_m;
   fa.root_L = root_L;
   fa.seg_kind[fa.nseg] = FlowArgs::ROOT;
@@ -455,7 +457,7 @@ static void flow_down(FlowArgs& fa, const WsLayout& wl, const double* root_m, co
   }
 }
 // smoother only: element-form down-sweep -- per node the aggregate of all LATER nodes (identity at the root)
-static void flow_down_elem(FlowArgs& fa, const WsLayout& wl, double* sx) {
+static void flow_down_elem(FlowArgs& fa, const WsLayout& wl, real* sx) {
   fa.sx = sx;
   fa.root_m = fa.root_L = nullptr;
   fa.seg_kind[fa.nseg] = FlowArgs::ROOT;
@@ -474,7 +476,7 @@ static void flow_down_elem(FlowArgs& fa, const WsLayout& wl, double* sx) {
 // general smoothing combines against log2(#chunks) cheaper state-form ones after the scan.  Measured on B200 (FHN,
 // D = 8): break-even at ~40 steps per chunk (N ~ 2^18.5); below that the state-form down-sweep stays.
 static bool elem_suffix(const WsLayout& wl) { return wl.L >= 48; }
-static int zero_flags(cudaStream_t s, const WsLayout& wl, double* ws) {
+static int zero_flags(cudaStream_t s, const WsLayout& wl, real* ws) {
   POF_CK(cudaMemsetAsync(ws + wl.o_flags, 0, wl.flag_words * sizeof(unsigned), s));
   return 0;
 }
@@ -485,8 +487,8 @@ enum { FL_FUP = 0, FL_FDN = 1, FL_SUP = 2, FL_SDN = 3 };
 // stage A: fold (+ in the time-sharded form, need_root: the filter up-sweep whose root is the shard's carry element;
 // on one GPU the up-sweep runs in the same dataflow launch as the down-sweep, in stage B)
 static int stage_a(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
-                   const WsLayout& wl, double* ws, bool need_root) {
-  double* fagg = ws + wl.o_fagg;
+                   const WsLayout& wl, real* ws, bool need_root) {
+  real* fagg = ws + wl.o_fagg;
   {
     ProfScope ps(ctx, POF_SEG_FOLD, s);
     POF_CK(ll->fold(s, a, fagg, ws + wl.o_faggm));
@@ -515,11 +517,11 @@ static int stage_a(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
 // (root_m, root_L), then the filter scan on `s` while the chunk-level smoothing elements and the smoother's up-sweep
 // run on the context's side stream (their inputs only depend on the fold and the filter tree), join, filter scalars.
 static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
-                   const WsLayout& wl, double* ws, const double* root_m, const double* root_L, double* fmeans,
-                   double* fchols, bool need_root, double n_obs_total, int calibrate, double* scalars) {
-  double* fagg = ws + wl.o_fagg;
-  double* fin = ws + wl.o_fin;
-  double* sagg = ws + wl.o_sagg;
+                   const WsLayout& wl, real* ws, const real* root_m, const real* root_L, real* fmeans,
+                   real* fchols, bool need_root, real n_obs_total, int calibrate, real* scalars) {
+  real* fagg = ws + wl.o_fagg;
+  real* fin = ws + wl.o_fin;
+  real* sagg = ws + wl.o_sagg;
   const TreeLaunch* tl = tree_for(ll, wl.D, flags);
   const bool per_level = !tl || (flags & POF_F_TREE_PER_LEVEL);
   const int up_top = wl.tl.nlev - 1 - (need_root ? 0 : 1);  // the root element is only consumed by the sharded form
@@ -596,17 +598,17 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
     POF_CK(cudaStreamWaitEvent(s, ctx->join, 0));
   else if (int rc = smoother_up(s))
     return rc;
-  k_reduce_parts_t<3, 1><<<1, 1024, 0, s>>>(ws + wl.o_part, wl.CS, ws + wl.o_sums, n_obs_total, (double)a.d, calibrate,
+  k_reduce_parts_t<3, 1><<<1, 1024, 0, s>>>(ws + wl.o_part, wl.CS, ws + wl.o_sums, n_obs_total, (real)a.d, calibrate,
                                             scalars);
   return (int)cudaGetLastError();
 }
 
 // stage C: smoother down-sweep from the seed (root_m, root_L) + smoother scan + smoother scalars
 static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
-                   const WsLayout& wl, double* ws, const double* root_m, const double* root_L, int emit_t0,
-                   const double* cscale, double* means, double* chols, double* scalars) {
-  double* sagg = ws + wl.o_sagg;
-  double* sin_ = ws + wl.o_sin;
+                   const WsLayout& wl, real* ws, const real* root_m, const real* root_L, int emit_t0,
+                   const real* cscale, real* means, real* chols, real* scalars) {
+  real* sagg = ws + wl.o_sagg;
+  real* sin_ = ws + wl.o_sin;
   const TreeLaunch* tl = tree_for(ll, wl.D, flags);
   const bool per_level = !tl || (flags & POF_F_TREE_PER_LEVEL);
   {
@@ -644,19 +646,19 @@ static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
 }
 
 static int run_pass(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
-                    const WsLayout& wl, double* ws, int64_t N, const double* x0_mean, const double* x0_chol,
-                    double* means, double* chols, double* fmeans, double* fchols, int calibrate, double* scalars) {
+                    const WsLayout& wl, real* ws, int64_t N, const real* x0_mean, const real* x0_chol,
+                    real* means, real* chols, real* fmeans, real* fchols, int calibrate, real* scalars) {
   if (int rc = zero_flags(s, wl, ws)) return rc;
   if (int rc = stage_a(s, ctx, flags, ll, a, wl, ws, false)) return rc;
   if (fmeans) {
-    POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    POF_CK(cudaMemcpyAsync(fmeans, x0_mean, wl.D * sizeof(real), cudaMemcpyDeviceToDevice, s));
+    POF_CK(cudaMemcpyAsync(fchols, x0_chol, wl.D * wl.D * sizeof(real), cudaMemcpyDeviceToDevice, s));
   }
-  if (int rc = stage_b(s, ctx, flags, ll, a, wl, ws, x0_mean, x0_chol, fmeans, fchols, false, (double)(N - 1), calibrate,
+  if (int rc = stage_b(s, ctx, flags, ll, a, wl, ws, x0_mean, x0_chol, fmeans, fchols, false, (real)(N - 1), calibrate,
                        scalars))
     return rc;
   // terminal smoothing state = filtered state at the last time point
-  const double* term = ws + wl.o_send + (wl.CS - 1) * wl.ST;
+  const real* term = ws + wl.o_send + (wl.CS - 1) * wl.ST;
   return stage_c(s, ctx, flags, ll, a, wl, ws, term, term + wl.D, 1, scalars + POF_S_CSCALE, means, chols, scalars);
 }
 
@@ -667,12 +669,13 @@ static int fill_params(int ivp_id, const double* params_host, int nparams, int d
   return 0;
 }
 
-}  // namespace pof
+}  // namespace POF_NS
 
-using namespace pof;
+using namespace POF_NS;
 
 extern "C" {
 
+#ifndef POF_F32
 int pof_supported(int d, int q) { return leaf_launch(d, q, 0) != nullptr ? 1 : 0; }
 int pof_supported_tile(int d, int q) { return tile_supported(d, q) ? 1 : 0; }
 
@@ -757,8 +760,8 @@ int pof_measure_dfma_tflops(pof_stream_t s_, double* tflops_out) {
   int dev = 0, sms = 0;
   POF_CK(cudaGetDevice(&dev));
   POF_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  double* sink = nullptr;
-  POF_CK(cudaMalloc(&sink, sizeof(double) * 1024));
+  real* sink = nullptr;
+  POF_CK(cudaMalloc(&sink, sizeof(real) * 1024));
   const int iters = 1 << 14, blocks = sms * 8, threads = 256;
   cudaEvent_t e0, e1;
   POF_CK(cudaEventCreate(&e0));
@@ -776,7 +779,7 @@ int pof_measure_dfma_tflops(pof_stream_t s_, double* tflops_out) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(sink);
-  const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  const real flops = 2.0 * 16.0 * (real)iters * (real)blocks * (real)threads;
   *tflops_out = flops / (best * 1e-3) / 1e12;
   return 0;
 }
@@ -796,10 +799,18 @@ int64_t pof_default_chunk_len(int64_t N, int d, int q, int sm_count, uint32_t fl
 size_t pof_workspace_bytes(int64_t N, int d, int q, int64_t chunk_len) {
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  return wl.total * sizeof(double);
+  return wl.total * sizeof(real);
 }
 
-int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out,
+#else
+size_t pof_workspace_bytes_f32(int64_t N, int d, int q, int64_t chunk_len) {
+  WsLayout wl;
+  wl.build(N - 1, d, q, chunk_len);
+  return wl.total * sizeof(real);
+}
+#endif  // !POF_F32
+
+int POF_SUFFIX(pof_filter_combine)(pof_stream_t s, int64_t n, int D, const real* e1, const real* e2, real* out,
                            uint32_t flags) {
   if (n <= 0) return 0;
   if (!(flags & POF_F_FAMILY_TILE))
@@ -807,7 +818,7 @@ int pof_filter_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, c
   if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
   return (int)tile_fcomb((cudaStream_t)s, D, n, e1, e2, out);
 }
-int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, const double* e2, double* out,
+int POF_SUFFIX(pof_smooth_combine)(pof_stream_t s, int64_t n, int D, const real* e1, const real* e2, real* out,
                            uint32_t flags) {
   if (n <= 0) return 0;
   if (!(flags & POF_F_FAMILY_TILE))
@@ -816,60 +827,65 @@ int pof_smooth_combine_f64(pof_stream_t s, int64_t n, int D, const double* e1, c
   return (int)tile_scomb((cudaStream_t)s, D, n, e1, e2, out);
 }
 
-int pof_linearize_ivp_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
-                          double scale0, double scale1, const double* means_t1, double* H, double* c) {
+int POF_SUFFIX(pof_linearize_ivp)(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d, int q,
+                          double scale0, double scale1, const real* means_t1, real* H, real* c) {
   IvpParams P;
   if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
   if (n <= 0) return 0;
+#ifndef POF_F32
   if (ivp_id == POF_IVP_LORENZ96) {
     k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, (cudaStream_t)s>>>(P.p[0], n, d, q, scale0, scale1, 1,
                                                                                   means_t1, H, c, nullptr);
     return (int)cudaGetLastError();
   }
+#endif
   k_linearize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, scale1, means_t1,
                                                                         H, c);
   return (int)cudaGetLastError();
 }
 
-int pof_linearize_ivp_compact_f64(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
-                                  int q, double scale0, const double* means_t1, double* Jc) {
+int POF_SUFFIX(pof_linearize_ivp_compact)(pof_stream_t s, int ivp_id, const double* params_host, int nparams, int64_t n, int d,
+                                  int q, double scale0, const real* means_t1, real* Jc) {
   IvpParams P;
   if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
   if (n <= 0) return 0;
+#ifndef POF_F32
   if (ivp_id == POF_IVP_LORENZ96) {
     k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, (cudaStream_t)s>>>(P.p[0], n, d, q, scale0, 0.0, 0,
                                                                                   means_t1, nullptr, nullptr, Jc);
     return (int)cudaGetLastError();
   }
+#endif
   k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, means_t1,
                                                                                 Jc);
   return (int)cudaGetLastError();
 }
 
-int pof_linear_filtsmooth_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
-                              int64_t chunk_len, const double* qL_host, const double* x0_mean, const double* x0_chol,
-                              const double* H, const double* c, double* means, double* chols, double* fmeans,
-                              double* fchols, int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
+int POF_SUFFIX(pof_linear_filtsmooth)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                              int64_t chunk_len, const double* qL_host, const real* x0_mean, const real* x0_chol,
+                              const real* H, const real* c, real* means, real* chols, real* fmeans,
+                              real* fchols, int calibrate, real* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
   const LeafLaunch* ll = leaf_launch(d, q, flags);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  if (ws_bytes < wl.total * sizeof(real)) return POF_E_WORKSPACE;
   LeafArgs a;
   if (int rc = make_args(N - 1, d, q, qL_host, H, c, wl, flags, a)) return rc;
-  return run_pass(s, ctx, flags, ll, a, wl, (double*)ws_, N, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate,
+  return run_pass(s, ctx, flags, ll, a, wl, (real*)ws_, N, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate,
                   scalars);
 }
 
+#ifndef POF_F32
 // general linear-Gaussian model: always the tile family (the only leaves that carry the D-column posterior factor and
 // read dense per-step transition models)
-int pof_linear_filtsmooth_general_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
-                                      int64_t chunk_len, const double* qL_host, const double* F, const double* QL,
-                                      const double* x0_mean, const double* x0_chol, const double* H, const double* c,
-                                      const double* cholR, double* means, double* chols, double* fmeans, double* fchols,
-                                      int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
+int POF_SUFFIX(pof_linear_filtsmooth_general)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t N, int d, int q,
+                                      int64_t chunk_len, const double* qL_host, const real* F, const real* QL,
+                                      const real* x0_mean, const real* x0_chol, const real* H, const real* c,
+                                      const real* cholR, real* means, real* chols, real* fmeans, real* fchols,
+                                      int calibrate, real* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
   if ((F == nullptr) != (QL == nullptr)) return POF_E_ARG;
@@ -879,21 +895,23 @@ int pof_linear_filtsmooth_general_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t 
   const LeafLaunch* ll = tile_leaf_launch();
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  if (ws_bytes < wl.total * sizeof(real)) return POF_E_WORKSPACE;
   LeafArgs a;
   double ql_dummy[36] = {0.0};
   if (int rc = make_args(N - 1, d, q, qL_host ? qL_host : ql_dummy, H, c, wl, flags, a)) return rc;
   a.R = cholR;
   a.F = F;
   a.QLd = QL;
-  return run_pass(s, ctx, flags, ll, a, wl, (double*)ws_, N, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate,
+  return run_pass(s, ctx, flags, ll, a, wl, (real*)ws_, N, x0_mean, x0_chol, means, chols, fmeans, fchols, calibrate,
                   scalars);
 }
 
-int pof_ieks_iteration_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+#endif  // !POF_F32
+
+int POF_SUFFIX(pof_ieks_iteration)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
                            int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
-                           double scale0, double scale1, const double* x0_mean, const double* x0_chol, double* means,
-                           double* chols, int calibrate, double* scalars, void* ws_, size_t ws_bytes) {
+                           double scale0, double scale1, const real* x0_mean, const real* x0_chol, real* means,
+                           real* chols, int calibrate, real* scalars, void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
   IvpParams P;
@@ -902,16 +920,18 @@ int pof_ieks_iteration_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int 
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
+  if (ws_bytes < wl.total * sizeof(real)) return POF_E_WORKSPACE;
+  real* ws = (real*)ws_;
   const long n = N - 1;
   const int D = wl.D;
-  double* lin = ws + wl.o_lin;
+  real* lin = ws + wl.o_lin;
   // compact linearisation [J_f | c] per step; both kernel families rebuild H = E1 - J_f E0 on load
+#ifndef POF_F32
   if (ivp_id == POF_IVP_LORENZ96)
     k_linearize_l96<<<(unsigned)((n * d + 255) / 256), 256, 0, s>>>(P.p[0], n, d, q, scale0, 0.0, 0, means + D,
                                                                     nullptr, nullptr, lin);
   else
+#endif
     k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, means + D, lin);
   POF_CK(cudaGetLastError());
   LeafArgs a;
@@ -923,9 +943,10 @@ int pof_ieks_iteration_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int 
                   scalars);
 }
 
-int pof_sequential_eks_f64(pof_stream_t s_, uint32_t flags, int ivp_id, const double* params_host, int nparams,
+#ifndef POF_F32
+int POF_SUFFIX(pof_sequential_eks)(pof_stream_t s_, uint32_t flags, int ivp_id, const double* params_host, int nparams,
                            int64_t N, int d, int q, const double* qL_host, double scale0, double scale1,
-                           const double* x0_mean, const double* x0_chol, double* means, double* chols, double* scalars,
+                           const real* x0_mean, const real* x0_chol, real* means, real* chols, real* scalars,
                            void* ws_, size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   if (N < 2) return POF_E_ARG;
@@ -937,29 +958,31 @@ int pof_sequential_eks_f64(pof_stream_t s_, uint32_t flags, int ivp_id, const do
   if (!ll || !ll->seq_eks) return POF_E_UNSUPPORTED_DQ;
   WsLayout wl;
   wl.build(N - 1, d, q, N - 1);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
-  double* ws = (double*)ws_;
+  if (ws_bytes < wl.total * sizeof(real)) return POF_E_WORKSPACE;
+  real* ws = (real*)ws_;
   LeafArgs a;
   if (int rc = make_args(N - 1, d, q, qL_host, nullptr, nullptr, wl, flags, a)) return rc;
   a.s0 = scale0;
   a.s1 = scale1;
-  double* x0 = ws + wl.o_misc;
+  real* x0 = ws + wl.o_misc;
   k_pack_state<<<1, 128, 0, s>>>(wl.D, x0_mean, x0_chol, x0);
   POF_CK(ll->seq_eks(s, a, ivp_id, P.p, x0, ws + wl.o_kern, means, chols, ws + wl.o_sums));
   // scalars: NLL slot holds the reference's `ell` = +sum loglik (sequential path sign, filter.py:91)
-  k_finalize_seq<<<1, 1, 0, s>>>(ws + wl.o_sums, (double)(N - 1), (double)d, scalars);
+  k_finalize_seq<<<1, 1, 0, s>>>(ws + wl.o_sums, (real)(N - 1), (real)d, scalars);
   return (int)cudaGetLastError();
 }
 
+#endif  // !POF_F32
+
 // ---- time-sharded stages
-static int shard_setup(int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host, const double* H,
-                       const double* c, const double* Jc, double s0, double s1, uint32_t flags, size_t ws_bytes,
+static int shard_setup(int64_t n_loc, int d, int q, int64_t chunk_len, const double* qL_host, const real* H,
+                       const real* c, const real* Jc, double s0, double s1, uint32_t flags, size_t ws_bytes,
                        const LeafLaunch*& ll, WsLayout& wl, LeafArgs& a) {
   if (n_loc < 1) return POF_E_ARG;
   ll = leaf_launch(d, q, flags);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
   wl.build(n_loc, d, q, chunk_len);
-  if (ws_bytes < wl.total * sizeof(double)) return POF_E_WORKSPACE;
+  if (ws_bytes < wl.total * sizeof(real)) return POF_E_WORKSPACE;
   if (int rc = make_args(n_loc, d, q, qL_host, H, c, wl, flags, a)) return rc;
   if (Jc) {
     a.Jc = Jc;
@@ -969,69 +992,69 @@ static int shard_setup(int64_t n_loc, int d, int q, int64_t chunk_len, const dou
   return 0;
 }
 static int shard_a(cudaStream_t s, pof_ctx* ctx, uint32_t flags, int64_t n_loc, int d, int q, int64_t chunk_len,
-                   const double* qL_host, const double* H, const double* c, const double* Jc, double s0, double s1,
-                   double* carry_f, void* ws_, size_t ws_bytes) {
+                   const double* qL_host, const real* H, const real* c, const real* Jc, double s0, double s1,
+                   real* carry_f, void* ws_, size_t ws_bytes) {
   const LeafLaunch* ll;
   WsLayout wl;
   LeafArgs a;
   if (int rc = shard_setup(n_loc, d, q, chunk_len, qL_host, H, c, Jc, s0, s1, flags, ws_bytes, ll, wl, a)) return rc;
-  double* ws = (double*)ws_;
+  real* ws = (real*)ws_;
   if (int rc = zero_flags(s, wl, ws)) return rc;
   if (int rc = stage_a(s, ctx, flags, ll, a, wl, ws, true)) return rc;
-  POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(double),
+  POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(real),
                          cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 static int shard_b(cudaStream_t s, pof_ctx* ctx, uint32_t flags, int64_t n_loc, int d, int q, int64_t chunk_len,
-                   const double* qL_host, const double* H, const double* c, const double* Jc, double s0, double s1,
-                   const double* state_in, double* fmeans, double* fchols, double* carry_s, double* state_end,
-                   double* partials, void* ws_, size_t ws_bytes) {
+                   const double* qL_host, const real* H, const real* c, const real* Jc, double s0, double s1,
+                   const real* state_in, real* fmeans, real* fchols, real* carry_s, real* state_end,
+                   real* partials, void* ws_, size_t ws_bytes) {
   const LeafLaunch* ll;
   WsLayout wl;
   LeafArgs a;
   if (int rc = shard_setup(n_loc, d, q, chunk_len, qL_host, H, c, Jc, s0, s1, flags, ws_bytes, ll, wl, a)) return rc;
-  double* ws = (double*)ws_;
+  real* ws = (real*)ws_;
   if (int rc = zero_flags(s, wl, ws)) return rc;
   if (int rc = stage_b(s, ctx, flags, ll, a, wl, ws, state_in, state_in + wl.D, fmeans, fchols, true, 1.0, 0, nullptr))
     return rc;
-  POF_CK(cudaMemcpyAsync(carry_s, ws + wl.o_sagg + wl.tl.off[wl.tl.nlev - 1] * wl.SE, wl.SE * sizeof(double),
+  POF_CK(cudaMemcpyAsync(carry_s, ws + wl.o_sagg + wl.tl.off[wl.tl.nlev - 1] * wl.SE, wl.SE * sizeof(real),
                          cudaMemcpyDeviceToDevice, s));
-  POF_CK(cudaMemcpyAsync(state_end, ws + wl.o_send + (wl.CS - 1) * wl.ST, wl.ST * sizeof(double),
+  POF_CK(cudaMemcpyAsync(state_end, ws + wl.o_send + (wl.CS - 1) * wl.ST, wl.ST * sizeof(real),
                          cudaMemcpyDeviceToDevice, s));
-  POF_CK(cudaMemcpyAsync(partials, ws + wl.o_sums, 3 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  POF_CK(cudaMemcpyAsync(partials, ws + wl.o_sums, 3 * sizeof(real), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
-int pof_shard_stage_a_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
-                          int64_t chunk_len, const double* qL_host, const double* H, const double* c, double* carry_f,
+int POF_SUFFIX(pof_shard_stage_a)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const real* H, const real* c, real* carry_f,
                           void* ws_, size_t ws_bytes) {
   return shard_a((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, carry_f, ws_,
                  ws_bytes);
 }
-int pof_shard_stage_a_compact_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
-                                  int64_t chunk_len, const double* qL_host, const double* Jc, double scale0,
-                                  double scale1, double* carry_f, void* ws_, size_t ws_bytes) {
+int POF_SUFFIX(pof_shard_stage_a_compact)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host, const real* Jc, double scale0,
+                                  double scale1, real* carry_f, void* ws_, size_t ws_bytes) {
   return shard_a((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1,
                  carry_f, ws_, ws_bytes);
 }
-int pof_shard_stage_b_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
-                          int64_t chunk_len, const double* qL_host, const double* H, const double* c,
-                          const double* state_in, double* fmeans, double* fchols, double* carry_s, double* state_end,
-                          double* partials, void* ws_, size_t ws_bytes) {
+int POF_SUFFIX(pof_shard_stage_b)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const real* H, const real* c,
+                          const real* state_in, real* fmeans, real* fchols, real* carry_s, real* state_end,
+                          real* partials, void* ws_, size_t ws_bytes) {
   return shard_b((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, H, c, nullptr, 0.0, 0.0, state_in,
                  fmeans, fchols, carry_s, state_end, partials, ws_, ws_bytes);
 }
-int pof_shard_stage_b_compact_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
-                                  int64_t chunk_len, const double* qL_host, const double* Jc, double scale0,
-                                  double scale1, const double* state_in, double* fmeans, double* fchols,
-                                  double* carry_s, double* state_end, double* partials, void* ws_, size_t ws_bytes) {
+int POF_SUFFIX(pof_shard_stage_b_compact)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                                  int64_t chunk_len, const double* qL_host, const real* Jc, double scale0,
+                                  double scale1, const real* state_in, real* fmeans, real* fchols,
+                                  real* carry_s, real* state_end, real* partials, void* ws_, size_t ws_bytes) {
   return shard_b((cudaStream_t)s_, ctx, flags, n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, Jc, scale0, scale1,
                  state_in, fmeans, fchols, carry_s, state_end, partials, ws_, ws_bytes);
 }
 
-int pof_shard_stage_c_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
-                          int64_t chunk_len, const double* qL_host, const double* seed, int is_last_rank, int has_row0,
-                          const double* cscale, double* means, double* chols, double* partials2, void* ws_,
+int POF_SUFFIX(pof_shard_stage_c)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
+                          int64_t chunk_len, const double* qL_host, const real* seed, int is_last_rank, int has_row0,
+                          const real* cscale, real* means, real* chols, real* partials2, void* ws_,
                           size_t ws_bytes) {
   cudaStream_t s = (cudaStream_t)s_;
   (void)is_last_rank;
@@ -1041,25 +1064,28 @@ int pof_shard_stage_c_f64(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int64
   if (int rc = shard_setup(n_loc, d, q, chunk_len, qL_host, nullptr, nullptr, nullptr, 0.0, 0.0, flags, ws_bytes, ll,
                            wl, a))
     return rc;
-  double* ws = (double*)ws_;
+  real* ws = (real*)ws_;
   if (int rc = zero_flags(s, wl, ws)) return rc;
   // local row of state t' is t' - (1 - has_row0): shift the base pointers so that the kernels can index by t'
   const long shift = has_row0 ? 0 : 1;
-  double* mb = means - shift * wl.D;
-  double* cb = chols ? chols - shift * (long)wl.D * wl.D : nullptr;
+  real* mb = means - shift * wl.D;
+  real* cb = chols ? chols - shift * (long)wl.D * wl.D : nullptr;
   if (int rc = stage_c(s, ctx, flags, ll, a, wl, ws, seed, seed + wl.D, has_row0, cscale, mb, cb, nullptr)) return rc;
-  POF_CK(cudaMemcpyAsync(partials2, ws + wl.o_sums + 8, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  POF_CK(cudaMemcpyAsync(partials2, ws + wl.o_sums + 8, 2 * sizeof(real), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
 // ---- fused rank-carry exchanges (register-resident family; else the caller uses the chain entry points below)
+#ifndef POF_F32
 int pof_shard_exchange_supported(int D, uint32_t flags) {
   return (!(flags & POF_F_FAMILY_TILE) && tree_launch(D) != nullptr) ? 1 : 0;
 }
-int pof_shard_exchange_filter_f64(pof_stream_t s, uint32_t flags, int D, int rank, int world, const double* gathered,
-                                  int64_t stride, const double* x0_mean, const double* x0_chol, double* state_in,
-                                  double* scratch) {
-  if (!pof_shard_exchange_supported(D, flags)) return POF_E_UNSUPPORTED_DQ;
+#endif  // !POF_F32
+
+int POF_SUFFIX(pof_shard_exchange_filter)(pof_stream_t s, uint32_t flags, int D, int rank, int world, const real* gathered,
+                                  int64_t stride, const real* x0_mean, const real* x0_chol, real* state_in,
+                                  real* scratch) {
+  if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) return POF_E_UNSUPPORTED_DQ;
   if (rank < 0 || rank >= world) return POF_E_ARG;
   ExchangeArgs A = {};
   A.rank = rank;
@@ -1072,10 +1098,10 @@ int pof_shard_exchange_filter_f64(pof_stream_t s, uint32_t flags, int D, int ran
   A.scratch = scratch;
   return (int)tree_launch(D)->fexchange((cudaStream_t)s, A);
 }
-int pof_shard_exchange_smooth_f64(pof_stream_t s, uint32_t flags, int D, int d, int rank, int world,
-                                  int64_t n_steps_total, int calibrate, const double* gathered, int64_t stride,
-                                  double* seed, double* scratch, double* cscale, double* scalars) {
-  if (!pof_shard_exchange_supported(D, flags)) return POF_E_UNSUPPORTED_DQ;
+int POF_SUFFIX(pof_shard_exchange_smooth)(pof_stream_t s, uint32_t flags, int D, int d, int rank, int world,
+                                  int64_t n_steps_total, int calibrate, const real* gathered, int64_t stride,
+                                  real* seed, real* scratch, real* cscale, real* scalars) {
+  if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) return POF_E_UNSUPPORTED_DQ;
   if (rank < 0 || rank >= world || !cscale) return POF_E_ARG;
   ExchangeArgs A = {};
   A.rank = rank;
@@ -1084,16 +1110,16 @@ int pof_shard_exchange_smooth_f64(pof_stream_t s, uint32_t flags, int D, int d, 
   A.stride = stride;
   A.state_out = seed;
   A.scratch = scratch;
-  A.n_obs = (double)n_steps_total;
-  A.d_obs = (double)d;
+  A.n_obs = (real)n_steps_total;
+  A.d_obs = (real)d;
   A.calibrate = calibrate;
   A.cscale = cscale;
   A.scalars = scalars;
   return (int)tree_launch(D)->sexchange((cudaStream_t)s, A);
 }
 // scalars[POF_S_OBJ], scalars[POF_S_NOT_CLOSE] <- sums over the ranks' (obj, not-close) pairs, in rank order
-__global__ void k_exchange_sums2(int world, const double* __restrict__ gathered, double* __restrict__ scalars) {
-  double a = 0.0, b = 0.0;
+static __global__ void k_exchange_sums2(int world, const real* __restrict__ gathered, real* __restrict__ scalars) {
+  real a = 0.0, b = 0.0;
   for (int r = 0; r < world; ++r) {
     a += gathered[2 * r];
     b += gathered[2 * r + 1];
@@ -1101,36 +1127,39 @@ __global__ void k_exchange_sums2(int world, const double* __restrict__ gathered,
   scalars[POF_S_OBJ] = a;
   scalars[POF_S_NOT_CLOSE] = b;
 }
-int pof_shard_exchange_scalars_f64(pof_stream_t s, int world, const double* gathered, double* scalars) {
+int POF_SUFFIX(pof_shard_exchange_scalars)(pof_stream_t s, int world, const real* gathered, real* scalars) {
   k_exchange_sums2<<<1, 1, 0, (cudaStream_t)s>>>(world, gathered, scalars);
   return (int)cudaGetLastError();
 }
 
-int pof_filter_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
-                               const double* elems, double* state_out, double* scratch) {
+#ifndef POF_F32
+int POF_SUFFIX(pof_filter_apply_chain)(pof_stream_t s, uint32_t flags, int D, int count, const real* state_in,
+                               const real* elems, real* state_out, real* scratch) {
   if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) {
     if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
     return (int)tile_fchain((cudaStream_t)s, D, count, state_in, elems, state_out, scratch);
   }
-  const int smem = coop_ws_doubles(D) * (int)sizeof(double);
+  const int smem = coop_ws_doubles(D) * (int)sizeof(real);
   POF_CK(ensure_smem(k_filter_chain, smem));
   k_filter_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
   return (int)cudaGetLastError();
 }
-int pof_smooth_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,
-                               const double* elems, double* state_out, double* scratch) {
+int POF_SUFFIX(pof_smooth_apply_chain)(pof_stream_t s, uint32_t flags, int D, int count, const real* state_in,
+                               const real* elems, real* state_out, real* scratch) {
   if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) {
     if (!tile_tree_supported(D)) return POF_E_UNSUPPORTED_DQ;
     return (int)tile_schain((cudaStream_t)s, D, count, state_in, elems, state_out, scratch);
   }
-  const int smem = coop_ws_doubles(D) * (int)sizeof(double);
+  const int smem = coop_ws_doubles(D) * (int)sizeof(real);
   POF_CK(ensure_smem(k_smooth_chain, smem));
   k_smooth_chain<<<1, 32, smem, (cudaStream_t)s>>>(D, count, state_in, elems, state_out, scratch);
   return (int)cudaGetLastError();
 }
 
-int pof_prior_init_f64(pof_stream_t s, int64_t N, int d, int q, const double* qL_host, const double* ts,
-                       const double* m0, double* means, double* chols) {
+#endif  // !POF_F32
+
+int POF_SUFFIX(pof_prior_init)(pof_stream_t s, int64_t N, int d, int q, const double* qL_host, const real* ts,
+                       const real* m0, real* means, real* chols) {
   if (N < 1 || d < 1 || q < 1 || q > 5) return POF_E_ARG;
   QLParam ql;
   for (int i = 0; i < 36; ++i) ql.v[i] = (i < (q + 1) * (q + 1)) ? qL_host[i] : 0.0;
@@ -1139,8 +1168,8 @@ int pof_prior_init_f64(pof_stream_t s, int64_t N, int d, int q, const double* qL
   return (int)cudaGetLastError();
 }
 
-int pof_project_f64(pof_stream_t s, int64_t N, int d, int q, double scale0, const double* mult_dev,
-                    const double* means, const double* chols, double* ymean, double* ychol) {
+int POF_SUFFIX(pof_project)(pof_stream_t s, int64_t N, int d, int q, double scale0, const real* mult_dev,
+                    const real* means, const real* chols, real* ymean, real* ychol) {
   const long total = (long)N * d * (d * (q + 1) + 1);
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -1,0 +1,3 @@
+// fp32 build of pof_api.cu (namespace pof32, C ABI entry points *_f32): see pof_real.cuh
+#define POF_F32 1
+#include "pof_api.cu"

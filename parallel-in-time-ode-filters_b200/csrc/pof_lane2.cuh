@@ -2,7 +2,7 @@
 // D-row matrix (row = lane + s*G, s = 0,1), G = pow2ceil(ceil(D/2)): D = 8 -> 4 lanes per chunk, 8 chunks per warp.
 //
 // Why two rows per lane (measured on B200 with the one-row kernels of pof_lane.cuh, profiles/r01_*): every
-// Householder pivot has to deliver its K+1 pivot-row entries to every lane, 2 crossbar wavefronts per double per warp
+// Householder pivot has to deliver its K+1 pivot-row entries to every lane, 2 crossbar wavefronts per real per warp
 // (shared memory or shuffle alike), while a lane with one row does only 2(K+1) FMAs with them -- the kernels sat at
 // ~35 % FP64-pipe utilisation with the shared-memory/shuffle crossbar 55-65 % busy and 8 warps per SM (255 registers)
 // leaving dependency ("wait") stalls exposed.  With two rows per lane the same broadcast feeds twice the FMAs, the two
@@ -17,9 +17,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pof_real.cuh"
 #include "pof_small.cuh"
 
-namespace pof {
+namespace POF_NS {
+// binomial coefficients of the Pascal blocks in the scalar type of this build
+__host__ __device__ constexpr real binomr(int n, int k) { return (real)pof::binom(n, k); }
 
 template <int d, int q>
 struct Lane2 {
@@ -40,7 +43,7 @@ struct Lane2 {
 #define POF_FOLD_MZ 4
 #endif
   static constexpr int MZ = (POF_FOLD_MZ * d <= D) ? POF_FOLD_MZ : (D / d);
-  static constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+  static constexpr real LOG_2PI = 1.8378770664093454835606594728112;
   // per-group shared memory (doubles): two row-exchange matrices, two gather vectors, this group's rows of QL
   static constexpr int LDM = D + 1;
   static constexpr int VEC = ((D + 1) / 2) * 2;
@@ -53,10 +56,10 @@ struct Lane2 {
   static constexpr int SM_GROUP = RAW + (((G % 16) - (RAW % 16)) + 16) % 16;
 
   struct Lin {
-    const double* __restrict__ H;
-    const double* __restrict__ c;
-    const double* __restrict__ Jc;
-    double s0, s1;
+    const real* __restrict__ H;
+    const real* __restrict__ c;
+    const real* __restrict__ Jc;
+    real s0, s1;
   };
 
   struct Ctx {
@@ -65,16 +68,16 @@ struct Lane2 {
     int rc[R];         // clamped row index for addressing
     int rb[R], blk0[R];
     unsigned mask;
-    double* mat;       // 2 exchange matrices
-    double* vec;       // 2 gather vectors
-    double* tq;        // this lane's rows of QL, lane-minor: tq[(s*D + j)*G] (conflict-free across the group)
-    double* lbuf;      // 2 x NJP doubles: compact linearisations staged by cp.async (global -> shared, no registers)
+    real* mat;       // 2 exchange matrices
+    real* vec;       // 2 gather vectors
+    real* tq;        // this lane's rows of QL, lane-minor: tq[(s*D + j)*G] (conflict-free across the group)
+    real* lbuf;      // 2 x NJP doubles: compact linearisations staged by cp.async (global -> shared, no registers)
     int vflip;
-    double cf[R][Q1];  // Pascal coefficients of the owned rows of F
+    real cf[R][Q1];  // Pascal coefficients of the owned rows of F
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
   };
 
-  static __device__ __forceinline__ void init_ctx(Ctx& c, double* sm_group, const double* qL) {
+  static __device__ __forceinline__ void init_ctx(Ctx& c, real* sm_group, const real* qL) {
     const int lane = threadIdx.x & 31;
     c.l = lane % G;
     c.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
@@ -91,15 +94,15 @@ struct Lane2 {
       c.blk0[s] = c.rc[s] - c.rb[s];
 #pragma unroll
       for (int i = 0; i < Q1; ++i) {
-        double v = 0.0;
+        real v = 0.0;
 #pragma unroll
         for (int b = 0; b < Q1; ++b)
-          if (c.rb[s] == b && i >= b) v = binom(q - b, i - b);
+          if (c.rb[s] == b && i >= b) v = binomr(q - b, i - b);
         c.cf[s][i] = v;
       }
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        double v = 0.0;
+        real v = 0.0;
 #pragma unroll
         for (int b = 0; b < Q1; ++b)
           if (c.rb[s] == b && (j / Q1) * Q1 == c.blk0[s] && (j % Q1) <= b) v = qL[b * Q1 + (j % Q1)];
@@ -110,36 +113,21 @@ struct Lane2 {
   }
 
   // ---------------------------------------------------------------------------------------------- small helpers
-  static __device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-  }
-  static __device__ __forceinline__ double fast_rsqrt(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double hx = 0.5 * x;
-    double e = fma(-hx * r, r, 0.5);
-    r = fma(r, e, r);
-    e = fma(-hx * r, r, 0.5);
-    return fma(r, e, r);
-  }
+  static __device__ __forceinline__ real fast_rcp(real x) { return POF_NS::fast_rcp(x); }
+  static __device__ __forceinline__ real fast_rsqrt(real x) { return POF_NS::fast_rsqrt(x); }
   // sum_j a[j]*b[j] with several independent accumulators: the leaf recursions are bound by dependent-issue latency
   // ("wait" stalls with 2 warps per scheduler), so every long FMA chain is split and tree-added
   template <int n>
-  static __device__ __forceinline__ double dotn(const double* a, const double* b) {
+  static __device__ __forceinline__ real dotn(const real* a, const real* b) {
     if constexpr (n <= 0) {
       return 0.0;
     } else if constexpr (n < 4) {
-      double s = a[0] * b[0];
+      real s = a[0] * b[0];
 #pragma unroll
       for (int j = 1; j < n; ++j) s = fma(a[j], b[j], s);
       return s;
     } else if constexpr (n < 10) {
-      double s0 = a[0] * b[0], s1 = a[1] * b[1];
+      real s0 = a[0] * b[0], s1 = a[1] * b[1];
 #pragma unroll
       for (int j = 2; j + 1 < n; j += 2) {
         s0 = fma(a[j], b[j], s0);
@@ -148,7 +136,7 @@ struct Lane2 {
       if constexpr (n % 2) s0 = fma(a[n - 1], b[n - 1], s0);
       return s0 + s1;
     } else {
-      double s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
+      real s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
 #pragma unroll
       for (int j = 4; j + 3 < n; j += 4) {
         s0 = fma(a[j], b[j], s0);
@@ -163,20 +151,20 @@ struct Lane2 {
     }
   }
   struct HH {
-    double s, tp, beta;
+    real s, tp, beta;
   };
   // Householder for the row (alpha, x[0..n)):  H = I - tp v v^T, v = (s, x), H (alpha, x)^T = (beta, 0)
   template <int n>
-  static __device__ __forceinline__ HH house(double alpha, const double* x) {
-    const double sigma = dotn<n>(x, x);
-    const double nrm2 = fma(alpha, alpha, sigma);
+  static __device__ __forceinline__ HH house(real alpha, const real* x) {
+    const real sigma = dotn<n>(x, x);
+    const real nrm2 = fma(alpha, alpha, sigma);
     // rsqrt.approx.ftz flushes subnormal inputs to zero (-> inf -> NaN in the Newton step): a row whose squared norm
     // is below 2^-1000 is treated as already reduced (identity reflector), as a zero tail is
-    const bool nz = sigma > 0.0 && nrm2 > 0x1p-1000;
-    const double rn = fast_rsqrt(nrm2);
-    const double nrm = nrm2 * rn;
-    const double beta = (alpha >= 0.0) ? -nrm : nrm;
-    const double s = alpha - beta;
+    const bool nz = sigma > real(0) && nrm2 > tiny_norm2();
+    const real rn = fast_rsqrt(nrm2);
+    const real nrm = nrm2 * rn;
+    const real beta = (alpha >= 0.0) ? -nrm : nrm;
+    const real s = alpha - beta;
     HH h;
     h.beta = nz ? beta : alpha;
     h.s = nz ? s : 0.0;
@@ -186,12 +174,12 @@ struct Lane2 {
   static __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
   }
-  static __device__ __forceinline__ double bshfl(const Ctx& c, double x, int src) {
+  static __device__ __forceinline__ real bshfl(const Ctx& c, real x, int src) {
     return __shfl_sync(c.mask, x, ((threadIdx.x & 31) / G) * G + src);
   }
   // out[row] = x[s] of the lane owning `row`
-  static __device__ __forceinline__ void gather(Ctx& c, const double (&x)[R], double (&out)[D]) {
-    double* v = c.vec + c.vflip * VEC;
+  static __device__ __forceinline__ void gather(Ctx& c, const real (&x)[R], real (&out)[D]) {
+    real* v = c.vec + c.vflip * VEC;
     c.vflip ^= 1;
 #pragma unroll
     for (int s = 0; s < R; ++s)
@@ -202,8 +190,8 @@ struct Lane2 {
   }
   // publish the owned rows (columns [J0, D)) into exchange matrix `which`
   template <int J0>
-  static __device__ __forceinline__ const double* publish(Ctx& c, int which, const double (&x)[R][D]) {
-    double* M = c.mat + which * D * LDM;
+  static __device__ __forceinline__ const real* publish(Ctx& c, int which, const real (&x)[R][D]) {
+    real* M = c.mat + which * D * LDM;
     c.sync();
 #pragma unroll
     for (int s = 0; s < R; ++s)
@@ -216,37 +204,37 @@ struct Lane2 {
   }
   // y[s][j] = (F X)[row_s][j], j in [J0, D), from the published rows of X
   template <int J0>
-  static __device__ __forceinline__ void mulF_rows(const Ctx& c, const double* M, double (&y)[R][D]) {
+  static __device__ __forceinline__ void mulF_rows(const Ctx& c, const real* M, real (&y)[R][D]) {
 #pragma unroll
     for (int s = 0; s < R; ++s) {
 #pragma unroll
       for (int j = J0; j < D; ++j) y[s][j] = 0.0;
 #pragma unroll
       for (int i = 0; i < Q1; ++i) {
-        const double* rowp = M + (c.blk0[s] + i) * LDM;
+        const real* rowp = M + (c.blk0[s] + i) * LDM;
 #pragma unroll
         for (int j = J0; j < D; ++j) y[s][j] = fma(c.cf[s][i], rowp[j], y[s][j]);
       }
     }
   }
-  static __device__ __forceinline__ void mulF_vec(double (&m)[D]) {
+  static __device__ __forceinline__ void mulF_vec(real (&m)[D]) {
 #pragma unroll
     for (int b = 0; b < d; ++b) {
 #pragma unroll
       for (int i = 0; i < Q1; ++i) {
 #pragma unroll
-        for (int j = i + 1; j < Q1; ++j) m[b * Q1 + i] = fma(binom(q - i, j - i), m[b * Q1 + j], m[b * Q1 + i]);
+        for (int j = i + 1; j < Q1; ++j) m[b * Q1 + i] = fma(binomr(q - i, j - i), m[b * Q1 + j], m[b * Q1 + i]);
       }
     }
   }
-  static __device__ __forceinline__ double pick(const double (&x)[D], int idx) {
-    double v = 0.0;
+  static __device__ __forceinline__ real pick(const real (&x)[D], int idx) {
+    real v = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i)
       if (i == idx) v = x[i];
     return v;
   }
-  static __device__ __forceinline__ void load_tq(const Ctx& c, double (&t)[R][D]) {
+  static __device__ __forceinline__ void load_tq(const Ctx& c, real (&t)[R][D]) {
 #pragma unroll
     for (int s = 0; s < R; ++s) {
 #pragma unroll
@@ -260,13 +248,13 @@ struct Lane2 {
   // (the per-slot update is a template on the slot so that slots lying entirely above the pivot vanish at compile
   // time)
   template <int I, int J0, bool PASS>
-  static __device__ __forceinline__ void tp_step2(Ctx& cx, double (&t)[R][D], double (&c)[R][D], double (*pt)[D],
-                                                  double (*pc)[D]) {
+  static __device__ __forceinline__ void tp_step2(Ctx& cx, real (&t)[R][D], real (&c)[R][D], real (*pt)[D],
+                                                  real (*pc)[D]) {
     if constexpr (I < D) {
       constexpr int K = D - J0;
       constexpr int so = I / G;
       const int lo = I % G;
-      double piv[K + 1];
+      real piv[K + 1];
       piv[0] = bshfl(cx, t[so][I], lo);
 #pragma unroll
       for (int j = 0; j < K; ++j) piv[1 + j] = bshfl(cx, c[so][J0 + j], lo);
@@ -276,7 +264,7 @@ struct Lane2 {
       if constexpr (PASS) {
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-          double u = fma(h.s, pt[s][I], dotn<K>(&pc[s][J0], piv + 1));
+          real u = fma(h.s, pt[s][I], dotn<K>(&pc[s][J0], piv + 1));
           u *= h.tp;
           pt[s][I] = fma(-u, h.s, pt[s][I]);
 #pragma unroll
@@ -287,10 +275,10 @@ struct Lane2 {
     }
   }
   template <int S, int I, int J0, int K>
-  static __device__ __forceinline__ void row_update(const Ctx& cx, const HH& h, const double* piv, double (&t)[R][D],
-                                                    double (&c)[R][D]) {
+  static __device__ __forceinline__ void row_update(const Ctx& cx, const HH& h, const real* piv, real (&t)[R][D],
+                                                    real (&c)[R][D]) {
     if constexpr (S * G + G - 1 >= I) {  // some row of this slot is at or below the pivot
-      double w = fma(h.s, t[S][I], dotn<K>(&c[S][J0], piv + 1));  // the dot does not wait for the reflector
+      real w = fma(h.s, t[S][I], dotn<K>(&c[S][J0], piv + 1));  // the dot does not wait for the reflector
       w = (cx.row[S] >= I) ? w * h.tp : 0.0;
       t[S][I] = (cx.row[S] == I) ? h.beta : fma(-w, h.s, t[S][I]);
 #pragma unroll
@@ -298,19 +286,19 @@ struct Lane2 {
     }
   }
   template <int J0, bool PASS>
-  static __device__ __forceinline__ void tpqrt(Ctx& cx, double (&t)[R][D], double (&c)[R][D], double (*pt)[D],
-                                               double (*pc)[D]) {
+  static __device__ __forceinline__ void tpqrt(Ctx& cx, real (&t)[R][D], real (&c)[R][D], real (*pt)[D],
+                                               real (*pc)[D]) {
     tp_step2<0, J0, PASS>(cx, t, c, pt, pc);
   }
 
   // plain right-Householder lower-triangularisation of the D x (D - J0) matrix held in columns [J0, D) of x; the
   // result is written as a lower-triangular D x D factor into columns [0, D - J0) (pivot I uses column J0 + I)
   template <int S, int I, int J0>
-  static __device__ __forceinline__ void tria_update(const Ctx& cx, const HH& h, const double* piv,
-                                                     double (&x)[R][D]) {
+  static __device__ __forceinline__ void tria_update(const Ctx& cx, const HH& h, const real* piv,
+                                                     real (&x)[R][D]) {
     if constexpr (S * G + G - 1 >= I) {
       constexpr int n = D - J0 - I;
-      double w = fma(h.s, x[S][J0 + I], dotn<n - 1>(&x[S][J0 + I + 1], piv + 1));
+      real w = fma(h.s, x[S][J0 + I], dotn<n - 1>(&x[S][J0 + I + 1], piv + 1));
       w = (cx.row[S] >= I) ? w * h.tp : 0.0;
       x[S][J0 + I] = (cx.row[S] == I) ? h.beta : fma(-w, h.s, x[S][J0 + I]);
 #pragma unroll
@@ -318,12 +306,12 @@ struct Lane2 {
     }
   }
   template <int I, int J0>
-  static __device__ __forceinline__ void tria_step(Ctx& cx, double (&x)[R][D]) {
+  static __device__ __forceinline__ void tria_step(Ctx& cx, real (&x)[R][D]) {
     if constexpr (I + 1 < D - J0) {
       constexpr int n = D - J0 - I;
       constexpr int so = I / G;
       const int lo = I % G;
-      double piv[n];
+      real piv[n];
 #pragma unroll
       for (int j = 0; j < n; ++j) piv[j] = bshfl(cx, x[so][J0 + I + j], lo);
       const HH h = house<n - 1>(piv[0], piv + 1);
@@ -334,7 +322,7 @@ struct Lane2 {
   }
   // x (columns [J0, D)) -> lower-triangular factor in out (columns [0, D)), zero above the diagonal / beyond D-J0
   template <int J0>
-  static __device__ __forceinline__ void tria_rows(Ctx& cx, double (&x)[R][D], double (&out)[R][D]) {
+  static __device__ __forceinline__ void tria_rows(Ctx& cx, real (&x)[R][D], real (&out)[R][D]) {
     tria_step<0, J0>(cx, x);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -347,11 +335,11 @@ struct Lane2 {
   // result is left in x.  (Smoother: x = E L_{k+1}, y = the UNtriangularised Phi22~ block of the step's joint QR --
   // only y y^T matters, so the filter scan does not triangularise it.)
   template <int S, int I, int JS>
-  static __device__ __forceinline__ void tria2_update(const Ctx& cx, const HH& h, const double* piv, double (&x)[R][D],
-                                                      double (&y)[R][D]) {
+  static __device__ __forceinline__ void tria2_update(const Ctx& cx, const HH& h, const real* piv, real (&x)[R][D],
+                                                      real (&y)[R][D]) {
     if constexpr (S * G + G - 1 >= I) {
       constexpr int n1 = D - I, n2 = D - JS;
-      double w = fma(h.s, x[S][I], dotn<n1 - 1>(&x[S][I + 1], piv + 1) + dotn<n2>(&y[S][JS], piv + n1));
+      real w = fma(h.s, x[S][I], dotn<n1 - 1>(&x[S][I + 1], piv + 1) + dotn<n2>(&y[S][JS], piv + n1));
       w = (cx.row[S] >= I) ? w * h.tp : 0.0;
       x[S][I] = (cx.row[S] == I) ? h.beta : fma(-w, h.s, x[S][I]);
 #pragma unroll
@@ -361,12 +349,12 @@ struct Lane2 {
     }
   }
   template <int I, int JS>
-  static __device__ __forceinline__ void tria2_step(Ctx& cx, double (&x)[R][D], double (&y)[R][D]) {
+  static __device__ __forceinline__ void tria2_step(Ctx& cx, real (&x)[R][D], real (&y)[R][D]) {
     if constexpr (I < D) {
       constexpr int n1 = D - I, n2 = D - JS;
       constexpr int so = I / G;
       const int lo = I % G;
-      double piv[n1 + n2];
+      real piv[n1 + n2];
 #pragma unroll
       for (int j = 0; j < n1; ++j) piv[j] = bshfl(cx, x[so][I + j], lo);
 #pragma unroll
@@ -380,12 +368,12 @@ struct Lane2 {
 
   // ---------------------------------------------------------------------------------------------- linearisation access
   struct LinK {  // one step's linearisation, compact or dense
-    double J[d][d], c[d];
-    const double* Hd;  // dense H of this step, or null
+    real J[d][d], c[d];
+    const real* Hd;  // dense H of this step, or null
   };
   static __device__ __forceinline__ void load_lin(const Lin& L, long k, LinK& o) {
     if (L.Jc) {
-      const double* p = L.Jc + k * (d * d + d);
+      const real* p = L.Jc + k * (d * d + d);
 #pragma unroll
       for (int a = 0; a < d; ++a) {
         o.c[a] = __ldg(p + d * d + a);
@@ -407,7 +395,7 @@ struct Lane2 {
   // prediction QR it was spilled right after the load, which exposed the full DRAM latency -- ncu: STL on long_sb)
   static __device__ __forceinline__ void prefetch_lin(const Lin& L, long k) {
     if (L.Jc) {
-      const double* p = L.Jc + k * (d * d + d);
+      const real* p = L.Jc + k * (d * d + d);
       prefetch_l2(p);
       prefetch_l2(p + (d * d + d) - 1);
     } else {
@@ -422,17 +410,20 @@ struct Lane2 {
   static constexpr int CPD = (G >= 2 && NJ % 2 == 0) ? 2 : 1;  // doubles per copy (16-byte copies need alignment)
   static __device__ __forceinline__ void stage_lin(const Ctx& cx, const Lin& L, long k, bool valid) {
     if (L.Jc && valid) {
-      const double* src = L.Jc + k * NJ;
-      double* dst = cx.lbuf + (k & 1) * NJP;
+      const real* src = L.Jc + k * NJ;
+      real* dst = cx.lbuf + (k & 1) * NJP;
 #pragma unroll
       for (int i0 = 0; i0 < NJ / CPD; i0 += G) {
         const int i = i0 + cx.l;
         if (i < NJ / CPD) {
           const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i * CPD);
-          if constexpr (CPD == 2)
+          constexpr int BYTES = CPD * (int)sizeof(real);
+          if constexpr (BYTES == 16)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + i * CPD) : "memory");
-          else
+          else if constexpr (BYTES == 8)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + i * CPD) : "memory");
+          else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(src + i * CPD) : "memory");
         }
       }
     }
@@ -443,7 +434,7 @@ struct Lane2 {
     if (L.Jc) {
       asm volatile("cp.async.wait_group 1;" ::: "memory");
       cx.sync();
-      const double* p = cx.lbuf + (k & 1) * NJP;
+      const real* p = cx.lbuf + (k & 1) * NJP;
 #pragma unroll
       for (int a = 0; a < d; ++a) {
         o.c[a] = p[d * d + a];
@@ -456,12 +447,12 @@ struct Lane2 {
     }
   }
   // (H X)[a][col] for a column `col` of a published D-row matrix M
-  static __device__ __forceinline__ void H_times_col(const Lin& L, const LinK& lk, const double* M, int col,
-                                                     double (&out)[d]) {
+  static __device__ __forceinline__ void H_times_col(const Lin& L, const LinK& lk, const real* M, int col,
+                                                     real (&out)[d]) {
     if (lk.Hd == nullptr) {
 #pragma unroll
       for (int a = 0; a < d; ++a) {
-        double s = L.s1 * M[(a * Q1 + 1) * LDM + col];
+        real s = L.s1 * M[(a * Q1 + 1) * LDM + col];
 #pragma unroll
         for (int b = 0; b < d; ++b) s = fma(-L.s0 * lk.J[a][b], M[(b * Q1) * LDM + col], s);
         out[a] = s;
@@ -471,19 +462,19 @@ struct Lane2 {
       for (int a = 0; a < d; ++a) out[a] = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const double v = M[i * LDM + col];
+        const real v = M[i * LDM + col];
 #pragma unroll
         for (int a = 0; a < d; ++a) out[a] = fma(__ldg(lk.Hd + a * D + i), v, out[a]);
       }
     }
   }
   // H v + c for a replicated vector v
-  static __device__ __forceinline__ void H_times_vec(const Lin& L, const LinK& lk, const double (&v)[D],
-                                                     double (&out)[d]) {
+  static __device__ __forceinline__ void H_times_vec(const Lin& L, const LinK& lk, const real (&v)[D],
+                                                     real (&out)[d]) {
     if (lk.Hd == nullptr) {
 #pragma unroll
       for (int a = 0; a < d; ++a) {
-        double s = fma(L.s1, v[a * Q1 + 1], lk.c[a]);
+        real s = fma(L.s1, v[a * Q1 + 1], lk.c[a]);
 #pragma unroll
         for (int b = 0; b < d; ++b) s = fma(-L.s0 * lk.J[a][b], v[b * Q1], s);
         out[a] = s;
@@ -491,7 +482,7 @@ struct Lane2 {
     } else {
 #pragma unroll
       for (int a = 0; a < d; ++a) {
-        double s = lk.c[a];
+        real s = lk.c[a];
 #pragma unroll
         for (int i = 0; i < D; ++i) s = fma(__ldg(lk.Hd + a * D + i), v[i], s);
         out[a] = s;
@@ -501,12 +492,12 @@ struct Lane2 {
 
   // ---------------------------------------------------------------------------------------------- measurement update
   template <int A>
-  static __device__ __forceinline__ void update_pivot(double (&t)[R][D], double (&W)[d][D]) {
+  static __device__ __forceinline__ void update_pivot(real (&t)[R][D], real (&W)[d][D]) {
     if constexpr (A < d) {
       const HH h = house<D - A - 1>(W[A][A], &W[A][A + 1]);
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        double w = fma(h.s, t[s][A], dotn<D - A - 1>(&t[s][A + 1], &W[A][A + 1]));
+        real w = fma(h.s, t[s][A], dotn<D - A - 1>(&t[s][A + 1], &W[A][A + 1]));
         w *= h.tp;
         t[s][A] = fma(-w, h.s, t[s][A]);
 #pragma unroll
@@ -514,7 +505,7 @@ struct Lane2 {
       }
 #pragma unroll
       for (int a2 = A + 1; a2 < d; ++a2) {
-        double u = fma(h.s, W[a2][A], dotn<D - A - 1>(&W[a2][A + 1], &W[A][A + 1]));
+        real u = fma(h.s, W[a2][A], dotn<D - A - 1>(&W[a2][A + 1], &W[A][A + 1]));
         u *= h.tp;
         W[a2][A] = fma(-u, h.s, W[a2][A]);
 #pragma unroll
@@ -526,17 +517,17 @@ struct Lane2 {
   }
   // In: t = rows of the predicted factor T (lower triangular, zeros above the diagonal).  Out: SLinv-ready SL, and
   // t = [Kbar | posterior factor] rows.  M: T must have been published into exchange matrix 0 by the caller.
-  static __device__ __forceinline__ void update(Ctx& cx, const Lin& L, const LinK& lk, const double* MT,
-                                                double (&t)[R][D], double (&SL)[d][d]) {
-    double wc[d][R];
+  static __device__ __forceinline__ void update(Ctx& cx, const Lin& L, const LinK& lk, const real* MT,
+                                                real (&t)[R][D], real (&SL)[d][d]) {
+    real wc[d][R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      double o[d];
+      real o[d];
       H_times_col(L, lk, MT, cx.rc[s], o);
 #pragma unroll
       for (int a = 0; a < d; ++a) wc[a][s] = o[a];
     }
-    double W[d][D];
+    real W[d][D];
 #pragma unroll
     for (int a = 0; a < d; ++a) gather(cx, wc[a], W[a]);
     update_pivot<0>(t, W);
@@ -546,10 +537,10 @@ struct Lane2 {
       for (int e = 0; e < d; ++e) SL[a][e] = (e <= a) ? W[a][e] : 0.0;
     }
   }
-  static __device__ __forceinline__ void solveSL(const double (&SL)[d][d], const double (&y)[d], double (&z)[d]) {
+  static __device__ __forceinline__ void solveSL(const real (&SL)[d][d], const real (&y)[d], real (&z)[d]) {
 #pragma unroll
     for (int a = 0; a < d; ++a) {
-      double s = y[a];
+      real s = y[a];
 #pragma unroll
       for (int j = 0; j < a; ++j) s = fma(-SL[a][j], z[j], s);
       z[a] = s * fast_rcp(SL[a][a]);
@@ -559,20 +550,20 @@ struct Lane2 {
   // ================================================================== filter phase 1: chunk -> filtering element
   template <bool FIRST>
   static __device__ __forceinline__ void fold_step(Ctx& cx, const Lin& lin, long k, bool emit_pre,
-                                                   double (&a)[R][D], double (&b)[R], double (&uf)[R][D],
-                                                   double (&eta)[R], double (&z)[R][D], double (&gt)[R][D], int slot,
-                                                   double* __restrict__ aggm, bool has_next) {
+                                                   real (&a)[R][D], real (&b)[R], real (&uf)[R][D],
+                                                   real (&eta)[R], real (&z)[R][D], real (&gt)[R][D], int slot,
+                                                   real* __restrict__ aggm, bool has_next) {
     stage_lin(cx, lin, k + 1, has_next);
     // ---- predict: A <- F A, b <- F b, T = tria([F Uf, QL])
-    double t[R][D];
+    real t[R][D];
     {
-      const double* M = publish<0>(cx, 0, a);
+      const real* M = publish<0>(cx, 0, a);
       mulF_rows<0>(cx, M, a);
-      double bv[D];
+      real bv[D];
       gather(cx, b, bv);
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        double acc = 0.0;
+        real acc = 0.0;
 #pragma unroll
         for (int i = 0; i < Q1; ++i) acc = fma(cx.cf[s][i], pick(bv, cx.blk0[s] + i), acc);
         b[s] = acc;
@@ -580,8 +571,8 @@ struct Lane2 {
     }
     load_tq(cx, t);
     if constexpr (!FIRST) {
-      double cc[R][D];
-      const double* M2 = publish<d>(cx, 1, uf);
+      real cc[R][D];
+      const real* M2 = publish<d>(cx, 1, uf);
       mulF_rows<d>(cx, M2, cc);
       tpqrt<d, false>(cx, t, cc, nullptr, nullptr);
     }
@@ -602,34 +593,34 @@ struct Lane2 {
         }
     }
     // ---- update
-    double SL[d][d];
+    real SL[d][d];
     LinK lk;
     fetch_lin(cx, lin, k, lk);
-    const double* MT = publish<0>(cx, 1, t);
+    const real* MT = publish<0>(cx, 1, t);
     update(cx, lin, lk, MT, t, SL);
     // ---- G = SL^{-1} (H A) (columns over the owned rows' indices), zz = SL^{-1}(H b + c)
-    double bv[D];
+    real bv[D];
     gather(cx, b, bv);
-    const double* MA = publish<0>(cx, 0, a);
-    double g[d][R], rv[d], zz[d];
+    const real* MA = publish<0>(cx, 0, a);
+    real g[d][R], rv[d], zz[d];
     H_times_vec(lin, lk, bv, rv);
     solveSL(SL, rv, zz);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      double o[d], gg[d];
+      real o[d], gg[d];
       H_times_col(lin, lk, MA, cx.rc[s], o);
       solveSL(SL, o, gg);
 #pragma unroll
       for (int e = 0; e < d; ++e) g[e][s] = gg[e];
     }
-    double Gf[d][D];
+    real Gf[d][D];
 #pragma unroll
     for (int e = 0; e < d; ++e) gather(cx, g[e], Gf[e]);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
 #pragma unroll
       for (int e = 0; e < d; ++e) {
-        const double kb = t[s][e];
+        const real kb = t[s][e];
         b[s] = fma(-kb, zz[e], b[s]);
         eta[s] = fma(-g[e][s], zz[e], eta[s]);
 #pragma unroll
@@ -649,7 +640,7 @@ struct Lane2 {
     }
   }
   // Z <- tria([Z | pending columns]); pending <- 0
-  static __device__ __forceinline__ void flush_z(Ctx& cx, double (&z)[R][D], double (&gt)[R][D]) {
+  static __device__ __forceinline__ void flush_z(Ctx& cx, real (&z)[R][D], real (&gt)[R][D]) {
     tpqrt<D - MZ * d, false>(cx, z, gt, nullptr, nullptr);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -658,9 +649,9 @@ struct Lane2 {
     }
   }
 
-  static __device__ __forceinline__ void fold(Ctx& cx, long k0, long k1, const Lin& lin, double* __restrict__ agg,
-                                              double* __restrict__ aggm) {
-    double a[R][D], uf[R][D], z[R][D], b[R], eta[R];
+  static __device__ __forceinline__ void fold(Ctx& cx, long k0, long k1, const Lin& lin, real* __restrict__ agg,
+                                              real* __restrict__ aggm) {
+    real a[R][D], uf[R][D], z[R][D], b[R], eta[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       b[s] = 0.0;
@@ -672,7 +663,7 @@ struct Lane2 {
         z[s][j] = 0.0;
       }
     }
-    double gt[R][D];
+    real gt[R][D];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
 #pragma unroll
@@ -709,29 +700,29 @@ struct Lane2 {
   }
 
   // ================================================================== filter phase 3: seeded square-root KF
-  static __device__ __forceinline__ void store_row(double* __restrict__ p, const double (&x)[D]) {
+  static __device__ __forceinline__ void store_row(real* __restrict__ p, const real (&x)[D]) {
     if constexpr (D % 2 == 0) {
-      double2* p2 = reinterpret_cast<double2*>(p);
+      real2* p2 = reinterpret_cast<real2*>(p);
 #pragma unroll
-      for (int j = 0; j < D / 2; ++j) p2[j] = make_double2(x[2 * j], x[2 * j + 1]);
+      for (int j = 0; j < D / 2; ++j) p2[j] = make_real2(x[2 * j], x[2 * j + 1]);
     } else {
 #pragma unroll
       for (int j = 0; j < D; ++j) p[j] = x[j];
     }
   }
   struct Stats {
-    double nll, s1, s2;
+    real nll, s1, s2;
   };
   // J0 = first non-zero column of the incoming factor (0 for a chunk's first step, d afterwards)
   template <int J0>
-  static __device__ __forceinline__ void scan_step(Ctx& cx, const Lin& lin, long k, double (&m)[R], double (&uf)[R][D],
-                                                   double* __restrict__ kern, Stats& st, double* __restrict__ fmeans,
-                                                   double* __restrict__ fchols, bool has_next) {
+  static __device__ __forceinline__ void scan_step(Ctx& cx, const Lin& lin, long k, real (&m)[R], real (&uf)[R][D],
+                                                   real* __restrict__ kern, Stats& st, real* __restrict__ fmeans,
+                                                   real* __restrict__ fchols, bool has_next) {
     stage_lin(cx, lin, k + 1, has_next);
     // ---- predict + backward kernel: [[F Uf, QL],[Uf, 0]] -> [[T, 0],[Phi21, Phi22~]]
-    double t[R][D], cc[R][D], e[R][D];
+    real t[R][D], cc[R][D], e[R][D];
     {
-      const double* M = publish<J0>(cx, 0, uf);
+      const real* M = publish<J0>(cx, 0, uf);
       mulF_rows<J0>(cx, M, cc);
     }
     load_tq(cx, t);
@@ -742,20 +733,20 @@ struct Lane2 {
     }
     tpqrt<J0, true>(cx, t, cc, e, uf);
     // ---- E rows: e <- e T^{-1}
-    const double* MT = publish<0>(cx, 1, t);
+    const real* MT = publish<0>(cx, 1, t);
     {
-      double dinv[R], inv[D];
+      real dinv[R], inv[D];
 #pragma unroll
       for (int s = 0; s < R; ++s) dinv[s] = fast_rcp(pick(t[s], cx.rc[s]));
       gather(cx, dinv, inv);
 #pragma unroll
       for (int j = D - 1; j >= 0; --j) {
-        double acc[R];
+        real acc[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) acc[s] = e[s][j];
 #pragma unroll
         for (int i = j + 1; i < D; ++i) {
-          const double tv = MT[i * LDM + j];
+          const real tv = MT[i * LDM + j];
 #pragma unroll
           for (int s = 0; s < R; ++s) acc[s] = fma(-e[s][i], tv, acc[s]);
         }
@@ -764,12 +755,12 @@ struct Lane2 {
       }
     }
     // ---- means: mp = F m ; g = m - E mp
-    double mv[D], g[R];
+    real mv[D], g[R];
     gather(cx, m, mv);
     mulF_vec(mv);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      double acc = m[s];
+      real acc = m[s];
 #pragma unroll
       for (int i = 0; i < D; ++i) acc = fma(-e[s][i], mv[i], acc);
       g[s] = acc;
@@ -777,7 +768,7 @@ struct Lane2 {
     // ---- store the step's backward kernel (g | E | Phi22~): the noise factor stays UNtriangularised -- the smoother
     // only needs Phi22~ Phi22~^T and triangularises [E L | Phi22~] in one go (D - J0 - 1 pivots less per step here)
     {
-      double* kp = kern + k * NE;
+      real* kp = kern + k * NE;
 #pragma unroll
       for (int s = 0; s < R; ++s)
         if (cx.row[s] < D) kp[cx.row[s]] = g[s];
@@ -785,7 +776,7 @@ struct Lane2 {
       store_rows_pm<(J0 / PW) * PW>(cx, kp + D + D * D, uf);
     }
     // ---- measurement update
-    double SL[d][d], y[d], zz[d];
+    real SL[d][d], y[d], zz[d];
     LinK lk;
     fetch_lin(cx, lin, k, lk);
     update(cx, lin, lk, MT, t, SL);
@@ -793,7 +784,7 @@ struct Lane2 {
     solveSL(SL, y, zz);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      double acc = pick(mv, cx.rc[s]);
+      real acc = pick(mv, cx.rc[s]);
 #pragma unroll
       for (int a = 0; a < d; ++a) acc = fma(-t[s][a], zz[a], acc);
       m[s] = acc;
@@ -801,7 +792,7 @@ struct Lane2 {
       for (int j = 0; j < D; ++j) uf[s][j] = (j < d) ? 0.0 : t[s][j];
     }
     // ---- innovation statistics (replicated)
-    double q2 = 0.0, lg = 0.0;
+    real q2 = 0.0, lg = 0.0;
 #pragma unroll
     for (int a = 0; a < d; ++a) {
       q2 = fma(zz[a], zz[a], q2);
@@ -809,10 +800,10 @@ struct Lane2 {
     }
     st.nll += 0.5 * q2 + lg + 0.5 * d * LOG_2PI;
     st.s2 += q2;
-    double wv[d], ww = 0.0;
+    real wv[d], ww = 0.0;
 #pragma unroll
     for (int a = d - 1; a >= 0; --a) {
-      double acc = y[a];
+      real acc = y[a];
 #pragma unroll
       for (int e2 = a + 1; e2 < d; ++e2) acc = fma(-SL[e2][a], wv[e2], acc);
       wv[a] = acc * fast_rcp(SL[a][a]);
@@ -831,10 +822,10 @@ struct Lane2 {
   }
 
   static __device__ __forceinline__ void scan(Ctx& cx, long k0, long k1, const Lin& lin,
-                                              const double* __restrict__ state_in, double* __restrict__ kern,
-                                              double* __restrict__ state_end, double* __restrict__ part,
-                                              double* __restrict__ fmeans, double* __restrict__ fchols) {
-    double m[R], uf[R][D];
+                                              const real* __restrict__ state_in, real* __restrict__ kern,
+                                              real* __restrict__ state_end, real* __restrict__ part,
+                                              real* __restrict__ fmeans, real* __restrict__ fchols) {
+    real m[R], uf[R][D];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const bool ok = cx.row[s] < D;
@@ -847,7 +838,7 @@ struct Lane2 {
     scan_step<0>(cx, lin, k0, m, uf, kern, st, fmeans, fchols, k0 + 1 < k1);
     for (long k = k0 + 1; k < k1; ++k) scan_step<d>(cx, lin, k, m, uf, kern, st, fmeans, fchols, k + 1 < k1);
     // filtered end state with a lower-triangular factor
-    double le[R][D];
+    real le[R][D];
     tria_rows<d>(cx, uf, le);
 #pragma unroll
     for (int s = 0; s < R; ++s)
@@ -874,17 +865,17 @@ struct Lane2 {
   // pieces 8 D bytes apart: 8 instead of ~20 L1 tag look-ups and half the L2 sectors per warp access (ncu, r01).
   static constexpr int PW = (D % 2 == 0) ? 2 : 1;
   template <int JS = 0>  // columns [JS, D) only (JS a multiple of PW)
-  static __device__ __forceinline__ void load_rows(const Ctx& cx, const double* __restrict__ base, double (&x)[R][D]) {
+  static __device__ __forceinline__ void load_rows(const Ctx& cx, const real* __restrict__ base, real (&x)[R][D]) {
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int rc = cx.rc[s];
 #pragma unroll
       for (int j = 0; j < JS; ++j) x[s][j] = 0.0;
       if constexpr (PW == 2) {
-        const double2* pe = reinterpret_cast<const double2*>(base) + rc;
+        const real2* pe = reinterpret_cast<const real2*>(base) + rc;
 #pragma unroll
         for (int j = JS / 2; j < D / 2; ++j) {
-          const double2 a = pe[j * D];
+          const real2 a = pe[j * D];
           x[s][2 * j] = a.x;
           x[s][2 * j + 1] = a.y;
         }
@@ -895,16 +886,16 @@ struct Lane2 {
     }
   }
   template <int JS>
-  static __device__ __forceinline__ void store_rows_pm(const Ctx& cx, double* __restrict__ base,
-                                                       const double (&x)[R][D]) {
+  static __device__ __forceinline__ void store_rows_pm(const Ctx& cx, real* __restrict__ base,
+                                                       const real (&x)[R][D]) {
 #pragma unroll
     for (int s = 0; s < R; ++s)
       if (cx.row[s] < D) {
         const int r = cx.row[s];
         if constexpr (PW == 2) {
-          double2* pe = reinterpret_cast<double2*>(base) + r;
+          real2* pe = reinterpret_cast<real2*>(base) + r;
 #pragma unroll
-          for (int j = JS / 2; j < D / 2; ++j) pe[j * D] = make_double2(x[s][2 * j], x[s][2 * j + 1]);
+          for (int j = JS / 2; j < D / 2; ++j) pe[j * D] = make_real2(x[s][2 * j], x[s][2 * j + 1]);
         } else {
 #pragma unroll
           for (int j = JS; j < D; ++j) base[j * D + r] = x[s][j];
@@ -913,8 +904,8 @@ struct Lane2 {
   }
   // L2 prefetch of one step's backward kernel (NE contiguous doubles) and the previous mean of that row, spread over
   // the group's lanes in 128-byte strides
-  static __device__ __forceinline__ void prefetch_step(const Ctx& cx, const double* __restrict__ kp,
-                                                       const double* __restrict__ mrow) {
+  static __device__ __forceinline__ void prefetch_step(const Ctx& cx, const real* __restrict__ kp,
+                                                       const real* __restrict__ mrow) {
 #pragma unroll
     for (int o = 0; o < NE; o += 16 * G) {
       const int off = o + 16 * cx.l;
@@ -926,10 +917,10 @@ struct Lane2 {
       prefetch_l2(mrow + D - 1);
     }
   }
-  static __device__ __forceinline__ double emit(const Ctx& cx, long t, const double (&m)[R], const double (&l)[R][D],
-                                                double cscale, const double (&old)[R], double* __restrict__ means,
-                                                double* __restrict__ chols) {
-    double bad = 0.0;
+  static __device__ __forceinline__ real emit(const Ctx& cx, long t, const real (&m)[R], const real (&l)[R][D],
+                                                real cscale, const real (&old)[R], real* __restrict__ means,
+                                                real* __restrict__ chols) {
+    real bad = 0.0;
 #pragma unroll
     for (int s = 0; s < R; ++s)
       if (cx.row[s] < D) {
@@ -938,7 +929,7 @@ struct Lane2 {
         bad += close ? 0.0 : 1.0;
         means[t * D + r] = m[s];
         if (chols) {
-          double rowv[D];
+          real rowv[D];
 #pragma unroll
           for (int j = 0; j < D; ++j) rowv[j] = (j <= r) ? cscale * l[s][j] : 0.0;
           store_row(chols + (t * D + r) * D, rowv);
@@ -948,13 +939,13 @@ struct Lane2 {
   }
   template <int JS>
   static __device__ __forceinline__ void smooth_step(Ctx& cx, long k, bool has_prev, bool emit_t0,
-                                                     const double* qLinvdiag, const double* qL,
-                                                     const double* __restrict__ kern, double cscale,
-                                                     double* __restrict__ means, double* __restrict__ chols,
-                                                     double (&m)[R], double (&l)[R][D], double& obj, double& bad) {
-    double g[R], e[R][D], ph[R][D], old[R];
+                                                     const real* qLinvdiag, const real* qL,
+                                                     const real* __restrict__ kern, real cscale,
+                                                     real* __restrict__ means, real* __restrict__ chols,
+                                                     real (&m)[R], real (&l)[R][D], real& obj, real& bad) {
+    real g[R], e[R][D], ph[R][D], old[R];
     {
-      const double* kp = kern + k * NE;
+      const real* kp = kern + k * NE;
 #pragma unroll
       for (int s = 0; s < R; ++s) {
         g[s] = kp[cx.rc[s]];
@@ -964,10 +955,10 @@ struct Lane2 {
       load_rows<JS>(cx, kp + D + D * D, ph);
     }
     if (has_prev) prefetch_step(cx, kern + (k - 1) * NE, means + (k - 1) * D);
-    const double* ML = publish<0>(cx, 0, l);
-    double mv[D];
+    const real* ML = publish<0>(cx, 0, l);
+    real mv[D];
     gather(cx, m, mv);
-    double mn[R], cd[R][D];
+    real mn[R], cd[R][D];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       mn[s] = g[s];
@@ -980,14 +971,14 @@ struct Lane2 {
       for (int s = 0; s < R; ++s) mn[s] = fma(e[s][i], mv[i], mn[s]);
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
-        const double lv = ML[i * LDM + j];
+        const real lv = ML[i * LDM + j];
 #pragma unroll
         for (int s = 0; s < R; ++s) cd[s][j] = fma(e[s][i], lv, cd[s][j]);
       }
     }
     tria2_step<0, JS>(cx, cd, ph);
     // objective increment |QL^{-1}(m_k - F m_{k+1})|^2 (replicated)
-    double fm[D], rr[D], dr[R];
+    real fm[D], rr[D], dr[R];
 #pragma unroll
     for (int i = 0; i < D; ++i) fm[i] = mv[i];
     mulF_vec(fm);
@@ -998,7 +989,7 @@ struct Lane2 {
     for (int b = 0; b < d; ++b) {
 #pragma unroll
       for (int i = 0; i < Q1; ++i) {
-        double acc = rr[b * Q1 + i];
+        real acc = rr[b * Q1 + i];
 #pragma unroll
         for (int j = 0; j < i; ++j) acc = fma(-qL[i * Q1 + j], rr[b * Q1 + j], acc);
         acc *= qLinvdiag[i];
@@ -1015,11 +1006,11 @@ struct Lane2 {
     if (k > 0 || emit_t0) bad += emit(cx, k, m, l, cscale, old, means, chols);
   }
   static __device__ __forceinline__ void smooth(Ctx& cx, long k0, long k1, bool last, bool emit_t0,
-                                                const double* qLinvdiag, const double* qL,
-                                                const double* __restrict__ seed, const double* __restrict__ kern,
-                                                double cscale, double* __restrict__ means,
-                                                double* __restrict__ chols, double* __restrict__ part) {
-    double m[R], l[R][D], old[R];
+                                                const real* qLinvdiag, const real* qL,
+                                                const real* __restrict__ seed, const real* __restrict__ kern,
+                                                real cscale, real* __restrict__ means,
+                                                real* __restrict__ chols, real* __restrict__ part) {
+    real m[R], l[R][D], old[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const bool ok = cx.row[s] < D;
@@ -1027,7 +1018,7 @@ struct Lane2 {
 #pragma unroll
       for (int j = 0; j < D; ++j) l[s][j] = (ok && j <= cx.rc[s]) ? seed[D + cx.rc[s] * D + j] : 0.0;
     }
-    double obj = 0.0, bad = 0.0;
+    real obj = 0.0, bad = 0.0;
     if (last) {
 #pragma unroll
       for (int s = 0; s < R; ++s) old[s] = means[k1 * D + cx.rc[s]];
@@ -1051,4 +1042,4 @@ struct Lane2 {
   }
 };
 
-}  // namespace pof
+}  // namespace POF_NS

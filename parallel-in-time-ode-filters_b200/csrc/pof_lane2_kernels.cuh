@@ -3,7 +3,7 @@
 #include "pof_lane2.cuh"
 #include "pof_launch.cuh"
 
-namespace pof {
+namespace POF_NS {
 
 constexpr int LANE2_WARPS = 4;
 
@@ -14,11 +14,11 @@ struct Lane2Setup {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     return ((long)blockIdx.x * LANE2_WARPS + warp) * LN::GPW + lane / LN::G;
   }
-  static __device__ __forceinline__ double* smem_of_thread(double* sm) {
+  static __device__ __forceinline__ real* smem_of_thread(real* sm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     return sm + (warp * LN::GPW + lane / LN::G) * LN::SM_GROUP;
   }
-  static constexpr int smem_bytes() { return LANE2_WARPS * LN::GPW * LN::SM_GROUP * (int)sizeof(double); }
+  static constexpr int smem_bytes() { return LANE2_WARPS * LN::GPW * LN::SM_GROUP * (int)sizeof(real); }
   static unsigned grid(long CS) {
     const long per_block = (long)LANE2_WARPS * LN::GPW;
     return (unsigned)((CS + per_block - 1) / per_block);
@@ -27,8 +27,8 @@ struct Lane2Setup {
 
 template <int d, int q>
 __global__ void __launch_bounds__(LANE2_WARPS * 32)
-    k_lane2_fold(LeafArgs a, double* __restrict__ fagg, double* __restrict__ faggm) {
-  extern __shared__ __align__(16) double sm[];
+    k_lane2_fold(LeafArgs a, real* __restrict__ fagg, real* __restrict__ faggm) {
+  extern __shared__ __align__(16) real sm[];
   using LN = Lane2<d, q>;
   const long ch = Lane2Setup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
 
 template <int d, int q>
 __global__ void __launch_bounds__(LANE2_WARPS * 32)
-    k_lane2_scan(LeafArgs a, const double* __restrict__ fin, double* __restrict__ kern, double* __restrict__ send,
-                 double* __restrict__ part, double* __restrict__ fmeans, double* __restrict__ fchols) {
-  extern __shared__ __align__(16) double sm[];
+    k_lane2_scan(LeafArgs a, const real* __restrict__ fin, real* __restrict__ kern, real* __restrict__ send,
+                 real* __restrict__ part, real* __restrict__ fmeans, real* __restrict__ fchols) {
+  extern __shared__ __align__(16) real sm[];
   using LN = Lane2<d, q>;
   const long ch = Lane2Setup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
@@ -60,22 +60,22 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
 
 template <int d, int q>
 __global__ void __launch_bounds__(LANE2_WARPS * 32)
-    k_lane2_smooth(LeafArgs a, const double* __restrict__ sin, const double* __restrict__ kern, int emit_t0,
-                   const double* __restrict__ cscale, double* __restrict__ means, double* __restrict__ chols,
-                   double* __restrict__ part2) {
-  extern __shared__ __align__(16) double sm[];
+    k_lane2_smooth(LeafArgs a, const real* __restrict__ sin, const real* __restrict__ kern, int emit_t0,
+                   const real* __restrict__ cscale, real* __restrict__ means, real* __restrict__ chols,
+                   real* __restrict__ part2) {
+  extern __shared__ __align__(16) real sm[];
   using LN = Lane2<d, q>;
   const long ch = Lane2Setup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
   typename LN::Ctx cx;
   LN::init_ctx(cx, Lane2Setup<d, q>::smem_of_thread(sm), a.ql.v);
   constexpr int D = LN::D, ST = D * D + D;
-  double qinv[LN::Q1];
+  real qinv[LN::Q1];
 #pragma unroll
   for (int i = 0; i < LN::Q1; ++i) qinv[i] = 1.0 / a.ql.v[i * LN::Q1 + i];
   const long k0 = ch * a.L;
   const long k1 = (k0 + a.L < a.n) ? k0 + a.L : a.n;
-  const double cs = cscale ? *cscale : 1.0;
+  const real cs = cscale ? *cscale : 1.0;
   LN::smooth(cx, k0, k1, ch == a.CS - 1, emit_t0 != 0, qinv, a.ql.v, sin + ch * ST, kern, cs, means, chols,
              part2 + ch * 2);
 }
@@ -87,22 +87,22 @@ struct Lane2Launchers {
   static cudaError_t prep(K kernel) {
     return ensure_smem(kernel, LS::smem_bytes());
   }
-  static cudaError_t fold(cudaStream_t s, const LeafArgs& a, double* fagg, double* faggm) {
+  static cudaError_t fold(cudaStream_t s, const LeafArgs& a, real* fagg, real* faggm) {
     if (cudaError_t e = prep(k_lane2_fold<d, q>)) return e;
     k_lane2_fold<d, q><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes(), s>>>(a, fagg, faggm);
     return cudaGetLastError();
   }
   // the chunk smoothing elements come from the chunk-level op (pof_treelane.cuh): sagg must be null
-  static cudaError_t scan(cudaStream_t s, const LeafArgs& a, const double* fin, double* kern, double* sagg,
-                          double* send, double* part, double* fmeans, double* fchols) {
+  static cudaError_t scan(cudaStream_t s, const LeafArgs& a, const real* fin, real* kern, real* sagg,
+                          real* send, real* part, real* fmeans, real* fchols) {
     if (sagg) return cudaErrorInvalidValue;
     if (cudaError_t e = ensure_smem(k_lane2_scan<d, q>, LS::smem_bytes(), true)) return e;
     k_lane2_scan<d, q><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes(), s>>>(a, fin, kern, send, part, fmeans,
                                                                                   fchols);
     return cudaGetLastError();
   }
-  static cudaError_t smooth(cudaStream_t s, const LeafArgs& a, const double* sin, const double* kern, int emit_t0,
-                            const double* cscale, double* means, double* chols, double* part2) {
+  static cudaError_t smooth(cudaStream_t s, const LeafArgs& a, const real* sin, const real* kern, int emit_t0,
+                            const real* cscale, real* means, real* chols, real* part2) {
     if (cudaError_t e = prep(k_lane2_smooth<d, q>)) return e;
     k_lane2_smooth<d, q><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes(), s>>>(a, sin, kern, emit_t0, cscale,
                                                                                     means, chols, part2);
@@ -114,14 +114,14 @@ struct Lane2Launchers {
   }
 };
 
-}  // namespace pof
+}  // namespace POF_NS
 
 // only state dimensions whose tree sweeps have the register-resident chunk-level op (2D <= 32)
 #define POF_LANE2_CASE(dd, qq) \
   case qq:                     \
     if constexpr (dd * (qq + 1) <= 16) return Lane2Launchers<dd, qq>::get(); else return nullptr;
 #define POF_DEFINE_LANE2_D(dd)                 \
-  namespace pof {                              \
+  namespace POF_NS {                              \
   const LeafLaunch* lane2_launch_d##dd(int q) { \
     switch (q) {                               \
       POF_LANE2_CASE(dd, 1)                    \

@@ -5,7 +5,9 @@
 
 #include <mutex>
 
-namespace pof {
+#include "pof_real.cuh"
+
+namespace POF_NS {
 
 // Raise a kernel's dynamic shared-memory limit ONCE per (kernel, device): cudaFuncSetAttribute is a driver call of
 // several microseconds, and calling it on every launch made the tiny tree kernels launch-bound.
@@ -50,41 +52,42 @@ inline cudaError_t ensure_smem(K kernel, int bytes, bool max_carveout = false) {
 }
 
 struct QLParam {
-  double v[36];  // (q+1) x (q+1) row-major, q <= 5; lives in the kernel-parameter constant bank
+  real v[36];  // (q+1) x (q+1) row-major, q <= 5; lives in the kernel-parameter constant bank
 };
 
 struct LeafArgs {
   long n;    // local number of steps
   long L;    // chunk length
   long CS;   // number of chunks
-  const double* H;  // dense linearisation (n,d,D), (n,d) ...
-  const double* c;
-  const double* Jc;  // ... or compact: per step [J_f (d x d) | c (d)], H = E1 - J_f E0 rebuilt on load (Jc != null)
-  double s0, s1;     // Nordsieck scalings: E0 = s0 e_0^T, E1 = s1 e_1^T per block
+  const real* H;  // dense linearisation (n,d,D), (n,d) ...
+  const real* c;
+  const real* Jc;  // ... or compact: per step [J_f (d x d) | c (d)], H = E1 - J_f E0 rebuilt on load (Jc != null)
+  real s0, s1;     // Nordsieck scalings: E0 = s0 e_0^T, E1 = s1 e_1^T per block
   QLParam ql;
   int d, q;          // runtime dimensions (the tile family is not templated on them)
-  const double* R;   // observation-noise factors cholR (n,d,d), or null = noiseless (tile family only)
-  const double* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
-  const double* QLd; // preconditioned IWP described by ql (tile family only)
+  const real* R;   // observation-noise factors cholR (n,d,d), or null = noiseless (tile family only)
+  const real* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
+  const real* QLd; // preconditioned IWP described by ql (tile family only)
   int tile_reg;      // tile family: register-resident Householder sweeps (default; 0 with POF_F_TILE_SMEM_QR)
 };
 
 struct LeafLaunch {
   // faggm (may be null): the chunk's filtering element BEFORE its last measurement update (lane kernels only)
-  cudaError_t (*fold)(cudaStream_t, const LeafArgs&, double* fagg, double* faggm);
+  cudaError_t (*fold)(cudaStream_t, const LeafArgs&, real* fagg, real* faggm);
   // sagg null: do not compose the chunk's smoothing element inside the scan (lane kernels only)
-  cudaError_t (*scan)(cudaStream_t, const LeafArgs&, const double* fin, double* kern, double* sagg, double* send,
-                      double* part, double* fmeans, double* fchols);
-  cudaError_t (*smooth)(cudaStream_t, const LeafArgs&, const double* sin, const double* kern, int emit_t0,
-                        const double* cscale, double* means, double* chols, double* part2);
+  cudaError_t (*scan)(cudaStream_t, const LeafArgs&, const real* fin, real* kern, real* sagg, real* send,
+                      real* part, real* fmeans, real* fchols);
+  cudaError_t (*smooth)(cudaStream_t, const LeafArgs&, const real* sin, const real* kern, int emit_t0,
+                        const real* cscale, real* means, real* chols, real* part2);
   // sequential extended Kalman smoother relinearised at the predicted mean (one thread; baseline path), or null
-  cudaError_t (*seq_eks)(cudaStream_t, const LeafArgs&, int ivp_id, const double* params8, const double* x0,
-                         double* kern, double* means, double* chols, double* part);
+  cudaError_t (*seq_eks)(cudaStream_t, const LeafArgs&, int ivp_id, const real* params8, const real* x0,
+                         real* kern, real* means, real* chols, real* part);
   int chunks_per_warp;  // 32 / G for the lane-cooperative kernels
   int has_pre_update;   // 1 if fold emits faggm (the chunk's element before its last update); both families do
   int is_tile;          // 1 for the CTA-per-chunk large-state family (pof_tile.cu): chunks_per_warp is 0 there
 };
 
+#ifndef POF_F32
 // one-thread sequential EKS (pof_seq_kernels.cuh): only `seq_eks` is set; nullptr if q is not compiled in
 const LeafLaunch* seq_launch_d1(int q);
 const LeafLaunch* seq_launch_d2(int q);
@@ -101,19 +104,39 @@ bool tile_supported(int d, int q);
 bool tile_tree_supported(int D);
 int tile_ctas_per_sm(int d, int q);
 const LeafLaunch* tile_leaf_launch();
-cudaError_t tile_fup(cudaStream_t, int D, const double* child, long nchild, double* parent, long nparent);
-cudaError_t tile_fdown(cudaStream_t, int D, const double* pin, long nparent, const double* cagg, long nchild,
-                       double* cin);
-cudaError_t tile_sup(cudaStream_t, int D, const double* child, long nchild, double* parent, long nparent);
-cudaError_t tile_sdown(cudaStream_t, int D, const double* pin, long nparent, const double* cagg, long nchild,
-                       double* cin);
-cudaError_t tile_chunkk(cudaStream_t, int D, const double* fin, const double* faggm, double* sagg, long CS);
-cudaError_t tile_fcomb(cudaStream_t, int D, long n, const double* e1, const double* e2, double* out);
-cudaError_t tile_scomb(cudaStream_t, int D, long n, const double* e1, const double* e2, double* out);
-cudaError_t tile_fchain(cudaStream_t, int D, int count, const double* state_in, const double* elems,
-                        double* state_out, double* scratch);
-cudaError_t tile_schain(cudaStream_t, int D, int count, const double* state_in, const double* elems,
-                        double* state_out, double* scratch);
+cudaError_t tile_fup(cudaStream_t, int D, const real* child, long nchild, real* parent, long nparent);
+cudaError_t tile_fdown(cudaStream_t, int D, const real* pin, long nparent, const real* cagg, long nchild,
+                       real* cin);
+cudaError_t tile_sup(cudaStream_t, int D, const real* child, long nchild, real* parent, long nparent);
+cudaError_t tile_sdown(cudaStream_t, int D, const real* pin, long nparent, const real* cagg, long nchild,
+                       real* cin);
+cudaError_t tile_chunkk(cudaStream_t, int D, const real* fin, const real* faggm, real* sagg, long CS);
+cudaError_t tile_fcomb(cudaStream_t, int D, long n, const real* e1, const real* e2, real* out);
+cudaError_t tile_scomb(cudaStream_t, int D, long n, const real* e1, const real* e2, real* out);
+cudaError_t tile_fchain(cudaStream_t, int D, int count, const real* state_in, const real* elems,
+                        real* state_out, real* scratch);
+cudaError_t tile_schain(cudaStream_t, int D, int count, const real* state_in, const real* elems,
+                        real* state_out, real* scratch);
+
+#else
+// fp32 build: only the register-resident family exists (the large-state tile kernels and the one-thread sequential EKS
+// are fp64 only)
+const LeafLaunch* lane2_launch_d1(int q);
+const LeafLaunch* lane2_launch_d2(int q);
+const LeafLaunch* lane2_launch_d3(int q);
+const LeafLaunch* lane2_launch_d4(int q);
+inline bool tile_supported(int, int) { return false; }
+inline bool tile_tree_supported(int) { return false; }
+inline int tile_ctas_per_sm(int, int) { return 1; }
+inline const LeafLaunch* tile_leaf_launch() { return nullptr; }
+inline cudaError_t tile_fup(cudaStream_t, int, const real*, long, real*, long) { return cudaErrorNotSupported; }
+inline cudaError_t tile_fdown(cudaStream_t, int, const real*, long, const real*, long, real*) { return cudaErrorNotSupported; }
+inline cudaError_t tile_sup(cudaStream_t, int, const real*, long, real*, long) { return cudaErrorNotSupported; }
+inline cudaError_t tile_sdown(cudaStream_t, int, const real*, long, const real*, long, real*) { return cudaErrorNotSupported; }
+inline cudaError_t tile_chunkk(cudaStream_t, int, const real*, const real*, real*, long) { return cudaErrorNotSupported; }
+inline cudaError_t tile_fcomb(cudaStream_t, int, long, const real*, const real*, real*) { return cudaErrorNotSupported; }
+inline cudaError_t tile_scomb(cudaStream_t, int, long, const real*, const real*, real*) { return cudaErrorNotSupported; }
+#endif
 
 // One whole tree sweep (an up-sweep and/or a down-sweep over the chunk carries) as ONE kernel without level barriers:
 // a DATAFLOW schedule.  Work items (one associative combine each) are numbered in level order; every warp draws the
@@ -135,11 +158,11 @@ struct FlowArgs {
                                  // ticket never straddles two segments: its items must not depend on each other)
   int up_lo, up_hi;         // levels built by UP segments of THIS launch (their flags are waited for); elements of
                             // any other level were complete before the launch
-  double* agg;              // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
-  double* st;               // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
-  double* sx;               // smoother, element-form down-sweep (DOWN_E): per node the aggregate of everything LATER
-  const double* root_m;     // state of the root node for the down-sweep (ROOT item): mean (D), factor (D x D);
-  const double* root_L;     // null with DOWN_E segments: the root's "later" aggregate is the identity element
+  real* agg;              // elements per node (filtering: 3D^2+2D doubles, smoothing: 2D^2+D)
+  real* st;               // states per node (D + D^2 doubles): incoming filtered / outgoing smoothed states
+  real* sx;               // smoother, element-form down-sweep (DOWN_E): per node the aggregate of everything LATER
+  const real* root_m;     // state of the root node for the down-sweep (ROOT item): mean (D), factor (D x D);
+  const real* root_L;     // null with DOWN_E segments: the root's "later" aggregate is the identity element
   unsigned* flag_up;        // per node: element complete   } zeroed by a stream-ordered memset before the launch
   unsigned* flag_dn;        // per node: state complete     }
   unsigned* ticket;         // the ticket counter           }
@@ -147,22 +170,22 @@ struct FlowArgs {
 
 struct ExchangeArgs {
   int rank, world;
-  const double* gathered;   // world payloads, `stride` doubles each
+  const real* gathered;   // world payloads, `stride` doubles each
   long stride;
-  const double* x0_mean;    // filter: initial state
-  const double* x0_chol;
-  double* state_out;        // D + D*D: incoming filtered state / smoothing seed of this rank
-  double* scratch;          // D + D*D
+  const real* x0_mean;    // filter: initial state
+  const real* x0_chol;
+  real* state_out;        // D + D*D: incoming filtered state / smoothing seed of this rank
+  real* scratch;          // D + D*D
   // smoother exchange only
-  double n_obs, d_obs;      // total number of observations n and their dimension d (sigma^2 = sum / n / d)
+  real n_obs, d_obs;      // total number of observations n and their dimension d (sigma^2 = sum / n / d)
   int calibrate;
-  double* cscale;           // out: sqrt(sigma^2) or 1
-  double* scalars;          // out: POF scalars vector (nll, ssq, ssq_proper, cscale slots), or null
+  real* cscale;           // out: sqrt(sigma^2) or 1
+  real* scalars;          // out: POF scalars vector (nll, ssq, ssq_proper, cscale slots), or null
 };
 
 // register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> CTA-per-node tile kernels
 struct TreeLaunch {
-  typedef cudaError_t (*Fn)(cudaStream_t, const double* a, long na, const double* b, double* c, long nb);
+  typedef cudaError_t (*Fn)(cudaStream_t, const real* a, long na, const real* b, real* c, long nb);
   Fn fup, fdown, sup, sdown, fcomb, scomb, chunkk, sseed;
   typedef cudaError_t (*FlowFn)(cudaStream_t, const FlowArgs&);
   FlowFn fflow, sflow;     // whole-sweep dataflow kernels (filtering / smoothing)
@@ -173,4 +196,4 @@ const TreeLaunch* tree_launch_a(int D);
 const TreeLaunch* tree_launch_b(int D);
 const TreeLaunch* tree_launch_c(int D);
 
-}  // namespace pof
+}  // namespace POF_NS

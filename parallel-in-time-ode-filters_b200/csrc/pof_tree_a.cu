@@ -1,5 +1,5 @@
 #include "pof_tree_kernels.cuh"
-namespace pof {
+namespace POF_NS {
 const TreeLaunch* tree_launch_a(int D) {
   switch (D) {
     case 2: return TreeLaunchers<2>::get();

@@ -1,5 +1,5 @@
 #include "pof_tree_kernels.cuh"
-namespace pof {
+namespace POF_NS {
 const TreeLaunch* tree_launch_b(int D) {
   switch (D) {
     case 9: return TreeLaunchers<9>::get();

@@ -1,5 +1,5 @@
 #include "pof_tree_kernels.cuh"
-namespace pof {
+namespace POF_NS {
 const TreeLaunch* tree_launch_c(int D) {
   switch (D) {
     case 15: return TreeLaunchers<15>::get();

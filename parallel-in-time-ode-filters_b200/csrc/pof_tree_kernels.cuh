@@ -4,7 +4,7 @@
 #include "pof_launch.cuh"
 #include "pof_treelane.cuh"
 
-namespace pof {
+namespace POF_NS {
 
 constexpr int TL_WARPS = 4;
 
@@ -12,7 +12,7 @@ enum TreeOp { T_FUP = 0, T_FDOWN, T_SUP, T_SDOWN, T_FCOMB, T_SCOMB, T_CHUNKK, T_
 
 // (L2 loads: inside a dataflow sweep the source was written by another SM during the SAME kernel)
 template <int D, int G>
-__device__ __forceinline__ void group_copy(int r, double* dst, const double* src, int n) {
+__device__ __forceinline__ void group_copy(int r, real* dst, const real* src, int n) {
   for (int i = r; i < n; i += G) dst[i] = __ldcg(src + i);
 }
 
@@ -28,8 +28,8 @@ __device__ __forceinline__ void group_copy(int r, double* dst, const double* src
 // two warps any register count fits into what those leave free)
 template <int D, int OP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-    k_tree(const double* __restrict__ a, long na, const double* __restrict__ b, double* __restrict__ c, long nb) {
-  extern __shared__ __align__(16) double sm[];
+    k_tree(const real* __restrict__ a, long na, const real* __restrict__ b, real* __restrict__ c, long nb) {
+  extern __shared__ __align__(16) real sm[];
   using TL = TreeLane<D>;
   constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB || OP == T_CHUNKK);
   constexpr int G = FILT ? TL::G2 : TL::GS;
@@ -42,19 +42,19 @@ __global__ void __launch_bounds__(WARPS * 32)
   typename TL::Ctx cx;
   TL::template init<G>(cx, sm + (warp * CPW + lane / G) * SMC, FILT ? TL::NMAT : TL::NMAT_S);
   if constexpr (OP == T_FUP) {
-    const double* lc = a + 2 * i * FE;
+    const real* lc = a + 2 * i * FE;
     if (2 * i + 1 < na) TL::template filter_combine<false>(cx, lc, lc + FE, c + i * FE);
     else group_copy<D, G>(cx.r, c + i * FE, lc, FE);
   } else if constexpr (OP == T_FDOWN) {
-    const double* p = a + i * ST;
+    const real* p = a + i * ST;
     group_copy<D, G>(cx.r, c + 2 * i * ST, p, ST);
     if (2 * i + 1 < na) TL::template filter_combine<true>(cx, p, b + 2 * i * FE, c + (2 * i + 1) * ST);
   } else if constexpr (OP == T_SUP) {
-    const double* lc = a + 2 * i * SE;
+    const real* lc = a + 2 * i * SE;
     if (2 * i + 1 < na) TL::template smooth_combine<false>(cx, lc + SE, lc, c + i * SE);
     else group_copy<D, G>(cx.r, c + i * SE, lc, SE);
   } else if constexpr (OP == T_SDOWN) {
-    const double* p = a + i * ST;
+    const real* p = a + i * ST;
     if (2 * i + 1 < na) {
       group_copy<D, G>(cx.r, c + (2 * i + 1) * ST, p, ST);
       TL::template smooth_combine<true>(cx, p, b + (2 * i + 1) * SE, c + 2 * i * ST);
@@ -86,7 +86,7 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 
 template <int D, bool FILT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) real sm[];
   using TL = TreeLane<D>;
   constexpr int G = FILT ? TL::G2 : TL::GS;
   constexpr int CPW = 32 / G;
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
     __syncwarp();
     if (live) {
       if (kind == FlowArgs::UP) {
-        const double* lc = A.agg + (A.off[lev - 1] + 2 * i) * EL;
-        double* pa = A.agg + (A.off[lev] + i) * EL;
+        const real* lc = A.agg + (A.off[lev - 1] + 2 * i) * EL;
+        real* pa = A.agg + (A.off[lev] + i) * EL;
         if (2 * i + 1 < A.sz[lev - 1]) {
           if constexpr (FILT) TL::template filter_combine<false>(cx, lc, lc + EL, pa);
           else TL::template smooth_combine<false>(cx, lc + EL, lc, pa);
@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
         if (cx.r == 0) st_release(A.flag_up + A.off[lev] + i, 1u);
       } else if (kind == FlowArgs::ROOT) {
         if (A.root_m) {
-          double* r = A.st + A.off[A.nlev - 1] * ST;
+          real* r = A.st + A.off[A.nlev - 1] * ST;
           for (int j = cx.r; j < ST; j += G) r[j] = (j < D) ? __ldcg(A.root_m + j) : __ldcg(A.root_L + (j - D));
         } else if constexpr (!FILT) {
           // element-form down-sweep of the smoother: nothing lies later than the root -> the identity element
           // (g = 0, E = I, D = 0); combining it with any element returns that element exactly
-          double* r = A.sx + A.off[A.nlev - 1] * SE;
+          real* r = A.sx + A.off[A.nlev - 1] * SE;
           for (int j = cx.r; j < SE; j += G) r[j] = (j >= D && j < D + D * D && (j - D) / D == (j - D) % D) ? 1.0 : 0.0;
         }
         __threadfence();
@@ -164,9 +164,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
       } else if (kind == FlowArgs::DOWN_E) {
         if constexpr (!FILT) {
           // exclusive-suffix ELEMENTS: X(right child) = X(parent); X(left child) = op(later = X(parent), right child)
-          const double* px = A.sx + (A.off[lev] + i) * SE;
-          const double* el = A.agg + A.off[lev - 1] * SE;
-          double* cxs = A.sx + A.off[lev - 1] * SE;
+          const real* px = A.sx + (A.off[lev] + i) * SE;
+          const real* el = A.agg + A.off[lev - 1] * SE;
+          real* cxs = A.sx + A.off[lev - 1] * SE;
           const bool two = 2 * i + 1 < A.sz[lev - 1];
           if (two) {
             group_copy<D, G>(cx.r, cxs + (2 * i + 1) * SE, px, SE);
@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
           }
         }
       } else {
-        const double* p = A.st + (A.off[lev] + i) * ST;
-        const double* el = A.agg + A.off[lev - 1] * EL;
-        double* cs = A.st + A.off[lev - 1] * ST;
+        const real* p = A.st + (A.off[lev] + i) * ST;
+        const real* el = A.agg + A.off[lev - 1] * EL;
+        real* cs = A.st + A.off[lev - 1] * ST;
         const bool two = 2 * i + 1 < A.sz[lev - 1];
         if constexpr (FILT) {
           group_copy<D, G>(cx.r, cs + 2 * i * ST, p, ST);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
 //             smoothing carries W-1 .. rank+1                                 (smoother.py:53-63 in state form)
 template <int D, bool FILT>
 __global__ void __launch_bounds__(32) k_exchange(const ExchangeArgs A) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) real sm[];
   using TL = TreeLane<D>;
   constexpr int G = FILT ? TL::G2 : TL::GS;
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(32) k_exchange(const ExchangeArgs A) {
   if constexpr (FILT) {
     // pack x0 into the scratch/state ping-pong so that the last combine writes state_out
     const int count = A.rank;
-    double* bufs[2] = {A.state_out, A.scratch};
+    real* bufs[2] = {A.state_out, A.scratch};
     int cur = count & 1;  // after `count` flips the result sits in bufs[0]
     for (int j = cx.r; j < ST; j += G) bufs[cur][j] = (j < D) ? __ldcg(A.x0_mean + j) : __ldcg(A.x0_chol + (j - D));
     __threadfence();
@@ -245,15 +245,15 @@ __global__ void __launch_bounds__(32) k_exchange(const ExchangeArgs A) {
     // gathered payload of rank r: [smoothing carry SE | filtered end state ST | nll, s1, s2 partial sums]
     const int W = A.world;
     if (cx.r == 0) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      real s0 = 0.0, s1 = 0.0, s2 = 0.0;
       for (int r = 0; r < W; ++r) {
-        const double* p = A.gathered + (long)r * A.stride + SE + ST;
+        const real* p = A.gathered + (long)r * A.stride + SE + ST;
         s0 += __ldcg(p);
         s1 += __ldcg(p + 1);
         s2 += __ldcg(p + 2);
       }
-      const double ssq = s1 / A.n_obs / A.d_obs;
-      const double cs = A.calibrate ? sqrt(ssq) : 1.0;
+      const real ssq = s1 / A.n_obs / A.d_obs;
+      const real cs = A.calibrate ? sqrt(ssq) : 1.0;
       *A.cscale = cs;
       if (A.scalars) {
         A.scalars[0] = s0;                       // POF_S_NLL
@@ -263,14 +263,14 @@ __global__ void __launch_bounds__(32) k_exchange(const ExchangeArgs A) {
       }
     }
     const int count = W - 1 - A.rank;
-    double* bufs[2] = {A.state_out, A.scratch};
+    real* bufs[2] = {A.state_out, A.scratch};
     int cur = count & 1;
-    const double* term = A.gathered + (long)(W - 1) * A.stride + SE;
+    const real* term = A.gathered + (long)(W - 1) * A.stride + SE;
     for (int j = cx.r; j < ST; j += G) bufs[cur][j] = __ldcg(term + j);
     __threadfence();
     cx.sync();
     for (int i = 0; i < count; ++i) {  // later carries first: W-1, W-2, .., rank+1
-      const double* el = A.gathered + (long)(W - 1 - i) * A.stride;
+      const real* el = A.gathered + (long)(W - 1 - i) * A.stride;
       TL::template smooth_combine<true>(cx, bufs[cur], el, bufs[cur ^ 1]);
       __threadfence();
       cx.sync();
@@ -283,13 +283,13 @@ template <int D>
 struct TreeLaunchers {
   using TL = TreeLane<D>;
   template <int OP>
-  static cudaError_t run(cudaStream_t s, const double* a, long na, const double* b, double* c, long nb) {
+  static cudaError_t run(cudaStream_t s, const real* a, long na, const real* b, real* c, long nb) {
     constexpr bool FILT = (OP == T_FUP || OP == T_FDOWN || OP == T_FCOMB || OP == T_CHUNKK);
     constexpr int G = FILT ? TL::G2 : TL::GS;
     constexpr int CPW = 32 / G;
     // the ops that run on the side stream (next to the resident CTAs of the filter scan) use two-warp CTAs
     constexpr int WARPS = (OP == T_CHUNKK || OP == T_SUP) ? 2 : TL_WARPS;
-    constexpr int smem = WARPS * CPW * (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(double);
+    constexpr int smem = WARPS * CPW * (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(real);
     if (nb <= 0) return cudaSuccess;
     if (cudaError_t e = ensure_smem(k_tree<D, OP, WARPS>, smem, WARPS == 2)) return e;
     const long per_block = (long)WARPS * CPW;
@@ -302,7 +302,7 @@ struct TreeLaunchers {
     constexpr int G = FILT ? TL::G2 : TL::GS;
     constexpr int CPW = 32 / G;
     constexpr int WARPS = FILT ? TL_WARPS : 2;  // smoother sweeps run next to the filter scan's resident CTAs
-    constexpr int smem = WARPS * CPW * (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(double);
+    constexpr int smem = WARPS * CPW * (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(real);
     auto kern = k_tree_flow<D, FILT, WARPS>;
     if (cudaError_t e = ensure_smem(kern, smem, !FILT)) return e;
     static int max_grid[64] = {0};
@@ -332,7 +332,7 @@ struct TreeLaunchers {
   }
   template <bool FILT>
   static cudaError_t exchange(cudaStream_t s, const ExchangeArgs& A) {
-    constexpr int smem = (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(double);
+    constexpr int smem = (FILT ? TL::SM_COMBINE : TL::SM_COMBINE_S) * (int)sizeof(real);
     if (cudaError_t e = ensure_smem(k_exchange<D, FILT>, smem)) return e;
     k_exchange<D, FILT><<<1, 32, smem, s>>>(A);
     return cudaGetLastError();
@@ -345,4 +345,4 @@ struct TreeLaunchers {
   }
 };
 
-}  // namespace pof
+}  // namespace POF_NS

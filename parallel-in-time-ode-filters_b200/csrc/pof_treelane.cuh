@@ -12,9 +12,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pof_real.cuh"
 #include "pof_small.cuh"
 
-namespace pof {
+namespace POF_NS {
 
 template <int D>
 struct TreeLane {
@@ -41,14 +42,14 @@ struct TreeLane {
   struct Ctx {
     int r;  // lane within the combine's group
     unsigned mask;
-    double* sm;
+    real* sm;
     int nmat;  // matrices staged ahead of the broadcast slots (NMAT, or NMAT_S for the smoothing operator)
     int flip, vflip;
-    __device__ __forceinline__ double* mat(int which) const { return sm + which * MAT; }
+    __device__ __forceinline__ real* mat(int which) const { return sm + which * MAT; }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
   };
   template <int G>
-  static __device__ __forceinline__ void init(Ctx& c, double* sm, int nmat = NMAT) {
+  static __device__ __forceinline__ void init(Ctx& c, real* sm, int nmat = NMAT) {
     const int lane = threadIdx.x & 31;
     c.nmat = nmat;
     c.r = lane % G;
@@ -58,35 +59,20 @@ struct TreeLane {
     c.vflip = 0;
   }
 
-  static __device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-  }
-  static __device__ __forceinline__ double fast_rsqrt(double x) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double hx = 0.5 * x;
-    double e = fma(-hx * r, r, 0.5);
-    r = fma(r, e, r);
-    e = fma(-hx * r, r, 0.5);
-    return fma(r, e, r);
-  }
+  static __device__ __forceinline__ real fast_rcp(real x) { return POF_NS::fast_rcp(x); }
+  static __device__ __forceinline__ real fast_rsqrt(real x) { return POF_NS::fast_rsqrt(x); }
   // multi-accumulator dot product (the combines are latency chains: split every long FMA chain)
   template <int n>
-  static __device__ __forceinline__ double dotn(const double* a, const double* b) {
+  static __device__ __forceinline__ real dotn(const real* a, const real* b) {
     if constexpr (n <= 0) {
       return 0.0;
     } else if constexpr (n < 4) {
-      double s = a[0] * b[0];
+      real s = a[0] * b[0];
 #pragma unroll
       for (int j = 1; j < n; ++j) s = fma(a[j], b[j], s);
       return s;
     } else if constexpr (n < 10) {
-      double s0 = a[0] * b[0], s1 = a[1] * b[1];
+      real s0 = a[0] * b[0], s1 = a[1] * b[1];
 #pragma unroll
       for (int j = 2; j + 1 < n; j += 2) {
         s0 = fma(a[j], b[j], s0);
@@ -95,7 +81,7 @@ struct TreeLane {
       if constexpr (n % 2) s0 = fma(a[n - 1], b[n - 1], s0);
       return s0 + s1;
     } else {
-      double s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
+      real s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
 #pragma unroll
       for (int j = 4; j + 3 < n; j += 4) {
         s0 = fma(a[j], b[j], s0);
@@ -110,17 +96,17 @@ struct TreeLane {
     }
   }
   struct HH {
-    double s, tp, beta;
+    real s, tp, beta;
   };
   template <int n>
-  static __device__ __forceinline__ HH house(double alpha, const double* x) {
-    const double sigma = dotn<n>(x, x);
-    const double nrm2 = fma(alpha, alpha, sigma);
-    const bool nz = sigma > 0.0 && nrm2 > 0x1p-1000;  // see pof_lane2.cuh: subnormal norms would turn into NaN
-    const double rn = fast_rsqrt(nrm2);
-    const double nrm = nrm2 * rn;
-    const double beta = (alpha >= 0.0) ? -nrm : nrm;
-    const double s = alpha - beta;
+  static __device__ __forceinline__ HH house(real alpha, const real* x) {
+    const real sigma = dotn<n>(x, x);
+    const real nrm2 = fma(alpha, alpha, sigma);
+    const bool nz = sigma > real(0) && nrm2 > tiny_norm2();  // see pof_real.cuh: subnormal norms would turn into NaN
+    const real rn = fast_rsqrt(nrm2);
+    const real nrm = nrm2 * rn;
+    const real beta = (alpha >= 0.0) ? -nrm : nrm;
+    const real s = alpha - beta;
     HH h;
     h.beta = nz ? beta : alpha;
     h.s = nz ? s : 0.0;
@@ -130,17 +116,17 @@ struct TreeLane {
 
   // lane `src` publishes n doubles into broadcast slot `slot_id` (0/1: two independent streams), all lanes read
   template <int n>
-  static __device__ __forceinline__ void bcast(Ctx& c, int slot_id, const double (&x)[n], int src, double (&out)[n]) {
-    double2* slot = reinterpret_cast<double2*>(c.sm + c.nmat * MAT + (2 * slot_id + c.flip) * BCW);
+  static __device__ __forceinline__ void bcast(Ctx& c, int slot_id, const real (&x)[n], int src, real (&out)[n]) {
+    real2* slot = reinterpret_cast<real2*>(c.sm + c.nmat * MAT + (2 * slot_id + c.flip) * BCW);
     if (c.r == src) {
 #pragma unroll
-      for (int j = 0; j + 1 < n; j += 2) slot[j / 2] = make_double2(x[j], x[j + 1]);
-      if (n % 2) slot[n / 2] = make_double2(x[n - 1], 0.0);
+      for (int j = 0; j + 1 < n; j += 2) slot[j / 2] = make_real2(x[j], x[j + 1]);
+      if (n % 2) slot[n / 2] = make_real2(x[n - 1], 0.0);
     }
     c.sync();
 #pragma unroll
     for (int j = 0; j + 1 < n; j += 2) {
-      const double2 v = slot[j / 2];
+      const real2 v = slot[j / 2];
       out[j] = v.x;
       out[j + 1] = v.y;
     }
@@ -148,8 +134,8 @@ struct TreeLane {
   }
   // out[j] = x of lane j (j < n)
   template <int n>
-  static __device__ __forceinline__ void allgather(Ctx& c, double x, double (&out)[n]) {
-    double* v = c.sm + c.nmat * MAT + 4 * BCW + c.vflip * VEC;
+  static __device__ __forceinline__ void allgather(Ctx& c, real x, real (&out)[n]) {
+    real* v = c.sm + c.nmat * MAT + 4 * BCW + c.vflip * VEC;
     c.vflip ^= 1;
     if (c.r < n) v[c.r] = x;
     c.sync();
@@ -157,14 +143,14 @@ struct TreeLane {
     for (int j = 0; j < n; ++j) out[j] = v[j];
   }
   // row `row` of matrix `which` <- x   (caller syncs)
-  static __device__ __forceinline__ void put_row(Ctx& c, int which, int row, const double (&x)[D]) {
-    double* M = c.mat(which) + row * LDM;
+  static __device__ __forceinline__ void put_row(Ctx& c, int which, int row, const real (&x)[D]) {
+    real* M = c.mat(which) + row * LDM;
 #pragma unroll
     for (int j = 0; j < D; ++j) M[j] = x[j];
   }
   // y[c] = sum_k a[k] * M[k][c]   (row vector times staged matrix)
-  static __device__ __forceinline__ void row_times(const Ctx& c, int which, const double (&a)[D], double (&y)[D]) {
-    const double* M = c.mat(which);
+  static __device__ __forceinline__ void row_times(const Ctx& c, int which, const real (&a)[D], real (&y)[D]) {
+    const real* M = c.mat(which);
 #pragma unroll
     for (int j = 0; j < D; ++j) y[j] = 0.0;
 #pragma unroll
@@ -174,14 +160,14 @@ struct TreeLane {
     }
   }
   // y[c] = sum_k M1[k][col] * M2[k][c]   (column `col` of M1, transposed, times M2)
-  static __device__ __forceinline__ void col_times(const Ctx& c, int which1, int col, int which2, double (&y)[D]) {
-    const double* M1 = c.mat(which1);
-    const double* M2 = c.mat(which2);
+  static __device__ __forceinline__ void col_times(const Ctx& c, int which1, int col, int which2, real (&y)[D]) {
+    const real* M1 = c.mat(which1);
+    const real* M2 = c.mat(which2);
 #pragma unroll
     for (int j = 0; j < D; ++j) y[j] = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const double a = M1[k * LDM + col];
+      const real a = M1[k * LDM + col];
 #pragma unroll
       for (int j = 0; j < D; ++j) y[j] = fma(a, M2[k * LDM + j], y[j]);
     }
@@ -189,13 +175,13 @@ struct TreeLane {
   // Operand loads go to L2 (ld.global.cg): inside a dataflow sweep (k_tree_flow) the operands were written by other
   // SMs during the SAME kernel, and a node's first/last cache line can be shared with its neighbour's, so a line
   // cached in L1 by an earlier read may be stale.  (Per-level launches read L2-resident data anyway.)
-  static __device__ __forceinline__ double ldg(const double* p) { return __ldcg(p); }
-  static __device__ __forceinline__ void load_row(const double* p, double (&x)[D]) {
+  static __device__ __forceinline__ real ldg(const real* p) { return __ldcg(p); }
+  static __device__ __forceinline__ void load_row(const real* p, real (&x)[D]) {
     if constexpr (D % 2 == 0) {
-      const double2* p2 = reinterpret_cast<const double2*>(p);
+      const real2* p2 = reinterpret_cast<const real2*>(p);
 #pragma unroll
       for (int j = 0; j < D / 2; ++j) {
-        const double2 v = __ldcg(p2 + j);
+        const real2 v = __ldcg(p2 + j);
         x[2 * j] = v.x;
         x[2 * j + 1] = v.y;
       }
@@ -204,7 +190,7 @@ struct TreeLane {
       for (int j = 0; j < D; ++j) x[j] = __ldcg(p + j);
     }
   }
-  static __device__ __forceinline__ void store_row_tri(double* __restrict__ p, int row, const double* x) {
+  static __device__ __forceinline__ void store_row_tri(real* __restrict__ p, int row, const real* x) {
 #pragma unroll
     for (int j = 0; j < D; ++j) p[j] = (j <= row) ? x[j] : 0.0;
   }
@@ -213,28 +199,28 @@ struct TreeLane {
   // (rows [0,D) use pivot lane I, rows [D,2D) use pivot lane D+I) when DUAL, else a single matrix whose rows are the
   // lanes [0, NR)
   template <int I, int NC, int NPIV, bool DUAL>
-  static __device__ __forceinline__ void tria_step(Ctx& cx, double (&x)[NC]) {
+  static __device__ __forceinline__ void tria_step(Ctx& cx, real (&x)[NC]) {
     if constexpr (I < NPIV && I + 1 < NC) {
       constexpr int n = NC - I;
-      double mine[n], piv[n];
+      real mine[n], piv[n];
 #pragma unroll
       for (int j = I; j < NC; ++j) mine[j - I] = x[j];
       const bool second = DUAL && cx.r >= D;
       if (DUAL) {
         // both halves publish into their own slot; each lane reads its half's slot
-        double2* s0 = reinterpret_cast<double2*>(cx.sm + cx.nmat * MAT + (0 + cx.flip) * BCW);
-        double2* s1 = reinterpret_cast<double2*>(cx.sm + cx.nmat * MAT + (2 + cx.flip) * BCW);
+        real2* s0 = reinterpret_cast<real2*>(cx.sm + cx.nmat * MAT + (0 + cx.flip) * BCW);
+        real2* s1 = reinterpret_cast<real2*>(cx.sm + cx.nmat * MAT + (2 + cx.flip) * BCW);
         if (cx.r == I || cx.r == D + I) {
-          double2* s = second ? s1 : s0;
+          real2* s = second ? s1 : s0;
 #pragma unroll
-          for (int j = 0; j + 1 < n; j += 2) s[j / 2] = make_double2(mine[j], mine[j + 1]);
-          if (n % 2) s[n / 2] = make_double2(mine[n - 1], 0.0);
+          for (int j = 0; j + 1 < n; j += 2) s[j / 2] = make_real2(mine[j], mine[j + 1]);
+          if (n % 2) s[n / 2] = make_real2(mine[n - 1], 0.0);
         }
         cx.sync();
-        const double2* s = second ? s1 : s0;
+        const real2* s = second ? s1 : s0;
 #pragma unroll
         for (int j = 0; j + 1 < n; j += 2) {
-          const double2 v = s[j / 2];
+          const real2 v = s[j / 2];
           piv[j] = v.x;
           piv[j + 1] = v.y;
         }
@@ -245,7 +231,7 @@ struct TreeLane {
         cx.flip ^= 1;
       }
       const HH h = house<n - 1>(piv[0], piv + 1);
-      double w = fma(h.s, x[I], dotn<NC - I - 1>(&x[I + 1], piv + 1));  // the dot does not wait for the reflector
+      real w = fma(h.s, x[I], dotn<NC - I - 1>(&x[I + 1], piv + 1));  // the dot does not wait for the reflector
       const int rr = second ? cx.r - D : cx.r;
       w = (rr >= I) ? w * h.tp : 0.0;
       x[I] = (rr == I) ? h.beta : fma(-w, h.s, x[I]);
@@ -258,36 +244,36 @@ struct TreeLane {
   // ------------------------------------------------------------------------------------------- filtering operator
   // e1: earlier (packed element, or packed state when STATE), e2: later element; out: element, or state when STATE
   template <bool STATE>
-  static __device__ __forceinline__ void filter_combine(Ctx& cx, const double* __restrict__ e1,
-                                                        const double* __restrict__ e2, double* __restrict__ out) {
+  static __device__ __forceinline__ void filter_combine(Ctx& cx, const real* __restrict__ e1,
+                                                        const real* __restrict__ e2, real* __restrict__ out) {
     constexpr int DD = D * D;
     const int r = cx.r;
     const bool top = r < D;
     const bool bot = r >= D && r < W2;
     const int rr = top ? r : (bot ? r - D : 0);
     // element pointers
-    const double* A1 = e1;
-    const double* b1 = STATE ? e1 : e1 + DD;
-    const double* U1 = STATE ? e1 + D : e1 + DD + D;
-    const double* n1 = e1 + 2 * DD + D;
-    const double* Z1 = e1 + 2 * DD + 2 * D;
-    const double* A2 = e2;
-    const double* b2 = e2 + DD;
-    const double* U2 = e2 + DD + D;
-    const double* n2 = e2 + 2 * DD + D;
-    const double* Z2 = e2 + 2 * DD + 2 * D;
+    const real* A1 = e1;
+    const real* b1 = STATE ? e1 : e1 + DD;
+    const real* U1 = STATE ? e1 + D : e1 + DD + D;
+    const real* n1 = e1 + 2 * DD + D;
+    const real* Z1 = e1 + 2 * DD + 2 * D;
+    const real* A2 = e2;
+    const real* b2 = e2 + DD;
+    const real* U2 = e2 + DD + D;
+    const real* n2 = e2 + 2 * DD + D;
+    const real* Z2 = e2 + 2 * DD + 2 * D;
 
     // ALL global operands are loaded here, in one round of independent loads: every later load would sit behind a
     // __syncwarp (a memory barrier the compiler cannot hoist loads across) and cost its own L2 round trip (~0.4 us)
     // on the dependent chain of the sweep -- five such round trips per combine before this was hoisted.
-    double u1[D], z2[D], a1[D], a2[D], q2[D];
+    real u1[D], z2[D], a1[D], a2[D], q2[D];
     load_row(U1 + rr * D, u1);
     load_row(Z2 + rr * D, z2);
     if (!STATE) load_row(A1 + rr * D, a1);
     load_row(A2 + rr * D, a2);
     load_row((bot && !STATE) ? Z1 + rr * D : U2 + rr * D, q2);
-    const double b1r = ldg(b1 + rr), n2r = ldg(n2 + rr), b2r = ldg(b2 + rr);
-    double n1r = 0.0;
+    const real b1r = ldg(b1 + rr), n2r = ldg(n2 + rr), b2r = ldg(b2 + rr);
+    real n1r = 0.0;
     if (!STATE) n1r = ldg(n1 + rr);
     // stage U1, Z2 (and A1): lanes [0,D) publish U1 rows, lanes [D,2D) publish Z2 rows
     if (top) put_row(cx, mU1, rr, u1);
@@ -297,9 +283,9 @@ struct TreeLane {
     }
     cx.sync();
     // Xi rows: top r: [ (U1^T Z2)[r,:], e_r ] ; bottom r: [ Z2[r,:], 0 ]
-    double x[W2];
+    real x[W2];
     {
-      double y[D];
+      real y[D];
       col_times(cx, mU1, rr, mZ2, y);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
@@ -313,7 +299,7 @@ struct TreeLane {
     tria_step<0, W2, D, false>(cx, x);
     // publish Xi11 (lanes top), Xi21 and B (lanes bottom)
     {
-      double lo[D], hi[D];
+      real lo[D], hi[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         lo[j] = x[j];
@@ -331,12 +317,12 @@ struct TreeLane {
     }
     cx.sync();
     // Y row r = U1[r,:] Xi11^{-T}  (forward substitution), lanes top (others compute harmlessly on row rr)
-    double y[D];
+    real y[D];
     {
-      const double* X11 = cx.mat(mX11);
+      const real* X11 = cx.mat(mX11);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        double acc = u1[j];
+        real acc = u1[j];
 #pragma unroll
         for (int i = 0; i < j; ++i) acc = fma(-y[i], X11[j * LDM + i], acc);
         y[j] = acc * fast_rcp(X11[j * LDM + j]);
@@ -344,12 +330,12 @@ struct TreeLane {
     }
     if (top) put_row(cx, mY, rr, y);
     // G row r = e_r - Y[r,:] Xi21^T
-    double g[D];
+    real g[D];
     {
-      const double* X21 = cx.mat(mX21);
+      const real* X21 = cx.mat(mX21);
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        double acc = (c == rr) ? 1.0 : 0.0;
+        real acc = (c == rr) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) acc = fma(-y[k], X21[c * LDM + k], acc);
         g[c] = acc;
@@ -359,34 +345,34 @@ struct TreeLane {
     cx.sync();
     // ---- b = A2 G (b1 + U1 U1^T eta2) + b2
     {
-      double v[D], t[D];
+      real v[D], t[D];
       allgather<D>(cx, top ? n2r : 0.0, v);
       // (U1^T eta2)[rr]: column rr of U1
-      double s = 0.0;
-      const double* MU = cx.mat(mU1);
+      real s = 0.0;
+      const real* MU = cx.mat(mU1);
 #pragma unroll
       for (int k = 0; k < D; ++k) s = fma(MU[k * LDM + rr], v[k], s);
       allgather<D>(cx, s, t);
-      double t0 = b1r;
+      real t0 = b1r;
 #pragma unroll
       for (int k = 0; k < D; ++k) t0 = fma(u1[k], t[k], t0);
       allgather<D>(cx, t0, v);
-      double t2 = 0.0;
+      real t2 = 0.0;
 #pragma unroll
       for (int k = 0; k < D; ++k) t2 = fma(g[k], v[k], t2);
       allgather<D>(cx, t2, t);
-      double bo = b2r;
+      real bo = b2r;
 #pragma unroll
       for (int k = 0; k < D; ++k) bo = fma(a2[k], t[k], bo);
       if (top) (STATE ? out : out + DD)[rr] = bo;
     }
     // ---- rows for the second triangularisation: top: [A2 Y | U2] -> U ; bottom: [A1^T Xi22 | Z1] -> Z
-    double x2[W2];
+    real x2[W2];
     {
-      double p[D];
+      real p[D];
       row_times(cx, mY, a2, p);
       if (!STATE) {
-        double pz[D];
+        real pz[D];
         col_times(cx, mA1, rr, mX22, pz);
 #pragma unroll
         for (int j = 0; j < D; ++j) p[j] = bot ? pz[j] : p[j];
@@ -399,7 +385,7 @@ struct TreeLane {
     }
     if (!STATE) {
       // ---- A = A2 (G A1)
-      double pr[D], ao[D];
+      real pr[D], ao[D];
       row_times(cx, mA1, g, pr);
       if (top) put_row(cx, mP, rr, pr);
       cx.sync();
@@ -409,24 +395,24 @@ struct TreeLane {
         for (int j = 0; j < D; ++j) out[rr * D + j] = ao[j];
       }
       // ---- eta = A1^T G^T (eta2 - Z2 Z2^T b1) + eta1
-      double v[D], t[D];
+      real v[D], t[D];
       allgather<D>(cx, top ? b1r : 0.0, v);
-      double s = 0.0;
-      const double* MZ = cx.mat(mZ2);
+      real s = 0.0;
+      const real* MZ = cx.mat(mZ2);
 #pragma unroll
       for (int k = 0; k < D; ++k) s = fma(MZ[k * LDM + rr], v[k], s);  // (Z2^T b1)[rr]
       allgather<D>(cx, s, t);
-      double s0 = n2r;
+      real s0 = n2r;
 #pragma unroll
       for (int k = 0; k < D; ++k) s0 = fma(-MZ[rr * LDM + k], t[k], s0);  // eta2 - Z2 (Z2^T b1)
       allgather<D>(cx, s0, v);
-      double s2 = 0.0;
-      const double* MG = cx.mat(mG);
+      real s2 = 0.0;
+      const real* MG = cx.mat(mG);
 #pragma unroll
       for (int k = 0; k < D; ++k) s2 = fma(MG[k * LDM + rr], v[k], s2);  // (G^T s)[rr]
       allgather<D>(cx, s2, t);
-      double eo = n1r;
-      const double* MA = cx.mat(mA1);
+      real eo = n1r;
+      const real* MA = cx.mat(mA1);
 #pragma unroll
       for (int k = 0; k < D; ++k) eo = fma(MA[k * LDM + rr], t[k], eo);  // (A1^T .)[rr]
       if (top) out[2 * DD + D + rr] = eo;
@@ -443,32 +429,32 @@ struct TreeLane {
   //    x_s | y_{1:e-1} ~ N(m', Y Y^T),  Y = L Xi11^{-T},  m' = G (m + L L^T eta)      (as in the filtering operator)
   //    tria([[A Y, U],[Y, 0]]) = [[Phi11, 0],[Phi21, Phi22]],  E = Phi21 Phi11^{-1},  g = m' - E (A m' + b),  Dm = Phi22
   // One such op per chunk replaces L-1 per-step compositions inside the filter scan.
-  static __device__ __forceinline__ void chunk_kernel(Ctx& cx, const double* __restrict__ st,
-                                                      const double* __restrict__ e2, double* __restrict__ out) {
+  static __device__ __forceinline__ void chunk_kernel(Ctx& cx, const real* __restrict__ st,
+                                                      const real* __restrict__ e2, real* __restrict__ out) {
     constexpr int DD = D * D;
     const int r = cx.r;
     const bool top = r < D;
     const bool bot = r >= D && r < W2;
     const int rr = top ? r : (bot ? r - D : 0);
-    const double* b1 = st;
-    const double* U1 = st + D;
-    const double* A2 = e2;
-    const double* b2 = e2 + DD;
-    const double* U2 = e2 + DD + D;
-    const double* n2 = e2 + 2 * DD + D;
-    const double* Z2 = e2 + 2 * DD + 2 * D;
-    double u1[D], z2[D], a2[D], q2[D];
+    const real* b1 = st;
+    const real* U1 = st + D;
+    const real* A2 = e2;
+    const real* b2 = e2 + DD;
+    const real* U2 = e2 + DD + D;
+    const real* n2 = e2 + 2 * DD + D;
+    const real* Z2 = e2 + 2 * DD + 2 * D;
+    real u1[D], z2[D], a2[D], q2[D];
     load_row(U1 + rr * D, u1);
     load_row(Z2 + rr * D, z2);
     load_row(A2 + rr * D, a2);
     load_row(U2 + rr * D, q2);
-    const double b1r = ldg(b1 + rr), n2r = ldg(n2 + rr), b2r = ldg(b2 + rr);
+    const real b1r = ldg(b1 + rr), n2r = ldg(n2 + rr), b2r = ldg(b2 + rr);
     if (top) put_row(cx, mU1, rr, u1);
     if (bot) put_row(cx, mZ2, rr, z2);
     cx.sync();
-    double x[W2];
+    real x[W2];
     {
-      double y0[D];
+      real y0[D];
       col_times(cx, mU1, rr, mZ2, y0);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
@@ -478,31 +464,31 @@ struct TreeLane {
     }
     tria_step<0, W2, D, false>(cx, x);
     {
-      double lo[D];
+      real lo[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) lo[j] = (top && j > rr) ? 0.0 : x[j];
       if (top) put_row(cx, mX11, rr, lo);
       if (bot) put_row(cx, mX21, rr, lo);
     }
     cx.sync();
-    double y[D];
+    real y[D];
     {
-      const double* X11 = cx.mat(mX11);
+      const real* X11 = cx.mat(mX11);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        double acc = u1[j];
+        real acc = u1[j];
 #pragma unroll
         for (int i = 0; i < j; ++i) acc = fma(-y[i], X11[j * LDM + i], acc);
         y[j] = acc * fast_rcp(X11[j * LDM + j]);
       }
     }
     if (top) put_row(cx, mY, rr, y);
-    double g[D];
+    real g[D];
     {
-      const double* X21 = cx.mat(mX21);
+      const real* X21 = cx.mat(mX21);
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        double acc = (c == rr) ? 1.0 : 0.0;
+        real acc = (c == rr) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) acc = fma(-y[k], X21[c * LDM + k], acc);
         g[c] = acc;
@@ -510,32 +496,32 @@ struct TreeLane {
     }
     cx.sync();
     // m' = G (m + L L^T eta)  and  v = A m' + b
-    double mp[D], vf[D];
+    real mp[D], vf[D];
     {
-      double v[D], t[D];
+      real v[D], t[D];
       allgather<D>(cx, top ? n2r : 0.0, v);
-      double s = 0.0;
-      const double* MU = cx.mat(mU1);
+      real s = 0.0;
+      const real* MU = cx.mat(mU1);
 #pragma unroll
       for (int k = 0; k < D; ++k) s = fma(MU[k * LDM + rr], v[k], s);
       allgather<D>(cx, s, t);
-      double t0 = b1r;
+      real t0 = b1r;
 #pragma unroll
       for (int k = 0; k < D; ++k) t0 = fma(u1[k], t[k], t0);
       allgather<D>(cx, t0, v);
-      double t2 = 0.0;
+      real t2 = 0.0;
 #pragma unroll
       for (int k = 0; k < D; ++k) t2 = fma(g[k], v[k], t2);
       allgather<D>(cx, t2, mp);
-      double av = b2r;
+      real av = b2r;
 #pragma unroll
       for (int k = 0; k < D; ++k) av = fma(a2[k], mp[k], av);
       allgather<D>(cx, av, vf);
     }
     // joint array [[A Y, U],[Y, 0]]
-    double x2[W2];
+    real x2[W2];
     {
-      double p[D];
+      real p[D];
       row_times(cx, mY, a2, p);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
@@ -545,7 +531,7 @@ struct TreeLane {
     }
     tria_step<0, W2, W2, false>(cx, x2);
     {
-      double lo[D];
+      real lo[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) lo[j] = (j <= rr) ? x2[j] : 0.0;
       cx.sync();
@@ -553,19 +539,19 @@ struct TreeLane {
       cx.sync();
     }
     // E row (bottom lanes): e Phi11 = phi21  (backward substitution over the columns)
-    double e[D];
+    real e[D];
     {
-      const double* P11 = cx.mat(mX11);
+      const real* P11 = cx.mat(mX11);
 #pragma unroll
       for (int j = D - 1; j >= 0; --j) {
-        double acc = x2[j];
+        real acc = x2[j];
 #pragma unroll
         for (int i = j + 1; i < D; ++i) acc = fma(-e[i], P11[i * LDM + j], acc);
         e[j] = acc * fast_rcp(P11[j * LDM + j]);
       }
     }
     if (bot) {
-      double go = 0.0;
+      real go = 0.0;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         go = (k == rr) ? mp[k] : go;
@@ -582,44 +568,44 @@ struct TreeLane {
   // ------------------------------------------------------------------------------------------- smoothing operator
   // e1: LATER (packed element, or packed state when STATE), e2: EARLIER element.  GS lanes, lane r owns row r.
   template <bool STATE>
-  static __device__ __forceinline__ void smooth_combine(Ctx& cx, const double* __restrict__ e1,
-                                                        const double* __restrict__ e2, double* __restrict__ out) {
+  static __device__ __forceinline__ void smooth_combine(Ctx& cx, const real* __restrict__ e1,
+                                                        const real* __restrict__ e2, real* __restrict__ out) {
     constexpr int DD = D * D;
     const int r = cx.r;
     const bool act = r < D;
     const int rr = act ? r : 0;
-    const double* g1 = e1;
-    const double* E1 = e1 + D;
-    const double* D1 = STATE ? e1 + D : e1 + D + DD;
-    const double* g2 = e2;
-    const double* E2 = e2 + D;
-    const double* D2 = e2 + D + DD;
-    double row[D], row1[D], e2r[D], d2[D], v[D];
+    const real* g1 = e1;
+    const real* E1 = e1 + D;
+    const real* D1 = STATE ? e1 + D : e1 + D + DD;
+    const real* g2 = e2;
+    const real* E2 = e2 + D;
+    const real* D2 = e2 + D + DD;
+    real row[D], row1[D], e2r[D], d2[D], v[D];
     load_row(D1 + rr * D, row);
     if (!STATE) load_row(E1 + rr * D, row1);
     load_row(E2 + rr * D, e2r);
     load_row(D2 + rr * D, d2);
-    const double g1r = ldg(g1 + rr), g2r = ldg(g2 + rr);
+    const real g1r = ldg(g1 + rr), g2r = ldg(g2 + rr);
     if (act) put_row(cx, sD1, rr, row);
     if (!STATE) {
       if (act) put_row(cx, sE1, rr, row1);
     }
     allgather<D>(cx, act ? g1r : 0.0, v);  // also orders the put_rows before the reads below
-    double go = g2r;
+    real go = g2r;
 #pragma unroll
     for (int k = 0; k < D; ++k) go = fma(e2r[k], v[k], go);
     if (act) out[rr] = go;
     if (!STATE) {
-      double eo[D];
+      real eo[D];
       row_times(cx, sE1, e2r, eo);
       if (act) {
 #pragma unroll
         for (int j = 0; j < D; ++j) out[D + rr * D + j] = eo[j];
       }
     }
-    double x[W2];
+    real x[W2];
     {
-      double p[D];
+      real p[D];
       row_times(cx, sD1, e2r, p);
 #pragma unroll
       for (int j = 0; j < D; ++j) {
@@ -632,4 +618,4 @@ struct TreeLane {
   }
 };
 
-}  // namespace pof
+}  // namespace POF_NS

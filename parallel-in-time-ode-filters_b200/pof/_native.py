@@ -98,6 +98,10 @@ def _load():
         "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_prior_init_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
     }
+    # the optional fp32 mode: the register-resident kernels compiled with the scalar type float export the same entry
+    # points with the suffix _f32 (same argument lists; device arrays are float, host-side arguments stay double)
+    for name in F32_ENTRY_POINTS:
+        sig[name] = sig[name[:-4] + "_f64"] if name != "pof_workspace_bytes_f32" else sig["pof_workspace_bytes"]
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
@@ -105,6 +109,13 @@ def _load():
     return lib
 
 
+F32_ENTRY_POINTS = [
+    "pof_workspace_bytes_f32", "pof_filter_combine_f32", "pof_smooth_combine_f32", "pof_linearize_ivp_f32",
+    "pof_linearize_ivp_compact_f32", "pof_linear_filtsmooth_f32", "pof_ieks_iteration_f32", "pof_shard_stage_a_f32",
+    "pof_shard_stage_b_f32", "pof_shard_stage_a_compact_f32", "pof_shard_stage_b_compact_f32", "pof_shard_stage_c_f32",
+    "pof_shard_exchange_filter_f32", "pof_shard_exchange_smooth_f32", "pof_shard_exchange_scalars_f32",
+    "pof_prior_init_f32", "pof_project_f32",
+]
 LIB = _load()
 EXPORTED = [
     "pof_supported", "pof_supported_tile", "pof_ctx_create", "pof_ctx_destroy", "pof_ctx_profile_enable",
@@ -116,7 +127,16 @@ EXPORTED = [
     "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64", "pof_project_f64", "pof_prior_init_f64",
     "pof_shard_exchange_supported", "pof_shard_exchange_filter_f64", "pof_shard_exchange_smooth_f64",
     "pof_shard_exchange_scalars_f64",
-]
+] + F32_ENTRY_POINTS
+
+
+def fn(base, dtype):
+    """entry point `base`_f64 or `base`_f32 for a tensor dtype (fp32: the register-resident family only)"""
+    if dtype == torch.float64:
+        return getattr(LIB, base + "_f64")
+    if dtype == torch.float32:
+        return getattr(LIB, base + "_f32")
+    raise NativeError(f"unsupported dtype {dtype}")
 
 # kernel-family flags of the C ABI (include/pof_b200.h).  DEFAULT_FLAGS is what the facade passes; tests / scripts may
 # change it (e.g. F_FAMILY_TILE to run the large-state kernels on small problems) -- the library itself holds no
@@ -139,11 +159,17 @@ def check(rc, what):
 
 
 def require_cuda(*tensors):
+    dt = None
     for t in tensors:
         if t is None:
             continue
-        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
-            raise NativeError("pof_b200 kernels need contiguous float64 CUDA tensors (there is no CPU fallback)")
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in (torch.float64, torch.float32)
+                and t.is_contiguous()):
+            raise NativeError("pof_b200 kernels need contiguous float64 (or, fp32 mode, float32) CUDA tensors "
+                              "(there is no CPU fallback)")
+        if dt is not None and t.dtype != dt:
+            raise NativeError("all arrays of a call must have the same dtype")
+        dt = t.dtype
 
 
 def ptr(t):
@@ -218,9 +244,11 @@ class Workspace:
     _cache = {}
     _CACHE_MAX = 4
 
-    def __init__(self, N, d, q, chunk_len, device):
+    def __init__(self, N, d, q, chunk_len, device, dtype=torch.float64):
         self.N, self.d, self.q, self.chunk_len = int(N), int(d), int(q), int(chunk_len)
-        self.nbytes = int(LIB.pof_workspace_bytes(self.N, self.d, self.q, self.chunk_len))
+        self.dtype = dtype
+        wsb = LIB.pof_workspace_bytes if dtype == torch.float64 else LIB.pof_workspace_bytes_f32
+        self.nbytes = int(wsb(self.N, self.d, self.q, self.chunk_len))
         self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         self.ctx = Context(device)  # side stream + events of the passes that use this workspace
 
@@ -228,18 +256,18 @@ class Workspace:
     def ws_ptr(self):
         return ctypes.c_void_p(self.buf.data_ptr())
 
-    def matches(self, N, d, q, chunk_len):
-        return (self.N, self.d, self.q, self.chunk_len) == (int(N), int(d), int(q), int(chunk_len))
+    def matches(self, N, d, q, chunk_len, dtype=torch.float64):
+        return (self.N, self.d, self.q, self.chunk_len, self.dtype) == (int(N), int(d), int(q), int(chunk_len), dtype)
 
     @classmethod
-    def get(cls, N, d, q, chunk_len, device):
+    def get(cls, N, d, q, chunk_len, device, dtype=torch.float64):
         stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
-        key = (int(N), int(d), int(q), int(chunk_len), str(device), int(stream))
+        key = (int(N), int(d), int(q), int(chunk_len), str(device), int(stream), str(dtype))
         ws = cls._cache.pop(key, None)
         if ws is None:
             while len(cls._cache) >= cls._CACHE_MAX:
                 cls._cache.pop(next(iter(cls._cache)))  # least recently used; holders keep their own reference
-            ws = cls(N, d, q, chunk_len, device)
+            ws = cls(N, d, q, chunk_len, device, dtype)
         cls._cache[key] = ws  # most recently used last
         return ws
 

@@ -57,14 +57,17 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
     dev = means_io.device
     if chunk_len is None:
         chunk_len = (nat.default_chunk_len_tile if general else nat.default_chunk_len)(N, d, q, dev.index)
+    dt = means_io.dtype
     if ws is None:
-        ws = nat.Workspace.get(N, d, q, chunk_len, dev)
-    elif not ws.matches(N, d, q, chunk_len):
+        ws = nat.Workspace.get(N, d, q, chunk_len, dev, dt)
+    elif not ws.matches(N, d, q, chunk_len, dt):
         raise nat.NativeError("workspace was created for a different problem shape")
     if scalars is None:
-        scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+        scalars = torch.zeros(nat.NSCALARS, dtype=dt, device=dev)
     qLh, qLp = nat.host_doubles(qL)
     if general:
+        if dt != torch.float64:
+            raise nat.NativeError("noisy observations / general transition models: fp64 only (large-state kernels)")
         rc = nat.LIB.pof_linear_filtsmooth_general_f64(
             nat.stream_ptr(), ws.ctx.ptr, nat.flags(), N, d, q, int(chunk_len), qLp, nat.ptr(Fd), nat.ptr(QLd), nat.ptr(x0.mean),
             nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c), nat.ptr(cholR), nat.ptr(means_io), nat.ptr(chols),
@@ -72,7 +75,7 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
             ws.ws_ptr, ws.nbytes)
         nat.check(rc, "pof_linear_filtsmooth_general_f64")
         return scalars
-    rc = nat.LIB.pof_linear_filtsmooth_f64(
+    rc = nat.fn("pof_linear_filtsmooth", dt)(
         nat.stream_ptr(), ws.ctx.ptr, nat.flags(), N, d, q, int(chunk_len), qLp, nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(H), nat.ptr(c),
         nat.ptr(means_io), nat.ptr(chols), nat.ptr(fmeans), nat.ptr(fchols), int(bool(calibrate)), nat.ptr(scalars),
         ws.ws_ptr, ws.nbytes)
@@ -89,16 +92,17 @@ def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len
     dev = means_io.device
     if chunk_len is None:
         chunk_len = nat.default_chunk_len(N, d, q, dev.index)
+    dt = means_io.dtype
     if ws is None:
-        ws = nat.Workspace.get(N, d, q, chunk_len, dev)
-    elif not ws.matches(N, d, q, chunk_len):
+        ws = nat.Workspace.get(N, d, q, chunk_len, dev, dt)
+    elif not ws.matches(N, d, q, chunk_len, dt):
         raise nat.NativeError("workspace was created for a different problem shape")
     if scalars is None:
-        scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+        scalars = torch.zeros(nat.NSCALARS, dtype=dt, device=dev)
     ivp_id, params = lin["builtin"]
     ph, pp = nat.host_doubles(list(params) + [0.0])
     qLh, qLp = nat.host_doubles(qL)
-    rc = nat.LIB.pof_ieks_iteration_f64(
+    rc = nat.fn("pof_ieks_iteration", dt)(
         nat.stream_ptr(), ws.ctx.ptr, nat.flags(), ivp_id, pp, len(params), N, d, q, int(chunk_len), qLp, lin["scale0"], lin["scale1"],
         nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(means_io), nat.ptr(chols), int(bool(calibrate)),
         nat.ptr(scalars), ws.ws_ptr, ws.nbytes)
@@ -117,7 +121,7 @@ class GraphedIteration:
         if chunk_len is None:
             chunk_len = nat.default_chunk_len(N, lin["d"], lin["q"], dev.index)
         # the graph bakes the workspace address in: this object owns the workspace for as long as it lives
-        self.ws = nat.Workspace(N, lin["d"], lin["q"], chunk_len, dev)
+        self.ws = nat.Workspace(N, lin["d"], lin["q"], chunk_len, dev, means.dtype)
         self.kw = dict(calibrate=calibrate, chunk_len=chunk_len, scalars=scalars, ws=self.ws)
         self.graph = None
 

@@ -136,7 +136,10 @@ class ShardedPass:
         z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)
         self.carry_f, self.gather_f = z(self.FE), z(self.world * self.FE)
         self.state_in, self.seed = z(self.ST), z(self.ST)
-        self.pay_b, self.gather_b = z(self.SE + self.ST + 3), z(self.world * (self.SE + self.ST + 3))
+        # payload of the second exchange: [smoothing carry SE | end state ST | 3 partial sums | 1 pad]: an EVEN number of
+        # doubles, so that every rank's slot in the gathered buffer stays 16-byte aligned (the kernels use 128-bit loads)
+        self.PB = self.SE + self.ST + 4
+        self.pay_b, self.gather_b = z(self.PB), z(self.world * self.PB)
         self.pay_c, self.gather_c = z(2), z(self.world * 2)
         self.cscale = z(1)
         self.x0_state = z(self.ST)
@@ -169,10 +172,10 @@ class ShardedPass:
         shift = 0 if self.has_row0 else 1  # local row of state t' is t' - shift
         fm = None if fmeans is None else fmeans
         be.stage_b(H_loc, c_loc, self.state_in, _shifted(fm, shift, D), _shifted(fchols, shift, D * D), pb[:SE],
-                   pb[SE:SE + ST], pb[SE + ST:])
+                   pb[SE:SE + ST], pb[SE + ST:SE + ST + 3])
         self._all_gather(self.gather_b, pb)
-        gb = self.gather_b.view(W, SE + ST + 3)
-        sums = gb[:, SE + ST:].sum(dim=0)  # same order on every rank -> bitwise identical scalars
+        gb = self.gather_b.view(W, self.PB)
+        sums = gb[:, SE + ST:SE + ST + 3].sum(dim=0)  # same order on every rank -> bitwise identical scalars
         nll = sums[0]
         ssq = sums[1] / self.n / self.d
         ssq_proper = sums[2] / self.n / self.d
@@ -215,13 +218,13 @@ def _phase_b(self, st):
         fchols[0].copy_(x0_chol)
     shift = 0 if self.has_row0 else 1
     self.backend.stage_b(H_loc, c_loc, self.state_in, _shifted(fmeans, shift, D), _shifted(fchols, shift, D * D),
-                         pb[:SE], pb[SE:SE + ST], pb[SE + ST:])
+                         pb[:SE], pb[SE:SE + ST], pb[SE + ST:SE + ST + 3])
 
 
 def _phase_c(self, st):
     means_loc, chols_loc, calibrate = st[4], st[5], st[6]
     D, SE, ST, W, r = self.D, self.SE, self.ST, self.world, self.rank
-    self.backend.exchange_smooth(D, self.d, r, W, self.n, calibrate, self.gather_b, SE + ST + 3, self.seed,
+    self.backend.exchange_smooth(D, self.d, r, W, self.n, calibrate, self.gather_b, self.PB, self.seed,
                                  self.cscale, self.scalars)
     self.backend.stage_c(self.seed, r == W - 1, self.has_row0, self.cscale, means_loc, chols_loc, self.pay_c)
 

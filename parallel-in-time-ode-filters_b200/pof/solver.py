@@ -12,23 +12,33 @@ from .step import linearize_into
 from .utils import MVNSqrt
 
 
-def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, sequential=False, chunk_len=None):
+def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, sequential=False, chunk_len=None,
+          dtype=torch.float64):
     """reference solver.py:11-73.  The IEKS loop keeps every array on the device; per iteration the host reads back
-    five scalars (nll, obj, sigma^2, #means not close, NaN state) to evaluate the reference's stopping rule."""
+    five scalars (nll, obj, sigma^2, #means not close, NaN state) to evaluate the reference's stopping rule.
+
+    dtype=torch.float32 selects the optional fp32 mode (the reference without JAX_ENABLE_X64): the set-up stays fp64,
+    the iterations run the fp32 build of the register-resident kernels (built-in `pof.ivp` problems with D <= 16);
+    results are float32 tensors.  The mean-convergence rule keeps the reference's absolute tolerance 1e-8, which fp32
+    cannot meet: the loop then ends on the objective rule (rtol 1e-6) or `maxiters`."""
     setup = set_up_solver(f=f, y0=y0, ts=ts, order=order)
     x0, om, dev = setup["x0"], setup["om"], setup["_device"]
     lin = om.f._pof_lin
     d, q = lin["d"], order
     states = get_initial_trajectory(setup, method=init, means_only=True)
+    if dtype != torch.float64:
+        if lin["builtin"] is None or sequential:
+            raise NotImplementedError("fp32 mode: built-in pof.ivp vector fields, parallel pass only")
+        x0 = MVNSqrt(x0.mean.to(dtype), x0.chol.to(dtype))
 
-    means = states.mean.contiguous()
+    means = states.mean.to(dtype).contiguous()
     N, D = means.shape
     n = N - 1
-    chols = torch.empty((N, D, D), dtype=torch.float64, device=dev)
+    chols = torch.empty((N, D, D), dtype=dtype, device=dev)
     if lin["builtin"] is None:
         H = torch.empty((n, d, D), dtype=torch.float64, device=dev)
         c = torch.empty((n, d), dtype=torch.float64, device=dev)
-    scalars = torch.zeros(nat.NSCALARS, dtype=torch.float64, device=dev)
+    scalars = torch.zeros(nat.NSCALARS, dtype=dtype, device=dev)
     if sequential:
         chunk_len = n
     elif chunk_len is None:
@@ -72,10 +82,10 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
     if calibrate:
         info_dict["calibrated"] = True
     # final calibration (the second one, solver.py:66-69) fused with the E0 projection (solver.py:71)
-    ymean = torch.empty((N, d), dtype=torch.float64, device=dev)
-    ychol = torch.empty((N, d, D), dtype=torch.float64, device=dev)
+    ymean = torch.empty((N, d), dtype=dtype, device=dev)
+    ychol = torch.empty((N, d, D), dtype=dtype, device=dev)
     mult = scalars[nat.S_CSCALE:nat.S_CSCALE + 1] if calibrate else None
-    rc = nat.LIB.pof_project_f64(nat.stream_ptr(), N, d, q, setup["_scale0"], nat.ptr(mult), nat.ptr(means),
+    rc = nat.fn("pof_project", dtype)(nat.stream_ptr(), N, d, q, setup["_scale0"], nat.ptr(mult), nat.ptr(means),
                                  nat.ptr(chols), nat.ptr(ymean), nat.ptr(ychol))
     nat.check(rc, "pof_project_f64")
     return MVNSqrt(ymean, ychol), info_dict
