@@ -17,7 +17,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 2**20
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ivp = pof.ivp.fitzhughnagumo()
 setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=np.linspace(0, 100, N), order=3)
-st = get_initial_trajectory(setup, method="constant")
+st = get_initial_trajectory(setup, method="constant", means_only=True)
 lin = setup["om"].f._pof_lin
 means = st.mean.contiguous().clone()
 chols = torch.empty((N, 8, 8), dtype=torch.float64, device=means.device)

@@ -2,8 +2,9 @@
 
     python scripts/summarize_ncu.py <launch_list.csv> <full.ncu-rep> <tag> [<more.ncu-rep> ...]
 
-Also refreshes profiles/r01_traffic.json (dram bytes, FP64-pipe utilisation and LSU utilisation per kernel), which
-bench.py reads for `roofline.traffic` / `fp64_pipe_utilisation_ncu`.
+Also writes profiles/r02_ncu_kernels.json (dram bytes, FP64-pipe / LSU / issue utilisation per kernel) together with
+the hash of the kernel sources the capture was taken from: bench.py reports these counters (`roofline.frac`,
+`roofline.traffic`) only while that hash equals the hash of the sources the running library was built from.
 """
 import collections
 import csv
@@ -59,11 +60,25 @@ def num(v, unit=""):
     return x * scale
 
 
-traffic_path = os.path.join(out_dir, "r01_traffic.json")
+traffic_path = os.path.join(out_dir, "r02_ncu_kernels.json")
 try:
     traffic = json.load(open(traffic_path))
 except Exception:
     traffic = {}
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hashlib  # noqa: E402
+
+
+def kernel_source_hash():  # must equal bench.kernel_source_hash()
+    cs = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "parallel-in-time-ode-filters_b200",
+                      "csrc")
+    h = hashlib.sha256()
+    for f in ("pof_lane2.cuh", "pof_lane2_kernels.cuh", "pof_small.cuh"):
+        h.update(open(os.path.join(cs, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+traffic["kernel_source_hash"] = kernel_source_hash()
 seen = {}
 with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as fh:
     fh.write(f"# {tag}: ncu --set full --clock-control none, first launch of each kernel\n\n")
@@ -73,7 +88,7 @@ with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as fh:
         hdr, units = rr[0], rr[1]
         idx = {h: i for i, h in enumerate(hdr)}
         for r in rr[2:]:
-            name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("pof::", "")
+            name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("pof::", "").replace(" ", "")
             if name in seen:
                 continue
             seen[name] = 1
@@ -91,12 +106,13 @@ with open(f"{out_dir}/{tag}_ncu_full_summary.md", "w") as fh:
             g = lambda m: num(r[idx[m]], units[idx[m]])
             traffic[name] = {
                 "dram_bytes_read": g("dram__bytes_read.sum"), "dram_bytes_write": g("dram__bytes_write.sum"),
+                "dram_bytes": g("dram__bytes_read.sum") + g("dram__bytes_write.sum"),
                 "duration_ms_under_ncu": g("gpu__time_duration.sum"),
                 "fp64_pipe_pct": g("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
                 "lsu_pipe_pct": g("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                 "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                 "registers": g("launch__registers_per_thread"),
-                "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, N=2^20, FHN order 3)",
+                "source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full --clock-control none)",
             }
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 print("wrote", f"{out_dir}/{tag}_launch_shares.md", f"{out_dir}/{tag}_ncu_full_summary.md", traffic_path)
