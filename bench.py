@@ -343,6 +343,8 @@ def run_native(args):
             setup = dict(setup, x0=MVNSqrt(setup["x0"].mean.to(tdt), setup["x0"].chol.to(tdt)))
         return setup, row.repeat(rows, 1).to(tdt).contiguous(), k_lo, k_hi
 
+    exch = {"kind": "none (single GPU)"}
+
     def make_step(setup, means, chols, k_lo, k_hi, n_tot, calibrate=True):
         """-> (step callable returning the 5 scalars as a device tensor, graph object, chunk_len, launches, ctx)"""
         lin = setup["om"].f._pof_lin
@@ -378,6 +380,7 @@ def run_native(args):
             return out5
 
         fused = GraphedCall(eager)
+        exch["kind"] = sp.exchange
         L = sp.backend.chunk_len
         # linearise + the kernels of a pass + the separate up-sweep launch of stage A + the three exchange kernels
         launches = 1 + int(nat.LIB.pof_launches_per_pass(n_loc + 1, d_, q_, L, nat.flags())) + 1 + 3
@@ -586,7 +589,7 @@ def run_native(args):
                "sample": f"one oracle IEKS iteration (NumPy port of the reference, JAX association order, {cores} "
                          f"threads) at N={n_cpu}, MEASURED at that N (no extrapolation)", "n_time": n_cpu}
 
-    cfg = dict(workload_config(args, world, N_total), chunk_len=int(L), finite=finite,
+    cfg = dict(workload_config(args, world, N_total), chunk_len=int(L), finite=finite, exchange=exch["kind"],
                l2="working set per step (~3 GB at 2^20 points) exceeds L2 (126 MB); no explicit flush" if flush is None
                else "L2 flushed between timed iterations (a 252 MB buffer is written before each)")
     if its_to_converge is not None:

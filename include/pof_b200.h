@@ -24,6 +24,8 @@ extern "C" {
 
 typedef void* pof_stream_t; /* cudaStream_t */
 typedef struct pof_ctx pof_ctx_t; /* opaque: side stream + events of one (concurrently running) pass */
+typedef struct pof_p2p pof_p2p_t; /* opaque: peer-memory exchange area of one rank of a time-sharded run */
+#define POF_P2P_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
 
 /* flags (bitwise or) */
 #define POF_F_FAMILY_TILE 1u    /* use the large-state kernels (one CTA per chunk / tree node) even where the
@@ -231,6 +233,28 @@ int pof_shard_exchange_smooth_f64(pof_stream_t s, uint32_t flags, int D, int d, 
                                   int64_t n_steps_total, int calibrate, const double* gathered, int64_t stride,
                                   double* seed, double* scratch, double* cscale, double* scalars);
 int pof_shard_exchange_scalars_f64(pof_stream_t s, int world, const double* gathered, double* scalars);
+
+/* The same three exchanges over PEER MEMORY instead of a collective library (one process per GPU of one NVLink /
+ * NVSwitch box, world <= 8): every rank owns an exchange area (slots for the payloads of all ranks, double-buffered,
+ * plus flags); the exchange kernel stores this rank's payload into its slot of EVERY rank's area with plain stores
+ * over NVLink, releases a flag there, waits for the flags of the ranks it needs in its own area and folds -- compute
+ * and collective in ONE launch, no NCCL call, capturable into a CUDA graph.
+ *   pof_p2p_create  : allocates the local area (cudaMalloc: CUDA IPC handles refer to whole allocations) and returns
+ *                     its IPC handle; the caller exchanges the world handles (any host-side mechanism)
+ *   pof_p2p_connect : opens the peers' areas (cudaIpcOpenMemHandle, enables peer access)
+ *   pof_p2p_status  : 0, or 1 if an exchange gave up waiting for a peer after ~2 s (it never hangs the GPU)
+ * payloads: filter = carry_f (3D^2+2D); smoother = [carry_s | state_end | partials (3) | pad] (2D^2+D + D+D*D + 4);
+ * scalars = (obj, not-close). */
+int pof_p2p_create(int rank, int world, int D, pof_p2p_t** out, unsigned char* handle_out /* POF_P2P_HANDLE_BYTES */);
+int pof_p2p_connect(pof_p2p_t* p, const unsigned char* handles /* world x POF_P2P_HANDLE_BYTES, rank order */);
+void pof_p2p_destroy(pof_p2p_t* p);
+int pof_p2p_status(pof_p2p_t* p, int* status_host);
+int pof_p2p_exchange_filter_f64(pof_stream_t s, uint32_t flags, pof_p2p_t* p, const double* carry_f,
+                                const double* x0_mean, const double* x0_chol, double* state_in, double* scratch);
+int pof_p2p_exchange_smooth_f64(pof_stream_t s, uint32_t flags, pof_p2p_t* p, int d, int64_t n_steps_total,
+                                int calibrate, const double* payload, double* seed, double* scratch, double* cscale,
+                                double* scalars);
+int pof_p2p_exchange_scalars_f64(pof_stream_t s, pof_p2p_t* p, const double* pair, double* scalars);
 
 /* state <- op(state, elems[0]), op(.., elems[1]), ... (count packed filter elements, earlier first) */
 int pof_filter_apply_chain_f64(pof_stream_t s, uint32_t flags, int D, int count, const double* state_in,

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -1133,6 +1134,145 @@ int POF_SUFFIX(pof_shard_exchange_scalars)(pof_stream_t s, int world, const real
 }
 
 #ifndef POF_F32
+// ---- peer-memory exchanges (CUDA IPC): every rank owns one exchange area; peers store their payloads into it over
+// NVLink and release a flag, the exchange kernel (k_exchange with A.p2p) pushes, waits and folds in ONE launch.
+struct pof_p2p {
+  int rank = 0, world = 1, D = 0;
+  unsigned long long* area = nullptr;     // local, cudaMalloc'ed (IPC handles refer to whole allocations)
+  unsigned long long* peer[8] = {nullptr};
+  size_t words = 0;
+  long stride[3] = {0, 0, 0};
+  long slot_word[3] = {0, 0, 0};
+};
+enum { P2P_FLAG0 = 8, P2P_SLOTS = 32 };
+
+int pof_p2p_create(int rank, int world, int D, pof_p2p_t** out, unsigned char* handle_out) {
+  if (!out || !handle_out || world < 1 || world > 8 || rank < 0 || rank >= world || D < 1) return POF_E_ARG;
+  pof_p2p* p = new pof_p2p();
+  p->rank = rank;
+  p->world = world;
+  p->D = D;
+  const long FE = 3L * D * D + 2 * D, SE = 2L * D * D + D, ST = (long)D * D + D;
+  p->stride[0] = FE;
+  p->stride[1] = SE + ST + 4;
+  p->stride[2] = 2;
+  long w = P2P_SLOTS;
+  for (int x = 0; x < 3; ++x) {
+    p->slot_word[x] = w;
+    w += 2L * world * p->stride[x];  // two parities
+    w = (w + 1) & ~1L;               // 16-byte aligned regions
+  }
+  p->words = (size_t)w;
+  cudaError_t e = cudaMalloc(&p->area, p->words * 8);
+  if (e == cudaSuccess) e = cudaMemset(p->area, 0, p->words * 8);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->area);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (p->area) cudaFree(p->area);
+    delete p;
+    return (int)e;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == POF_P2P_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  p->peer[rank] = p->area;
+  *out = p;
+  return 0;
+}
+// handles: world x POF_P2P_HANDLE_BYTES in rank order (exchanged by the caller with any host-side mechanism)
+int pof_p2p_connect(pof_p2p_t* p, const unsigned char* handles) {
+  if (!p || !handles) return POF_E_ARG;
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * POF_P2P_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return (int)e;
+    }
+    p->peer[r] = (unsigned long long*)ptr;
+  }
+  return 0;
+}
+void pof_p2p_destroy(pof_p2p_t* p) {
+  if (!p) return;
+  for (int r = 0; r < p->world; ++r)
+    if (r != p->rank && p->peer[r]) cudaIpcCloseMemHandle(p->peer[r]);
+  if (p->area) cudaFree(p->area);
+  delete p;
+}
+// 0 = ok, 1 = an exchange timed out waiting for a peer (synchronises the device)
+int pof_p2p_status(pof_p2p_t* p, int* status_host) {
+  if (!p || !status_host) return POF_E_ARG;
+  unsigned long long v = 0;
+  cudaError_t e = cudaMemcpy(&v, p->area, 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return (int)e;
+  *status_host = (int)v;
+  return 0;
+}
+static void p2p_fill(ExchangeArgs& A, const pof_p2p* p, int x, const real* payload) {
+  A.p2p = 1;
+  A.rank = p->rank;
+  A.world = p->world;
+  A.payload = payload;
+  A.stride = p->stride[x];
+  for (int r = 0; r < 8; ++r) A.peer[r] = r < p->world ? p->peer[r] : nullptr;
+  A.epoch_word = 1 + x;
+  A.flag_word = P2P_FLAG0 + 8 * x;
+  A.slot_word = p->slot_word[x];
+}
+int pof_p2p_exchange_filter_f64(pof_stream_t s, uint32_t flags, pof_p2p_t* p, const real* carry_f, const real* x0_mean,
+                                const real* x0_chol, real* state_in, real* scratch) {
+  if (!p) return POF_E_ARG;
+  if ((flags & POF_F_FAMILY_TILE) || tree_launch(p->D) == nullptr) return POF_E_UNSUPPORTED_DQ;
+  ExchangeArgs A = {};
+  p2p_fill(A, p, 0, carry_f);
+  A.x0_mean = x0_mean;
+  A.x0_chol = x0_chol;
+  A.state_out = state_in;
+  A.scratch = scratch;
+  return (int)tree_launch(p->D)->fexchange((cudaStream_t)s, A);
+}
+int pof_p2p_exchange_smooth_f64(pof_stream_t s, uint32_t flags, pof_p2p_t* p, int d, int64_t n_steps_total,
+                                int calibrate, const real* payload, real* seed, real* scratch, real* cscale,
+                                real* scalars) {
+  if (!p || !cscale) return POF_E_ARG;
+  if ((flags & POF_F_FAMILY_TILE) || tree_launch(p->D) == nullptr) return POF_E_UNSUPPORTED_DQ;
+  ExchangeArgs A = {};
+  p2p_fill(A, p, 1, payload);
+  A.state_out = seed;
+  A.scratch = scratch;
+  A.n_obs = (real)n_steps_total;
+  A.d_obs = (real)d;
+  A.calibrate = calibrate;
+  A.cscale = cscale;
+  A.scalars = scalars;
+  return (int)tree_launch(p->D)->sexchange((cudaStream_t)s, A);
+}
+// the third exchange: (obj, not-close) pairs of all ranks -> scalars[OBJ], scalars[NOT_CLOSE], summed in rank order
+static __global__ void __launch_bounds__(32) k_exchange_scalars_p2p(ExchangeArgs A) {
+  const real* g = p2p_exchange(A, 0, A.world);
+  if ((threadIdx.x & 31) == 0) {
+    real a = 0.0, b = 0.0;
+    for (int r = 0; r < A.world; ++r) {
+      a += __ldcg(g + 2 * r);
+      b += __ldcg(g + 2 * r + 1);
+    }
+    A.scalars[POF_S_OBJ] = a;
+    A.scalars[POF_S_NOT_CLOSE] = b;
+  }
+}
+int pof_p2p_exchange_scalars_f64(pof_stream_t s, pof_p2p_t* p, const real* pair, real* scalars) {
+  if (!p || !scalars) return POF_E_ARG;
+  ExchangeArgs A = {};
+  p2p_fill(A, p, 2, pair);
+  A.scalars = scalars;
+  k_exchange_scalars_p2p<<<1, 32, 0, (cudaStream_t)s>>>(A);
+  return (int)cudaGetLastError();
+}
+
 int POF_SUFFIX(pof_filter_apply_chain)(pof_stream_t s, uint32_t flags, int D, int count, const real* state_in,
                                const real* elems, real* state_out, real* scratch) {
   if ((flags & POF_F_FAMILY_TILE) || tree_launch(D) == nullptr) {

@@ -170,7 +170,7 @@ struct FlowArgs {
 
 struct ExchangeArgs {
   int rank, world;
-  const real* gathered;   // world payloads, `stride` doubles each
+  const real* gathered;   // world payloads, `stride` doubles each (ignored with peer memory: the local slots are used)
   long stride;
   const real* x0_mean;    // filter: initial state
   const real* x0_chol;
@@ -181,7 +181,61 @@ struct ExchangeArgs {
   int calibrate;
   real* cscale;           // out: sqrt(sigma^2) or 1
   real* scalars;          // out: POF scalars vector (nll, ssq, ssq_proper, cscale slots), or null
+  // ---- peer-memory form (pof_p2p_*): the kernel ITSELF moves the payload -- it stores this rank's payload into its
+  // slot of every peer's exchange area over NVLink, releases a flag there, waits for the flags of the ranks it
+  // needs in its own area, and folds: compute and collective in one launch, no NCCL call.  p2p = 0: plain form.
+  int p2p;
+  const real* payload;          // this rank's payload (stride values)
+  unsigned long long* peer[8];  // exchange areas of all ranks (8-byte words; peer[rank] is the local one)
+  long epoch_word, flag_word, slot_word;  // word offsets: this exchange's epoch counter, flags[world], slots[2][world][stride]
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Peer-memory exchange prologue (one warp): push `payload` into this rank's slot of every rank's exchange area, release
+// the flag there, wait for the ranks < need_below ... i.e. all r with need(r).  Flags carry a monotonically increasing
+// epoch (kept in the local area, advanced by this kernel), slots are double-buffered by its parity.  A wait that
+// exceeds ~2 s (a peer that died) sets the area's status word instead of hanging the GPU.
+// Returns the address of the gathered payloads (world x stride) in the LOCAL area.
+__device__ __forceinline__ const real* p2p_exchange(const ExchangeArgs& A, int need_lo, int need_hi) {
+  const int lane = threadIdx.x & 31;
+  const int W = A.world;
+  unsigned long long* mine = A.peer[A.rank];
+  const unsigned long long e = mine[A.epoch_word] + 1ull;
+  const long par = (long)(e & 1ull);
+  const long slot = (par * W + A.rank) * A.stride;  // (in values, inside the slot region that starts at slot_word)
+  for (int p = 0; p < W; ++p) {
+    real* dst = reinterpret_cast<real*>(A.peer[p] + A.slot_word) + slot;
+    for (long j = lane; j < A.stride; j += 32) dst[j] = A.payload[j];
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < W) st_release_sys(A.peer[lane] + A.flag_word + A.rank, e);
+  const bool need = lane < W && lane >= need_lo && lane < need_hi && lane != A.rank;
+  const long long t0 = clock64();
+  while (true) {
+    const bool ok = !need || ld_acquire_sys(mine + A.flag_word + lane) >= e;
+    if (__all_sync(0xffffffffu, ok)) break;
+    if (clock64() - t0 > 4000000000ll) {
+      if (lane == 0) mine[0] = 1ull;  // status: timed out
+      break;
+    }
+    __nanosleep(100);
+  }
+  __syncwarp();
+  if (lane == 0) mine[A.epoch_word] = e;
+  return reinterpret_cast<const real*>(mine + A.slot_word) + par * W * A.stride;
+}
+
+#endif  // __CUDACC__
+
 
 // register-resident tree sweeps (pof_treelane.cuh), 2D <= 32; nullptr -> CTA-per-node tile kernels
 struct TreeLaunch {

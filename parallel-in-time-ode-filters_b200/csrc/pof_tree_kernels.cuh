@@ -218,12 +218,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
 //             calibration scale; seed = terminal state (last rank's end state) combined with the later ranks'
 //             smoothing carries W-1 .. rank+1                                 (smoother.py:53-63 in state form)
 template <int D, bool FILT>
-__global__ void __launch_bounds__(32) k_exchange(const ExchangeArgs A) {
+__global__ void __launch_bounds__(32) k_exchange(ExchangeArgs A) {
   extern __shared__ __align__(16) real sm[];
   using TL = TreeLane<D>;
   constexpr int G = FILT ? TL::G2 : TL::GS;
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
   const int lane = threadIdx.x & 31;
+  if (A.p2p) {
+    static_assert(sizeof(real) == 8 || sizeof(real) == 4, "");
+    // filter: the carries of the earlier ranks; smoother: every rank's payload (the partial sums of all are needed)
+    A.gathered = FILT ? p2p_exchange(A, 0, A.rank) : p2p_exchange(A, 0, A.world);
+  }
   if (lane >= G) return;
   typename TL::Ctx cx;
   TL::template init<G>(cx, sm, FILT ? TL::NMAT : TL::NMAT_S);

@@ -93,6 +93,14 @@ def _load():
             _c_int, [_c_dp, U, _c_int, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_dp, _c_i64, _c_dp, _c_dp, _c_dp,
                      _c_dp]),
         "pof_shard_exchange_scalars_f64": (_c_int, [_c_dp, _c_int, _c_dp, _c_dp]),
+        "pof_p2p_create": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_void_p), _c_dp]),
+        "pof_p2p_connect": (_c_int, [_c_dp, _c_dp]),
+        "pof_p2p_destroy": (None, [_c_dp]),
+        "pof_p2p_status": (_c_int, [_c_dp, ctypes.POINTER(ctypes.c_int)]),
+        "pof_p2p_exchange_filter_f64": (_c_int, [_c_dp, U, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_p2p_exchange_smooth_f64": (
+            _c_int, [_c_dp, U, _c_dp, _c_int, _c_i64, _c_int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
+        "pof_p2p_exchange_scalars_f64": (_c_int, [_c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_filter_apply_chain_f64": (_c_int, [_c_dp, U, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_smooth_apply_chain_f64": (_c_int, [_c_dp, U, _c_int, _c_int, _c_dp, _c_dp, _c_dp, _c_dp]),
         "pof_project_f64": (_c_int, [_c_dp, _c_i64, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp]),
@@ -126,8 +134,10 @@ EXPORTED = [
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_shard_stage_c_f64",
     "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64", "pof_project_f64", "pof_prior_init_f64",
     "pof_shard_exchange_supported", "pof_shard_exchange_filter_f64", "pof_shard_exchange_smooth_f64",
-    "pof_shard_exchange_scalars_f64",
+    "pof_shard_exchange_scalars_f64", "pof_p2p_create", "pof_p2p_connect", "pof_p2p_destroy", "pof_p2p_status",
+    "pof_p2p_exchange_filter_f64", "pof_p2p_exchange_smooth_f64", "pof_p2p_exchange_scalars_f64",
 ] + F32_ENTRY_POINTS
+P2P_HANDLE_BYTES = 64
 
 
 def fn(base, dtype):

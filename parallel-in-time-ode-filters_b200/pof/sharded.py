@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -113,11 +114,51 @@ class CudaBackend:
                                                      nat.ptr(state_out), nat.ptr(self.scratch)), "smooth_chain")
 
 
+class PeerExchange:
+    """Peer-memory exchange areas of a time-sharded run (`pof_p2p_*`): one process per GPU of ONE NVLink / NVSwitch
+    box.  Every rank allocates its area inside the library (CUDA IPC needs whole allocations), the 64-byte IPC handles
+    are all-gathered once with torch.distributed, and from then on an exchange is ONE kernel per rank that stores its
+    payload into every peer's area, releases a flag there, waits for the flags it needs and folds the carries -- no
+    collective call in the pass."""
+
+    def __init__(self, rank, world, D, group, device):
+        import numpy as np
+
+        self._p = ctypes.c_void_p()
+        h = (ctypes.c_ubyte * nat.P2P_HANDLE_BYTES)()
+        nat.check(nat.LIB.pof_p2p_create(rank, world, D, ctypes.byref(self._p), ctypes.cast(h, ctypes.c_void_p)),
+                  "pof_p2p_create")
+        mine = torch.tensor(list(h), dtype=torch.uint8, device=device)
+        allh = torch.empty(world * nat.P2P_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        self._handles = np.ascontiguousarray(allh.cpu().numpy())
+        nat.check(nat.LIB.pof_p2p_connect(self._p, self._handles.ctypes.data_as(ctypes.c_void_p)), "pof_p2p_connect")
+        dist.barrier(group=group)  # every area is mapped everywhere before the first store
+
+    @property
+    def ptr(self):
+        return self._p
+
+    def status(self):
+        st = ctypes.c_int(0)
+        nat.check(nat.LIB.pof_p2p_status(self._p, ctypes.byref(st)), "pof_p2p_status")
+        return st.value
+
+    def close(self):
+        if self._p:
+            nat.LIB.pof_p2p_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+
 class ShardedPass:
     """One linear filter+smoother pass over a time-sharded trajectory (the multi-GPU form of
     pof.parallel_filtsmooth.linear_filtsmooth; reference pof/parallel_filtsmooth/__init__.py:5-10)."""
 
-    def __init__(self, N, d, q, qL, *, rank=None, world=None, group=None, device=None, chunk_len=None, backend=None):
+    def __init__(self, N, d, q, qL, *, rank=None, world=None, group=None, device=None, chunk_len=None, backend=None,
+                 exchange="auto"):
+        """exchange: "nccl" = all-gathers + one fused fold kernel per exchange; "p2p" = peer-memory exchange kernels
+        (no collective in the pass; one NVLink box, register-resident kernel family); "auto" = p2p where it can be set
+        up (world > 1, a real process group, CUDA IPC available), else nccl."""
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -144,6 +185,25 @@ class ShardedPass:
         self.cscale = z(1)
         self.x0_state = z(self.ST)
         self.scalars = z(nat.NSCALARS)
+        self.p2p = None
+        want = exchange if exchange != "auto" else os.environ.get("POF_B200_EXCHANGE", "auto")
+        can = (self.world > 1 and backend is None and dist.is_available() and dist.is_initialized()
+               and self.device.type == "cuda" and getattr(self.backend, "fused_exchange", False))
+        if want in ("p2p", "auto") and can:
+            try:
+                self.p2p = PeerExchange(self.rank, self.world, D, group, self.device)
+            except Exception:
+                if want == "p2p":
+                    raise
+                self.p2p = None
+            # every rank must take the same path: fall back together if any rank could not map its peers
+            ok = torch.tensor([1 if self.p2p is not None else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if self.p2p is not None:
+                    self.p2p.close()
+                self.p2p = None
+        self.exchange = "p2p" if self.p2p is not None else "nccl"
 
     def _all_gather(self, out, inp):
         if self.world == 1:
@@ -197,11 +257,14 @@ def _run_fused(self, x0_mean, x0_chol, H_loc, c_loc, means_loc, chols_loc, calib
     that a test can drive several "virtual ranks" in lockstep on one GPU (tests/test_gpu_sharded.py)."""
     st = (x0_mean, x0_chol, H_loc, c_loc, means_loc, chols_loc, calibrate, fmeans, fchols)
     self.phase_a(st)
-    self._all_gather(self.gather_f, self.carry_f)
+    if self.p2p is None:
+        self._all_gather(self.gather_f, self.carry_f)
     self.phase_b(st)
-    self._all_gather(self.gather_b, self.pay_b)
+    if self.p2p is None:
+        self._all_gather(self.gather_b, self.pay_b)
     self.phase_c(st)
-    self._all_gather(self.gather_c, self.pay_c)
+    if self.p2p is None:
+        self._all_gather(self.gather_c, self.pay_c)
     return self.phase_d()
 
 
@@ -212,7 +275,13 @@ def _phase_a(self, st):
 def _phase_b(self, st):
     x0_mean, x0_chol, H_loc, c_loc, _, _, _, fmeans, fchols = st
     D, SE, ST, pb = self.D, self.SE, self.ST, self.pay_b
-    self.backend.exchange_filter(D, self.rank, self.world, self.gather_f, self.FE, x0_mean, x0_chol, self.state_in)
+    if self.p2p is not None:  # push my carry to every peer, wait for the earlier ranks', fold: one kernel, no collective
+        nat.check(nat.LIB.pof_p2p_exchange_filter_f64(nat.stream_ptr(), nat.flags(), self.p2p.ptr,
+                                                      nat.ptr(self.carry_f), nat.ptr(x0_mean), nat.ptr(x0_chol),
+                                                      nat.ptr(self.state_in), nat.ptr(self.backend.scratch)),
+                  "p2p_exchange_filter")
+    else:
+        self.backend.exchange_filter(D, self.rank, self.world, self.gather_f, self.FE, x0_mean, x0_chol, self.state_in)
     if fmeans is not None and self.has_row0:
         fmeans[0].copy_(x0_mean)
         fchols[0].copy_(x0_chol)
@@ -224,14 +293,24 @@ def _phase_b(self, st):
 def _phase_c(self, st):
     means_loc, chols_loc, calibrate = st[4], st[5], st[6]
     D, SE, ST, W, r = self.D, self.SE, self.ST, self.world, self.rank
-    self.backend.exchange_smooth(D, self.d, r, W, self.n, calibrate, self.gather_b, self.PB, self.seed,
-                                 self.cscale, self.scalars)
+    if self.p2p is not None:
+        nat.check(nat.LIB.pof_p2p_exchange_smooth_f64(nat.stream_ptr(), nat.flags(), self.p2p.ptr, self.d, self.n,
+                                                      int(bool(calibrate)), nat.ptr(self.pay_b), nat.ptr(self.seed),
+                                                      nat.ptr(self.backend.scratch), nat.ptr(self.cscale),
+                                                      nat.ptr(self.scalars)), "p2p_exchange_smooth")
+    else:
+        self.backend.exchange_smooth(D, self.d, r, W, self.n, calibrate, self.gather_b, self.PB, self.seed,
+                                     self.cscale, self.scalars)
     self.backend.stage_c(self.seed, r == W - 1, self.has_row0, self.cscale, means_loc, chols_loc, self.pay_c)
 
 
 def _phase_d(self):
     sc = self.scalars
-    self.backend.exchange_scalars(self.world, self.gather_c, sc)
+    if self.p2p is not None:
+        nat.check(nat.LIB.pof_p2p_exchange_scalars_f64(nat.stream_ptr(), self.p2p.ptr, nat.ptr(self.pay_c),
+                                                       nat.ptr(sc)), "p2p_exchange_scalars")
+    else:
+        self.backend.exchange_scalars(self.world, self.gather_c, sc)
     return dict(nll=sc[nat.S_NLL], obj=sc[nat.S_OBJ], ssq=sc[nat.S_SSQ], ssq_proper=sc[nat.S_SSQ_PROPER],
                 not_close=sc[nat.S_NOT_CLOSE], scalars=sc)
 
