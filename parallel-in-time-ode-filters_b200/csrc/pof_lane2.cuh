@@ -55,6 +55,14 @@ struct Lane2 {
   // distinct banks as well).  ncu before: 2x excess wavefronts on every STS and on the column reads (stride == 2).
   static constexpr int SM_GROUP = RAW + (((G % 16) - (RAW % 16)) + 16) % 16;
 
+  // ---- smoother: bulk-copy (TMA engine) staging of the next step's backward kernel.  One step's kernel (g | E | noise
+  // factor: NE contiguous values) is copied global -> shared by ONE cp.async.bulk per chunk while the current step
+  // computes, its completion is signalled on an mbarrier that belongs to the chunk's lane group; the step then reads
+  // its rows with LDS.  (Before: 14 LDG.128 per lane and step hit L2 after a prefetch -- ncu: long_scoreboard 9 % +
+  // mio_throttle 8 % of the smoother's stall samples.)  Needs 16-byte aligned sizes; block = NE values + the mbarrier.
+  static constexpr int STG = ((NE * (int)sizeof(real) + 8 + 15) / 16) * 16 / (int)sizeof(real);
+  static constexpr bool STG_OK = (NE * sizeof(real)) % 16 == 0 && (STG * sizeof(real)) % 16 == 0;
+
   struct Lin {
     const real* __restrict__ H;
     const real* __restrict__ c;
@@ -72,6 +80,8 @@ struct Lane2 {
     real* vec;       // 2 gather vectors
     real* tq;        // this lane's rows of QL, lane-minor: tq[(s*D + j)*G] (conflict-free across the group)
     real* lbuf;      // 2 x NJP doubles: compact linearisations staged by cp.async (global -> shared, no registers)
+    real* stg;       // smoother with bulk-copy staging: this group's staging block (NE values, then the mbarrier), or null
+    unsigned stg_phase;
     int vflip;
     real cf[R][Q1];  // Pascal coefficients of the owned rows of F
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
@@ -85,6 +95,8 @@ struct Lane2 {
     c.vec = sm_group + 2 * D * LDM;
     c.tq = c.vec + 2 * VEC + c.l;
     c.lbuf = c.vec + 2 * VEC + R * G * D;
+    c.stg = nullptr;
+    c.stg_phase = 0;
     c.vflip = 0;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -937,6 +949,47 @@ struct Lane2 {
       }
     return bad;
   }
+  static __device__ __forceinline__ unsigned stg_bar(const Ctx& cx) {
+    return (unsigned)__cvta_generic_to_shared(cx.stg + NE);
+  }
+  // leader lane: arm the group's mbarrier with the byte count and start the bulk copy of one step's kernel
+  static __device__ __forceinline__ void stage_issue(const Ctx& cx, const real* __restrict__ src) {
+    if (cx.l == 0) {
+      const unsigned bar = stg_bar(cx), dst = (unsigned)__cvta_generic_to_shared(cx.stg);
+      constexpr unsigned BYTES = NE * sizeof(real);
+      // the group's reads of the block (generic proxy) are ordered before the engine's writes (async proxy)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src), "r"(BYTES), "r"(bar)
+                   : "memory");
+    }
+  }
+  static __device__ __forceinline__ void stage_wait(Ctx& cx) {
+    const unsigned bar = stg_bar(cx);
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(cx.stg_phase)
+        : "memory");
+    cx.stg_phase ^= 1u;
+  }
+  static __device__ __forceinline__ void stage_init(Ctx& cx, real* block) {
+    cx.stg = block;
+    cx.stg_phase = 0;
+    if (cx.l == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(stg_bar(cx)), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cx.sync();
+  }
+
   template <int JS>
   static __device__ __forceinline__ void smooth_step(Ctx& cx, long k, bool has_prev, bool emit_t0,
                                                      const real* qLinvdiag, const real* qL,
@@ -944,7 +997,25 @@ struct Lane2 {
                                                      real* __restrict__ means, real* __restrict__ chols,
                                                      real (&m)[R], real (&l)[R][D], real& obj, real& bad) {
     real g[R], e[R][D], ph[R][D], old[R];
-    {
+    if (cx.stg) {
+      stage_wait(cx);  // this step's kernel has landed in the group's staging block
+      const real* kp = cx.stg;
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        g[s] = kp[cx.rc[s]];
+        old[s] = (k > 0 || emit_t0) ? means[k * D + cx.rc[s]] : 0.0;
+      }
+      load_rows<0>(cx, kp + D, e);
+      load_rows<JS>(cx, kp + D + D * D, ph);
+      cx.sync();  // every lane of the group has its rows: the block may be overwritten
+      if (has_prev) {
+        stage_issue(cx, kern + (k - 1) * NE);
+        if (cx.l == 0) {
+          prefetch_l2(means + (k - 1) * D);
+          prefetch_l2(means + (k - 1) * D + D - 1);
+        }
+      }
+    } else {
       const real* kp = kern + k * NE;
 #pragma unroll
       for (int s = 0; s < R; ++s) {
@@ -953,8 +1024,8 @@ struct Lane2 {
       }
       load_rows<0>(cx, kp + D, e);
       load_rows<JS>(cx, kp + D + D * D, ph);
+      if (has_prev) prefetch_step(cx, kern + (k - 1) * NE, means + (k - 1) * D);
     }
-    if (has_prev) prefetch_step(cx, kern + (k - 1) * NE, means + (k - 1) * D);
     const real* ML = publish<0>(cx, 0, l);
     real mv[D];
     gather(cx, m, mv);
@@ -1028,7 +1099,10 @@ struct Lane2 {
     // row k-1) is prefetched into L2 while step k computes.  (Holding the next kernel in registers spilled; mixing
     // DRAM-latency loads for step k-1 with L2 hits for step k made every consumer wait for the slowest load, because
     // the few load scoreboards are shared -- ncu: long_scoreboard on the first shuffle of Dk, 33 % of the samples.)
-    prefetch_step(cx, kern + (k1 - 1) * NE, means + (k1 - 1) * D);
+    if (cx.stg)
+      stage_issue(cx, kern + (k1 - 1) * NE);
+    else
+      prefetch_step(cx, kern + (k1 - 1) * NE, means + (k1 - 1) * D);
     // the noise factor of a step has D - d columns, except for the chunk's first step (full incoming factor)
     for (long k = k1 - 1; k > k0; --k)
       smooth_step<(d / PW) * PW>(cx, k, true, emit_t0, qLinvdiag, qL, kern, cscale, means, chols, m, l, obj, bad);

@@ -19,6 +19,13 @@ struct Lane2Setup {
     return sm + (warp * LN::GPW + lane / LN::G) * LN::SM_GROUP;
   }
   static constexpr int smem_bytes() { return LANE2_WARPS * LN::GPW * LN::SM_GROUP * (int)sizeof(real); }
+  // smoother with bulk-copy staging: one staging block per chunk behind the groups' work areas (16-byte aligned).
+  // Only used where TWO CTAs per SM still fit (the kernels run one wave of 2 CTAs x 4 warps per SM).
+  static __host__ __device__ constexpr int stage_offset() { return ((LANE2_WARPS * LN::GPW * LN::SM_GROUP + 1) / 2) * 2; }
+  static constexpr int smem_bytes_staged() {
+    return (stage_offset() + LANE2_WARPS * LN::GPW * LN::STG) * (int)sizeof(real);
+  }
+  static constexpr bool staged_ok() { return LN::STG_OK && 2 * (smem_bytes_staged() + 1024) <= 227 * 1024; }
   static unsigned grid(long CS) {
     const long per_block = (long)LANE2_WARPS * LN::GPW;
     return (unsigned)((CS + per_block - 1) / per_block);
@@ -58,7 +65,8 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
   LN::scan(cx, k0, k1, lin, fin + ch * ST, kern, send + ch * ST, part + ch * 3, fmeans, fchols);
 }
 
-template <int d, int q>
+// STAGED: the next step's backward kernel is brought into shared memory by the bulk-copy (TMA) engine (pof_lane2.cuh)
+template <int d, int q, bool STAGED>
 __global__ void __launch_bounds__(LANE2_WARPS * 32)
     k_lane2_smooth(LeafArgs a, const real* __restrict__ sin, const real* __restrict__ kern, int emit_t0,
                    const real* __restrict__ cscale, real* __restrict__ means, real* __restrict__ chols,
@@ -69,6 +77,10 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
   if (ch >= a.CS) return;
   typename LN::Ctx cx;
   LN::init_ctx(cx, Lane2Setup<d, q>::smem_of_thread(sm), a.ql.v);
+  if constexpr (STAGED) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LN::stage_init(cx, sm + Lane2Setup<d, q>::stage_offset() + (warp * LN::GPW + lane / LN::G) * LN::STG);
+  }
   constexpr int D = LN::D, ST = D * D + D;
   real qinv[LN::Q1];
 #pragma unroll
@@ -103,9 +115,17 @@ struct Lane2Launchers {
   }
   static cudaError_t smooth(cudaStream_t s, const LeafArgs& a, const real* sin, const real* kern, int emit_t0,
                             const real* cscale, real* means, real* chols, real* part2) {
-    if (cudaError_t e = prep(k_lane2_smooth<d, q>)) return e;
-    k_lane2_smooth<d, q><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes(), s>>>(a, sin, kern, emit_t0, cscale,
-                                                                                    means, chols, part2);
+    if constexpr (LS::staged_ok()) {
+      if (!a.no_tma) {
+        if (cudaError_t e = ensure_smem(k_lane2_smooth<d, q, true>, LS::smem_bytes_staged())) return e;
+        k_lane2_smooth<d, q, true><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes_staged(), s>>>(
+            a, sin, kern, emit_t0, cscale, means, chols, part2);
+        return cudaGetLastError();
+      }
+    }
+    if (cudaError_t e = prep(k_lane2_smooth<d, q, false>)) return e;
+    k_lane2_smooth<d, q, false><<<LS::grid(a.CS), LANE2_WARPS * 32, LS::smem_bytes(), s>>>(a, sin, kern, emit_t0,
+                                                                                           cscale, means, chols, part2);
     return cudaGetLastError();
   }
   static const LeafLaunch* get() {

@@ -43,12 +43,14 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["lane2", "tile"])
+@pytest.fixture(params=["lane2", "tile", "lane2_no_tma"])
 def leaf_impl(request, monkeypatch, native_lib):
     """Both kernel families: the register-resident lane-cooperative kernels (default for d <= 4, D <= 16) and the
     large-state CTA-per-chunk kernels forced onto the same problems (explicit ABI flag POF_F_FAMILY_TILE)."""
     if request.param == "tile":
         monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_FAMILY_TILE)
+    if request.param == "lane2_no_tma":  # the smoother without the bulk-copy staging (flag POF_F_NO_TMA)
+        monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_NO_TMA)
     return request.param
 
 
@@ -77,21 +79,23 @@ def test_ieks_step_matches_oracle(native_lib, leaf_impl, name, kw, N, q, L):
 
     # The reference's result depends on the association order of its scan at the 1e-9 level on badly scaled
     # problems (JAX tree vs left fold of the SAME formulas: 5.6e-8 on the SEIR outputs, 3e-9 on nll for logistic
-    # order 4), so every gate is  max(stated tolerance, 10 x that schedule dependence of the oracle itself).
+    # order 4), so every gate is  max(stated tolerance, 10 x that schedule dependence of the oracle itself) -- with the
+    # band CAPPED (1e-6 relative): a large disagreement between the oracle's own schedules must not widen a gate
+    # without limit.
     oout2, nll2, obj2, _, ossqp2 = O.linear_filtsmooth(osetup["x0"], osetup["dtm"], odom, scan=O.sequential_scan)
     E0 = osetup["E0"]
     m, Lc = out.mean.cpu().numpy(), out.chol.cpu().numpy()
     y, yo = m @ E0.T, oout.mean @ E0.T
     scale = np.abs(yo).max(axis=0)
     band = np.abs(oout2.mean @ E0.T - yo).max(axis=0)
-    tol_y = np.maximum(1e-9 * scale + 1e-12, 10 * band)
+    tol_y = np.maximum(1e-9 * scale + 1e-12, np.minimum(10 * band, 1e-6 * scale))
     assert (np.abs(y - yo) <= tol_y).all(), (np.abs(y - yo).max(axis=0), tol_y)
     C, Co = _cov(Lc), _cov(oout.chol)
     Cy, Cyo = E0 @ C @ E0.T, E0 @ Co @ E0.T
     assert np.abs(Cy - Cyo).max() <= 1e-7 * np.abs(Cyo).max()
     assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
-    tol_nll = max(1e-9 * abs(onll) + 1e-9, 10 * abs(nll2 - onll))
-    tol_obj = max(1e-9 * abs(oobj), 10 * abs(obj2 - oobj))
+    tol_nll = max(1e-9 * abs(onll) + 1e-9, min(10 * abs(nll2 - onll), 1e-6 * abs(onll)))
+    tol_obj = max(1e-9 * abs(oobj), min(10 * abs(obj2 - oobj), 1e-6 * abs(oobj)))
     assert abs(float(nll) - onll) <= tol_nll
     assert abs(float(obj) - oobj) <= tol_obj
     assert abs(float(ssq) - ossq) <= 1e-2 * abs(ossq)
@@ -104,7 +108,7 @@ def test_ieks_step_matches_oracle(native_lib, leaf_impl, name, kw, N, q, L):
     if N <= 512:
         cs = np.abs(oout.mean).max(axis=0)
         band_m = np.abs(oout2.mean - oout.mean).max(axis=0)
-        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, 10 * band_m)).all()
+        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, np.minimum(10 * band_m, 1e-6 * cs))).all()
     # smoothed chol is lower triangular like the reference's
     assert np.abs(np.triu(Lc, 1)).max() == 0.0
 

@@ -40,13 +40,13 @@ def _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=False, full_state=Tru
     y, yo = m @ E0.T, oout.mean @ E0.T
     scale = np.abs(yo).max(axis=0)
     band = np.abs(oout2.mean @ E0.T - yo).max(axis=0)
-    tol_y = np.maximum(1e-9 * scale + 1e-12, 10 * band)
+    tol_y = np.maximum(1e-9 * scale + 1e-12, np.minimum(10 * band, 1e-6 * scale))  # (band capped)
     assert (np.abs(y - yo) <= tol_y).all(), (np.abs(y - yo).max(axis=0), tol_y)
     C, Co = _cov(Lc), _cov(oout.chol)
     assert np.abs(E0 @ C @ E0.T - E0 @ Co @ E0.T).max() <= 1e-7 * np.abs(E0 @ Co @ E0.T).max()
     assert np.abs(C - Co).max() <= 1e-7 * np.abs(Co).max()
-    assert abs(float(nll) - onll) <= max(1e-9 * abs(onll) + 1e-9, 10 * abs(nll2 - onll))
-    assert abs(float(obj) - oobj) <= max(1e-9 * abs(oobj), 10 * abs(obj2 - oobj))
+    assert abs(float(nll) - onll) <= max(1e-9 * abs(onll) + 1e-9, min(10 * abs(nll2 - onll), 1e-6 * abs(onll)))
+    assert abs(float(obj) - oobj) <= max(1e-9 * abs(oobj), min(10 * abs(obj2 - oobj), 1e-6 * abs(oobj)))
     if not noisy:
         # the reference's sigma^2 (whiten solves with L^T, utils.py:110-112) depends on which of the valid innovation
         # factors the QR returns; the dependence grows with d (1.4 % at d = 16, N = 150 between LAPACK and these sweeps)
@@ -55,7 +55,7 @@ def _check_pass(out, nll, obj, ssq, osetup, odom, N, noisy=False, full_state=Tru
     if N <= 512 and full_state:
         cs = np.abs(oout.mean).max(axis=0)
         band_m = np.abs(oout2.mean - oout.mean).max(axis=0)
-        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, 10 * band_m)).all()
+        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, np.minimum(10 * band_m, 1e-6 * cs))).all()
     assert np.abs(np.triu(Lc, 1)).max() == 0.0
 
 
