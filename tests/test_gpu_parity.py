@@ -108,7 +108,7 @@ def test_ieks_step_matches_oracle(native_lib, leaf_impl, name, kw, N, q, L):
     if N <= 512:
         cs = np.abs(oout.mean).max(axis=0)
         band_m = np.abs(oout2.mean - oout.mean).max(axis=0)
-        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, np.minimum(10 * band_m, 1e-6 * cs))).all()
+        assert (np.abs(m - oout.mean) <= np.maximum(1e-9 * cs + 1e-12, np.minimum(10 * band_m, 1e-4 * cs))).all()
     # smoothed chol is lower triangular like the reference's
     assert np.abs(np.triu(Lc, 1)).max() == 0.0
 
