@@ -33,8 +33,9 @@ typedef struct pof_p2p pof_p2p_t; /* opaque: peer-memory exchange area of one ra
 #define POF_F_TILE_SMEM_QR 2u   /* large-state kernels: shared-memory Householder sweeps instead of the register-
                                    resident ones (A/B measurement; slower on B200) */
 #define POF_F_TREE_PER_LEVEL 4u /* one kernel launch per tree level instead of the dataflow sweeps (A/B measurement) */
-#define POF_F_NO_TMA 8u         /* smoother: plain global loads instead of the bulk-copy (TMA engine) staging of the
-                                   per-step backward kernels (A/B measurement) */
+#define POF_F_SMOOTH_TMA 8u     /* smoother: bulk-copy (TMA engine, cp.async.bulk + mbarrier) staging of the per-step
+                                   backward kernels instead of plain global loads.  OFF by default: measured 30x
+                                   SLOWER on B200 (64 independent 1 KB streams per SM) */
 
 #define POF_E_UNSUPPORTED_DQ (-1) /* (d, q) combination not compiled in */
 #define POF_E_WORKSPACE (-2)      /* workspace too small */

@@ -403,7 +403,7 @@ static int make_args(long n, int d, int q, const double* qL_host, const real* H,
   a.F = nullptr;
   a.QLd = nullptr;
   a.tile_reg = (flags & POF_F_TILE_SMEM_QR) ? 0 : 1;
-  a.no_tma = (flags & POF_F_NO_TMA) ? 1 : 0;
+  a.no_tma = (flags & POF_F_SMOOTH_TMA) ? 0 : 1;
   a.d = d;
   a.q = q;
   a.s0 = a.s1 = 0.0;

@@ -55,11 +55,15 @@ struct Lane2 {
   // distinct banks as well).  ncu before: 2x excess wavefronts on every STS and on the column reads (stride == 2).
   static constexpr int SM_GROUP = RAW + (((G % 16) - (RAW % 16)) + 16) % 16;
 
-  // ---- smoother: bulk-copy (TMA engine) staging of the next step's backward kernel.  One step's kernel (g | E | noise
-  // factor: NE contiguous values) is copied global -> shared by ONE cp.async.bulk per chunk while the current step
-  // computes, its completion is signalled on an mbarrier that belongs to the chunk's lane group; the step then reads
-  // its rows with LDS.  (Before: 14 LDG.128 per lane and step hit L2 after a prefetch -- ncu: long_scoreboard 9 % +
-  // mio_throttle 8 % of the smoother's stall samples.)  Needs 16-byte aligned sizes; block = NE values + the mbarrier.
+  // ---- smoother, OPT-IN (flag POF_F_SMOOTH_TMA): bulk-copy (TMA engine) staging of the next step's backward kernel.
+  // One step's kernel (g | E | noise factor: NE contiguous values) is copied global -> shared by ONE cp.async.bulk per
+  // chunk while the current step computes, its completion is signalled on an mbarrier that belongs to the chunk's lane
+  // group; the step then reads its rows with LDS (168 instead of 255 registers).  Built to remove the 14 LDG.128 per
+  // lane and step (ncu: long_scoreboard 9 % + mio_throttle 8 % of the smoother's stall samples).  MEASURED on B200:
+  // correct, but 30x SLOWER (13.9 ms instead of 0.455 ms at N = 2^20, with or without the proxy fence, blocking or
+  // non-blocking wait): 64 independent 1 KB streams per SM = ~1e6 bulk copies per pass complete at only ~0.5 copies
+  // per microsecond and SM -- the copy engine is made for few large tiles, not for many small ones.  Hence off by
+  // default; kept because the negative result is the evidence.  Needs 16-byte aligned sizes; block = NE values + mbarrier.
   static constexpr int STG = ((NE * (int)sizeof(real) + 8 + 15) / 16) * 16 / (int)sizeof(real);
   static constexpr bool STG_OK = (NE * sizeof(real)) % 16 == 0 && (STG * sizeof(real)) % 16 == 0;
 
@@ -957,8 +961,8 @@ struct Lane2 {
     if (cx.l == 0) {
       const unsigned bar = stg_bar(cx), dst = (unsigned)__cvta_generic_to_shared(cx.stg);
       constexpr unsigned BYTES = NE * sizeof(real);
-      // the group's reads of the block (generic proxy) are ordered before the engine's writes (async proxy)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // (write-after-read on the block: the group's reads completed before the __syncwarp that precedes this call --
+      // the same consumer-release ordering TMA pipelines rely on; a fence.proxy.async here cost ~2 us per call)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                    "l"(src), "r"(BYTES), "r"(bar)

@@ -69,7 +69,7 @@ struct LeafArgs {
   const real* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
   const real* QLd; // preconditioned IWP described by ql (tile family only)
   int tile_reg;      // tile family: register-resident Householder sweeps (default; 0 with POF_F_TILE_SMEM_QR)
-  int no_tma;        // lane2 smoother: plain global loads instead of the bulk-copy staging (POF_F_NO_TMA; A/B)
+  int no_tma;        // lane2 smoother: 0 = bulk-copy (TMA) staging of the backward kernels (POF_F_SMOOTH_TMA; measured slower)
 };
 
 struct LeafLaunch {

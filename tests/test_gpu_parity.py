@@ -43,14 +43,14 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["lane2", "tile", "lane2_no_tma"])
+@pytest.fixture(params=["lane2", "tile", "lane2_tma"])
 def leaf_impl(request, monkeypatch, native_lib):
     """Both kernel families: the register-resident lane-cooperative kernels (default for d <= 4, D <= 16) and the
     large-state CTA-per-chunk kernels forced onto the same problems (explicit ABI flag POF_F_FAMILY_TILE)."""
     if request.param == "tile":
         monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_FAMILY_TILE)
-    if request.param == "lane2_no_tma":  # the smoother without the bulk-copy staging (flag POF_F_NO_TMA)
-        monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_NO_TMA)
+    if request.param == "lane2_tma":  # the smoother with bulk-copy (TMA engine) staging (opt-in flag POF_F_SMOOTH_TMA)
+        monkeypatch.setattr(native_lib, "DEFAULT_FLAGS", native_lib.F_SMOOTH_TMA)
     return request.param
 
 
