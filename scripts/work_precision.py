@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--exp-step", type=int, default=2)
     ap.add_argument("--seq-max-exp", type=int, default=12, help="largest N for the sequential solvers (one thread)")
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--tag", default="r02")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles"))
     a = ap.parse_args()
     orders = [int(x) for x in a.orders.split(",")]
@@ -102,7 +103,7 @@ def main():
             print(name, {k: (f"{v:.3e}" if isinstance(v, float) else v) for k, v in row.items()
                          if k == "Ns" or k.startswith("IEKS(3)")}, flush=True)
         cols = ["Ns"] + sorted({k for r in rows for k in r if k != "Ns"})
-        path = os.path.join(a.out, f"r01_work_precision_{name}_{dev}.csv")
+        path = os.path.join(a.out, f"{a.tag}_work_precision_{name}_{dev}.csv")
         with open(path, "w", newline="") as fh:
             w = csv.DictWriter(fh, fieldnames=cols)
             w.writeheader()
