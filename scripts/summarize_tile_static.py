@@ -54,6 +54,6 @@ out += ["", "Reading.  One inlined copy of the sweeps per kernel (the leaf recur
         "`LDS`/`STS` (address space known).  Earlier structures of the same source — sweeps as `__noinline__` functions called from",
         "several places, or six instantiations per call site — made ptxas keep whole register files in local memory (100–280",
         "`LDL` per pivot body) or drop to 32–64 registers with 30 KB of spills; `__launch_bounds__(256, 1)` is required too.",
-        "The register sweeps are opt-in (`POF_B200_TILE_SWEEP=reg`); the default shared-memory sweep (`tile_tria_smem`) has no spills either.", ""]
+        "The register sweeps are the default (measured 1.65x faster on config 5); the shared-memory sweep (`tile_tria_smem`, flag POF_F_TILE_SMEM_QR) has no spills either.", ""]
 open(os.path.join(ROOT, "profiles", "r01_tile_static.md"), "w").write("\n".join(out))
 print("\n".join(out))
