@@ -600,7 +600,7 @@ def run_native(args):
     seg = {nm: (v[0] / max(1, v[1])) for nm, v in seg_raw.items()}
     ncu = ncu_counters()
     dominant = max(("fold", "scan", "smooth"), key=lambda k: seg[k])
-    kname = {"fold": "k_lane2_fold<2,3>", "scan": "k_lane2_scan<2,3>", "smooth": "k_lane2_smooth<2,3>"}
+    kname = {"fold": "k_lane2_fold<2,3>", "scan": "k_lane2_scan<2,3>", "smooth": "k_lane2_smooth<2,3,0>"}
 
     def hbm_view(k):
         t = seg[k]

@@ -61,10 +61,7 @@ def num(v, unit=""):
 
 
 traffic_path = os.path.join(out_dir, "r02_ncu_kernels.json")
-try:
-    traffic = json.load(open(traffic_path))
-except Exception:
-    traffic = {}
+traffic = {}  # rebuilt from the captures given on the command line (never merged with an older capture)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hashlib  # noqa: E402
 
