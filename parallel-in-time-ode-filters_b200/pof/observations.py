@@ -36,8 +36,9 @@ def linearize_ek0(f, x):
     res = f(m)
     d = res.shape[0]
     q = m.shape[0] // d - 1
-    E1 = torch.kron(torch.eye(d, dtype=m.dtype, device=m.device),
-                    torch.eye(1, q + 1, 1, dtype=m.dtype, device=m.device))
+    e1 = torch.zeros((1, q + 1), dtype=m.dtype, device=m.device)
+    e1[0, 1] = 1.0
+    E1 = torch.kron(torch.eye(d, dtype=m.dtype, device=m.device), e1)
     return AffineModel(E1, res - E1 @ m, torch.zeros((d, d), dtype=m.dtype, device=m.device))
 
 

@@ -74,3 +74,79 @@ def test_lorenz96_matches_the_oracle_definition(native_lib):
     assert float(x0.chol.abs().max()) == 0.0
     small = pof.ivp.lorenz96(d=8)
     assert small.dimension == 8
+
+
+def test_observation_model_variants(native_lib):
+    """reference observations.py:35-83 (`linearize`, `linearize_ek0`, `uncertain_linearize`, `linearize_regularized`):
+    shapes, the affine identity H m + b == f(m) (reference tests/test_observations.py:18-33), and the stacked
+    Levenberg-Marquardt model [EK1 ; x ~ N(m, I / l)] with the reference's offset convention"""
+    from pof.observations import (AffineModel, linearize, linearize_ek0, linearize_regularized, uncertain_linearize)
+    from pof.utils import MVNSqrt
+
+    d, q = 2, 2
+    D = d * (q + 1)
+    unit = lambda i: torch.eye(q + 1, dtype=torch.float64)[i:i + 1]
+    E0 = torch.kron(torch.eye(d, dtype=torch.float64), unit(0))
+    E1 = torch.kron(torch.eye(d, dtype=torch.float64), unit(1))
+    f = lambda x: E1 @ x - torch.sin(E0 @ x)
+    m = torch.linspace(0.1, 0.6, D, dtype=torch.float64)
+    L = torch.tril(torch.full((D, D), 0.1, dtype=torch.float64)) + 0.5 * torch.eye(D, dtype=torch.float64)
+    x = MVNSqrt(m, L)
+    lin = linearize(f, x)
+    assert isinstance(lin, AffineModel) and lin.H.shape == (d, D) and lin.b.shape == (d,)
+    assert float(lin.cholR.abs().max()) == 0.0
+    np.testing.assert_allclose((lin.H @ m + lin.b).numpy(), f(m).numpy(), rtol=1e-14)
+    ek0 = linearize_ek0(f, x)
+    np.testing.assert_allclose(ek0.H.numpy(), E1.numpy())
+    np.testing.assert_allclose((ek0.H @ m + ek0.b).numpy(), f(m).numpy(), rtol=1e-14)
+    unc = uncertain_linearize(f, x)
+    np.testing.assert_allclose((unc.cholR @ unc.cholR.T).numpy(), (lin.H @ L @ L.T @ lin.H.T).numpy(), rtol=1e-12)
+    reg = linearize_regularized(f, x, 4.0)
+    assert reg.H.shape == (d + D, D) and reg.b.shape == (d + D,) and reg.cholR.shape == (d + D, d + D)
+    np.testing.assert_allclose(reg.H[:d].numpy(), lin.H.numpy())
+    np.testing.assert_allclose(reg.H[d:].numpy(), np.eye(D))
+    np.testing.assert_allclose(reg.b.numpy(), np.concatenate([f(m).numpy(), -m.numpy()]))
+    np.testing.assert_allclose(np.diag(reg.cholR.numpy()), np.concatenate([np.zeros(d), np.full(D, 0.5)]))
+
+
+def test_iterator_and_batch_modules_import(native_lib):
+    """the generator API and the batch solver are importable without a GPU (they only launch work when called)"""
+    import pof.batch
+    import pof.iterators
+
+    assert callable(pof.iterators.ieks_iterator) and callable(pof.iterators.qpm_ieks_iterator)
+    assert callable(pof.batch.solve_batch)
+    with pytest.raises(NotImplementedError):
+        pof.iterators.lm_ieks_iterator(None, None, None, None)
+
+
+def test_oracle_qpm_reaches_the_plain_ieks_solution():
+    """oracle restatement of the quadratic-penalty iterator (iterators.py:53-112): it ends with reg = 0 at the fixed
+    point of the plain IEKS"""
+    oivp = oivps.logistic()
+    ts = np.linspace(0, 10, 40)
+    s = O.set_up_solver(oivp, ts, 2)
+    regs = []
+    for st, nll, obj, reg in O.qpm_ieks_iterator(s, O.get_initial_trajectory(s)):
+        regs.append(reg)
+        assert len(regs) < 400
+    assert regs[0] == 1e20 and regs[-1] == 0.0 and all(a >= b for a, b in zip(regs, regs[1:]))
+    ys, info = O.solve(oivp, ts, 2)
+    np.testing.assert_allclose(st.mean @ s["E0"].T, ys.mean, rtol=0, atol=1e-10)
+
+
+def test_oracle_prior_init_is_the_taylor_prediction():
+    """oracle restatement of init="prior" (initialization.py:66-89): row k is the Taylor polynomial of the initial
+    derivatives over the ABSOLUTE time ts[k] (quirk Q6), factor -P_k QL under LAPACK's sign convention"""
+    oivp = oivps.logistic()
+    q = 3
+    ts = np.array([0.0, 0.5, 1.0, 2.5])
+    st = O.prior_init(oivp, q, ts)
+    m0 = O.taylor_mode_init(oivp, q).mean
+    for k, t in enumerate(ts[1:], start=1):
+        want = [sum(t ** (j - i) / math.factorial(j - i) * m0[j] for j in range(i, q + 1)) for i in range(q + 1)]
+        np.testing.assert_allclose(st.mean[k], want, rtol=1e-12)
+        P, _ = O.nordsieck_preconditioner(1, q, t)
+        _, QL = O.preconditioned_discretize(1, q)
+        np.testing.assert_allclose(st.chol[k], -P @ QL, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(st.mean[0], m0)
