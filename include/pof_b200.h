@@ -168,6 +168,20 @@ int pof_ieks_iteration_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int i
                            const double* x0_mean, const double* x0_chol, double* means, double* chols, int calibrate,
                            double* scalars, void* ws, size_t ws_bytes);
 
+/* The same iteration WITH the stopping rule evaluated on the device -- the body AND the condition of the reference's
+ *   jax.lax.while_loop(cond, body, val)   pof/solver.py:36-57, pof/convergence_criteria.py:4-13.
+ * loop_state (device, 8 doubles, zero-initialised by the caller): [0] stop flag, [1] iterations done, [2] obj and
+ * [3] nll of the last iteration.  After the pass a one-thread kernel sets the flag when the rule fires
+ * (isnan | isclose(obj_old, obj, rtol 1e-6, atol 1e-9) | no mean entry moved) or iterations > maxiters; once it is
+ * set, every kernel of later calls returns at once and means / chols / scalars stay those of the final iteration.
+ * The host may therefore enqueue several steps (or replays of a captured CUDA graph) without synchronising in between.
+ * Register-resident family only (POF_E_UNSUPPORTED_DQ otherwise). */
+int pof_ieks_loop_step_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                           int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                           double scale0, double scale1, const double* x0_mean, const double* x0_chol, double* means,
+                           double* chols, int calibrate, double* scalars, double* loop_state, int64_t maxiters,
+                           void* ws, size_t ws_bytes);
+
 /* Sequential extended Kalman smoother for a built-in IVP -- replaces
  *   pof.sequential_filtsmooth.filtsmooth(x0, dtm, om)   pof/sequential_filtsmooth/__init__.py:5-10
  * (EKF relinearised at the predicted mean of every step, filter.py:9-30, then RTS, smoother.py:8-28), the numerical
@@ -308,6 +322,11 @@ int pof_ieks_iteration_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int i
                            int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
                            double scale0, double scale1, const float* x0_mean, const float* x0_chol, float* means,
                            float* chols, int calibrate, float* scalars, void* ws, size_t ws_bytes);
+int pof_ieks_loop_step_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                           int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                           double scale0, double scale1, const float* x0_mean, const float* x0_chol, float* means,
+                           float* chols, int calibrate, float* scalars, float* loop_state, int64_t maxiters, void* ws,
+                           size_t ws_bytes);
 int pof_shard_stage_a_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
                           int64_t chunk_len, const double* qL_host, const float* H, const float* c, float* carry_f,
                           void* ws, size_t ws_bytes);

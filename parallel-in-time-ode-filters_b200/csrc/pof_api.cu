@@ -114,8 +114,9 @@ __global__ void __launch_bounds__(32)
 template <int NC, int MODE>
 __global__ void __launch_bounds__(1024) k_reduce_parts_t(const real* __restrict__ part, long cnt,
                                                          real* __restrict__ out, real n, real d, int calibrate,
-                                                         real* __restrict__ scal) {
+                                                         real* __restrict__ scal, const real* __restrict__ stop) {
   __shared__ real sh[32][NC];
+  if (stop && *stop != real(0)) return;  // device-side IEKS loop ended: the scalars stay those of the final iteration
   real s[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) s[j] = 0.0;
@@ -198,9 +199,9 @@ __global__ void __launch_bounds__(256)
 // compact linearisation: per step [J_f (d x d) | c (d)] with c = J_f y - f(y); the leaf kernels rebuild H on load
 __global__ void __launch_bounds__(256)
     k_linearize_compact(int ivp_id, IvpParams P, long n, int d, int q, double scale0,
-                        const real* __restrict__ means_t1, real* __restrict__ Jc) {
+                        const real* __restrict__ means_t1, real* __restrict__ Jc, const real* __restrict__ stop) {
   const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+  if (k >= n || (stop && *stop != real(0))) return;
   const int Q1 = q + 1, D = d * Q1;
   double y[4], f[4], J[16];
   for (int b = 0; b < d; ++b) y[b] = scale0 * (double)means_t1[k * D + b * Q1];
@@ -404,6 +405,7 @@ static int make_args(long n, int d, int q, const double* qL_host, const real* H,
   a.QLd = nullptr;
   a.tile_reg = (flags & POF_F_TILE_SMEM_QR) ? 0 : 1;
   a.no_tma = (flags & POF_F_SMOOTH_TMA) ? 0 : 1;
+  a.stop = nullptr;
   a.d = d;
   a.q = q;
   a.s0 = a.s1 = 0.0;
@@ -430,6 +432,7 @@ static void flow_begin(FlowArgs& fa, const WsLayout& wl, real* agg, real* st, un
   fa.flag_up = f_up;
   fa.flag_dn = f_dn;
   fa.ticket = ticket;
+  fa.stop = nullptr;
 }
 // up-sweep: build levels 1 .. top from their children
 static void flow_up(FlowArgs& fa, const WsLayout& wl, int top) {
@@ -501,6 +504,7 @@ static int stage_a(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
   if (tl && !(flags & POF_F_TREE_PER_LEVEL)) {
     FlowArgs fa;
     flow_begin(fa, wl, fagg, ws + wl.o_fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
+    fa.stop = a.stop;
     flow_up(fa, wl, wl.tl.nlev - 1);
     if (fa.nseg) POF_CK(tl->fflow(s, fa));
     return 0;
@@ -532,6 +536,7 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
     if (!per_level) {
       FlowArgs fa;
       flow_begin(fa, wl, fagg, fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
+      fa.stop = a.stop;
       if (!need_root) flow_up(fa, wl, up_top);
       flow_down(fa, wl, root_m, root_L);
       POF_CK(tl->fflow(s, fa));
@@ -571,6 +576,7 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
       // the filter scan; once the terminal state exists, ONE state-form combine per chunk remains (stage C).
       FlowArgs fa;
       flow_begin(fa, wl, sagg, ws + wl.o_sin, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SUP));
+      fa.stop = a.stop;
       flow_up(fa, wl, up_top);
       if (elem_suffix(wl)) flow_down_elem(fa, wl, ws + wl.o_sx);
       if (fa.nseg) POF_CK(tl->sflow(st, fa));
@@ -601,7 +607,7 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
   else if (int rc = smoother_up(s))
     return rc;
   k_reduce_parts_t<3, 1><<<1, 1024, 0, s>>>(ws + wl.o_part, wl.CS, ws + wl.o_sums, n_obs_total, (real)a.d, calibrate,
-                                            scalars);
+                                            scalars, a.stop);
   return (int)cudaGetLastError();
 }
 
@@ -622,6 +628,7 @@ static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
       } else {
         FlowArgs fa;
         flow_begin(fa, wl, sagg, sin_, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SDOWN));
+        fa.stop = a.stop;
         flow_down(fa, wl, root_m, root_L);
         POF_CK(tl->sflow(s, fa));
       }
@@ -643,7 +650,7 @@ static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
     ProfScope ps(ctx, POF_SEG_SMOOTH, s);
     POF_CK(ll->smooth(s, a, sin_, ws + wl.o_kern, emit_t0, cscale, means, chols, ws + wl.o_part2));
   }
-  k_reduce_parts_t<2, 2><<<1, 1024, 0, s>>>(ws + wl.o_part2, wl.CS, ws + wl.o_sums + 8, 0.0, 0.0, 0, scalars);
+  k_reduce_parts_t<2, 2><<<1, 1024, 0, s>>>(ws + wl.o_part2, wl.CS, ws + wl.o_sums + 8, 0.0, 0.0, 0, scalars, a.stop);
   return (int)cudaGetLastError();
 }
 
@@ -859,7 +866,7 @@ int POF_SUFFIX(pof_linearize_ivp_compact)(pof_stream_t s, int ivp_id, const doub
   }
 #endif
   k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(ivp_id, P, n, d, q, scale0, means_t1,
-                                                                                Jc);
+                                                                                Jc, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -910,16 +917,35 @@ int POF_SUFFIX(pof_linear_filtsmooth_general)(pof_stream_t s_, pof_ctx_t* ctx, u
 
 #endif  // !POF_F32
 
-int POF_SUFFIX(pof_ieks_iteration)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
-                           int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
-                           double scale0, double scale1, const real* x0_mean, const real* x0_chol, real* means,
-                           real* chols, int calibrate, real* scalars, void* ws_, size_t ws_bytes) {
-  cudaStream_t s = (cudaStream_t)s_;
+// loop_state (device, 8 values; null = a single iteration): [0] stop flag, [1] iterations done, [2] obj of the last
+// iteration, [3] nll of the last iteration.  With it every kernel returns at once when the flag is set, and k_crit
+// evaluates the reference's stopping rule (convergence_criteria.py:4-13, solver.py:36-45) on the device.
+static __global__ void k_crit(const real* __restrict__ scal, real* __restrict__ ls, double maxiters) {
+  if (ls[0] != real(0)) return;
+  const double k = (double)ls[1] + 1.0;
+  const double obj = (double)scal[POF_S_OBJ], nll = (double)scal[POF_S_NLL], bad = (double)scal[POF_S_NOT_CLOSE];
+  const double obj_old = (double)ls[2];
+  const bool isnan_ = (obj != obj) || (nll != nll);
+  // numpy / jax isclose(a = obj_old, b = obj): |a - b| <= atol + rtol |b|, rtol 1e-6, atol 1e-9
+  const bool obj_conv = !isnan_ && fabs(obj_old - obj) <= 1e-9 + 1e-6 * fabs(obj);
+  const bool conv = isnan_ || obj_conv || bad == 0.0;
+  ls[1] = (real)k;
+  ls[2] = (real)obj;
+  ls[3] = (real)nll;
+  ls[0] = (conv || !(k <= maxiters)) ? real(1) : real(0);
+}
+
+static int ieks_iteration_impl(cudaStream_t s, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                               int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                               double scale0, double scale1, const real* x0_mean, const real* x0_chol, real* means,
+                               real* chols, int calibrate, real* scalars, real* loop_state, double maxiters, void* ws_,
+                               size_t ws_bytes) {
   if (N < 2) return POF_E_ARG;
   IvpParams P;
   if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
   const LeafLaunch* ll = leaf_launch(d, q, flags);
   if (!ll) return POF_E_UNSUPPORTED_DQ;
+  if (loop_state && tree_for(ll, d * (q + 1), flags) == nullptr) return POF_E_UNSUPPORTED_DQ;  // register-resident family
   WsLayout wl;
   wl.build(N - 1, d, q, chunk_len);
   if (ws_bytes < wl.total * sizeof(real)) return POF_E_WORKSPACE;
@@ -934,15 +960,43 @@ int POF_SUFFIX(pof_ieks_iteration)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t fla
                                                                     nullptr, nullptr, lin);
   else
 #endif
-    k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, means + D, lin);
+    k_linearize_compact<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ivp_id, P, n, d, q, scale0, means + D, lin,
+                                                                    loop_state);
   POF_CK(cudaGetLastError());
   LeafArgs a;
   if (int rc = make_args(n, d, q, qL_host, nullptr, nullptr, wl, flags, a)) return rc;
   a.Jc = lin;
   a.s0 = scale0;
   a.s1 = scale1;
-  return run_pass(s, ctx, flags, ll, a, wl, ws, N, x0_mean, x0_chol, means, chols, nullptr, nullptr, calibrate,
-                  scalars);
+  a.stop = loop_state;
+  if (int rc = run_pass(s, ctx, flags, ll, a, wl, ws, N, x0_mean, x0_chol, means, chols, nullptr, nullptr, calibrate,
+                        scalars))
+    return rc;
+  if (loop_state) k_crit<<<1, 1, 0, s>>>(scalars, loop_state, maxiters);
+  return (int)cudaGetLastError();
+}
+
+int POF_SUFFIX(pof_ieks_iteration)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int ivp_id,
+                                   const double* params_host, int nparams, int64_t N, int d, int q, int64_t chunk_len,
+                                   const double* qL_host, double scale0, double scale1, const real* x0_mean,
+                                   const real* x0_chol, real* means, real* chols, int calibrate, real* scalars,
+                                   void* ws_, size_t ws_bytes) {
+  return ieks_iteration_impl((cudaStream_t)s_, ctx, flags, ivp_id, params_host, nparams, N, d, q, chunk_len, qL_host,
+                             scale0, scale1, x0_mean, x0_chol, means, chols, calibrate, scalars, nullptr, 0.0, ws_,
+                             ws_bytes);
+}
+// One step of the IEKS loop WITH the stopping rule on the device (the reference's lax.while_loop body + cond,
+// solver.py:36-57): the host may enqueue several of these back to back without synchronising; once the rule has
+// fired, the remaining calls are no-ops and `means`, `chols`, `scalars` stay those of the final iteration.
+int POF_SUFFIX(pof_ieks_loop_step)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flags, int ivp_id,
+                                   const double* params_host, int nparams, int64_t N, int d, int q, int64_t chunk_len,
+                                   const double* qL_host, double scale0, double scale1, const real* x0_mean,
+                                   const real* x0_chol, real* means, real* chols, int calibrate, real* scalars,
+                                   real* loop_state, int64_t maxiters, void* ws_, size_t ws_bytes) {
+  if (!loop_state) return POF_E_ARG;
+  return ieks_iteration_impl((cudaStream_t)s_, ctx, flags, ivp_id, params_host, nparams, N, d, q, chunk_len, qL_host,
+                             scale0, scale1, x0_mean, x0_chol, means, chols, calibrate, scalars, loop_state,
+                             (double)maxiters, ws_, ws_bytes);
 }
 
 #ifndef POF_F32

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
     k_lane2_fold(LeafArgs a, real* __restrict__ fagg, real* __restrict__ faggm) {
   extern __shared__ __align__(16) real sm[];
   using LN = Lane2<d, q>;
+  if (a.stop && *a.stop != real(0)) return;  // the device-side IEKS loop has ended
   const long ch = Lane2Setup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
   typename LN::Ctx cx;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
                  real* __restrict__ part, real* __restrict__ fmeans, real* __restrict__ fchols) {
   extern __shared__ __align__(16) real sm[];
   using LN = Lane2<d, q>;
+  if (a.stop && *a.stop != real(0)) return;
   const long ch = Lane2Setup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
   typename LN::Ctx cx;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(LANE2_WARPS * 32)
                    real* __restrict__ part2) {
   extern __shared__ __align__(16) real sm[];
   using LN = Lane2<d, q>;
+  if (a.stop && *a.stop != real(0)) return;  // (means, chols and the partial sums stay those of the final iteration)
   const long ch = Lane2Setup<d, q>::chunk_of_thread();
   if (ch >= a.CS) return;
   typename LN::Ctx cx;

@@ -69,6 +69,8 @@ struct LeafArgs {
   const real* F;   // general per-step transition model (n,D,D) x 2 (QLd lower triangular), or null = the
   const real* QLd; // preconditioned IWP described by ql (tile family only)
   int tile_reg;      // tile family: register-resident Householder sweeps (default; 0 with POF_F_TILE_SMEM_QR)
+  const real* stop;  // device-side IEKS loop (pof_ieks_loop_step): if non-null and *stop != 0 the loop has ended and
+                     // every kernel that touches persistent state (or does real work) returns at once
   int no_tma;        // lane2 smoother: 0 = bulk-copy (TMA) staging of the backward kernels (POF_F_SMOOTH_TMA; measured slower)
 };
 
@@ -167,6 +169,7 @@ struct FlowArgs {
   unsigned* flag_up;        // per node: element complete   } zeroed by a stream-ordered memset before the launch
   unsigned* flag_dn;        // per node: state complete     }
   unsigned* ticket;         // the ticket counter           }
+  const real* stop;         // as LeafArgs::stop
 };
 
 struct ExchangeArgs {

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
   constexpr int FE = 3 * D * D + 2 * D, SE = 2 * D * D + D, ST = D * D + D;
   constexpr int EL = FILT ? FE : SE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (A.stop && *A.stop != real(0)) return;  // the device-side IEKS loop has ended
   typename TL::Ctx cx;
   TL::template init<G>(cx, sm + (warp * CPW + lane / G) * SMC, FILT ? TL::NMAT : TL::NMAT_S);
   const long total = A.seg_begin[A.nseg];

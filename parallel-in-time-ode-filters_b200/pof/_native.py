@@ -69,6 +69,9 @@ def _load():
         "pof_ieks_iteration_f64": (
             _c_int, [_c_dp, _c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dbl, _c_dbl,
                      _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_sz]),
+        "pof_ieks_loop_step_f64": (
+            _c_int, [_c_dp, _c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dbl, _c_dbl,
+                     _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_i64, _c_dp, _c_sz]),
         "pof_sequential_eks_f64": (
             _c_int, [_c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
                      _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
@@ -119,7 +122,8 @@ def _load():
 
 F32_ENTRY_POINTS = [
     "pof_workspace_bytes_f32", "pof_filter_combine_f32", "pof_smooth_combine_f32", "pof_linearize_ivp_f32",
-    "pof_linearize_ivp_compact_f32", "pof_linear_filtsmooth_f32", "pof_ieks_iteration_f32", "pof_shard_stage_a_f32",
+    "pof_linearize_ivp_compact_f32", "pof_linear_filtsmooth_f32", "pof_ieks_iteration_f32", "pof_ieks_loop_step_f32",
+    "pof_shard_stage_a_f32",
     "pof_shard_stage_b_f32", "pof_shard_stage_a_compact_f32", "pof_shard_stage_b_compact_f32", "pof_shard_stage_c_f32",
     "pof_shard_exchange_filter_f32", "pof_shard_exchange_smooth_f32", "pof_shard_exchange_scalars_f32",
     "pof_prior_init_f32", "pof_project_f32",
@@ -130,7 +134,7 @@ EXPORTED = [
     "pof_ctx_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops", "pof_default_chunk_len",
     "pof_workspace_bytes", "pof_filter_combine_f64", "pof_smooth_combine_f64", "pof_linearize_ivp_f64",
     "pof_linearize_ivp_compact_f64", "pof_linear_filtsmooth_f64", "pof_linear_filtsmooth_general_f64",
-    "pof_ieks_iteration_f64", "pof_sequential_eks_f64", "pof_shard_stage_a_f64", "pof_shard_stage_b_f64",
+    "pof_ieks_iteration_f64", "pof_ieks_loop_step_f64", "pof_sequential_eks_f64", "pof_shard_stage_a_f64", "pof_shard_stage_b_f64",
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_shard_stage_c_f64",
     "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64", "pof_project_f64", "pof_prior_init_f64",
     "pof_shard_exchange_supported", "pof_shard_exchange_filter_f64", "pof_shard_exchange_smooth_f64",

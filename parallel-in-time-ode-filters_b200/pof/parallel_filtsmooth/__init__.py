@@ -83,9 +83,12 @@ def run_pass(x0: MVNSqrt, qL, H, c, means_io, chols, *, d, q, calibrate, chunk_l
     return scalars
 
 
-def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len=None, scalars=None, ws=None):
+def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len=None, scalars=None, ws=None,
+                  loop_state=None, maxiters=10_000):
     """One fused IEKS iteration for a built-in IVP (linearise + pass, `pof_ieks_iteration_f64`): the body of the
-    reference's while loop (pof/solver.py:48-55 -> pof/step.py:33-45).  `lin` is `om.f._pof_lin`."""
+    reference's while loop (pof/solver.py:48-55 -> pof/step.py:33-45).  `lin` is `om.f._pof_lin`.
+    With `loop_state` (8 zeros on the device) the stopping rule is evaluated on the device too
+    (`pof_ieks_loop_step_f64`): once it has fired, further calls are no-ops."""
     N = means_io.shape[0]
     d, q = lin["d"], lin["q"]
     nat.require_cuda(x0.mean, x0.chol, means_io, chols)
@@ -102,6 +105,14 @@ def run_iteration(x0: MVNSqrt, qL, lin, means_io, chols, *, calibrate, chunk_len
     ivp_id, params = lin["builtin"]
     ph, pp = nat.host_doubles(list(params) + [0.0])
     qLh, qLp = nat.host_doubles(qL)
+    if loop_state is not None:
+        nat.require_cuda(loop_state, means_io)
+        rc = nat.fn("pof_ieks_loop_step", dt)(
+            nat.stream_ptr(), ws.ctx.ptr, nat.flags(), ivp_id, pp, len(params), N, d, q, int(chunk_len), qLp,
+            lin["scale0"], lin["scale1"], nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(means_io), nat.ptr(chols),
+            int(bool(calibrate)), nat.ptr(scalars), nat.ptr(loop_state), int(maxiters), ws.ws_ptr, ws.nbytes)
+        nat.check(rc, "pof_ieks_loop_step")
+        return scalars
     rc = nat.fn("pof_ieks_iteration", dt)(
         nat.stream_ptr(), ws.ctx.ptr, nat.flags(), ivp_id, pp, len(params), N, d, q, int(chunk_len), qLp, lin["scale0"], lin["scale1"],
         nat.ptr(x0.mean), nat.ptr(x0.chol), nat.ptr(means_io), nat.ptr(chols), int(bool(calibrate)),
@@ -115,14 +126,16 @@ class GraphedIteration:
     cost ~0.1 ms of launch gaps otherwise; CUDA streams and graphs replace the reference's jit-compiled loop body).
     All buffers are fixed: `means` is updated in place by every replay, `scalars` holds the iteration's scalars."""
 
-    def __init__(self, x0, qL, lin, means, chols, scalars, *, calibrate=True, chunk_len=None):
+    def __init__(self, x0, qL, lin, means, chols, scalars, *, calibrate=True, chunk_len=None, loop_state=None,
+                 maxiters=10_000):
         self.args = (x0, qL, lin, means, chols)
         N, dev = means.shape[0], means.device
         if chunk_len is None:
             chunk_len = nat.default_chunk_len(N, lin["d"], lin["q"], dev.index)
         # the graph bakes the workspace address in: this object owns the workspace for as long as it lives
         self.ws = nat.Workspace(N, lin["d"], lin["q"], chunk_len, dev, means.dtype)
-        self.kw = dict(calibrate=calibrate, chunk_len=chunk_len, scalars=scalars, ws=self.ws)
+        self.kw = dict(calibrate=calibrate, chunk_len=chunk_len, scalars=scalars, ws=self.ws, loop_state=loop_state,
+                       maxiters=maxiters)
         self.graph = None
 
     def _eager(self):

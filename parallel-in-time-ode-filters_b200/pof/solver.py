@@ -48,7 +48,33 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
     nll_old = obj_old = 0.0
     k = 0
     fused = None
-    while True:
+    # Built-in vector field on the register-resident kernels: the whole loop -- body AND stopping rule -- runs on the
+    # device (`pof_ieks_loop_step`: the reference's lax.while_loop, solver.py:36-57).  The host replays the captured
+    # iteration `burst` times between two reads of the loop state; iterations enqueued after the rule has fired are
+    # no-ops, so results and iteration counts are exactly those of a loop that checks after every iteration.  Small
+    # problems (an iteration of ~0.2 ms, comparable to a host round trip) run 8 iterations per read, large ones 1.
+    D_ = d * (q + 1)
+    device_loop = (lin["builtin"] is not None and not sequential
+                   and bool(nat.LIB.pof_shard_exchange_supported(D_, nat.flags())))
+    if device_loop:
+        loop_state = torch.zeros(8, dtype=dtype, device=dev)
+        fused = GraphedIteration(x0, setup["_qL"], lin, means, chols, scalars, calibrate=True, chunk_len=chunk_len,
+                                 loop_state=loop_state, maxiters=maxiters)
+        burst = 1 if N >= 2 ** 17 else 8
+        first = True
+        while True:
+            for _ in range(1 if first else burst):
+                fused()
+            if first:
+                fused.capture()
+                first = False
+            st = torch.cat([loop_state[:4], scalars]).cpu()  # the only host synchronisation of the burst
+            if float(st[0]) != 0.0:
+                break
+        k = int(st[1])
+        sc = st[4:]
+        nll, obj, ssq = float(sc[nat.S_NLL]), float(sc[nat.S_OBJ]), float(sc[nat.S_SSQ])
+    while not device_loop:
         if k >= 1:
             converged = crit_scalars(obj, obj_old, nll, nll_old, n_bad)
             if converged or not (k <= maxiters):

@@ -7,9 +7,8 @@ marshalling (pointer order, shapes, chunk lengths, workspace sizes), and the tes
 points at a kernel, not at Python.  Written when the tile kernels could not be run on a B200 (GPU budget spent).
 
     python scripts/dryrun_gpu_tests_on_host.py [-k expr]
-    POF_DRYRUN_FILE=test_gpu_parity.py python scripts/dryrun_gpu_tests_on_host.py -k "not thread and not lane1"
-        (the older parity tests through the same fake library: 47 pass; the three that do not need CUDA itself
-        -- sharded stages, torch.cuda calls -- or count roundoff-driven IEKS iterations of a different kernel family)
+    POF_DRYRUN_FILE=test_gpu_parity.py python scripts/dryrun_gpu_tests_on_host.py -k "tile"
+        (the parity tests of the tile family through the same fake library)
 """
 import ctypes
 import os
@@ -161,6 +160,9 @@ class FakeLib:
         out[0], out[1], out[2], out[3] = -sums[0], sums[3], sums[1] / (N - 1) / d, sums[2] / (N - 1) / d
         out[5] = 1.0
         return rc
+
+    def pof_shard_exchange_supported(self, D, flags):
+        return 0  # no register-resident family in the host simulator: solve() keeps its host-side loop
 
     def pof_ctx_create(self, out):
         return 0
