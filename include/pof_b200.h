@@ -182,6 +182,25 @@ int pof_ieks_loop_step_f64(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int i
                            double* chols, int calibrate, double* scalars, double* loop_state, int64_t maxiters,
                            void* ws, size_t ws_bytes);
 
+/* The WHOLE loop as one launch -- the reference's jax.lax.while_loop (pof/solver.py:36-57) as a CUDA graph: the body
+ * (one pof_ieks_loop_step on fixed buffers) sits in a WHILE conditional node whose condition the stopping-rule kernel
+ * sets on the device (cudaGraphSetConditional), so the loop runs to convergence / maxiters without the host.
+ *   create : records the body for exactly the given buffers (all pointers are baked in and must stay valid; call
+ *            after at least one eager pof_ieks_loop_step on the same workspace); no kernel runs.
+ *   launch : enqueues the loop on stream s; stream-ordered, returns at once.  loop_state is NOT reset: zero it (or
+ *            keep the count of earlier eager steps in it) before launching.  If its stop flag is already set the
+ *            launch is a no-op.
+ * Returns POF_E_UNSUPPORTED_DQ where pof_ieks_loop_step does, a CUDA error code if the driver cannot build
+ * conditional nodes (callers then fall back to enqueuing pof_ieks_loop_step themselves). */
+typedef struct pof_loop pof_loop_t;
+int pof_ieks_loop_create_f64(pof_loop_t** out, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                             int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                             double scale0, double scale1, const double* x0_mean, const double* x0_chol,
+                             double* means, double* chols, int calibrate, double* scalars, double* loop_state,
+                             int64_t maxiters, void* ws, size_t ws_bytes);
+int pof_ieks_loop_launch(pof_loop_t* loop, pof_stream_t s);
+void pof_ieks_loop_destroy(pof_loop_t* loop);
+
 /* Sequential extended Kalman smoother for a built-in IVP -- replaces
  *   pof.sequential_filtsmooth.filtsmooth(x0, dtm, om)   pof/sequential_filtsmooth/__init__.py:5-10
  * (EKF relinearised at the predicted mean of every step, filter.py:9-30, then RTS, smoother.py:8-28), the numerical
@@ -327,6 +346,11 @@ int pof_ieks_loop_step_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int i
                            double scale0, double scale1, const float* x0_mean, const float* x0_chol, float* means,
                            float* chols, int calibrate, float* scalars, float* loop_state, int64_t maxiters, void* ws,
                            size_t ws_bytes);
+int pof_ieks_loop_create_f32(pof_loop_t** out, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
+                             int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
+                             double scale0, double scale1, const float* x0_mean, const float* x0_chol, float* means,
+                             float* chols, int calibrate, float* scalars, float* loop_state, int64_t maxiters,
+                             void* ws, size_t ws_bytes);
 int pof_shard_stage_a_f32(pof_stream_t s, pof_ctx_t* ctx, uint32_t flags, int64_t n_loc, int d, int q,
                           int64_t chunk_len, const double* qL_host, const float* H, const float* c, float* carry_f,
                           void* ws, size_t ws_bytes);

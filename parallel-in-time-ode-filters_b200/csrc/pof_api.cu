@@ -920,8 +920,13 @@ int POF_SUFFIX(pof_linear_filtsmooth_general)(pof_stream_t s_, pof_ctx_t* ctx, u
 // loop_state (device, 8 values; null = a single iteration): [0] stop flag, [1] iterations done, [2] obj of the last
 // iteration, [3] nll of the last iteration.  With it every kernel returns at once when the flag is set, and k_crit
 // evaluates the reference's stopping rule (convergence_criteria.py:4-13, solver.py:36-45) on the device.
-static __global__ void k_crit(const real* __restrict__ scal, real* __restrict__ ls, double maxiters) {
-  if (ls[0] != real(0)) return;
+// In a loop graph (pof_ieks_loop_create) it also sets the WHILE node's condition.
+static __global__ void k_crit(const real* __restrict__ scal, real* __restrict__ ls, double maxiters,
+                              cudaGraphConditionalHandle cond, int has_cond) {
+  if (ls[0] != real(0)) {
+    if (has_cond) cudaGraphSetConditional(cond, 0u);
+    return;
+  }
   const double k = (double)ls[1] + 1.0;
   const double obj = (double)scal[POF_S_OBJ], nll = (double)scal[POF_S_NLL], bad = (double)scal[POF_S_NOT_CLOSE];
   const double obj_old = (double)ls[2];
@@ -932,14 +937,16 @@ static __global__ void k_crit(const real* __restrict__ scal, real* __restrict__ 
   ls[1] = (real)k;
   ls[2] = (real)obj;
   ls[3] = (real)nll;
-  ls[0] = (conv || !(k <= maxiters)) ? real(1) : real(0);
+  const bool stop = conv || !(k <= maxiters);
+  ls[0] = stop ? real(1) : real(0);
+  if (has_cond) cudaGraphSetConditional(cond, stop ? 0u : 1u);
 }
 
 static int ieks_iteration_impl(cudaStream_t s, pof_ctx_t* ctx, uint32_t flags, int ivp_id, const double* params_host,
                                int nparams, int64_t N, int d, int q, int64_t chunk_len, const double* qL_host,
                                double scale0, double scale1, const real* x0_mean, const real* x0_chol, real* means,
                                real* chols, int calibrate, real* scalars, real* loop_state, double maxiters, void* ws_,
-                               size_t ws_bytes) {
+                               size_t ws_bytes, const cudaGraphConditionalHandle* cond = nullptr) {
   if (N < 2) return POF_E_ARG;
   IvpParams P;
   if (int rc = fill_params(ivp_id, params_host, nparams, d, P)) return rc;
@@ -972,7 +979,8 @@ static int ieks_iteration_impl(cudaStream_t s, pof_ctx_t* ctx, uint32_t flags, i
   if (int rc = run_pass(s, ctx, flags, ll, a, wl, ws, N, x0_mean, x0_chol, means, chols, nullptr, nullptr, calibrate,
                         scalars))
     return rc;
-  if (loop_state) k_crit<<<1, 1, 0, s>>>(scalars, loop_state, maxiters);
+  if (loop_state)
+    k_crit<<<1, 1, 0, s>>>(scalars, loop_state, maxiters, cond ? *cond : cudaGraphConditionalHandle(), cond ? 1 : 0);
   return (int)cudaGetLastError();
 }
 
@@ -998,6 +1006,66 @@ int POF_SUFFIX(pof_ieks_loop_step)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t fla
                              scale0, scale1, x0_mean, x0_chol, means, chols, calibrate, scalars, loop_state,
                              (double)maxiters, ws_, ws_bytes);
 }
+
+// The loop as ONE graph launch: body = one loop step, recorded by stream capture into the body graph of a WHILE
+// conditional node; k_crit sets the node's condition.  (CUDA graphs in place of the reference's traced while_loop.)
+int POF_SUFFIX(pof_ieks_loop_create)(pof_loop_t** out, pof_ctx_t* ctx, uint32_t flags, int ivp_id,
+                                     const double* params_host, int nparams, int64_t N, int d, int q,
+                                     int64_t chunk_len, const double* qL_host, double scale0, double scale1,
+                                     const real* x0_mean, const real* x0_chol, real* means, real* chols, int calibrate,
+                                     real* scalars, real* loop_state, int64_t maxiters, void* ws_, size_t ws_bytes) {
+  if (!out || !loop_state) return POF_E_ARG;
+  *out = nullptr;
+  pof_loop* lp = new pof_loop();
+  cudaStream_t cs = nullptr;  // capture needs a non-default stream of its own
+  cudaGraphConditionalHandle cond;
+  cudaGraphNodeParams np = {};
+  cudaGraphNode_t node;
+  cudaGraph_t body = nullptr, captured = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaGraphCreate(&lp->graph, 0);
+  if (e == cudaSuccess) e = cudaGraphConditionalHandleCreate(&cond, lp->graph, 1, cudaGraphCondAssignDefault);
+  if (e == cudaSuccess) {
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    e = cudaGraphAddNode(&node, lp->graph, nullptr, 0, &np);
+  }
+  if (e == cudaSuccess) body = np.conditional.phGraph_out[0];
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+  if (e == cudaSuccess) {
+    rc = ieks_iteration_impl(cs, ctx, flags, ivp_id, params_host, nparams, N, d, q, chunk_len, qL_host, scale0, scale1,
+                             x0_mean, x0_chol, means, chols, calibrate, scalars, loop_state, (double)maxiters, ws_,
+                             ws_bytes, &cond);
+    e = cudaStreamEndCapture(cs, &captured);
+  }
+  if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&lp->exec, lp->graph, 0);
+  if (cs) cudaStreamDestroy(cs);
+  if (e != cudaSuccess || rc != 0) {
+    (void)cudaGetLastError();
+    if (lp->exec) cudaGraphExecDestroy(lp->exec);
+    if (lp->graph) cudaGraphDestroy(lp->graph);
+    delete lp;
+    return rc != 0 ? rc : (int)e;
+  }
+  *out = lp;
+  return 0;
+}
+
+#ifndef POF_F32
+int pof_ieks_loop_launch(pof_loop_t* lp, pof_stream_t s) {
+  if (!lp || !lp->exec) return POF_E_ARG;
+  return (int)cudaGraphLaunch(lp->exec, (cudaStream_t)s);
+}
+void pof_ieks_loop_destroy(pof_loop_t* lp) {
+  if (!lp) return;
+  if (lp->exec) cudaGraphExecDestroy(lp->exec);
+  if (lp->graph) cudaGraphDestroy(lp->graph);
+  delete lp;
+}
+#endif
 
 #ifndef POF_F32
 int POF_SUFFIX(pof_sequential_eks)(pof_stream_t s_, uint32_t flags, int ivp_id, const double* params_host, int nparams,

@@ -21,3 +21,9 @@ struct pof_ctx {
   long cnt[POF_SEG_COUNT] = {0};
 };
 
+
+// the IEKS loop as a graph with a WHILE conditional node (pof_ieks_loop_create_*)
+struct pof_loop {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};

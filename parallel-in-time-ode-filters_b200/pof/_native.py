@@ -72,6 +72,13 @@ def _load():
         "pof_ieks_loop_step_f64": (
             _c_int, [_c_dp, _c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64, _c_dp, _c_dbl, _c_dbl,
                      _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_i64, _c_dp, _c_sz]),
+        # (out, ctx, flags, ivp, params, nparams, N, d, q, chunk_len, qL, s0, s1, x0m, x0c, means, chols, calibrate,
+        #  scalars, loop_state, maxiters, ws, ws_bytes)
+        "pof_ieks_loop_create_f64": (
+            _c_int, [ctypes.POINTER(ctypes.c_void_p), _c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_i64,
+                     _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp, _c_dp, _c_dp, _c_int, _c_dp, _c_dp, _c_i64, _c_dp, _c_sz]),
+        "pof_ieks_loop_launch": (_c_int, [_c_dp, _c_dp]),
+        "pof_ieks_loop_destroy": (None, [_c_dp]),
         "pof_sequential_eks_f64": (
             _c_int, [_c_dp, U, _c_int, _c_dp, _c_int, _c_i64, _c_int, _c_int, _c_dp, _c_dbl, _c_dbl, _c_dp, _c_dp,
                      _c_dp, _c_dp, _c_dp, _c_dp, _c_sz]),
@@ -123,6 +130,7 @@ def _load():
 F32_ENTRY_POINTS = [
     "pof_workspace_bytes_f32", "pof_filter_combine_f32", "pof_smooth_combine_f32", "pof_linearize_ivp_f32",
     "pof_linearize_ivp_compact_f32", "pof_linear_filtsmooth_f32", "pof_ieks_iteration_f32", "pof_ieks_loop_step_f32",
+    "pof_ieks_loop_create_f32",
     "pof_shard_stage_a_f32",
     "pof_shard_stage_b_f32", "pof_shard_stage_a_compact_f32", "pof_shard_stage_b_compact_f32", "pof_shard_stage_c_f32",
     "pof_shard_exchange_filter_f32", "pof_shard_exchange_smooth_f32", "pof_shard_exchange_scalars_f32",
@@ -134,7 +142,8 @@ EXPORTED = [
     "pof_ctx_profile_read", "pof_launches_per_pass", "pof_measure_dfma_tflops", "pof_default_chunk_len",
     "pof_workspace_bytes", "pof_filter_combine_f64", "pof_smooth_combine_f64", "pof_linearize_ivp_f64",
     "pof_linearize_ivp_compact_f64", "pof_linear_filtsmooth_f64", "pof_linear_filtsmooth_general_f64",
-    "pof_ieks_iteration_f64", "pof_ieks_loop_step_f64", "pof_sequential_eks_f64", "pof_shard_stage_a_f64", "pof_shard_stage_b_f64",
+    "pof_ieks_iteration_f64", "pof_ieks_loop_step_f64", "pof_ieks_loop_create_f64", "pof_ieks_loop_launch",
+    "pof_ieks_loop_destroy", "pof_sequential_eks_f64", "pof_shard_stage_a_f64", "pof_shard_stage_b_f64",
     "pof_shard_stage_a_compact_f64", "pof_shard_stage_b_compact_f64", "pof_shard_stage_c_f64",
     "pof_filter_apply_chain_f64", "pof_smooth_apply_chain_f64", "pof_project_f64", "pof_prior_init_f64",
     "pof_shard_exchange_supported", "pof_shard_exchange_filter_f64", "pof_shard_exchange_smooth_f64",
@@ -157,6 +166,8 @@ def fn(base, dtype):
 # switches and reads no environment variables.
 F_FAMILY_TILE, F_TILE_SMEM_QR, F_TREE_PER_LEVEL, F_SMOOTH_TMA = 1, 2, 4, 8
 DEFAULT_FLAGS = int(os.environ.get("POF_B200_FLAGS", "0"))
+# solve(): run the IEKS loop as one CUDA graph with a WHILE conditional node (False: replay single iterations in bursts)
+USE_LOOP_GRAPH = os.environ.get("POF_B200_LOOP_GRAPH", "1") != "0"
 SEGMENTS = ["fold", "filter_up_sharded", "filter_tree", "scan", "smooth_up_side_stream", "smooth_down", "smooth"]
 
 

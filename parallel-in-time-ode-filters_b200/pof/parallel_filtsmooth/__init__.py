@@ -137,9 +137,44 @@ class GraphedIteration:
         self.kw = dict(calibrate=calibrate, chunk_len=chunk_len, scalars=scalars, ws=self.ws, loop_state=loop_state,
                        maxiters=maxiters)
         self.graph = None
+        self._loop = None
 
     def _eager(self):
         run_iteration(*self.args, **self.kw)
+
+    def capture_loop(self):
+        """Build the WHOLE loop as one CUDA graph (`pof_ieks_loop_create`: the body in a WHILE conditional node whose
+        condition the stopping-rule kernel sets on the device).  Needs `loop_state`; call after one eager iteration.
+        Returns False if the driver cannot build it (the caller then replays single iterations)."""
+        x0, qL, lin, means, chols = self.args
+        kw = self.kw
+        if kw["loop_state"] is None:
+            raise nat.NativeError("capture_loop needs a loop_state")
+        ivp_id, params = lin["builtin"]
+        ph, pp = nat.host_doubles(list(params) + [0.0])
+        qLh, qLp = nat.host_doubles(qL)
+        out = ctypes.c_void_p()
+        rc = nat.fn("pof_ieks_loop_create", means.dtype)(
+            ctypes.byref(out), self.ws.ctx.ptr, nat.flags(), ivp_id, pp, len(params), means.shape[0], lin["d"],
+            lin["q"], int(kw["chunk_len"]), qLp, lin["scale0"], lin["scale1"], nat.ptr(x0.mean), nat.ptr(x0.chol),
+            nat.ptr(means), nat.ptr(chols), int(bool(kw["calibrate"])), nat.ptr(kw["scalars"]),
+            nat.ptr(kw["loop_state"]), int(kw["maxiters"]), self.ws.ws_ptr, self.ws.nbytes)
+        if rc != 0:
+            return False
+        self._loop = out
+        return True
+
+    def launch_loop(self):
+        """enqueue the loop graph on the current stream: iterates until the device-side rule stops it"""
+        nat.check(nat.LIB.pof_ieks_loop_launch(self._loop, nat.stream_ptr()), "pof_ieks_loop_launch")
+
+    def __del__(self):
+        try:
+            if self._loop:
+                nat.LIB.pof_ieks_loop_destroy(self._loop)
+                self._loop = None
+        except Exception:
+            pass
 
     def capture(self):
         """call after at least one eager iteration (kernel attributes and workspaces exist)"""

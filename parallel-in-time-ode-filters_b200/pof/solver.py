@@ -49,10 +49,11 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
     k = 0
     fused = None
     # Built-in vector field on the register-resident kernels: the whole loop -- body AND stopping rule -- runs on the
-    # device (`pof_ieks_loop_step`: the reference's lax.while_loop, solver.py:36-57).  The host replays the captured
-    # iteration `burst` times between two reads of the loop state; iterations enqueued after the rule has fired are
-    # no-ops, so results and iteration counts are exactly those of a loop that checks after every iteration.  Small
-    # problems (an iteration of ~0.2 ms, comparable to a host round trip) run 8 iterations per read, large ones 1.
+    # device (the reference's lax.while_loop, solver.py:36-57).  After one eager iteration the remaining ones are ONE
+    # launch of a CUDA graph whose body sits in a WHILE conditional node (`pof_ieks_loop_create`); the host reads the
+    # loop state once, at the end.  Where the driver cannot build conditional nodes, a captured single iteration
+    # (`pof_ieks_loop_step`) is replayed `burst` times between two reads of the loop state instead: iterations
+    # enqueued after the rule has fired are no-ops, so results and iteration counts are the same either way.
     D_ = d * (q + 1)
     device_loop = (lin["builtin"] is not None and not sequential
                    and bool(nat.LIB.pof_shard_exchange_supported(D_, nat.flags())))
@@ -60,17 +61,19 @@ def solve(*, f, y0, ts, order, init="prior", calibrate=True, maxiters=10_000, se
         loop_state = torch.zeros(8, dtype=dtype, device=dev)
         fused = GraphedIteration(x0, setup["_qL"], lin, means, chols, scalars, calibrate=True, chunk_len=chunk_len,
                                  loop_state=loop_state, maxiters=maxiters)
-        burst = 1 if N >= 2 ** 17 else 8
-        first = True
-        while True:
-            for _ in range(1 if first else burst):
-                fused()
-            if first:
-                fused.capture()
-                first = False
-            st = torch.cat([loop_state[:4], scalars]).cpu()  # the only host synchronisation of the burst
-            if float(st[0]) != 0.0:
-                break
+        read_state = lambda: torch.cat([loop_state[:4], scalars]).cpu()  # synchronises
+        fused()
+        if nat.USE_LOOP_GRAPH and fused.capture_loop():
+            fused.launch_loop()
+            st = read_state()
+        else:
+            burst = 1 if N >= 2 ** 17 else 8
+            fused.capture()
+            st = read_state()
+            while float(st[0]) == 0.0:
+                for _ in range(burst):
+                    fused()
+                st = read_state()
         k = int(st[1])
         sc = st[4:]
         nll, obj, ssq = float(sc[nat.S_NLL]), float(sc[nat.S_OBJ]), float(sc[nat.S_SSQ])

@@ -6,9 +6,12 @@ import numpy as np, torch
 import pof.ivp
 from pof.solver import solve
 
+from pof import _native as nat
+
 ivp = pof.ivp.fitzhughnagumo()
 rows = []
-for e in [8, 10, 12, 14, 16, 19]:
+for e, graph in [(e, g) for e in [8, 10, 12, 14, 16, 19] for g in (True, False)]:
+    nat.USE_LOOP_GRAPH = graph
     ts = np.linspace(0, 100, 2 ** e)
     solve(f=ivp.f, y0=ivp.y0, ts=ts, order=3, init="constant", maxiters=1000)
     torch.cuda.synchronize()
@@ -19,7 +22,7 @@ for e in [8, 10, 12, 14, 16, 19]:
         torch.cuda.synchronize()
         best = min(best, time.perf_counter() - t0)
         its = info["iterations"]
-    rows.append({"log2n": e, "iterations": its, "solve_s": best, "ms_per_iteration_incl_setup": 1e3 * best / its})
+    rows.append({"log2n": e, "loop": "while-graph" if graph else "bursts of captured iterations", "iterations": its, "solve_s": best, "ms_per_iteration_incl_setup": 1e3 * best / its})
     print(rows[-1], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "r02_time_solves.json"), "w"), indent=1)
