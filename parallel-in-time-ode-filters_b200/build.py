@@ -72,8 +72,10 @@ def build(force=False, verbose=False):
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(op)
-        if (force or not flags_same or not os.path.exists(op)
-                or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr_time)):
+        dep_time = max(os.path.getmtime(sp), hdr_time)
+        if src.endswith("_f32.cu"):  # the fp32 translation units #include their fp64 twin
+            dep_time = max(dep_time, os.path.getmtime(os.path.join(CSRC, src.replace("_f32.cu", ".cu"))))
+        if force or not flags_same or not os.path.exists(op) or os.path.getmtime(op) < dep_time:
             jobs.append((sp, op))
 
     def run(job):

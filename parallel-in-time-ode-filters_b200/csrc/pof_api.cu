@@ -355,7 +355,7 @@ struct WsLayout {
     o_sums = take(16);
     o_misc = take((size_t)2 * ST + 64);
     flag_words = 4 * (size_t)tl.total + 64;  // [tickets (3 x 16 words) | f_up | f_dn | s_up | s_dn]
-    o_flags = take((flag_words + 1) / 2);
+    o_flags = take((flag_words * sizeof(unsigned) + sizeof(real) - 1) / sizeof(real));  // in units of the scalar type
     total = o;
   }
   unsigned* ticket(real* ws, int which) const { return (unsigned*)(ws + o_flags) + 16 * which; }

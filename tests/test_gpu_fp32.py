@@ -71,3 +71,32 @@ def test_fp32_rejects_what_it_does_not_cover(native_lib):
     ivp = pof.ivp.lorenz96(tmax=0.2, d=8)
     with pytest.raises(Exception):
         solve(f=ivp.f, y0=ivp.y0, ts=np.linspace(0, 0.2, 50), order=3, init="constant", dtype=torch.float32)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("N", [256, 5000, 70_000])
+def test_pass_stays_inside_its_workspace(native_lib, dtype, N):
+    """`pof_workspace_bytes[_f32]` must cover everything a pass touches (the dataflow flag area is 32-bit words in a
+    buffer laid out in units of the scalar type): canary bytes behind the workspace survive an iteration"""
+    import pof.ivp
+    from pof import _native as nat
+    from pof.convenience import get_initial_trajectory, set_up_solver
+    from pof.parallel_filtsmooth import run_iteration
+    from pof.utils import MVNSqrt
+
+    ivp = pof.ivp.fitzhughnagumo()
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=np.linspace(0, 10, N), order=3)
+    lin = setup["om"].f._pof_lin
+    x0 = MVNSqrt(setup["x0"].mean.to(dtype), setup["x0"].chol.to(dtype))
+    means = get_initial_trajectory(setup, method="constant", means_only=True).mean.to(dtype).contiguous()
+    chols = torch.empty((N, 8, 8), dtype=dtype, device=means.device)
+    L = nat.default_chunk_len(N, 2, 3, means.device.index)
+    ws = nat.Workspace(N, 2, 3, L, means.device, dtype)
+    tail = 1 << 16
+    big = torch.full((ws.nbytes + tail,), 0xAB, dtype=torch.uint8, device=means.device)
+    ws.buf = big  # same size handed to the library, canary behind it
+    for _ in range(2):
+        run_iteration(x0, setup["_qL"], lin, means, chols, calibrate=True, chunk_len=L, ws=ws)
+    torch.cuda.synchronize()
+    assert bool((big[ws.nbytes:] == 0xAB).all())
+    assert bool(torch.isfinite(means).all())
