@@ -36,6 +36,8 @@ typedef struct pof_p2p pof_p2p_t; /* opaque: peer-memory exchange area of one ra
 #define POF_F_SMOOTH_TMA 8u     /* smoother: bulk-copy (TMA engine, cp.async.bulk + mbarrier) staging of the per-step
                                    backward kernels instead of plain global loads.  OFF by default: measured 30x
                                    SLOWER on B200 (64 independent 1 KB streams per SM) */
+#define POF_F_TREE_UPDOWN 16u   /* filter tree: plain up-sweep / down-sweep over all levels instead of the hybrid whose
+                                   top levels are ONE Kogge-Stone scan (half the dependent levels; A/B measurement) */
 
 #define POF_E_UNSUPPORTED_DQ (-1) /* (d, q) combination not compiled in */
 #define POF_E_WORKSPACE (-2)      /* workspace too small */

@@ -325,6 +325,12 @@ struct WsLayout {
   size_t o_lin, o_faggm, o_fagg, o_fin, o_sagg, o_sin, o_sx, o_kern, o_send, o_part, o_part2, o_sums, o_misc, o_flags,
       total;  // in doubles
   size_t flag_words;  // 32-bit words of the dataflow flag area (zeroed at the start of every stage)
+  // hybrid filter sweep (FlowArgs in pof_launch.cuh): Kogge-Stone scan over the nodes of level ks_base, the lowest
+  // level narrow enough for one round of resident warps; ks_steps = 0: the tree is too shallow to gain from it
+  static constexpr long KS_MAX = 1536;
+  int ks_base, ks_steps;
+  long ks_n;
+  size_t o_ks, ks_flag_word;
   void build(long n, int d, int q, long chunk_len) {
     D = d * (q + 1);
     FE = 3 * D * D + 2 * D;
@@ -354,7 +360,15 @@ struct WsLayout {
     o_part2 = take((size_t)CS * 2);
     o_sums = take(16);
     o_misc = take((size_t)2 * ST + 64);
-    flag_words = 4 * (size_t)tl.total + 64;  // [tickets (3 x 16 words) | f_up | f_dn | s_up | s_dn]
+    ks_base = 0;
+    while (ks_base < tl.nlev - 1 && tl.sz[ks_base] > KS_MAX) ++ks_base;
+    ks_n = tl.sz[ks_base];
+    ks_steps = 0;
+    while ((1L << ks_steps) < ks_n) ++ks_steps;
+    if (D > 16 || tl.nlev - 1 - ks_base < 2) ks_steps = 0;  // register-resident trees only; needs >= 2 levels to replace
+    o_ks = take((size_t)ks_steps * ks_n * FE);
+    ks_flag_word = 4 * (size_t)tl.total + 64;
+    flag_words = ks_flag_word + (size_t)ks_steps * ks_n;  // [tickets (3 x 16 words) | f_up | f_dn | s_up | s_dn | ks]
     o_flags = take((flag_words * sizeof(unsigned) + sizeof(real) - 1) / sizeof(real));  // in units of the scalar type
     total = o;
   }
@@ -433,6 +447,38 @@ static void flow_begin(FlowArgs& fa, const WsLayout& wl, real* agg, real* st, un
   fa.flag_dn = f_dn;
   fa.ticket = ticket;
   fa.stop = nullptr;
+  fa.ks_base = fa.ks_steps = 0;
+  fa.ks_n = 0;
+  fa.ks = nullptr;
+  fa.flag_ks = nullptr;
+  fa.ks_wait = 0;
+}
+// hybrid filter sweep: up-sweep to level ks_base, Kogge-Stone scan over its nodes, states of that level from the
+// root state, down-sweep from there
+static void flow_hybrid(FlowArgs& fa, const WsLayout& wl, real* ws, const real* root_m, const real* root_L) {
+  auto seg = [&](int kind, int level, long count) {
+    fa.seg_kind[fa.nseg] = kind;
+    fa.seg_level[fa.nseg] = level;
+    fa.seg_count[fa.nseg] = count;
+    ++fa.nseg;
+  };
+  fa.ks_base = wl.ks_base;
+  fa.ks_steps = wl.ks_steps;
+  fa.ks_n = wl.ks_n;
+  fa.ks = ws + wl.o_ks;
+  fa.flag_ks = (unsigned*)(ws + wl.o_flags) + wl.ks_flag_word;
+  fa.ks_wait = 1;
+  fa.root_m = root_m;
+  fa.root_L = root_L;
+  seg(FlowArgs::ROOT, wl.tl.nlev - 1, 1);
+  if (wl.ks_base >= 1) {
+    fa.up_lo = 1;
+    fa.up_hi = wl.ks_base;
+    for (int l = 1; l <= wl.ks_base; ++l) seg(FlowArgs::UP, l, wl.tl.sz[l]);
+  }
+  for (int st = 1; st <= wl.ks_steps; ++st) seg(FlowArgs::KS, st, wl.ks_n - (1L << (st - 1)));
+  seg(FlowArgs::KS_APPLY, wl.ks_base, wl.ks_n);
+  for (int l = wl.ks_base; l >= 1; --l) seg(FlowArgs::DOWN, l, wl.tl.sz[l]);
 }
 // up-sweep: build levels 1 .. top from their children
 static void flow_up(FlowArgs& fa, const WsLayout& wl, int top) {
@@ -537,8 +583,12 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
       FlowArgs fa;
       flow_begin(fa, wl, fagg, fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
       fa.stop = a.stop;
-      if (!need_root) flow_up(fa, wl, up_top);
-      flow_down(fa, wl, root_m, root_L);
+      if (!need_root && wl.ks_steps > 0 && !(flags & POF_F_TREE_UPDOWN)) {
+        flow_hybrid(fa, wl, ws, root_m, root_L);
+      } else {
+        if (!need_root) flow_up(fa, wl, up_top);
+        flow_down(fa, wl, root_m, root_L);
+      }
       POF_CK(tl->fflow(s, fa));
     } else {
       if (!need_root)

@@ -150,7 +150,7 @@ inline cudaError_t tile_scomb(cudaStream_t, int, long, const real*, const real*,
 // a level costs one warm combine plus an L2 round trip for the flag.
 struct FlowArgs {
   static constexpr int MAXL = 40;
-  enum Kind { UP = 0, ROOT = 1, DOWN = 2, DOWN_E = 3 };
+  enum Kind { UP = 0, ROOT = 1, DOWN = 2, DOWN_E = 3, KS = 4, KS_APPLY = 5 };
   int nlev;                 // levels of the tree (level 0 = chunks)
   long off[MAXL], sz[MAXL];
   int nseg;                 // segments in execution order: segment j has seg_count[j] independent items
@@ -170,6 +170,19 @@ struct FlowArgs {
   unsigned* flag_dn;        // per node: state complete     }
   unsigned* ticket;         // the ticket counter           }
   const real* stop;         // as LeafArgs::stop
+  // ---- hybrid filter sweep: the levels above `ks_base` are replaced by ONE Kogge-Stone inclusive scan over the ks_n
+  // nodes of that level (ks_steps = ceil(log2 ks_n) dependent steps instead of 2 x that many up/down levels; the extra
+  // combines run on warps that the narrow top levels leave idle anyway).  Step s (KS segment, level = s) combines, for
+  // every node j >= 2^(s-1), the window ending at j - 2^(s-1) with the node's own window; a node's window element is
+  // final after step nbits(j) and is never copied: step s reads node j' at level min(s-1, nbits(j')).  Level 0 = the
+  // elements of tree level ks_base (agg), level s >= 1 = ks + (s-1) * ks_n elements.  KS_APPLY then turns the
+  // inclusive elements into incoming states: state(j) = root state (+) element(j-1), and the down-sweep continues
+  // from level ks_base.
+  int ks_base, ks_steps;
+  long ks_n;
+  real* ks;
+  unsigned* flag_ks;        // ks_steps x ks_n, zeroed with the other flags
+  int ks_wait;              // 1: the KS elements are built by this launch (wait for their flags); 0: complete before
 };
 
 struct ExchangeArgs {

@@ -84,6 +84,17 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Kogge-Stone stage of the hybrid filter sweep (FlowArgs): where node j's window element lives and which flag says so
+__device__ __forceinline__ int ks_nbits(long j) { return j == 0 ? 0 : 64 - __clzll(j); }
+template <int EL>
+__device__ __forceinline__ real* ks_elem(const FlowArgs& A, int l, long j) {
+  return l == 0 ? A.agg + (A.off[A.ks_base] + j) * EL : A.ks + ((long)(l - 1) * A.ks_n + j) * EL;
+}
+__device__ __forceinline__ const unsigned* ks_flag(const FlowArgs& A, int l, long j) {
+  if (l == 0) return (A.ks_base >= A.up_lo && A.ks_base <= A.up_hi) ? A.flag_up + A.off[A.ks_base] + j : nullptr;
+  return A.ks_wait ? A.flag_ks + (long)(l - 1) * A.ks_n + j : nullptr;
+}
+
 template <int D, bool FILT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
   extern __shared__ __align__(16) real sm[];
@@ -129,6 +140,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
       dep0 = A.flag_dn + A.off[lev] + i;
       const long e = FILT ? 2 * i : 2 * i + 1;  // the child element the combine reads
       if (2 * i + 1 < A.sz[lev - 1] && lev - 1 >= A.up_lo && lev - 1 <= A.up_hi) dep1 = A.flag_up + A.off[lev - 1] + e;
+    } else if (live && kind == FlowArgs::KS) {
+      // step lev: node j = i + 2^(lev-1); (window ending at i, as final as it is after step lev-1) (+) (own window)
+      const int la = min(lev - 1, ks_nbits(i));
+      dep0 = ks_flag(A, la, i);
+      dep1 = ks_flag(A, lev - 1, i + (1L << (lev - 1)));
+    } else if (live && kind == FlowArgs::KS_APPLY) {
+      dep0 = A.flag_dn + A.off[A.nlev - 1];
+      if (i >= 1) dep1 = ks_flag(A, ks_nbits(i - 1), i - 1);
     }
     while (true) {
       const bool ok = (!dep0 || ld_acquire(dep0) != 0u) && (!dep1 || ld_acquire(dep1) != 0u);
@@ -149,6 +168,28 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
         __threadfence();
         cx.sync();
         if (cx.r == 0) st_release(A.flag_up + A.off[lev] + i, 1u);
+      } else if (kind == FlowArgs::KS) {
+        if constexpr (FILT) {
+          const long j = i + (1L << (lev - 1));
+          TL::template filter_combine<false>(cx, ks_elem<EL>(A, min(lev - 1, ks_nbits(i)), i),
+                                             ks_elem<EL>(A, lev - 1, j), ks_elem<EL>(A, lev, j));
+          __threadfence();
+          cx.sync();
+          if (cx.r == 0) st_release(A.flag_ks + (long)(lev - 1) * A.ks_n + j, 1u);
+        }
+      } else if (kind == FlowArgs::KS_APPLY) {
+        if constexpr (FILT) {
+          const real* root = A.st + A.off[A.nlev - 1] * ST;
+          real* out = A.st + (A.off[A.ks_base] + i) * ST;
+          if (i == 0) {
+            if (out != root) group_copy<D, G>(cx.r, out, root, ST);
+          } else {
+            TL::template filter_combine<true>(cx, root, ks_elem<EL>(A, ks_nbits(i - 1), i - 1), out);
+          }
+          __threadfence();
+          cx.sync();
+          if (cx.r == 0) st_release(A.flag_dn + A.off[A.ks_base] + i, 1u);
+        }
       } else if (kind == FlowArgs::ROOT) {
         if (A.root_m) {
           real* r = A.st + A.off[A.nlev - 1] * ST;

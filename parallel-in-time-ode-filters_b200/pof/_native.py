@@ -164,7 +164,7 @@ def fn(base, dtype):
 # kernel-family flags of the C ABI (include/pof_b200.h).  DEFAULT_FLAGS is what the facade passes; tests / scripts may
 # change it (e.g. F_FAMILY_TILE to run the large-state kernels on small problems) -- the library itself holds no
 # switches and reads no environment variables.
-F_FAMILY_TILE, F_TILE_SMEM_QR, F_TREE_PER_LEVEL, F_SMOOTH_TMA = 1, 2, 4, 8
+F_FAMILY_TILE, F_TILE_SMEM_QR, F_TREE_PER_LEVEL, F_SMOOTH_TMA, F_TREE_UPDOWN = 1, 2, 4, 8, 16
 DEFAULT_FLAGS = int(os.environ.get("POF_B200_FLAGS", "0"))
 # solve(): run the IEKS loop as one CUDA graph with a WHILE conditional node (False: replay single iterations in bursts)
 USE_LOOP_GRAPH = os.environ.get("POF_B200_LOOP_GRAPH", "1") != "0"
