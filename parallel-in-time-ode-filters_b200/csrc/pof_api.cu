@@ -453,32 +453,45 @@ static void flow_begin(FlowArgs& fa, const WsLayout& wl, real* agg, real* st, un
   fa.flag_ks = nullptr;
   fa.ks_wait = 0;
 }
-// hybrid filter sweep: up-sweep to level ks_base, Kogge-Stone scan over its nodes, states of that level from the
-// root state, down-sweep from there
-static void flow_hybrid(FlowArgs& fa, const WsLayout& wl, real* ws, const real* root_m, const real* root_L) {
-  auto seg = [&](int kind, int level, long count) {
-    fa.seg_kind[fa.nseg] = kind;
-    fa.seg_level[fa.nseg] = level;
-    fa.seg_count[fa.nseg] = count;
-    ++fa.nseg;
-  };
+// hybrid filter sweep, first half: up-sweep to level ks_base, Kogge-Stone scan over its nodes (the last node's final
+// element is the aggregate of the whole sequence: the time-sharded form's carry, ks_total())
+static void flow_seg(FlowArgs& fa, int kind, int level, long count) {
+  fa.seg_kind[fa.nseg] = kind;
+  fa.seg_level[fa.nseg] = level;
+  fa.seg_count[fa.nseg] = count;
+  ++fa.nseg;
+}
+static bool use_hybrid(const WsLayout& wl, unsigned flags) { return wl.ks_steps > 0 && !(flags & POF_F_TREE_UPDOWN); }
+static void flow_hybrid_fields(FlowArgs& fa, const WsLayout& wl, real* ws, int ks_wait) {
   fa.ks_base = wl.ks_base;
   fa.ks_steps = wl.ks_steps;
   fa.ks_n = wl.ks_n;
   fa.ks = ws + wl.o_ks;
   fa.flag_ks = (unsigned*)(ws + wl.o_flags) + wl.ks_flag_word;
-  fa.ks_wait = 1;
-  fa.root_m = root_m;
-  fa.root_L = root_L;
-  seg(FlowArgs::ROOT, wl.tl.nlev - 1, 1);
+  fa.ks_wait = ks_wait;
+}
+static void flow_hybrid_up(FlowArgs& fa, const WsLayout& wl, real* ws) {
+  flow_hybrid_fields(fa, wl, ws, 1);
   if (wl.ks_base >= 1) {
     fa.up_lo = 1;
     fa.up_hi = wl.ks_base;
-    for (int l = 1; l <= wl.ks_base; ++l) seg(FlowArgs::UP, l, wl.tl.sz[l]);
+    for (int l = 1; l <= wl.ks_base; ++l) flow_seg(fa, FlowArgs::UP, l, wl.tl.sz[l]);
   }
-  for (int st = 1; st <= wl.ks_steps; ++st) seg(FlowArgs::KS, st, wl.ks_n - (1L << (st - 1)));
-  seg(FlowArgs::KS_APPLY, wl.ks_base, wl.ks_n);
-  for (int l = wl.ks_base; l >= 1; --l) seg(FlowArgs::DOWN, l, wl.tl.sz[l]);
+  for (int st = 1; st <= wl.ks_steps; ++st) flow_seg(fa, FlowArgs::KS, st, wl.ks_n - (1L << (st - 1)));
+}
+static const real* ks_total(const WsLayout& wl, const real* ws) {  // ks_steps >= 1: the last node's level is ks_steps
+  return ws + wl.o_ks + ((size_t)(wl.ks_steps - 1) * wl.ks_n + (wl.ks_n - 1)) * wl.FE;
+}
+// second half: states of level ks_base from the root state, down-sweep from there.  ks_wait = 0: the Kogge-Stone
+// elements were completed by an earlier launch.
+static void flow_hybrid_down(FlowArgs& fa, const WsLayout& wl, real* ws, const real* root_m, const real* root_L,
+                             int ks_wait) {
+  flow_hybrid_fields(fa, wl, ws, ks_wait);
+  fa.root_m = root_m;
+  fa.root_L = root_L;
+  flow_seg(fa, FlowArgs::ROOT, wl.tl.nlev - 1, 1);
+  flow_seg(fa, FlowArgs::KS_APPLY, wl.ks_base, wl.ks_n);
+  for (int l = wl.ks_base; l >= 1; --l) flow_seg(fa, FlowArgs::DOWN, l, wl.tl.sz[l]);
 }
 // up-sweep: build levels 1 .. top from their children
 static void flow_up(FlowArgs& fa, const WsLayout& wl, int top) {
@@ -551,7 +564,8 @@ static int stage_a(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
     FlowArgs fa;
     flow_begin(fa, wl, fagg, ws + wl.o_fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
     fa.stop = a.stop;
-    flow_up(fa, wl, wl.tl.nlev - 1);
+    if (use_hybrid(wl, flags)) flow_hybrid_up(fa, wl, ws);
+    else flow_up(fa, wl, wl.tl.nlev - 1);
     if (fa.nseg) POF_CK(tl->fflow(s, fa));
     return 0;
   }
@@ -583,8 +597,9 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
       FlowArgs fa;
       flow_begin(fa, wl, fagg, fin, wl.flags(ws, FL_FUP), wl.flags(ws, FL_FDN), wl.ticket(ws, TK_FILTER));
       fa.stop = a.stop;
-      if (!need_root && wl.ks_steps > 0 && !(flags & POF_F_TREE_UPDOWN)) {
-        flow_hybrid(fa, wl, ws, root_m, root_L);
+      if (use_hybrid(wl, flags)) {
+        if (!need_root) flow_hybrid_up(fa, wl, ws);
+        flow_hybrid_down(fa, wl, ws, root_m, root_L, need_root ? 0 : 1);
       } else {
         if (!need_root) flow_up(fa, wl, up_top);
         flow_down(fa, wl, root_m, root_L);
@@ -1175,8 +1190,11 @@ static int shard_a(cudaStream_t s, pof_ctx* ctx, uint32_t flags, int64_t n_loc, 
   real* ws = (real*)ws_;
   if (int rc = zero_flags(s, wl, ws)) return rc;
   if (int rc = stage_a(s, ctx, flags, ll, a, wl, ws, true)) return rc;
-  POF_CK(cudaMemcpyAsync(carry_f, ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE, wl.FE * sizeof(real),
-                         cudaMemcpyDeviceToDevice, s));
+  // the shard's carry = aggregate of all its chunks: the tree's root element, or with the hybrid sweep the final
+  // element of the last Kogge-Stone node
+  const bool hybrid = tree_for(ll, wl.D, flags) && !(flags & POF_F_TREE_PER_LEVEL) && use_hybrid(wl, flags);
+  const real* total = hybrid ? ks_total(wl, ws) : ws + wl.o_fagg + wl.tl.off[wl.tl.nlev - 1] * wl.FE;
+  POF_CK(cudaMemcpyAsync(carry_f, total, wl.FE * sizeof(real), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 static int shard_b(cudaStream_t s, pof_ctx* ctx, uint32_t flags, int64_t n_loc, int d, int q, int64_t chunk_len,
