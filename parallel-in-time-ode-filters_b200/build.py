@@ -23,7 +23,7 @@ SOURCES = [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-]
+] + os.environ.get("POF_NVCC_EXTRA", "").split()  # e.g. -DPOF_TUNE: tuning hooks of scripts/tune_tree.py (never shipped)
 
 
 HASH = LIB + ".srchash"

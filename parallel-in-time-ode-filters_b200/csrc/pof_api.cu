@@ -326,8 +326,15 @@ struct WsLayout {
       total;  // in doubles
   size_t flag_words;  // 32-bit words of the dataflow flag area (zeroed at the start of every stage)
   // hybrid filter sweep (FlowArgs in pof_launch.cuh): Kogge-Stone scan over the nodes of level ks_base, the lowest
-  // level narrow enough for one round of resident warps; ks_steps = 0: the tree is too shallow to gain from it
-  static constexpr long KS_MAX = 1536;
+  // level with at most KS_MAX nodes; ks_steps = 0: the tree is too shallow to gain from it.  KS_MAX measured on B200
+  // (scripts/tune_tree.py, profiles/r02t_tune_tree.json): flat between 192 and 3072 -- a wider base saves levels but
+  // its steps get slower (1184 concurrent combines: 12-14 us per step; 256: 8.4 us) -- 384 is best or within noise of
+  // the best at every N: one combining warp per SM and step at 9472 chunks.
+#if defined(POF_TUNE) && !defined(POF_F32)
+  static long KS_MAX;
+#else
+  static constexpr long KS_MAX = 384;
+#endif
   int ks_base, ks_steps;
   long ks_n;
   size_t o_ks, ks_flag_word;
@@ -428,6 +435,25 @@ static int make_args(long n, int d, int q, const double* qL_host, const real* H,
   return 0;
 }
 
+#if defined(POF_TUNE) && !defined(POF_F32)
+long WsLayout::KS_MAX = 384;
+int g_poll_ns = 64;
+extern "C" void pof_tune_ks_max(long v) { WsLayout::KS_MAX = v; }
+extern "C" void pof_tune_poll_ns(int v) { g_poll_ns = v; }
+// out: [flag area offset in bytes, nodes in total, levels, ks_base, ks_steps, ks_n, ks_flag_word, sz[0..levels)]
+extern "C" void pof_tune_flag_layout(long n, int d, int q, long chunk_len, long* out) {
+  WsLayout wl;
+  wl.build(n, d, q, chunk_len);
+  out[0] = (long)(wl.o_flags * sizeof(real));
+  out[1] = wl.tl.total;
+  out[2] = wl.tl.nlev;
+  out[3] = wl.ks_base;
+  out[4] = wl.ks_steps;
+  out[5] = wl.ks_n;
+  out[6] = (long)wl.ks_flag_word;
+  for (int l = 0; l < wl.tl.nlev; ++l) out[7 + l] = wl.tl.sz[l];
+}
+#endif
 // ---- dataflow sweeps (FlowArgs, pof_launch.cuh)
 static void flow_begin(FlowArgs& fa, const WsLayout& wl, real* agg, real* st, unsigned* f_up, unsigned* f_dn,
                        unsigned* ticket) {
@@ -452,6 +478,11 @@ static void flow_begin(FlowArgs& fa, const WsLayout& wl, real* agg, real* st, un
   fa.ks = nullptr;
   fa.flag_ks = nullptr;
   fa.ks_wait = 0;
+#if defined(POF_TUNE) && !defined(POF_F32)
+  fa.poll_ns = g_poll_ns;
+#else
+  fa.poll_ns = 64;
+#endif
 }
 // hybrid filter sweep, first half: up-sweep to level ks_base, Kogge-Stone scan over its nodes (the last node's final
 // element is the aggregate of the whole sequence: the time-sharded form's carry, ks_total())

@@ -183,6 +183,7 @@ struct FlowArgs {
   real* ks;
   unsigned* flag_ks;        // ks_steps x ks_n, zeroed with the other flags
   int ks_wait;              // 1: the KS elements are built by this launch (wait for their flags); 0: complete before
+  int poll_ns;              // back-off between two polls of the dependency flags
 };
 
 struct ExchangeArgs {

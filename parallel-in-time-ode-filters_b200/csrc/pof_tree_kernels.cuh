@@ -81,6 +81,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+#ifdef POF_TUNE
+  // tuning builds: the flag value is a time stamp (ns, low 31 bits) so that the host can read when each node completed
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  v = (unsigned)(t & 0x7fffffffu) | 0x80000000u;
+#endif
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
@@ -152,44 +158,53 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
     while (true) {
       const bool ok = (!dep0 || ld_acquire(dep0) != 0u) && (!dep1 || ld_acquire(dep1) != 0u);
       if (__all_sync(0xffffffffu, ok)) break;
-      __nanosleep(64);
+      if (A.poll_ns > 0) __nanosleep(A.poll_ns);
     }
     __syncwarp();
     if (live) {
+      // ONE call site per combine form: the element-form and the state-form combine are ~4000 straight-line
+      // instructions each; inlined once per item kind the kernel was 257 KB of code, and (measured with time-stamped
+      // flags) every change of kind cost an extra ~8 us of cold instruction fetches on the critical path.
+      const real* in1 = nullptr;   // element form: earlier (filter) / later (smoother) element; state form: the state
+      const real* in2 = nullptr;
+      real* outp = nullptr;
+      int form = 0;                // 0: no combine, 1: element form, 2: state form
+      const real* cp_src = nullptr;
+      real* cp_dst = nullptr;
+      int cp_n = 0;
+      unsigned* rel0 = nullptr;
+      unsigned* rel1 = nullptr;
       if (kind == FlowArgs::UP) {
         const real* lc = A.agg + (A.off[lev - 1] + 2 * i) * EL;
         real* pa = A.agg + (A.off[lev] + i) * EL;
         if (2 * i + 1 < A.sz[lev - 1]) {
-          if constexpr (FILT) TL::template filter_combine<false>(cx, lc, lc + EL, pa);
-          else TL::template smooth_combine<false>(cx, lc + EL, lc, pa);
+          form = 1;
+          in1 = FILT ? lc : lc + EL;
+          in2 = FILT ? lc + EL : lc;
+          outp = pa;
         } else {
-          group_copy<D, G>(cx.r, pa, lc, EL);
+          cp_src = lc, cp_dst = pa, cp_n = EL;
         }
-        __threadfence();
-        cx.sync();
-        if (cx.r == 0) st_release(A.flag_up + A.off[lev] + i, 1u);
+        rel0 = A.flag_up + A.off[lev] + i;
       } else if (kind == FlowArgs::KS) {
-        if constexpr (FILT) {
-          const long j = i + (1L << (lev - 1));
-          TL::template filter_combine<false>(cx, ks_elem<EL>(A, min(lev - 1, ks_nbits(i)), i),
-                                             ks_elem<EL>(A, lev - 1, j), ks_elem<EL>(A, lev, j));
-          __threadfence();
-          cx.sync();
-          if (cx.r == 0) st_release(A.flag_ks + (long)(lev - 1) * A.ks_n + j, 1u);
-        }
+        const long j = i + (1L << (lev - 1));
+        form = 1;
+        in1 = ks_elem<EL>(A, min(lev - 1, ks_nbits(i)), i);
+        in2 = ks_elem<EL>(A, lev - 1, j);
+        outp = ks_elem<EL>(A, lev, j);
+        rel0 = A.flag_ks + (long)(lev - 1) * A.ks_n + j;
       } else if (kind == FlowArgs::KS_APPLY) {
-        if constexpr (FILT) {
-          const real* root = A.st + A.off[A.nlev - 1] * ST;
-          real* out = A.st + (A.off[A.ks_base] + i) * ST;
-          if (i == 0) {
-            if (out != root) group_copy<D, G>(cx.r, out, root, ST);
-          } else {
-            TL::template filter_combine<true>(cx, root, ks_elem<EL>(A, ks_nbits(i - 1), i - 1), out);
-          }
-          __threadfence();
-          cx.sync();
-          if (cx.r == 0) st_release(A.flag_dn + A.off[A.ks_base] + i, 1u);
+        const real* root = A.st + A.off[A.nlev - 1] * ST;
+        real* out = A.st + (A.off[A.ks_base] + i) * ST;
+        if (i == 0) {
+          if (out != root) cp_src = root, cp_dst = out, cp_n = ST;
+        } else {
+          form = 2;
+          in1 = root;
+          in2 = ks_elem<EL>(A, ks_nbits(i - 1), i - 1);
+          outp = out;
         }
+        rel0 = A.flag_dn + A.off[A.ks_base] + i;
       } else if (kind == FlowArgs::ROOT) {
         if (A.root_m) {
           real* r = A.st + A.off[A.nlev - 1] * ST;
@@ -200,51 +215,51 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
           real* r = A.sx + A.off[A.nlev - 1] * SE;
           for (int j = cx.r; j < SE; j += G) r[j] = (j >= D && j < D + D * D && (j - D) / D == (j - D) % D) ? 1.0 : 0.0;
         }
-        __threadfence();
-        cx.sync();
-        if (cx.r == 0) st_release(A.flag_dn + A.off[A.nlev - 1], 1u);
+        rel0 = A.flag_dn + A.off[A.nlev - 1];
       } else if (kind == FlowArgs::DOWN_E) {
-        if constexpr (!FILT) {
-          // exclusive-suffix ELEMENTS: X(right child) = X(parent); X(left child) = op(later = X(parent), right child)
-          const real* px = A.sx + (A.off[lev] + i) * SE;
-          const real* el = A.agg + A.off[lev - 1] * SE;
-          real* cxs = A.sx + A.off[lev - 1] * SE;
-          const bool two = 2 * i + 1 < A.sz[lev - 1];
-          if (two) {
-            group_copy<D, G>(cx.r, cxs + (2 * i + 1) * SE, px, SE);
-            TL::template smooth_combine<false>(cx, px, el + (2 * i + 1) * SE, cxs + 2 * i * SE);
-          } else {
-            group_copy<D, G>(cx.r, cxs + 2 * i * SE, px, SE);
-          }
-          __threadfence();
-          cx.sync();
-          if (cx.r == 0) {
-            st_release(A.flag_dn + A.off[lev - 1] + 2 * i, 1u);
-            if (two) st_release(A.flag_dn + A.off[lev - 1] + 2 * i + 1, 1u);
-          }
+        // exclusive-suffix ELEMENTS: X(right child) = X(parent); X(left child) = op(later = X(parent), right child)
+        const real* px = A.sx + (A.off[lev] + i) * SE;
+        const real* el = A.agg + A.off[lev - 1] * SE;
+        real* cxs = A.sx + A.off[lev - 1] * SE;
+        const bool two = 2 * i + 1 < A.sz[lev - 1];
+        cp_src = px, cp_dst = cxs + (two ? 2 * i + 1 : 2 * i) * SE, cp_n = SE;
+        if (two) {
+          form = 1;
+          in1 = px;
+          in2 = el + (2 * i + 1) * SE;
+          outp = cxs + 2 * i * SE;
+          rel1 = A.flag_dn + A.off[lev - 1] + 2 * i + 1;
         }
-      } else {
+        rel0 = A.flag_dn + A.off[lev - 1] + 2 * i;
+      } else {  // DOWN, state form
         const real* p = A.st + (A.off[lev] + i) * ST;
         const real* el = A.agg + A.off[lev - 1] * EL;
         real* cs = A.st + A.off[lev - 1] * ST;
         const bool two = 2 * i + 1 < A.sz[lev - 1];
-        if constexpr (FILT) {
-          group_copy<D, G>(cx.r, cs + 2 * i * ST, p, ST);
-          if (two) TL::template filter_combine<true>(cx, p, el + 2 * i * EL, cs + (2 * i + 1) * ST);
-        } else {
-          if (two) {
-            group_copy<D, G>(cx.r, cs + (2 * i + 1) * ST, p, ST);
-            TL::template smooth_combine<true>(cx, p, el + (2 * i + 1) * EL, cs + 2 * i * ST);
-          } else {
-            group_copy<D, G>(cx.r, cs + 2 * i * ST, p, ST);
-          }
+        // filter: the left child starts where its parent starts; smoother: the right child ends where its parent ends
+        cp_src = p, cp_dst = cs + ((FILT || !two) ? 2 * i : 2 * i + 1) * ST, cp_n = ST;
+        if (two) {
+          form = 2;
+          in1 = p;
+          in2 = el + (FILT ? 2 * i : 2 * i + 1) * EL;
+          outp = cs + (FILT ? 2 * i + 1 : 2 * i) * ST;
+          rel1 = A.flag_dn + A.off[lev - 1] + 2 * i + 1;
         }
-        __threadfence();
-        cx.sync();
-        if (cx.r == 0) {
-          st_release(A.flag_dn + A.off[lev - 1] + 2 * i, 1u);
-          if (two) st_release(A.flag_dn + A.off[lev - 1] + 2 * i + 1, 1u);
-        }
+        rel0 = A.flag_dn + A.off[lev - 1] + 2 * i;
+      }
+      if (cp_n) group_copy<D, G>(cx.r, cp_dst, cp_src, cp_n);
+      if (form == 1) {
+        if constexpr (FILT) TL::template filter_combine<false>(cx, in1, in2, outp);
+        else TL::template smooth_combine<false>(cx, in1, in2, outp);
+      } else if (form == 2) {
+        if constexpr (FILT) TL::template filter_combine<true>(cx, in1, in2, outp);
+        else TL::template smooth_combine<true>(cx, in1, in2, outp);
+      }
+      __threadfence();
+      cx.sync();
+      if (cx.r == 0) {
+        if (rel0) st_release(rel0, 1u);
+        if (rel1) st_release(rel1, 1u);
       }
     }
     __syncwarp();
