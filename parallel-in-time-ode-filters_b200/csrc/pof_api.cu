@@ -337,7 +337,7 @@ struct WsLayout {
 #endif
   int ks_base, ks_steps;
   long ks_n;
-  size_t o_ks, ks_flag_word;
+  size_t o_ks, ks_flag_word, o_ks_s, ks_flag_word_s;  // filter scan; smoother (suffix) scan
   void build(long n, int d, int q, long chunk_len) {
     D = d * (q + 1);
     FE = 3 * D * D + 2 * D;
@@ -375,7 +375,9 @@ struct WsLayout {
     if (D > 16 || tl.nlev - 1 - ks_base < 2) ks_steps = 0;  // register-resident trees only; needs >= 2 levels to replace
     o_ks = take((size_t)ks_steps * ks_n * FE);
     ks_flag_word = 4 * (size_t)tl.total + 64;
-    flag_words = ks_flag_word + (size_t)ks_steps * ks_n;  // [tickets (3 x 16 words) | f_up | f_dn | s_up | s_dn | ks]
+    o_ks_s = take((size_t)ks_steps * ks_n * SE);
+    ks_flag_word_s = ks_flag_word + (size_t)ks_steps * ks_n;
+    flag_words = ks_flag_word_s + (size_t)ks_steps * ks_n;  // [tickets (3 x 16) | f_up | f_dn | s_up | s_dn | ks | ks_s]
     o_flags = take((flag_words * sizeof(unsigned) + sizeof(real) - 1) / sizeof(real));  // in units of the scalar type
     total = o;
   }
@@ -566,11 +568,35 @@ static void flow_down_elem(FlowArgs& fa, const WsLayout& wl, real* sx) {
     ++fa.nseg;
   }
 }
+// smoother, element-form suffix scan as a hybrid sweep: up-sweep to level ks_base, Kogge-Stone SUFFIX scan over its
+// nodes, "everything later" aggregates of that level, element-form down-sweep from there
+static void flow_hybrid_suffix(FlowArgs& fa, const WsLayout& wl, real* ws) {
+  flow_hybrid_fields(fa, wl, ws, 1);
+  fa.ks = ws + wl.o_ks_s;
+  fa.flag_ks = (unsigned*)(ws + wl.o_flags) + wl.ks_flag_word_s;
+  fa.sx = ws + wl.o_sx;
+  fa.root_m = fa.root_L = nullptr;
+  if (wl.ks_base >= 1) {
+    fa.up_lo = 1;
+    fa.up_hi = wl.ks_base;
+    for (int l = 1; l <= wl.ks_base; ++l) flow_seg(fa, FlowArgs::UP, l, wl.tl.sz[l]);
+  }
+  for (int st = 1; st <= wl.ks_steps; ++st) flow_seg(fa, FlowArgs::KS, st, wl.ks_n - (1L << (st - 1)));
+  flow_seg(fa, FlowArgs::KS_APPLY, wl.ks_base, wl.ks_n);
+  for (int l = wl.ks_base; l >= 1; --l) flow_seg(fa, FlowArgs::DOWN_E, l, wl.tl.sz[l]);
+}
 // Element-form suffix scan of the smoother (its whole tree work runs concurrently with the filter scan, one state
 // combine per chunk remains afterwards) pays when the filter scan is long enough to hide it: 2 x log2(#chunks)
 // general smoothing combines against log2(#chunks) cheaper state-form ones after the scan.  Measured on B200 (FHN,
 // D = 8): break-even at ~40 steps per chunk (N ~ 2^18.5); below that the state-form down-sweep stays.
-static bool elem_suffix(const WsLayout& wl) { return wl.L >= 48; }
+// With the hybrid sweep (one GPU) the element-form scan has ~half the dependent steps: it then also pays for shorter
+// chunks as long as there are enough of them (>= 1024: below that the state-form sweep after the scan is as short).
+static bool hybrid_suffix(const WsLayout& wl, unsigned flags, bool sharded) {
+  return !sharded && use_hybrid(wl, flags) && (wl.L >= 48 || wl.CS >= 1024);
+}
+static bool elem_suffix(const WsLayout& wl, unsigned flags, bool sharded) {
+  return wl.L >= 48 || hybrid_suffix(wl, flags, sharded);
+}
 static int zero_flags(cudaStream_t s, const WsLayout& wl, real* ws) {
   POF_CK(cudaMemsetAsync(ws + wl.o_flags, 0, wl.flag_words * sizeof(unsigned), s));
   return 0;
@@ -673,8 +699,12 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
       FlowArgs fa;
       flow_begin(fa, wl, sagg, ws + wl.o_sin, wl.flags(ws, FL_SUP), wl.flags(ws, FL_SDN), wl.ticket(ws, TK_SUP));
       fa.stop = a.stop;
-      flow_up(fa, wl, up_top);
-      if (elem_suffix(wl)) flow_down_elem(fa, wl, ws + wl.o_sx);
+      if (hybrid_suffix(wl, flags, need_root)) {
+        flow_hybrid_suffix(fa, wl, ws);
+      } else {
+        flow_up(fa, wl, up_top);
+        if (elem_suffix(wl, flags, need_root)) flow_down_elem(fa, wl, ws + wl.o_sx);
+      }
       if (fa.nseg) POF_CK(tl->sflow(st, fa));
       return 0;
     }
@@ -710,7 +740,7 @@ static int stage_b(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
 // stage C: smoother down-sweep from the seed (root_m, root_L) + smoother scan + smoother scalars
 static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunch* ll, const LeafArgs& a,
                    const WsLayout& wl, real* ws, const real* root_m, const real* root_L, int emit_t0,
-                   const real* cscale, real* means, real* chols, real* scalars) {
+                   const real* cscale, real* means, real* chols, real* scalars, bool sharded) {
   real* sagg = ws + wl.o_sagg;
   real* sin_ = ws + wl.o_sin;
   const TreeLaunch* tl = tree_for(ll, wl.D, flags);
@@ -718,7 +748,7 @@ static int stage_c(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaunc
   {
     ProfScope ps(ctx, POF_SEG_SDOWN, s);
     if (!per_level) {
-      if (elem_suffix(wl)) {
+      if (elem_suffix(wl, flags, sharded)) {
         // seeds of all chunks at once: (terminal state) combined with the chunk's "everything later" aggregate
         POF_CK(tl->sseed(s, root_m, 1, ws + wl.o_sx, sin_, wl.CS));
       } else {
@@ -764,7 +794,8 @@ static int run_pass(cudaStream_t s, pof_ctx* ctx, unsigned flags, const LeafLaun
     return rc;
   // terminal smoothing state = filtered state at the last time point
   const real* term = ws + wl.o_send + (wl.CS - 1) * wl.ST;
-  return stage_c(s, ctx, flags, ll, a, wl, ws, term, term + wl.D, 1, scalars + POF_S_CSCALE, means, chols, scalars);
+  return stage_c(s, ctx, flags, ll, a, wl, ws, term, term + wl.D, 1, scalars + POF_S_CSCALE, means, chols, scalars,
+                 false);
 }
 
 static int fill_params(int ivp_id, const double* params_host, int nparams, int d, IvpParams& P) {
@@ -850,7 +881,7 @@ int64_t pof_launches_per_pass(int64_t N, int d, int q, int64_t chunk_len, uint32
   const int64_t leaf = 3, chunkk = 1, reduce = 2;
   if (tl && !(flags & POF_F_TREE_PER_LEVEL)) {
     // smoother: element-form suffix scan (1) + chunk seeds (1), or up-sweep (1 if it has a level to build) + down-sweep
-    const int64_t sm = elem_suffix(wl) ? 2 : ((wl.tl.nlev >= 3 ? 1 : 0) + 1);
+    const int64_t sm = elem_suffix(wl, flags, false) ? 2 : ((wl.tl.nlev >= 3 ? 1 : 0) + 1);
     return leaf + chunkk + reduce + 1 /*filter tree*/ + sm;
   }
   const int up_total = wl.tl.nlev >= 2 ? wl.tl.nlev - 2 : 0;  // the root combine is skipped on one GPU
@@ -1293,7 +1324,8 @@ int POF_SUFFIX(pof_shard_stage_c)(pof_stream_t s_, pof_ctx_t* ctx, uint32_t flag
   const long shift = has_row0 ? 0 : 1;
   real* mb = means - shift * wl.D;
   real* cb = chols ? chols - shift * (long)wl.D * wl.D : nullptr;
-  if (int rc = stage_c(s, ctx, flags, ll, a, wl, ws, seed, seed + wl.D, has_row0, cscale, mb, cb, nullptr)) return rc;
+  if (int rc = stage_c(s, ctx, flags, ll, a, wl, ws, seed, seed + wl.D, has_row0, cscale, mb, cb, nullptr, true))
+    return rc;
   POF_CK(cudaMemcpyAsync(partials2, ws + wl.o_sums + 8, 2 * sizeof(real), cudaMemcpyDeviceToDevice, s));
   return 0;
 }

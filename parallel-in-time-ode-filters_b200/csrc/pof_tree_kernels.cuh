@@ -147,13 +147,20 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
       const long e = FILT ? 2 * i : 2 * i + 1;  // the child element the combine reads
       if (2 * i + 1 < A.sz[lev - 1] && lev - 1 >= A.up_lo && lev - 1 <= A.up_hi) dep1 = A.flag_up + A.off[lev - 1] + e;
     } else if (live && kind == FlowArgs::KS) {
-      // step lev: node j = i + 2^(lev-1); (window ending at i, as final as it is after step lev-1) (+) (own window)
-      const int la = min(lev - 1, ks_nbits(i));
-      dep0 = ks_flag(A, la, i);
-      dep1 = ks_flag(A, lev - 1, i + (1L << (lev - 1)));
+      // step lev, in scan order r (filter: r = node, prefix scan; smoother: r counts from the LAST node, suffix scan):
+      // node r = i + 2^(lev-1) combines the window ending at r' = i (as final as it is after step lev-1) with its own
+      const long nb1 = A.ks_n - 1;
+      const long ra = i, rj = i + (1L << (lev - 1));
+      dep0 = ks_flag(A, min(lev - 1, ks_nbits(ra)), FILT ? ra : nb1 - ra);
+      dep1 = ks_flag(A, lev - 1, FILT ? rj : nb1 - rj);
     } else if (live && kind == FlowArgs::KS_APPLY) {
-      dep0 = A.flag_dn + A.off[A.nlev - 1];
-      if (i >= 1) dep1 = ks_flag(A, ks_nbits(i - 1), i - 1);
+      if constexpr (FILT) {
+        dep0 = A.flag_dn + A.off[A.nlev - 1];
+        if (i >= 1) dep1 = ks_flag(A, ks_nbits(i - 1), i - 1);
+      } else {
+        const long r = A.ks_n - 1 - i;  // node i needs the inclusive suffix of node i + 1 (scan position r - 1)
+        if (r >= 1) dep0 = ks_flag(A, ks_nbits(r - 1), i + 1);
+      }
     }
     while (true) {
       const bool ok = (!dep0 || ld_acquire(dep0) != 0u) && (!dep1 || ld_acquire(dep1) != 0u);
@@ -187,22 +194,36 @@ __global__ void __launch_bounds__(WARPS * 32) k_tree_flow(const FlowArgs A) {
         }
         rel0 = A.flag_up + A.off[lev] + i;
       } else if (kind == FlowArgs::KS) {
-        const long j = i + (1L << (lev - 1));
+        const long nb1 = A.ks_n - 1;
+        const long ra = i, rj = i + (1L << (lev - 1));
+        const long ja = FILT ? ra : nb1 - ra, j = FILT ? rj : nb1 - rj;
         form = 1;
-        in1 = ks_elem<EL>(A, min(lev - 1, ks_nbits(i)), i);
+        in1 = ks_elem<EL>(A, min(lev - 1, ks_nbits(ra)), ja);  // filter: the EARLIER window; smoother: the LATER one
         in2 = ks_elem<EL>(A, lev - 1, j);
         outp = ks_elem<EL>(A, lev, j);
         rel0 = A.flag_ks + (long)(lev - 1) * A.ks_n + j;
       } else if (kind == FlowArgs::KS_APPLY) {
-        const real* root = A.st + A.off[A.nlev - 1] * ST;
-        real* out = A.st + (A.off[A.ks_base] + i) * ST;
-        if (i == 0) {
-          if (out != root) cp_src = root, cp_dst = out, cp_n = ST;
+        if constexpr (FILT) {
+          const real* root = A.st + A.off[A.nlev - 1] * ST;
+          real* out = A.st + (A.off[A.ks_base] + i) * ST;
+          if (i == 0) {
+            if (out != root) cp_src = root, cp_dst = out, cp_n = ST;
+          } else {
+            form = 2;
+            in1 = root;
+            in2 = ks_elem<EL>(A, ks_nbits(i - 1), i - 1);
+            outp = out;
+          }
         } else {
-          form = 2;
-          in1 = root;
-          in2 = ks_elem<EL>(A, ks_nbits(i - 1), i - 1);
-          outp = out;
+          // element-form suffix scan: a node's "everything later" aggregate is the inclusive suffix of the next node
+          // (the identity element g = 0, E = I, D = 0 behind the last one)
+          const long r = A.ks_n - 1 - i;
+          real* out = A.sx + (A.off[A.ks_base] + i) * SE;
+          if (r == 0) {
+            for (int j = cx.r; j < SE; j += G) out[j] = (j >= D && j < D + D * D && (j - D) / D == (j - D) % D) ? 1.0 : 0.0;
+          } else {
+            cp_src = ks_elem<EL>(A, ks_nbits(r - 1), i + 1), cp_dst = out, cp_n = SE;
+          }
         }
         rel0 = A.flag_dn + A.off[A.ks_base] + i;
       } else if (kind == FlowArgs::ROOT) {
