@@ -660,3 +660,38 @@ def qpm_ieks_iterator(setup, init_traj: MVNSqrt, reg_start=1e20, reg_final=1e-20
                 tau = min(tau_final, 1e-5)
         if np.isnan(nll) or np.isnan(obj):
             break
+
+
+# --------------------------------------------------------------------------------------
+# Levenberg-Marquardt-style iteration  (pof/iterators.py:109-133, pof/observations.py:65-83; upstream: uncalled, WIP)
+# --------------------------------------------------------------------------------------
+def stack_regularized(dom: AffineModel, means, reg):
+    """observations.py:65-83 `linearize_regularized`, batched: [EK1 ; x ~ N(m, I / reg)], offsets `[f(m), -m]` as upstream
+    (f(m) = b + H m for the EK1 model: b = f(m) - H m)."""
+    n, d, D = dom.H.shape
+    res = dom.b + np.einsum("nij,nj->ni", dom.H, means)
+    eye = np.broadcast_to(np.eye(D), (n, D, D))
+    cholR = np.zeros((n, d + D, d + D))
+    cholR[:, d:, d:] = eye / np.sqrt(reg)
+    return AffineModel(np.concatenate([dom.H, eye], axis=1), np.concatenate([res, -means], axis=1), cholR)
+
+
+def lm_ieks_iterator(setup, init_traj: MVNSqrt, reg=1.0, scan=associative_scan):
+    """iterators.py:109-133: yields (states, nll, obj, reg); `reg` stays constant (the accept / reject step is commented
+    out upstream); stops when nll and obj are both isclose (rtol 1e-5, atol 1e-8) to the previous iterate's, or on NaN."""
+    x0, dtm = setup["x0"], setup["dtm"]
+
+    def one(states):
+        means = states.mean[1:]
+        out, nll, obj, _, _ = linear_filtsmooth(x0, dtm, stack_regularized(linearize_at(setup, means), means, reg),
+                                                scan=scan)
+        return out, nll, obj
+
+    out, nll, obj = one(init_traj)
+    yield out, nll, obj, reg
+    while True:
+        nll_old, obj_old = nll, obj
+        out, nll, obj = one(out)
+        yield out, nll, obj, reg
+        if (np.isclose(nll_old, nll) and np.isclose(obj_old, obj)) or np.isnan(nll) or np.isnan(obj):
+            break

@@ -6,9 +6,10 @@ method: the ODE residual is observed with noise R = (reg / n) I that is driven g
 for problems on which the plain Gauss-Newton iteration diverges.  The noisy passes (cholR != 0) run on the
 large-state CUDA kernels (`pof_linear_filtsmooth_general_f64`); nothing is computed on the host.
 
-Not provided: `lm_ieks_iterator` needs observations of dimension d + D (reference observations.py:66-83,
-`linearize_regularized`), which the kernels -- whose observation dimension is the ODE dimension d -- do not take;
-`linearize_regularized` itself is available in pof.observations and `lm_ieks_iterator` raises NotImplementedError.
+`lm_ieks_iterator` (upstream: uncalled, work in progress) stacks the EK1 model with a pseudo-observation of the whole
+state (reference observations.py:65-83): observation dimension d + D, which the kernels -- whose observation dimension
+is the ODE dimension d -- do not take.  Its passes run through torch's batched library calls on the device
+(`pof.parallel_filtsmooth.library_pass`): functional, not a performance path.
 """
 import torch
 
@@ -16,6 +17,7 @@ from . import convergence_criteria
 from .convenience import get_initial_trajectory, set_up_solver
 from .observations import AffineModel
 from .parallel_filtsmooth import linear_filtsmooth
+from .parallel_filtsmooth.library_pass import linear_filtsmooth_library
 from .step import ieks_step, linearize_at_previous_states
 
 
@@ -79,12 +81,41 @@ def _qpm_ieks_iterator(dtm, om, x0, init_traj, reg_start=1e20, reg_final=1e-20, 
             break
 
 
+def stack_regularized(dom, means, reg):
+    """Batched `linearize_regularized` (reference observations.py:65-83) from the EK1 model `dom` linearised at `means`
+    (n, D): the ODE observation stacked with the pseudo-observation x ~ N(m, I / reg); observation dimension d + D.
+    Kept with the reference's (work-in-progress) offsets `full_b = [f(m), -m]` -- NOT the EK1 offset f(m) - H m."""
+    H, b = dom.H, dom.b
+    n, d, D = H.shape
+    res = b + torch.einsum("nij,nj->ni", H, means)  # EK1: b = f(m) - H m
+    eye = torch.eye(D, dtype=H.dtype, device=H.device).expand(n, D, D)
+    cholR = torch.zeros((n, d + D, d + D), dtype=H.dtype, device=H.device)
+    cholR[:, d:, d:] = eye / reg ** 0.5
+    return AffineModel(torch.cat([H, eye], dim=1), torch.cat([res, -means], dim=1), cholR)
+
+
 def lm_ieks_iterator(dtm, om, x0, init_traj, reg=1e0, nu=10.0):
-    """reference iterators.py:115-138 (Levenberg-Marquardt: observations of dimension d + D)"""
-    raise NotImplementedError(
-        "lm_ieks_iterator: the regularised observation model has dimension d + D (pof.observations."
-        "linearize_regularized); the CUDA kernels take observations of the ODE dimension d only -- use "
-        "qpm_ieks_iterator for a regularised iteration")
+    """reference iterators.py:109-133 (Levenberg-Marquardt-style regularisation; upstream the accept / reject step that
+    would use `nu` is commented out, so `reg` stays constant).  Yields (states, nll, obj, reg); stops when nll AND obj
+    are `isclose` (rtol 1e-5, atol 1e-8) to the previous iterate's, or on NaN.  Every trajectory is linearised at its
+    states 1..n (the upstream first call vmaps over all of `init_traj`, which only fits a trajectory of n states)."""
+
+    def one(states):
+        means = states.mean[1:]
+        dom = stack_regularized(linearize_at_previous_states(om, states), means, reg)
+        out, nll, obj, _ = linear_filtsmooth_library(x0, dtm, dom)
+        return out, nll, obj
+
+    isclose = lambda a, b: bool(torch.isclose(torch.as_tensor(a), torch.as_tensor(b), rtol=1e-5, atol=1e-8))
+    out, nll, obj = one(init_traj)
+    yield out, nll, obj, reg
+    while True:
+        nll_old, obj_old = nll, obj
+        out, nll, obj = one(out)
+        yield out, nll, obj, reg
+        if (isclose(nll_old, nll) and isclose(obj_old, obj)) or bool(torch.isnan(torch.as_tensor(nll))) or bool(
+                torch.isnan(torch.as_tensor(obj))):
+            break
 
 
 def admm_ieks_iterator(*, f, y0, ts, order, init="prior"):

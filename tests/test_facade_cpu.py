@@ -115,9 +115,7 @@ def test_iterator_and_batch_modules_import(native_lib):
     import pof.iterators
 
     assert callable(pof.iterators.ieks_iterator) and callable(pof.iterators.qpm_ieks_iterator)
-    assert callable(pof.batch.solve_batch)
-    with pytest.raises(NotImplementedError):
-        pof.iterators.lm_ieks_iterator(None, None, None, None)
+    assert callable(pof.batch.solve_batch) and callable(pof.iterators.lm_ieks_iterator)
 
 
 def test_oracle_qpm_reaches_the_plain_ieks_solution():
