@@ -11,9 +11,14 @@
 
 using namespace pof;
 
+// ks_max > 0: the HYBRID tree schedule of the CUDA library (pof_api.cu: flow_hybrid_up / flow_hybrid_down /
+// flow_hybrid_suffix, pof_tree_kernels.cuh: KS / KS_APPLY items) -- up-sweep to the first level with <= ks_max nodes,
+// Kogge-Stone scan over its nodes (a node's window is final after step nbits(r) of its scan position r and is never
+// copied), states / "later" aggregates of that level, down-sweep from there; executed sequentially in item order.
+static int hs_nbits(long j) { int b = 0; while (j) { ++b; j >>= 1; } return b; }
 template <int d, int q>
 static int run(long N, long L, const double* qL, const double* x0, const double* H, const double* c, double* means,
-               double* chols, double* fmeans, double* fchols, int calibrate, double* scalars) {
+               double* chols, double* fmeans, double* fchols, int calibrate, double* scalars, long ks_max = 0) {
   using CK = Chunk<d, q>;
   constexpr int D = CK::D;
   const long n = N - 1;
@@ -27,17 +32,44 @@ static int run(long N, long L, const double* qL, const double* x0, const double*
   Warp w;
   // phase 1
   for (long ch = 0; ch < CS; ++ch) CK::fold(ch * L, std::min((ch + 1) * L, n), H, c, qL, &fagg[ch * FE]);
+  // base level of the Kogge-Stone stage (hybrid schedule), as WsLayout::build in pof_api.cu
+  int B = 0;
+  long nB = 0;
+  int K = 0;
+  if (ks_max > 0) {
+    while (B < tl.nlev - 1 && tl.sz[B] > ks_max) ++B;
+    nB = tl.sz[B];
+    while ((1L << K) < nB) ++K;
+    if (tl.nlev - 1 - B < 2) K = 0;
+  }
+  const int up_top = K > 0 ? B : tl.nlev - 1;
   // up-sweep
-  for (int l = 0; l + 1 < tl.nlev; ++l)
+  for (int l = 0; l + 1 <= up_top; ++l)
     for (long i = 0; i < tl.sz[l + 1]; ++i) {
       double* par = &fagg[(tl.off[l + 1] + i) * FE];
       const double* lc = &fagg[(tl.off[l] + 2 * i) * FE];
       if (2 * i + 1 < tl.sz[l]) filter_combine(w, D, lc, lc + FE, par, smem.data(), false);
       else std::memcpy(par, lc, FE * sizeof(double));
     }
+  int down_from = tl.nlev - 1;
+  if (K > 0) {
+    // Kogge-Stone PREFIX scan over the nodes of level B, then incoming states of that level from x0
+    std::vector<double> ks((size_t)K * nB * FE);
+    auto elem = [&](int l, long j) { return l == 0 ? &fagg[(tl.off[B] + j) * FE] : &ks[((size_t)(l - 1) * nB + j) * FE]; };
+    for (int st = 1; st <= K; ++st)
+      for (long i = 0; i + (1L << (st - 1)) < nB; ++i) {
+        const long j = i + (1L << (st - 1));
+        filter_combine(w, D, elem(std::min(st - 1, hs_nbits(i)), i), elem(st - 1, j), elem(st, j), smem.data(), false);
+      }
+    std::memcpy(&fin[tl.off[B] * ST], x0, ST * sizeof(double));
+    for (long j = 1; j < nB; ++j)
+      filter_combine(w, D, x0, elem(hs_nbits(j - 1), j - 1), &fin[(tl.off[B] + j) * ST], smem.data(), true);
+    down_from = B;
+  } else {
+    std::memcpy(&fin[(tl.off[tl.nlev - 1]) * ST], x0, ST * sizeof(double));
+  }
   // down-sweep (exclusive, state form)
-  std::memcpy(&fin[(tl.off[tl.nlev - 1]) * ST], x0, ST * sizeof(double));
-  for (int l = tl.nlev - 1; l >= 1; --l)
+  for (int l = down_from; l >= 1; --l)
     for (long i = 0; i < tl.sz[l]; ++i) {
       const double* pin = &fin[(tl.off[l] + i) * ST];
       std::memcpy(&fin[(tl.off[l - 1] + 2 * i) * ST], pin, ST * sizeof(double));
@@ -57,25 +89,60 @@ static int run(long N, long L, const double* qL, const double* x0, const double*
   for (long ch = 0; ch < CS; ++ch) { nll += part[ch * 3]; s1 += part[ch * 3 + 1]; s2 += part[ch * 3 + 2]; }
   const double ssq = s1 / n / d, ssqp = s2 / n / d;
   // smoother tree
-  for (int l = 0; l + 1 < tl.nlev; ++l)
+  for (int l = 0; l + 1 <= up_top; ++l)
     for (long i = 0; i < tl.sz[l + 1]; ++i) {
       double* par = &sagg[(tl.off[l + 1] + i) * SE];
       const double* lc = &sagg[(tl.off[l] + 2 * i) * SE];
       if (2 * i + 1 < tl.sz[l]) smooth_combine(w, D, lc + SE, lc, par, smem.data(), false);
       else std::memcpy(par, lc, SE * sizeof(double));
     }
-  std::memcpy(&sin_[(tl.off[tl.nlev - 1]) * ST], &send[(CS - 1) * ST], ST * sizeof(double));
-  for (int l = tl.nlev - 1; l >= 1; --l)
-    for (long i = 0; i < tl.sz[l]; ++i) {
-      const double* pin = &sin_[(tl.off[l] + i) * ST];
-      if (2 * i + 1 < tl.sz[l - 1]) {
-        std::memcpy(&sin_[(tl.off[l - 1] + 2 * i + 1) * ST], pin, ST * sizeof(double));
-        smooth_combine(w, D, pin, &sagg[(tl.off[l - 1] + 2 * i + 1) * SE], &sin_[(tl.off[l - 1] + 2 * i) * ST],
-                       smem.data(), true);
+  if (K > 0) {
+    // element-form SUFFIX scan: Kogge-Stone over level B in scan order r = nB-1-node, "everything later" aggregates,
+    // element-form down-sweep, then one state-form combine per chunk with the terminal state
+    std::vector<double> ks((size_t)K * nB * SE), sx((size_t)tl.total * SE);
+    auto elem = [&](int l, long j) { return l == 0 ? &sagg[(tl.off[B] + j) * SE] : &ks[((size_t)(l - 1) * nB + j) * SE]; };
+    for (int st = 1; st <= K; ++st)
+      for (long i = 0; i + (1L << (st - 1)) < nB; ++i) {
+        const long ja = nB - 1 - i, j = nB - 1 - (i + (1L << (st - 1)));
+        smooth_combine(w, D, elem(std::min(st - 1, hs_nbits(i)), ja), elem(st - 1, j), elem(st, j), smem.data(), false);
+      }
+    for (long i = 0; i < nB; ++i) {
+      double* out = &sx[(tl.off[B] + i) * SE];
+      const long r = nB - 1 - i;
+      if (r == 0) {
+        std::fill(out, out + SE, 0.0);
+        for (int k = 0; k < D; ++k) out[D + k * D + k] = 1.0;  // identity element: g = 0, E = I, D = 0
       } else {
-        std::memcpy(&sin_[(tl.off[l - 1] + 2 * i) * ST], pin, ST * sizeof(double));
+        std::memcpy(out, elem(hs_nbits(r - 1), i + 1), SE * sizeof(double));
       }
     }
+    for (int l = B; l >= 1; --l)
+      for (long i = 0; i < tl.sz[l]; ++i) {
+        const double* px = &sx[(tl.off[l] + i) * SE];
+        if (2 * i + 1 < tl.sz[l - 1]) {
+          std::memcpy(&sx[(tl.off[l - 1] + 2 * i + 1) * SE], px, SE * sizeof(double));
+          smooth_combine(w, D, px, &sagg[(tl.off[l - 1] + 2 * i + 1) * SE], &sx[(tl.off[l - 1] + 2 * i) * SE],
+                         smem.data(), false);
+        } else {
+          std::memcpy(&sx[(tl.off[l - 1] + 2 * i) * SE], px, SE * sizeof(double));
+        }
+      }
+    for (long ch = 0; ch < CS; ++ch)
+      smooth_combine(w, D, &send[(CS - 1) * ST], &sx[ch * SE], &sin_[ch * ST], smem.data(), true);
+  } else {
+    std::memcpy(&sin_[(tl.off[tl.nlev - 1]) * ST], &send[(CS - 1) * ST], ST * sizeof(double));
+    for (int l = tl.nlev - 1; l >= 1; --l)
+      for (long i = 0; i < tl.sz[l]; ++i) {
+        const double* pin = &sin_[(tl.off[l] + i) * ST];
+        if (2 * i + 1 < tl.sz[l - 1]) {
+          std::memcpy(&sin_[(tl.off[l - 1] + 2 * i + 1) * ST], pin, ST * sizeof(double));
+          smooth_combine(w, D, pin, &sagg[(tl.off[l - 1] + 2 * i + 1) * SE], &sin_[(tl.off[l - 1] + 2 * i) * ST],
+                         smem.data(), true);
+        } else {
+          std::memcpy(&sin_[(tl.off[l - 1] + 2 * i) * ST], pin, ST * sizeof(double));
+        }
+      }
+  }
   const double cscale = calibrate ? sqrt(ssq) : 1.0;
   for (long ch = 0; ch < CS; ++ch)
     CK::smooth(ch * L, std::min((ch + 1) * L, n), ch == CS - 1, true, qL, &sin_[ch * ST], kern.data(), CS, ch, cscale,
@@ -271,6 +338,17 @@ int hs_linear_filtsmooth(int d, int q, long N, long L, const double* qL, const d
                          int calibrate, double* scalars) {
 #define CASE(dd, qq) \
   if (d == dd && q == qq) return run<dd, qq>(N, L, qL, x0, H, c, means, chols, fmeans, fchols, calibrate, scalars);
+  CASE(1, 1) CASE(1, 2) CASE(1, 3) CASE(1, 4) CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(3, 3) CASE(4, 2) CASE(4, 3)
+#undef CASE
+  return -1;
+}
+// the same pass with the hybrid tree schedule (ks_max = WsLayout::KS_MAX in the library: 384)
+int hs_linear_filtsmooth_hybrid(int d, int q, long N, long L, long ks_max, const double* qL, const double* x0,
+                                const double* H, const double* c, double* means, double* chols, double* fmeans,
+                                double* fchols, int calibrate, double* scalars) {
+#define CASE(dd, qq)          \
+  if (d == dd && q == qq)     \
+    return run<dd, qq>(N, L, qL, x0, H, c, means, chols, fmeans, fchols, calibrate, scalars, ks_max);
   CASE(1, 1) CASE(1, 2) CASE(1, 3) CASE(1, 4) CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(3, 3) CASE(4, 2) CASE(4, 3)
 #undef CASE
   return -1;

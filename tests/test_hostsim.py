@@ -82,3 +82,44 @@ def test_warp_combine_matches_oracle_operator(lib):
         np.testing.assert_allclose(out[2 * DD + D:2 * DD + 2 * D], ref[3][0], atol=1e-10 * np.abs(ref[3]).max())
         np.testing.assert_allclose(_cov(out[2 * DD + 2 * D:].reshape(D, D)), _cov(ref[4][0]),
                                    atol=1e-10 * np.abs(_cov(ref[4])).max())
+
+
+@pytest.mark.parametrize("name,kw,N,q,L,ks_max", [
+    ("fitzhughnagumo", {}, 100, 3, 4, 4), ("fitzhughnagumo", {}, 100, 3, 4, 8), ("fitzhughnagumo", {}, 100, 3, 7, 2),
+    ("fitzhughnagumo", {}, 1024, 3, 16, 8), ("fitzhughnagumo", {}, 1024, 3, 4, 384), ("fitzhughnagumo", {}, 777, 3, 3, 5),
+    ("logistic", {}, 64, 3, 2, 3), ("rigid_body", {}, 256, 3, 4, 6), ("lotkavolterra", {}, 300, 2, 5, 7),
+])
+def test_hybrid_tree_schedule_matches_oracle(lib, name, kw, N, q, L, ks_max):
+    """The library's HYBRID tree schedule (up-sweep to the first narrow level, Kogge-Stone prefix scan over its nodes for
+    the filter, the mirrored suffix scan in element form for the smoother, down-sweeps from that level) restated on the
+    host with the device combines: same results as the reference's scans, for base levels of every shape (odd node
+    counts, non-powers of two, the library's own KS_MAX = 384)."""
+    ivp = getattr(ivps, name)(**kw)
+    ts = np.linspace(ivp.t0, ivp.tmax, N)
+    setup = O.set_up_solver(ivp, ts, q)
+    st = O.get_initial_trajectory(setup)
+    dom = O.linearize_at(setup, st.mean[1:])
+    d = setup["d"]
+    D = d * (q + 1)
+    qL = np.ascontiguousarray(O.preconditioned_discretize_1d(q)[1])
+    x0 = np.concatenate([setup["x0"].mean, setup["x0"].chol.ravel()])
+    H, c = np.ascontiguousarray(dom.H), np.ascontiguousarray(dom.b)
+    res = {}
+    for tag, km in (("hybrid", ks_max), ("plain", 0)):
+        means, chols = st.mean.copy(), np.zeros((N, D, D))
+        fm, fc, sc = np.zeros((N, D)), np.zeros((N, D, D)), np.zeros(8)
+        rc = lib.hs_linear_filtsmooth_hybrid(d, q, ctypes.c_long(N), ctypes.c_long(L), ctypes.c_long(km), _p(qL),
+                                             _p(x0), _p(H), _p(c), _p(means), _p(chols), _p(fm), _p(fc), 0, _p(sc))
+        assert rc == 0
+        res[tag] = (means, chols, fm, fc, sc)
+    means, chols, fm, fc, sc = res["hybrid"]
+    filt, nll, _, ssq, ssqp = O.linear_noiseless_filtering(setup["x0"], setup["dtm"], dom)
+    out, obj = O.smoothing(setup["dtm"], filt)
+    assert np.abs(fm - filt.mean).max() <= 1e-9 * np.abs(filt.mean).max()
+    assert np.abs(_cov(fc) - _cov(filt.chol)).max() <= 1e-10 * np.abs(_cov(filt.chol)).max()
+    assert np.abs(means - out.mean).max() <= 1e-9 * np.abs(out.mean).max()
+    assert np.abs(_cov(chols) - _cov(out.chol)).max() <= 1e-10 * np.abs(_cov(out.chol)).max()
+    assert abs(sc[0] - nll) <= 1e-9 * abs(nll) and abs(sc[1] - obj) <= 1e-9 * abs(obj)
+    assert abs(sc[3] - ssqp) <= 1e-9 * ssqp
+    # and the two schedules agree with each other far below the gates (same leaves, different association order)
+    assert np.abs(means - res["plain"][0]).max() <= 1e-10 * np.abs(out.mean).max()
