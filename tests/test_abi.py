@@ -63,3 +63,32 @@ def test_no_cpu_fallback(monkeypatch):
 
     with pytest.raises(nat.NativeError):
         nat.require_cuda(torch.zeros(3, dtype=torch.float64))
+
+
+def test_header_is_plain_c_and_links(native_lib, tmp_path):
+    """The boundary is a C ABI: include/pof_b200.h compiles as ISO C99 (no C++ or torch types in any signature) and a
+    plain C program links against libpof_b200.so and calls its host-only queries."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "pof_b200.h"\n'
+        "int main(void) {\n"
+        "  pof_ctx_t* ctx = 0; pof_loop_t* loop = 0; pof_p2p_t* p2p = 0;\n"
+        "  size_t b = pof_workspace_bytes(1 << 20, 2, 3, 111);\n"
+        "  size_t b32 = pof_workspace_bytes_f32(1 << 20, 2, 3, 111);\n"
+        "  long long launches = (long long)pof_launches_per_pass(1 << 20, 2, 3, 111, 0u);\n"
+        "  (void)ctx; (void)loop; (void)p2p;\n"
+        '  printf("%d %d %lld %d\\n", pof_supported(2, 3), b > b32 && b32 > 0, launches, (int)POF_F_TREE_UPDOWN);\n'
+        "  return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(native_lib.LIB_PATH)
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                    "-L", libdir, "-lpof_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["1", "1", "9", "16"]
