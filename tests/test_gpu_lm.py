@@ -1,16 +1,13 @@
 """`pof.iterators.lm_ieks_iterator` on the GPU against its oracle restatement, iterate by iterate.
 
 The passes of this iterator (observation dimension d + D) run through torch's batched library calls
-(`pof.parallel_filtsmooth.library_pass`), which are checked against the oracle on CPU tensors in
-tests/test_library_pass.py.  This file was written after the round's GPU budget was spent: its first run on hardware
-is the driver's, hence the non-strict xfail marker (a pass shows up as XPASS, a failure does not stop the suite)."""
+(`pof.parallel_filtsmooth.library_pass`, also checked against the oracle on CPU tensors in tests/test_library_pass.py);
+the linearisation is the fused CUDA kernel."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of this path happens after the round's GPU "
-                                                     "budget; validated on CPU tensors in test_library_pass.py")]
+pytestmark = pytest.mark.gpu
 
 from oracle import ivps as oivps  # noqa: E402
 from oracle import pof_oracle as O  # noqa: E402
