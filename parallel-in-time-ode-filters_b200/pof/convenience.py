@@ -9,6 +9,26 @@ from .transitions import (IWP, TransitionModel, discretize_transitions, nordsiec
 from .utils import MVNSqrt
 
 
+def linearize_observation_model(observation_model, trajectory):
+    """reference convenience.py:9-10: the EK1 linearisation (observations.py:35-40) at EVERY state of `trajectory`
+    (MVNSqrt with means (n, D)) -> AffineModel(H (n,d,D), b (n,d), cholR (n,d,d) = 0).  Models made by `set_up_solver`
+    for a built-in `pof.ivp` problem use the fused CUDA kernel, any other callable torch autodiff on the means' device."""
+    from .observations import AffineModel
+    from .step import linearize_at_previous_states
+
+    means = trajectory.mean
+    if getattr(observation_model.f, "_pof_lin", None) is not None:
+        # `linearize_at_previous_states` linearises at rows 1..n of a trajectory: put a dummy row in front
+        padded = MVNSqrt(torch.cat([means[:1], means]), None)
+        return linearize_at_previous_states(observation_model, padded)
+    f = observation_model.f
+    H = torch.func.vmap(torch.func.jacfwd(f))(means)
+    res = torch.func.vmap(f)(means)
+    b = res - torch.einsum("nij,nj->ni", H, means)
+    n, d = b.shape
+    return AffineModel(H, b, torch.zeros((n, d, d), dtype=means.dtype, device=means.device))
+
+
 def _device():
     if not torch.cuda.is_available():
         raise RuntimeError("pof_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")

@@ -93,3 +93,33 @@ def coarse_ekf_init(*, f, y0, order, ts, N=10):
     idxs = np.clip(np.floor(ts / coarse_dt).astype(np.int64), 0, N - 1)
     idx_t = torch.from_numpy(idxs).to(out.mean.device)
     return MVNSqrt(out.mean.index_select(0, idx_t), out.chol.index_select(0, idx_t))
+
+
+def _prior_init(*, x0, dtm):
+    """reference initialization.py:75-80: every row k >= 1 is x0 pushed through transition k ALONE (not the product of
+    the transitions up to k): mean F_k m0, factor tria([F_k L0 | QL_k]); row 0 is x0.  dtm: (n,D,D) models."""
+    from .utils import MVNSqrt, tria
+
+    F, QL = dtm.F, dtm.QL
+    if F.dim() != 3:
+        raise ValueError("_prior_init needs per-step transition models (n,D,D), e.g. from discretize_transitions")
+    n = F.shape[0]
+    means = torch.einsum("nij,j->ni", F, x0.mean)
+    chols = tria(torch.cat([F @ x0.chol.unsqueeze(0).expand(n, *x0.chol.shape), QL], dim=-1))
+    return MVNSqrt(torch.cat([x0.mean[None], means]), torch.cat([x0.chol[None], chols]))
+
+
+def updated_prior_init(*, x0, dtm, om):
+    """reference initialization.py:92-100: the prior trajectory with every state updated on its own linearised
+    (noiseless) observation"""
+    from .observations import linearize
+    from .sequential_filtsmooth.loops import _sqrt_update
+    from .utils import MVNSqrt
+
+    states = _prior_init(x0=x0, dtm=dtm)
+    out = []
+    for k in range(states.mean.shape[0]):
+        x = MVNSqrt(states.mean[k], states.chol[k])
+        H, b, cholR = linearize(om, x)
+        out.append(_sqrt_update(H, cholR, b, x)[0])
+    return MVNSqrt(torch.stack([o.mean for o in out]), torch.stack([o.chol for o in out]))

@@ -221,10 +221,38 @@ class GraphedCall:
         return self.out
 
 
+def _outside_the_kernels(dom: AffineModel):
+    """True for model shapes the CUDA kernels do not take: observation dimension != ODE dimension d with D = d (q+1),
+    or q = 0 (e.g. the 1-dimensional Wiener process of the reference's tests/test_filtsmooth.py).  Those run through
+    torch's batched library calls on the tensors' device (`library_pass`), announced by a warning -- never silently."""
+    _, dy, D = dom.H.shape
+    out = D % dy != 0 or D // dy < 2
+    if out:
+        import warnings
+
+        warnings.warn(f"pof: observation dimension {dy} with state dimension {D} is outside the CUDA kernels "
+                      "(they need D = d (q+1), q >= 1): this pass runs through torch library calls", stacklevel=3)
+    return out
+
+
+def smoothing(transition_models, filtered_states):
+    """reference parallel_filtsmooth/smoother.py:8-22 as a stand-alone call: RTS smoothing of GIVEN filtered states by
+    the associative suffix scan -> (MVNSqrt smoothed, obj).  The kernels of this package never materialise this seam
+    (the filter scan hands its backward kernels straight to the smoother inside `linear_filtsmooth`), so the
+    stand-alone form runs through torch's batched library calls on the states' device (`library_pass`)."""
+    from .library_pass import smoothing_library
+
+    return smoothing_library(transition_models, filtered_states)
+
+
 def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=None, info=None):
     """reference parallel_filtsmooth/__init__.py:5-10 -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq).
     `info` (optional dict) receives the pass's full scalar vector (`info["scalars"]`, indices `_native.S_*`, e.g. the
     QR-sign-invariant sigma^2 `S_SSQ_PROPER` that the reference does not return)."""
+    if _outside_the_kernels(linear_observations):
+        from .library_pass import linear_filtsmooth_library
+
+        return linear_filtsmooth_library(x0, linear_transitions, linear_observations)
     n, d, q, D, qL, dense = _model_dims(linear_transitions, linear_observations)
     dev = linear_observations.H.device
     means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)
@@ -239,6 +267,10 @@ def linear_filtsmooth(x0, linear_transitions, linear_observations, *, chunk_len=
 def linear_noiseless_filtering(x0, transition_models, observation_models, *, chunk_len=None):
     """reference parallel_filtsmooth/filter.py:18-47 -> (filtered MVNSqrt, nll, obj, ssq).
     The filtered chols are square-root factors (chol @ chol.T is the covariance) but not triangular."""
+    if _outside_the_kernels(observation_models):
+        from .library_pass import linear_noiseless_filtering_library
+
+        return linear_noiseless_filtering_library(x0, transition_models, observation_models)
     n, d, q, D, qL, dense = _model_dims(transition_models, observation_models)
     dev = observation_models.H.device
     means = torch.zeros((n + 1, D), dtype=torch.float64, device=dev)

@@ -112,16 +112,18 @@ def _smooth_op(e1, e2):
     return _mv(E2, g1) + g2, E2 @ E1, _tria(torch.cat([E2 @ D1, D2], dim=-1))
 
 
-def linear_filtsmooth_library(x0: MVNSqrt, dtm, dom):
-    """`linear_filtsmooth(x0, dtm, dom)` (parallel_filtsmooth/__init__.py:5-10) for any observation dimension:
-    -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq), uncalibrated, like the reference."""
+def _rep(M, n):
+    return M if M.dim() == 3 else M.unsqueeze(0).expand(n, *M.shape)
+
+
+def linear_noiseless_filtering_library(x0: MVNSqrt, dtm, dom):
+    """`linear_noiseless_filtering(x0, dtm, dom)` (filter.py:18-47) for any state / observation dimension
+    -> (filtered MVNSqrt (N,D), (N,D,D), nll, obj, ssq)"""
     H, c, cholR = dom.H, dom.b, dom.cholR
     n, ny, nx = H.shape
-    rep = lambda M: M if M.dim() == 3 else M.unsqueeze(0).expand(n, nx, nx)
-    F, QL = rep(dtm.F), rep(dtm.QL)
+    F, QL = _rep(dtm.F, n), _rep(dtm.QL, n)
     if cholR is None:
         cholR = torch.zeros((n, ny, ny), dtype=H.dtype, device=H.device)
-    # ---- filter (filter.py:18-47)
     _, fm, fL, _, _ = _scan(_filter_op, _filter_elements(F, QL, H, c, cholR, x0.mean, x0.chol))
     fm = torch.cat([x0.mean[None], fm])
     fL = torch.cat([x0.chol[None], fL])
@@ -135,18 +137,34 @@ def linear_filtsmooth_library(x0: MVNSqrt, dtm, dom):
     y = _solve_lower(oL, om)
     logdet = torch.diagonal(oL, dim1=-2, dim2=-1).abs().log().sum(-1)
     nll = (0.5 * (y * y).sum(-1) + logdet + ny * math.log(2 * math.pi) / 2.0).sum()
-    # ---- smoother (smoother.py:8-50): elements from the joint triangularisation, suffix scan
-    zeros = torch.zeros((n, nx, nx), dtype=H.dtype, device=H.device)
+    # the filter's objective with the reference's swapped arguments (filter.py:43-45, utils.py:97-101)
+    wq = _solve_lower(QL, fm[:-1] - _mv(F, fm[1:]))
+    return MVNSqrt(fm, fL), nll, (wq * wq).sum(), ssq
+
+
+def smoothing_library(dtm, filtered: MVNSqrt):
+    """`smoothing(dtm, filtered)` (smoother.py:8-50): elements from the joint triangularisation, suffix scan
+    -> (smoothed MVNSqrt, obj)"""
+    fm, fL = filtered.mean, filtered.chol
+    n, nx = fm.shape[0] - 1, fm.shape[1]
+    F, QL = _rep(dtm.F, n), _rep(dtm.QL, n)
+    zeros = torch.zeros((n, nx, nx), dtype=fm.dtype, device=fm.device)
     Phi = _tria(torch.cat([torch.cat([F @ fL[:-1], QL], dim=-1), torch.cat([fL[:-1], zeros], dim=-1)], dim=-2))
     Phi11, Phi21, Dm = Phi[:, :nx, :nx], Phi[:, nx:, :nx], Phi[:, nx:, nx:]
     E = _T(torch.linalg.solve(_T(Phi11), _T(Phi21)))  # smoother.py:48 is a general solve upstream
-    g = fm[:-1] - _mv(E, pm)
+    g = fm[:-1] - _mv(E, _mv(F, fm[:-1]))
     gs = torch.cat([g, fm[-1:]])
     Es = torch.cat([E, torch.zeros_like(fL[-1:])])
     Ds = torch.cat([Dm, fL[-1:]])
     sm, _, sL = _scan(_smooth_op, (gs, Es, Ds), reverse=True)
     # objective with the reference's swapped arguments (smoother.py:20, utils.py:97-101)
-    r = sm[:-1] - _mv(F, sm[1:])
-    wq = _solve_lower(QL, r)
-    obj = (wq * wq).sum()
-    return MVNSqrt(sm, sL), nll, obj, ssq
+    wq = _solve_lower(QL, sm[:-1] - _mv(F, sm[1:]))
+    return MVNSqrt(sm, sL), (wq * wq).sum()
+
+
+def linear_filtsmooth_library(x0: MVNSqrt, dtm, dom):
+    """`linear_filtsmooth(x0, dtm, dom)` (parallel_filtsmooth/__init__.py:5-10) for any observation dimension:
+    -> (MVNSqrt(means (N,D), chols (N,D,D)), nll, obj, ssq), uncalibrated, like the reference."""
+    filtered, nll, _, ssq = linear_noiseless_filtering_library(x0, dtm, dom)
+    out, obj = smoothing_library(dtm, filtered)
+    return out, nll, obj, ssq

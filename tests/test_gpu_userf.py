@@ -88,3 +88,31 @@ def test_solve_batch_equals_separate_solves(native_lib):
         ref, rinfo = solve(f=p["f"], y0=p["y0"], ts=p["ts"], order=3, init="constant", maxiters=300)
         assert info["iterations"] == rinfo["iterations"]
         assert torch.equal(ys.mean, ref.mean) and torch.equal(ys.chol, ref.chol)
+
+
+def test_reference_benchmark_call_shapes(native_lib):
+    """The calls of the reference's single-step benchmark (experiments/1_single_step_runtime_gpus/collect_data.py:22-42):
+    `linearize_observation_model(om, states[1:])` + `linear_filtsmooth`, and `seq_fs(x0, dtm, om)`, on the CUDA paths."""
+    import pof.ivp
+    from pof.convenience import get_initial_trajectory, linearize_observation_model, set_up_solver
+    from pof.parallel_filtsmooth import linear_filtsmooth
+    from pof.sequential_filtsmooth import filtsmooth as seq_fs
+    from pof.sequential_filtsmooth.eks import eks_filtsmooth
+    from pof.step import linearize_at_previous_states
+    from pof.utils import MVNSqrt
+
+    ivp = pof.ivp.fitzhughnagumo()
+    N = 64
+    setup = set_up_solver(f=ivp.f, y0=ivp.y0, ts=np.linspace(0, 5, N), order=3)
+    x0, dtm, om = setup["x0"], setup["dtm"], setup["om"]
+    states = get_initial_trajectory(setup, method="constant")
+    dom = linearize_observation_model(om, MVNSqrt(states.mean[1:], states.chol[1:]))
+    dom2 = linearize_at_previous_states(om, states)
+    assert dom.H.shape == (N - 1, 2, 8) and torch.equal(dom.H, dom2.H) and torch.equal(dom.b, dom2.b)
+    out, nll, obj, ssq = linear_filtsmooth(x0, dtm, dom)
+    assert out.mean.shape == (N, 8) and bool(torch.isfinite(out.mean).all())
+    s1, ell1, obj1, ssq1 = seq_fs(x0, dtm, om, n=N - 1)
+    s2, ell2, obj2, ssq2 = eks_filtsmooth(setup)
+    assert torch.equal(s1.mean, s2.mean) and (ell1, obj1, ssq1) == (ell2, obj2, ssq2)
+    with pytest.raises(ValueError):
+        seq_fs(x0, dtm, om)  # one (D,D) copy of the model: the number of steps has to be given
