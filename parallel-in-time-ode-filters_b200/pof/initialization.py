@@ -123,3 +123,33 @@ def updated_prior_init(*, x0, dtm, om):
         H, b, cholR = linearize(om, x)
         out.append(_sqrt_update(H, cholR, b, x)[0])
     return MVNSqrt(torch.stack([o.mean for o in out]), torch.stack([o.chol for o in out]))
+
+
+def uncertain_init(f, y0, num_derivatives, var=1.0):
+    """reference initialization.py:25-40: mean [y0, f(y0), 0, ...] per dimension, unit-variance (x var) factors on the
+    derivatives of order >= 2, zero variance on y0 and f(y0)"""
+    from .utils import MVNSqrt
+
+    y0 = _cpu64(y0)
+    d, q = y0.shape[0], num_derivatives
+    dy0 = _cpu64(f(None, y0))
+    m0 = torch.cat([y0[:, None], dy0[:, None], torch.zeros((d, q - 1), dtype=torch.float64)], dim=1).reshape(-1)
+    diag = torch.full((d * (q + 1),), float(var), dtype=torch.float64)
+    for j in range(d):
+        diag[(q + 1) * j] = 0.0
+        diag[(q + 1) * j + 1] = 0.0
+    return MVNSqrt(m0, torch.diag(diag.sqrt()))
+
+
+def classic_to_init(*, ys, order, f=None):
+    """reference initialization.py:58-72: a trajectory of ODE states ys (N, d) -> state trajectory
+    [y, f(y), 0, ...] per dimension with zero covariance factors"""
+    from .utils import MVNSqrt
+
+    ys = _cpu64(ys)
+    N, d = ys.shape
+    dys = torch.stack([_cpu64(f(None, y)) for y in ys]) if f is not None else torch.zeros_like(ys)
+    traj = torch.cat([ys[:, :, None], dys[:, :, None], torch.zeros((N, d, order - 1), dtype=torch.float64)], dim=2)
+    traj = traj.reshape(N, -1)
+    D = traj.shape[1]
+    return MVNSqrt(traj, torch.zeros((N, D, D), dtype=torch.float64))

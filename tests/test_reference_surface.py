@@ -142,3 +142,24 @@ def test_utils_helpers_match_the_oracle(native_lib):
                                O.objective_function_value(mn, m, F, chol), rtol=1e-12)
     z = append_zeros_along_new_axis(T(x), 3)
     assert z.shape == (4, 4) and bool((z[0] == T(x)).all()) and float(z[1:].abs().max()) == 0.0
+
+
+def test_small_initialisers_like_the_reference(native_lib):
+    """reference initialization.py:25-40 (`uncertain_init`), :58-72 (`classic_to_init`), :42-56 (`constant_init`)"""
+    import pof.ivp
+    from pof.initialization import classic_to_init, constant_init, uncertain_init
+
+    ivp = pof.ivp.lotkavolterra()
+    y0 = torch.as_tensor(np.asarray(ivp.y0), dtype=torch.float64)
+    f0 = torch.as_tensor(np.asarray(ivp.f(None, y0)), dtype=torch.float64)
+    x0 = uncertain_init(ivp.f, ivp.y0, 3, var=4.0)
+    assert x0.mean.shape == (8,) and x0.chol.shape == (8, 8)
+    np.testing.assert_allclose(x0.mean.numpy()[[0, 4]], y0.numpy())
+    np.testing.assert_allclose(x0.mean.numpy()[[1, 5]], f0.numpy())
+    np.testing.assert_allclose(np.diag(x0.chol.numpy()), [0, 0, 2, 2, 0, 0, 2, 2])
+    ys = torch.stack([y0, 2 * y0, 3 * y0])
+    tr = classic_to_init(ys=ys, order=2, f=ivp.f)
+    assert tr.mean.shape == (3, 6) and tr.chol.shape == (3, 6, 6) and float(tr.chol.abs().max()) == 0.0
+    np.testing.assert_allclose(tr.mean.numpy()[:, [0, 3]], ys.numpy())
+    c = constant_init(y0=ivp.y0, order=2, ts=np.arange(5), f=ivp.f)
+    np.testing.assert_allclose(c.mean.numpy(), np.repeat(tr.mean.numpy()[:1], 5, axis=0))
