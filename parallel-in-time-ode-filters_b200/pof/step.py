@@ -42,6 +42,12 @@ def linearize_at_previous_states(om, prev_states):
     return AffineModel(H, c, torch.zeros((n, d, d), dtype=torch.float64, device=means.device))
 
 
+def inflate(state):
+    """reference step.py:26-30: add 1e-3 to the diagonal of a covariance factor"""
+    eye = torch.eye(state.chol.shape[0], dtype=state.chol.dtype, device=state.chol.device)
+    return MVNSqrt(state.mean, state.chol + eye * 1e-3)
+
+
 def ieks_step(*, om, dtm, x0, states, calibrate=True, sequential=False):
     """reference step.py:33-45"""
     dom = linearize_at_previous_states(om, states)

@@ -23,6 +23,27 @@ class IWP(NamedTuple):
     num_derivatives: int
 
 
+def hilbert(n):
+    """reference transitions.py:28-29"""
+    return scipy.linalg.hilbert(n)
+
+
+def pascal(n):
+    """reference transitions.py:32-34 (lower-triangular Pascal matrix)"""
+    return scipy.linalg.pascal(n, kind="lower", exact=False)
+
+
+def nordsieck_preconditioner_1d(iwp: IWP, dt):
+    """reference transitions.py:54-61"""
+    sv, svi = nordsieck_scalings(iwp, dt)
+    return np.diag(sv), np.diag(svi)
+
+
+def projection_matrix_1d(iwp: IWP, derivative_to_project_onto):
+    """reference transitions.py:81-82"""
+    return np.eye(1, iwp.num_derivatives + 1, derivative_to_project_onto)
+
+
 def preconditioned_discretize_1d(iwp: IWP):
     """reference transitions.py:37-41"""
     q = iwp.num_derivatives

@@ -148,3 +148,23 @@ def test_oracle_prior_init_is_the_taylor_prediction():
         _, QL = O.preconditioned_discretize(1, q)
         np.testing.assert_allclose(st.chol[k], -P @ QL, rtol=1e-12, atol=1e-300)
     np.testing.assert_allclose(st.mean[0], m0)
+
+
+def test_small_transition_helpers(native_lib):
+    """reference transitions.py:28-34, 54-61, 81-82 and step.py:26-30"""
+    from pof.step import inflate
+    from pof.transitions import (IWP, hilbert, nordsieck_preconditioner, nordsieck_preconditioner_1d, pascal,
+                                 preconditioned_discretize_1d, projection_matrix, projection_matrix_1d)
+    from pof.utils import MVNSqrt
+
+    iwp = IWP(num_derivatives=3, wiener_process_dimension=2)
+    A, L = preconditioned_discretize_1d(iwp)
+    np.testing.assert_allclose(A, np.flip(pascal(4)))
+    np.testing.assert_allclose(L @ L.T, np.flip(hilbert(4)), rtol=1e-12)
+    P1, PI1 = nordsieck_preconditioner_1d(iwp, 0.3)
+    P, PI = nordsieck_preconditioner(iwp, 0.3)
+    np.testing.assert_allclose(np.kron(np.eye(2), P1), P)
+    np.testing.assert_allclose(P1 @ PI1, np.eye(4), rtol=1e-13)
+    np.testing.assert_allclose(np.kron(np.eye(2), projection_matrix_1d(iwp, 1)), projection_matrix(iwp, 1))
+    x = inflate(MVNSqrt(torch.zeros(3, dtype=torch.float64), torch.zeros((3, 3), dtype=torch.float64)))
+    np.testing.assert_allclose(x.chol.numpy(), 1e-3 * np.eye(3))
